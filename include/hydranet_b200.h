@@ -1,0 +1,226 @@
+/* hydranet_b200 -- C ABI of the B200-native HydraNet hot path.
+ *
+ * Boundary: the reference's Python `HydraNet.forward` (model/model.py:159-198)
+ * and the three static decoders (head_seg/segmentation.py:107-125, head_detect/detection.py:232-245
+ * -> head_detect/detection_loss.py:70-108, head_lane/lanedetect.py:103-116 ->
+ * head_lane/lane_codec.py:116-219 + lane_codec_utils.py:487-542) bottom out in the entry points
+ * below.  Plain pointers and sizes only; device pointers are raw CUDA addresses, `stream` is a
+ * cudaStream_t passed as void*.  Every function returns 0 on success or an HN_ERR_* code
+ * (cf. the reference's own int-returning C API, deploy/src/interface/Hydranet.h:83-111);
+ * hn_last_error() returns a thread-local message.  There is no CPU fallback behind any of them.
+ *
+ * Activations are NHWC bf16 "views": a base pointer plus element strides, so padded buffers,
+ * channel slices and strided (stride-2) sub-samplings are all expressed without copies.
+ */
+#ifndef HYDRANET_B200_H
+#define HYDRANET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HN_OK 0
+#define HN_ERR_ARG 1
+#define HN_ERR_CUDA 2
+#define HN_ERR_UNSUPPORTED 3
+
+#define HN_ACT_NONE 0
+#define HN_ACT_RELU 1
+#define HN_ACT_SWISH 2
+#define HN_ACT_ELU 3
+#define HN_ACT_SIGMOID 4
+
+#define HN_HALO_NONE 0
+#define HN_HALO_REFLECT 1   /* nn.ReflectionPad2d(1): head_seg/segmentation.py:40 */
+#define HN_HALO_REPLICATE 2 /* reflect-pad of a nearest-x2 upsample == replicate-pad of its source */
+
+#define HN_EPI_STD 0
+#define HN_EPI_SEGOUT 1 /* sub-pixel seg logits (fp32 NCHW) + fused argmax */
+
+#define HN_MAX_SRC 6
+#define HN_MAX_TAPS 96
+
+/* 4-D NHWC bf16 view; channel stride is 1; strides in elements. */
+typedef struct hn_view {
+    const void* ptr;
+    int32_t N, H, W, C;
+    int64_t stride_n, stride_y, stride_x;
+} hn_view;
+
+/* One K-step (64 input channels) of the implicit GEMM: which source, which spatial shift, which
+ * channel offset.  The packed weight matrix stores its K columns in exactly this order. */
+typedef struct hn_tap {
+    int8_t src, dy, dx, rsv0;
+    int16_t c0, rsv1;
+} hn_tap;
+
+/* Convolution as implicit GEMM on tcgen05 (replaces every nn.Conv2d(+BatchNorm2d)(+activation)
+ * call of model/net/anynet.py:8-76, net/common.py:35-114, net/bifpn.py:57-99,
+ * head_seg/segmentation.py:16-48, head_detect/detection.py:28-83, head_lane/lanedetect.py:45-64).
+ * out[n, y*s+oy, x*s+ox, :cout] = act(sum_taps src[tap.src][n, y+dy, x+dx, c0:c0+64] . W + bias) (+res) */
+typedef struct hn_conv_desc {
+    hn_view src[HN_MAX_SRC];
+    int32_t n_src;
+    const void* weight; /* bf16 [w_rows][num_taps*64], row = output channel */
+    int32_t w_rows;
+    int32_t num_taps;
+    hn_tap taps[HN_MAX_TAPS];
+    int32_t flat;           /* 1: rows = src[0].W consecutive pixels (H=N=1), tile = 128 rows */
+    int32_t tile_h, tile_w; /* spatial tile, tile_h*tile_w == 128 */
+    int32_t n_img, out_h, out_w; /* tile-space extent per image (before out_scale) */
+    int32_t flat_hw;        /* flat: rows per image (for out_stride_n addressing) */
+    int32_t cout, bn, stages;
+    const float* bias; /* fp32 [>= n_tiles*bn] */
+    int32_t act;
+    int32_t epi;
+    void* out;
+    int32_t out_fp32;
+    int64_t out_stride_n, out_stride_y, out_stride_x; /* elements of the output dtype */
+    int32_t out_scale, out_oy, out_ox;
+    int32_t halo;
+    const void* res; /* bf16 residual view of the output pixels (own strides) */
+    int64_t res_stride_n, res_stride_y, res_stride_x;
+    int32_t res_relu;
+    int32_t grouped; /* 1: block-diagonal (grouped) conv: tap channel offset += n-tile origin; needs bn == 64 */
+    void* out2;      /* HN_EPI_SEGOUT: uint8 class map [N][2*out_h][2*out_w] or NULL */
+    int32_t n_cls;   /* HN_EPI_SEGOUT: classes per sub-pixel (columns = 4 parities x 8) */
+} hn_conv_desc;
+
+/* Stem: 3x3 s2 p1 conv 3->32 + folded BN + ReLU, fp32 NCHW in, bf16 NHWC out (anynet.py:8-20). */
+typedef struct hn_stem_desc {
+    const float* x; /* [N][3][H][W] */
+    int32_t N, H, W;
+    const float* w; /* [27][32] fp32, BN folded: index (ci*9+ky*3+kx)*32+co */
+    const float* b; /* [32] */
+    hn_view out;    /* [N][H/2][W/2][32] */
+} hn_stem_desc;
+
+#define HN_IN_SAME 0
+#define HN_IN_UP2 1  /* nearest x2 of a half-resolution view */
+#define HN_IN_POOL 2 /* 3x3 s2 max over a double-resolution view zero-padded right/bottom (common.py:138-151) */
+
+/* BiFPN fusion node front half: weighted sum -> swish -> depthwise 3x3 (zero pad 1)
+ * (net/bifpn.py:170-231 + common.py:91-101).  With n_in==1, w={1}, swish=0 it is the plain
+ * depthwise conv of the detection towers (detection.py:33-37). */
+typedef struct hn_node_desc {
+    int32_t n_in;
+    hn_view in[3];
+    int32_t mode[3];
+    float w[3];
+    int32_t swish;
+    const float* dw; /* fp32 [9][C] */
+    hn_view out;
+} hn_node_desc;
+
+#define HN_POOL_ZERO_RB 0 /* MaxPool2dStaticSamePadding(3,2): zero pad right/bottom, zeros take part */
+#define HN_POOL_NEGINF 1  /* nn.MaxPool2d(3,2,padding=1) (lanedetect.py:41) */
+typedef struct hn_pool_desc {
+    hn_view in, out;
+    int32_t mode;
+} hn_pool_desc;
+
+/* Lane fuse to stride 32: cat(maxpool(maxpool(P3)), maxpool(P4), P5, up2(P6)) (lanedetect.py:76-80)
+ * or to stride 16: cat(maxpool(P3), up2(P5), P4, up4(P6)) (lanedetect.py:70-74). */
+typedef struct hn_lanefuse_desc {
+    hn_view p3, p4, p5, p6, out;
+    int32_t stride; /* 16 or 32 */
+} hn_lanefuse_desc;
+
+/* Squeeze-excite: x *= sigmoid(W2 relu(W1 mean_hw(x) + b1) + b2), in place (anynet.py:39-47,68-69). */
+typedef struct hn_se_desc {
+    hn_view x;
+    float* pooled; /* scratch fp32 [N][C], zeroed by the op */
+    float* scale;  /* scratch fp32 [N][C] */
+    const float *w1, *b1, *w2, *b2; /* w1 [S][C], w2 [C][S] */
+    int32_t S;
+} hn_se_desc;
+
+/* Detection decode + NMS (detection_loss.py:7-108; torchvision.ops.boxes.batched_nms semantics). */
+#define HN_NMS_AUTO_CUDA 0 /* coordinate trick iff 4*n <= 100000 (torchvision boxes.py, CUDA tensors) */
+#define HN_NMS_AUTO_CPU 1  /* coordinate trick iff 4*n <= 4000 */
+#define HN_NMS_TRICK 2
+#define HN_NMS_VANILLA 3
+typedef struct hn_det_desc {
+    const float* anchors;        /* [A][4] y1,x1,y2,x2 */
+    const float* regression;     /* [N][A][4] dy,dx,dh,dw */
+    const float* classification; /* [N][A][ncls] post-sigmoid */
+    int32_t N, A, ncls;
+    int32_t img_h, img_w;
+    float conf_thres, iou_thres;
+    int32_t nms_mode;
+    /* workspace, device: see hn_det_workspace_bytes */
+    void* workspace;
+    int64_t workspace_bytes;
+    /* outputs, device */
+    float* out_boxes;   /* [N][A][4] xyxy, kept boxes in score-descending order */
+    float* out_scores;  /* [N][A] */
+    int64_t* out_class; /* [N][A] */
+    int32_t* out_count; /* [N] kept per image */
+    int32_t* out_cand;  /* [N] candidates over threshold per image (diagnostic) */
+    /* optional: skip the decode and use these pre-decoded candidates ("identical pre-NMS inputs") */
+    const float* pre_boxes; /* [N][A][4] or NULL */
+} hn_det_desc;
+
+/* Lane decode + lane NMS (lane_codec.py:116-219, lane_codec_utils.py:487-542). One image per row. */
+typedef struct hn_lane_desc {
+    const float* cls; /* [N][fh*fw][2] logits, or probabilities if cls_is_prob */
+    const float* loc; /* [N][fh*fw][2*ppl+2] */
+    int32_t N, fh, fw, ppl;
+    int32_t cls_is_prob;
+    float conf_thres, nms_thres;
+    int32_t use_mean;
+    double step_w, interval, points_per_anchor; /* Python floats of the codec (lane_codec.py:33-46) */
+    float input_width, margin_width;
+    void* workspace; /* device scratch, hn_lane_workspace_bytes(N, fh*fw, ppl) */
+    /* outputs, device */
+    int32_t* out_count; /* [N] lanes after NMS */
+    int32_t* out_meta;  /* [N][fh*fw][4]: anchor index, start_pos, end_pos, n_points */
+    float* out_prob;    /* [N][fh*fw] */
+    float* out_x;       /* [N][fh*fw][ppl] x of every point, ordered bottom(start_pos) -> top */
+    int32_t* out_cand;  /* [N] lanes before NMS */
+} hn_lane_desc;
+
+/* ---- single-shot entry points (each enqueues on `stream` and returns) ---- */
+int hn_conv_fwd(const hn_conv_desc* d, void* stream);
+int hn_stem_fwd(const hn_stem_desc* d, void* stream);
+int hn_node_fwd(const hn_node_desc* d, void* stream);
+int hn_pool_fwd(const hn_pool_desc* d, void* stream);
+int hn_lanefuse_fwd(const hn_lanefuse_desc* d, void* stream);
+int hn_se_fwd(const hn_se_desc* d, void* stream);
+int hn_seg_argmax(const float* logits, int32_t N, int32_t C, int64_t HW, int64_t* out_i64, uint8_t* out_u8,
+                  void* stream);
+int hn_u8_to_i64(const uint8_t* in, int64_t* out, int64_t n, void* stream);
+int64_t hn_det_workspace_bytes(int32_t N, int32_t A);
+int hn_det_decode_nms(const hn_det_desc* d, void* stream);
+int64_t hn_lane_workspace_bytes(int32_t N, int32_t n_anchor, int32_t ppl);
+int hn_lane_decode_nms(const hn_lane_desc* d, void* stream);
+
+/* ---- plan: a recorded schedule of the ops above, replayed with one call (or as a CUDA graph) ---- */
+typedef struct hn_plan hn_plan;
+int hn_plan_create(hn_plan** out);
+int hn_plan_destroy(hn_plan* p);
+int hn_plan_add_conv(hn_plan* p, const hn_conv_desc* d);
+int hn_plan_add_stem(hn_plan* p, const hn_stem_desc* d);
+int hn_plan_add_node(hn_plan* p, const hn_node_desc* d);
+int hn_plan_add_pool(hn_plan* p, const hn_pool_desc* d);
+int hn_plan_add_lanefuse(hn_plan* p, const hn_lanefuse_desc* d);
+int hn_plan_add_se(hn_plan* p, const hn_se_desc* d);
+int hn_plan_add_det(hn_plan* p, const hn_det_desc* d);
+int hn_plan_add_lane(hn_plan* p, const hn_lane_desc* d);
+int hn_plan_size(const hn_plan* p);
+int hn_plan_num_launches(const hn_plan* p); /* kernels one replay launches */
+int hn_plan_run(hn_plan* p, void* stream);
+int hn_plan_run_range(hn_plan* p, int first, int last, void* stream);
+int hn_plan_graph_capture(hn_plan* p, void* stream); /* instantiate a CUDA graph of the whole plan */
+int hn_plan_graph_launch(hn_plan* p, void* stream);
+
+int hn_version(void);
+const char* hn_last_error(void);
+int hn_device_sm_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYDRANET_B200_H */

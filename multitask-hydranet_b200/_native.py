@@ -1,0 +1,149 @@
+"""ctypes binding of ``libhydranet_b200.so`` (the C ABI declared in ``include/hydranet_b200.h``).
+
+The library is loaded eagerly and loudly: if it is missing the import raises -- there is no CPU or
+PyTorch fallback behind any entry point.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhydranet_b200.so")
+
+HN_MAX_SRC = 6
+HN_MAX_TAPS = 96
+
+ACT_NONE, ACT_RELU, ACT_SWISH, ACT_ELU, ACT_SIGMOID = range(5)
+HALO_NONE, HALO_REFLECT, HALO_REPLICATE = range(3)
+EPI_STD, EPI_SEGOUT = range(2)
+IN_SAME, IN_UP2, IN_POOL = range(3)
+POOL_ZERO_RB, POOL_NEGINF = range(2)
+NMS_AUTO_CUDA, NMS_AUTO_CPU, NMS_TRICK, NMS_VANILLA = range(4)
+
+
+class View(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+                ("stride_n", C.c_int64), ("stride_y", C.c_int64), ("stride_x", C.c_int64)]
+
+
+class Tap(C.Structure):
+    _fields_ = [("src", C.c_int8), ("dy", C.c_int8), ("dx", C.c_int8), ("rsv0", C.c_int8),
+                ("c0", C.c_int16), ("rsv1", C.c_int16)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("src", View * HN_MAX_SRC), ("n_src", C.c_int32), ("weight", C.c_void_p), ("w_rows", C.c_int32),
+                ("num_taps", C.c_int32), ("taps", Tap * HN_MAX_TAPS), ("flat", C.c_int32),
+                ("tile_h", C.c_int32), ("tile_w", C.c_int32),
+                ("n_img", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32), ("flat_hw", C.c_int32),
+                ("cout", C.c_int32), ("bn", C.c_int32), ("stages", C.c_int32),
+                ("bias", C.c_void_p), ("act", C.c_int32), ("epi", C.c_int32),
+                ("out", C.c_void_p), ("out_fp32", C.c_int32),
+                ("out_stride_n", C.c_int64), ("out_stride_y", C.c_int64), ("out_stride_x", C.c_int64),
+                ("out_scale", C.c_int32), ("out_oy", C.c_int32), ("out_ox", C.c_int32), ("halo", C.c_int32),
+                ("res", C.c_void_p), ("res_stride_n", C.c_int64), ("res_stride_y", C.c_int64), ("res_stride_x", C.c_int64),
+                ("res_relu", C.c_int32), ("grouped", C.c_int32), ("out2", C.c_void_p), ("n_cls", C.c_int32)]
+
+
+class StemDesc(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("w", C.c_void_p), ("b", C.c_void_p), ("out", View)]
+
+
+class NodeDesc(C.Structure):
+    _fields_ = [("n_in", C.c_int32), ("in_", View * 3), ("mode", C.c_int32 * 3), ("w", C.c_float * 3),
+                ("swish", C.c_int32), ("dw", C.c_void_p), ("out", View)]
+
+
+class PoolDesc(C.Structure):
+    _fields_ = [("in_", View), ("out", View), ("mode", C.c_int32)]
+
+
+class LaneFuseDesc(C.Structure):
+    _fields_ = [("p3", View), ("p4", View), ("p5", View), ("p6", View), ("out", View), ("stride", C.c_int32)]
+
+
+class SeDesc(C.Structure):
+    _fields_ = [("x", View), ("pooled", C.c_void_p), ("scale", C.c_void_p),
+                ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("S", C.c_int32)]
+
+
+class DetDesc(C.Structure):
+    _fields_ = [("anchors", C.c_void_p), ("regression", C.c_void_p), ("classification", C.c_void_p),
+                ("N", C.c_int32), ("A", C.c_int32), ("ncls", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32),
+                ("conf_thres", C.c_float), ("iou_thres", C.c_float), ("nms_mode", C.c_int32),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+                ("out_boxes", C.c_void_p), ("out_scores", C.c_void_p), ("out_class", C.c_void_p),
+                ("out_count", C.c_void_p), ("out_cand", C.c_void_p), ("pre_boxes", C.c_void_p)]
+
+
+class LaneDesc(C.Structure):
+    _fields_ = [("cls", C.c_void_p), ("loc", C.c_void_p),
+                ("N", C.c_int32), ("fh", C.c_int32), ("fw", C.c_int32), ("ppl", C.c_int32),
+                ("cls_is_prob", C.c_int32), ("conf_thres", C.c_float), ("nms_thres", C.c_float), ("use_mean", C.c_int32),
+                ("step_w", C.c_double), ("interval", C.c_double), ("points_per_anchor", C.c_double),
+                ("input_width", C.c_float), ("margin_width", C.c_float), ("workspace", C.c_void_p),
+                ("out_count", C.c_void_p), ("out_meta", C.c_void_p), ("out_prob", C.c_void_p), ("out_x", C.c_void_p),
+                ("out_cand", C.c_void_p)]
+
+
+#: every symbol ``include/hydranet_b200.h`` declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "hn_conv_fwd": (C.c_int, [C.POINTER(ConvDesc), _P]),
+    "hn_stem_fwd": (C.c_int, [C.POINTER(StemDesc), _P]),
+    "hn_node_fwd": (C.c_int, [C.POINTER(NodeDesc), _P]),
+    "hn_pool_fwd": (C.c_int, [C.POINTER(PoolDesc), _P]),
+    "hn_lanefuse_fwd": (C.c_int, [C.POINTER(LaneFuseDesc), _P]),
+    "hn_se_fwd": (C.c_int, [C.POINTER(SeDesc), _P]),
+    "hn_seg_argmax": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P]),
+    "hn_u8_to_i64": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "hn_det_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "hn_det_decode_nms": (C.c_int, [C.POINTER(DetDesc), _P]),
+    "hn_lane_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "hn_lane_decode_nms": (C.c_int, [C.POINTER(LaneDesc), _P]),
+    "hn_plan_create": (C.c_int, [C.POINTER(_P)]),
+    "hn_plan_destroy": (C.c_int, [_P]),
+    "hn_plan_add_conv": (C.c_int, [_P, C.POINTER(ConvDesc)]),
+    "hn_plan_add_stem": (C.c_int, [_P, C.POINTER(StemDesc)]),
+    "hn_plan_add_node": (C.c_int, [_P, C.POINTER(NodeDesc)]),
+    "hn_plan_add_pool": (C.c_int, [_P, C.POINTER(PoolDesc)]),
+    "hn_plan_add_lanefuse": (C.c_int, [_P, C.POINTER(LaneFuseDesc)]),
+    "hn_plan_add_se": (C.c_int, [_P, C.POINTER(SeDesc)]),
+    "hn_plan_add_det": (C.c_int, [_P, C.POINTER(DetDesc)]),
+    "hn_plan_add_lane": (C.c_int, [_P, C.POINTER(LaneDesc)]),
+    "hn_plan_size": (C.c_int, [_P]),
+    "hn_plan_num_launches": (C.c_int, [_P]),
+    "hn_plan_run": (C.c_int, [_P, _P]),
+    "hn_plan_run_range": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "hn_plan_graph_capture": (C.c_int, [_P, _P]),
+    "hn_plan_graph_launch": (C.c_int, [_P, _P]),
+    "hn_version": (C.c_int, []),
+    "hn_last_error": (C.c_char_p, []),
+    "hn_device_sm_count": (C.c_int, []),
+}
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "hydranet_b200: native library %s is missing. Build it with `python -c 'import __graft_entry__ as g; "
+        "g.build()'` (or ./build.sh). There is no CPU / PyTorch fallback for this path." % LIB_PATH)
+
+lib = C.CDLL(LIB_PATH)
+for _name, (_res, _args) in SYMBOLS.items():
+    _fn = getattr(lib, _name)  # AttributeError here == header / library mismatch
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def check(rc):
+    """Raise on a non-zero status, mirroring the reference's Python exceptions."""
+    if rc != 0:
+        raise NativeError("hydranet_b200 native call failed (code %d): %s" % (rc, lib.hn_last_error().decode()))
+
+
+def view(t, N, H, W, Cc, sn, sy, sx, offset=0):
+    """hn_view over a bf16 tensor's storage, ``offset`` in elements from ``t.data_ptr()``."""
+    return View(t.data_ptr() + 2 * offset, N, H, W, Cc, sn, sy, sx)

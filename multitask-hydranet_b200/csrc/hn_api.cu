@@ -1,0 +1,163 @@
+// C-ABI plumbing: error string, version, device query, and the plan (a recorded schedule of ops).
+#include <stdarg.h>
+
+#include <vector>
+
+#include "hn_common.cuh"
+#include "hn_ops.h"
+
+static thread_local char g_err[1024] = "";
+
+void hn_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* hn_last_error(void) { return g_err; }
+extern "C" int hn_version(void) { return 100; }
+extern "C" int hn_device_sm_count(void) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+enum OpKind { OP_CONV, OP_STEM, OP_NODE, OP_POOL, OP_LANEFUSE, OP_SE, OP_DET, OP_LANE };
+
+struct PlanOp {
+    OpKind kind;
+    ConvLaunch conv;  // OP_CONV (tensor maps pre-encoded)
+    hn_stem_desc stem;
+    hn_node_desc node;
+    hn_pool_desc pool;
+    hn_lanefuse_desc lanefuse;
+    hn_se_desc se;
+    hn_det_desc det;
+    hn_lane_desc lane;
+};
+
+struct hn_plan {
+    std::vector<PlanOp*> ops;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    ~hn_plan() {
+        for (auto* o : ops) delete o;
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+    }
+};
+
+extern "C" int hn_plan_create(hn_plan** out) {
+    HN_REQUIRE(out != nullptr, "null out");
+    *out = new hn_plan();
+    return HN_OK;
+}
+extern "C" int hn_plan_destroy(hn_plan* p) {
+    delete p;
+    return HN_OK;
+}
+extern "C" int hn_plan_size(const hn_plan* p) { return p ? (int)p->ops.size() : -1; }
+
+#define PLAN_ADD(NAME, KIND, FIELD, DESC_T)                                  \
+    extern "C" int hn_plan_add_##NAME(hn_plan* p, const DESC_T* d) {         \
+        HN_REQUIRE(p != nullptr && d != nullptr, "null plan/desc");          \
+        PlanOp* o = new PlanOp();                                            \
+        o->kind = KIND;                                                      \
+        o->FIELD = *d;                                                       \
+        p->ops.push_back(o);                                                 \
+        return HN_OK;                                                        \
+    }
+PLAN_ADD(stem, OP_STEM, stem, hn_stem_desc)
+PLAN_ADD(node, OP_NODE, node, hn_node_desc)
+PLAN_ADD(pool, OP_POOL, pool, hn_pool_desc)
+PLAN_ADD(lanefuse, OP_LANEFUSE, lanefuse, hn_lanefuse_desc)
+PLAN_ADD(se, OP_SE, se, hn_se_desc)
+PLAN_ADD(det, OP_DET, det, hn_det_desc)
+PLAN_ADD(lane, OP_LANE, lane, hn_lane_desc)
+
+extern "C" int hn_plan_add_conv(hn_plan* p, const hn_conv_desc* d) {
+    HN_REQUIRE(p != nullptr && d != nullptr, "null plan/desc");
+    PlanOp* o = new PlanOp();
+    o->kind = OP_CONV;
+    int rc = hn_conv_prepare(d, &o->conv);
+    if (rc) {
+        delete o;
+        return rc;
+    }
+    p->ops.push_back(o);
+    return HN_OK;
+}
+
+static int op_launches(const PlanOp* o) {
+    switch (o->kind) {
+        case OP_SE: return 3;
+        case OP_DET: return hn_det_num_launches(&o->det);
+        case OP_LANE: return 1;
+        default: return 1;
+    }
+}
+
+extern "C" int hn_plan_num_launches(const hn_plan* p) {
+    if (!p) return -1;
+    int n = 0;
+    for (auto* o : p->ops) n += op_launches(o);
+    return n;
+}
+
+extern "C" int hn_plan_run_range(hn_plan* p, int first, int last, void* stream) {
+    HN_REQUIRE(p != nullptr, "null plan");
+    HN_REQUIRE(first >= 0 && last <= (int)p->ops.size() && first <= last, "bad op range [%d,%d)", first, last);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    for (int i = first; i < last; ++i) {
+        PlanOp* o = p->ops[i];
+        int rc = HN_OK;
+        switch (o->kind) {
+            case OP_CONV: rc = hn_conv_launch(&o->conv, s); break;
+            case OP_STEM: rc = hn_stem_fwd(&o->stem, stream); break;
+            case OP_NODE: rc = hn_node_fwd(&o->node, stream); break;
+            case OP_POOL: rc = hn_pool_fwd(&o->pool, stream); break;
+            case OP_LANEFUSE: rc = hn_lanefuse_fwd(&o->lanefuse, stream); break;
+            case OP_SE: rc = hn_se_fwd(&o->se, stream); break;
+            case OP_DET: rc = hn_det_decode_nms(&o->det, stream); break;
+            case OP_LANE: rc = hn_lane_decode_nms(&o->lane, stream); break;
+        }
+        if (rc) return rc;
+    }
+    return HN_OK;
+}
+
+extern "C" int hn_plan_run(hn_plan* p, void* stream) {
+    HN_REQUIRE(p != nullptr, "null plan");
+    return hn_plan_run_range(p, 0, (int)p->ops.size(), stream);
+}
+
+extern "C" int hn_plan_graph_capture(hn_plan* p, void* stream) {
+    HN_REQUIRE(p != nullptr, "null plan");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (p->exec) {
+        cudaGraphExecDestroy(p->exec);
+        p->exec = nullptr;
+    }
+    if (p->graph) {
+        cudaGraphDestroy(p->graph);
+        p->graph = nullptr;
+    }
+    HN_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    int rc = hn_plan_run(p, stream);
+    cudaError_t e = cudaStreamEndCapture(s, &p->graph);
+    if (rc) return rc;
+    HN_CHECK_CUDA(e);
+    HN_CHECK_CUDA(cudaGraphInstantiate(&p->exec, p->graph, 0));
+    return HN_OK;
+}
+
+extern "C" int hn_plan_graph_launch(hn_plan* p, void* stream) {
+    HN_REQUIRE(p != nullptr && p->exec != nullptr, "plan has no captured graph");
+    HN_CHECK_CUDA(cudaGraphLaunch(p->exec, reinterpret_cast<cudaStream_t>(stream)));
+    return HN_OK;
+}

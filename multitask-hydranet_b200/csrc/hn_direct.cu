@@ -1,0 +1,484 @@
+// HBM-bound operators of the HydraNet forward: stem, BiFPN fusion node (+depthwise), max-pools,
+// lane multi-scale fuse, squeeze-excite.  All activations are NHWC bf16 views; threads own 8-channel
+// (16-byte) vectors so every global access is a coalesced 128-bit transaction.
+#include "hn_ops.h"
+
+struct View {
+    const bf16* ptr;
+    int N, H, W, C;
+    long long sn, sy, sx;
+};
+static inline View to_view(const hn_view& v) {
+    View r;
+    r.ptr = reinterpret_cast<const bf16*>(v.ptr);
+    r.N = v.N; r.H = v.H; r.W = v.W; r.C = v.C;
+    r.sn = v.stride_n; r.sy = v.stride_y; r.sx = v.stride_x;
+    return r;
+}
+static int check_view(const hn_view& v, const char* what) {
+    HN_REQUIRE(v.ptr != nullptr, "%s: null view", what);
+    HN_REQUIRE((reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0 && v.C % 8 == 0 && v.stride_x % 8 == 0 && v.stride_y % 8 == 0 &&
+                   v.stride_n % 8 == 0,
+               "%s: view must be 16-byte aligned with C and strides in multiples of 8 (C=%d)", what, v.C);
+    return HN_OK;
+}
+
+__device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    float2 a = hn_unpack_bf16x2(u.x), b = hn_unpack_bf16x2(u.y), c = hn_unpack_bf16x2(u.z), d = hn_unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
+    uint4 u;
+    u.x = hn_pack_bf16x2(f[0], f[1]); u.y = hn_pack_bf16x2(f[2], f[3]);
+    u.z = hn_pack_bf16x2(f[4], f[5]); u.w = hn_pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ const bf16* vptr(const View& v, int n, int y, int x, int c) {
+    return v.ptr + (long long)n * v.sn + (long long)y * v.sy + (long long)x * v.sx + c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem: 3x3 s2 p1, 3 -> 32, fp32 NCHW -> bf16 NHWC, BN folded, ReLU
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) hn_stem_kernel(const float* __restrict__ x, int N, int H, int W,
+                                                      const float* __restrict__ w, const float* __restrict__ b,
+                                                      View out) {
+    __shared__ float sw[27 * 32];
+    __shared__ float sb[32];
+    for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = w[i];
+    if (threadIdx.x < 32) sb[threadIdx.x] = b[threadIdx.x];
+    __syncthreads();
+    const int OH = out.H, OW = out.W;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)N * OH * OW;
+    if (idx >= total) return;
+    int ox = (int)(idx % OW);
+    int oy = (int)((idx / OW) % OH);
+    int n = (int)(idx / ((long long)OW * OH));
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = sb[c];
+    const float* xin = x + (long long)n * 3 * H * W;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            int iy = oy * 2 - 1 + ky;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                int ix = ox * 2 - 1 + kx;
+                float v = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xin + ((long long)ci * H + iy) * W + ix) : 0.0f;
+                const float4* wr = reinterpret_cast<const float4*>(sw + (ci * 9 + ky * 3 + kx) * 32);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    float4 ww = wr[c4];
+                    acc[c4 * 4 + 0] = fmaf(v, ww.x, acc[c4 * 4 + 0]);
+                    acc[c4 * 4 + 1] = fmaf(v, ww.y, acc[c4 * 4 + 1]);
+                    acc[c4 * 4 + 2] = fmaf(v, ww.z, acc[c4 * 4 + 2]);
+                    acc[c4 * 4 + 3] = fmaf(v, ww.w, acc[c4 * 4 + 3]);
+                }
+            }
+        }
+    }
+    bf16* o = const_cast<bf16*>(vptr(out, n, oy, ox, 0));
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(acc[c8 * 8 + j], 0.0f);
+        store8(o + c8 * 8, f);
+    }
+}
+
+extern "C" int hn_stem_fwd(const hn_stem_desc* d, void* stream) {
+    HN_REQUIRE(d && d->x && d->w && d->b, "stem: null pointer");
+    if (int rc = check_view(d->out, "stem.out")) return rc;
+    HN_REQUIRE(d->out.C == 32 && d->out.N == d->N && d->out.H == (d->H + 1) / 2 && d->out.W == (d->W + 1) / 2,
+               "stem: output view %dx%dx%dx%d does not match input %dx3x%dx%d", d->out.N, d->out.H, d->out.W, d->out.C, d->N,
+               d->H, d->W);
+    long long total = (long long)d->N * d->out.H * d->out.W;
+    hn_stem_kernel<<<hn_cdiv(total, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d->x, d->N, d->H, d->W, d->w,
+                                                                                          d->b, to_view(d->out));
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BiFPN node front half: weighted sum of <=3 inputs (same / nearest-up2 / zero-padded max-pool)
+// -> swish -> depthwise 3x3 (zero pad 1).  The fused value of the (T+2)^2 halo tile is computed once
+// into shared memory (fp32), the depthwise taps then read it from there.
+// ------------------------------------------------------------------------------------------------
+struct NodeParams {
+    int n_in;
+    View in[3];
+    int mode[3];
+    float w[3];
+    int swish;
+    const float* dw;
+    View out;
+    int tiles_x, tiles_y;
+};
+
+static constexpr int kNodeT = 8;
+
+__device__ __forceinline__ void node_fetch(const View& v, int mode, int n, int y, int x, int c, float (&f)[8]) {
+    if (mode == HN_IN_SAME) {
+        load8(vptr(v, n, y, x, c), f);
+    } else if (mode == HN_IN_UP2) {
+        load8(vptr(v, n, y >> 1, x >> 1, c), f);
+    } else {
+        // 3x3 stride-2 max over the input padded with one zero row/col at the bottom/right
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = -INFINITY;
+        for (int dy = 0; dy < 3; ++dy) {
+            int iy = 2 * y + dy;
+            for (int dx = 0; dx < 3; ++dx) {
+                int ix = 2 * x + dx;
+                float g[8];
+                if (iy < v.H && ix < v.W) {
+                    load8(vptr(v, n, iy, ix, c), g);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) g[j] = 0.0f;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], g[j]);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) hn_node_kernel(const __grid_constant__ NodeParams p) {
+    extern __shared__ float s_tile[];  // [(T+2)*(T+2)][C]
+    const int C = p.out.C, CV = C >> 3;
+    const int per_img = p.tiles_x * p.tiles_y;
+    const int n = blockIdx.x / per_img;
+    const int r = blockIdx.x - n * per_img;
+    const int y0 = (r / p.tiles_x) * kNodeT, x0 = (r % p.tiles_x) * kNodeT;
+    const int HT = kNodeT + 2;
+    for (int it = threadIdx.x; it < HT * HT * CV; it += blockDim.x) {
+        int cv = it % CV, px = it / CV;
+        int hy = px / HT, hx = px - hy * HT;
+        int y = y0 + hy - 1, x = x0 + hx - 1;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+        if (y >= 0 && y < p.out.H && x >= 0 && x < p.out.W) {
+            for (int i = 0; i < p.n_in; ++i) {
+                float f[8];
+                node_fetch(p.in[i], p.mode[i], n, y, x, cv * 8, f);
+                // the reference evaluates w0*a + w1*b (+ w2*c) left to right in fp32 (bifpn.py:170-231)
+                if (i == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = p.w[0] * f[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = acc[j] + p.w[i] * f[j];
+                }
+            }
+            if (p.swish) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = acc[j] * hn_sigmoid(acc[j]);
+            }
+        }
+        float4* dst = reinterpret_cast<float4*>(s_tile + (long long)px * C + cv * 8);
+        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    __syncthreads();
+    for (int it = threadIdx.x; it < kNodeT * kNodeT * CV; it += blockDim.x) {
+        int cv = it % CV, px = it / CV;
+        int ty = px / kNodeT, tx = px - ty * kNodeT;
+        int y = y0 + ty, x = x0 + tx;
+        if (y >= p.out.H || x >= p.out.W) continue;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float4* sv = reinterpret_cast<const float4*>(s_tile + (long long)((ty + ky) * HT + tx + kx) * C + cv * 8);
+                const float4* wv = reinterpret_cast<const float4*>(p.dw + (ky * 3 + kx) * C + cv * 8);
+                float4 a0 = sv[0], a1 = sv[1];
+                float4 w0 = __ldg(wv), w1 = __ldg(wv + 1);
+                acc[0] = fmaf(a0.x, w0.x, acc[0]); acc[1] = fmaf(a0.y, w0.y, acc[1]);
+                acc[2] = fmaf(a0.z, w0.z, acc[2]); acc[3] = fmaf(a0.w, w0.w, acc[3]);
+                acc[4] = fmaf(a1.x, w1.x, acc[4]); acc[5] = fmaf(a1.y, w1.y, acc[5]);
+                acc[6] = fmaf(a1.z, w1.z, acc[6]); acc[7] = fmaf(a1.w, w1.w, acc[7]);
+            }
+        }
+        store8(const_cast<bf16*>(vptr(p.out, n, y, x, cv * 8)), acc);
+    }
+}
+
+extern "C" int hn_node_fwd(const hn_node_desc* d, void* stream) {
+    HN_REQUIRE(d && d->n_in >= 1 && d->n_in <= 3 && d->dw, "node: bad descriptor");
+    if (int rc = check_view(d->out, "node.out")) return rc;
+    NodeParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_in = d->n_in;
+    for (int i = 0; i < d->n_in; ++i) {
+        if (int rc = check_view(d->in[i], "node.in")) return rc;
+        const hn_view& v = d->in[i];
+        HN_REQUIRE(v.C == d->out.C && v.N == d->out.N, "node: input %d channel/batch mismatch", i);
+        if (d->mode[i] == HN_IN_SAME) HN_REQUIRE(v.H == d->out.H && v.W == d->out.W, "node: SAME input %d size mismatch", i);
+        else if (d->mode[i] == HN_IN_UP2)
+            HN_REQUIRE(v.H * 2 == d->out.H && v.W * 2 == d->out.W, "node: UP2 input %d is %dx%d for output %dx%d", i, v.H, v.W,
+                       d->out.H, d->out.W);
+        else if (d->mode[i] == HN_IN_POOL)
+            HN_REQUIRE((v.H - 2) / 2 + 1 == d->out.H && (v.W - 2) / 2 + 1 == d->out.W,
+                       "node: POOL input %d is %dx%d for output %dx%d", i, v.H, v.W, d->out.H, d->out.W);
+        else HN_REQUIRE(false, "node: unknown input mode %d", d->mode[i]);
+        p.in[i] = to_view(v);
+        p.mode[i] = d->mode[i];
+        p.w[i] = d->w[i];
+    }
+    p.swish = d->swish;
+    p.dw = d->dw;
+    p.out = to_view(d->out);
+    p.tiles_x = hn_cdiv(d->out.W, kNodeT);
+    p.tiles_y = hn_cdiv(d->out.H, kNodeT);
+    size_t smem = (size_t)(kNodeT + 2) * (kNodeT + 2) * d->out.C * sizeof(float);
+    HN_REQUIRE(smem <= 200 * 1024, "node: C=%d too large for the halo tile", d->out.C);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        HN_CHECK_CUDA(cudaFuncSetAttribute(hn_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    hn_node_kernel<<<p.tiles_x * p.tiles_y * d->out.N, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// standalone 3x3 stride-2 max-pool
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pool_neginf(const View& v, int n, int y, int x, int c, float (&f)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = -INFINITY;
+    for (int dy = -1; dy <= 1; ++dy) {
+        int iy = 2 * y + dy;
+        if (iy < 0 || iy >= v.H) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+            int ix = 2 * x + dx;
+            if (ix < 0 || ix >= v.W) continue;
+            float g[8];
+            load8(vptr(v, n, iy, ix, c), g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], g[j]);
+        }
+    }
+}
+
+__global__ void hn_pool_kernel(View in, View out, int mode) {
+    const int CV = out.C >> 3;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)out.N * out.H * out.W * CV;
+    if (idx >= total) return;
+    int cv = (int)(idx % CV);
+    long long t = idx / CV;
+    int x = (int)(t % out.W);
+    t /= out.W;
+    int y = (int)(t % out.H);
+    int n = (int)(t / out.H);
+    float f[8];
+    if (mode == HN_POOL_ZERO_RB) node_fetch(in, HN_IN_POOL, n, y, x, cv * 8, f);
+    else pool_neginf(in, n, y, x, cv * 8, f);
+    store8(const_cast<bf16*>(vptr(out, n, y, x, cv * 8)), f);
+}
+
+extern "C" int hn_pool_fwd(const hn_pool_desc* d, void* stream) {
+    HN_REQUIRE(d != nullptr, "pool: null desc");
+    if (int rc = check_view(d->in, "pool.in")) return rc;
+    if (int rc = check_view(d->out, "pool.out")) return rc;
+    HN_REQUIRE(d->in.C == d->out.C && d->in.N == d->out.N, "pool: channel/batch mismatch");
+    if (d->mode == HN_POOL_ZERO_RB)
+        HN_REQUIRE((d->in.H - 2) / 2 + 1 == d->out.H && (d->in.W - 2) / 2 + 1 == d->out.W, "pool: size mismatch");
+    else
+        HN_REQUIRE((d->in.H - 1) / 2 + 1 == d->out.H && (d->in.W - 1) / 2 + 1 == d->out.W, "pool: size mismatch");
+    long long total = (long long)d->out.N * d->out.H * d->out.W * (d->out.C / 8);
+    hn_pool_kernel<<<hn_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(to_view(d->in), to_view(d->out),
+                                                                                          d->mode);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lane fuse
+// ------------------------------------------------------------------------------------------------
+struct LaneFuseParams {
+    View p3, p4, p5, p6, out;
+    int stride;
+};
+
+__global__ void hn_lanefuse_kernel(const __grid_constant__ LaneFuseParams p) {
+    const int C = p.p3.C, CV = C >> 3;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)p.out.N * p.out.H * p.out.W * 4 * CV;
+    if (idx >= total) return;
+    int cv = (int)(idx % CV);
+    long long t = idx / CV;
+    int part = (int)(t % 4);
+    t /= 4;
+    int x = (int)(t % p.out.W);
+    t /= p.out.W;
+    int y = (int)(t % p.out.H);
+    int n = (int)(t / p.out.H);
+    const int c = cv * 8;
+    float f[8];
+    if (p.stride == 32) {
+        if (part == 0) {
+            // maxpool(maxpool(P3)): evaluate the inner pool at the (up to 9) valid outer taps
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = -INFINITY;
+            const int H1 = (p.p3.H - 1) / 2 + 1, W1 = (p.p3.W - 1) / 2 + 1;
+            for (int dy = -1; dy <= 1; ++dy) {
+                int iy = 2 * y + dy;
+                if (iy < 0 || iy >= H1) continue;
+                for (int dx = -1; dx <= 1; ++dx) {
+                    int ix = 2 * x + dx;
+                    if (ix < 0 || ix >= W1) continue;
+                    float g[8];
+                    pool_neginf(p.p3, n, iy, ix, c, g);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], g[j]);
+                }
+            }
+        } else if (part == 1) {
+            pool_neginf(p.p4, n, y, x, c, f);
+        } else if (part == 2) {
+            load8(vptr(p.p5, n, y, x, c), f);
+        } else {
+            load8(vptr(p.p6, n, y >> 1, x >> 1, c), f);
+        }
+    } else {
+        if (part == 0) pool_neginf(p.p3, n, y, x, c, f);
+        else if (part == 1) load8(vptr(p.p5, n, y >> 1, x >> 1, c), f);
+        else if (part == 2) load8(vptr(p.p4, n, y, x, c), f);
+        else load8(vptr(p.p6, n, y >> 2, x >> 2, c), f);
+    }
+    store8(const_cast<bf16*>(vptr(p.out, n, y, x, part * C + c)), f);
+}
+
+extern "C" int hn_lanefuse_fwd(const hn_lanefuse_desc* d, void* stream) {
+    HN_REQUIRE(d != nullptr && (d->stride == 16 || d->stride == 32), "lanefuse: stride must be 16 or 32");
+    const hn_view* vs[5] = {&d->p3, &d->p4, &d->p5, &d->p6, &d->out};
+    for (int i = 0; i < 5; ++i)
+        if (int rc = check_view(*vs[i], "lanefuse")) return rc;
+    HN_REQUIRE(d->out.C == 4 * d->p3.C && d->p4.C == d->p3.C && d->p5.C == d->p3.C && d->p6.C == d->p3.C,
+               "lanefuse: channel mismatch");
+    if (d->stride == 32)
+        HN_REQUIRE(d->out.H == d->p5.H && d->out.W == d->p5.W && d->p6.H * 2 == d->out.H && d->p6.W * 2 == d->out.W &&
+                       (d->p4.H - 1) / 2 + 1 == d->out.H && ((d->p3.H - 1) / 2 + 1 - 1) / 2 + 1 == d->out.H,
+                   "lanefuse: pyramid sizes inconsistent for stride 32");
+    else
+        HN_REQUIRE(d->out.H == d->p4.H && d->out.W == d->p4.W && d->p5.H * 2 == d->out.H && d->p6.H * 4 == d->out.H &&
+                       (d->p3.H - 1) / 2 + 1 == d->out.H,
+                   "lanefuse: pyramid sizes inconsistent for stride 16");
+    LaneFuseParams p;
+    p.p3 = to_view(d->p3); p.p4 = to_view(d->p4); p.p5 = to_view(d->p5); p.p6 = to_view(d->p6); p.out = to_view(d->out);
+    p.stride = d->stride;
+    long long total = (long long)d->out.N * d->out.H * d->out.W * 4 * (d->p3.C / 8);
+    hn_lanefuse_kernel<<<hn_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// squeeze-excite: pool -> fc -> scale (in place)
+// ------------------------------------------------------------------------------------------------
+static constexpr int kSePixPerBlock = 256;
+
+__global__ void __launch_bounds__(256) hn_se_pool_kernel(View x, float* __restrict__ pooled) {
+    // block = (image, chunk of pixels); thread = channel vector x pixel lane
+    const int CV = x.C >> 3;
+    const int n = blockIdx.y;
+    const int HW = x.H * x.W;
+    const int p0 = blockIdx.x * kSePixPerBlock;
+    const int p1 = min(p0 + kSePixPerBlock, HW);
+    const int lanes = blockDim.x / CV;  // pixel lanes per block (>=1)
+    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+    if (pl >= lanes) return;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    for (int px = p0 + pl; px < p1; px += lanes) {
+        int y = px / x.W, xx = px - y * x.W;
+        float f[8];
+        load8(vptr(x, n, y, xx, cv * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(pooled + (long long)n * x.C + cv * 8 + j, acc[j]);
+}
+
+__global__ void __launch_bounds__(256) hn_se_fc_kernel(const float* __restrict__ pooled, float* __restrict__ scale, int C, int S,
+                                                       float inv_hw, const float* __restrict__ w1, const float* __restrict__ b1,
+                                                       const float* __restrict__ w2, const float* __restrict__ b2) {
+    extern __shared__ float sm[];  // mean[C], hidden[S]
+    float* mean = sm;
+    float* hid = sm + C;
+    const int n = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = pooled[(long long)n * C + c] * inv_hw;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int s = warp; s < S; s += nw) {
+        float a = 0.0f;
+        for (int c = lane; c < C; c += 32) a = fmaf(w1[(long long)s * C + c], mean[c], a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) hid[s] = fmaxf(a + b1[s], 0.0f);
+    }
+    __syncthreads();
+    for (int c = warp; c < C; c += nw) {
+        float a = 0.0f;
+        for (int s = lane; s < S; s += 32) a = fmaf(w2[(long long)c * S + s], hid[s], a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) scale[(long long)n * C + c] = 1.0f / (1.0f + expf(-(a + b2[c])));
+    }
+}
+
+__global__ void hn_se_scale_kernel(View x, const float* __restrict__ scale) {
+    const int CV = x.C >> 3;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)x.N * x.H * x.W * CV;
+    if (idx >= total) return;
+    int cv = (int)(idx % CV);
+    long long t = idx / CV;
+    int xx = (int)(t % x.W);
+    t /= x.W;
+    int y = (int)(t % x.H);
+    int n = (int)(t / x.H);
+    bf16* p = const_cast<bf16*>(vptr(x, n, y, xx, cv * 8));
+    float f[8];
+    load8(p, f);
+    const float4* s4 = reinterpret_cast<const float4*>(scale + (long long)n * x.C + cv * 8);
+    float4 s0 = s4[0], s1 = s4[1];
+    f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
+    f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+    store8(p, f);
+}
+
+extern "C" int hn_se_fwd(const hn_se_desc* d, void* stream) {
+    HN_REQUIRE(d && d->pooled && d->scale && d->w1 && d->b1 && d->w2 && d->b2 && d->S >= 1, "se: bad descriptor");
+    if (int rc = check_view(d->x, "se.x")) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int C = d->x.C, CV = C / 8, HW = d->x.H * d->x.W;
+    HN_REQUIRE(CV <= 256, "se: C=%d too wide", C);
+    HN_CHECK_CUDA(cudaMemsetAsync(d->pooled, 0, sizeof(float) * (size_t)d->x.N * C, s));
+    int threads = (256 / CV) * CV;
+    dim3 grid(hn_cdiv(HW, kSePixPerBlock), d->x.N);
+    hn_se_pool_kernel<<<grid, threads, 0, s>>>(to_view(d->x), d->pooled);
+    HN_CHECK_CUDA(cudaGetLastError());
+    hn_se_fc_kernel<<<d->x.N, 256, (C + d->S) * sizeof(float), s>>>(d->pooled, d->scale, C, d->S, 1.0f / (float)HW, d->w1, d->b1,
+                                                                   d->w2, d->b2);
+    HN_CHECK_CUDA(cudaGetLastError());
+    long long total = (long long)d->x.N * HW * CV;
+    hn_se_scale_kernel<<<hn_cdiv(total, 256), 256, 0, s>>>(to_view(d->x), d->scale);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}

@@ -1,0 +1,33 @@
+// Internal (non-ABI) declarations shared between translation units.
+#pragma once
+#include "hn_common.cuh"
+
+struct alignas(64) ConvParams {
+    CUtensorMap tmA[HN_MAX_SRC];
+    CUtensorMap tmB;
+    int flat, TH, TW, n_img, H, W, tiles_x, tiles_y, flat_hw, flat_m;
+    int num_taps, cout, bn, stages, tmem_cols;
+    const float* bias;
+    int act, epi;
+    void* out;
+    int out_fp32;
+    long long osn, osy, osx;
+    int oscale, ooy, oox, halo;
+    const bf16* res;
+    long long rsn, rsy, rsx;
+    int res_relu, grouped;
+    uint8_t* out2;
+    int n_cls;
+    hn_tap taps[HN_MAX_TAPS];
+};
+
+
+struct ConvLaunch {
+    ConvParams prm;
+    dim3 grid;
+    size_t smem;
+};
+
+int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L);
+int hn_conv_launch(const ConvLaunch* L, cudaStream_t stream);
+int hn_det_num_launches(const hn_det_desc* d);

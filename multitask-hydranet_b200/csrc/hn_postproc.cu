@@ -1,0 +1,630 @@
+// Post-processing of the three heads on the GPU.
+//   seg : arg-max over classes (torch.argmax semantics: first maximum, NaN counts as maximum)
+//   det : box decode + clip + score threshold + class-aware greedy NMS with torchvision's exact
+//         fp32 arithmetic and tie order
+//   lane: per-anchor polyline decode + greedy lane NMS with the reference's fp32/py-float arithmetic
+// Arithmetic that must be bit-exact uses __f*_rn intrinsics so nvcc cannot contract it into FMAs.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "hn_ops.h"
+
+// ------------------------------------------------------------------------------------------------
+// segmentation arg-max
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool greater_or_nan(float v, float best) {
+    return (v > best) || (v != v && best == best);
+}
+
+__global__ void hn_seg_argmax_kernel(const float* __restrict__ logits, int C, long long HW, long long total_px,
+                                     int64_t* __restrict__ out64, uint8_t* __restrict__ out8) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= total_px) return;
+    long long n = i / HW, p = i - n * HW;
+    const float* base = logits + n * C * HW + p;
+    if (p + 3 < HW && (HW & 3) == 0) {
+        float4 best = *reinterpret_cast<const float4*>(base);
+        int b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+        for (int k = 1; k < C; ++k) {
+            float4 v = *reinterpret_cast<const float4*>(base + k * HW);
+            if (greater_or_nan(v.x, best.x)) { best.x = v.x; b0 = k; }
+            if (greater_or_nan(v.y, best.y)) { best.y = v.y; b1 = k; }
+            if (greater_or_nan(v.z, best.z)) { best.z = v.z; b2 = k; }
+            if (greater_or_nan(v.w, best.w)) { best.w = v.w; b3 = k; }
+        }
+        if (out64) { out64[i] = b0; out64[i + 1] = b1; out64[i + 2] = b2; out64[i + 3] = b3; }
+        if (out8) *reinterpret_cast<uchar4*>(out8 + i) = make_uchar4((uint8_t)b0, (uint8_t)b1, (uint8_t)b2, (uint8_t)b3);
+    } else {
+        for (int j = 0; j < 4 && i + j < total_px; ++j) {
+            long long ii = i + j;
+            long long nn = ii / HW, pp = ii - nn * HW;
+            const float* b = logits + nn * C * HW + pp;
+            float best = b[0];
+            int bi = 0;
+            for (int k = 1; k < C; ++k) {
+                float v = b[k * HW];
+                if (greater_or_nan(v, best)) { best = v; bi = k; }
+            }
+            if (out64) out64[ii] = bi;
+            if (out8) out8[ii] = (uint8_t)bi;
+        }
+    }
+}
+
+extern "C" int hn_seg_argmax(const float* logits, int32_t N, int32_t C, int64_t HW, int64_t* out_i64, uint8_t* out_u8,
+                             void* stream) {
+    HN_REQUIRE(logits && (out_i64 || out_u8) && N >= 0 && C >= 1 && C <= 255 && HW >= 0, "seg_argmax: bad arguments");
+    long long total = (long long)N * HW;
+    if (total == 0) return HN_OK;
+    HN_REQUIRE((reinterpret_cast<uintptr_t>(logits) & 15) == 0, "seg_argmax: logits must be 16-byte aligned");
+    hn_seg_argmax_kernel<<<hn_cdiv(hn_cdiv(total, 4), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        logits, C, HW, total, out_i64, out_u8);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+__global__ void hn_u8_to_i64_kernel(const uint8_t* __restrict__ in, int64_t* __restrict__ out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+extern "C" int hn_u8_to_i64(const uint8_t* in, int64_t* out, int64_t n, void* stream) {
+    HN_REQUIRE(in && out && n >= 0, "u8_to_i64: bad arguments");
+    if (n == 0) return HN_OK;
+    hn_u8_to_i64_kernel<<<hn_cdiv(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, out, n);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// detection
+// ------------------------------------------------------------------------------------------------
+// sort key: [img:8][cls:4][~score:32][anchor:20]; invalid (below threshold) = all ones
+static constexpr int kAnchorBits = 20, kScoreShift = 20, kClsShift = 52, kImgShift = 56;
+static constexpr int kMaxCls = 16;
+
+__device__ __forceinline__ uint32_t float_desc_key(float f) {
+    uint32_t u = __float_as_uint(f);
+    u ^= (u >> 31) ? 0xFFFFFFFFu : 0x80000000u;  // ascending-sortable
+    return ~u;                                    // descending
+}
+__device__ __forceinline__ int float_to_ordered(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+
+struct DetWs {
+    float4* boxes;      // [N*A] decoded + clipped
+    float* scores;      // [N*A]
+    uint64_t* keys;     // [N*A]
+    uint64_t* keys_alt; // [N*A]
+    int* n_cand;        // [N]
+    int* max_coord;     // [N] ordered-int of the max coordinate over candidates
+    int* seg_start;     // [N*16]
+    int* seg_end;       // [N*16]
+    int* seg_kept;      // [N*16]
+    float4* kept_boxes; // [N*A] compacted per segment (NMS-space coordinates)
+    uint64_t* kept_keys;// [N*A] compacted per segment
+    void* cub_tmp;
+    size_t cub_bytes;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+
+static size_t det_cub_bytes(long long n) {
+    size_t bytes = 0;
+    cub::DoubleBuffer<uint64_t> db(nullptr, nullptr);
+    cub::DeviceRadixSort::SortKeys(nullptr, bytes, db, (int)n, 0, 64, (cudaStream_t)0);
+    return bytes;
+}
+
+static size_t det_layout(int N, int A, void* base, DetWs* ws) {
+    size_t off = 0;
+    long long NA = (long long)N * A;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += align_up(bytes);
+        return base ? reinterpret_cast<uint8_t*>(base) + o : nullptr;
+    };
+    DetWs w;
+    w.boxes = reinterpret_cast<float4*>(take(NA * 16));
+    w.scores = reinterpret_cast<float*>(take(NA * 4));
+    w.keys = reinterpret_cast<uint64_t*>(take(NA * 8));
+    w.keys_alt = reinterpret_cast<uint64_t*>(take(NA * 8));
+    w.n_cand = reinterpret_cast<int*>(take(N * 4));
+    w.max_coord = reinterpret_cast<int*>(take(N * 4));
+    w.seg_start = reinterpret_cast<int*>(take(N * kMaxCls * 4));
+    w.seg_end = reinterpret_cast<int*>(take(N * kMaxCls * 4));
+    w.seg_kept = reinterpret_cast<int*>(take(N * kMaxCls * 4));
+    w.kept_boxes = reinterpret_cast<float4*>(take(NA * 16));
+    w.kept_keys = reinterpret_cast<uint64_t*>(take(NA * 8));
+    w.cub_bytes = det_cub_bytes(NA);
+    w.cub_tmp = take(w.cub_bytes);
+    if (ws) *ws = w;
+    return off;
+}
+
+extern "C" int64_t hn_det_workspace_bytes(int32_t N, int32_t A) {
+    if (N <= 0 || A <= 0) return 256;
+    return (int64_t)det_layout(N, A, nullptr, nullptr);
+}
+
+int hn_det_num_launches(const hn_det_desc*) { return 5 + 10; }  // 5 own kernels + CUB onesweep passes
+
+// decode (BBoxTransform + ClipBoxes, detection_loss.py:7-52), score = max over classes, threshold
+__global__ void hn_det_decode_kernel(const float* __restrict__ anchors, const float* __restrict__ reg,
+                                     const float* __restrict__ cls, const float* __restrict__ pre_boxes, int N, int A,
+                                     int ncls, float wmax, float hmax, float thr, DetWs ws) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)N * A) return;
+    int n = (int)(idx / A), a = (int)(idx - (long long)n * A);
+    const float* c = cls + idx * ncls;
+    float best = c[0];
+    int bi = 0;
+    for (int k = 1; k < ncls; ++k) {
+        float v = c[k];
+        if (greater_or_nan(v, best)) { best = v; bi = k; }
+    }
+    float4 box;
+    if (pre_boxes) {
+        box = *reinterpret_cast<const float4*>(pre_boxes + idx * 4);
+    } else {
+        float4 an = *reinterpret_cast<const float4*>(anchors + (long long)a * 4);  // y1,x1,y2,x2
+        float4 rg = *reinterpret_cast<const float4*>(reg + idx * 4);               // dy,dx,dh,dw
+        float yca = __fdiv_rn(__fadd_rn(an.x, an.z), 2.0f);
+        float xca = __fdiv_rn(__fadd_rn(an.y, an.w), 2.0f);
+        float ha = __fsub_rn(an.z, an.x);
+        float wa = __fsub_rn(an.w, an.y);
+        // exp evaluated in double and rounded once: correctly rounded fp32 (oracle does the same)
+        float w = __fmul_rn((float)exp((double)rg.w), wa);
+        float h = __fmul_rn((float)exp((double)rg.z), ha);
+        float yc = __fadd_rn(__fmul_rn(rg.x, ha), yca);
+        float xc = __fadd_rn(__fmul_rn(rg.y, wa), xca);
+        float hh = __fdiv_rn(h, 2.0f), hw = __fdiv_rn(w, 2.0f);
+        box.x = fmaxf(__fsub_rn(xc, hw), 0.0f);  // xmin
+        box.y = fmaxf(__fsub_rn(yc, hh), 0.0f);  // ymin
+        box.z = fminf(__fadd_rn(xc, hw), wmax);  // xmax
+        box.w = fminf(__fadd_rn(yc, hh), hmax);  // ymax
+    }
+    ws.boxes[idx] = box;
+    ws.scores[idx] = best;
+    uint64_t key = ~0ull;
+    if (best > thr) {
+        key = ((uint64_t)n << kImgShift) | ((uint64_t)bi << kClsShift) | ((uint64_t)float_desc_key(best) << kScoreShift) |
+              (uint64_t)a;
+        atomicAdd(ws.n_cand + n, 1);
+        float m = fmaxf(fmaxf(box.x, box.y), fmaxf(box.z, box.w));
+        atomicMax(ws.max_coord + n, float_to_ordered(m));
+    }
+    ws.keys[idx] = key;
+}
+
+__global__ void hn_det_segments_kernel(const uint64_t* __restrict__ keys, long long total, int* seg_start, int* seg_end) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    uint64_t k = keys[i];
+    if (k == ~0ull) return;
+    int seg = (int)(k >> kClsShift);  // img*16 + cls
+    if (i == 0 || (int)(keys[i - 1] >> kClsShift) != seg) seg_start[seg] = (int)i;
+    if (i + 1 == total || keys[i + 1] == ~0ull || (int)(keys[i + 1] >> kClsShift) != seg) seg_end[seg] = (int)(i + 1);
+}
+
+__device__ __forceinline__ bool iou_gt(const float4& a, float area_a, const float4& b, float area_b, float thr) {
+    // torchvision nms: inter / (area_i + area_j - inter) > thr, all fp32
+    float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+    float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+    float inter = __fmul_rn(w, h);
+    float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+    return ovr > thr;
+}
+__device__ __forceinline__ float box_area(const float4& b) { return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y)); }
+
+static constexpr int kNmsChunk = 512;
+
+// One CTA per (image, class) segment of the sorted candidates: greedy NMS in sorted order, processed
+// in chunks of 512: (1) every candidate of the chunk is tested against all boxes kept so far,
+// (2) survivors are resolved against each other with a 512x512 bit matrix walked by one warp.
+__global__ void __launch_bounds__(kNmsChunk) hn_det_nms_kernel(DetWs ws, int A, float iou_thr, int nms_mode) {
+    __shared__ float4 s_box[kNmsChunk];
+    __shared__ float s_area[kNmsChunk];
+    __shared__ unsigned long long s_mask[kNmsChunk][kNmsChunk / 64];
+    __shared__ unsigned long long s_alive[kNmsChunk / 64];
+    __shared__ int s_nk;
+    const int seg = blockIdx.x;
+    const int n = seg / kMaxCls, cls = seg % kMaxCls;
+    const int s0 = ws.seg_start[seg], s1 = ws.seg_end[seg];
+    const int tid = threadIdx.x;
+    if (tid == 0) s_nk = 0;
+    if (s1 <= s0) {
+        if (tid == 0) ws.seg_kept[seg] = 0;
+        return;
+    }
+    // coordinate trick (torchvision boxes.py _batched_nms_coordinate_trick): offset = cls * (max + 1)
+    const int ncand = ws.n_cand[n];
+    bool trick = nms_mode == HN_NMS_TRICK ||
+                 (nms_mode == HN_NMS_AUTO_CUDA && (long long)ncand * 4 <= 100000) ||
+                 (nms_mode == HN_NMS_AUTO_CPU && (long long)ncand * 4 <= 4000);
+    float offset = 0.0f;
+    if (trick) offset = __fmul_rn((float)cls, __fadd_rn(ordered_to_float(ws.max_coord[n]), 1.0f));
+    float4* kept_boxes = ws.kept_boxes + s0;
+    uint64_t* kept_keys = ws.kept_keys + s0;
+    __syncthreads();
+
+    for (int c0 = s0; c0 < s1; c0 += kNmsChunk) {
+        const int j = c0 + tid;
+        const bool have = j < s1;
+        float4 b = make_float4(0, 0, 0, 0);
+        uint64_t key = 0;
+        if (have) {
+            key = ws.keys[j];
+            int a = (int)(key & ((1u << kAnchorBits) - 1));
+            b = ws.boxes[(long long)n * A + a];
+            if (trick) {
+                b.x = __fadd_rn(b.x, offset); b.y = __fadd_rn(b.y, offset);
+                b.z = __fadd_rn(b.z, offset); b.w = __fadd_rn(b.w, offset);
+            }
+        }
+        const float area = box_area(b);
+        // (1) against everything kept so far
+        const int nk = s_nk;
+        bool alive = have;
+        for (int k = 0; k < nk; ++k) {
+            float4 kb = kept_boxes[k];
+            if (alive && iou_gt(kb, box_area(kb), b, area, iou_thr)) alive = false;
+            if ((k & 31) == 31 && !__any_sync(0xffffffffu, alive)) break;
+        }
+        s_box[tid] = b;
+        s_area[tid] = area;
+        if (tid < kNmsChunk / 64) s_alive[tid] = 0ull;
+        __syncthreads();
+        if (alive) atomicOr(&s_alive[tid >> 6], 1ull << (tid & 63));
+        // (2) intra-chunk suppression rows (only rows of live boxes are ever read)
+        if (alive) {
+            for (int w = 0; w < kNmsChunk / 64; ++w) {
+                unsigned long long bits = 0ull;
+                if (w >= (tid >> 6)) {
+                    for (int t = 0; t < 64; ++t) {
+                        int o = w * 64 + t;
+                        if (o > tid && iou_gt(b, area, s_box[o], s_area[o], iou_thr)) bits |= 1ull << t;
+                    }
+                }
+                s_mask[tid][w] = bits;
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {
+            // lane w (< 8) owns word w of the live set; walk the live boxes in order
+            const int lane = tid;
+            unsigned long long live = lane < kNmsChunk / 64 ? s_alive[lane] : 0ull;
+            int nkept = s_nk;
+            while (true) {
+                unsigned nz = __ballot_sync(0xffffffffu, live != 0ull);
+                if (nz == 0) break;
+                int w = __ffs(nz) - 1;
+                unsigned long long lw = __shfl_sync(0xffffffffu, live, w);
+                int i = w * 64 + __ffsll((long long)lw) - 1;
+                // keep box i, drop what it suppresses
+                if (lane < kNmsChunk / 64) {
+                    live &= ~s_mask[i][lane];
+                    if (lane == w) live &= ~(1ull << (i & 63));
+                }
+                if (lane == 0) {
+                    kept_boxes[nkept] = s_box[i];
+                    kept_keys[nkept] = ws.keys[c0 + i];
+                }
+                ++nkept;
+            }
+            if (lane == 0) s_nk = nkept;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) ws.seg_kept[seg] = s_nk;
+}
+
+// final order = score descending, ties by ascending candidate index, across classes: the rank of a
+// kept box is the number of kept boxes (all classes) whose (~score, anchor) key is smaller
+__global__ void hn_det_gather_kernel(DetWs ws, int A, float* __restrict__ out_boxes, float* __restrict__ out_scores,
+                                     int64_t* __restrict__ out_class, int* __restrict__ out_count) {
+    const int seg = blockIdx.x;
+    const int n = seg / kMaxCls, cls = seg % kMaxCls;
+    const int nk = ws.seg_kept[seg];
+    const uint64_t low_mask = (1ull << kClsShift) - 1;
+    if (cls == 0 && threadIdx.x == 0) {
+        int tot = 0;
+        for (int c = 0; c < kMaxCls; ++c) tot += ws.seg_kept[n * kMaxCls + c];
+        out_count[n] = tot;
+    }
+    const uint64_t* mine = ws.kept_keys + ws.seg_start[seg];
+    for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+        uint64_t key = mine[i] & low_mask;
+        int rank = i;
+        for (int c = 0; c < kMaxCls; ++c) {
+            if (c == cls) continue;
+            int oseg = n * kMaxCls + c;
+            int cnt = ws.seg_kept[oseg];
+            if (cnt == 0) continue;
+            const uint64_t* other = ws.kept_keys + ws.seg_start[oseg];
+            int lo = 0, hi = cnt;  // first element with key >= mine
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if ((other[mid] & low_mask) < key) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        int a = (int)(key & ((1u << kAnchorBits) - 1));
+        long long src = (long long)n * A + a, dst = (long long)n * A + rank;
+        *reinterpret_cast<float4*>(out_boxes + dst * 4) = ws.boxes[src];
+        out_scores[dst] = ws.scores[src];
+        out_class[dst] = cls;
+    }
+}
+
+__global__ void hn_det_init_kernel(DetWs ws, int N) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) {
+        ws.n_cand[i] = 0;
+        ws.max_coord[i] = float_to_ordered(-INFINITY);
+    }
+    if (i < N * kMaxCls) {
+        ws.seg_start[i] = 0;
+        ws.seg_end[i] = 0;
+        ws.seg_kept[i] = 0;
+    }
+}
+
+__global__ void hn_copy_i32_kernel(const int* in, int* out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+
+extern "C" int hn_det_decode_nms(const hn_det_desc* d, void* stream) {
+    HN_REQUIRE(d != nullptr, "det: null desc");
+    HN_REQUIRE(d->N >= 0 && d->N <= 255 && d->A >= 0 && d->A < (1 << kAnchorBits) && d->ncls >= 1 && d->ncls <= kMaxCls,
+               "det: N<=255, A<2^20, ncls<=16 required (N=%d A=%d ncls=%d)", d->N, d->A, d->ncls);
+    HN_REQUIRE(d->classification && d->out_boxes && d->out_scores && d->out_class && d->out_count, "det: null pointer");
+    HN_REQUIRE(d->pre_boxes || (d->anchors && d->regression), "det: need anchors+regression or pre_boxes");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (d->N == 0) return HN_OK;
+    if (d->A == 0) {
+        HN_CHECK_CUDA(cudaMemsetAsync(d->out_count, 0, sizeof(int) * d->N, s));
+        if (d->out_cand) HN_CHECK_CUDA(cudaMemsetAsync(d->out_cand, 0, sizeof(int) * d->N, s));
+        return HN_OK;
+    }
+    HN_REQUIRE(d->workspace && d->workspace_bytes >= hn_det_workspace_bytes(d->N, d->A), "det: workspace too small");
+    DetWs ws;
+    det_layout(d->N, d->A, d->workspace, &ws);
+    const long long NA = (long long)d->N * d->A;
+    hn_det_init_kernel<<<hn_cdiv(d->N * kMaxCls, 256), 256, 0, s>>>(ws, d->N);
+    HN_CHECK_CUDA(cudaGetLastError());
+    hn_det_decode_kernel<<<hn_cdiv(NA, 256), 256, 0, s>>>(d->anchors, d->regression, d->classification, d->pre_boxes, d->N,
+                                                         d->A, d->ncls, (float)(d->img_w - 1), (float)(d->img_h - 1),
+                                                         d->conf_thres, ws);
+    HN_CHECK_CUDA(cudaGetLastError());
+    cub::DoubleBuffer<uint64_t> db(ws.keys, ws.keys_alt);
+    size_t tmp = ws.cub_bytes;
+    HN_CHECK_CUDA(cub::DeviceRadixSort::SortKeys(ws.cub_tmp, tmp, db, (int)NA, 0, 64, s));
+    ws.keys = db.Current();
+    ws.keys_alt = db.Alternate();
+    hn_det_segments_kernel<<<hn_cdiv(NA, 256), 256, 0, s>>>(ws.keys, NA, ws.seg_start, ws.seg_end);
+    HN_CHECK_CUDA(cudaGetLastError());
+    hn_det_nms_kernel<<<d->N * kMaxCls, kNmsChunk, 0, s>>>(ws, d->A, d->iou_thres, d->nms_mode);
+    HN_CHECK_CUDA(cudaGetLastError());
+    hn_det_gather_kernel<<<d->N * kMaxCls, 256, 0, s>>>(ws, d->A, d->out_boxes, d->out_scores, d->out_class, d->out_count);
+    HN_CHECK_CUDA(cudaGetLastError());
+    if (d->out_cand) {
+        hn_copy_i32_kernel<<<hn_cdiv(d->N, 256), 256, 0, s>>>(ws.n_cand, d->out_cand, d->N);
+        HN_CHECK_CUDA(cudaGetLastError());
+    }
+    return HN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lane decode + NMS: one CTA per image
+// ------------------------------------------------------------------------------------------------
+struct LaneParams {
+    const float* cls;
+    const float* loc;
+    int N, fh, fw, ppl, cls_is_prob, use_mean;
+    float conf_thres, nms_thres;
+    double step_w, interval, ppa;
+    float x_lim_up, x_lim_down;
+    float* ws_x;    // [N][na][ppl] x by absolute position
+    int* ws_i;      // [N][na][4]: anchor, start, end, order
+    float* ws_prob; // [N][na]
+    int* out_count;
+    int* out_meta;
+    float* out_prob;
+    float* out_x;
+    int* out_cand;
+};
+
+extern "C" int64_t hn_lane_workspace_bytes(int32_t N, int32_t n_anchor, int32_t ppl) {
+    if (N <= 0 || n_anchor <= 0 || ppl <= 0) return 256;
+    return (int64_t)(align_up((size_t)N * n_anchor * ppl * 4) + align_up((size_t)N * n_anchor * 16) +
+                     align_up((size_t)N * n_anchor * 4) + align_up((size_t)N * n_anchor * 4));
+}
+
+__device__ __forceinline__ float lane_dist(const float* x1, int s1, int e1, const float* x2, int s2, int e2, int use_mean,
+                                           bool* no_overlap) {
+    // calc_err_dis_with_pos (lane_codec_utils.py:487-515): x arrays are indexed by absolute position
+    int ms = max(s1, s2), me = min(e1, e2);
+    *no_overlap = (me <= ms) || (ms < 0) || (me < 1);
+    if (*no_overlap) return 0.0f;
+    float dis = 0.0f;
+    for (int i = ms; i < me; ++i) dis = __fadd_rn(dis, fabsf(__fsub_rn(x1[i], x2[i])));
+    dis = __fdiv_rn(dis, (float)(me - ms));
+    if (use_mean) return dis;
+    float ds = fabsf(__fsub_rn(x1[ms], x2[ms]));
+    dis = fmaxf(dis, ds);
+    float de = fabsf(__fsub_rn(x1[me - 1], x2[me - 1]));
+    dis = fmaxf(dis, de);
+    return dis;
+}
+
+__global__ void __launch_bounds__(256) hn_lane_kernel(const __grid_constant__ LaneParams p) {
+    extern __shared__ int s_dyn[];
+    const int na = p.fh * p.fw;
+    int* s_order = s_dyn;            // [na] sorted position -> candidate slot
+    int* s_supp = s_dyn + na;        // [na] suppressed flag per sorted position
+    __shared__ int s_ncand, s_nkeep;
+    const int n = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+    const int L = 2 * p.ppl + 2;
+    float* wx = p.ws_x + (long long)n * na * p.ppl;
+    int* wi = p.ws_i + (long long)n * na * 4;
+    float* wp = p.ws_prob + (long long)n * na;
+    if (tid == 0) { s_ncand = 0; s_nkeep = 0; }
+    __syncthreads();
+
+    // ---- decode: one warp per anchor (lane_codec.py:139-217) ----
+    for (int a = warp; a < na; a += nwarp) {
+        const float* c = p.cls + ((long long)n * na + a) * 2;
+        float prob;
+        if (p.cls_is_prob) {
+            prob = c[1];
+        } else {
+            float m = fmaxf(c[0], c[1]);
+            float e0 = expf(c[0] - m), e1 = expf(c[1] - m);
+            prob = e1 / (e0 + e1);
+        }
+        if (prob < p.conf_thres) continue;
+        const int h = a / p.fw, w = a - h * p.fw;
+        const int y_pos = (int)((double)(p.fh - 1 - h) * p.ppa);
+        const float cx = (float)(((double)w + 0.5) * p.step_w);
+        const float itv = (float)p.interval;
+        const float* loc = p.loc + ((long long)n * na + a) * L;
+        const float end_up = loc[p.ppl + 1], end_down = loc[p.ppl];
+        // up branch: first failing index
+        int n_up = p.ppl;
+        for (int base = 0; base < p.ppl; base += 32) {
+            int i = base + lane;
+            bool fail = true;
+            float x = 0.0f;
+            if (i < p.ppl) {
+                x = __fadd_rn(cx, __fmul_rn(loc[p.ppl + 2 + i], itv));
+                fail = ((float)i >= end_up) || (y_pos + i >= p.ppl) || (x < 0.0f) || (x >= p.x_lim_up);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, fail);
+            if (m) { n_up = base + __ffs(m) - 1; break; }
+        }
+        int n_down = y_pos;
+        for (int base = 0; base < y_pos; base += 32) {
+            int i = base + lane;
+            bool fail = true;
+            if (i < y_pos) {
+                float x = __fadd_rn(cx, __fmul_rn(loc[i], itv));
+                fail = ((float)i >= end_down) || (y_pos - 1 - i < 0) || (x < 0.0f) || (x >= p.x_lim_down);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, fail);
+            if (m) { n_down = base + __ffs(m) - 1; break; }
+        }
+        if (n_up + n_down < 2) continue;
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(&s_ncand, 1);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        const int start = y_pos - n_down, end = y_pos + n_up;
+        float* xs = wx + (long long)slot * p.ppl;
+        for (int pos = start + lane; pos < end; pos += 32) {
+            float x = pos < y_pos ? __fadd_rn(cx, __fmul_rn(loc[y_pos - 1 - pos], itv))
+                                  : __fadd_rn(cx, __fmul_rn(loc[p.ppl + 2 + pos - y_pos], itv));
+            xs[pos] = x;
+        }
+        if (lane == 0) {
+            wi[slot * 4 + 0] = a;
+            wi[slot * 4 + 1] = start;
+            wi[slot * 4 + 2] = end;
+            wp[slot] = prob;
+        }
+    }
+    __syncthreads();
+    const int nc = s_ncand;
+    // ---- stable sort by prob descending (sorted(lane_set) with Lane.__lt__, lane_codec_utils.py:62-64):
+    //      rank = number of candidates that come first; ties keep (h, w) scan order = anchor order
+    for (int i = tid; i < nc; i += blockDim.x) {
+        float pi = wp[i];
+        int ai = wi[i * 4];
+        int rank = 0;
+        for (int j = 0; j < nc; ++j) {
+            float pj = wp[j];
+            rank += (pj > pi) || (pj == pi && wi[j * 4] < ai);
+        }
+        s_order[rank] = i;
+        s_supp[rank] = 0;
+    }
+    __syncthreads();
+    // ---- greedy NMS (nms_with_pos, lane_codec_utils.py:518-542) ----
+    const bool far_suppresses = 10e6 <= (double)p.nms_thres;
+    for (int i = 0; i < nc; ++i) {
+        if (s_supp[i]) continue;  // uniform: s_supp only changes between barriers
+        const int si = s_order[i];
+        if (tid == 0) {
+            int k = s_nkeep++;
+            int* om = p.out_meta + ((long long)n * na + k) * 4;
+            om[0] = wi[si * 4]; om[1] = wi[si * 4 + 1]; om[2] = wi[si * 4 + 2]; om[3] = wi[si * 4 + 2] - wi[si * 4 + 1];
+            p.out_prob[(long long)n * na + k] = wp[si];
+        }
+        const float* xi = wx + (long long)si * p.ppl;
+        const int st_i = wi[si * 4 + 1], en_i = wi[si * 4 + 2];
+        for (int t = i + 1 + tid; t < nc; t += blockDim.x) {
+            if (s_supp[t]) continue;
+            const int stt = s_order[t];
+            bool no_ov;
+            float dis = lane_dist(xi, st_i, en_i, wx + (long long)stt * p.ppl, wi[stt * 4 + 1], wi[stt * 4 + 2], p.use_mean,
+                                  &no_ov);
+            bool sup = no_ov ? far_suppresses : (dis <= p.nms_thres);
+            if (sup) s_supp[t] = 1;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    // ---- emit x of kept lanes in list order (bottom -> top) ----
+    const int nk = s_nkeep;
+    for (int k = warp; k < nk; k += nwarp) {
+        const int* om = p.out_meta + ((long long)n * na + k) * 4;
+        // find the slot again through the anchor id
+        int a = om[0], start = om[1], cnt = om[3];
+        int slot = -1;
+        for (int j = lane; j < nc; j += 32)
+            if (wi[j * 4] == a) slot = j;
+        for (int o = 16; o > 0; o >>= 1) slot = max(slot, __shfl_xor_sync(0xffffffffu, slot, o));
+        const float* xs = wx + (long long)slot * p.ppl;
+        float* ox = p.out_x + ((long long)n * na + k) * p.ppl;
+        for (int q = lane; q < cnt; q += 32) ox[q] = xs[start + q];
+    }
+    if (tid == 0) {
+        p.out_count[n] = nk;
+        if (p.out_cand) p.out_cand[n] = nc;
+    }
+}
+
+extern "C" int hn_lane_decode_nms(const hn_lane_desc* d, void* stream) {
+    HN_REQUIRE(d != nullptr, "lane: null desc");
+    HN_REQUIRE(d->N >= 0 && d->fh >= 1 && d->fw >= 1 && d->ppl >= 1, "lane: bad sizes");
+    if (d->N == 0) return HN_OK;
+    HN_REQUIRE(d->cls && d->loc && d->workspace && d->out_count && d->out_meta && d->out_prob && d->out_x, "lane: null pointer");
+    const int na = d->fh * d->fw;
+    HN_REQUIRE(na <= 8192, "lane: at most 8192 anchors per image");
+    LaneParams p;
+    p.cls = d->cls; p.loc = d->loc;
+    p.N = d->N; p.fh = d->fh; p.fw = d->fw; p.ppl = d->ppl; p.cls_is_prob = d->cls_is_prob; p.use_mean = d->use_mean;
+    p.conf_thres = d->conf_thres; p.nms_thres = d->nms_thres;
+    p.step_w = d->step_w; p.interval = d->interval; p.ppa = d->points_per_anchor;
+    p.x_lim_up = d->input_width;
+    p.x_lim_down = (float)((double)d->input_width + (double)d->margin_width);
+    uint8_t* w = reinterpret_cast<uint8_t*>(d->workspace);
+    p.ws_x = reinterpret_cast<float*>(w);
+    w += align_up((size_t)d->N * na * d->ppl * 4);
+    p.ws_i = reinterpret_cast<int*>(w);
+    w += align_up((size_t)d->N * na * 16);
+    p.ws_prob = reinterpret_cast<float*>(w);
+    p.out_count = d->out_count; p.out_meta = d->out_meta; p.out_prob = d->out_prob; p.out_x = d->out_x; p.out_cand = d->out_cand;
+    size_t smem = (size_t)na * 2 * sizeof(int);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        HN_CHECK_CUDA(cudaFuncSetAttribute(hn_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    hn_lane_kernel<<<d->N, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}

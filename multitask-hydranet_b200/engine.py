@@ -1,0 +1,745 @@
+"""Schedule builder for the native HydraNet forward.
+
+Turns a ``HydraNet`` parameter tree into (a) packed weights -- BatchNorm folded, K-major bf16
+matrices whose K columns follow a per-layer *tap table* -- and (b) a flat list of operator specs
+(``ConvSpec`` / ``NodeSpec`` / ...) over NHWC bf16 buffers, which ``Plan.compile`` hands to the C
+ABI (``hn_plan_add_*``) once; a forward is then a single ``hn_plan_run``.
+
+Graph being scheduled (reference file:line, /root/reference/model):
+  backbone  net/anynet.py:136-145 (Stem 8-20, XBlock 64-76)
+  neck      net/bifpn.py:156-233, net/common.py:76-151
+  seg head  head_seg/segmentation.py:84-105
+  detect    head_detect/detection.py:28-83, 211-215
+  lane      head_lane/lanedetect.py:66-96
+
+Design notes:
+  * a 3x3 conv over ``cat(up2(X), S)`` never materialises the up-sampled tensor: per output parity
+    (py, px) the up-sampled part collapses to a 2x2 conv over X with pre-summed weights, the skip part
+    reads S through stride-2 phase views; reflect-pad of up2(X) == replicate-pad of X.
+  * grouped 3x3 convs (8 channels / group) run on the tensor cores as block-diagonal 64x64 tiles.
+  * zero padding comes for free from TMA out-of-bounds fill; reflect / replicate halos are written by
+    the producing conv's epilogue into 1-pixel padded buffers.
+"""
+import math
+
+import torch
+
+from . import _native as nv
+
+
+# ------------------------------------------------------------------------------------------------
+# views and buffers
+# ------------------------------------------------------------------------------------------------
+class V:
+    """4-D NHWC view (element strides) into a tensor's storage."""
+
+    def __init__(self, t, off, N, H, W, C, sn, sy, sx):
+        self.t, self.off, self.N, self.H, self.W, self.C, self.sn, self.sy, self.sx = t, off, N, H, W, C, sn, sy, sx
+
+    def to_c(self):
+        return nv.View(self.t.data_ptr() + self.t.element_size() * self.off, self.N, self.H, self.W, self.C,
+                       self.sn, self.sy, self.sx)
+
+    def chan(self, c0, c):
+        return V(self.t, self.off + c0, self.N, self.H, self.W, c, self.sn, self.sy, self.sx)
+
+    def phase(self, ry, rx):
+        """rows ry, ry+2, ... and columns rx, rx+2, ... of this view."""
+        return V(self.t, self.off + ry * self.sy + rx * self.sx, self.N, (self.H - ry + 1) // 2, (self.W - rx + 1) // 2,
+                 self.C, self.sn, 2 * self.sy, 2 * self.sx)
+
+    def flat(self):
+        """[1,1,N*H*W,C] row view; only for views whose pixels are equally spaced."""
+        assert self.sy == self.W * self.sx and self.sn == self.H * self.sy, "view is not flattenable"
+        return V(self.t, self.off, 1, 1, self.N * self.H * self.W, self.C, 0, 0, self.sx)
+
+    def is_flattenable(self):
+        return self.sy == self.W * self.sx and self.sn == self.H * self.sy
+
+    def torch_view(self):
+        return self.t.view(-1).as_strided((self.N, self.H, self.W, self.C), (self.sn, self.sy, self.sx, 1), self.off)
+
+
+class Buf:
+    """NHWC activation buffer with an optional 1-pixel halo (zero-initialised once)."""
+
+    def __init__(self, device, dtype, N, H, W, C, pad=0, halo=nv.HALO_NONE):
+        self.N, self.H, self.W, self.C, self.pad, self.halo = N, H, W, C, pad, halo
+        self.Hp, self.Wp = H + 2 * pad, W + 2 * pad
+        self.t = torch.zeros((N, self.Hp, self.Wp, C), device=device, dtype=dtype)
+
+    def _strides(self):
+        return self.Hp * self.Wp * self.C, self.Wp * self.C, self.C
+
+    def interior(self):
+        sn, sy, sx = self._strides()
+        return V(self.t, self.pad * sy + self.pad * sx, self.N, self.H, self.W, self.C, sn, sy, sx)
+
+    def padded(self):
+        sn, sy, sx = self._strides()
+        return V(self.t, 0, self.N, self.Hp, self.Wp, self.C, sn, sy, sx)
+
+
+# ------------------------------------------------------------------------------------------------
+# operator specs
+# ------------------------------------------------------------------------------------------------
+class ConvSpec:
+    kind = "conv"
+
+    def __init__(self, name):
+        self.name = name
+        self.src = []          # list[V]
+        self.taps = []         # list[(src, dy, dx, c0)]
+        self.weight = None     # [rows, ntaps*64]
+        self.bias = None       # fp32 [rows]
+        self.flat = 0
+        self.tile = (8, 16)
+        self.n_img = self.out_h = self.out_w = 0
+        self.flat_hw = 0
+        self.cout = 0
+        self.bn = 64
+        self.stages = 4
+        self.act = nv.ACT_NONE
+        self.epi = nv.EPI_STD
+        self.out_t = None
+        self.out_off = 0
+        self.out_fp32 = 0
+        self.out_strides = (0, 0, 0)
+        self.out_scale, self.out_oy, self.out_ox = 1, 0, 0
+        self.halo = nv.HALO_NONE
+        self.res = None        # V
+        self.res_relu = 0
+        self.grouped = 0
+        self.out2 = None
+        self.n_cls = 0
+        self.macs = 0          # algorithmic multiply-accumulates of the reference layer(s) this op computes
+        self.group = ""        # subsystem tag for per-op timing
+
+    def to_desc(self):
+        d = nv.ConvDesc()
+        assert len(self.src) <= nv.HN_MAX_SRC and len(self.taps) <= nv.HN_MAX_TAPS, self.name
+        for i, v in enumerate(self.src):
+            d.src[i] = v.to_c()
+        d.n_src = len(self.src)
+        d.weight = self.weight.data_ptr()
+        d.w_rows = self.weight.shape[0]
+        d.num_taps = len(self.taps)
+        assert self.weight.shape[1] == 64 * len(self.taps), self.name
+        for i, (s, dy, dx, c0) in enumerate(self.taps):
+            d.taps[i] = nv.Tap(s, dy, dx, 0, c0, 0)
+        d.flat = self.flat
+        d.tile_h, d.tile_w = self.tile
+        d.n_img, d.out_h, d.out_w, d.flat_hw = self.n_img, self.out_h, self.out_w, self.flat_hw
+        d.cout, d.bn, d.stages = self.cout, self.bn, self.stages
+        d.bias = self.bias.data_ptr() if self.bias is not None else None
+        d.act, d.epi = self.act, self.epi
+        d.out = self.out_t.data_ptr() + self.out_t.element_size() * self.out_off
+        d.out_fp32 = self.out_fp32
+        d.out_stride_n, d.out_stride_y, d.out_stride_x = self.out_strides
+        d.out_scale, d.out_oy, d.out_ox, d.halo = self.out_scale, self.out_oy, self.out_ox, self.halo
+        if self.res is not None:
+            d.res = self.res.t.data_ptr() + self.res.t.element_size() * self.res.off
+            d.res_stride_n, d.res_stride_y, d.res_stride_x = self.res.sn, self.res.sy, self.res.sx
+        d.res_relu, d.grouped = self.res_relu, self.grouped
+        d.out2 = self.out2.data_ptr() if self.out2 is not None else None
+        d.n_cls = self.n_cls
+        return d
+
+    def add_to(self, plan):
+        nv.check(nv.lib.hn_plan_add_conv(plan, self.to_desc()))
+
+    launches = 1
+
+
+class StemSpec:
+    kind, launches, group = "stem", 1, "backbone"
+
+    def __init__(self, x, w, b, out):
+        self.x, self.w, self.b, self.out, self.name = x, w, b, out, "stem"
+        self.macs = out.N * out.H * out.W * 32 * 27
+
+    def to_desc(self):
+        N, _, H, W = self.x.shape
+        return nv.StemDesc(self.x.data_ptr(), N, H, W, self.w.data_ptr(), self.b.data_ptr(), self.out.to_c())
+
+    def add_to(self, plan):
+        nv.check(nv.lib.hn_plan_add_stem(plan, self.to_desc()))
+
+
+class NodeSpec:
+    kind, launches = "node", 1
+
+    def __init__(self, name, ins, modes, ws, swish, dw, out, group):
+        self.name, self.ins, self.modes, self.ws, self.swish, self.dw, self.out, self.group = \
+            name, ins, modes, ws, swish, dw, out, group
+        self.macs = out.N * out.H * out.W * out.C * 9
+
+    def to_desc(self):
+        d = nv.NodeDesc()
+        d.n_in = len(self.ins)
+        for i, v in enumerate(self.ins):
+            d.in_[i] = v.to_c()
+            d.mode[i] = self.modes[i]
+            d.w[i] = self.ws[i]
+        d.swish = self.swish
+        d.dw = self.dw.data_ptr()
+        d.out = self.out.to_c()
+        return d
+
+    def add_to(self, plan):
+        nv.check(nv.lib.hn_plan_add_node(plan, self.to_desc()))
+
+
+class PoolSpec:
+    kind, launches, macs = "pool", 1, 0
+
+    def __init__(self, name, vin, vout, mode, group):
+        self.name, self.vin, self.vout, self.mode, self.group = name, vin, vout, mode, group
+
+    def to_desc(self):
+        return nv.PoolDesc(self.vin.to_c(), self.vout.to_c(), self.mode)
+
+    def add_to(self, plan):
+        nv.check(nv.lib.hn_plan_add_pool(plan, self.to_desc()))
+
+
+class LaneFuseSpec:
+    kind, launches, macs, group = "lanefuse", 1, 0, "lane"
+
+    def __init__(self, p3, p4, p5, p6, out, stride):
+        self.p3, self.p4, self.p5, self.p6, self.out, self.stride, self.name = p3, p4, p5, p6, out, stride, "lane.fuse"
+
+    def to_desc(self):
+        return nv.LaneFuseDesc(self.p3.to_c(), self.p4.to_c(), self.p5.to_c(), self.p6.to_c(), self.out.to_c(), self.stride)
+
+    def add_to(self, plan):
+        nv.check(nv.lib.hn_plan_add_lanefuse(plan, self.to_desc()))
+
+
+class SeSpec:
+    kind, launches, group = "se", 3, "backbone"
+
+    def __init__(self, name, x, pooled, scale, w1, b1, w2, b2):
+        self.name, self.x, self.pooled, self.scale, self.w1, self.b1, self.w2, self.b2 = name, x, pooled, scale, w1, b1, w2, b2
+        self.macs = x.N * 2 * w1.shape[0] * w1.shape[1]
+
+    def to_desc(self):
+        return nv.SeDesc(self.x.to_c(), self.pooled.data_ptr(), self.scale.data_ptr(), self.w1.data_ptr(), self.b1.data_ptr(),
+                         self.w2.data_ptr(), self.b2.data_ptr(), self.w1.shape[0])
+
+    def add_to(self, plan):
+        nv.check(nv.lib.hn_plan_add_se(plan, self.to_desc()))
+
+
+# ------------------------------------------------------------------------------------------------
+# weight folding / packing helpers
+# ------------------------------------------------------------------------------------------------
+def fold_bn(weight, bias, bn):
+    """conv(+bias) followed by eval-mode BatchNorm -> equivalent (weight, bias), fp32."""
+    w = weight.detach().float()
+    b = bias.detach().float() if bias is not None else torch.zeros(w.shape[0], device=w.device)
+    if bn is not None:
+        scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+        w = w * scale.view(-1, 1, 1, 1)
+        b = (b - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+    return w, b
+
+
+def choose_bn(cout):
+    """N tile: a multiple of 16, at most 256, splitting wide layers evenly."""
+    if cout <= 256:
+        return max(16, (cout + 15) // 16 * 16)
+    n_tiles = (cout + 255) // 256
+    per = (cout + n_tiles - 1) // n_tiles
+    return (per + 15) // 16 * 16
+
+
+def choose_stages(bn, ntaps):
+    stage = 16384 + bn * 128
+    budget = 200 * 1024 if bn > 128 else 100 * 1024  # <=128: leave room for two CTAs per SM
+    return int(max(2, min(8, ntaps, budget // stage)))
+
+
+def choose_tile(H, W):
+    best = None
+    for th, tw in ((8, 16), (16, 8), (4, 32), (32, 4), (2, 64), (1, 128), (64, 2)):
+        n = math.ceil(H / th) * math.ceil(W / tw)
+        if best is None or n < best[0]:
+            best = (n, (th, tw))
+    return best[1]
+
+
+def pack_weight(entries, cout, bn, wdtype, device):
+    """entries: [(src, dy, dx, W[cout, Csrc])] -> (taps, K-major matrix [rows_pad, ntaps*64])."""
+    taps, cols = [], []
+    for (s, dy, dx, wt) in entries:
+        cs = wt.shape[1]
+        for c0 in range(0, cs, 64):
+            w = min(64, cs - c0)
+            blk = torch.zeros((cout, 64), dtype=torch.float32, device=device)
+            blk[:, :w] = wt[:, c0:c0 + w]
+            taps.append((s, dy, dx, c0))
+            cols.append(blk)
+    wm = torch.cat(cols, 1)
+    rows = (cout + bn - 1) // bn * bn
+    out = torch.zeros((rows, wm.shape[1]), dtype=torch.float32, device=device)
+    out[:cout] = wm
+    return taps, out.to(wdtype).contiguous()
+
+
+def pad_bias(b, cout, bn):
+    rows = (cout + bn - 1) // bn * bn
+    out = torch.zeros(rows, dtype=torch.float32, device=b.device)
+    out[:cout] = b
+    return out
+
+
+# row/column tap sets of the parity-collapsed up-sampled 3x3 conv: parity -> [(source shift, [k...])]
+UP_SETS = {0: [(-1, [0]), (0, [1, 2])], 1: [(0, [0, 1]), (1, [2])]}
+
+
+class Builder:
+    """Emits the op list for one (batch, height, width)."""
+
+    def __init__(self, model, B, H, W, device, act_dtype=torch.bfloat16):
+        self.m, self.B, self.H, self.W, self.dev, self.dt = model, B, H, W, device, act_dtype
+        self.ops = []
+        self.keep = []  # tensors that must stay alive
+        self.out = {}
+
+    # -- small helpers --
+    def buf(self, H, W, C, pad=0, halo=nv.HALO_NONE):
+        return Buf(self.dev, self.dt, self.B, H, W, C, pad, halo)
+
+    def f32(self, t):
+        t = t.detach().float().contiguous().to(self.dev)
+        self.keep.append(t)
+        return t
+
+    def _finish(self, cs, entries, cout, bias, bn=None):
+        cs.cout = cout
+        cs.bn = bn or choose_bn(cout)
+        cs.taps, cs.weight = pack_weight(entries, cout, cs.bn, self.dt, self.dev)
+        cs.bias = pad_bias(bias.to(self.dev), cout, cs.bn)
+        cs.stages = choose_stages(cs.bn, len(cs.taps))
+        self.ops.append(cs)
+        return cs
+
+    def _set_out_buf(self, cs, ob, vin_like=None):
+        """Route the output into buffer ``ob`` (interior), choosing flat or spatial tiling."""
+        vi = ob.interior()
+        cs.out_t, cs.out_off = ob.t, vi.off
+        cs.out_strides = (vi.sn, vi.sy, vi.sx)
+        cs.halo = ob.halo if ob.pad else nv.HALO_NONE
+        cs.n_img, cs.out_h, cs.out_w = ob.N, ob.H, ob.W
+
+    def conv1x1(self, name, vin, w, b, ob, act, group, res=None, res_relu=0, out_chan=None):
+        """1x1 conv of view ``vin`` into buffer ``ob`` (optionally a channel slice)."""
+        cs = ConvSpec(name)
+        cs.group, cs.act, cs.res, cs.res_relu = group, act, res, res_relu
+        cout = w.shape[0]
+        self._set_out_buf(cs, ob)
+        flat = vin.is_flattenable() and ob.pad == 0 and (res is None or res.is_flattenable())
+        if flat:
+            cs.flat, cs.flat_hw = 1, vin.H * vin.W
+            cs.src = [vin.flat()]
+            cs.out_strides = (ob.H * ob.W * ob.C, 0, ob.C)
+            if res is not None:
+                cs.res = V(res.t, res.off, 1, 1, res.N * res.H * res.W, res.C, res.H * res.W * res.sx, 0, res.sx)
+        else:
+            cs.src = [vin]
+            cs.tile = choose_tile(ob.H, ob.W)
+        cs.macs = ob.N * ob.H * ob.W * cout * w.shape[1]
+        return self._finish(cs, [(0, 0, 0, w.reshape(cout, -1))], cout, b)
+
+    # -- backbone --
+    def backbone(self, x_static):
+        net = self.m.backbone.net
+        B = self.B
+        H1, W1 = (self.H + 1) // 2, (self.W + 1) // 2
+        stem = net.stem
+        w, b = fold_bn(stem.conv.weight, None, stem.bn)
+        wk = self.f32(w.permute(1, 2, 3, 0).reshape(27, 32))
+        sb = self.buf(H1, W1, 32)
+        self.ops.append(StemSpec(x_static, wk, self.f32(b), sb.interior()))
+        cur, curH, curW = sb, H1, W1
+        feats = []
+        n_stage = self.m.backbone.stage_num
+        seg_on = self.m.segheader is not None
+        for s in range(n_stage):
+            stage = getattr(net, "stage_%d" % s)
+            blocks = list(stage.blocks.children())
+            for bi, blk in enumerate(blocks):
+                nm = "backbone.s%d.b%d" % (s, bi)
+                st, mid, cout = blk.stride, blk.mid, blk.cout
+                Ho, Wo = (curH - 1) // st + 1, (curW - 1) // st + 1
+                vin = cur.interior()
+                # 1x1 + BN + ReLU
+                w1, b1 = fold_bn(blk.conv_block_1[0].weight, None, blk.conv_block_1[1])
+                a = self.buf(curH, curW, mid)
+                self.conv1x1(nm + ".c1", vin, w1, b1, a, nv.ACT_RELU, "backbone")
+                # grouped 3x3 (+BN+ReLU), stride st
+                g = self.buf(Ho, Wo, mid)
+                self.gconv(nm + ".c2", a, blk, g, st)
+                # squeeze-excite (in place)
+                if blk.se is not None:
+                    S = blk.se[1].weight.shape[0]
+                    pooled = torch.zeros((B, mid), dtype=torch.float32, device=self.dev)
+                    scale = torch.zeros((B, mid), dtype=torch.float32, device=self.dev)
+                    self.ops.append(SeSpec(nm + ".se", g.interior(), pooled, scale,
+                                           self.f32(blk.se[1].weight.reshape(S, mid)), self.f32(blk.se[1].bias),
+                                           self.f32(blk.se[3].weight.reshape(mid, S)), self.f32(blk.se[3].bias)))
+                # shortcut
+                if blk.shortcut is not None:
+                    ws, bs = fold_bn(blk.shortcut[0].weight, None, blk.shortcut[1])
+                    sc = self.buf(Ho, Wo, cout)
+                    vs = vin.phase(0, 0) if st == 2 else vin
+                    self.conv1x1(nm + ".sc", vs, ws, bs, sc, nv.ACT_NONE, "backbone")
+                    res = sc.interior()
+                else:
+                    res = vin
+                last = bi == len(blocks) - 1
+                pad = 1 if (last and s == 0 and seg_on) else 0
+                ob = self.buf(Ho, Wo, cout, pad, nv.HALO_REFLECT if pad else nv.HALO_NONE)
+                w3, b3 = fold_bn(blk.conv_block_3[0].weight, None, blk.conv_block_3[1])
+                self.conv1x1(nm + ".c3", g.interior(), w3, b3, ob, nv.ACT_NONE, "backbone", res=res, res_relu=1)
+                cur, curH, curW = ob, Ho, Wo
+            feats.append(cur)
+        return feats
+
+    def gconv(self, name, a, blk, ob, stride):
+        conv, bn = blk.conv_block_2[0], blk.conv_block_2[1]
+        w, b = fold_bn(conv.weight, None, bn)  # [C, gw, 3, 3]
+        C, gw = w.shape[0], w.shape[1]
+        assert gw == 8 and C % 8 == 0, "grouped conv path assumes group width 8"
+        cs = ConvSpec(name)
+        cs.group, cs.act, cs.grouped = "backbone", nv.ACT_RELU, 1
+        self._set_out_buf(cs, ob)
+        cs.tile = choose_tile(ob.H, ob.W)
+        va = a.interior()
+        if stride == 1:
+            cs.src = [va]
+            where = {(ky, kx): (0, ky - 1, kx - 1) for ky in range(3) for kx in range(3)}
+        else:
+            cs.src = [va.phase(0, 0), va.phase(0, 1), va.phase(1, 0), va.phase(1, 1)]
+            # input row 2y+ky-1 = 2(y+ay)+ry
+            ph = {0: (1, -1), 1: (0, 0), 2: (1, 0)}
+            where = {(ky, kx): (ph[ky][0] * 2 + ph[kx][0], ph[ky][1], ph[kx][1]) for ky in range(3) for kx in range(3)}
+        bn_t = 64
+        rows = (C + bn_t - 1) // bn_t * bn_t
+        wm = torch.zeros((rows, 9 * 64), dtype=torch.float32, device=w.device)
+        co = torch.arange(C, device=w.device)
+        base = (co // 8) * 8 - (co // 64) * 64
+        taps = []
+        for ky in range(3):
+            for kx in range(3):
+                t = ky * 3 + kx
+                s, dy, dx = where[(ky, kx)]
+                taps.append((s, dy, dx, 0))
+                for j in range(8):
+                    wm[co, t * 64 + base + j] = w[:, j, ky, kx]
+        cs.cout, cs.bn = C, bn_t
+        cs.taps, cs.weight = taps, wm.to(self.dt).contiguous().to(self.dev)
+        cs.bias = pad_bias(b.to(self.dev), C, bn_t)
+        cs.stages = choose_stages(bn_t, 9)
+        cs.macs = ob.N * ob.H * ob.W * C * 8 * 9
+        self.ops.append(cs)
+
+    # -- neck --
+    def sepconv(self, name, ins, modes, ws, swish, sep, bn, ob, act, group, h, w, out_fp32=None):
+        """node/depthwise kernel -> pointwise GEMM (+bias, folded BN, activation)."""
+        C = sep.depthwise_conv.conv.weight.shape[0]
+        tmp = self.buf(h, w, C)
+        dw = self.f32(sep.depthwise_conv.conv.weight.reshape(C, 9).t())
+        self.ops.append(NodeSpec(name + ".dw", ins, modes, ws, swish, dw, tmp.interior(), group))
+        pw, pb = fold_bn(sep.pointwise_conv.conv.weight, sep.pointwise_conv.conv.bias, bn)
+        if out_fp32 is None:
+            return self.conv1x1(name + ".pw", tmp.interior(), pw, pb, ob, act, group)
+        # fp32 head output: rows of a [B, total, k] tensor
+        t, row0, k = out_fp32
+        cs = ConvSpec(name + ".pw")
+        cs.group, cs.act = group, act
+        cs.flat, cs.flat_hw = 1, h * w
+        cs.src = [tmp.interior().flat()]
+        cs.out_t, cs.out_off, cs.out_fp32 = t, row0 * k, 1
+        cout = pw.shape[0]
+        cs.out_strides = (t.shape[1] * k, 0, cout)
+        cs.macs = self.B * h * w * cout * C
+        return self._finish(cs, [(0, 0, 0, pw.reshape(cout, -1))], cout, pb)
+
+    def neck(self, feats):
+        cells = list(self.m.neck.bifpn.children())
+        seg_on = self.m.segheader is not None
+        levels = None
+        for ci, cell in enumerate(cells):
+            nm = "neck.c%d" % ci
+            last = ci == len(cells) - 1
+            eps = cell.epsilon
+            if cell.first_time:
+                if len(feats) == 4:
+                    c3, c4, c5 = feats[-3:]
+                    r = cell.p5_to_p6
+                    w, b = fold_bn(r[0].conv.weight, r[0].conv.bias, r[1])
+                    t6 = self.buf(c5.H, c5.W, w.shape[0])
+                    self.conv1x1(nm + ".p5_to_p6", c5.interior(), w, b, t6, nv.ACT_NONE, "neck")
+                    p6_in = self.buf((c5.H - 2) // 2 + 1, (c5.W - 2) // 2 + 1, w.shape[0])
+                    self.ops.append(PoolSpec(nm + ".p6pool", t6.interior(), p6_in.interior(), nv.POOL_ZERO_RB, "neck"))
+                else:
+                    c3, c4, c5, c6 = feats[-4:]
+                    r = cell.p6_down_channel
+                    w, b = fold_bn(r[0].conv.weight, r[0].conv.bias, r[1])
+                    p6_in = self.buf(c6.H, c6.W, w.shape[0])
+                    self.conv1x1(nm + ".p6_down", c6.interior(), w, b, p6_in, nv.ACT_NONE, "neck")
+                ch = p6_in.C
+                p7_in = self.buf((p6_in.H - 2) // 2 + 1, (p6_in.W - 2) // 2 + 1, ch)
+                self.ops.append(PoolSpec(nm + ".p7pool", p6_in.interior(), p7_in.interior(), nv.POOL_ZERO_RB, "neck"))
+                r = cell.p3_down_channel
+                w, b = fold_bn(r[0].conv.weight, r[0].conv.bias, r[1])
+                p3b = self.buf(c3.H, c3.W, ch)
+                self.conv1x1(nm + ".p3_down", c3.interior(), w, b, p3b, nv.ACT_NONE, "neck")
+
+                def two(ra, rb, c, tag):  # the two reducers of one level share their input: one GEMM
+                    wa, ba = fold_bn(ra[0].conv.weight, ra[0].conv.bias, ra[1])
+                    wb, bb = fold_bn(rb[0].conv.weight, rb[0].conv.bias, rb[1])
+                    ob = self.buf(c.H, c.W, 2 * ch)
+                    self.conv1x1(nm + tag, c.interior(), torch.cat([wa, wb], 0), torch.cat([ba, bb], 0), ob, nv.ACT_NONE, "neck")
+                    return ob.interior().chan(0, ch), ob.interior().chan(ch, ch)
+
+                p4_a, p4_b = two(cell.p4_down_channel, cell.p4_down_channel_2, c4, ".p4_down")
+                p5_a, p5_b = two(cell.p5_down_channel, cell.p5_down_channel_2, c5, ".p5_down")
+                p3_in, p6v, p7v = p3b.interior(), p6_in.interior(), p7_in.interior()
+            else:
+                p3_in, p4_a, p5_a, p6v, p7v = [l.interior() for l in levels]
+                p4_b, p5_b = p4_a, p5_a
+                ch = p3_in.C
+
+            def wts(p):
+                w = torch.relu(p.detach().float())
+                w = w / (torch.sum(w, dim=0) + eps)
+                return [float(v) for v in w.cpu()]
+
+            def node(tag, sep, ins, modes, ws, h, w, pad=0):
+                ob = self.buf(h, w, ch, pad, nv.HALO_REFLECT if pad else nv.HALO_NONE)
+                self.sepconv(nm + "." + tag, ins, modes, ws, 1, sep, sep.bn, ob, nv.ACT_NONE, "neck", h, w)
+                return ob
+
+            S, U, P = nv.IN_SAME, nv.IN_UP2, nv.IN_POOL
+            p6_up = node("conv6_up", cell.conv6_up, [p6v, p7v], [S, U], wts(cell.p6_w1), p6v.H, p6v.W)
+            p5_up = node("conv5_up", cell.conv5_up, [p5_a, p6_up.interior()], [S, U], wts(cell.p5_w1), p5_a.H, p5_a.W)
+            p4_up = node("conv4_up", cell.conv4_up, [p4_a, p5_up.interior()], [S, U], wts(cell.p4_w1), p4_a.H, p4_a.W)
+            segpad = 1 if (last and seg_on) else 0
+            p3_out = node("conv3_up", cell.conv3_up, [p3_in, p4_up.interior()], [S, U], wts(cell.p3_w1), p3_in.H, p3_in.W, segpad)
+            p4_out = node("conv4_down", cell.conv4_down, [p4_b, p4_up.interior(), p3_out.interior()], [S, S, P],
+                          wts(cell.p4_w2), p4_a.H, p4_a.W, segpad)
+            p5_out = node("conv5_down", cell.conv5_down, [p5_b, p5_up.interior(), p4_out.interior()], [S, S, P],
+                          wts(cell.p5_w2), p5_a.H, p5_a.W, segpad)
+            p6_out = node("conv6_down", cell.conv6_down, [p6v, p6_up.interior(), p5_out.interior()], [S, S, P],
+                          wts(cell.p6_w2), p6v.H, p6v.W)
+            p7_out = node("conv7_down", cell.conv7_down, [p7v, p6_out.interior()], [S, P], wts(cell.p7_w2), p7v.H, p7v.W)
+            levels = [p3_out, p4_out, p5_out, p6_out, p7_out]
+        return levels
+
+    # -- segmentation head --
+    def conv3x3_plain(self, name, ib, w, b, ob, act):
+        """3x3 over a reflect-padded buffer."""
+        cs = ConvSpec(name)
+        cs.group, cs.act = "seg", act
+        self._set_out_buf(cs, ob)
+        cs.tile = choose_tile(ob.H, ob.W)
+        cs.src = [ib.padded()]
+        cout = w.shape[0]
+        entries = [(0, ky, kx, w[:, :, ky, kx]) for ky in range(3) for kx in range(3)]
+        cs.macs = ob.N * ob.H * ob.W * cout * w.shape[1] * 9
+        return self._finish(cs, entries, cout, b)
+
+    def conv3x3_up(self, name, upb, skipb, w, b, ob, act):
+        """3x3 (reflect pad) over cat(up2(upb), skipb) as four parity-collapsed convs."""
+        cout, cup = w.shape[0], upb.C
+        assert upb.pad == 1 and upb.halo == nv.HALO_REPLICATE
+        for py in range(2):
+            for px in range(2):
+                cs = ConvSpec("%s.p%d%d" % (name, py, px))
+                cs.group, cs.act = "seg", act
+                self._set_out_buf(cs, ob)
+                # tile space = source resolution, output pixel (2y+py, 2x+px)
+                cs.out_h, cs.out_w = upb.H, upb.W
+                cs.out_scale, cs.out_oy, cs.out_ox = 2, py, px
+                cs.tile = choose_tile(upb.H, upb.W)
+                cs.src = [upb.padded()]
+                entries = []
+                for (sy, kys) in UP_SETS[py]:
+                    for (sx, kxs) in UP_SETS[px]:
+                        wt = sum(w[:, :cup, ky, kx] for ky in kys for kx in kxs)
+                        entries.append((0, sy + 1, sx + 1, wt))
+                if skipb is not None:
+                    assert skipb.pad == 1 and skipb.halo == nv.HALO_REFLECT
+                    sp = skipb.padded()
+                    cs.src += [sp.phase(0, 0), sp.phase(0, 1), sp.phase(1, 0), sp.phase(1, 1)]
+                    for ky in range(3):
+                        for kx in range(3):
+                            ry, ay = (py + ky) % 2, (py + ky) // 2
+                            rx, ax = (px + kx) % 2, (px + kx) // 2
+                            entries.append((1 + ry * 2 + rx, ay, ax, w[:, cup:, ky, kx]))
+                cs.macs = (ob.N * ob.H * ob.W * cout * w.shape[1] * 9) // 4
+                self._finish(cs, entries, cout, b)
+
+    def seg_out(self, name, ib, w, b, logits, cls_map):
+        """final 3x3 over up2(ib): sub-pixel conv at source resolution, 4 parities x 8 columns."""
+        ncls = w.shape[0]
+        assert ncls <= 8 and ib.pad == 1 and ib.halo == nv.HALO_REPLICATE
+        cs = ConvSpec(name)
+        cs.group, cs.epi, cs.n_cls = "seg", nv.EPI_SEGOUT, ncls
+        cs.src = [ib.padded()]
+        cs.n_img, cs.out_h, cs.out_w = ib.N, ib.H, ib.W
+        cs.tile = choose_tile(ib.H, ib.W)
+        cs.out_t, cs.out_off, cs.out_fp32 = logits, 0, 1
+        cs.out2 = cls_map
+        entries = []
+        bias = torch.zeros(32, dtype=torch.float32, device=w.device)
+        for sy in (-1, 0, 1):
+            for sx in (-1, 0, 1):
+                wt = torch.zeros((32, w.shape[1]), dtype=torch.float32, device=w.device)
+                for py in range(2):
+                    for px in range(2):
+                        kys = [k for (s, ks) in UP_SETS[py] if s == sy for k in ks]
+                        kxs = [k for (s, ks) in UP_SETS[px] if s == sx for k in ks]
+                        r0 = (py * 2 + px) * 8
+                        for ky in kys:
+                            for kx in kxs:
+                                wt[r0:r0 + ncls] += w[:, :, ky, kx]
+                entries.append((0, sy + 1, sx + 1, wt))
+        for p in range(4):
+            bias[p * 8:p * 8 + ncls] = b
+        cs.macs = ib.N * ib.H * ib.W * 4 * ncls * w.shape[1] * 9
+        return self._finish(cs, entries, 32, bias, bn=32)
+
+    def seg_head(self, feats0, levels):
+        dec = list(self.m.segheader.decoder.children())
+        n = len(self.m.segheader.num_ch_enc)
+        skips = [feats0] + levels[:n - 1]          # input_features
+        x = skips[-1]                              # reflect-padded P5 (or deepest feature)
+        R, RP = nv.HALO_REFLECT, nv.HALO_REPLICATE
+        for i in range(n):
+            c0, c1 = dec[2 * i].conv.conv, dec[2 * i + 1].conv.conv
+            a = self.buf(x.H, x.W, c0.weight.shape[0], 1, RP)
+            self.conv3x3_plain("seg.d%d" % (2 * i), x, c0.weight.detach().float(), c0.bias.detach().float(), a, nv.ACT_ELU)
+            skip = skips[n - 2 - i] if i < n - 1 else None
+            last = i == n - 1
+            ob = self.buf(a.H * 2, a.W * 2, c1.weight.shape[0], 1, RP if last else R)
+            self.conv3x3_up("seg.d%d" % (2 * i + 1), a, skip, c1.weight.detach().float(), c1.bias.detach().float(), ob, nv.ACT_ELU)
+            x = ob
+        oc = dec[-1].conv
+        ncls = oc.weight.shape[0]
+        logits = torch.empty((self.B, ncls, x.H * 2, x.W * 2), dtype=torch.float32, device=self.dev)
+        cls_map = torch.empty((self.B, x.H * 2, x.W * 2), dtype=torch.uint8, device=self.dev)
+        self.seg_out("seg.out", x, oc.weight.detach().float(), oc.bias.detach().float(), logits, cls_map)
+        self.out["seg"] = logits
+        self.out["seg_cls_u8"] = cls_map
+
+    # -- detection head --
+    def det_head(self, levels):
+        dh = self.m.detectheader
+        na, ncls = dh.num_anchors, dh.num_classes
+        total = sum(l.H * l.W for l in levels) * na
+        reg = torch.empty((self.B, total, 4), dtype=torch.float32, device=self.dev)
+        cls = torch.empty((self.B, total, ncls), dtype=torch.float32, device=self.dev)
+        row0 = 0
+        for li, lv in enumerate(levels):
+            for tname, tower, out_t, k, act in (("reg", dh.regressor, reg, 4, nv.ACT_NONE),
+                                                ("cls", dh.classifier, cls, ncls, nv.ACT_SIGMOID)):
+                cur = lv
+                for i in range(tower.num_layers):
+                    ob = self.buf(lv.H, lv.W, lv.C)
+                    self.sepconv("det.%s.l%d.%d" % (tname, li, i), [cur.interior()], [nv.IN_SAME], [1.0], 0, tower.conv_list[i],
+                                 tower.bn_list[li][i], ob, nv.ACT_SWISH, "detect", lv.H, lv.W)
+                    cur = ob
+                self.sepconv("det.%s.l%d.hdr" % (tname, li), [cur.interior()], [nv.IN_SAME], [1.0], 0, tower.header, None, None,
+                             act, "detect", lv.H, lv.W, out_fp32=(out_t, row0, k))
+            row0 += lv.H * lv.W * na
+        self.out["regression"], self.out["classification"] = reg, cls
+
+    # -- lane head --
+    def lane_head(self, levels):
+        lh = self.m.laneheader
+        p3, p4, p5, p6 = levels[:4]
+        if lh.stride == 32:
+            fh, fw = p5.H, p5.W
+        elif lh.stride == 16:
+            fh, fw = p4.H, p4.W
+        else:
+            raise ValueError("lane anchor_stride must be 16 or 32 (lanedetect.py:70-83)")
+        C = p3.C
+        fused = self.buf(fh, fw, 4 * C)
+        self.ops.append(LaneFuseSpec(p3.interior(), p4.interior(), p5.interior(), p6.interior(), fused.interior(), lh.stride))
+        branches = [lh.conv_cls_conv, lh.conv_up_conv, lh.conv_down_conv]
+        ws, bs = zip(*[fold_bn(br[0].weight, None, br[1]) for br in branches])
+        hid = self.buf(fh, fw, 4 * C * 3)
+        self.conv1x1("lane.hidden", fused.interior(), torch.cat(ws, 0), torch.cat(bs, 0), hid, nv.ACT_RELU, "lane")
+        ncls = lh.num_classes
+        nup, ndown = lh.lane_up_pts_num, lh.lane_down_pts_num
+        pcls = torch.empty((self.B, fh * fw, ncls), dtype=torch.float32, device=self.dev)
+        ploc = torch.empty((self.B, fh * fw, nup + ndown), dtype=torch.float32, device=self.dev)
+        for bi, (br, t, col0) in enumerate(((lh.conv_cls_conv, pcls, 0), (lh.conv_up_conv, ploc, ndown), (lh.conv_down_conv, ploc, 0))):
+            conv = br[3]
+            cout = conv.weight.shape[0]
+            cs = ConvSpec("lane.out%d" % bi)
+            cs.group = "lane"
+            cs.flat, cs.flat_hw = 1, fh * fw
+            cs.src = [hid.interior().chan(bi * 4 * C, 4 * C).flat()]
+            cs.out_t, cs.out_off, cs.out_fp32 = t, col0, 1
+            cs.out_strides = (t.shape[1] * t.shape[2], 0, t.shape[2])
+            cs.macs = self.B * fh * fw * cout * 4 * C
+            self._finish(cs, [(0, 0, 0, conv.weight.detach().float().reshape(cout, -1))], cout, conv.bias.detach().float())
+        self.out["predict_cls"], self.out["predict_loc"] = pcls, ploc
+
+    def build(self, x_static):
+        feats = self.backbone(x_static)
+        levels = self.neck(feats)
+        if self.m.segheader is not None:
+            self.seg_head(feats[0], levels)
+        if self.m.detectheader is not None:
+            self.det_head(levels)
+        if self.m.laneheader is not None:
+            self.lane_head(levels)
+        return self
+
+
+class Plan:
+    """Compiled schedule for one input shape: static input, buffers, native plan handle."""
+
+    def __init__(self, model, B, H, W, device):
+        self.B, self.H, self.W, self.device = B, H, W, device
+        self.x = torch.zeros((B, 3, H, W), dtype=torch.float32, device=device)
+        self.builder = Builder(model, B, H, W, device).build(self.x)
+        self.ops = self.builder.ops
+        self.out = self.builder.out
+        import ctypes
+        self.handle = ctypes.c_void_p()
+        nv.check(nv.lib.hn_plan_create(ctypes.byref(self.handle)))
+        for op in self.ops:
+            try:
+                op.add_to(self.handle)
+            except nv.NativeError as e:
+                raise nv.NativeError("while adding op %s: %s" % (op.name, e))
+        self.n_launches = nv.lib.hn_plan_num_launches(self.handle)
+        self.graph_ready = False
+
+    def run(self, stream_ptr):
+        nv.check(nv.lib.hn_plan_run(self.handle, stream_ptr))
+
+    def run_range(self, first, last, stream_ptr):
+        nv.check(nv.lib.hn_plan_run_range(self.handle, first, last, stream_ptr))
+
+    def capture(self, stream_ptr):
+        nv.check(nv.lib.hn_plan_graph_capture(self.handle, stream_ptr))
+        self.graph_ready = True
+
+    def launch_graph(self, stream_ptr):
+        nv.check(nv.lib.hn_plan_graph_launch(self.handle, stream_ptr))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                nv.lib.hn_plan_destroy(self.handle)
+        except Exception:
+            pass

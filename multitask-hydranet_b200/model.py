@@ -1,0 +1,124 @@
+"""Drop-in ``HydraNet`` facade (reference: model/model.py:26-264).
+
+Same constructor, attribute names, ``state_dict`` keys, ``forward(x, mode)`` signature and output
+structure as the reference.  In eval mode the forward runs entirely in the native sm_100a engine
+(``engine.py`` -> ``libhydranet_b200.so``); there is no PyTorch/cuDNN or CPU fallback: a missing
+library fails at import, a CPU tensor raises.
+"""
+import torch
+from torch import nn
+
+from . import _native as nv
+from .engine import Plan
+from .heads import DetectionHeader, LaneHeader, SegmentHeader
+from .modules import RegNetY, StackBiFPN
+
+
+class HydraNet(nn.Module):
+    def __init__(self, cfgs, onnx_export=False):
+        super().__init__()
+        self.cfgs, self.onnx_export = cfgs, onnx_export
+        self.net_input_width = cfgs["dataloader"]["network_input_width"]
+        self.net_input_height = cfgs["dataloader"]["network_input_height"]
+        bb = cfgs["backbone"]
+        self.backbone = RegNetY(bb["initial_width"], bb["slope"], bb["quantized_param"], bb["network_depth"],
+                                bb["bottleneck_ratio"], bb["group_width"], bb["stride"], bb["se_ratio"])
+        self.fpn_num_filters, self.fpn_cell_repeats = bb["fpn_num_filters"], bb["fpn_cell_repeats"]
+        self.conv_channel_coef = bb["conv_channel_coef"]
+        self.neck = StackBiFPN(self.fpn_num_filters, self.fpn_cell_repeats, self.conv_channel_coef)
+
+        self.train_detect = cfgs["train"]["train_detect"]
+        if self.train_detect:
+            dc = cfgs["detection"]
+            self.num_classes = dc["num_classes"]
+            r1, r2 = dc["aspect_ratios_factor"]
+            self.aspect_ratios = [(1.0, 1.0), (r1, r2), (r2, r1)]
+            self.scales = [2 ** s for s in dc["scales_factor"]]
+            self.detectheader = DetectionHeader(dc["num_classes"], dc["fpn_num_filters_detect"], self.aspect_ratios,
+                                                self.scales, dc["box_class_repeats"], dc["pyramid_levels"],
+                                                dc["anchor_scale"], onnx_export)
+        else:
+            self.detectheader = None
+
+        self.train_seg = cfgs["train"]["train_seg"]
+        if self.train_seg:
+            sc = cfgs["segment"]
+            self.segment_class_list = sc["class_list"]
+            self.segheader = SegmentHeader(sc["channel_dimension_seg_encode"], sc["channel_dimension_seg_decode"],
+                                           len(sc["class_list"]))
+        else:
+            self.segheader = None
+
+        self.train_lane = cfgs["train"]["train_lane"]
+        if self.train_lane:
+            lc = cfgs["lane"]
+            self.laneheader = LaneHeader(lc["base_channel"], lc["num_classes"], lc["anchor_stride"], self.net_input_width,
+                                         self.net_input_height, lc["interval"])
+        else:
+            self.laneheader = None
+        self.loss_detect = self.loss_seg = self.loss_cls = self.loss_reg = None
+        self._plans = {}
+        self._sig = None
+        self.use_graph = False
+
+    # -- native engine management ------------------------------------------------------------
+    def _signature(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def plan(self, B, H, W, device):
+        sig = self._signature()
+        if sig != self._sig:  # weights changed (load_state_dict, optimizer step, .cuda()): re-pack
+            self._plans, self._sig = {}, sig
+        key = (B, H, W, str(device))
+        if key not in self._plans:
+            with torch.no_grad():
+                self._plans[key] = Plan(self, B, H, W, device)
+        return self._plans[key]
+
+    def forward(self, x, mode="train"):
+        if self.training:
+            raise NotImplementedError(
+                "hydranet_b200 round 1 implements the eval-mode (folded-BN) forward natively; the train-mode "
+                "step (batch-stat BN, dgrad/wgrad) is not built yet -- call .eval() first")
+        if not x.is_cuda:
+            raise RuntimeError("HydraNet.forward: input must be a CUDA tensor -- the B200 path has no CPU fallback")
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError("expected input of shape [B, 3, H, W]")
+        B, _, H, W = x.shape
+        if self.train_detect:
+            for s in self.detectheader.anchors.strides:
+                if W % s != 0 or H % s != 0:
+                    raise ValueError('input size must be divided by the stride.')
+        plan = self.plan(B, H, W, x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        plan.x.copy_(x)
+        if self.use_graph:
+            if not plan.graph_ready:
+                plan.run(stream)  # warm-up outside capture (lazy function attributes)
+                plan.capture(stream)
+            plan.launch_graph(stream)
+        else:
+            plan.run(stream)
+        o = plan.out
+        output_dict = {}
+        if self.train_seg:
+            output_dict["seg"] = o["seg"]
+        anchors = regression = classification = lane_cls = lane_reg = None
+        if self.train_detect:
+            anchors = self.detectheader.anchors(x, x.dtype)
+            regression, classification = o["regression"], o["classification"]
+            output_dict["detection"] = {"anchors": anchors, "regression": regression, "classification": classification}
+        if self.train_lane:
+            lane_cls, lane_reg = o["predict_cls"], o["predict_loc"]
+            output_dict["lane"] = dict(predict_cls=lane_cls, predict_loc=lane_reg)
+        if mode != "deploy":
+            return output_dict
+        seg_cls = None
+        if self.train_seg:  # fused arg-max of the last seg conv (model.py:197)
+            u8 = o["seg_cls_u8"]
+            seg_cls = torch.empty(u8.shape, dtype=torch.int64, device=u8.device)
+            nv.check(nv.lib.hn_u8_to_i64(u8.data_ptr(), seg_cls.data_ptr(), u8.numel(), stream))
+        return seg_cls, anchors, regression, classification, lane_cls, lane_reg
+
+    def cal_loss(self, pred_dict, gt_dict):
+        raise NotImplementedError("losses are training-only glue (SURVEY.md section 2.1 row 7) and not built in round 1")
