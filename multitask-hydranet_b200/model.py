@@ -59,6 +59,7 @@ class HydraNet(nn.Module):
         self.loss_detect = self.loss_seg = self.loss_cls = self.loss_reg = None
         self._plans = {}
         self._sig = None
+        self._last_plan = None
         self.use_graph = False
 
     # -- native engine management ------------------------------------------------------------
@@ -100,6 +101,7 @@ class HydraNet(nn.Module):
         else:
             plan.run(stream)
         o = plan.out
+        self._last_plan = plan
         output_dict = {}
         if self.train_seg:
             output_dict["seg"] = o["seg"]
@@ -119,6 +121,10 @@ class HydraNet(nn.Module):
             seg_cls = torch.empty(u8.shape, dtype=torch.int64, device=u8.device)
             nv.check(nv.lib.hn_u8_to_i64(u8.data_ptr(), seg_cls.data_ptr(), u8.numel(), stream))
         return seg_cls, anchors, regression, classification, lane_cls, lane_reg
+
+    def seg_class_map(self):
+        """uint8 [B,H,W] arg-max of the last forward's seg logits (fused into the final conv's epilogue)."""
+        return self._last_plan.out["seg_cls_u8"]
 
     def cal_loss(self, pred_dict, gt_dict):
         raise NotImplementedError("losses are training-only glue (SURVEY.md section 2.1 row 7) and not built in round 1")

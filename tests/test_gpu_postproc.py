@@ -1,0 +1,222 @@
+"""GPU parity tests of the post-processing kernels (-m gpu): bit-exact against the numpy oracle
+(oracle/postproc_ref.py, pinned against the live reference + torchvision) and against the golden
+outputs of the live reference's own decoders."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import hydranet_b200 as hb
+from hydranet_b200 import _native as nv
+from hydranet_b200.heads import make_anchors
+from oracle import postproc_ref as pr
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+# ------------------------------------------------------------------ segmentation arg-max
+@pytest.mark.parametrize("shape", [(2, 5, 640, 640), (1, 5, 1280, 1280), (3, 7, 33, 17), (1, 1, 8, 8), (0, 5, 16, 16)])
+def test_seg_argmax_bit_exact(shape):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(shape, generator=g)
+    if x.numel():
+        x = torch.round(x * 4) / 4  # plenty of exact ties -> lowest index must win
+    ref = torch.argmax(x, 1) if x.numel() else torch.zeros((0,) + shape[2:], dtype=torch.int64)
+    out = hb.SegmentHeader.argmax(x.cuda())
+    assert out.dtype == torch.int64 and torch.equal(out.cpu(), ref)
+
+
+def test_seg_argmax_nan_semantics():
+    x = torch.randn(1, 5, 16, 16)
+    x[0, 3, 2, 2] = float("nan")
+    x[0, 1, 5, 5] = float("nan"); x[0, 4, 5, 5] = float("nan")
+    assert torch.equal(hb.SegmentHeader.argmax(x.cuda()).cpu(), torch.argmax(x, 1))
+
+
+# ------------------------------------------------------------------ detection
+def _det_compare(out, ref, ties_as_sets=False):
+    assert len(out) == len(ref)
+    for o, r in zip(out, ref):
+        assert len(o["scores"]) == len(r["scores"])
+        if len(r["scores"]) == 0:
+            assert o["rois"].shape == (0,) and o["class_ids"].shape == (0,)
+            continue
+        assert o["rois"].dtype == np.float32 and o["class_ids"].dtype == np.int64 and o["scores"].dtype == np.float32
+        assert np.array_equal(o["scores"], r["scores"])
+        if not ties_as_sets:
+            assert np.array_equal(o["class_ids"], r["class_ids"]) and np.array_equal(o["rois"], r["rois"])
+        else:  # vanilla dispatch ends with an unstable score sort: equal-score runs compared as sets
+            key = lambda d: sorted(map(tuple, np.concatenate([d["scores"][:, None], d["class_ids"][:, None].astype(np.float64), d["rois"]], 1).tolist()))
+            assert key(o) == key(r)
+
+
+@pytest.mark.parametrize("name,hw", [("big_128x128", (128, 128)), ("small_128x256", (128, 256))])
+def test_det_decode_matches_live_reference_golden(name, hw):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    reg, cls, anc = (torch.from_numpy(g[k]).cuda() for k in ("regression", "classification", "anchors"))
+    thr = float(g["det_thr"])
+    boxes, scores, cids, count, _ = hb.DetectionHeader.decode_device(hw, reg, cls, anc, thr, 0.3, nms_mode=nv.NMS_AUTO_CPU)
+    for i in range(2):
+        k = int(count[i])
+        assert k == len(g["det%d_scores" % i])
+        assert np.array_equal(scores[i, :k].cpu().numpy(), g["det%d_scores" % i])
+        assert np.array_equal(cids[i, :k].cpu().numpy(), g["det%d_class_ids" % i])
+        # boxes: the reference's fp32 exp may differ from the correctly rounded one by 1 ulp
+        assert np.allclose(boxes[i, :k].cpu().numpy(), g["det%d_rois" % i], rtol=3e-7, atol=1e-4)
+
+
+def _synth_det(N, H, W, seed, hot=False):
+    rng = np.random.default_rng(seed)
+    anc = make_anchors((H, W), 2.0, [8, 16, 32, 64, 128], [2 ** 0.0, 2 ** 0.333, 2 ** 0.667], [(1.0, 1.0), (1.4, 0.7), (0.7, 1.4)])
+    A = anc.shape[1]
+    reg = rng.normal(0, 0.3, (N, A, 4)).astype(np.float32)
+    if hot:  # random-init-like: every score within [0.47, 0.53] -> every anchor is a candidate
+        cls = (0.5 + rng.uniform(-0.03, 0.03, (N, A, 9))).astype(np.float32)
+    else:
+        cls = (1.0 / (1.0 + np.exp(-rng.normal(0, 1, (N, A, 9))))).astype(np.float32)
+    # force score ties so that the stable tie order is exercised
+    n7 = cls[:, 1::7].shape[1]
+    cls[:, 0:7 * n7:7] = cls[:, 1::7]
+    return anc, reg, cls
+
+
+@pytest.mark.parametrize("mode,pmode", [(nv.NMS_TRICK, "trick"), (nv.NMS_VANILLA, "vanilla"), (nv.NMS_AUTO_CUDA, None)])
+def test_det_decode_nms_bit_exact_vs_oracle(mode, pmode):
+    H = W = 256
+    anc, reg, cls = _synth_det(3, H, W, 5)
+    thr = 0.8
+    out = []
+    boxes, scores, cids, count, cand = hb.DetectionHeader.decode_device((H, W), torch.from_numpy(reg).cuda(), torch.from_numpy(cls).cuda(),
+                                                                        torch.from_numpy(anc).cuda(), thr, 0.3, nms_mode=mode)
+    for i in range(3):
+        k = int(count[i])
+        out.append({"rois": boxes[i, :k].cpu().numpy(), "class_ids": cids[i, :k].cpu().numpy(), "scores": scores[i, :k].cpu().numpy()}
+                   if k else {"rois": np.array(()), "class_ids": np.array(()), "scores": np.array(())})
+    ref = pr.det_postprocess(anc, reg, cls, H, W, thr, 0.3, device="cuda", mode=pmode)
+    assert [int(c) for c in cand] == [int((cls[i].max(1) > np.float32(thr)).sum()) for i in range(3)]
+    _det_compare(out, ref, ties_as_sets=(pmode == "vanilla"))
+
+
+def test_det_public_decode_api_and_empty():
+    H = W = 128
+    anc, reg, cls = _synth_det(2, H, W, 7)
+    imgs = torch.zeros(2, 3, H, W, device="cuda")
+    cls[1] = 0.1  # image 1: nothing over threshold -> empty arrays like the reference
+    out = hb.DetectionHeader.decode(imgs, torch.from_numpy(reg).cuda(), torch.from_numpy(cls).cuda(), torch.from_numpy(anc).cuda(), 0.7, 0.3)
+    ref = pr.det_postprocess(anc, reg, cls, H, W, 0.7, 0.3, device="cuda")
+    _det_compare(out, ref)
+    assert out[1]["rois"].shape == (0,)
+    assert hb.DetectionHeader.decode(None, None, None, None) is None
+
+
+def test_det_stress_max_anchors_640():
+    """BASELINE config 5(i): every one of the 76 725 anchors is an NMS candidate."""
+    H = W = 640
+    anc, reg, cls = _synth_det(1, H, W, 11, hot=True)
+    assert anc.shape[1] == 76725
+    boxes, scores, cids, count, cand = hb.DetectionHeader.decode_device((H, W), torch.from_numpy(reg).cuda(), torch.from_numpy(cls).cuda(),
+                                                                        torch.from_numpy(anc).cuda(), 0.3, 0.3)
+    assert int(cand[0]) == 76725
+    ref = pr.det_postprocess(anc, reg, cls, H, W, 0.3, 0.3, device="cuda")[0]  # 306 900 coords > 100 000 -> per-class
+    k = int(count[0])
+    out = {"rois": boxes[0, :k].cpu().numpy(), "class_ids": cids[0, :k].cpu().numpy(), "scores": scores[0, :k].cpu().numpy()}
+    _det_compare([out], [ref], ties_as_sets=True)
+    # size-independent properties: sorted by score, no surviving same-class pair above the IoU threshold
+    assert np.all(np.diff(out["scores"]) <= 0)
+    sub = np.random.default_rng(0).choice(k, size=min(k, 1500), replace=False)
+    b, c = out["rois"][sub], out["class_ids"][sub]
+    x1, y1 = np.maximum(b[:, None, 0], b[None, :, 0]), np.maximum(b[:, None, 1], b[None, :, 1])
+    x2, y2 = np.minimum(b[:, None, 2], b[None, :, 2]), np.minimum(b[:, None, 3], b[None, :, 3])
+    inter = np.maximum(0, x2 - x1) * np.maximum(0, y2 - y1)
+    area = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    iou = inter / (area[:, None] + area[None, :] - inter)
+    np.fill_diagonal(iou, 0)
+    assert not np.any((iou > np.float32(0.3)) & (c[:, None] == c[None, :]))
+
+
+def test_det_pre_boxes_identical_inputs():
+    """NMS given identical pre-NMS boxes (north_star): feed the oracle's decoded boxes."""
+    H = W = 256
+    anc, reg, cls = _synth_det(2, H, W, 13)
+    pre = pr.bbox_transform_clip(anc.reshape(-1, 4), reg, H, W)
+    boxes, scores, cids, count, _ = hb.DetectionHeader.decode_device((H, W), None, torch.from_numpy(cls).cuda(), None, 0.75, 0.3,
+                                                                     pre_boxes=torch.from_numpy(pre).cuda())
+    ref = pr.det_postprocess(anc, reg, cls, H, W, 0.75, 0.3, device="cuda", pre_boxes=pre)
+    out = [{"rois": boxes[i, :int(count[i])].cpu().numpy(), "class_ids": cids[i, :int(count[i])].cpu().numpy(),
+            "scores": scores[i, :int(count[i])].cpu().numpy()} for i in range(2)]
+    _det_compare(out, ref)
+
+
+# ------------------------------------------------------------------ lanes
+def _lane_compare(lanes, ref):
+    assert len(lanes) == len(ref)
+    for l, r in zip(lanes, ref):
+        assert np.float32(l.prob) == np.float32(r["prob"]) and l.start_pos == r["start_pos"] and l.end_pos == r["end_pos"]
+        assert l.ax == r["ax"] and l.ay == r["ay"]
+        xs = np.array([p.x for p in l.lane], dtype=np.float32)
+        ys = np.array([p.y for p in l.lane], dtype=np.float64)
+        assert np.array_equal(xs, r["xs"]) and np.array_equal(ys, r["ys"])
+
+
+@pytest.mark.parametrize("name,hw,stride", [("big_128x128", (128, 128), 32), ("small_128x256", (128, 256), 32)])
+def test_lane_decode_matches_live_reference_golden(name, hw, stride):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    H, W = hw
+    codec = hb.LaneCodec(W, H, stride, int(H / 8), True, 1, True)
+    for b in range(2):
+        prob = torch.from_numpy(g["lane%d_softmax" % b]).cuda()
+        loc = torch.from_numpy(g["predict_loc"][b]).cuda()
+        count, meta, p, xs, _ = hb.LaneHeader.decode_device(prob, loc, codec, 0.3, 30, False, cls_is_prob=True)
+        lanes = hb.LaneHeader.lanes_from_device(count.cpu(), meta, p, xs, codec, 0)
+        npts = g["lane%d_npts" % b]
+        assert len(lanes) == len(npts)
+        assert np.array_equal(np.array([l.prob for l in lanes], dtype=np.float32), g["lane%d_prob" % b])
+        assert np.array_equal(np.array([l.start_pos for l in lanes]), g["lane%d_start" % b])
+        assert np.array_equal(np.array([l.end_pos for l in lanes]), g["lane%d_end" % b])
+        assert np.array_equal(np.concatenate([[p_.x for p_ in l.lane] for l in lanes]).astype(np.float32), g["lane%d_xs" % b])
+        assert np.array_equal(np.concatenate([[p_.y for p_ in l.lane] for l in lanes]).astype(np.float64), g["lane%d_ys" % b])
+        # logits path (softmax on the device): same lane set on this data
+        lanes2 = hb.LaneHeader.decode(torch.from_numpy(g["predict_cls"][b]).cuda(), loc, codec, 0.3, 30, False)
+        assert [l.start_pos for l in lanes2] == [l.start_pos for l in lanes]
+
+
+@pytest.mark.parametrize("H,W,ppl,use_mean,thr,nms", [(640, 640, 80, False, 0.5, 80), (640, 640, 80, True, 0.3, 100),
+                                                      (1280, 1280, 160, False, 0.5, 100), (128, 256, 16, False, 0.9, 80)])
+def test_lane_decode_nms_bit_exact_vs_oracle(H, W, ppl, use_mean, thr, nms):
+    """BASELINE config 5(ii): 400 and 1 600 anchors, cls logits N(0,3), loc N(0,2), end-pos U(0,ppl)."""
+    rng = np.random.default_rng(H + ppl)
+    codec = hb.LaneCodec(W, H, 32, ppl, True, 1, True)
+    na = codec.feature_size
+    N = 2
+    logits = rng.normal(0, 3, (N, na, 2)).astype(np.float32)
+    loc = rng.normal(0, 2, (N, na, 2 * ppl + 2)).astype(np.float32)
+    loc[:, :, ppl] = rng.uniform(0, ppl, (N, na)).astype(np.float32)
+    loc[:, :, ppl + 1] = rng.uniform(0, ppl, (N, na)).astype(np.float32)
+    prob = pr.softmax2(logits)
+    n5 = prob[:, 1::5].shape[1]
+    prob[:, 0:5 * n5:5, 1] = prob[:, 1::5, 1]  # probability ties -> stable order
+    count, meta, p, xs, cand = hb.LaneHeader.decode_device(torch.from_numpy(prob).cuda(), torch.from_numpy(loc).cuda(), codec, thr, nms,
+                                                           use_mean, cls_is_prob=True)
+    for b in range(N):
+        ref = pr.lane_decode_nms(prob[b], loc[b], codec.feature_height, codec.feature_width, ppl, 32, codec.interval, W, H, thr, nms,
+                                 use_mean, cls_is_prob=True)
+        lanes = hb.LaneHeader.lanes_from_device(count.cpu(), meta, p, xs, codec, b)
+        _lane_compare(lanes, ref)
+    assert int(cand.max()) >= int(count.max())
+
+
+def test_lane_empty_and_codec_decode_lane():
+    codec = hb.LaneCodec(640, 640, 32, 80, True, 1, True)
+    rng = np.random.default_rng(3)
+    prob = np.zeros((400, 2), dtype=np.float32); prob[:, 0] = 1
+    loc = rng.normal(0, 2, (400, 162)).astype(np.float32)
+    assert hb.LaneHeader.decode(torch.from_numpy(prob).cuda() * 20, torch.from_numpy(loc).cuda(), codec, 0.5, 100) == []
+    p2 = pr.softmax2(rng.normal(0, 3, (400, 2)).astype(np.float32))
+    loc[:, 80] = 40; loc[:, 81] = 40
+    cands = codec.decode_lane(torch.from_numpy(p2).cuda(), torch.from_numpy(loc).cuda(), 0.6)
+    ref = pr.decode_lane(p2[:, 1], loc, 20, 20, 80, 32, 8.0, 640, 640, 0.6)
+    _lane_compare(cands, ref)
+    js = hb.LaneHeader.scale_to_org(cands[:3], 640, 640, 1920, 1080)
+    assert "Lines" in js
