@@ -204,6 +204,13 @@ def run_native(args):
                 a[0] += evs[i].elapsed_time(evs[i + 1]) / reps
                 a[1] += op.macs if rep == 1 else 0
                 a[2] += 1 if rep == 1 else 0
+        if args.dump_ops:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", "op_times.txt"), "w") as f:
+                for i, op in enumerate(plan.ops):
+                    ms_i = evs[i].elapsed_time(evs[i + 1])
+                    f.write("%4d %-30s %-8s %-9s %9.4f ms %8.3f GFLOP %8.2f TFLOP/s\n" % (
+                        i, op.name, op.kind, op.group, ms_i, 2e-9 * op.macs, 2e-9 * op.macs / max(ms_i, 1e-6)))
         conv_ms = sum(v[0] for k, v in tot.items() if k[0] == "conv")
         conv_flops = 2.0 * sum(v[1] for k, v in tot.items() if k[0] == "conv")
         conv_n = sum(v[2] for k, v in tot.items() if k[0] == "conv")
@@ -299,6 +306,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--dump-ops", action="store_true", help="write per-op device times to gpurun_out/op_times.txt")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -52,9 +52,10 @@ __global__ void hn_seg_argmax_kernel(const float* __restrict__ logits, int C, lo
 
 extern "C" int hn_seg_argmax(const float* logits, int32_t N, int32_t C, int64_t HW, int64_t* out_i64, uint8_t* out_u8,
                              void* stream) {
-    HN_REQUIRE(logits && (out_i64 || out_u8) && N >= 0 && C >= 1 && C <= 255 && HW >= 0, "seg_argmax: bad arguments");
+    HN_REQUIRE(N >= 0 && C >= 1 && C <= 255 && HW >= 0, "seg_argmax: bad arguments");
     long long total = (long long)N * HW;
     if (total == 0) return HN_OK;
+    HN_REQUIRE(logits && (out_i64 || out_u8), "seg_argmax: bad arguments");
     HN_REQUIRE((reinterpret_cast<uintptr_t>(logits) & 15) == 0, "seg_argmax: logits must be 16-byte aligned");
     hn_seg_argmax_kernel<<<hn_cdiv(hn_cdiv(total, 4), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         logits, C, HW, total, out_i64, out_u8);
@@ -104,11 +105,50 @@ struct DetWs {
     int* seg_kept;      // [N*16]
     float4* kept_boxes; // [N*A] compacted per segment (NMS-space coordinates)
     uint64_t* kept_keys;// [N*A] compacted per segment
+    int* kept_next;     // [N*A] linked list through the kept boxes of one grid cell
+    int* heads;         // [N*16][kGridHeads] list heads of the per-level spatial grids (-1 = empty)
     void* cub_tmp;
     size_t cub_bytes;
 };
 
 static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+
+// Spatial index over the kept boxes of one (image, class) segment.  Boxes are binned by size level
+// l = floor(log2(max(w,h) / c0)) (cell size c0*2^l, so a level-l box is smaller than two cells) and
+// by the cell of their centre.  IoU > thr > 0 implies (a) the boxes intersect and (b) their widths and
+// heights are each within a factor 1/thr, so a candidate only visits levels within +-delta of its own
+// and the cells its extent (grown by one cell) touches: exact pruning, not an approximation.
+static constexpr int kGridLevels = 8;
+static constexpr int kGridHeads = 6144;
+struct GridGeom {
+    int nlev, delta, prune;
+    float c0;
+    int nx[kGridLevels], ny[kGridLevels], base[kGridLevels];
+};
+
+static GridGeom make_grid(int img_h, int img_w, float iou_thr) {
+    GridGeom g;
+    memset(&g, 0, sizeof(g));
+    int mx = img_w > img_h ? img_w : img_h;
+    float c0 = 16.0f;
+    while (mx / c0 > 64.0f) c0 *= 2.0f;
+    g.c0 = c0;
+    g.nlev = kGridLevels;
+    int off = 0;
+    for (int l = 0; l < kGridLevels; ++l) {
+        float c = c0 * (float)(1 << l);
+        int nx = (int)(img_w / c) + 2, ny = (int)(img_h / c) + 2;
+        if (l == kGridLevels - 1) nx = ny = 1;  // unbounded sizes: one bucket
+        if (off + nx * ny > kGridHeads) { nx = ny = 1; }
+        g.nx[l] = nx; g.ny[l] = ny; g.base[l] = off;
+        off += nx * ny;
+    }
+    g.prune = iou_thr > 0.0078125f;
+    int d = 1;
+    if (g.prune) { float r = 1.0f / iou_thr; while ((float)(1 << (d - 1)) < r) ++d; }  // floor(log2(1/thr)) + 1 or more
+    g.delta = g.prune ? d : kGridLevels;
+    return g;
+}
 
 static size_t det_cub_bytes(long long n) {
     size_t bytes = 0;
@@ -137,6 +177,8 @@ static size_t det_layout(int N, int A, void* base, DetWs* ws) {
     w.seg_kept = reinterpret_cast<int*>(take(N * kMaxCls * 4));
     w.kept_boxes = reinterpret_cast<float4*>(take(NA * 16));
     w.kept_keys = reinterpret_cast<uint64_t*>(take(NA * 8));
+    w.kept_next = reinterpret_cast<int*>(take(NA * 4));
+    w.heads = reinterpret_cast<int*>(take((size_t)N * kMaxCls * kGridHeads * 4));
     w.cub_bytes = det_cub_bytes(NA);
     w.cub_tmp = take(w.cub_bytes);
     if (ws) *ws = w;
@@ -213,6 +255,7 @@ __device__ __forceinline__ bool iou_gt(const float4& a, float area_a, const floa
     float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
     float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
     float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+    if (thr >= 0.0f && (w <= 0.0f || h <= 0.0f)) return false;  // inter == 0 -> ovr is 0 or NaN: never > thr
     float inter = __fmul_rn(w, h);
     float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
     return ovr > thr;
@@ -221,10 +264,19 @@ __device__ __forceinline__ float box_area(const float4& b) { return __fmul_rn(__
 
 static constexpr int kNmsChunk = 512;
 
+__device__ __forceinline__ int grid_level(float m, const GridGeom& g) {
+    int l = 0;
+    float c = g.c0 * 2.0f;
+    while (l < g.nlev - 1 && m >= c) { c *= 2.0f; ++l; }
+    return l;
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
 // One CTA per (image, class) segment of the sorted candidates: greedy NMS in sorted order, processed
-// in chunks of 512: (1) every candidate of the chunk is tested against all boxes kept so far,
-// (2) survivors are resolved against each other with a 512x512 bit matrix walked by one warp.
-__global__ void __launch_bounds__(kNmsChunk) hn_det_nms_kernel(DetWs ws, int A, float iou_thr, int nms_mode) {
+// in chunks of 512: (1) every candidate of the chunk is tested against the boxes kept so far that the
+// spatial index says can overlap it, (2) survivors are resolved against each other with a 512x512 bit
+// matrix walked by one warp, which also inserts the newly kept boxes into the index.
+__global__ void __launch_bounds__(kNmsChunk) hn_det_nms_kernel(DetWs ws, int A, float iou_thr, int nms_mode, GridGeom g) {
     __shared__ float4 s_box[kNmsChunk];
     __shared__ float s_area[kNmsChunk];
     __shared__ unsigned long long s_mask[kNmsChunk][kNmsChunk / 64];
@@ -248,15 +300,16 @@ __global__ void __launch_bounds__(kNmsChunk) hn_det_nms_kernel(DetWs ws, int A, 
     if (trick) offset = __fmul_rn((float)cls, __fadd_rn(ordered_to_float(ws.max_coord[n]), 1.0f));
     float4* kept_boxes = ws.kept_boxes + s0;
     uint64_t* kept_keys = ws.kept_keys + s0;
+    int* kept_next = ws.kept_next + s0;
+    int* heads = ws.heads + (size_t)seg * kGridHeads;
     __syncthreads();
 
     for (int c0 = s0; c0 < s1; c0 += kNmsChunk) {
         const int j = c0 + tid;
         const bool have = j < s1;
         float4 b = make_float4(0, 0, 0, 0);
-        uint64_t key = 0;
         if (have) {
-            key = ws.keys[j];
+            uint64_t key = ws.keys[j];
             int a = (int)(key & ((1u << kAnchorBits) - 1));
             b = ws.boxes[(long long)n * A + a];
             if (trick) {
@@ -265,13 +318,44 @@ __global__ void __launch_bounds__(kNmsChunk) hn_det_nms_kernel(DetWs ws, int A, 
             }
         }
         const float area = box_area(b);
-        // (1) against everything kept so far
+        // (1) against the kept boxes that can overlap this one
         const int nk = s_nk;
         bool alive = have;
-        for (int k = 0; k < nk; ++k) {
-            float4 kb = kept_boxes[k];
-            if (alive && iou_gt(kb, box_area(kb), b, area, iou_thr)) alive = false;
-            if ((k & 31) == 31 && !__any_sync(0xffffffffu, alive)) break;
+        if (alive && nk > 0) {
+            if (!g.prune) {
+                for (int k = 0; k < nk && alive; ++k) {
+                    float4 kb = kept_boxes[k];
+                    if (iou_gt(kb, box_area(kb), b, area, iou_thr)) alive = false;
+                }
+            } else {
+                const float wj = b.z - b.x, hj = b.w - b.y;
+                const float cx = 0.5f * (b.x + b.z) - offset, cy = 0.5f * (b.y + b.w) - offset;
+                const int t = grid_level(fmaxf(wj, hj), g);
+                const int l_lo = max(0, t - g.delta), l_hi = min(g.nlev - 1, t + g.delta);
+                for (int l = l_lo; l <= l_hi && alive; ++l) {
+                    const float cl = g.c0 * (float)(1 << l);
+                    const float inv = 1.0f / cl;
+                    const int nx = g.nx[l], ny = g.ny[l];
+                    int x_lo = 0, x_hi = 0, y_lo = 0, y_hi = 0;
+                    if (nx * ny > 1) {
+                        const float rx = 0.5f * fmaxf(wj, 0.0f) + cl + 1.0f, ry = 0.5f * fmaxf(hj, 0.0f) + cl + 1.0f;
+                        x_lo = clampi((int)floorf((cx - rx) * inv), 0, nx - 1);
+                        x_hi = clampi((int)floorf((cx + rx) * inv), 0, nx - 1);
+                        y_lo = clampi((int)floorf((cy - ry) * inv), 0, ny - 1);
+                        y_hi = clampi((int)floorf((cy + ry) * inv), 0, ny - 1);
+                    }
+                    for (int yy = y_lo; yy <= y_hi && alive; ++yy) {
+                        for (int xx = x_lo; xx <= x_hi && alive; ++xx) {
+                            int k = heads[g.base[l] + yy * nx + xx];
+                            while (k >= 0) {
+                                float4 kb = kept_boxes[k];
+                                if (iou_gt(kb, box_area(kb), b, area, iou_thr)) { alive = false; break; }
+                                k = kept_next[k];
+                            }
+                        }
+                    }
+                }
+            }
         }
         s_box[tid] = b;
         s_area[tid] = area;
@@ -309,8 +393,19 @@ __global__ void __launch_bounds__(kNmsChunk) hn_det_nms_kernel(DetWs ws, int A, 
                     if (lane == w) live &= ~(1ull << (i & 63));
                 }
                 if (lane == 0) {
-                    kept_boxes[nkept] = s_box[i];
+                    float4 kb = s_box[i];
+                    kept_boxes[nkept] = kb;
                     kept_keys[nkept] = ws.keys[c0 + i];
+                    if (g.prune) {
+                        const float cx = 0.5f * (kb.x + kb.z) - offset, cy = 0.5f * (kb.y + kb.w) - offset;
+                        const int l = grid_level(fmaxf(kb.z - kb.x, kb.w - kb.y), g);
+                        const float inv = 1.0f / (g.c0 * (float)(1 << l));
+                        int cell = g.base[l];
+                        if (g.nx[l] * g.ny[l] > 1)
+                            cell += clampi((int)floorf(cy * inv), 0, g.ny[l] - 1) * g.nx[l] + clampi((int)floorf(cx * inv), 0, g.nx[l] - 1);
+                        kept_next[nkept] = heads[cell];
+                        heads[cell] = nkept;
+                    }
                 }
                 ++nkept;
             }
@@ -394,6 +489,7 @@ extern "C" int hn_det_decode_nms(const hn_det_desc* d, void* stream) {
     DetWs ws;
     det_layout(d->N, d->A, d->workspace, &ws);
     const long long NA = (long long)d->N * d->A;
+    HN_CHECK_CUDA(cudaMemsetAsync(ws.heads, 0xFF, (size_t)d->N * kMaxCls * kGridHeads * 4, s));
     hn_det_init_kernel<<<hn_cdiv(d->N * kMaxCls, 256), 256, 0, s>>>(ws, d->N);
     HN_CHECK_CUDA(cudaGetLastError());
     hn_det_decode_kernel<<<hn_cdiv(NA, 256), 256, 0, s>>>(d->anchors, d->regression, d->classification, d->pre_boxes, d->N,
@@ -407,7 +503,8 @@ extern "C" int hn_det_decode_nms(const hn_det_desc* d, void* stream) {
     ws.keys_alt = db.Alternate();
     hn_det_segments_kernel<<<hn_cdiv(NA, 256), 256, 0, s>>>(ws.keys, NA, ws.seg_start, ws.seg_end);
     HN_CHECK_CUDA(cudaGetLastError());
-    hn_det_nms_kernel<<<d->N * kMaxCls, kNmsChunk, 0, s>>>(ws, d->A, d->iou_thres, d->nms_mode);
+    GridGeom geom = make_grid(d->img_h, d->img_w, d->iou_thres);
+    hn_det_nms_kernel<<<d->N * kMaxCls, kNmsChunk, 0, s>>>(ws, d->A, d->iou_thres, d->nms_mode, geom);
     HN_CHECK_CUDA(cudaGetLastError());
     hn_det_gather_kernel<<<d->N * kMaxCls, 256, 0, s>>>(ws, d->A, d->out_boxes, d->out_scores, d->out_class, d->out_count);
     HN_CHECK_CUDA(cudaGetLastError());

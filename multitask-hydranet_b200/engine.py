@@ -630,8 +630,8 @@ class Builder:
             x = ob
         oc = dec[-1].conv
         ncls = oc.weight.shape[0]
-        logits = torch.empty((self.B, ncls, x.H * 2, x.W * 2), dtype=torch.float32, device=self.dev)
-        cls_map = torch.empty((self.B, x.H * 2, x.W * 2), dtype=torch.uint8, device=self.dev)
+        logits = torch.zeros((self.B, ncls, x.H * 2, x.W * 2), dtype=torch.float32, device=self.dev)
+        cls_map = torch.zeros((self.B, x.H * 2, x.W * 2), dtype=torch.uint8, device=self.dev)
         self.seg_out("seg.out", x, oc.weight.detach().float(), oc.bias.detach().float(), logits, cls_map)
         self.out["seg"] = logits
         self.out["seg_cls_u8"] = cls_map
@@ -641,8 +641,8 @@ class Builder:
         dh = self.m.detectheader
         na, ncls = dh.num_anchors, dh.num_classes
         total = sum(l.H * l.W for l in levels) * na
-        reg = torch.empty((self.B, total, 4), dtype=torch.float32, device=self.dev)
-        cls = torch.empty((self.B, total, ncls), dtype=torch.float32, device=self.dev)
+        reg = torch.zeros((self.B, total, 4), dtype=torch.float32, device=self.dev)
+        cls = torch.zeros((self.B, total, ncls), dtype=torch.float32, device=self.dev)
         row0 = 0
         for li, lv in enumerate(levels):
             for tname, tower, out_t, k, act in (("reg", dh.regressor, reg, 4, nv.ACT_NONE),
@@ -677,8 +677,8 @@ class Builder:
         self.conv1x1("lane.hidden", fused.interior(), torch.cat(ws, 0), torch.cat(bs, 0), hid, nv.ACT_RELU, "lane")
         ncls = lh.num_classes
         nup, ndown = lh.lane_up_pts_num, lh.lane_down_pts_num
-        pcls = torch.empty((self.B, fh * fw, ncls), dtype=torch.float32, device=self.dev)
-        ploc = torch.empty((self.B, fh * fw, nup + ndown), dtype=torch.float32, device=self.dev)
+        pcls = torch.zeros((self.B, fh * fw, ncls), dtype=torch.float32, device=self.dev)
+        ploc = torch.zeros((self.B, fh * fw, nup + ndown), dtype=torch.float32, device=self.dev)
         for bi, (br, t, col0) in enumerate(((lh.conv_cls_conv, pcls, 0), (lh.conv_up_conv, ploc, ndown), (lh.conv_down_conv, ploc, 0))):
             conv = br[3]
             cout = conv.weight.shape[0]

@@ -42,9 +42,9 @@ def lanes_to_arrays(lanes):
                 ys=np.concatenate([np.array([p.y for p in l.lane], dtype=np.float64) for l in lanes]) if lanes else np.zeros(0, np.float64))
 
 
-def main():
+def main(out_dir=GOLD):
     ref_model, RefLaneCodec = ref_live.import_reference()
-    os.makedirs(GOLD, exist_ok=True)
+    os.makedirs(out_dir, exist_ok=True)
     torch.set_num_threads(8)
     for name, (cfg, H, W) in cfg_variants().items():
         net = ref_model.HydraNet(cfg).eval()
@@ -101,7 +101,7 @@ def main():
         for i, r in enumerate(ref_det):
             gold["det%d_rois" % i], gold["det%d_class_ids" % i], gold["det%d_scores" % i] = r["rois"], r["class_ids"], r["scores"]
         gold.update(lane_gold)
-        np.savez_compressed(os.path.join(GOLD, name + ".npz"), **gold)
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), **gold)
         print(name, "ok:", {k: v.shape for k, v in gold.items() if hasattr(v, "shape") and v.ndim > 0 and not k.startswith("lane")},
               "det kept", [len(r["scores"]) for r in ref_det], "lanes", [len(lane_gold["lane%d_prob" % b]) for b in range(2)])
 
