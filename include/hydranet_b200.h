@@ -128,12 +128,16 @@ typedef struct hn_lanefuse_desc {
     int32_t stride; /* 16 or 32 */
 } hn_lanefuse_desc;
 
-/* Squeeze-excite: x *= sigmoid(W2 relu(W1 mean_hw(x) + b1) + b2), in place (anynet.py:39-47,68-69). */
+/* Squeeze-excite: x *= sigmoid(W2 relu(W1 mean_hw(x) + b1) + b2), in place (anynet.py:39-47,68-69).
+ * Two launches: (pool + FC1 by the last-arriving block of each image), (FC2 + scale).  `counter` must
+ * be zero on first use; the op leaves it zeroed again. */
 typedef struct hn_se_desc {
     hn_view x;
-    float* pooled; /* scratch fp32 [N][C], zeroed by the op */
-    float* scale;  /* scratch fp32 [N][C] */
-    const float *w1, *b1, *w2, *b2; /* w1 [S][C], w2 [C][S] */
+    float* pooled;    /* scratch fp32 [N][ceil(H*W/128)][C] per-chunk partial sums */
+    float* hidden;    /* scratch fp32 [N][S] */
+    int32_t* counter; /* scratch int32 [N] */
+    const float *w1, *b1; /* w1 [S][C] */
+    const float *w2t, *b2; /* w2 transposed: [S][C] */
     int32_t S;
 } hn_se_desc;
 
@@ -216,6 +220,8 @@ int hn_plan_run_range(hn_plan* p, int first, int last, void* stream);
 int hn_plan_graph_capture(hn_plan* p, void* stream); /* instantiate a CUDA graph of the whole plan */
 int hn_plan_graph_launch(hn_plan* p, void* stream);
 
+/* diagnostics: when set (before a conv is prepared), every conv CTA stores 16 int64 globaltimer stamps */
+void hn_conv_set_debug_buffer(void* device_i64);
 int hn_version(void);
 const char* hn_last_error(void);
 int hn_device_sm_count(void);

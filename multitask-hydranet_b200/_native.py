@@ -63,8 +63,8 @@ class LaneFuseDesc(C.Structure):
 
 
 class SeDesc(C.Structure):
-    _fields_ = [("x", View), ("pooled", C.c_void_p), ("scale", C.c_void_p),
-                ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("S", C.c_int32)]
+    _fields_ = [("x", View), ("pooled", C.c_void_p), ("hidden", C.c_void_p), ("counter", C.c_void_p),
+                ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2t", C.c_void_p), ("b2", C.c_void_p), ("S", C.c_int32)]
 
 
 class DetDesc(C.Structure):
@@ -117,6 +117,7 @@ SYMBOLS = {
     "hn_plan_run_range": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "hn_plan_graph_capture": (C.c_int, [_P, _P]),
     "hn_plan_graph_launch": (C.c_int, [_P, _P]),
+    "hn_conv_set_debug_buffer": (None, [_P]),
     "hn_version": (C.c_int, []),
     "hn_last_error": (C.c_char_p, []),
     "hn_device_sm_count": (C.c_int, []),

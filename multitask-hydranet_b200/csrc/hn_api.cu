@@ -95,7 +95,7 @@ extern "C" int hn_plan_add_conv(hn_plan* p, const hn_conv_desc* d) {
 
 static int op_launches(const PlanOp* o) {
     switch (o->kind) {
-        case OP_SE: return 3;
+        case OP_SE: return 2;
         case OP_DET: return hn_det_num_launches(&o->det);
         case OP_LANE: return 1;
         default: return 1;

@@ -14,16 +14,174 @@
 #include "hn_ops.h"
 
 static constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
+static constexpr int kEpiThreads = 128;
 
-__device__ __forceinline__ void store_row_chunk_bf16(bf16* base, const long long* offs, int ndst, int col,
-                                                     const uint32_t (&pk)[8]) {
-    for (int d = 0; d < ndst; ++d) {
-        uint4* dst = reinterpret_cast<uint4*>(base + offs[d] + col);
-        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+__device__ __forceinline__ long long hn_globaltimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void hn_named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void hn_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
+          "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]),
+          "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+template <int NC>
+__device__ __forceinline__ void hn_tmem_ldN(uint32_t taddr, uint32_t (&v)[NC]) {
+    if constexpr (NC == 32) hn_tmem_ld32(taddr, v);
+    else hn_tmem_ld16(taddr, v);
+}
+
+// tile index -> origin
+struct TileOrigin {
+    int n0, img, y0, x0;
+};
+__device__ __forceinline__ TileOrigin tile_origin(const ConvParams& p, int t) {
+    TileOrigin o;
+    int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
+    o.n0 = nt * p.bn;
+    if (p.flat) {
+        o.img = 0; o.y0 = 0; o.x0 = mt * 128;
+    } else {
+        int per_img = p.tiles_x * p.tiles_y;
+        o.img = mt / per_img;
+        int r = mt - o.img * per_img;
+        o.y0 = (r / p.tiles_x) * p.TH;
+        o.x0 = (r % p.tiles_x) * p.TW;
+    }
+    return o;
+}
+
+template <int NC>
+__device__ __forceinline__ void apply_act(float (&f)[NC], int act) {
+    switch (act) {
+        case HN_ACT_RELU:
+#pragma unroll
+            for (int j = 0; j < NC; ++j) f[j] = fmaxf(f[j], 0.0f);
+            break;
+        case HN_ACT_SWISH:
+#pragma unroll
+            for (int j = 0; j < NC; ++j) f[j] = f[j] * hn_sigmoid(f[j]);
+            break;
+        case HN_ACT_ELU:
+#pragma unroll
+            for (int j = 0; j < NC; ++j) f[j] = f[j] > 0.0f ? f[j] : expm1f(f[j]);
+            break;
+        case HN_ACT_SIGMOID:
+#pragma unroll
+            for (int j = 0; j < NC; ++j) f[j] = 1.0f / (1.0f + expf(-f[j]));
+            break;
+        default: break;
     }
 }
 
+// per-row epilogue state
+struct EpiRow {
+    bool valid;
+    int n_i, Y, X;
+    long long off0, roff;
+    int ym1, ym2, xm1, xm2;  // mirrored halo coordinates (INT_MIN when absent)
+};
+static constexpr int kNoCoord = -2147483647;
+
+template <int NC>
+__device__ __forceinline__ void epi_chunk_std(const ConvParams& p, const EpiRow& e, const float* s_bias, int c, int n0,
+                                              uint32_t (&v)[NC]) {
+    const int n = n0 + c;
+    if (!e.valid || n >= p.cout) return;
+    float f[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) f[j] = __uint_as_float(v[j]) + s_bias[c + j];
+    apply_act<NC>(f, p.act);
+    if (p.out_fp32) {
+        float* outf = reinterpret_cast<float*>(p.out) + e.off0;
+#pragma unroll
+        for (int j = 0; j < NC; ++j)
+            if (n + j < p.cout) outf[n + j] = f[j];
+        return;
+    }
+    const int nvec = min(NC / 8, (p.cout - n) / 8);  // 8-channel vectors to store (cout % 8 == 0)
+    if (p.res) {
+        const uint4* r = reinterpret_cast<const uint4*>(p.res + e.roff + n);
+#pragma unroll
+        for (int q = 0; q < NC / 8; ++q) {
+            if (q < nvec) {
+                uint4 rv = r[q];
+                float2 t0 = hn_unpack_bf16x2(rv.x), t1 = hn_unpack_bf16x2(rv.y), t2 = hn_unpack_bf16x2(rv.z), t3 = hn_unpack_bf16x2(rv.w);
+                f[q * 8 + 0] += t0.x; f[q * 8 + 1] += t0.y; f[q * 8 + 2] += t1.x; f[q * 8 + 3] += t1.y;
+                f[q * 8 + 4] += t2.x; f[q * 8 + 5] += t2.y; f[q * 8 + 6] += t3.x; f[q * 8 + 7] += t3.y;
+            }
+        }
+        if (p.res_relu) {
+#pragma unroll
+            for (int j = 0; j < NC; ++j) f[j] = fmaxf(f[j], 0.0f);
+        }
+    }
+    uint4 pk[NC / 8];
+#pragma unroll
+    for (int q = 0; q < NC / 8; ++q)
+        pk[q] = make_uint4(hn_pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]), hn_pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]),
+                           hn_pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]), hn_pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]));
+    bf16* outb = reinterpret_cast<bf16*>(p.out);
+    {
+        uint4* dst = reinterpret_cast<uint4*>(outb + e.off0 + n);
+#pragma unroll
+        for (int q = 0; q < NC / 8; ++q)
+            if (q < nvec) dst[q] = pk[q];
+    }
+    if (p.halo != HN_HALO_NONE) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int yy = a == 0 ? e.Y : (a == 1 ? e.ym1 : e.ym2);
+            if (yy == kNoCoord) continue;
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                const int xx = b == 0 ? e.X : (b == 1 ? e.xm1 : e.xm2);
+                if (xx == kNoCoord || (a == 0 && b == 0)) continue;
+                uint4* dst = reinterpret_cast<uint4*>(outb + (long long)e.n_i * p.osn + (long long)yy * p.osy + (long long)xx * p.osx + n);
+#pragma unroll
+                for (int q = 0; q < NC / 8; ++q)
+                    if (q < nvec) dst[q] = pk[q];
+            }
+        }
+    }
+}
+
+// columns = 4 sub-pixel parities x 8 (n_cls valid): fp32 NCHW logits + fused arg-max
+__device__ __forceinline__ void epi_chunk_segout(const ConvParams& p, const EpiRow& e, const float* s_bias, int c,
+                                                 uint32_t (&v)[16]) {
+    if (!e.valid) return;
+    const int OH = p.H * 2, OW = p.W * 2;
+    float* outf = reinterpret_cast<float*>(p.out);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        int par = (c >> 3) + h;
+        int yy = e.Y * 2 + (par >> 1), xx = e.X * 2 + (par & 1);
+        float best = 0.f;
+        int bi = 0;
+        for (int k = 0; k < p.n_cls; ++k) {
+            float f = __uint_as_float(v[h * 8 + k]) + s_bias[c + h * 8 + k];
+            outf[(((long long)e.n_i * p.n_cls + k) * OH + yy) * OW + xx] = f;
+            if (k == 0 || f > best) { best = f; bi = k; }
+        }
+        if (p.out2) p.out2[((long long)e.n_i * OH + yy) * OW + xx] = (uint8_t)bi;
+    }
+}
+
+// Persistent kernel: every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (m fastest, so
+// concurrently running CTAs share the weight tile in L2).  Shared-memory ring (full/empty mbarriers)
+// between the TMA producer and the MMA issuer; two TMEM accumulators (acc_full/acc_empty) so the
+// epilogue of tile i overlaps the main loop of tile i+1.
 __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -34,25 +192,16 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
     uint8_t* sB = smem + stages * kATileBytes;
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(sB + stages * b_tile_bytes);
     uint64_t* bar_empty = bar_full + stages;
-    uint64_t* bar_acc = bar_empty + stages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 1);
-    float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
+    uint64_t* bar_acc_full = bar_empty + stages;   // [2]
+    uint64_t* bar_acc_empty = bar_acc_full + 2;    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+    float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);  // [2][BN]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n0 = blockIdx.y * BN;
-
-    // tile origin
-    int img = 0, y0 = 0, x0 = 0;
-    if (p.flat) {
-        x0 = blockIdx.x * 128;
-    } else {
-        int per_img = p.tiles_x * p.tiles_y;
-        img = blockIdx.x / per_img;
-        int r = blockIdx.x - img * per_img;
-        y0 = (r / p.tiles_x) * p.TH;
-        x0 = (r % p.tiles_x) * p.TW;
-    }
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    long long* dbg = p.dbg ? p.dbg + (long long)blockIdx.x * 16 : nullptr;
+    if (dbg && threadIdx.x == 0) dbg[0] = hn_globaltimer();
 
     if (warp == 0 && lane == 0) {
         hn_tma_prefetch_desc(&p.tmB);
@@ -61,192 +210,154 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
             hn_mbar_init(&bar_full[s], 1);
             hn_mbar_init(&bar_empty[s], 1);
         }
-        hn_mbar_init(bar_acc, 1);
+        for (int a = 0; a < 2; ++a) {
+            hn_mbar_init(&bar_acc_full[a], 1);
+            hn_mbar_init(&bar_acc_empty[a], kEpiThreads / 32);
+        }
         hn_mbar_fence_init();
     }
     if (warp == 1) {
         hn_tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
         hn_tmem_relinquish();
     }
-    if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < BN; i += 128) s_bias[i] = p.bias ? p.bias[n0 + i] : 0.0f;
-    }
     hn_tc_fence_before();
     __syncthreads();
     hn_tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (dbg && threadIdx.x == 0) dbg[1] = hn_globaltimer();
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
             const uint32_t stage_bytes = (uint32_t)(kATileBytes + b_tile_bytes);
-            const int c_shift = p.grouped ? n0 : 0;
             int s = 0;
             uint32_t ph = 0;
-            for (int k = 0; k < p.num_taps; ++k) {
-                hn_mbar_wait(&bar_empty[s], ph ^ 1);
-                hn_mbar_expect_tx(&bar_full[s], stage_bytes);
-                const hn_tap t = p.taps[k];
-                hn_tma_load_4d(sA + s * kATileBytes, &p.tmA[t.src], &bar_full[s], (int)t.c0 + c_shift, x0 + (int)t.dx,
-                               y0 + (int)t.dy, img);
-                hn_tma_load_2d(sB + s * b_tile_bytes, &p.tmB, &bar_full[s], k * 64, n0);
-                if (++s == stages) { s = 0; ph ^= 1; }
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const TileOrigin o = tile_origin(p, t);
+                const int c_shift = p.grouped ? o.n0 : 0;
+                for (int k = 0; k < p.num_taps; ++k) {
+                    hn_mbar_wait(&bar_empty[s], ph ^ 1);
+                    hn_mbar_expect_tx(&bar_full[s], stage_bytes);
+                    const hn_tap tp = p.taps[k];
+                    hn_tma_load_4d(sA + s * kATileBytes, &p.tmA[tp.src], &bar_full[s], (int)tp.c0 + c_shift, o.x0 + (int)tp.dx,
+                                   o.y0 + (int)tp.dy, o.img);
+                    hn_tma_load_2d(sB + s * b_tile_bytes, &p.tmB, &bar_full[s], k * 64, o.n0);
+                    if (++s == stages) { s = 0; ph ^= 1; }
+                }
+                if (dbg && t == (int)blockIdx.x) dbg[2] = hn_globaltimer();
             }
         }
     } else if (warp == 1) {
         // ------------------------------ MMA issuer ------------------------------
         if (lane == 0) {
             const uint32_t idesc = hn_umma_idesc_bf16(128, BN);
-            int s = 0;
-            uint32_t ph = 0;
-            for (int k = 0; k < p.num_taps; ++k) {
-                hn_mbar_wait(&bar_full[s], ph);
+            int s = 0, a = 0;
+            uint32_t ph = 0, aph = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                hn_mbar_wait(&bar_acc_empty[a], aph ^ 1);  // epilogue has drained this accumulator
                 hn_tc_fence_after();
-                const uint32_t a_addr = hn_smem_u32(sA + s * kATileBytes);
-                const uint32_t b_addr = hn_smem_u32(sB + s * b_tile_bytes);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.acc_stride);
+                for (int k = 0; k < p.num_taps; ++k) {
+                    hn_mbar_wait(&bar_full[s], ph);
+                    hn_tc_fence_after();
+                    if (dbg && t == (int)blockIdx.x && k == 0) dbg[3] = hn_globaltimer();
+                    const uint32_t a_addr = hn_smem_u32(sA + s * kATileBytes);
+                    const uint32_t b_addr = hn_smem_u32(sB + s * b_tile_bytes);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    uint64_t da = hn_umma_desc_sw128(a_addr + kk * 32);
-                    uint64_t db = hn_umma_desc_sw128(b_addr + kk * 32);
-                    hn_umma_bf16(tmem_base, da, db, idesc, (uint32_t)((k | kk) != 0));
+                    for (int kk = 0; kk < 4; ++kk) {
+                        uint64_t da = hn_umma_desc_sw128(a_addr + kk * 32);
+                        uint64_t db = hn_umma_desc_sw128(b_addr + kk * 32);
+                        hn_umma_bf16(d_tmem, da, db, idesc, (uint32_t)((k | kk) != 0));
+                    }
+                    hn_umma_commit(&bar_empty[s]);  // frees the smem slot once these MMAs retire
+                    if (++s == stages) { s = 0; ph ^= 1; }
                 }
-                hn_umma_commit(&bar_empty[s]);  // frees the smem slot once these MMAs retire
-                if (++s == stages) { s = 0; ph ^= 1; }
+                hn_umma_commit(&bar_acc_full[a]);  // accumulator complete
+                if (dbg && t == (int)blockIdx.x) dbg[4] = hn_globaltimer();
+                if (++a == 2) { a = 0; aph ^= 1; }
             }
-            hn_umma_commit(bar_acc);  // accumulator complete
         }
     } else {
-        // ------------------------------ epilogue ------------------------------
+        // ------------------------------ epilogue (warps 2..5) ------------------------------
         const int q = warp & 3;  // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;
-        bool valid;
-        int n_i, Y = 0, X = 0;
-        long long off0, roff;
-        if (p.flat) {
-            long long m = (long long)x0 + row;
-            valid = m < p.flat_m;
-            n_i = (int)(m / p.flat_hw);
-            long long pix = m - (long long)n_i * p.flat_hw;
-            off0 = (long long)n_i * p.osn + pix * p.osx;
-            roff = (long long)n_i * p.rsn + pix * p.rsx;
-        } else {
-            int ty = row / p.TW, tx = row - ty * p.TW;
-            int y = y0 + ty, x = x0 + tx;
-            valid = (y < p.H) && (x < p.W);
-            n_i = img;
-            Y = y * p.oscale + p.ooy;
-            X = x * p.oscale + p.oox;
-            off0 = (long long)n_i * p.osn + (long long)Y * p.osy + (long long)X * p.osx;
-            roff = (long long)n_i * p.rsn + (long long)Y * p.rsy + (long long)X * p.rsx;
-        }
-        // destinations: the pixel itself plus mirrored halo copies
-        long long offs[9];
-        int ndst = 1;
-        offs[0] = off0;
-        if (!p.flat && p.halo != HN_HALO_NONE && valid) {
-            const int OH = p.H * p.oscale, OW = p.W * p.oscale;
-            int ys[3], xs[3], ny = 1, nx = 1;
-            ys[0] = Y;
-            xs[0] = X;
-            if (p.halo == HN_HALO_REFLECT) {
-                if (Y == 1) ys[ny++] = -1;
-                if (Y == OH - 2) ys[ny++] = OH;
-                if (X == 1) xs[nx++] = -1;
-                if (X == OW - 2) xs[nx++] = OW;
+        const int et = threadIdx.x - 64;
+        int a = 0;
+        uint32_t aph = 0;
+        int ntile = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ntile) {
+            const TileOrigin o = tile_origin(p, t);
+            float* bias_s = s_bias + a * BN;
+            for (int i = et; i < BN; i += kEpiThreads) bias_s[i] = p.bias ? p.bias[o.n0 + i] : 0.0f;
+            EpiRow e;
+            e.ym1 = e.ym2 = e.xm1 = e.xm2 = kNoCoord;
+            e.Y = e.X = 0;
+            if (p.flat) {
+                long long m = (long long)o.x0 + row;
+                e.valid = m < p.flat_m;
+                e.n_i = (int)(m / p.flat_hw);
+                long long pix = m - (long long)e.n_i * p.flat_hw;
+                e.off0 = (long long)e.n_i * p.osn + pix * p.osx;
+                e.roff = (long long)e.n_i * p.rsn + pix * p.rsx;
             } else {
-                if (Y == 0) ys[ny++] = -1;
-                if (Y == OH - 1) ys[ny++] = OH;
-                if (X == 0) xs[nx++] = -1;
-                if (X == OW - 1) xs[nx++] = OW;
-            }
-            ndst = 0;
-            for (int a = 0; a < ny; ++a)
-                for (int b = 0; b < nx; ++b)
-                    offs[ndst++] = (long long)n_i * p.osn + (long long)ys[a] * p.osy + (long long)xs[b] * p.osx;
-        }
-
-        hn_mbar_wait(bar_acc, 0);
-        hn_tc_fence_after();
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
-
-        if (p.epi == HN_EPI_SEGOUT) {
-            // columns = 4 sub-pixel parities x 8 (n_cls valid): fp32 NCHW logits + fused argmax
-            const int OH = p.H * 2, OW = p.W * 2;
-            float* outf = reinterpret_cast<float*>(p.out);
-            for (int c = 0; c < BN; c += 16) {
-                uint32_t v[16];
-                hn_tmem_ld16(t_row + c, v);
-                hn_tmem_ld_wait();
-                if (valid) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        int par = (c >> 3) + h;
-                        int yy = Y * 2 + (par >> 1), xx = X * 2 + (par & 1);
-                        float best = 0.f;
-                        int bi = 0;
-                        for (int k = 0; k < p.n_cls; ++k) {
-                            float f = __uint_as_float(v[h * 8 + k]) + s_bias[c + h * 8 + k];
-                            outf[(((long long)n_i * p.n_cls + k) * OH + yy) * OW + xx] = f;
-                            if (k == 0 || f > best) { best = f; bi = k; }
-                        }
-                        if (p.out2) p.out2[((long long)n_i * OH + yy) * OW + xx] = (uint8_t)bi;
-                    }
-                }
-            }
-        } else if (p.out_fp32) {
-            float* outf = reinterpret_cast<float*>(p.out);
-            for (int c = 0; c < BN; c += 16) {
-                uint32_t v[16];
-                hn_tmem_ld16(t_row + c, v);
-                hn_tmem_ld_wait();
-                if (valid) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        int n = n0 + c + j;
-                        if (n < p.cout) outf[off0 + n] = hn_act(__uint_as_float(v[j]) + s_bias[c + j], p.act);
-                    }
-                }
-            }
-        } else {
-            bf16* outb = reinterpret_cast<bf16*>(p.out);
-            for (int c = 0; c < BN; c += 16) {
-                uint32_t v[16];
-                hn_tmem_ld16(t_row + c, v);
-                hn_tmem_ld_wait();
-                const int n = n0 + c;
-                if (valid && n < p.cout) {
-                    float f[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) f[j] = hn_act(__uint_as_float(v[j]) + s_bias[c + j], p.act);
-                    const bool second = (n + 8) < p.cout;
-                    if (p.res) {
-                        const uint4* r = reinterpret_cast<const uint4*>(p.res + roff + n);
-                        uint4 r0 = r[0];
-                        uint4 r1 = second ? r[1] : make_uint4(0, 0, 0, 0);
-                        uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float2 t = hn_unpack_bf16x2(rr[j]);
-                            f[2 * j] += t.x;
-                            f[2 * j + 1] += t.y;
-                        }
-                        if (p.res_relu) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
-                        }
-                    }
-                    uint32_t pk[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) pk[j] = hn_pack_bf16x2(f[2 * j], f[2 * j + 1]);
-                    if (second) {
-                        store_row_chunk_bf16(outb, offs, ndst, n, pk);
+                int ty = row / p.TW, tx = row - ty * p.TW;
+                int y = o.y0 + ty, x = o.x0 + tx;
+                e.valid = (y < p.H) && (x < p.W);
+                e.n_i = o.img;
+                e.Y = y * p.oscale + p.ooy;
+                e.X = x * p.oscale + p.oox;
+                e.off0 = (long long)e.n_i * p.osn + (long long)e.Y * p.osy + (long long)e.X * p.osx;
+                e.roff = (long long)e.n_i * p.rsn + (long long)e.Y * p.rsy + (long long)e.X * p.rsx;
+                if (p.halo != HN_HALO_NONE && p.epi == HN_EPI_STD) {
+                    const int OH = p.H * p.oscale, OW = p.W * p.oscale;
+                    if (p.halo == HN_HALO_REFLECT) {
+                        if (e.Y == 1) e.ym1 = -1;
+                        if (e.Y == OH - 2) e.ym2 = OH;
+                        if (e.X == 1) e.xm1 = -1;
+                        if (e.X == OW - 2) e.xm2 = OW;
                     } else {
-                        for (int d = 0; d < ndst; ++d)
-                            *reinterpret_cast<uint4*>(outb + offs[d] + n) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        if (e.Y == 0) e.ym1 = -1;
+                        if (e.Y == OH - 1) e.ym2 = OH;
+                        if (e.X == 0) e.xm1 = -1;
+                        if (e.X == OW - 1) e.xm2 = OW;
                     }
                 }
             }
+            hn_named_bar_sync(1, kEpiThreads);  // bias staged
+            hn_mbar_wait(&bar_acc_full[a], aph);
+            hn_tc_fence_after();
+            if (dbg && ntile == 0 && et == 0) dbg[5] = hn_globaltimer();
+            const uint32_t t_row = tmem_base + (uint32_t)(a * p.acc_stride) + ((uint32_t)(q * 32) << 16);
+            if (p.epi == HN_EPI_SEGOUT) {
+                for (int c = 0; c < BN; c += 16) {
+                    uint32_t v[16];
+                    hn_tmem_ld16(t_row + c, v);
+                    hn_tmem_ld_wait();
+                    epi_chunk_segout(p, e, bias_s, c, v);
+                }
+            } else {
+                int c = 0;
+                for (; c + 32 <= BN; c += 32) {
+                    uint32_t v[32];
+                    hn_tmem_ld32(t_row + c, v);
+                    hn_tmem_ld_wait();
+                    epi_chunk_std<32>(p, e, bias_s, c, o.n0, v);
+                }
+                if (c < BN) {
+                    uint32_t v[16];
+                    hn_tmem_ld16(t_row + c, v);
+                    hn_tmem_ld_wait();
+                    epi_chunk_std<16>(p, e, bias_s, c, o.n0, v);
+                }
+            }
+            // all TMEM reads of this accumulator are complete: hand it back to the MMA issuer
+            hn_tc_fence_before();
+            __syncwarp();
+            if (lane == 0) hn_mbar_arrive(&bar_acc_empty[a]);
+            if (dbg && ntile == 0 && et == 0) dbg[6] = hn_globaltimer();
+            if (++a == 2) { a = 0; aph ^= 1; }
         }
+        if (dbg && et == 0) dbg[8] = ntile;
     }
 
     hn_tc_fence_before();
@@ -255,6 +366,7 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
         hn_tc_fence_after();
         hn_tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
+    if (dbg && threadIdx.x == 0) dbg[7] = hn_globaltimer();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -314,6 +426,9 @@ static int encode_weight_map(CUtensorMap* tm, const void* w, int rows, int kcols
     return HN_OK;
 }
 
+static void* g_conv_dbg = nullptr;
+extern "C" void hn_conv_set_debug_buffer(void* p) { g_conv_dbg = p; }
+
 static int round_pow2_cols(int bn) {
     int c = 32;
     while (c < bn) c <<= 1;
@@ -348,7 +463,9 @@ int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L) {
     p.cout = d->cout;
     p.bn = d->bn;
     p.stages = d->stages;
-    p.tmem_cols = round_pow2_cols(d->bn);
+    p.acc_stride = round_pow2_cols(d->bn);
+    p.tmem_cols = 2 * p.acc_stride;  // two accumulators: epilogue of tile i overlaps main loop of tile i+1
+    p.dbg = reinterpret_cast<long long*>(g_conv_dbg);
     p.bias = d->bias;
     p.act = d->act;
     p.epi = d->epi;
@@ -394,9 +511,17 @@ int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L) {
     }
     int n_tiles = hn_cdiv(d->cout, d->bn);
     if (d->epi == HN_EPI_SEGOUT) n_tiles = 1;
-    L->grid = dim3((unsigned)m_tiles, (unsigned)n_tiles, 1);
-    L->smem = 1024 + (size_t)d->stages * (kATileBytes + d->bn * 128) + (2 * d->stages + 1) * 8 + 16 + d->bn * 4 + 64;
+    p.m_tiles = m_tiles;
+    p.n_tiles = n_tiles;
+    L->smem = 1024 + (size_t)d->stages * (kATileBytes + d->bn * 128) + (2 * d->stages + 4) * 8 + 16 + 2 * d->bn * 4 + 64;
     HN_REQUIRE(L->smem <= 227 * 1024, "conv needs %zu bytes of shared memory (> 227 KB): lower stages/bn", L->smem);
+    // persistent grid: one CTA per SM, or two when shared memory and TMEM (512 columns) allow it
+    int sms = hn_device_sm_count();
+    if (sms <= 0) sms = 148;
+    int per_sm = (2 * (L->smem + 1024) <= 227 * 1024 && 2 * p.tmem_cols <= 512) ? 2 : 1;
+    long long total = (long long)m_tiles * n_tiles;
+    long long g = (long long)sms * per_sm;
+    L->grid = dim3((unsigned)(total < g ? total : g), 1, 1);
     return HN_OK;
 }
 

@@ -387,98 +387,139 @@ extern "C" int hn_lanefuse_fwd(const hn_lanefuse_desc* d, void* stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// squeeze-excite: pool -> fc -> scale (in place)
+// squeeze-excite, two launches:
+//   1. per (image, pixel chunk): channel sums -> per-chunk partials; the block that arrives last for
+//      its image adds the partials in chunk order (deterministic), runs FC1 (+ReLU) and re-arms the
+//      arrival counter, so no memset is ever needed;
+//   2. per (image, pixel chunk): FC2 (+sigmoid) recomputed per block (it is tiny) -> scale in place.
 // ------------------------------------------------------------------------------------------------
-static constexpr int kSePixPerBlock = 256;
+static constexpr int kSePix = 128;      // pixels per block
+static constexpr int kSeThreads = 512;
 
-__global__ void __launch_bounds__(256) hn_se_pool_kernel(View x, float* __restrict__ pooled) {
-    // block = (image, chunk of pixels); thread = channel vector x pixel lane
-    const int CV = x.C >> 3;
+__global__ void __launch_bounds__(kSeThreads) hn_se_pool_fc1_kernel(View x, float* __restrict__ pooled, float* __restrict__ hidden,
+                                                                    int* __restrict__ counter, int S, float inv_hw,
+                                                                    const float* __restrict__ w1, const float* __restrict__ b1) {
+    extern __shared__ float sm[];  // [lanes][C] partial sums, later mean[C]
+    __shared__ int s_last;
+    const int C = x.C, CV = C >> 3;
     const int n = blockIdx.y;
     const int HW = x.H * x.W;
-    const int p0 = blockIdx.x * kSePixPerBlock;
-    const int p1 = min(p0 + kSePixPerBlock, HW);
-    const int lanes = blockDim.x / CV;  // pixel lanes per block (>=1)
+    const int p0 = blockIdx.x * kSePix, p1 = min(p0 + kSePix, HW);
+    const int lanes = min(blockDim.x / CV, kSePix);
     const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
-    if (pl >= lanes) return;
-    float acc[8];
+    if (pl < lanes) {
+        float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-    for (int px = p0 + pl; px < p1; px += lanes) {
-        int y = px / x.W, xx = px - y * x.W;
-        float f[8];
-        load8(vptr(x, n, y, xx, cv * 8), f);
+        for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+        for (int px = p0 + pl; px < p1; px += lanes) {
+            int y = px / x.W, xx = px - y * x.W;
+            float f[8];
+            load8(vptr(x, n, y, xx, cv * 8), f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sm[pl * C + cv * 8 + j] = acc[j];
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(pooled + (long long)n * x.C + cv * 8 + j, acc[j]);
-}
-
-__global__ void __launch_bounds__(256) hn_se_fc_kernel(const float* __restrict__ pooled, float* __restrict__ scale, int C, int S,
-                                                       float inv_hw, const float* __restrict__ w1, const float* __restrict__ b1,
-                                                       const float* __restrict__ w2, const float* __restrict__ b2) {
-    extern __shared__ float sm[];  // mean[C], hidden[S]
+    __syncthreads();
+    const int nchunk = gridDim.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.0f;
+        for (int l = 0; l < lanes; ++l) a += sm[l * C + c];
+        pooled[((long long)n * nchunk + blockIdx.x) * C + c] = a;  // per-chunk partial: fixed summation order, deterministic
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(counter + n, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
     float* mean = sm;
-    float* hid = sm + C;
-    const int n = blockIdx.x;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = pooled[(long long)n * C + c] * inv_hw;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float* pp = pooled + (long long)n * nchunk * C + c;
+        float a = 0.0f;
+        int k = 0;
+        for (; k + 8 <= nchunk; k += 8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldcg(pp + (long long)(k + j) * C);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a += v[j];
+        }
+        for (; k < nchunk; ++k) a += __ldcg(pp + (long long)k * C);
+        mean[c] = a * inv_hw;
+    }
+    if (threadIdx.x == 0) counter[n] = 0;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     for (int s = warp; s < S; s += nw) {
-        float a = 0.0f;
-        for (int c = lane; c < C; c += 32) a = fmaf(w1[(long long)s * C + c], mean[c], a);
+        const float* wr = w1 + (long long)s * C;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        int c = lane;
+        for (; c + 96 < C; c += 128) {
+            a0 = fmaf(__ldg(wr + c), mean[c], a0);
+            a1 = fmaf(__ldg(wr + c + 32), mean[c + 32], a1);
+            a2 = fmaf(__ldg(wr + c + 64), mean[c + 64], a2);
+            a3 = fmaf(__ldg(wr + c + 96), mean[c + 96], a3);
+        }
+        for (; c < C; c += 32) a0 = fmaf(__ldg(wr + c), mean[c], a0);
+        float a = (a0 + a1) + (a2 + a3);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) hid[s] = fmaxf(a + b1[s], 0.0f);
-    }
-    __syncthreads();
-    for (int c = warp; c < C; c += nw) {
-        float a = 0.0f;
-        for (int s = lane; s < S; s += 32) a = fmaf(w2[(long long)c * S + s], hid[s], a);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) scale[(long long)n * C + c] = 1.0f / (1.0f + expf(-(a + b2[c])));
+        if (lane == 0) hidden[(long long)n * S + s] = fmaxf(a + b1[s], 0.0f);
     }
 }
 
-__global__ void hn_se_scale_kernel(View x, const float* __restrict__ scale) {
-    const int CV = x.C >> 3;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)x.N * x.H * x.W * CV;
-    if (idx >= total) return;
-    int cv = (int)(idx % CV);
-    long long t = idx / CV;
-    int xx = (int)(t % x.W);
-    t /= x.W;
-    int y = (int)(t % x.H);
-    int n = (int)(t / x.H);
-    bf16* p = const_cast<bf16*>(vptr(x, n, y, xx, cv * 8));
-    float f[8];
-    load8(p, f);
-    const float4* s4 = reinterpret_cast<const float4*>(scale + (long long)n * x.C + cv * 8);
-    float4 s0 = s4[0], s1 = s4[1];
-    f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
-    f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
-    store8(p, f);
+__global__ void __launch_bounds__(kSeThreads) hn_se_fc2_scale_kernel(View x, const float* __restrict__ hidden, int S,
+                                                                     const float* __restrict__ w2t, const float* __restrict__ b2) {
+    extern __shared__ float sm[];  // hid[S], scale[C]
+    float* hid = sm;
+    float* scale = sm + S;
+    const int C = x.C, CV = C >> 3;
+    const int n = blockIdx.y;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) hid[s] = hidden[(long long)n * S + s];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a0 = 0.0f, a1 = 0.0f;
+        int s = 0;
+        for (; s + 1 < S; s += 2) {
+            a0 = fmaf(__ldg(w2t + (long long)s * C + c), hid[s], a0);
+            a1 = fmaf(__ldg(w2t + (long long)(s + 1) * C + c), hid[s + 1], a1);
+        }
+        if (s < S) a0 = fmaf(__ldg(w2t + (long long)s * C + c), hid[s], a0);
+        scale[c] = 1.0f / (1.0f + expf(-(a0 + a1 + b2[c])));
+    }
+    __syncthreads();
+    const int HW = x.H * x.W;
+    const int p0 = blockIdx.x * kSePix, p1 = min(p0 + kSePix, HW);
+    for (int it = threadIdx.x; it < (p1 - p0) * CV; it += blockDim.x) {
+        int cv = it % CV, px = p0 + it / CV;
+        int y = px / x.W, xx = px - y * x.W;
+        bf16* p = const_cast<bf16*>(vptr(x, n, y, xx, cv * 8));
+        float f[8];
+        load8(p, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= scale[cv * 8 + j];
+        store8(p, f);
+    }
 }
 
 extern "C" int hn_se_fwd(const hn_se_desc* d, void* stream) {
-    HN_REQUIRE(d && d->pooled && d->scale && d->w1 && d->b1 && d->w2 && d->b2 && d->S >= 1, "se: bad descriptor");
+    HN_REQUIRE(d && d->pooled && d->hidden && d->counter && d->w1 && d->b1 && d->w2t && d->b2 && d->S >= 1, "se: bad descriptor");
     if (int rc = check_view(d->x, "se.x")) return rc;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const int C = d->x.C, CV = C / 8, HW = d->x.H * d->x.W;
-    HN_REQUIRE(CV <= 256, "se: C=%d too wide", C);
-    HN_CHECK_CUDA(cudaMemsetAsync(d->pooled, 0, sizeof(float) * (size_t)d->x.N * C, s));
-    int threads = (256 / CV) * CV;
-    dim3 grid(hn_cdiv(HW, kSePixPerBlock), d->x.N);
-    hn_se_pool_kernel<<<grid, threads, 0, s>>>(to_view(d->x), d->pooled);
+    HN_REQUIRE(CV <= kSeThreads, "se: C=%d too wide", C);
+    dim3 grid(hn_cdiv(HW, kSePix), d->x.N);
+    int lanes = kSeThreads / CV;
+    if (lanes > kSePix) lanes = kSePix;
+    size_t smem1 = (size_t)lanes * C * sizeof(float);
+    if (smem1 < (size_t)C * sizeof(float)) smem1 = (size_t)C * sizeof(float);
+    HN_REQUIRE(smem1 <= 48 * 1024, "se: shared memory");
+    hn_se_pool_fc1_kernel<<<grid, kSeThreads, smem1, s>>>(to_view(d->x), d->pooled, d->hidden, d->counter, d->S, 1.0f / (float)HW,
+                                                         d->w1, d->b1);
     HN_CHECK_CUDA(cudaGetLastError());
-    hn_se_fc_kernel<<<d->x.N, 256, (C + d->S) * sizeof(float), s>>>(d->pooled, d->scale, C, d->S, 1.0f / (float)HW, d->w1, d->b1,
-                                                                   d->w2, d->b2);
-    HN_CHECK_CUDA(cudaGetLastError());
-    long long total = (long long)d->x.N * HW * CV;
-    hn_se_scale_kernel<<<hn_cdiv(total, 256), 256, 0, s>>>(to_view(d->x), d->scale);
+    hn_se_fc2_scale_kernel<<<grid, kSeThreads, (size_t)(C + d->S) * sizeof(float), s>>>(to_view(d->x), d->hidden, d->S, d->w2t, d->b2);
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }

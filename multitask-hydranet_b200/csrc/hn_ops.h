@@ -7,6 +7,8 @@ struct alignas(64) ConvParams {
     CUtensorMap tmB;
     int flat, TH, TW, n_img, H, W, tiles_x, tiles_y, flat_hw, flat_m;
     int num_taps, cout, bn, stages, tmem_cols;
+    int m_tiles, n_tiles, acc_stride;
+    long long* dbg;  // optional per-CTA timestamps (globaltimer ns), 16 slots per CTA
     const float* bias;
     int act, epi;
     void* out;

@@ -197,7 +197,8 @@ __global__ void hn_det_decode_kernel(const float* __restrict__ anchors, const fl
                                      const float* __restrict__ cls, const float* __restrict__ pre_boxes, int N, int A,
                                      int ncls, float wmax, float hmax, float thr, DetWs ws) {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)N * A) return;
+    const bool valid = idx < (long long)N * A;
+    if (!valid) idx = (long long)N * A - 1;
     int n = (int)(idx / A), a = (int)(idx - (long long)n * A);
     const float* c = cls + idx * ncls;
     float best = c[0];
@@ -227,17 +228,32 @@ __global__ void hn_det_decode_kernel(const float* __restrict__ anchors, const fl
         box.z = fminf(__fadd_rn(xc, hw), wmax);  // xmax
         box.w = fminf(__fadd_rn(yc, hh), hmax);  // ymax
     }
-    ws.boxes[idx] = box;
-    ws.scores[idx] = best;
+    const bool cand = valid && best > thr;
     uint64_t key = ~0ull;
-    if (best > thr) {
+    int ord = float_to_ordered(-INFINITY);
+    if (cand) {
         key = ((uint64_t)n << kImgShift) | ((uint64_t)bi << kClsShift) | ((uint64_t)float_desc_key(best) << kScoreShift) |
               (uint64_t)a;
-        atomicAdd(ws.n_cand + n, 1);
-        float m = fmaxf(fmaxf(box.x, box.y), fmaxf(box.z, box.w));
-        atomicMax(ws.max_coord + n, float_to_ordered(m));
+        ord = float_to_ordered(fmaxf(fmaxf(box.x, box.y), fmaxf(box.z, box.w)));
     }
-    ws.keys[idx] = key;
+    if (valid) {
+        ws.boxes[idx] = box;
+        ws.scores[idx] = best;
+        ws.keys[idx] = key;
+    }
+    // per-image candidate count and max coordinate: one atomic per warp when the warp sits in one image
+    const int n0 = __shfl_sync(0xffffffffu, n, 0);
+    const unsigned m = __ballot_sync(0xffffffffu, cand);
+    if (__all_sync(0xffffffffu, n == n0)) {
+        int wmaxo = __reduce_max_sync(0xffffffffu, ord);
+        if ((threadIdx.x & 31) == 0 && m) {
+            atomicAdd(ws.n_cand + n0, __popc(m));
+            atomicMax(ws.max_coord + n0, wmaxo);
+        }
+    } else if (cand) {
+        atomicAdd(ws.n_cand + n, 1);
+        atomicMax(ws.max_coord + n, ord);
+    }
 }
 
 __global__ void hn_det_segments_kernel(const uint64_t* __restrict__ keys, long long total, int* seg_start, int* seg_end) {
@@ -281,7 +297,8 @@ __global__ void __launch_bounds__(kNmsChunk) hn_det_nms_kernel(DetWs ws, int A, 
     __shared__ float s_area[kNmsChunk];
     __shared__ unsigned long long s_mask[kNmsChunk][kNmsChunk / 64];
     __shared__ unsigned long long s_alive[kNmsChunk / 64];
-    __shared__ int s_nk;
+    __shared__ unsigned short s_keptlist[kNmsChunk];
+    __shared__ int s_nk, s_new;
     const int seg = blockIdx.x;
     const int n = seg / kMaxCls, cls = seg % kMaxCls;
     const int s0 = ws.seg_start[seg], s1 = ws.seg_end[seg];
@@ -377,39 +394,47 @@ __global__ void __launch_bounds__(kNmsChunk) hn_det_nms_kernel(DetWs ws, int A, 
         }
         __syncthreads();
         if (tid < 32) {
-            // lane w (< 8) owns word w of the live set; walk the live boxes in order
+            // lane w (< 8) owns word w of the live set; walk the live boxes in order (shared memory only)
             const int lane = tid;
             unsigned long long live = lane < kNmsChunk / 64 ? s_alive[lane] : 0ull;
-            int nkept = s_nk;
+            int nnew = 0;
             while (true) {
                 unsigned nz = __ballot_sync(0xffffffffu, live != 0ull);
                 if (nz == 0) break;
                 int w = __ffs(nz) - 1;
                 unsigned long long lw = __shfl_sync(0xffffffffu, live, w);
                 int i = w * 64 + __ffsll((long long)lw) - 1;
-                // keep box i, drop what it suppresses
                 if (lane < kNmsChunk / 64) {
                     live &= ~s_mask[i][lane];
                     if (lane == w) live &= ~(1ull << (i & 63));
                 }
-                if (lane == 0) {
-                    float4 kb = s_box[i];
-                    kept_boxes[nkept] = kb;
-                    kept_keys[nkept] = ws.keys[c0 + i];
-                    if (g.prune) {
-                        const float cx = 0.5f * (kb.x + kb.z) - offset, cy = 0.5f * (kb.y + kb.w) - offset;
-                        const int l = grid_level(fmaxf(kb.z - kb.x, kb.w - kb.y), g);
-                        const float inv = 1.0f / (g.c0 * (float)(1 << l));
-                        int cell = g.base[l];
-                        if (g.nx[l] * g.ny[l] > 1)
-                            cell += clampi((int)floorf(cy * inv), 0, g.ny[l] - 1) * g.nx[l] + clampi((int)floorf(cx * inv), 0, g.nx[l] - 1);
-                        kept_next[nkept] = heads[cell];
-                        heads[cell] = nkept;
-                    }
-                }
-                ++nkept;
+                if (lane == 0) s_keptlist[nnew] = (unsigned short)i;
+                ++nnew;
             }
-            if (lane == 0) s_nk = nkept;
+            if (lane == 0) s_new = nnew;
+        }
+        __syncthreads();
+        // publish the newly kept boxes (in order) and insert them into the spatial index, in parallel
+        {
+            const int nk0 = s_nk, nnew = s_new;
+            if (tid < nnew) {
+                const int i = s_keptlist[tid];
+                const int slot = nk0 + tid;
+                float4 kb = s_box[i];
+                kept_boxes[slot] = kb;
+                kept_keys[slot] = ws.keys[c0 + i];
+                if (g.prune) {
+                    const float cx = 0.5f * (kb.x + kb.z) - offset, cy = 0.5f * (kb.y + kb.w) - offset;
+                    const int l = grid_level(fmaxf(kb.z - kb.x, kb.w - kb.y), g);
+                    const float inv = 1.0f / (g.c0 * (float)(1 << l));
+                    int cell = g.base[l];
+                    if (g.nx[l] * g.ny[l] > 1)
+                        cell += clampi((int)floorf(cy * inv), 0, g.ny[l] - 1) * g.nx[l] + clampi((int)floorf(cx * inv), 0, g.nx[l] - 1);
+                    kept_next[slot] = atomicExch(&heads[cell], slot);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) s_nk = nk0 + nnew;
         }
         __syncthreads();
     }

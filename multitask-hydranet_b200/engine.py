@@ -217,15 +217,16 @@ class LaneFuseSpec:
 
 
 class SeSpec:
-    kind, launches, group = "se", 3, "backbone"
+    kind, launches, group = "se", 2, "backbone"
 
-    def __init__(self, name, x, pooled, scale, w1, b1, w2, b2):
-        self.name, self.x, self.pooled, self.scale, self.w1, self.b1, self.w2, self.b2 = name, x, pooled, scale, w1, b1, w2, b2
+    def __init__(self, name, x, pooled, hidden, counter, w1, b1, w2t, b2):
+        self.name, self.x, self.pooled, self.hidden, self.counter = name, x, pooled, hidden, counter
+        self.w1, self.b1, self.w2t, self.b2 = w1, b1, w2t, b2
         self.macs = x.N * 2 * w1.shape[0] * w1.shape[1]
 
     def to_desc(self):
-        return nv.SeDesc(self.x.to_c(), self.pooled.data_ptr(), self.scale.data_ptr(), self.w1.data_ptr(), self.b1.data_ptr(),
-                         self.w2.data_ptr(), self.b2.data_ptr(), self.w1.shape[0])
+        return nv.SeDesc(self.x.to_c(), self.pooled.data_ptr(), self.hidden.data_ptr(), self.counter.data_ptr(),
+                         self.w1.data_ptr(), self.b1.data_ptr(), self.w2t.data_ptr(), self.b2.data_ptr(), self.w1.shape[0])
 
     def add_to(self, plan):
         nv.check(nv.lib.hn_plan_add_se(plan, self.to_desc()))
@@ -384,11 +385,12 @@ class Builder:
                 # squeeze-excite (in place)
                 if blk.se is not None:
                     S = blk.se[1].weight.shape[0]
-                    pooled = torch.zeros((B, mid), dtype=torch.float32, device=self.dev)
-                    scale = torch.zeros((B, mid), dtype=torch.float32, device=self.dev)
-                    self.ops.append(SeSpec(nm + ".se", g.interior(), pooled, scale,
+                    pooled = torch.zeros((B, (Ho * Wo + 127) // 128, mid), dtype=torch.float32, device=self.dev)
+                    hidden = torch.zeros((B, S), dtype=torch.float32, device=self.dev)
+                    counter = torch.zeros((B,), dtype=torch.int32, device=self.dev)
+                    self.ops.append(SeSpec(nm + ".se", g.interior(), pooled, hidden, counter,
                                            self.f32(blk.se[1].weight.reshape(S, mid)), self.f32(blk.se[1].bias),
-                                           self.f32(blk.se[3].weight.reshape(mid, S)), self.f32(blk.se[3].bias)))
+                                           self.f32(blk.se[3].weight.reshape(mid, S).t()), self.f32(blk.se[3].bias)))
                 # shortcut
                 if blk.shortcut is not None:
                     ws, bs = fold_bn(blk.shortcut[0].weight, None, blk.shortcut[1])

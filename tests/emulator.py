@@ -188,7 +188,7 @@ def run_se(ss):
     x = ss.x.torch_view()
     m = x.float().mean(dim=(1, 2))
     h = F.relu(m @ ss.w1.t() + ss.b1)
-    s = torch.sigmoid(h @ ss.w2.t() + ss.b2)
+    s = torch.sigmoid(h @ ss.w2t + ss.b2)
     x.copy_((x.float() * s[:, None, None, :]).to(x.dtype))
 
 
