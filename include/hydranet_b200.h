@@ -222,6 +222,7 @@ int hn_plan_graph_launch(hn_plan* p, void* stream);
 
 /* diagnostics: when set (before a conv is prepared), every conv CTA stores 16 int64 globaltimer stamps */
 void hn_conv_set_debug_buffer(void* device_i64);
+void hn_det_set_debug_buffer(void* device_i64); /* [N*16][8] int64 cycle counters of the NMS kernel */
 int hn_version(void);
 const char* hn_last_error(void);
 int hn_device_sm_count(void);

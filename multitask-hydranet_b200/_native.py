@@ -118,6 +118,7 @@ SYMBOLS = {
     "hn_plan_graph_capture": (C.c_int, [_P, _P]),
     "hn_plan_graph_launch": (C.c_int, [_P, _P]),
     "hn_conv_set_debug_buffer": (None, [_P]),
+    "hn_det_set_debug_buffer": (None, [_P]),
     "hn_version": (C.c_int, []),
     "hn_last_error": (C.c_char_p, []),
     "hn_device_sm_count": (C.c_int, []),

@@ -110,6 +110,19 @@ __device__ __forceinline__ void hn_tma_load_4d(void* dst, const void* tmap, uint
         : "memory");
 }
 
+__device__ __forceinline__ void hn_tma_store_4d(const void* tmap, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"((uint64_t)tmap),
+                 "r"(hn_smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void hn_tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void hn_tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void hn_tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void hn_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ---- tcgen05 / TMEM ----
 __device__ __forceinline__ void hn_tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(hn_smem_u32(dst_smem)),
@@ -174,7 +187,7 @@ __device__ __forceinline__ uint32_t hn_umma_idesc_bf16(int M, int N) {
 }
 
 // ---- numerics ----
-__device__ __forceinline__ float hn_sigmoid(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float hn_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float hn_act(float x, int act) {
     switch (act) {
         case HN_ACT_RELU: return fmaxf(x, 0.0f);

@@ -75,7 +75,7 @@ __device__ __forceinline__ void apply_act(float (&f)[NC], int act) {
             break;
         case HN_ACT_ELU:
 #pragma unroll
-            for (int j = 0; j < NC; ++j) f[j] = f[j] > 0.0f ? f[j] : expm1f(f[j]);
+            for (int j = 0; j < NC; ++j) f[j] = f[j] > 0.0f ? f[j] : __expf(f[j]) - 1.0f;
             break;
         case HN_ACT_SIGMOID:
 #pragma unroll
@@ -94,9 +94,11 @@ struct EpiRow {
 };
 static constexpr int kNoCoord = -2147483647;
 
+// `stage_row`: this thread's 128-byte row of the shared-memory staging tile (nullptr = direct global stores);
+// 16-byte chunk j of the row lives at chunk (j ^ (row & 7)) -- the 128B swizzle the output tensor map expects.
 template <int NC>
 __device__ __forceinline__ void epi_chunk_std(const ConvParams& p, const EpiRow& e, const float* s_bias, int c, int n0,
-                                              uint32_t (&v)[NC]) {
+                                              uint32_t (&v)[NC], uint8_t* stage_row, int row) {
     const int n = n0 + c;
     if (!e.valid || n >= p.cout) return;
     float f[NC];
@@ -133,7 +135,12 @@ __device__ __forceinline__ void epi_chunk_std(const ConvParams& p, const EpiRow&
         pk[q] = make_uint4(hn_pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]), hn_pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]),
                            hn_pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]), hn_pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]));
     bf16* outb = reinterpret_cast<bf16*>(p.out);
-    {
+    if (stage_row) {
+        const int j0 = (c & 63) >> 3;
+#pragma unroll
+        for (int q = 0; q < NC / 8; ++q)
+            *reinterpret_cast<uint4*>(stage_row + (((j0 + q) ^ (row & 7)) << 4)) = pk[q];
+    } else {
         uint4* dst = reinterpret_cast<uint4*>(outb + e.off0 + n);
 #pragma unroll
         for (int q = 0; q < NC / 8; ++q)
@@ -157,24 +164,28 @@ __device__ __forceinline__ void epi_chunk_std(const ConvParams& p, const EpiRow&
     }
 }
 
-// columns = 4 sub-pixel parities x 8 (n_cls valid): fp32 NCHW logits + fused arg-max
-__device__ __forceinline__ void epi_chunk_segout(const ConvParams& p, const EpiRow& e, const float* s_bias, int c,
-                                                 uint32_t (&v)[16]) {
+// columns = 4 sub-pixel parities x 8 (n_cls valid): fp32 NCHW logits + fused arg-max.  The two x-parities of
+// a class are adjacent in memory: one float2 (uchar2 for the class map) per (class, y-parity).
+__device__ __forceinline__ void epi_segout(const ConvParams& p, const EpiRow& e, const float* s_bias, uint32_t (&v)[32]) {
     if (!e.valid) return;
     const int OH = p.H * 2, OW = p.W * 2;
     float* outf = reinterpret_cast<float*>(p.out);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        int par = (c >> 3) + h;
-        int yy = e.Y * 2 + (par >> 1), xx = e.X * 2 + (par & 1);
-        float best = 0.f;
-        int bi = 0;
-        for (int k = 0; k < p.n_cls; ++k) {
-            float f = __uint_as_float(v[h * 8 + k]) + s_bias[c + h * 8 + k];
-            outf[(((long long)e.n_i * p.n_cls + k) * OH + yy) * OW + xx] = f;
-            if (k == 0 || f > best) { best = f; bi = k; }
+    for (int py = 0; py < 2; ++py) {
+        const int yy = e.Y * 2 + py, xx = e.X * 2;
+        float b0 = 0.f, b1 = 0.f;
+        int i0 = 0, i1 = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (k < p.n_cls) {
+                float f0 = __uint_as_float(v[(py * 2 + 0) * 8 + k]) + s_bias[(py * 2 + 0) * 8 + k];
+                float f1 = __uint_as_float(v[(py * 2 + 1) * 8 + k]) + s_bias[(py * 2 + 1) * 8 + k];
+                *reinterpret_cast<float2*>(outf + (((long long)e.n_i * p.n_cls + k) * OH + yy) * OW + xx) = make_float2(f0, f1);
+                if (k == 0 || f0 > b0) { b0 = f0; i0 = k; }
+                if (k == 0 || f1 > b1) { b1 = f1; i1 = k; }
+            }
         }
-        if (p.out2) p.out2[((long long)e.n_i * OH + yy) * OW + xx] = (uint8_t)bi;
+        if (p.out2) *reinterpret_cast<uchar2*>(p.out2 + ((long long)e.n_i * OH + yy) * OW + xx) = make_uchar2((uint8_t)i0, (uint8_t)i1);
     }
 }
 
@@ -190,7 +201,8 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
     const int b_tile_bytes = BN * 128;
     uint8_t* sA = smem;
     uint8_t* sB = smem + stages * kATileBytes;
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(sB + stages * b_tile_bytes);
+    uint8_t* sO = sB + stages * b_tile_bytes;  // n_staging x 16 KB output staging (1024-byte aligned)
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(sO + p.n_staging * kATileBytes);
     uint64_t* bar_empty = bar_full + stages;
     uint64_t* bar_acc_full = bar_empty + stages;   // [2]
     uint64_t* bar_acc_empty = bar_acc_full + 2;    // [2]
@@ -206,6 +218,7 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
     if (warp == 0 && lane == 0) {
         hn_tma_prefetch_desc(&p.tmB);
         hn_tma_prefetch_desc(&p.tmA[0]);
+        if (p.n_staging) hn_tma_prefetch_desc(&p.tmO);
         for (int s = 0; s < stages; ++s) {
             hn_mbar_init(&bar_full[s], 1);
             hn_mbar_init(&bar_empty[s], 1);
@@ -284,7 +297,7 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
         const int et = threadIdx.x - 64;
         int a = 0;
         uint32_t aph = 0;
-        int ntile = 0;
+        int ntile = 0, st_count = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ntile) {
             const TileOrigin o = tile_origin(p, t);
             float* bias_s = s_bias + a * BN;
@@ -329,11 +342,41 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
             if (dbg && ntile == 0 && et == 0) dbg[5] = hn_globaltimer();
             const uint32_t t_row = tmem_base + (uint32_t)(a * p.acc_stride) + ((uint32_t)(q * 32) << 16);
             if (p.epi == HN_EPI_SEGOUT) {
-                for (int c = 0; c < BN; c += 16) {
-                    uint32_t v[16];
-                    hn_tmem_ld16(t_row + c, v);
-                    hn_tmem_ld_wait();
-                    epi_chunk_segout(p, e, bias_s, c, v);
+                uint32_t v[32];
+                hn_tmem_ld32(t_row, v);
+                hn_tmem_ld_wait();
+                epi_segout(p, e, bias_s, v);
+            } else if (p.n_staging) {
+                // 64-channel slabs: registers -> swizzled shared-memory tile -> one TMA store per slab
+                for (int c = 0; c < BN; c += 64) {
+                    uint8_t* slab = sO + (st_count % p.n_staging) * kATileBytes;
+                    if (et == 0) {
+                        if (p.n_staging == 2) hn_tma_store_wait_read<1>(); else hn_tma_store_wait_read<0>();
+                    }
+                    hn_named_bar_sync(2, kEpiThreads);  // slab is free again
+                    uint8_t* stage_row = slab + row * 128;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int cc = c + h * 32;
+                        if (cc + 32 <= BN) {
+                            uint32_t v[32];
+                            hn_tmem_ld32(t_row + cc, v);
+                            hn_tmem_ld_wait();
+                            epi_chunk_std<32>(p, e, bias_s, cc, o.n0, v, stage_row, row);
+                        } else if (cc + 16 <= BN) {
+                            uint32_t v[16];
+                            hn_tmem_ld16(t_row + cc, v);
+                            hn_tmem_ld_wait();
+                            epi_chunk_std<16>(p, e, bias_s, cc, o.n0, v, stage_row, row);
+                        }
+                    }
+                    hn_fence_proxy_async();
+                    hn_named_bar_sync(3, kEpiThreads);  // slab fully written
+                    if (et == 0) {
+                        hn_tma_store_4d(&p.tmO, slab, o.n0 + c, o.x0, o.y0, o.img);
+                        hn_tma_store_commit();
+                    }
+                    ++st_count;
                 }
             } else {
                 int c = 0;
@@ -341,13 +384,13 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
                     uint32_t v[32];
                     hn_tmem_ld32(t_row + c, v);
                     hn_tmem_ld_wait();
-                    epi_chunk_std<32>(p, e, bias_s, c, o.n0, v);
+                    epi_chunk_std<32>(p, e, bias_s, c, o.n0, v, nullptr, row);
                 }
                 if (c < BN) {
                     uint32_t v[16];
                     hn_tmem_ld16(t_row + c, v);
                     hn_tmem_ld_wait();
-                    epi_chunk_std<16>(p, e, bias_s, c, o.n0, v);
+                    epi_chunk_std<16>(p, e, bias_s, c, o.n0, v, nullptr, row);
                 }
             }
             // all TMEM reads of this accumulator are complete: hand it back to the MMA issuer
@@ -357,6 +400,7 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
             if (dbg && ntile == 0 && et == 0) dbg[6] = hn_globaltimer();
             if (++a == 2) { a = 0; aph ^= 1; }
         }
+        if (p.n_staging && et == 0) hn_tma_store_wait_all();  // shared memory must outlive the bulk stores
         if (dbg && et == 0) dbg[8] = ntile;
     }
 
@@ -513,7 +557,27 @@ int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L) {
     if (d->epi == HN_EPI_SEGOUT) n_tiles = 1;
     p.m_tiles = m_tiles;
     p.n_tiles = n_tiles;
-    L->smem = 1024 + (size_t)d->stages * (kATileBytes + d->bn * 128) + (2 * d->stages + 4) * 8 + 16 + 2 * d->bn * 4 + 64;
+    const size_t base_smem = 1024 + (size_t)d->stages * (kATileBytes + d->bn * 128) + (2 * d->stages + 4) * 8 + 16 + 2 * d->bn * 4 + 64;
+    // bf16 outputs leave through shared memory + TMA store (coalesced, clipped by the tensor map) when the
+    // 64-channel slabs of an N tile never spill into the next tile's channels
+    p.n_staging = 0;
+    bool tma_out = d->epi == HN_EPI_STD && !d->out_fp32 && (n_tiles == 1 || d->bn % 64 == 0) &&
+                   (!d->flat || d->out_stride_n == (int64_t)d->flat_hw * d->out_stride_x);
+    if (tma_out && base_smem + kATileBytes <= 227 * 1024) {
+        p.n_staging = (base_smem + 2 * kATileBytes <= 227 * 1024) ? 2 : 1;
+        hn_view ov;
+        if (d->flat) {
+            ov.ptr = d->out; ov.N = 1; ov.H = 1; ov.W = p.flat_m; ov.C = d->cout;
+            ov.stride_n = 0; ov.stride_y = 0; ov.stride_x = d->out_stride_x;
+        } else {
+            ov.ptr = reinterpret_cast<const bf16*>(d->out) + (int64_t)p.ooy * p.osy + (int64_t)p.oox * p.osx;
+            ov.N = p.n_img; ov.H = p.H; ov.W = p.W; ov.C = d->cout;
+            ov.stride_n = p.osn; ov.stride_y = p.osy * p.oscale; ov.stride_x = p.osx * p.oscale;
+        }
+        int rc2 = encode_view_map(&p.tmO, ov, TW, TH);
+        if (rc2) return rc2;
+    }
+    L->smem = base_smem + (size_t)p.n_staging * kATileBytes;
     HN_REQUIRE(L->smem <= 227 * 1024, "conv needs %zu bytes of shared memory (> 227 KB): lower stages/bn", L->smem);
     // persistent grid: one CTA per SM, or two when shared memory and TMEM (512 columns) allow it
     int sms = hn_device_sm_count();

@@ -454,19 +454,24 @@ __global__ void __launch_bounds__(kSeThreads) hn_se_pool_fc1_kernel(View x, floa
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     for (int s = warp; s < S; s += nw) {
         const float* wr = w1 + (long long)s * C;
-        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-        int c = lane;
-        for (; c + 96 < C; c += 128) {
-            a0 = fmaf(__ldg(wr + c), mean[c], a0);
-            a1 = fmaf(__ldg(wr + c + 32), mean[c + 32], a1);
-            a2 = fmaf(__ldg(wr + c + 64), mean[c + 64], a2);
-            a3 = fmaf(__ldg(wr + c + 96), mean[c + 96], a3);
-        }
-        for (; c < C; c += 32) a0 = fmaf(__ldg(wr + c), mean[c], a0);
-        float a = (a0 + a1) + (a2 + a3);
+        // all loads of a batch are issued before the first use: one L2 round trip per 8 x 32 channels
+        float acc = 0.0f;
+        for (int c0 = 0; c0 < C; c0 += 256) {
+            float wv[8];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) hidden[(long long)n * S + s] = fmaxf(a + b1[s], 0.0f);
+            for (int j = 0; j < 8; ++j) {
+                int c = c0 + j * 32 + lane;
+                wv[j] = c < C ? __ldg(wr + c) : 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int c = c0 + j * 32 + lane;
+                if (c < C) acc = fmaf(wv[j], mean[c], acc);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) hidden[(long long)n * S + s] = fmaxf(acc + b1[s], 0.0f);
     }
 }
 
@@ -480,14 +485,16 @@ __global__ void __launch_bounds__(kSeThreads) hn_se_fc2_scale_kernel(View x, con
     for (int s = threadIdx.x; s < S; s += blockDim.x) hid[s] = hidden[(long long)n * S + s];
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float a0 = 0.0f, a1 = 0.0f;
-        int s = 0;
-        for (; s + 1 < S; s += 2) {
-            a0 = fmaf(__ldg(w2t + (long long)s * C + c), hid[s], a0);
-            a1 = fmaf(__ldg(w2t + (long long)(s + 1) * C + c), hid[s + 1], a1);
+        float a0 = 0.0f;
+        for (int s0 = 0; s0 < S; s0 += 16) {
+            float wv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) wv[j] = (s0 + j < S) ? __ldg(w2t + (long long)(s0 + j) * C + c) : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (s0 + j < S) a0 = fmaf(wv[j], hid[s0 + j], a0);
         }
-        if (s < S) a0 = fmaf(__ldg(w2t + (long long)s * C + c), hid[s], a0);
-        scale[c] = 1.0f / (1.0f + expf(-(a0 + a1 + b2[c])));
+        scale[c] = 1.0f / (1.0f + expf(-(a0 + b2[c])));
     }
     __syncthreads();
     const int HW = x.H * x.W;

@@ -5,6 +5,8 @@
 struct alignas(64) ConvParams {
     CUtensorMap tmA[HN_MAX_SRC];
     CUtensorMap tmB;
+    CUtensorMap tmO;  // bf16 output view (TMA store path)
+    int n_staging;    // 0: direct stores; 1/2: shared-memory staging buffers of 128 rows x 64 channels
     int flat, TH, TW, n_img, H, W, tiles_x, tiles_y, flat_hw, flat_m;
     int num_taps, cout, bn, stages, tmem_cols;
     int m_tiles, n_tiles, acc_stride;

@@ -109,6 +109,7 @@ struct DetWs {
     int* heads;         // [N*16][kGridHeads] list heads of the per-level spatial grids (-1 = empty)
     void* cub_tmp;
     size_t cub_bytes;
+    long long* dbg;     // optional [N*16][8] cycle counters of the NMS kernel
 };
 
 static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
@@ -179,6 +180,7 @@ static size_t det_layout(int N, int A, void* base, DetWs* ws) {
     w.kept_keys = reinterpret_cast<uint64_t*>(take(NA * 8));
     w.kept_next = reinterpret_cast<int*>(take(NA * 4));
     w.heads = reinterpret_cast<int*>(take((size_t)N * kMaxCls * kGridHeads * 4));
+    w.dbg = nullptr;
     w.cub_bytes = det_cub_bytes(NA);
     w.cub_tmp = take(w.cub_bytes);
     if (ws) *ws = w;
@@ -308,6 +310,8 @@ __global__ void __launch_bounds__(kNmsChunk) hn_det_nms_kernel(DetWs ws, int A, 
         if (tid == 0) ws.seg_kept[seg] = 0;
         return;
     }
+    long long* dbgc = ws.dbg ? ws.dbg + (long long)seg * 8 : nullptr;  // cycles: phase1, phase2, resolve, publish
+    long long t_mark = clock64();
     // coordinate trick (torchvision boxes.py _batched_nms_coordinate_trick): offset = cls * (max + 1)
     const int ncand = ws.n_cand[n];
     bool trick = nms_mode == HN_NMS_TRICK ||
@@ -379,20 +383,27 @@ __global__ void __launch_bounds__(kNmsChunk) hn_det_nms_kernel(DetWs ws, int A, 
         if (tid < kNmsChunk / 64) s_alive[tid] = 0ull;
         __syncthreads();
         if (alive) atomicOr(&s_alive[tid >> 6], 1ull << (tid & 63));
+        __syncthreads();
+        if (dbgc && tid == 0) { long long tt = clock64(); dbgc[0] += tt - t_mark; t_mark = tt; }
         // (2) intra-chunk suppression rows (only rows of live boxes are ever read)
         if (alive) {
             for (int w = 0; w < kNmsChunk / 64; ++w) {
                 unsigned long long bits = 0ull;
                 if (w >= (tid >> 6)) {
-                    for (int t = 0; t < 64; ++t) {
+                    unsigned long long cand = s_alive[w];  // only live, later boxes can be suppressed by this one
+                    if (w == (tid >> 6)) cand &= ~((2ull << (tid & 63)) - 1ull);
+                    while (cand) {
+                        int t = __ffsll((long long)cand) - 1;
+                        cand &= cand - 1;
                         int o = w * 64 + t;
-                        if (o > tid && iou_gt(b, area, s_box[o], s_area[o], iou_thr)) bits |= 1ull << t;
+                        if (iou_gt(b, area, s_box[o], s_area[o], iou_thr)) bits |= 1ull << t;
                     }
                 }
                 s_mask[tid][w] = bits;
             }
         }
         __syncthreads();
+        if (dbgc && tid == 0) { long long tt = clock64(); dbgc[1] += tt - t_mark; t_mark = tt; }
         if (tid < 32) {
             // lane w (< 8) owns word w of the live set; walk the live boxes in order (shared memory only)
             const int lane = tid;
@@ -414,6 +425,7 @@ __global__ void __launch_bounds__(kNmsChunk) hn_det_nms_kernel(DetWs ws, int A, 
             if (lane == 0) s_new = nnew;
         }
         __syncthreads();
+        if (dbgc && tid == 0) { long long tt = clock64(); dbgc[2] += tt - t_mark; t_mark = tt; }
         // publish the newly kept boxes (in order) and insert them into the spatial index, in parallel
         {
             const int nk0 = s_nk, nnew = s_new;
@@ -437,7 +449,9 @@ __global__ void __launch_bounds__(kNmsChunk) hn_det_nms_kernel(DetWs ws, int A, 
             if (tid == 0) s_nk = nk0 + nnew;
         }
         __syncthreads();
+        if (dbgc && tid == 0) { long long tt = clock64(); dbgc[3] += tt - t_mark; t_mark = tt; dbgc[4] += 1; }
     }
+    if (dbgc && tid == 0) { dbgc[5] = s1 - s0; dbgc[6] = s_nk; }
     if (tid == 0) ws.seg_kept[seg] = s_nk;
 }
 
@@ -497,6 +511,9 @@ __global__ void hn_copy_i32_kernel(const int* in, int* out, int n) {
     if (i < n) out[i] = in[i];
 }
 
+static void* g_det_dbg = nullptr;
+extern "C" void hn_det_set_debug_buffer(void* p) { g_det_dbg = p; }
+
 extern "C" int hn_det_decode_nms(const hn_det_desc* d, void* stream) {
     HN_REQUIRE(d != nullptr, "det: null desc");
     HN_REQUIRE(d->N >= 0 && d->N <= 255 && d->A >= 0 && d->A < (1 << kAnchorBits) && d->ncls >= 1 && d->ncls <= kMaxCls,
@@ -513,6 +530,7 @@ extern "C" int hn_det_decode_nms(const hn_det_desc* d, void* stream) {
     HN_REQUIRE(d->workspace && d->workspace_bytes >= hn_det_workspace_bytes(d->N, d->A), "det: workspace too small");
     DetWs ws;
     det_layout(d->N, d->A, d->workspace, &ws);
+    ws.dbg = reinterpret_cast<long long*>(g_det_dbg);
     const long long NA = (long long)d->N * d->A;
     HN_CHECK_CUDA(cudaMemsetAsync(ws.heads, 0xFF, (size_t)d->N * kMaxCls * kGridHeads * 4, s));
     hn_det_init_kernel<<<hn_cdiv(d->N * kMaxCls, 256), 256, 0, s>>>(ws, d->N);

@@ -247,17 +247,19 @@ def fold_bn(weight, bias, bn):
 
 
 def choose_bn(cout):
-    """N tile: a multiple of 16, at most 256, splitting wide layers evenly."""
+    """N tile: a multiple of 16, at most 256; layers wider than one tile use multiples of 64 (the TMA-store slab)."""
     if cout <= 256:
         return max(16, (cout + 15) // 16 * 16)
     n_tiles = (cout + 255) // 256
     per = (cout + n_tiles - 1) // n_tiles
-    return (per + 15) // 16 * 16
+    return (per + 63) // 64 * 64
 
 
 def choose_stages(bn, ntaps):
+    """Shared-memory ring depth: leave room for the output staging slabs (16 KB each) and, for narrow N tiles,
+    for a second co-resident CTA (227 KB and 512 TMEM columns per SM)."""
     stage = 16384 + bn * 128
-    budget = 200 * 1024 if bn > 128 else 100 * 1024  # <=128: leave room for two CTAs per SM
+    budget = (227 - 16 - 5) * 1024 if bn > 128 else (113 - 32 - 5) * 1024
     return int(max(2, min(8, ntaps, budget // stage)))
 
 

@@ -109,8 +109,8 @@ def test_regnet_plan_and_anchors():
 
 
 def test_tiling_heuristics():
-    assert engine.choose_bn(24) == 32 and engine.choose_bn(112) == 112 and engine.choose_bn(936) == 240 and engine.choose_bn(512) == 256
-    assert engine.choose_bn(1344) == 224 and engine.choose_bn(5) == 16
+    assert engine.choose_bn(24) == 32 and engine.choose_bn(112) == 112 and engine.choose_bn(936) == 256 and engine.choose_bn(512) == 256
+    assert engine.choose_bn(1344) == 256 and engine.choose_bn(5) == 16
     for hw in ((20, 20), (40, 40), (160, 160), (5, 5), (12, 20)):
         th, tw = engine.choose_tile(*hw)
         assert th * tw == 128
