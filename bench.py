@@ -153,26 +153,63 @@ def run_native(args):
     value = world * B * args.steps / (ms / 1e3)
 
     # ---------------- end to end through the public API with host buffers ----------------
-    def e2e_step(hx):
-        x = hx.to(dev, non_blocking=True)
-        out, d, l = step(x)
+    # Every step copies its own input batch host->device (pinned memory) and reads its results back; the
+    # copies run on side streams so that step i+1's upload and step i-1's download overlap step i's compute.
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    xin = [torch.empty((B, 3, H, W), dtype=torch.float32, device=dev) for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+    pinned = [None, None]
+
+    def upload(i):
+        k = i % 2
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_free[k])  # the compute that last read xin[k] has finished
+            xin[k].copy_(host[i % 2], non_blocking=True)
+            ev_in[k].record(s_in)
+
+    segcopy = [torch.empty((B, H, W), dtype=torch.uint8, device=dev) for _ in range(2)]
+
+    def download(k, seg_u8, d, l):
         boxes, scores, cids, count, _ = d
-        res = [out["seg_cls_u8"].cpu(), count.cpu(), l[0].cpu()]
-        kmax = int(res[1].max()) if B else 0
-        res += [boxes[:, :kmax].cpu(), scores[:, :kmax].cpu(), cids[:, :kmax].cpu()]
-        lk = int(res[2].max()) if B else 0
-        res += [l[1][:, :lk].cpu(), l[2][:, :lk].cpu(), l[3][:, :lk].cpu()]
+        srcs = [seg_u8, count, boxes, scores, cids, l[0], l[1], l[2], l[3]]
+        if pinned[k] is None:
+            pinned[k] = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in srcs]
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_done[k])
+            for p_, t in zip(pinned[k], srcs):
+                t.record_stream(s_out)  # per-call decoder outputs: keep the allocator from recycling them early
+                p_.copy_(t, non_blocking=True)
+        return pinned[k]
+
+    def e2e_loop(n):
+        res = None
+        for k in range(2):
+            ev_free[k].record(stream)
+        upload(0)
+        for i in range(n):
+            k = i % 2
+            if i + 1 < n:
+                upload(i + 1)
+            stream.wait_event(ev_in[k])
+            out, d, l = step(xin[k])
+            ev_free[k].record(stream)
+            segcopy[k].copy_(out["seg_cls_u8"])  # the class map is the plan's static buffer: snapshot it for the download
+            ev_done[k].record(stream)
+            res = download(k, segcopy[k], d, l)
+        s_out.synchronize()
         return res
 
-    for i in range(max(3, args.warmup // 2)):
-        res = e2e_step(host[i % 2])
+    e2e_loop(max(3, args.warmup // 2))
     barrier()
+    t0 = time.perf_counter()
     e0.record(stream)
-    for i in range(args.steps):
-        res = e2e_step(host[i % 2])
-    e1.record(stream)
+    res = e2e_loop(args.steps)
+    torch.cuda.synchronize(dev)
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    t = torch.tensor([e2e_wall_ms], device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())

@@ -128,18 +128,22 @@ typedef struct hn_lanefuse_desc {
     int32_t stride; /* 16 or 32 */
 } hn_lanefuse_desc;
 
-/* Squeeze-excite: x *= sigmoid(W2 relu(W1 mean_hw(x) + b1) + b2), in place (anynet.py:39-47,68-69).
- * Two launches: (pool + FC1 by the last-arriving block of each image), (FC2 + scale).  `counter` must
- * be zero on first use; the op leaves it zeroed again. */
-typedef struct hn_se_desc {
+/* Squeeze-excite (anynet.py:39-47,68-69) = hn_se_pool_fwd -> two tiny tensor-core GEMMs (hn_conv_fwd:
+ * FC1+ReLU over all images at once, FC2+sigmoid) -> hn_se_scale_fwd.
+ * pool: mean over H*W of every channel, bf16 [N][C].  Deterministic: per-chunk partial sums are added in
+ * chunk order by the block that arrives last for its image.  `counter` must be zero on first use. */
+typedef struct hn_se_pool_desc {
     hn_view x;
-    float* pooled;    /* scratch fp32 [N][ceil(H*W/128)][C] per-chunk partial sums */
-    float* hidden;    /* scratch fp32 [N][S] */
+    float* partial;   /* scratch fp32 [N][ceil(H*W/128)][C] */
     int32_t* counter; /* scratch int32 [N] */
-    const float *w1, *b1; /* w1 [S][C] */
-    const float *w2t, *b2; /* w2 transposed: [S][C] */
-    int32_t S;
-} hn_se_desc;
+    void* mean;       /* bf16 [N][C] */
+} hn_se_pool_desc;
+
+/* scale: x[n, :, :, c] *= scale[n][c] in place, scale bf16 [N][C] */
+typedef struct hn_se_scale_desc {
+    hn_view x;
+    const void* scale;
+} hn_se_scale_desc;
 
 /* Detection decode + NMS (detection_loss.py:7-108; torchvision.ops.boxes.batched_nms semantics). */
 #define HN_NMS_AUTO_CUDA 0 /* coordinate trick iff 4*n <= 100000 (torchvision boxes.py, CUDA tensors) */
@@ -192,7 +196,8 @@ int hn_stem_fwd(const hn_stem_desc* d, void* stream);
 int hn_node_fwd(const hn_node_desc* d, void* stream);
 int hn_pool_fwd(const hn_pool_desc* d, void* stream);
 int hn_lanefuse_fwd(const hn_lanefuse_desc* d, void* stream);
-int hn_se_fwd(const hn_se_desc* d, void* stream);
+int hn_se_pool_fwd(const hn_se_pool_desc* d, void* stream);
+int hn_se_scale_fwd(const hn_se_scale_desc* d, void* stream);
 int hn_seg_argmax(const float* logits, int32_t N, int32_t C, int64_t HW, int64_t* out_i64, uint8_t* out_u8,
                   void* stream);
 int hn_u8_to_i64(const uint8_t* in, int64_t* out, int64_t n, void* stream);
@@ -210,7 +215,8 @@ int hn_plan_add_stem(hn_plan* p, const hn_stem_desc* d);
 int hn_plan_add_node(hn_plan* p, const hn_node_desc* d);
 int hn_plan_add_pool(hn_plan* p, const hn_pool_desc* d);
 int hn_plan_add_lanefuse(hn_plan* p, const hn_lanefuse_desc* d);
-int hn_plan_add_se(hn_plan* p, const hn_se_desc* d);
+int hn_plan_add_se_pool(hn_plan* p, const hn_se_pool_desc* d);
+int hn_plan_add_se_scale(hn_plan* p, const hn_se_scale_desc* d);
 int hn_plan_add_det(hn_plan* p, const hn_det_desc* d);
 int hn_plan_add_lane(hn_plan* p, const hn_lane_desc* d);
 int hn_plan_size(const hn_plan* p);
@@ -223,6 +229,7 @@ int hn_plan_graph_launch(hn_plan* p, void* stream);
 /* diagnostics: when set (before a conv is prepared), every conv CTA stores 16 int64 globaltimer stamps */
 void hn_conv_set_debug_buffer(void* device_i64);
 void hn_det_set_debug_buffer(void* device_i64); /* [N*16][8] int64 cycle counters of the NMS kernel */
+void hn_det_force_sequential(int on);           /* tests: run the sequential per-class NMS kernel only */
 int hn_version(void);
 const char* hn_last_error(void);
 int hn_device_sm_count(void);

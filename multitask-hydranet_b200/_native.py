@@ -62,9 +62,12 @@ class LaneFuseDesc(C.Structure):
     _fields_ = [("p3", View), ("p4", View), ("p5", View), ("p6", View), ("out", View), ("stride", C.c_int32)]
 
 
-class SeDesc(C.Structure):
-    _fields_ = [("x", View), ("pooled", C.c_void_p), ("hidden", C.c_void_p), ("counter", C.c_void_p),
-                ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2t", C.c_void_p), ("b2", C.c_void_p), ("S", C.c_int32)]
+class SePoolDesc(C.Structure):
+    _fields_ = [("x", View), ("partial", C.c_void_p), ("counter", C.c_void_p), ("mean", C.c_void_p)]
+
+
+class SeScaleDesc(C.Structure):
+    _fields_ = [("x", View), ("scale", C.c_void_p)]
 
 
 class DetDesc(C.Structure):
@@ -94,7 +97,8 @@ SYMBOLS = {
     "hn_node_fwd": (C.c_int, [C.POINTER(NodeDesc), _P]),
     "hn_pool_fwd": (C.c_int, [C.POINTER(PoolDesc), _P]),
     "hn_lanefuse_fwd": (C.c_int, [C.POINTER(LaneFuseDesc), _P]),
-    "hn_se_fwd": (C.c_int, [C.POINTER(SeDesc), _P]),
+    "hn_se_pool_fwd": (C.c_int, [C.POINTER(SePoolDesc), _P]),
+    "hn_se_scale_fwd": (C.c_int, [C.POINTER(SeScaleDesc), _P]),
     "hn_seg_argmax": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P]),
     "hn_u8_to_i64": (C.c_int, [_P, _P, C.c_int64, _P]),
     "hn_det_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
@@ -108,7 +112,8 @@ SYMBOLS = {
     "hn_plan_add_node": (C.c_int, [_P, C.POINTER(NodeDesc)]),
     "hn_plan_add_pool": (C.c_int, [_P, C.POINTER(PoolDesc)]),
     "hn_plan_add_lanefuse": (C.c_int, [_P, C.POINTER(LaneFuseDesc)]),
-    "hn_plan_add_se": (C.c_int, [_P, C.POINTER(SeDesc)]),
+    "hn_plan_add_se_pool": (C.c_int, [_P, C.POINTER(SePoolDesc)]),
+    "hn_plan_add_se_scale": (C.c_int, [_P, C.POINTER(SeScaleDesc)]),
     "hn_plan_add_det": (C.c_int, [_P, C.POINTER(DetDesc)]),
     "hn_plan_add_lane": (C.c_int, [_P, C.POINTER(LaneDesc)]),
     "hn_plan_size": (C.c_int, [_P]),
@@ -119,6 +124,7 @@ SYMBOLS = {
     "hn_plan_graph_launch": (C.c_int, [_P, _P]),
     "hn_conv_set_debug_buffer": (None, [_P]),
     "hn_det_set_debug_buffer": (None, [_P]),
+    "hn_det_force_sequential": (None, [C.c_int]),
     "hn_version": (C.c_int, []),
     "hn_last_error": (C.c_char_p, []),
     "hn_device_sm_count": (C.c_int, []),

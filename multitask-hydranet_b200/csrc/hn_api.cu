@@ -27,7 +27,7 @@ extern "C" int hn_device_sm_count(void) {
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
-enum OpKind { OP_CONV, OP_STEM, OP_NODE, OP_POOL, OP_LANEFUSE, OP_SE, OP_DET, OP_LANE };
+enum OpKind { OP_CONV, OP_STEM, OP_NODE, OP_POOL, OP_LANEFUSE, OP_SE_POOL, OP_SE_SCALE, OP_DET, OP_LANE };
 
 struct PlanOp {
     OpKind kind;
@@ -36,7 +36,8 @@ struct PlanOp {
     hn_node_desc node;
     hn_pool_desc pool;
     hn_lanefuse_desc lanefuse;
-    hn_se_desc se;
+    hn_se_pool_desc se_pool;
+    hn_se_scale_desc se_scale;
     hn_det_desc det;
     hn_lane_desc lane;
 };
@@ -76,7 +77,8 @@ PLAN_ADD(stem, OP_STEM, stem, hn_stem_desc)
 PLAN_ADD(node, OP_NODE, node, hn_node_desc)
 PLAN_ADD(pool, OP_POOL, pool, hn_pool_desc)
 PLAN_ADD(lanefuse, OP_LANEFUSE, lanefuse, hn_lanefuse_desc)
-PLAN_ADD(se, OP_SE, se, hn_se_desc)
+PLAN_ADD(se_pool, OP_SE_POOL, se_pool, hn_se_pool_desc)
+PLAN_ADD(se_scale, OP_SE_SCALE, se_scale, hn_se_scale_desc)
 PLAN_ADD(det, OP_DET, det, hn_det_desc)
 PLAN_ADD(lane, OP_LANE, lane, hn_lane_desc)
 
@@ -95,7 +97,6 @@ extern "C" int hn_plan_add_conv(hn_plan* p, const hn_conv_desc* d) {
 
 static int op_launches(const PlanOp* o) {
     switch (o->kind) {
-        case OP_SE: return 2;
         case OP_DET: return hn_det_num_launches(&o->det);
         case OP_LANE: return 1;
         default: return 1;
@@ -122,7 +123,8 @@ extern "C" int hn_plan_run_range(hn_plan* p, int first, int last, void* stream) 
             case OP_NODE: rc = hn_node_fwd(&o->node, stream); break;
             case OP_POOL: rc = hn_pool_fwd(&o->pool, stream); break;
             case OP_LANEFUSE: rc = hn_lanefuse_fwd(&o->lanefuse, stream); break;
-            case OP_SE: rc = hn_se_fwd(&o->se, stream); break;
+            case OP_SE_POOL: rc = hn_se_pool_fwd(&o->se_pool, stream); break;
+            case OP_SE_SCALE: rc = hn_se_scale_fwd(&o->se_scale, stream); break;
             case OP_DET: rc = hn_det_decode_nms(&o->det, stream); break;
             case OP_LANE: rc = hn_lane_decode_nms(&o->lane, stream); break;
         }

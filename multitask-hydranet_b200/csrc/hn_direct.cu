@@ -387,19 +387,15 @@ extern "C" int hn_lanefuse_fwd(const hn_lanefuse_desc* d, void* stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// squeeze-excite, two launches:
-//   1. per (image, pixel chunk): channel sums -> per-chunk partials; the block that arrives last for
-//      its image adds the partials in chunk order (deterministic), runs FC1 (+ReLU) and re-arms the
-//      arrival counter, so no memset is ever needed;
-//   2. per (image, pixel chunk): FC2 (+sigmoid) recomputed per block (it is tiny) -> scale in place.
+// squeeze-excite: global average pool (deterministic) and in-place channel scaling; the two FC layers
+// in between run as tensor-core GEMMs over all images at once (engine.py)
 // ------------------------------------------------------------------------------------------------
 static constexpr int kSePix = 128;      // pixels per block
 static constexpr int kSeThreads = 512;
 
-__global__ void __launch_bounds__(kSeThreads) hn_se_pool_fc1_kernel(View x, float* __restrict__ pooled, float* __restrict__ hidden,
-                                                                    int* __restrict__ counter, int S, float inv_hw,
-                                                                    const float* __restrict__ w1, const float* __restrict__ b1) {
-    extern __shared__ float sm[];  // [lanes][C] partial sums, later mean[C]
+__global__ void __launch_bounds__(kSeThreads) hn_se_pool_kernel(View x, float* __restrict__ partial, int* __restrict__ counter,
+                                                                bf16* __restrict__ mean_out, float inv_hw) {
+    extern __shared__ float sm[];  // [lanes][C] partial sums
     __shared__ int s_last;
     const int C = x.C, CV = C >> 3;
     const int n = blockIdx.y;
@@ -426,17 +422,16 @@ __global__ void __launch_bounds__(kSeThreads) hn_se_pool_fc1_kernel(View x, floa
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float a = 0.0f;
         for (int l = 0; l < lanes; ++l) a += sm[l * C + c];
-        pooled[((long long)n * nchunk + blockIdx.x) * C + c] = a;  // per-chunk partial: fixed summation order, deterministic
+        partial[((long long)n * nchunk + blockIdx.x) * C + c] = a;  // fixed summation order: deterministic
     }
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(counter + n, 1) == (int)gridDim.x - 1);
+    if (threadIdx.x == 0) s_last = (atomicAdd(counter + n, 1) == nchunk - 1);
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    float* mean = sm;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float* pp = pooled + (long long)n * nchunk * C + c;
+        const float* pp = partial + (long long)n * nchunk * C + c;
         float a = 0.0f;
         int k = 0;
         for (; k + 8 <= nchunk; k += 8) {
@@ -447,86 +442,53 @@ __global__ void __launch_bounds__(kSeThreads) hn_se_pool_fc1_kernel(View x, floa
             for (int j = 0; j < 8; ++j) a += v[j];
         }
         for (; k < nchunk; ++k) a += __ldcg(pp + (long long)k * C);
-        mean[c] = a * inv_hw;
+        mean_out[(long long)n * C + c] = __float2bfloat16(a * inv_hw);
     }
     if (threadIdx.x == 0) counter[n] = 0;
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int s = warp; s < S; s += nw) {
-        const float* wr = w1 + (long long)s * C;
-        // all loads of a batch are issued before the first use: one L2 round trip per 8 x 32 channels
-        float acc = 0.0f;
-        for (int c0 = 0; c0 < C; c0 += 256) {
-            float wv[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                int c = c0 + j * 32 + lane;
-                wv[j] = c < C ? __ldg(wr + c) : 0.0f;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                int c = c0 + j * 32 + lane;
-                if (c < C) acc = fmaf(wv[j], mean[c], acc);
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) hidden[(long long)n * S + s] = fmaxf(acc + b1[s], 0.0f);
-    }
 }
 
-__global__ void __launch_bounds__(kSeThreads) hn_se_fc2_scale_kernel(View x, const float* __restrict__ hidden, int S,
-                                                                     const float* __restrict__ w2t, const float* __restrict__ b2) {
-    extern __shared__ float sm[];  // hid[S], scale[C]
-    float* hid = sm;
-    float* scale = sm + S;
-    const int C = x.C, CV = C >> 3;
-    const int n = blockIdx.y;
-    for (int s = threadIdx.x; s < S; s += blockDim.x) hid[s] = hidden[(long long)n * S + s];
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float a0 = 0.0f;
-        for (int s0 = 0; s0 < S; s0 += 16) {
-            float wv[16];
+__global__ void hn_se_scale_kernel(View x, const bf16* __restrict__ scale) {
+    const int CV = x.C >> 3;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)x.N * x.H * x.W * CV;
+    if (idx >= total) return;
+    int cv = (int)(idx % CV);
+    long long t = idx / CV;
+    int xx = (int)(t % x.W);
+    t /= x.W;
+    int y = (int)(t % x.H);
+    int n = (int)(t / x.H);
+    bf16* p = const_cast<bf16*>(vptr(x, n, y, xx, cv * 8));
+    float f[8], sc[8];
+    load8(p, f);
+    load8(scale + (long long)n * x.C + cv * 8, sc);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) wv[j] = (s0 + j < S) ? __ldg(w2t + (long long)(s0 + j) * C + c) : 0.0f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (s0 + j < S) a0 = fmaf(wv[j], hid[s0 + j], a0);
-        }
-        scale[c] = 1.0f / (1.0f + expf(-(a0 + b2[c])));
-    }
-    __syncthreads();
-    const int HW = x.H * x.W;
-    const int p0 = blockIdx.x * kSePix, p1 = min(p0 + kSePix, HW);
-    for (int it = threadIdx.x; it < (p1 - p0) * CV; it += blockDim.x) {
-        int cv = it % CV, px = p0 + it / CV;
-        int y = px / x.W, xx = px - y * x.W;
-        bf16* p = const_cast<bf16*>(vptr(x, n, y, xx, cv * 8));
-        float f[8];
-        load8(p, f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] *= scale[cv * 8 + j];
-        store8(p, f);
-    }
+    for (int j = 0; j < 8; ++j) f[j] *= sc[j];
+    store8(p, f);
 }
 
-extern "C" int hn_se_fwd(const hn_se_desc* d, void* stream) {
-    HN_REQUIRE(d && d->pooled && d->hidden && d->counter && d->w1 && d->b1 && d->w2t && d->b2 && d->S >= 1, "se: bad descriptor");
-    if (int rc = check_view(d->x, "se.x")) return rc;
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+extern "C" int hn_se_pool_fwd(const hn_se_pool_desc* d, void* stream) {
+    HN_REQUIRE(d && d->partial && d->counter && d->mean, "se_pool: bad descriptor");
+    if (int rc = check_view(d->x, "se_pool.x")) return rc;
     const int C = d->x.C, CV = C / 8, HW = d->x.H * d->x.W;
-    HN_REQUIRE(CV <= kSeThreads, "se: C=%d too wide", C);
+    HN_REQUIRE(CV <= kSeThreads, "se_pool: C=%d too wide", C);
     dim3 grid(hn_cdiv(HW, kSePix), d->x.N);
     int lanes = kSeThreads / CV;
     if (lanes > kSePix) lanes = kSePix;
-    size_t smem1 = (size_t)lanes * C * sizeof(float);
-    if (smem1 < (size_t)C * sizeof(float)) smem1 = (size_t)C * sizeof(float);
-    HN_REQUIRE(smem1 <= 48 * 1024, "se: shared memory");
-    hn_se_pool_fc1_kernel<<<grid, kSeThreads, smem1, s>>>(to_view(d->x), d->pooled, d->hidden, d->counter, d->S, 1.0f / (float)HW,
-                                                         d->w1, d->b1);
+    size_t smem = (size_t)lanes * C * sizeof(float);
+    HN_REQUIRE(smem <= 48 * 1024, "se_pool: shared memory");
+    hn_se_pool_kernel<<<grid, kSeThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+        to_view(d->x), d->partial, d->counter, reinterpret_cast<bf16*>(d->mean), 1.0f / (float)HW);
     HN_CHECK_CUDA(cudaGetLastError());
-    hn_se_fc2_scale_kernel<<<grid, kSeThreads, (size_t)(C + d->S) * sizeof(float), s>>>(to_view(d->x), d->hidden, d->S, d->w2t, d->b2);
+    return HN_OK;
+}
+
+extern "C" int hn_se_scale_fwd(const hn_se_scale_desc* d, void* stream) {
+    HN_REQUIRE(d && d->scale, "se_scale: bad descriptor");
+    if (int rc = check_view(d->x, "se_scale.x")) return rc;
+    long long total = (long long)d->x.N * d->x.H * d->x.W * (d->x.C / 8);
+    hn_se_scale_kernel<<<hn_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        to_view(d->x), reinterpret_cast<const bf16*>(d->scale));
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }

@@ -4,7 +4,9 @@
 //         fp32 arithmetic and tie order
 //   lane: per-anchor polyline decode + greedy lane NMS with the reference's fp32/py-float arithmetic
 // Arithmetic that must be bit-exact uses __f*_rn intrinsics so nvcc cannot contract it into FMAs.
+#include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "hn_ops.h"
 
@@ -110,7 +112,27 @@ struct DetWs {
     void* cub_tmp;
     size_t cub_bytes;
     long long* dbg;     // optional [N*16][8] cycle counters of the NMS kernel
+    // ---- parallel (dependency-round) NMS ----
+    float4* sbox;        // [N*A] NMS-space boxes in sorted order
+    uint32_t* ckey;      // [N*A] (segment, grid cell) key per sorted position, and its sorted copy
+    uint32_t* ckey_alt;
+    int* cval;           // [N*A] sorted position, and the cell-ordered permutation
+    int* cval_alt;
+    float4* cbox;        // [N*A] boxes in cell order
+    int* cell_start;     // [N*16*kCellStride] first / one-past-last cell-order index of every cell
+    int* cell_end;
+    int* preds;          // [N*A][kMaxPreds] earlier boxes of the same class with IoU > thr
+    int* npred;          // [N*A]
+    unsigned char* status; // [N*A] 0 undecided, 1 kept, 2 suppressed
+    int* kflag;          // [N*A] kept as int, and its exclusive scan
+    int* kscan;
+    int* overflow;       // [N] image has a box with more than kMaxPreds predecessors -> sequential kernel
+    int* changed;        // [2]
+    size_t cub2_bytes;
+    void* cub2_tmp;
 };
+static constexpr int kCellStride = 8192;  // >= kGridHeads, power of two
+static constexpr int kMaxPreds = 64;
 
 static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
 
@@ -183,6 +205,30 @@ static size_t det_layout(int N, int A, void* base, DetWs* ws) {
     w.dbg = nullptr;
     w.cub_bytes = det_cub_bytes(NA);
     w.cub_tmp = take(w.cub_bytes);
+    w.sbox = reinterpret_cast<float4*>(take(NA * 16));
+    w.ckey = reinterpret_cast<uint32_t*>(take(NA * 4));
+    w.ckey_alt = reinterpret_cast<uint32_t*>(take(NA * 4));
+    w.cval = reinterpret_cast<int*>(take(NA * 4));
+    w.cval_alt = reinterpret_cast<int*>(take(NA * 4));
+    w.cbox = reinterpret_cast<float4*>(take(NA * 16));
+    w.cell_start = reinterpret_cast<int*>(take((size_t)N * kMaxCls * kCellStride * 4));
+    w.cell_end = reinterpret_cast<int*>(take((size_t)N * kMaxCls * kCellStride * 4));
+    w.preds = reinterpret_cast<int*>(take(NA * kMaxPreds * 4));
+    w.npred = reinterpret_cast<int*>(take(NA * 4));
+    w.status = reinterpret_cast<unsigned char*>(take(NA));
+    w.kflag = reinterpret_cast<int*>(take(NA * 4));
+    w.kscan = reinterpret_cast<int*>(take(NA * 4));
+    w.overflow = reinterpret_cast<int*>(take(N * 4));
+    w.changed = reinterpret_cast<int*>(take(16));
+    {
+        size_t b1 = 0, b2 = 0;
+        cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr);
+        cub::DoubleBuffer<int> dv(nullptr, nullptr);
+        cub::DeviceRadixSort::SortPairs(nullptr, b1, dk, dv, (int)NA, 0, 32, (cudaStream_t)0);
+        cub::DeviceScan::ExclusiveSum(nullptr, b2, (int*)nullptr, (int*)nullptr, (int)NA, (cudaStream_t)0);
+        w.cub2_bytes = b1 > b2 ? b1 : b2;
+    }
+    w.cub2_tmp = take(w.cub2_bytes);
     if (ws) *ws = w;
     return off;
 }
@@ -192,7 +238,7 @@ extern "C" int64_t hn_det_workspace_bytes(int32_t N, int32_t A) {
     return (int64_t)det_layout(N, A, nullptr, nullptr);
 }
 
-int hn_det_num_launches(const hn_det_desc*) { return 5 + 10; }  // 5 own kernels + CUB onesweep passes
+int hn_det_num_launches(const hn_det_desc*) { return 11 + 16; }  // 11 own kernels + CUB sort / scan passes
 
 // decode (BBoxTransform + ClipBoxes, detection_loss.py:7-52), score = max over classes, threshold
 __global__ void hn_det_decode_kernel(const float* __restrict__ anchors, const float* __restrict__ reg,
@@ -294,7 +340,8 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 // in chunks of 512: (1) every candidate of the chunk is tested against the boxes kept so far that the
 // spatial index says can overlap it, (2) survivors are resolved against each other with a 512x512 bit
 // matrix walked by one warp, which also inserts the newly kept boxes into the index.
-__global__ void __launch_bounds__(kNmsChunk) hn_det_nms_kernel(DetWs ws, int A, float iou_thr, int nms_mode, GridGeom g) {
+__global__ void __launch_bounds__(kNmsChunk) hn_det_nms_kernel(DetWs ws, int A, float iou_thr, int nms_mode, GridGeom g,
+                                                               int only_overflow) {
     __shared__ float4 s_box[kNmsChunk];
     __shared__ float s_area[kNmsChunk];
     __shared__ unsigned long long s_mask[kNmsChunk][kNmsChunk / 64];
@@ -305,6 +352,7 @@ __global__ void __launch_bounds__(kNmsChunk) hn_det_nms_kernel(DetWs ws, int A, 
     const int n = seg / kMaxCls, cls = seg % kMaxCls;
     const int s0 = ws.seg_start[seg], s1 = ws.seg_end[seg];
     const int tid = threadIdx.x;
+    if (only_overflow && ws.overflow[n] == 0) return;  // this image was handled by the parallel path
     if (tid == 0) s_nk = 0;
     if (s1 <= s0) {
         if (tid == 0) ws.seg_kept[seg] = 0;
@@ -455,6 +503,156 @@ __global__ void __launch_bounds__(kNmsChunk) hn_det_nms_kernel(DetWs ws, int A, 
     if (tid == 0) ws.seg_kept[seg] = s_nk;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Parallel exact greedy NMS ("dependency rounds").  Greedy NMS is the lexicographically-first maximal
+// independent set of the conflict graph (edge = same class and IoU > thr) under the score order.  A box
+// is kept iff all its earlier conflicting neighbours are suppressed, suppressed iff one of them is kept:
+// with the per-box predecessor lists built once (spatial hash over ALL candidates, cells sorted by
+// priority), every round decides all boxes whose predecessors are decided, for all images and classes
+// at once.  With scores unrelated to position the number of rounds is O(log^2 n); the result is exactly
+// the sequential one, whatever the class skew.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float seg_offset(const DetWs& ws, int n, int cls, int nms_mode) {
+    const int ncand = ws.n_cand[n];
+    bool trick = nms_mode == HN_NMS_TRICK || (nms_mode == HN_NMS_AUTO_CUDA && (long long)ncand * 4 <= 100000) ||
+                 (nms_mode == HN_NMS_AUTO_CPU && (long long)ncand * 4 <= 4000);
+    return trick ? __fmul_rn((float)cls, __fadd_rn(ordered_to_float(ws.max_coord[n]), 1.0f)) : 0.0f;
+}
+__device__ __forceinline__ int grid_cell(const float4& b, float offset, const GridGeom& g) {
+    const float cx = 0.5f * (b.x + b.z) - offset, cy = 0.5f * (b.y + b.w) - offset;
+    const int l = grid_level(fmaxf(b.z - b.x, b.w - b.y), g);
+    const float inv = 1.0f / (g.c0 * (float)(1 << l));
+    int cell = g.base[l];
+    if (g.nx[l] * g.ny[l] > 1)
+        cell += clampi((int)floorf(cy * inv), 0, g.ny[l] - 1) * g.nx[l] + clampi((int)floorf(cx * inv), 0, g.nx[l] - 1);
+    return cell;
+}
+
+__global__ void hn_nms2_prepare_kernel(DetWs ws, long long NA, int A, int nms_mode, GridGeom g) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NA) return;
+    const uint64_t key = ws.keys[i];
+    ws.cval[i] = (int)i;
+    ws.kflag[i] = 0;
+    ws.status[i] = 2;
+    if (key == ~0ull) { ws.ckey[i] = 0xFFFFFFFFu; return; }
+    const int seg = (int)(key >> kClsShift), n = seg / kMaxCls, cls = seg % kMaxCls;
+    const int a = (int)(key & ((1u << kAnchorBits) - 1));
+    const float off = seg_offset(ws, n, cls, nms_mode);
+    float4 b = ws.boxes[(long long)n * A + a];
+    if (off != 0.0f) {
+        b.x = __fadd_rn(b.x, off); b.y = __fadd_rn(b.y, off); b.z = __fadd_rn(b.z, off); b.w = __fadd_rn(b.w, off);
+    }
+    ws.sbox[i] = b;
+    ws.ckey[i] = (uint32_t)seg * kCellStride + (uint32_t)grid_cell(b, off, g);
+}
+
+__global__ void hn_nms2_cells_kernel(DetWs ws, long long NA) {
+    long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= NA) return;
+    const uint32_t ck = ws.ckey[q];
+    if (ck == 0xFFFFFFFFu) return;
+    ws.cbox[q] = ws.sbox[ws.cval[q]];
+    if (q == 0 || ws.ckey[q - 1] != ck) ws.cell_start[ck] = (int)q;
+    if (q + 1 == NA || ws.ckey[q + 1] != ck) ws.cell_end[ck] = (int)(q + 1);
+}
+
+__global__ void __launch_bounds__(128) hn_nms2_build_kernel(DetWs ws, long long NA, int nms_mode, float iou_thr, GridGeom g) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NA) return;
+    const uint64_t key = ws.keys[i];
+    if (key == ~0ull) return;
+    const int seg = (int)(key >> kClsShift), n = seg / kMaxCls, cls = seg % kMaxCls;
+    const float offset = seg_offset(ws, n, cls, nms_mode);
+    const float4 b = ws.sbox[i];
+    const float area = box_area(b);
+    const float wj = b.z - b.x, hj = b.w - b.y;
+    const float cx = 0.5f * (b.x + b.z) - offset, cy = 0.5f * (b.y + b.w) - offset;
+    const int t = grid_level(fmaxf(wj, hj), g);
+    const int l_lo = max(0, t - g.delta), l_hi = min(g.nlev - 1, t + g.delta);
+    int* my = ws.preds + i * kMaxPreds;
+    int cnt = 0;
+    for (int l = l_lo; l <= l_hi; ++l) {
+        const float cl = g.c0 * (float)(1 << l);
+        const float inv = 1.0f / cl;
+        const int nx = g.nx[l], ny = g.ny[l];
+        int x_lo = 0, x_hi = 0, y_lo = 0, y_hi = 0;
+        if (nx * ny > 1) {
+            const float rx = 0.5f * fmaxf(wj, 0.0f) + cl + 1.0f, ry = 0.5f * fmaxf(hj, 0.0f) + cl + 1.0f;
+            x_lo = clampi((int)floorf((cx - rx) * inv), 0, nx - 1);
+            x_hi = clampi((int)floorf((cx + rx) * inv), 0, nx - 1);
+            y_lo = clampi((int)floorf((cy - ry) * inv), 0, ny - 1);
+            y_hi = clampi((int)floorf((cy + ry) * inv), 0, ny - 1);
+        }
+        for (int yy = y_lo; yy <= y_hi; ++yy) {
+            for (int xx = x_lo; xx <= x_hi; ++xx) {
+                const uint32_t ck = (uint32_t)seg * kCellStride + (uint32_t)(g.base[l] + yy * nx + xx);
+                const int e = ws.cell_end[ck];
+                for (int q = ws.cell_start[ck]; q < e; ++q) {
+                    const int m = ws.cval[q];
+                    if (m >= i) break;  // members of a cell are in priority order: only earlier boxes matter
+                    const float4 kb = ws.cbox[q];
+                    if (iou_gt(kb, box_area(kb), b, area, iou_thr)) {
+                        if (cnt < kMaxPreds) my[cnt] = m;
+                        ++cnt;
+                    }
+                }
+            }
+        }
+    }
+    ws.npred[i] = min(cnt, kMaxPreds);
+    if (cnt > kMaxPreds) ws.overflow[n] = 1;
+    ws.status[i] = cnt == 0 ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) hn_nms2_rounds_kernel(DetWs ws, long long NA) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    volatile int* changed = ws.changed;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int round = 0;
+    while (true) {
+        int* flag = ws.changed + (round & 1);
+        if (tid0 == 0) ws.changed[(round + 1) & 1] = 0;  // reset the other flag for the next round
+        bool any = false;
+        for (long long i = tid0; i < NA; i += stride) {
+            if (__ldcg(ws.status + i) != 0) continue;
+            const int np = ws.npred[i];
+            const int* my = ws.preds + i * kMaxPreds;
+            bool kept_pred = false, all_supp = true;
+            for (int k = 0; k < np; ++k) {
+                const unsigned char st = __ldcg(ws.status + my[k]);
+                if (st == 1) { kept_pred = true; break; }
+                if (st == 0) all_supp = false;
+            }
+            if (kept_pred) { ws.status[i] = 2; any = true; }
+            else if (all_supp) { ws.status[i] = 1; any = true; }
+        }
+        if (any) *flag = 1;
+        grid.sync();
+        const int c = changed[round & 1];
+        if (!c) break;
+        ++round;
+        grid.sync();
+    }
+    for (long long i = tid0; i < NA; i += stride) ws.kflag[i] = __ldcg(ws.status + i) == 1 ? 1 : 0;
+}
+
+__global__ void hn_nms2_compact_kernel(DetWs ws, long long NA) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NA) return;
+    const uint64_t key = ws.keys[i];
+    if (key == ~0ull) return;
+    const int seg = (int)(key >> kClsShift), n = seg / kMaxCls;
+    if (ws.overflow[n]) return;  // the sequential kernel owns this image
+    const int s0 = ws.seg_start[seg], s1 = ws.seg_end[seg];
+    const int base = ws.kscan[s0];
+    const int f = ws.kflag[i];
+    if (f) ws.kept_keys[s0 + ws.kscan[i] - base] = key;
+    if (i == s1 - 1) ws.seg_kept[seg] = ws.kscan[i] + f - base;
+}
+
 // final order = score descending, ties by ascending candidate index, across classes: the rank of a
 // kept box is the number of kept boxes (all classes) whose (~score, anchor) key is smaller
 __global__ void hn_det_gather_kernel(DetWs ws, int A, float* __restrict__ out_boxes, float* __restrict__ out_scores,
@@ -498,7 +696,9 @@ __global__ void hn_det_init_kernel(DetWs ws, int N) {
     if (i < N) {
         ws.n_cand[i] = 0;
         ws.max_coord[i] = float_to_ordered(-INFINITY);
+        ws.overflow[i] = 0;
     }
+    if (i < 2) ws.changed[i] = 0;
     if (i < N * kMaxCls) {
         ws.seg_start[i] = 0;
         ws.seg_end[i] = 0;
@@ -512,6 +712,8 @@ __global__ void hn_copy_i32_kernel(const int* in, int* out, int n) {
 }
 
 static void* g_det_dbg = nullptr;
+static int g_det_force_sequential = 0;
+extern "C" void hn_det_force_sequential(int on) { g_det_force_sequential = on; }
 extern "C" void hn_det_set_debug_buffer(void* p) { g_det_dbg = p; }
 
 extern "C" int hn_det_decode_nms(const hn_det_desc* d, void* stream) {
@@ -547,7 +749,40 @@ extern "C" int hn_det_decode_nms(const hn_det_desc* d, void* stream) {
     hn_det_segments_kernel<<<hn_cdiv(NA, 256), 256, 0, s>>>(ws.keys, NA, ws.seg_start, ws.seg_end);
     HN_CHECK_CUDA(cudaGetLastError());
     GridGeom geom = make_grid(d->img_h, d->img_w, d->iou_thres);
-    hn_det_nms_kernel<<<d->N * kMaxCls, kNmsChunk, 0, s>>>(ws, d->A, d->iou_thres, d->nms_mode, geom);
+    const bool parallel = geom.prune && !g_det_force_sequential;
+    if (parallel) {
+        HN_CHECK_CUDA(cudaMemsetAsync(ws.cell_start, 0, (size_t)d->N * kMaxCls * kCellStride * 4, s));
+        HN_CHECK_CUDA(cudaMemsetAsync(ws.cell_end, 0, (size_t)d->N * kMaxCls * kCellStride * 4, s));
+        hn_nms2_prepare_kernel<<<hn_cdiv(NA, 256), 256, 0, s>>>(ws, NA, d->A, d->nms_mode, geom);
+        HN_CHECK_CUDA(cudaGetLastError());
+        cub::DoubleBuffer<uint32_t> dk(ws.ckey, ws.ckey_alt);
+        cub::DoubleBuffer<int> dv(ws.cval, ws.cval_alt);
+        size_t tb = ws.cub2_bytes;
+        HN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub2_tmp, tb, dk, dv, (int)NA, 0, 32, s));
+        ws.ckey = dk.Current(); ws.ckey_alt = dk.Alternate();
+        ws.cval = dv.Current(); ws.cval_alt = dv.Alternate();
+        hn_nms2_cells_kernel<<<hn_cdiv(NA, 256), 256, 0, s>>>(ws, NA);
+        HN_CHECK_CUDA(cudaGetLastError());
+        hn_nms2_build_kernel<<<hn_cdiv(NA, 128), 128, 0, s>>>(ws, NA, d->nms_mode, d->iou_thres, geom);
+        HN_CHECK_CUDA(cudaGetLastError());
+        {
+            static int blocks_per_sm = 0;
+            if (blocks_per_sm == 0)
+                HN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, hn_nms2_rounds_kernel, 256, 0));
+            int sms = hn_device_sm_count();
+            long long want = (NA + 255) / 256, cap = (long long)sms * (blocks_per_sm > 0 ? blocks_per_sm : 1);
+            dim3 grid((unsigned)(want < cap ? want : cap));
+            long long na = NA;
+            void* args[] = {&ws, &na};
+            HN_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)hn_nms2_rounds_kernel, grid, dim3(256), args, 0, s));
+        }
+        tb = ws.cub2_bytes;
+        HN_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(ws.cub2_tmp, tb, ws.kflag, ws.kscan, (int)NA, s));
+        hn_nms2_compact_kernel<<<hn_cdiv(NA, 256), 256, 0, s>>>(ws, NA);
+        HN_CHECK_CUDA(cudaGetLastError());
+    }
+    // sequential kernel: whole problem when pruning is impossible (thr ~ 0), otherwise only flagged images
+    hn_det_nms_kernel<<<d->N * kMaxCls, kNmsChunk, 0, s>>>(ws, d->A, d->iou_thres, d->nms_mode, geom, parallel ? 1 : 0);
     HN_CHECK_CUDA(cudaGetLastError());
     hn_det_gather_kernel<<<d->N * kMaxCls, 256, 0, s>>>(ws, d->A, d->out_boxes, d->out_scores, d->out_class, d->out_count);
     HN_CHECK_CUDA(cudaGetLastError());

@@ -216,20 +216,30 @@ class LaneFuseSpec:
         nv.check(nv.lib.hn_plan_add_lanefuse(plan, self.to_desc()))
 
 
-class SeSpec:
-    kind, launches, group = "se", 2, "backbone"
+class SePoolSpec:
+    kind, launches, group, macs = "se_pool", 1, "backbone", 0
 
-    def __init__(self, name, x, pooled, hidden, counter, w1, b1, w2t, b2):
-        self.name, self.x, self.pooled, self.hidden, self.counter = name, x, pooled, hidden, counter
-        self.w1, self.b1, self.w2t, self.b2 = w1, b1, w2t, b2
-        self.macs = x.N * 2 * w1.shape[0] * w1.shape[1]
+    def __init__(self, name, x, partial, counter, mean):
+        self.name, self.x, self.partial, self.counter, self.mean = name, x, partial, counter, mean
 
     def to_desc(self):
-        return nv.SeDesc(self.x.to_c(), self.pooled.data_ptr(), self.hidden.data_ptr(), self.counter.data_ptr(),
-                         self.w1.data_ptr(), self.b1.data_ptr(), self.w2t.data_ptr(), self.b2.data_ptr(), self.w1.shape[0])
+        return nv.SePoolDesc(self.x.to_c(), self.partial.data_ptr(), self.counter.data_ptr(), self.mean.data_ptr())
 
     def add_to(self, plan):
-        nv.check(nv.lib.hn_plan_add_se(plan, self.to_desc()))
+        nv.check(nv.lib.hn_plan_add_se_pool(plan, self.to_desc()))
+
+
+class SeScaleSpec:
+    kind, launches, group, macs = "se_scale", 1, "backbone", 0
+
+    def __init__(self, name, x, scale):
+        self.name, self.x, self.scale = name, x, scale
+
+    def to_desc(self):
+        return nv.SeScaleDesc(self.x.to_c(), self.scale.data_ptr())
+
+    def add_to(self, plan):
+        nv.check(nv.lib.hn_plan_add_se_scale(plan, self.to_desc()))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -384,15 +394,9 @@ class Builder:
                 # grouped 3x3 (+BN+ReLU), stride st
                 g = self.buf(Ho, Wo, mid)
                 self.gconv(nm + ".c2", a, blk, g, st)
-                # squeeze-excite (in place)
+                # squeeze-excite (in place): pool -> FC1+ReLU -> FC2+sigmoid (GEMMs over all images) -> scale
                 if blk.se is not None:
-                    S = blk.se[1].weight.shape[0]
-                    pooled = torch.zeros((B, (Ho * Wo + 127) // 128, mid), dtype=torch.float32, device=self.dev)
-                    hidden = torch.zeros((B, S), dtype=torch.float32, device=self.dev)
-                    counter = torch.zeros((B,), dtype=torch.int32, device=self.dev)
-                    self.ops.append(SeSpec(nm + ".se", g.interior(), pooled, hidden, counter,
-                                           self.f32(blk.se[1].weight.reshape(S, mid)), self.f32(blk.se[1].bias),
-                                           self.f32(blk.se[3].weight.reshape(mid, S).t()), self.f32(blk.se[3].bias)))
+                    self.squeeze_excite(nm + ".se", g, blk.se)
                 # shortcut
                 if blk.shortcut is not None:
                     ws, bs = fold_bn(blk.shortcut[0].weight, None, blk.shortcut[1])
@@ -410,6 +414,37 @@ class Builder:
                 cur, curH, curW = ob, Ho, Wo
             feats.append(cur)
         return feats
+
+    def fc(self, name, vin_rows, w, b, out_t, act):
+        """rows x C matrix (a [1,1,rows,C] view) times w[cout, C] on the tensor cores, bf16 out_t [rows, cout]."""
+        cs = ConvSpec(name)
+        cs.group, cs.act = "backbone", act
+        cs.flat, cs.flat_hw = 1, vin_rows.W
+        cs.src = [vin_rows]
+        cs.out_t, cs.out_off = out_t, 0
+        cout = w.shape[0]
+        cs.out_strides = (vin_rows.W * cout, 0, cout)
+        cs.macs = vin_rows.W * cout * w.shape[1]
+        return self._finish(cs, [(0, 0, 0, w)], cout, b)
+
+    def squeeze_excite(self, name, g, se):
+        B, C, S = self.B, g.C, se[1].weight.shape[0]
+        Sp = (S + 7) // 8 * 8  # hidden width padded to the 16-byte channel granule
+        dev = self.dev
+        partial = torch.zeros((B, (g.H * g.W + 127) // 128, C), dtype=torch.float32, device=dev)
+        counter = torch.zeros((B,), dtype=torch.int32, device=dev)
+        mean = torch.zeros((B, C), dtype=self.dt, device=dev)
+        hidden = torch.zeros((B, Sp), dtype=self.dt, device=dev)
+        scale = torch.zeros((B, C), dtype=self.dt, device=dev)
+        self.ops.append(SePoolSpec(name + ".pool", g.interior(), partial, counter, mean))
+        w1 = torch.zeros((Sp, C), dtype=torch.float32, device=se[1].weight.device)
+        b1 = torch.zeros((Sp,), dtype=torch.float32, device=w1.device)
+        w1[:S], b1[:S] = se[1].weight.detach().float().reshape(S, C), se[1].bias.detach().float()
+        w2 = torch.zeros((C, Sp), dtype=torch.float32, device=w1.device)
+        w2[:, :S] = se[3].weight.detach().float().reshape(C, S)
+        self.fc(name + ".fc1", V(mean, 0, 1, 1, B, C, 0, 0, C), w1, b1, hidden, nv.ACT_RELU)
+        self.fc(name + ".fc2", V(hidden, 0, 1, 1, B, Sp, 0, 0, Sp), w2, se[3].bias.detach().float(), scale, nv.ACT_SIGMOID)
+        self.ops.append(SeScaleSpec(name + ".scale", g.interior(), scale))
 
     def gconv(self, name, a, blk, ob, stride):
         conv, bn = blk.conv_block_2[0], blk.conv_block_2[1]

@@ -184,12 +184,14 @@ def run_lanefuse(ls):
     ls.out.torch_view().copy_(y.permute(0, 2, 3, 1))
 
 
-def run_se(ss):
+def run_se_pool(ss):
     x = ss.x.torch_view()
-    m = x.float().mean(dim=(1, 2))
-    h = F.relu(m @ ss.w1.t() + ss.b1)
-    s = torch.sigmoid(h @ ss.w2t + ss.b2)
-    x.copy_((x.float() * s[:, None, None, :]).to(x.dtype))
+    ss.mean.copy_(x.float().mean(dim=(1, 2)).to(ss.mean.dtype))
+
+
+def run_se_scale(ss):
+    x = ss.x.torch_view()
+    x.copy_((x.float() * ss.scale.float()[:, None, None, :]).to(x.dtype))
 
 
 def run_stem(st):
@@ -198,7 +200,7 @@ def run_stem(st):
     st.out.torch_view().copy_(y.permute(0, 2, 3, 1))
 
 
-RUNNERS = {"conv": run_conv, "node": run_node, "pool": run_pool, "lanefuse": run_lanefuse, "se": run_se, "stem": run_stem}
+RUNNERS = {"conv": run_conv, "node": run_node, "pool": run_pool, "lanefuse": run_lanefuse, "se_pool": run_se_pool, "se_scale": run_se_scale, "stem": run_stem}
 
 
 def run_ops(ops):

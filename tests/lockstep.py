@@ -18,8 +18,10 @@ def _tensors_in(op):
         return [op.vin.t]
     if op.kind == "lanefuse":
         return [op.p3.t, op.p4.t, op.p5.t, op.p6.t]
-    if op.kind == "se":
+    if op.kind == "se_pool":
         return [op.x.t]
+    if op.kind == "se_scale":
+        return [op.x.t, op.scale]
     if op.kind == "stem":
         return [op.x]
     raise KeyError(op.kind)
@@ -34,7 +36,9 @@ def _tensors_out(op):
         return [op.vout.t]
     if op.kind == "lanefuse":
         return [op.out.t]
-    if op.kind == "se":
+    if op.kind == "se_pool":
+        return [op.mean]
+    if op.kind == "se_scale":
         return [op.x.t]
     if op.kind == "stem":
         return [op.out.t]

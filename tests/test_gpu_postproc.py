@@ -99,6 +99,46 @@ def test_det_decode_nms_bit_exact_vs_oracle(mode, pmode):
     _det_compare(out, ref, ties_as_sets=(pmode == "vanilla"))
 
 
+@pytest.mark.parametrize("force_seq", [0, 1])
+def test_det_dense_duplicates_overflow_and_sequential_path(force_seq):
+    """Hundreds of near-identical same-class boxes: more than 64 conflicting predecessors per box, so the
+    parallel path flags the image and the sequential kernel takes over; force_seq=1 runs the sequential
+    kernel for everything.  Both must equal the oracle bit for bit."""
+    H = W = 256
+    rng = np.random.default_rng(21)
+    anc, reg, cls = _synth_det(2, H, W, 17)
+    A = anc.shape[1]
+    # image 0: 400 anchors moved onto (almost) the same box, same class, distinct scores
+    idx = rng.choice(A, 400, replace=False)
+    pre = pr.bbox_transform_clip(anc.reshape(-1, 4), reg, H, W)
+    pre[0, idx] = np.array([60, 70, 150, 170], dtype=np.float32) + rng.uniform(-3, 3, (400, 4)).astype(np.float32)
+    cls[0, idx] = 0.01
+    cls[0, idx, 3] = rng.uniform(0.8, 0.99, 400).astype(np.float32)
+    nv.lib.hn_det_force_sequential(force_seq)
+    try:
+        boxes, scores, cids, count, _ = hb.DetectionHeader.decode_device((H, W), None, torch.from_numpy(cls).cuda(), None, 0.75, 0.3,
+                                                                         pre_boxes=torch.from_numpy(pre).cuda())
+        torch.cuda.synchronize()
+    finally:
+        nv.lib.hn_det_force_sequential(0)
+    ref = pr.det_postprocess(anc, reg, cls, H, W, 0.75, 0.3, device="cuda", pre_boxes=pre)
+    out = [{"rois": boxes[i, :int(count[i])].cpu().numpy(), "class_ids": cids[i, :int(count[i])].cpu().numpy(),
+            "scores": scores[i, :int(count[i])].cpu().numpy()} for i in range(2)]
+    _det_compare(out, ref)
+
+
+def test_det_iou_threshold_extremes():
+    """thr = 0 (any overlap suppresses; pruning disabled -> sequential kernel) and thr = 0.9."""
+    H = W = 128
+    anc, reg, cls = _synth_det(1, H, W, 19)
+    for thr in (0.0, 0.9):
+        boxes, scores, cids, count, _ = hb.DetectionHeader.decode_device((H, W), torch.from_numpy(reg).cuda(), torch.from_numpy(cls).cuda(),
+                                                                         torch.from_numpy(anc).cuda(), 0.7, thr)
+        ref = pr.det_postprocess(anc, reg, cls, H, W, 0.7, thr, device="cuda")
+        k = int(count[0])
+        _det_compare([{"rois": boxes[0, :k].cpu().numpy(), "class_ids": cids[0, :k].cpu().numpy(), "scores": scores[0, :k].cpu().numpy()}], ref)
+
+
 def test_det_public_decode_api_and_empty():
     H = W = 128
     anc, reg, cls = _synth_det(2, H, W, 7)
