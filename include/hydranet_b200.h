@@ -134,7 +134,8 @@ typedef struct hn_lanefuse_desc {
  * chunk order by the block that arrives last for its image.  `counter` must be zero on first use. */
 typedef struct hn_se_pool_desc {
     hn_view x;
-    float* partial;   /* scratch fp32 [N][ceil(H*W/128)][C] */
+    int32_t pix_per_block; /* pixels summed by one block (multiple of 128) */
+    float* partial;   /* scratch fp32 [N][ceil(H*W/pix_per_block)][C] */
     int32_t* counter; /* scratch int32 [N] */
     void* mean;       /* bf16 [N][C] */
 } hn_se_pool_desc;

@@ -63,7 +63,7 @@ class LaneFuseDesc(C.Structure):
 
 
 class SePoolDesc(C.Structure):
-    _fields_ = [("x", View), ("partial", C.c_void_p), ("counter", C.c_void_p), ("mean", C.c_void_p)]
+    _fields_ = [("x", View), ("pix_per_block", C.c_int32), ("partial", C.c_void_p), ("counter", C.c_void_p), ("mean", C.c_void_p)]
 
 
 class SeScaleDesc(C.Structure):

@@ -117,10 +117,8 @@ struct NodeParams {
     int swish;
     const float* dw;
     View out;
-    int tiles_x, tiles_y;
 };
 
-static constexpr int kNodeT = 8;
 
 __device__ __forceinline__ void node_fetch(const View& v, int mode, int n, int y, int x, int c, float (&f)[8]) {
     if (mode == HN_IN_SAME) {
@@ -149,67 +147,83 @@ __device__ __forceinline__ void node_fetch(const View& v, int mode, int n, int y
     }
 }
 
-__global__ void __launch_bounds__(256) hn_node_kernel(const __grid_constant__ NodeParams p) {
-    extern __shared__ float s_tile[];  // [(T+2)*(T+2)][C]
-    const int C = p.out.C, CV = C >> 3;
-    const int per_img = p.tiles_x * p.tiles_y;
-    const int n = blockIdx.x / per_img;
-    const int r = blockIdx.x - n * per_img;
-    const int y0 = (r / p.tiles_x) * kNodeT, x0 = (r % p.tiles_x) * kNodeT;
-    const int HT = kNodeT + 2;
-    for (int it = threadIdx.x; it < HT * HT * CV; it += blockDim.x) {
-        int cv = it % CV, px = it / CV;
-        int hy = px / HT, hx = px - hy * HT;
-        int y = y0 + hy - 1, x = x0 + hx - 1;
-        float acc[8];
+static constexpr int kNodeStrip = 8;  // output rows per thread
+
+// fused value (weighted sum -> swish) of one 8-channel vector at (y, x); zero outside the image (the depthwise
+// conv's zero padding)
+__device__ __forceinline__ void node_value(const NodeParams& p, int n, int y, int x, int c, float (&acc)[8]) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-        if (y >= 0 && y < p.out.H && x >= 0 && x < p.out.W) {
-            for (int i = 0; i < p.n_in; ++i) {
-                float f[8];
-                node_fetch(p.in[i], p.mode[i], n, y, x, cv * 8, f);
-                // the reference evaluates w0*a + w1*b (+ w2*c) left to right in fp32 (bifpn.py:170-231)
-                if (i == 0) {
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    if (y < 0 || y >= p.out.H || x < 0 || x >= p.out.W) return;
+    for (int i = 0; i < p.n_in; ++i) {
+        float f[8];
+        node_fetch(p.in[i], p.mode[i], n, y, x, c, f);
+        // the reference evaluates w0*a + w1*b (+ w2*c) left to right in fp32 (bifpn.py:170-231)
+        const float w = p.w[i];
+        if (i == 0) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] = p.w[0] * f[j];
-                } else {
+            for (int j = 0; j < 8; ++j) acc[j] = w * f[j];
+        } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] = acc[j] + p.w[i] * f[j];
-                }
-            }
-            if (p.swish) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = acc[j] * hn_sigmoid(acc[j]);
-            }
+            for (int j = 0; j < 8; ++j) acc[j] = acc[j] + w * f[j];
         }
-        float4* dst = reinterpret_cast<float4*>(s_tile + (long long)px * C + cv * 8);
-        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
-    __syncthreads();
-    for (int it = threadIdx.x; it < kNodeT * kNodeT * CV; it += blockDim.x) {
-        int cv = it % CV, px = it / CV;
-        int ty = px / kNodeT, tx = px - ty * kNodeT;
-        int y = y0 + ty, x = x0 + tx;
-        if (y >= p.out.H || x >= p.out.W) continue;
+    if (p.swish) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = acc[j] * hn_sigmoid(acc[j]);
+    }
+}
+
+// One thread = one (image, column x, 8-channel vector) and a strip of kNodeStrip output rows.  It keeps a
+// 3x3 window of fused values in registers and slides it down the strip: every fused value is computed by the
+// three threads that need it (x-1, x, x+1; the loads hit L1), nothing goes through shared memory and there
+// is no barrier.  Consecutive threads own consecutive channel vectors of a pixel: fully coalesced.
+__global__ void __launch_bounds__(256, 2) hn_node_kernel(const __grid_constant__ NodeParams p) {
+    const int C = p.out.C, CV = C >> 3;
+    const int strips = (p.out.H + kNodeStrip - 1) / kNodeStrip;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)p.out.N * strips * p.out.W * CV;
+    if (idx >= total) return;
+    const int cv = (int)(idx % CV);
+    long long t = idx / CV;
+    const int x = (int)(t % p.out.W);
+    t /= p.out.W;
+    const int strip = (int)(t % strips);
+    const int n = (int)(t / strips);
+    const int c = cv * 8;
+    const int y0 = strip * kNodeStrip;
+    const int y1 = min(y0 + kNodeStrip, p.out.H);
+    float win[3][3][8];  // [row][col][channel]
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) node_value(p, n, y0 - 1 + r, x - 1 + dx, c, win[r][dx]);
+    for (int y = y0; y < y1; ++y) {
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) node_value(p, n, y + 1, x - 1 + dx, c, win[2][dx]);
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
+        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                const float4* sv = reinterpret_cast<const float4*>(s_tile + (long long)((ty + ky) * HT + tx + kx) * C + cv * 8);
-                const float4* wv = reinterpret_cast<const float4*>(p.dw + (ky * 3 + kx) * C + cv * 8);
-                float4 a0 = sv[0], a1 = sv[1];
-                float4 w0 = __ldg(wv), w1 = __ldg(wv + 1);
-                acc[0] = fmaf(a0.x, w0.x, acc[0]); acc[1] = fmaf(a0.y, w0.y, acc[1]);
-                acc[2] = fmaf(a0.z, w0.z, acc[2]); acc[3] = fmaf(a0.w, w0.w, acc[3]);
-                acc[4] = fmaf(a1.x, w1.x, acc[4]); acc[5] = fmaf(a1.y, w1.y, acc[5]);
-                acc[6] = fmaf(a1.z, w1.z, acc[6]); acc[7] = fmaf(a1.w, w1.w, acc[7]);
+                const float4* wv = reinterpret_cast<const float4*>(p.dw + (ky * 3 + kx) * C + c);  // L1-resident
+                const float4 w0 = __ldg(wv), w1 = __ldg(wv + 1);
+                const float (&v)[8] = win[ky][kx];
+                acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]);
+                acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
+                acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]);
+                acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
             }
-        }
-        store8(const_cast<bf16*>(vptr(p.out, n, y, x, cv * 8)), acc);
+        store8(const_cast<bf16*>(vptr(p.out, n, y, x, c)), acc);
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                win[0][dx][j] = win[1][dx][j];
+                win[1][dx][j] = win[2][dx][j];
+            }
     }
 }
 
@@ -238,16 +252,9 @@ extern "C" int hn_node_fwd(const hn_node_desc* d, void* stream) {
     p.swish = d->swish;
     p.dw = d->dw;
     p.out = to_view(d->out);
-    p.tiles_x = hn_cdiv(d->out.W, kNodeT);
-    p.tiles_y = hn_cdiv(d->out.H, kNodeT);
-    size_t smem = (size_t)(kNodeT + 2) * (kNodeT + 2) * d->out.C * sizeof(float);
-    HN_REQUIRE(smem <= 200 * 1024, "node: C=%d too large for the halo tile", d->out.C);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        HN_CHECK_CUDA(cudaFuncSetAttribute(hn_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
-    hn_node_kernel<<<p.tiles_x * p.tiles_y * d->out.N, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    const int strips = (d->out.H + kNodeStrip - 1) / kNodeStrip;
+    long long total = (long long)d->out.N * strips * d->out.W * (d->out.C / 8);
+    hn_node_kernel<<<hn_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }
@@ -390,18 +397,17 @@ extern "C" int hn_lanefuse_fwd(const hn_lanefuse_desc* d, void* stream) {
 // squeeze-excite: global average pool (deterministic) and in-place channel scaling; the two FC layers
 // in between run as tensor-core GEMMs over all images at once (engine.py)
 // ------------------------------------------------------------------------------------------------
-static constexpr int kSePix = 128;      // pixels per block
 static constexpr int kSeThreads = 512;
 
 __global__ void __launch_bounds__(kSeThreads) hn_se_pool_kernel(View x, float* __restrict__ partial, int* __restrict__ counter,
-                                                                bf16* __restrict__ mean_out, float inv_hw) {
+                                                                bf16* __restrict__ mean_out, float inv_hw, int kSePix) {
     extern __shared__ float sm[];  // [lanes][C] partial sums
     __shared__ int s_last;
     const int C = x.C, CV = C >> 3;
     const int n = blockIdx.y;
     const int HW = x.H * x.W;
     const int p0 = blockIdx.x * kSePix, p1 = min(p0 + kSePix, HW);
-    const int lanes = min(blockDim.x / CV, kSePix);
+    const int lanes = blockDim.x / CV;
     const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
     if (pl < lanes) {
         float acc[8];
@@ -472,13 +478,13 @@ extern "C" int hn_se_pool_fwd(const hn_se_pool_desc* d, void* stream) {
     if (int rc = check_view(d->x, "se_pool.x")) return rc;
     const int C = d->x.C, CV = C / 8, HW = d->x.H * d->x.W;
     HN_REQUIRE(CV <= kSeThreads, "se_pool: C=%d too wide", C);
-    dim3 grid(hn_cdiv(HW, kSePix), d->x.N);
+    HN_REQUIRE(d->pix_per_block >= 128 && d->pix_per_block % 128 == 0, "se_pool: pix_per_block must be a multiple of 128");
+    dim3 grid(hn_cdiv(HW, d->pix_per_block), d->x.N);
     int lanes = kSeThreads / CV;
-    if (lanes > kSePix) lanes = kSePix;
     size_t smem = (size_t)lanes * C * sizeof(float);
     HN_REQUIRE(smem <= 48 * 1024, "se_pool: shared memory");
     hn_se_pool_kernel<<<grid, kSeThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-        to_view(d->x), d->partial, d->counter, reinterpret_cast<bf16*>(d->mean), 1.0f / (float)HW);
+        to_view(d->x), d->partial, d->counter, reinterpret_cast<bf16*>(d->mean), 1.0f / (float)HW, d->pix_per_block);
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }

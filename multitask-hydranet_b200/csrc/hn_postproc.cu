@@ -146,6 +146,7 @@ static constexpr int kGridHeads = 6144;
 struct GridGeom {
     int nlev, delta, prune;
     float c0;
+    float rfac;  // IoU > thr needs IoU_x > thr, i.e. |centre offset| < (w1+w2)/2 * (1-thr)/(1+thr) (same in y)
     int nx[kGridLevels], ny[kGridLevels], base[kGridLevels];
 };
 
@@ -170,6 +171,7 @@ static GridGeom make_grid(int img_h, int img_w, float iou_thr) {
     int d = 1;
     if (g.prune) { float r = 1.0f / iou_thr; while ((float)(1 << (d - 1)) < r) ++d; }  // floor(log2(1/thr)) + 1 or more
     g.delta = g.prune ? d : kGridLevels;
+    g.rfac = g.prune ? (1.0f - iou_thr) / (1.0f + iou_thr) * 1.0001f : 1.0f;
     return g;
 }
 
@@ -407,7 +409,7 @@ __global__ void __launch_bounds__(kNmsChunk) hn_det_nms_kernel(DetWs ws, int A, 
                     const int nx = g.nx[l], ny = g.ny[l];
                     int x_lo = 0, x_hi = 0, y_lo = 0, y_hi = 0;
                     if (nx * ny > 1) {
-                        const float rx = 0.5f * fmaxf(wj, 0.0f) + cl + 1.0f, ry = 0.5f * fmaxf(hj, 0.0f) + cl + 1.0f;
+                        const float rx = g.rfac * (0.5f * fmaxf(wj, 0.0f) + cl) + 1.0f, ry = g.rfac * (0.5f * fmaxf(hj, 0.0f) + cl) + 1.0f;
                         x_lo = clampi((int)floorf((cx - rx) * inv), 0, nx - 1);
                         x_hi = clampi((int)floorf((cx + rx) * inv), 0, nx - 1);
                         y_lo = clampi((int)floorf((cy - ry) * inv), 0, ny - 1);
@@ -557,8 +559,11 @@ __global__ void hn_nms2_cells_kernel(DetWs ws, long long NA) {
     if (q + 1 == NA || ws.ckey[q + 1] != ck) ws.cell_end[ck] = (int)(q + 1);
 }
 
-__global__ void __launch_bounds__(128) hn_nms2_build_kernel(DetWs ws, long long NA, int nms_mode, float iou_thr, GridGeom g) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per candidate: the lanes stride over the members of every cell in the candidate's window
+// (coalesced index / box loads, no divergence between candidates), conflicts are appended with a ballot
+__global__ void __launch_bounds__(256) hn_nms2_build_kernel(DetWs ws, long long NA, int nms_mode, float iou_thr, GridGeom g) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (i >= NA) return;
     const uint64_t key = ws.keys[i];
     if (key == ~0ull) return;
@@ -571,14 +576,14 @@ __global__ void __launch_bounds__(128) hn_nms2_build_kernel(DetWs ws, long long 
     const int t = grid_level(fmaxf(wj, hj), g);
     const int l_lo = max(0, t - g.delta), l_hi = min(g.nlev - 1, t + g.delta);
     int* my = ws.preds + i * kMaxPreds;
-    int cnt = 0;
+    int cnt = 0;  // warp-uniform
     for (int l = l_lo; l <= l_hi; ++l) {
         const float cl = g.c0 * (float)(1 << l);
         const float inv = 1.0f / cl;
         const int nx = g.nx[l], ny = g.ny[l];
         int x_lo = 0, x_hi = 0, y_lo = 0, y_hi = 0;
         if (nx * ny > 1) {
-            const float rx = 0.5f * fmaxf(wj, 0.0f) + cl + 1.0f, ry = 0.5f * fmaxf(hj, 0.0f) + cl + 1.0f;
+            const float rx = g.rfac * (0.5f * fmaxf(wj, 0.0f) + cl) + 1.0f, ry = g.rfac * (0.5f * fmaxf(hj, 0.0f) + cl) + 1.0f;
             x_lo = clampi((int)floorf((cx - rx) * inv), 0, nx - 1);
             x_hi = clampi((int)floorf((cx + rx) * inv), 0, nx - 1);
             y_lo = clampi((int)floorf((cy - ry) * inv), 0, ny - 1);
@@ -587,22 +592,35 @@ __global__ void __launch_bounds__(128) hn_nms2_build_kernel(DetWs ws, long long 
         for (int yy = y_lo; yy <= y_hi; ++yy) {
             for (int xx = x_lo; xx <= x_hi; ++xx) {
                 const uint32_t ck = (uint32_t)seg * kCellStride + (uint32_t)(g.base[l] + yy * nx + xx);
-                const int e = ws.cell_end[ck];
-                for (int q = ws.cell_start[ck]; q < e; ++q) {
-                    const int m = ws.cval[q];
-                    if (m >= i) break;  // members of a cell are in priority order: only earlier boxes matter
-                    const float4 kb = ws.cbox[q];
-                    if (iou_gt(kb, box_area(kb), b, area, iou_thr)) {
-                        if (cnt < kMaxPreds) my[cnt] = m;
-                        ++cnt;
+                const int s0 = ws.cell_start[ck], e = ws.cell_end[ck];
+                for (int q0 = s0; q0 < e; q0 += 32) {
+                    const int q = q0 + lane;
+                    int m = 0x7FFFFFFF;
+                    bool hit = false;
+                    if (q < e) {
+                        m = ws.cval[q];
+                        if (m < i) {
+                            const float4 kb = ws.cbox[q];
+                            hit = iou_gt(kb, box_area(kb), b, area, iou_thr);
+                        }
                     }
+                    const unsigned hm = __ballot_sync(0xffffffffu, hit);
+                    if (hit) {
+                        const int pos = cnt + __popc(hm & ((1u << lane) - 1u));
+                        if (pos < kMaxPreds) my[pos] = m;
+                    }
+                    cnt += __popc(hm);
+                    // members of a cell are in priority order: once one is not earlier than i, the rest are not either
+                    if (__any_sync(0xffffffffu, q < e && m >= i)) break;
                 }
             }
         }
     }
-    ws.npred[i] = min(cnt, kMaxPreds);
-    if (cnt > kMaxPreds) ws.overflow[n] = 1;
-    ws.status[i] = cnt == 0 ? 1 : 0;
+    if (lane == 0) {
+        ws.npred[i] = min(cnt, kMaxPreds);
+        if (cnt > kMaxPreds) ws.overflow[n] = 1;
+        ws.status[i] = cnt == 0 ? 1 : 0;
+    }
 }
 
 __global__ void __launch_bounds__(256) hn_nms2_rounds_kernel(DetWs ws, long long NA) {
@@ -763,7 +781,7 @@ extern "C" int hn_det_decode_nms(const hn_det_desc* d, void* stream) {
         ws.cval = dv.Current(); ws.cval_alt = dv.Alternate();
         hn_nms2_cells_kernel<<<hn_cdiv(NA, 256), 256, 0, s>>>(ws, NA);
         HN_CHECK_CUDA(cudaGetLastError());
-        hn_nms2_build_kernel<<<hn_cdiv(NA, 128), 128, 0, s>>>(ws, NA, d->nms_mode, d->iou_thres, geom);
+        hn_nms2_build_kernel<<<hn_cdiv(NA * 32, 256), 256, 0, s>>>(ws, NA, d->nms_mode, d->iou_thres, geom);
         HN_CHECK_CUDA(cudaGetLastError());
         {
             static int blocks_per_sm = 0;

@@ -219,11 +219,11 @@ class LaneFuseSpec:
 class SePoolSpec:
     kind, launches, group, macs = "se_pool", 1, "backbone", 0
 
-    def __init__(self, name, x, partial, counter, mean):
-        self.name, self.x, self.partial, self.counter, self.mean = name, x, partial, counter, mean
+    def __init__(self, name, x, pix, partial, counter, mean):
+        self.name, self.x, self.pix, self.partial, self.counter, self.mean = name, x, pix, partial, counter, mean
 
     def to_desc(self):
-        return nv.SePoolDesc(self.x.to_c(), self.partial.data_ptr(), self.counter.data_ptr(), self.mean.data_ptr())
+        return nv.SePoolDesc(self.x.to_c(), self.pix, self.partial.data_ptr(), self.counter.data_ptr(), self.mean.data_ptr())
 
     def add_to(self, plan):
         nv.check(nv.lib.hn_plan_add_se_pool(plan, self.to_desc()))
@@ -425,18 +425,21 @@ class Builder:
         cout = w.shape[0]
         cs.out_strides = (vin_rows.W * cout, 0, cout)
         cs.macs = vin_rows.W * cout * w.shape[1]
-        return self._finish(cs, [(0, 0, 0, w)], cout, b)
+        # one M tile only (rows = batch): narrow N tiles spread the weight read over many SMs
+        return self._finish(cs, [(0, 0, 0, w)], cout, b, bn=16 if cout <= 256 else 64)
 
     def squeeze_excite(self, name, g, se):
         B, C, S = self.B, g.C, se[1].weight.shape[0]
         Sp = (S + 7) // 8 * 8  # hidden width padded to the 16-byte channel granule
         dev = self.dev
-        partial = torch.zeros((B, (g.H * g.W + 127) // 128, C), dtype=torch.float32, device=dev)
+        hw = g.H * g.W
+        pix = min(2048, max(128, (hw // 16 + 127) // 128 * 128))  # ~16 blocks per image, 128..2048 pixels each
+        partial = torch.zeros((B, (hw + pix - 1) // pix, C), dtype=torch.float32, device=dev)
         counter = torch.zeros((B,), dtype=torch.int32, device=dev)
         mean = torch.zeros((B, C), dtype=self.dt, device=dev)
         hidden = torch.zeros((B, Sp), dtype=self.dt, device=dev)
         scale = torch.zeros((B, C), dtype=self.dt, device=dev)
-        self.ops.append(SePoolSpec(name + ".pool", g.interior(), partial, counter, mean))
+        self.ops.append(SePoolSpec(name + ".pool", g.interior(), pix, partial, counter, mean))
         w1 = torch.zeros((Sp, C), dtype=torch.float32, device=se[1].weight.device)
         b1 = torch.zeros((Sp,), dtype=torch.float32, device=w1.device)
         w1[:S], b1[:S] = se[1].weight.detach().float().reshape(S, C), se[1].bias.detach().float()

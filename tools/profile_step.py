@@ -32,6 +32,10 @@ def main():
                 if op.kind == "conv":
                     extra = "taps=%d bn=%d stages=%d cout=%d flat=%d tile=%s src=%d" % (len(op.taps), op.bn, op.stages, op.cout, op.flat, op.tile, len(op.src))
                 f.write("%4d %-30s %-8s launches=%d %s\n" % (i, op.name, op.kind, op.launches, extra))
+        convs = [op.name for op in plan.ops if op.kind == "conv"]
+        with open(os.path.join(ROOT, "gpurun_out", "conv_index.txt"), "w") as f:
+            for want in ("seg.d2", "seg.d3.p00", "seg.out", "backbone.s4.b5.c1"):
+                f.write("%s %d\n" % (want, convs.index(want)))
         torch.cuda.profiler.start()
         out = m(x)
         bench.postproc(hb, m, out, codec, ws)
