@@ -147,7 +147,9 @@ __device__ __forceinline__ void node_fetch(const View& v, int mode, int n, int y
     }
 }
 
-static constexpr int kNodeStrip = 8;  // output rows per thread
+static constexpr int kNodeTH = 8, kNodeTW = 16;         // output tile
+static constexpr int kNodeHH = kNodeTH + 2, kNodeHW = kNodeTW + 2;  // halo tile
+static constexpr int kNodeRows = 16;                      // threadIdx.y extent
 
 // fused value (weighted sum -> swish) of one 8-channel vector at (y, x); zero outside the image (the depthwise
 // conv's zero padding)
@@ -174,56 +176,57 @@ __device__ __forceinline__ void node_value(const NodeParams& p, int n, int y, in
     }
 }
 
-// One thread = one (image, column x, 8-channel vector) and a strip of kNodeStrip output rows.  It keeps a
-// 3x3 window of fused values in registers and slides it down the strip: every fused value is computed by the
-// three threads that need it (x-1, x, x+1; the loads hit L1), nothing goes through shared memory and there
-// is no barrier.  Consecutive threads own consecutive channel vectors of a pixel: fully coalesced.
-__global__ void __launch_bounds__(256, 2) hn_node_kernel(const __grid_constant__ NodeParams p) {
-    const int C = p.out.C, CV = C >> 3;
-    const int strips = (p.out.H + kNodeStrip - 1) / kNodeStrip;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)p.out.N * strips * p.out.W * CV;
-    if (idx >= total) return;
-    const int cv = (int)(idx % CV);
-    long long t = idx / CV;
-    const int x = (int)(t % p.out.W);
-    t /= p.out.W;
-    const int strip = (int)(t % strips);
-    const int n = (int)(t / strips);
-    const int c = cv * 8;
-    const int y0 = strip * kNodeStrip;
-    const int y1 = min(y0 + kNodeStrip, p.out.H);
-    float win[3][3][8];  // [row][col][channel]
+// CTA = (C/8) x 16 threads; threadIdx.x is the 8-channel vector (a pixel's channels are contiguous: coalesced),
+// threadIdx.y strides over pixels.  Phase 1 computes the fused value of the (8+2)x(16+2) halo tile once into
+// shared memory (fp32); phase 2 runs the depthwise taps from there with the 9x8 weights of the thread's
+// channel vector held in registers.
+__global__ void __launch_bounds__(256) hn_node_kernel(const __grid_constant__ NodeParams p) {
+    extern __shared__ float s_tile[];  // [kNodeHH * kNodeHW][C]
+    const int C = p.out.C;
+    const int cv = threadIdx.x, c = cv * 8;
+    const int tiles_x = (p.out.W + kNodeTW - 1) / kNodeTW, tiles_y = (p.out.H + kNodeTH - 1) / kNodeTH;
+    const int per_img = tiles_x * tiles_y;
+    const int n = blockIdx.x / per_img;
+    const int r = blockIdx.x - n * per_img;
+    const int y0 = (r / tiles_x) * kNodeTH, x0 = (r % tiles_x) * kNodeTW;
+    for (int hp = threadIdx.y; hp < kNodeHH * kNodeHW; hp += kNodeRows) {
+        const int hy = hp / kNodeHW, hx = hp - hy * kNodeHW;
+        float acc[8];
+        node_value(p, n, y0 + hy - 1, x0 + hx - 1, c, acc);
+        float4* dst = reinterpret_cast<float4*>(s_tile + hp * C + c);
+        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    float wgt[9][8];
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) node_value(p, n, y0 - 1 + r, x - 1 + dx, c, win[r][dx]);
-    for (int y = y0; y < y1; ++y) {
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) node_value(p, n, y + 1, x - 1 + dx, c, win[2][dx]);
+    for (int k = 0; k < 9; ++k) {
+        const float4* wv = reinterpret_cast<const float4*>(p.dw + k * C + c);
+        const float4 w0 = __ldg(wv), w1 = __ldg(wv + 1);
+        wgt[k][0] = w0.x; wgt[k][1] = w0.y; wgt[k][2] = w0.z; wgt[k][3] = w0.w;
+        wgt[k][4] = w1.x; wgt[k][5] = w1.y; wgt[k][6] = w1.z; wgt[k][7] = w1.w;
+    }
+    __syncthreads();
+    for (int op = threadIdx.y; op < kNodeTH * kNodeTW; op += kNodeRows) {
+        const int ty = op / kNodeTW, tx = op - ty * kNodeTW;
+        const int y = y0 + ty, x = x0 + tx;
+        if (y >= p.out.H || x >= p.out.W) continue;
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+        for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                const float4* wv = reinterpret_cast<const float4*>(p.dw + (ky * 3 + kx) * C + c);  // L1-resident
-                const float4 w0 = __ldg(wv), w1 = __ldg(wv + 1);
-                const float (&v)[8] = win[ky][kx];
-                acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]);
-                acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
-                acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]);
-                acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
+                const float4* sv = reinterpret_cast<const float4*>(s_tile + ((ty + ky) * kNodeHW + tx + kx) * C + c);
+                const float4 a0 = sv[0], a1 = sv[1];
+                const float (&w)[8] = wgt[ky * 3 + kx];
+                acc[0] = fmaf(a0.x, w[0], acc[0]); acc[1] = fmaf(a0.y, w[1], acc[1]);
+                acc[2] = fmaf(a0.z, w[2], acc[2]); acc[3] = fmaf(a0.w, w[3], acc[3]);
+                acc[4] = fmaf(a1.x, w[4], acc[4]); acc[5] = fmaf(a1.y, w[5], acc[5]);
+                acc[6] = fmaf(a1.z, w[6], acc[6]); acc[7] = fmaf(a1.w, w[7], acc[7]);
             }
+        }
         store8(const_cast<bf16*>(vptr(p.out, n, y, x, c)), acc);
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                win[0][dx][j] = win[1][dx][j];
-                win[1][dx][j] = win[2][dx][j];
-            }
     }
 }
 
@@ -252,9 +255,16 @@ extern "C" int hn_node_fwd(const hn_node_desc* d, void* stream) {
     p.swish = d->swish;
     p.dw = d->dw;
     p.out = to_view(d->out);
-    const int strips = (d->out.H + kNodeStrip - 1) / kNodeStrip;
-    long long total = (long long)d->out.N * strips * d->out.W * (d->out.C / 8);
-    hn_node_kernel<<<hn_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    const int CV = d->out.C / 8;
+    HN_REQUIRE(CV >= 1 && CV * kNodeRows <= 256, "node: C=%d not supported (at most 128 channels)", d->out.C);
+    const int tiles = hn_cdiv(d->out.W, kNodeTW) * hn_cdiv(d->out.H, kNodeTH);
+    size_t smem = (size_t)kNodeHH * kNodeHW * d->out.C * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        HN_CHECK_CUDA(cudaFuncSetAttribute(hn_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    hn_node_kernel<<<tiles * d->out.N, dim3(CV, kNodeRows), smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }

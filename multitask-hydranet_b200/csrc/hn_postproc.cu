@@ -119,8 +119,8 @@ struct DetWs {
     int* cval;           // [N*A] sorted position, and the cell-ordered permutation
     int* cval_alt;
     float4* cbox;        // [N*A] boxes in cell order
-    int* cell_start;     // [N*16*kCellStride] first / one-past-last cell-order index of every cell
-    int* cell_end;
+    int* cell_cnt;       // [N*16*kCellStride + 1] members per (segment, cell) ...
+    int* cell_begin;     // ... and its exclusive scan = first cell-order index of every cell (rows are contiguous)
     int* preds;          // [N*A][kMaxPreds] earlier boxes of the same class with IoU > thr
     int* npred;          // [N*A]
     unsigned char* status; // [N*A] 0 undecided, 1 kept, 2 suppressed
@@ -213,8 +213,8 @@ static size_t det_layout(int N, int A, void* base, DetWs* ws) {
     w.cval = reinterpret_cast<int*>(take(NA * 4));
     w.cval_alt = reinterpret_cast<int*>(take(NA * 4));
     w.cbox = reinterpret_cast<float4*>(take(NA * 16));
-    w.cell_start = reinterpret_cast<int*>(take((size_t)N * kMaxCls * kCellStride * 4));
-    w.cell_end = reinterpret_cast<int*>(take((size_t)N * kMaxCls * kCellStride * 4));
+    w.cell_cnt = reinterpret_cast<int*>(take(((size_t)N * kMaxCls * kCellStride + 1) * 4));
+    w.cell_begin = reinterpret_cast<int*>(take(((size_t)N * kMaxCls * kCellStride + 1) * 4));
     w.preds = reinterpret_cast<int*>(take(NA * kMaxPreds * 4));
     w.npred = reinterpret_cast<int*>(take(NA * 4));
     w.status = reinterpret_cast<unsigned char*>(take(NA));
@@ -227,7 +227,8 @@ static size_t det_layout(int N, int A, void* base, DetWs* ws) {
         cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr);
         cub::DoubleBuffer<int> dv(nullptr, nullptr);
         cub::DeviceRadixSort::SortPairs(nullptr, b1, dk, dv, (int)NA, 0, 32, (cudaStream_t)0);
-        cub::DeviceScan::ExclusiveSum(nullptr, b2, (int*)nullptr, (int*)nullptr, (int)NA, (cudaStream_t)0);
+        long long T = (long long)N * kMaxCls * kCellStride + 1;
+        cub::DeviceScan::ExclusiveSum(nullptr, b2, (int*)nullptr, (int*)nullptr, (int)(T > NA ? T : NA), (cudaStream_t)0);
         w.cub2_bytes = b1 > b2 ? b1 : b2;
     }
     w.cub2_tmp = take(w.cub2_bytes);
@@ -546,7 +547,9 @@ __global__ void hn_nms2_prepare_kernel(DetWs ws, long long NA, int A, int nms_mo
         b.x = __fadd_rn(b.x, off); b.y = __fadd_rn(b.y, off); b.z = __fadd_rn(b.z, off); b.w = __fadd_rn(b.w, off);
     }
     ws.sbox[i] = b;
-    ws.ckey[i] = (uint32_t)seg * kCellStride + (uint32_t)grid_cell(b, off, g);
+    const uint32_t ck = (uint32_t)seg * kCellStride + (uint32_t)grid_cell(b, off, g);
+    ws.ckey[i] = ck;
+    atomicAdd(ws.cell_cnt + ck, 1);
 }
 
 __global__ void hn_nms2_cells_kernel(DetWs ws, long long NA) {
@@ -555,68 +558,91 @@ __global__ void hn_nms2_cells_kernel(DetWs ws, long long NA) {
     const uint32_t ck = ws.ckey[q];
     if (ck == 0xFFFFFFFFu) return;
     ws.cbox[q] = ws.sbox[ws.cval[q]];
-    if (q == 0 || ws.ckey[q - 1] != ck) ws.cell_start[ck] = (int)q;
-    if (q + 1 == NA || ws.ckey[q + 1] != ck) ws.cell_end[ck] = (int)(q + 1);
 }
 
-// one warp per candidate: the lanes stride over the members of every cell in the candidate's window
-// (coalesced index / box loads, no divergence between candidates), conflicts are appended with a ballot
+// Eight lanes per candidate.  Cells of one grid row are consecutive in cell order, so the members of the
+// cells x_lo..x_hi of a window row form ONE contiguous index range: the group strides over it with coalesced
+// index / box loads; conflicts with earlier boxes are appended through a ballot.
+static constexpr int kBuildLanes = 8;
 __global__ void __launch_bounds__(256) hn_nms2_build_kernel(DetWs ws, long long NA, int nms_mode, float iou_thr, GridGeom g) {
-    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (i >= NA) return;
-    const uint64_t key = ws.keys[i];
-    if (key == ~0ull) return;
-    const int seg = (int)(key >> kClsShift), n = seg / kMaxCls, cls = seg % kMaxCls;
-    const float offset = seg_offset(ws, n, cls, nms_mode);
-    const float4 b = ws.sbox[i];
-    const float area = box_area(b);
-    const float wj = b.z - b.x, hj = b.w - b.y;
-    const float cx = 0.5f * (b.x + b.z) - offset, cy = 0.5f * (b.y + b.w) - offset;
-    const int t = grid_level(fmaxf(wj, hj), g);
-    const int l_lo = max(0, t - g.delta), l_hi = min(g.nlev - 1, t + g.delta);
-    int* my = ws.preds + i * kMaxPreds;
-    int cnt = 0;  // warp-uniform
-    for (int l = l_lo; l <= l_hi; ++l) {
-        const float cl = g.c0 * (float)(1 << l);
-        const float inv = 1.0f / cl;
-        const int nx = g.nx[l], ny = g.ny[l];
-        int x_lo = 0, x_hi = 0, y_lo = 0, y_hi = 0;
-        if (nx * ny > 1) {
-            const float rx = g.rfac * (0.5f * fmaxf(wj, 0.0f) + cl) + 1.0f, ry = g.rfac * (0.5f * fmaxf(hj, 0.0f) + cl) + 1.0f;
-            x_lo = clampi((int)floorf((cx - rx) * inv), 0, nx - 1);
-            x_hi = clampi((int)floorf((cx + rx) * inv), 0, nx - 1);
-            y_lo = clampi((int)floorf((cy - ry) * inv), 0, ny - 1);
-            y_hi = clampi((int)floorf((cy + ry) * inv), 0, ny - 1);
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kBuildLanes;
+    const int lane = threadIdx.x & 31, sub = lane & (kBuildLanes - 1), grp_shift = lane & ~(kBuildLanes - 1);
+    const unsigned grp_mask = ((1u << kBuildLanes) - 1u) << grp_shift;
+    uint64_t key = ~0ull;
+    if (i < NA) key = ws.keys[i];
+    const bool active = key != ~0ull;  // inactive groups still take part in the warp-wide ballots
+    int seg = 0, n = 0;
+    float offset = 0.0f, area = 0.0f, wj = 0.0f, hj = 0.0f, cx = 0.0f, cy = 0.0f;
+    float4 b = make_float4(0, 0, 0, 0);
+    int l_lo = 0, l_hi = -1;
+    if (active) {
+        seg = (int)(key >> kClsShift);
+        n = seg / kMaxCls;
+        offset = seg_offset(ws, n, seg % kMaxCls, nms_mode);
+        b = ws.sbox[i];
+        area = box_area(b);
+        wj = b.z - b.x; hj = b.w - b.y;
+        cx = 0.5f * (b.x + b.z) - offset; cy = 0.5f * (b.y + b.w) - offset;
+        const int t = grid_level(fmaxf(wj, hj), g);
+        l_lo = max(0, t - g.delta); l_hi = min(g.nlev - 1, t + g.delta);
+    }
+    int* my = ws.preds + (active ? i : 0) * kMaxPreds;
+    int cnt = 0;  // group-uniform
+    // the loops are warp-uniform in structure: every group walks its own (level, row, range) sequence, and the
+    // warp iterates until all four groups are done
+    int l = l_lo, yy = 0, y_hi = -1, q = 0, q_end = 0;
+    bool row_ready = false;
+    while (true) {
+        // advance to the next non-empty range of this group
+        while (active && !row_ready && l <= l_hi) {
+            const float cl = g.c0 * (float)(1 << l);
+            const float inv = 1.0f / cl;
+            const int nx = g.nx[l], ny = g.ny[l];
+            int x_lo = 0, x_hi = 0, y_lo = 0;
+            if (yy > y_hi) {  // entering level l: compute its window
+                int yh = 0;
+                if (nx * ny > 1) {
+                    const float ry = g.rfac * (0.5f * fmaxf(hj, 0.0f) + cl) + 1.0f;
+                    y_lo = clampi((int)floorf((cy - ry) * inv), 0, ny - 1);
+                    yh = clampi((int)floorf((cy + ry) * inv), 0, ny - 1);
+                }
+                yy = y_lo; y_hi = yh;
+            }
+            if (nx * ny > 1) {
+                const float rx = g.rfac * (0.5f * fmaxf(wj, 0.0f) + cl) + 1.0f;
+                x_lo = clampi((int)floorf((cx - rx) * inv), 0, nx - 1);
+                x_hi = clampi((int)floorf((cx + rx) * inv), 0, nx - 1);
+            }
+            const uint32_t k0 = (uint32_t)seg * kCellStride + (uint32_t)(g.base[l] + yy * nx + x_lo);
+            q = ws.cell_begin[k0];
+            q_end = ws.cell_begin[k0 + (x_hi - x_lo) + 1];
+            row_ready = q < q_end;
+            if (++yy > y_hi) { ++l; yy = 0; y_hi = -1; }
         }
-        for (int yy = y_lo; yy <= y_hi; ++yy) {
-            for (int xx = x_lo; xx <= x_hi; ++xx) {
-                const uint32_t ck = (uint32_t)seg * kCellStride + (uint32_t)(g.base[l] + yy * nx + xx);
-                const int s0 = ws.cell_start[ck], e = ws.cell_end[ck];
-                for (int q0 = s0; q0 < e; q0 += 32) {
-                    const int q = q0 + lane;
-                    int m = 0x7FFFFFFF;
-                    bool hit = false;
-                    if (q < e) {
-                        m = ws.cval[q];
-                        if (m < i) {
-                            const float4 kb = ws.cbox[q];
-                            hit = iou_gt(kb, box_area(kb), b, area, iou_thr);
-                        }
-                    }
-                    const unsigned hm = __ballot_sync(0xffffffffu, hit);
-                    if (hit) {
-                        const int pos = cnt + __popc(hm & ((1u << lane) - 1u));
-                        if (pos < kMaxPreds) my[pos] = m;
-                    }
-                    cnt += __popc(hm);
-                    // members of a cell are in priority order: once one is not earlier than i, the rest are not either
-                    if (__any_sync(0xffffffffu, q < e && m >= i)) break;
+        const bool work = active && row_ready;
+        if (!__any_sync(0xffffffffu, work)) break;
+        int m = 0x7FFFFFFF;
+        bool hit = false;
+        if (work) {
+            const int qq = q + sub;
+            if (qq < q_end) {
+                m = ws.cval[qq];
+                if (m < i) {
+                    const float4 kb = ws.cbox[qq];
+                    hit = iou_gt(kb, box_area(kb), b, area, iou_thr);
                 }
             }
+            q += kBuildLanes;
+            if (q >= q_end) row_ready = false;
         }
+        const unsigned hm = __ballot_sync(0xffffffffu, hit) & grp_mask;
+        if (hit) {
+            const int pos = cnt + __popc(hm & ((1u << lane) - 1u));
+            if (pos < kMaxPreds) my[pos] = m;
+        }
+        cnt += __popc(hm);
     }
-    if (lane == 0) {
+    if (active && sub == 0) {
         ws.npred[i] = min(cnt, kMaxPreds);
         if (cnt > kMaxPreds) ws.overflow[n] = 1;
         ws.status[i] = cnt == 0 ? 1 : 0;
@@ -769,8 +795,8 @@ extern "C" int hn_det_decode_nms(const hn_det_desc* d, void* stream) {
     GridGeom geom = make_grid(d->img_h, d->img_w, d->iou_thres);
     const bool parallel = geom.prune && !g_det_force_sequential;
     if (parallel) {
-        HN_CHECK_CUDA(cudaMemsetAsync(ws.cell_start, 0, (size_t)d->N * kMaxCls * kCellStride * 4, s));
-        HN_CHECK_CUDA(cudaMemsetAsync(ws.cell_end, 0, (size_t)d->N * kMaxCls * kCellStride * 4, s));
+        const long long T = (long long)d->N * kMaxCls * kCellStride + 1;
+        HN_CHECK_CUDA(cudaMemsetAsync(ws.cell_cnt, 0, (size_t)T * 4, s));
         hn_nms2_prepare_kernel<<<hn_cdiv(NA, 256), 256, 0, s>>>(ws, NA, d->A, d->nms_mode, geom);
         HN_CHECK_CUDA(cudaGetLastError());
         cub::DoubleBuffer<uint32_t> dk(ws.ckey, ws.ckey_alt);
@@ -781,7 +807,9 @@ extern "C" int hn_det_decode_nms(const hn_det_desc* d, void* stream) {
         ws.cval = dv.Current(); ws.cval_alt = dv.Alternate();
         hn_nms2_cells_kernel<<<hn_cdiv(NA, 256), 256, 0, s>>>(ws, NA);
         HN_CHECK_CUDA(cudaGetLastError());
-        hn_nms2_build_kernel<<<hn_cdiv(NA * 32, 256), 256, 0, s>>>(ws, NA, d->nms_mode, d->iou_thres, geom);
+        tb = ws.cub2_bytes;
+        HN_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(ws.cub2_tmp, tb, ws.cell_cnt, ws.cell_begin, (int)T, s));
+        hn_nms2_build_kernel<<<hn_cdiv(NA * kBuildLanes, 256), 256, 0, s>>>(ws, NA, d->nms_mode, d->iou_thres, geom);
         HN_CHECK_CUDA(cudaGetLastError());
         {
             static int blocks_per_sm = 0;
