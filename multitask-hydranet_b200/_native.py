@@ -123,6 +123,7 @@ SYMBOLS = {
     "hn_plan_graph_capture": (C.c_int, [_P, _P]),
     "hn_plan_graph_launch": (C.c_int, [_P, _P]),
     "hn_conv_set_debug_buffer": (None, [_P]),
+    "hn_conv_set_cluster": (None, [C.c_int]),
     "hn_det_set_debug_buffer": (None, [_P]),
     "hn_det_force_sequential": (None, [C.c_int]),
     "hn_version": (C.c_int, []),

@@ -110,6 +110,24 @@ __device__ __forceinline__ void hn_tma_load_4d(void* dst, const void* tmap, uint
         : "memory");
 }
 
+// B-tile slice multicast to every CTA of the cluster in `mask` (same smem offset / same mbarrier offset in each)
+__device__ __forceinline__ void hn_tma_load_2d_mcast(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+        "[%2], %5;" ::"r"(hn_smem_u32(dst)),
+        "l"((uint64_t)tmap), "r"(hn_smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t hn_cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void hn_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void hn_tma_store_4d(const void* tmap, const void* src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"((uint64_t)tmap),
                  "r"(hn_smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -156,6 +174,13 @@ __device__ __forceinline__ void hn_umma_bf16(uint32_t tmem_d, uint64_t desc_a, u
 // mbarrier arrive once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void hn_umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(hn_smem_u32(bar))
+                 : "memory");
+}
+// same, arriving on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void hn_umma_commit_mcast(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     hn_smem_u32(bar)),
+                 "h"(mask)
                  : "memory");
 }
 __device__ __forceinline__ void hn_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {

@@ -46,9 +46,11 @@ __device__ __forceinline__ void hn_tmem_ldN(uint32_t taddr, uint32_t (&v)[NC]) {
 struct TileOrigin {
     int n0, img, y0, x0;
 };
-__device__ __forceinline__ TileOrigin tile_origin(const ConvParams& p, int t) {
+// work item t = (n tile, group of `cluster` consecutive m tiles); CTA `rank` of the cluster takes m tile group*cluster+rank
+// (an m tile index past the end yields out-of-bounds coordinates: zero-filled loads, clipped / masked stores)
+__device__ __forceinline__ TileOrigin tile_origin(const ConvParams& p, int t, int rank) {
     TileOrigin o;
-    int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
+    int nt = t / p.m_groups, mt = (t - nt * p.m_groups) * p.cluster + rank;
     o.n0 = nt * p.bn;
     if (p.flat) {
         o.img = 0; o.y0 = 0; o.x0 = mt * 128;
@@ -211,7 +213,12 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int total_tiles = p.m_tiles * p.n_tiles;
+    // persistent loop over work items, one item per cluster per iteration
+    const int CS = p.cluster;
+    const int rank = CS > 1 ? (int)hn_cluster_ctarank() : 0;
+    const int total_tiles = p.m_groups * p.n_tiles;
+    const int t_first = blockIdx.x / CS, t_step = gridDim.x / CS;
+    const uint16_t cmask = (uint16_t)((1u << CS) - 1u);
     long long* dbg = p.dbg ? p.dbg + (long long)blockIdx.x * 16 : nullptr;
     if (dbg && threadIdx.x == 0) dbg[0] = hn_globaltimer();
 
@@ -221,7 +228,7 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
         if (p.n_staging) hn_tma_prefetch_desc(&p.tmO);
         for (int s = 0; s < stages; ++s) {
             hn_mbar_init(&bar_full[s], 1);
-            hn_mbar_init(&bar_empty[s], 1);
+            hn_mbar_init(&bar_empty[s], CS);  // every CTA of the cluster must have consumed the slot (B is multicast into it)
         }
         for (int a = 0; a < 2; ++a) {
             hn_mbar_init(&bar_acc_full[a], 1);
@@ -235,6 +242,7 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
     }
     hn_tc_fence_before();
     __syncthreads();
+    if (CS > 1) hn_cluster_sync();  // peers' barriers are initialised before anything remote touches them
     hn_tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (dbg && threadIdx.x == 0) dbg[1] = hn_globaltimer();
@@ -245,8 +253,9 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
             const uint32_t stage_bytes = (uint32_t)(kATileBytes + b_tile_bytes);
             int s = 0;
             uint32_t ph = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const TileOrigin o = tile_origin(p, t);
+            const int b_rows = BN / CS;  // this CTA's slice of the weight tile
+            for (int t = t_first; t < total_tiles; t += t_step) {
+                const TileOrigin o = tile_origin(p, t, rank);
                 const int c_shift = p.grouped ? o.n0 : 0;
                 for (int k = 0; k < p.num_taps; ++k) {
                     hn_mbar_wait(&bar_empty[s], ph ^ 1);
@@ -254,10 +263,14 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
                     const hn_tap tp = p.taps[k];
                     hn_tma_load_4d(sA + s * kATileBytes, &p.tmA[tp.src], &bar_full[s], (int)tp.c0 + c_shift, o.x0 + (int)tp.dx,
                                    o.y0 + (int)tp.dy, o.img);
-                    hn_tma_load_2d(sB + s * b_tile_bytes, &p.tmB, &bar_full[s], k * 64, o.n0);
+                    if (CS == 1)
+                        hn_tma_load_2d(sB + s * b_tile_bytes, &p.tmB, &bar_full[s], k * 64, o.n0);
+                    else
+                        hn_tma_load_2d_mcast(sB + s * b_tile_bytes + rank * b_rows * 128, &p.tmBpart, &bar_full[s], k * 64,
+                                             o.n0 + rank * b_rows, cmask);
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
-                if (dbg && t == (int)blockIdx.x) dbg[2] = hn_globaltimer();
+                if (dbg && t == t_first) dbg[2] = hn_globaltimer();
             }
         }
     } else if (warp == 1) {
@@ -266,14 +279,14 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
             const uint32_t idesc = hn_umma_idesc_bf16(128, BN);
             int s = 0, a = 0;
             uint32_t ph = 0, aph = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int t = t_first; t < total_tiles; t += t_step) {
                 hn_mbar_wait(&bar_acc_empty[a], aph ^ 1);  // epilogue has drained this accumulator
                 hn_tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.acc_stride);
                 for (int k = 0; k < p.num_taps; ++k) {
                     hn_mbar_wait(&bar_full[s], ph);
                     hn_tc_fence_after();
-                    if (dbg && t == (int)blockIdx.x && k == 0) dbg[3] = hn_globaltimer();
+                    if (dbg && t == t_first && k == 0) dbg[3] = hn_globaltimer();
                     const uint32_t a_addr = hn_smem_u32(sA + s * kATileBytes);
                     const uint32_t b_addr = hn_smem_u32(sB + s * b_tile_bytes);
 #pragma unroll
@@ -282,11 +295,12 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
                         uint64_t db = hn_umma_desc_sw128(b_addr + kk * 32);
                         hn_umma_bf16(d_tmem, da, db, idesc, (uint32_t)((k | kk) != 0));
                     }
-                    hn_umma_commit(&bar_empty[s]);  // frees the smem slot once these MMAs retire
+                    // frees the smem slot once these MMAs retire -- in every CTA of the cluster, whose producers multicast into it
+                    if (CS == 1) hn_umma_commit(&bar_empty[s]); else hn_umma_commit_mcast(&bar_empty[s], cmask);
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
                 hn_umma_commit(&bar_acc_full[a]);  // accumulator complete
-                if (dbg && t == (int)blockIdx.x) dbg[4] = hn_globaltimer();
+                if (dbg && t == t_first) dbg[4] = hn_globaltimer();
                 if (++a == 2) { a = 0; aph ^= 1; }
             }
         }
@@ -298,8 +312,8 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
         int a = 0;
         uint32_t aph = 0;
         int ntile = 0, st_count = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ntile) {
-            const TileOrigin o = tile_origin(p, t);
+        for (int t = t_first; t < total_tiles; t += t_step, ++ntile) {
+            const TileOrigin o = tile_origin(p, t, rank);
             float* bias_s = s_bias + a * BN;
             for (int i = et; i < BN; i += kEpiThreads) bias_s[i] = p.bias ? p.bias[o.n0 + i] : 0.0f;
             EpiRow e;
@@ -315,7 +329,7 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
             } else {
                 int ty = row / p.TW, tx = row - ty * p.TW;
                 int y = o.y0 + ty, x = o.x0 + tx;
-                e.valid = (y < p.H) && (x < p.W);
+                e.valid = (y < p.H) && (x < p.W) && (o.img < p.n_img);
                 e.n_i = o.img;
                 e.Y = y * p.oscale + p.ooy;
                 e.X = x * p.oscale + p.oox;
@@ -406,6 +420,7 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
 
     hn_tc_fence_before();
     __syncthreads();
+    if (CS > 1) hn_cluster_sync();  // no CTA leaves while a peer may still multicast into it / arrive on its barriers
     if (warp == 1) {
         hn_tc_fence_after();
         hn_tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -472,6 +487,8 @@ static int encode_weight_map(CUtensorMap* tm, const void* w, int rows, int kcols
 
 static void* g_conv_dbg = nullptr;
 extern "C" void hn_conv_set_debug_buffer(void* p) { g_conv_dbg = p; }
+static int g_conv_cluster = 0;  // 0 = default policy
+extern "C" void hn_conv_set_cluster(int cs) { g_conv_cluster = cs; }
 
 static int round_pow2_cols(int bn) {
     int c = 32;
@@ -557,6 +574,15 @@ int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L) {
     if (d->epi == HN_EPI_SEGOUT) n_tiles = 1;
     p.m_tiles = m_tiles;
     p.n_tiles = n_tiles;
+    // clusters of 2 along M share the weight tile through TMA multicast (halves its L2 traffic) for wide N tiles
+    int cs = (g_conv_cluster > 0) ? g_conv_cluster : 2;
+    if (d->bn < 128 || m_tiles < 2 || d->epi != HN_EPI_STD || (d->bn / cs) % 8 != 0) cs = 1;
+    p.cluster = cs;
+    p.m_groups = hn_cdiv(m_tiles, cs);
+    if (cs > 1) {
+        int rc3 = encode_weight_map(&p.tmBpart, d->weight, d->w_rows, d->num_taps * 64, d->bn / cs);
+        if (rc3) return rc3;
+    }
     const size_t base_smem = 1024 + (size_t)d->stages * (kATileBytes + d->bn * 128) + (2 * d->stages + 4) * 8 + 16 + 2 * d->bn * 4 + 64;
     // bf16 outputs leave through shared memory + TMA store (coalesced, clipped by the tensor map) when the
     // 64-channel slabs of an N tile never spill into the next tile's channels
@@ -583,9 +609,10 @@ int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L) {
     int sms = hn_device_sm_count();
     if (sms <= 0) sms = 148;
     int per_sm = (2 * (L->smem + 1024) <= 227 * 1024 && 2 * p.tmem_cols <= 512) ? 2 : 1;
-    long long total = (long long)m_tiles * n_tiles;
-    long long g = (long long)sms * per_sm;
-    L->grid = dim3((unsigned)(total < g ? total : g), 1, 1);
+    long long total = (long long)p.m_groups * n_tiles;      // work items (one per cluster per iteration)
+    long long g = (long long)sms * per_sm / cs;               // resident clusters
+    L->grid = dim3((unsigned)((total < g ? total : g) * cs), 1, 1);
+    L->cluster = cs;
     return HN_OK;
 }
 
@@ -596,8 +623,25 @@ int hn_conv_launch(const ConvLaunch* L, cudaStream_t stream) {
         attr_err = cudaFuncSetAttribute(hn_conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     HN_CHECK_CUDA(attr_err);
-    hn_conv_gemm_kernel<<<L->grid, 192, L->smem, stream>>>(L->prm);
-    HN_CHECK_CUDA(cudaGetLastError());
+    if (L->cluster <= 1) {
+        hn_conv_gemm_kernel<<<L->grid, 192, L->smem, stream>>>(L->prm);
+        HN_CHECK_CUDA(cudaGetLastError());
+        return HN_OK;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = L->grid;
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = L->smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)L->cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, hn_conv_gemm_kernel, L->prm));
     return HN_OK;
 }
 

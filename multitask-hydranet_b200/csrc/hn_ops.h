@@ -5,6 +5,9 @@
 struct alignas(64) ConvParams {
     CUtensorMap tmA[HN_MAX_SRC];
     CUtensorMap tmB;
+    CUtensorMap tmBpart;  // B tile slice of bn/cluster rows (cluster multicast)
+    int cluster;          // CTAs per cluster sharing the weight tile (1, 2 or 4)
+    int m_groups;         // ceil(m_tiles / cluster)
     CUtensorMap tmO;  // bf16 output view (TMA store path)
     int n_staging;    // 0: direct stores; 1/2: shared-memory staging buffers of 128 rows x 64 channels
     int flat, TH, TW, n_img, H, W, tiles_x, tiles_y, flat_hw, flat_m;
@@ -30,6 +33,7 @@ struct ConvLaunch {
     ConvParams prm;
     dim3 grid;
     size_t smem;
+    int cluster;
 };
 
 int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L);

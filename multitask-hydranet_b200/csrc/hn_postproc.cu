@@ -565,11 +565,16 @@ __global__ void hn_nms2_cells_kernel(DetWs ws, long long NA) {
 // index / box loads; conflicts with earlier boxes are appended through a ballot.
 static constexpr int kBuildLanes = 8;
 __global__ void __launch_bounds__(256) hn_nms2_build_kernel(DetWs ws, long long NA, int nms_mode, float iou_thr, GridGeom g) {
-    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kBuildLanes;
+    // candidates are taken in CELL order: neighbouring groups scan overlapping index ranges (L1 / L2 locality)
+    const long long slot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kBuildLanes;
     const int lane = threadIdx.x & 31, sub = lane & (kBuildLanes - 1), grp_shift = lane & ~(kBuildLanes - 1);
     const unsigned grp_mask = ((1u << kBuildLanes) - 1u) << grp_shift;
     uint64_t key = ~0ull;
-    if (i < NA) key = ws.keys[i];
+    long long i = 0;
+    if (slot < NA && ws.ckey[slot] != 0xFFFFFFFFu) {
+        i = ws.cval[slot];
+        key = ws.keys[i];
+    }
     const bool active = key != ~0ull;  // inactive groups still take part in the warp-wide ballots
     int seg = 0, n = 0;
     float offset = 0.0f, area = 0.0f, wj = 0.0f, hj = 0.0f, cx = 0.0f, cy = 0.0f;
@@ -680,6 +685,7 @@ __global__ void __launch_bounds__(256) hn_nms2_rounds_kernel(DetWs ws, long long
         ++round;
         grid.sync();
     }
+    if (tid0 == 0) ws.changed[2] = round + 1;  // diagnostics: number of rounds
     for (long long i = tid0; i < NA; i += stride) ws.kflag[i] = __ldcg(ws.status + i) == 1 ? 1 : 0;
 }
 

@@ -155,3 +155,24 @@ def test_cuda_graph_replay():
             g2 = m_gpu(x)["lane"]["predict_loc"].clone()
         s.synchronize()
     assert torch.equal(eager["predict_loc"], g1) and torch.equal(g1, g2)
+
+
+def test_cluster_multicast_equals_single_cta():
+    """Weight tiles multicast across a 2-CTA cluster must give bit-identical results to private loads."""
+    from hydranet_b200 import _native as nv
+    cfg = big_cfg(256, 256)
+    _, m_gpu, sd = _models(cfg)
+    x = synth.synth_input(3, 256, 256, seed=13).cuda()
+    outs = []
+    for cs in (1, 2):
+        nv.lib.hn_conv_set_cluster(cs)
+        try:
+            m_gpu._plans = {}
+            with torch.no_grad():
+                o = m_gpu(x)
+            outs.append({"seg": o["seg"].clone(), "reg": o["detection"]["regression"].clone(), "loc": o["lane"]["predict_loc"].clone()})
+        finally:
+            nv.lib.hn_conv_set_cluster(0)
+    m_gpu._plans = {}
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
