@@ -109,6 +109,7 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     hb, m, cfg = build_model(dev)
+    m.use_graph = not args.no_graph
     from hydranet_b200 import _native as nv
     B, H, W = args.batch, 640, 640
     codec = hb.LaneCodec(W, H, cfg["lane"]["anchor_stride"], int(H / cfg["lane"]["interval"]), True, 1, True)
@@ -116,6 +117,8 @@ def run_native(args):
     host = [torch.randn(B, 3, H, W, generator=g).pin_memory() for _ in range(2)]  # 157 MB each: larger than the 126 MB L2
     resident = [h.to(dev) for h in host]
     ws = torch.empty(nv.lib.hn_det_workspace_bytes(B, 76725), dtype=torch.uint8, device=dev)
+    # a non-default stream: the forward is replayed as a CUDA graph (capture is illegal on the legacy stream)
+    torch.cuda.set_stream(torch.cuda.Stream(dev))
     stream = torch.cuda.current_stream(dev)
 
     def step(x):
@@ -262,8 +265,33 @@ def run_native(args):
         # ---------------- CPU baseline: the oracle port of the reference path on the host cores ----------------
         cpu = cpu_baseline(m, cfg, seconds=args.cpu_seconds)
 
+    lat = None
+    if rank == 0 and not args.no_latency:
+        # p50 batch-1 latency (BASELINE.json metric): forward (CUDA graph) + all three decoders, device time
+        x1 = torch.randn(1, 3, H, W, device=dev)
+        ws1 = torch.empty(nv.lib.hn_det_workspace_bytes(1, 76725), dtype=torch.uint8, device=dev)
+
+        def step1():
+            with torch.no_grad():
+                out = m(x1)
+                return postproc(hb, m, out, codec, ws1)
+        for _ in range(5):
+            step1()
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(50):
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            step1()
+            b_.record(stream)
+            torch.cuda.synchronize(dev)
+            ts.append(a.elapsed_time(b_))
+        ts.sort()
+        lat = {"p50": round(ts[len(ts) // 2], 3), "p90": round(ts[int(len(ts) * 0.9)], 3), "unit": "ms", "batch": 1,
+               "what": "forward (CUDA graph replay) + det/lane/seg post-processing, device time"}
+
     if rank == 0:
-        n_launch = m.plan(B, H, W, dev).n_launches + 15 + 1 + 1  # forward + det (5 own + radix sort passes) + lane + u8->i64
+        n_launch = m.plan(B, H, W, dev).n_launches + 27 + 1 + 1  # forward + det (5 own + radix sort passes) + lane + u8->i64
         line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
@@ -273,7 +301,7 @@ def run_native(args):
                            "l2_policy": "2 alternating input batches of 157 MB each (> 126 MB L2)"},
                 "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": round(e2e_ms / args.steps, 3)},
-                "gpu_launches": n_launch * args.steps, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": n_launch * args.steps, "clocks": clocks, "latency_b1_ms": lat, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -344,6 +372,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--dump-ops", action="store_true", help="write per-op device times to gpurun_out/op_times.txt")
+    ap.add_argument("--no-latency", action="store_true", help="skip the batch-1 latency measurement")
+    ap.add_argument("--no-graph", action="store_true", help="launch the forward kernel by kernel instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

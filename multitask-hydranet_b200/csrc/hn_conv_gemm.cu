@@ -575,7 +575,8 @@ int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L) {
     p.m_tiles = m_tiles;
     p.n_tiles = n_tiles;
     // clusters of 2 along M share the weight tile through TMA multicast (halves its L2 traffic) for wide N tiles
-    int cs = (g_conv_cluster > 0) ? g_conv_cluster : 2;
+    // (measured on B200: no gain -- the main loop is bound by shared-memory bandwidth, not L2 -- so off by default)
+    int cs = (g_conv_cluster > 0) ? g_conv_cluster : 1;
     if (d->bn < 128 || m_tiles < 2 || d->epi != HN_EPI_STD || (d->bn / cs) % 8 != 0) cs = 1;
     p.cluster = cs;
     p.m_groups = hn_cdiv(m_tiles, cs);

@@ -149,7 +149,7 @@ __device__ __forceinline__ void node_fetch(const View& v, int mode, int n, int y
 
 static constexpr int kNodeTH = 8, kNodeTW = 16;         // output tile
 static constexpr int kNodeHH = kNodeTH + 2, kNodeHW = kNodeTW + 2;  // halo tile
-static constexpr int kNodeRows = 16;                      // threadIdx.y extent
+static constexpr int kNodeRows = 32;                      // threadIdx.y extent
 
 // fused value (weighted sum -> swish) of one 8-channel vector at (y, x); zero outside the image (the depthwise
 // conv's zero padding)
@@ -176,13 +176,15 @@ __device__ __forceinline__ void node_value(const NodeParams& p, int n, int y, in
     }
 }
 
-// CTA = (C/8) x 16 threads; threadIdx.x is the 8-channel vector (a pixel's channels are contiguous: coalesced),
+// CTA = (C/8) x 32 threads; threadIdx.x is the 8-channel vector (a pixel's channels are contiguous: coalesced),
 // threadIdx.y strides over pixels.  Phase 1 computes the fused value of the (8+2)x(16+2) halo tile once into
-// shared memory (fp32); phase 2 runs the depthwise taps from there with the 9x8 weights of the thread's
-// channel vector held in registers.
-__global__ void __launch_bounds__(256) hn_node_kernel(const __grid_constant__ NodeParams p) {
-    extern __shared__ float s_tile[];  // [kNodeHH * kNodeHW][C]
+// shared memory (fp32); phase 2 runs the depthwise taps from there, weights also in shared memory (keeps the
+// register count low enough for two 448-thread CTAs per SM: the kernel is latency-bound, occupancy matters).
+__global__ void __launch_bounds__(512, 2) hn_node_kernel(const __grid_constant__ NodeParams p) {
+    extern __shared__ float s_tile[];  // [kNodeHH * kNodeHW][C] fused values, then [9][C] depthwise weights
     const int C = p.out.C;
+    float* s_w = s_tile + kNodeHH * kNodeHW * C;
+    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 9 * C; i += blockDim.x * blockDim.y) s_w[i] = __ldg(p.dw + i);
     const int cv = threadIdx.x, c = cv * 8;
     const int tiles_x = (p.out.W + kNodeTW - 1) / kNodeTW, tiles_y = (p.out.H + kNodeTH - 1) / kNodeTH;
     const int per_img = tiles_x * tiles_y;
@@ -196,14 +198,6 @@ __global__ void __launch_bounds__(256) hn_node_kernel(const __grid_constant__ No
         float4* dst = reinterpret_cast<float4*>(s_tile + hp * C + c);
         dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
         dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    }
-    float wgt[9][8];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        const float4* wv = reinterpret_cast<const float4*>(p.dw + k * C + c);
-        const float4 w0 = __ldg(wv), w1 = __ldg(wv + 1);
-        wgt[k][0] = w0.x; wgt[k][1] = w0.y; wgt[k][2] = w0.z; wgt[k][3] = w0.w;
-        wgt[k][4] = w1.x; wgt[k][5] = w1.y; wgt[k][6] = w1.z; wgt[k][7] = w1.w;
     }
     __syncthreads();
     for (int op = threadIdx.y; op < kNodeTH * kNodeTW; op += kNodeRows) {
@@ -219,11 +213,12 @@ __global__ void __launch_bounds__(256) hn_node_kernel(const __grid_constant__ No
             for (int kx = 0; kx < 3; ++kx) {
                 const float4* sv = reinterpret_cast<const float4*>(s_tile + ((ty + ky) * kNodeHW + tx + kx) * C + c);
                 const float4 a0 = sv[0], a1 = sv[1];
-                const float (&w)[8] = wgt[ky * 3 + kx];
-                acc[0] = fmaf(a0.x, w[0], acc[0]); acc[1] = fmaf(a0.y, w[1], acc[1]);
-                acc[2] = fmaf(a0.z, w[2], acc[2]); acc[3] = fmaf(a0.w, w[3], acc[3]);
-                acc[4] = fmaf(a1.x, w[4], acc[4]); acc[5] = fmaf(a1.y, w[5], acc[5]);
-                acc[6] = fmaf(a1.z, w[6], acc[6]); acc[7] = fmaf(a1.w, w[7], acc[7]);
+                const float4* wv = reinterpret_cast<const float4*>(s_w + (ky * 3 + kx) * C + c);
+                const float4 w0 = wv[0], w1 = wv[1];
+                acc[0] = fmaf(a0.x, w0.x, acc[0]); acc[1] = fmaf(a0.y, w0.y, acc[1]);
+                acc[2] = fmaf(a0.z, w0.z, acc[2]); acc[3] = fmaf(a0.w, w0.w, acc[3]);
+                acc[4] = fmaf(a1.x, w1.x, acc[4]); acc[5] = fmaf(a1.y, w1.y, acc[5]);
+                acc[6] = fmaf(a1.z, w1.z, acc[6]); acc[7] = fmaf(a1.w, w1.w, acc[7]);
             }
         }
         store8(const_cast<bf16*>(vptr(p.out, n, y, x, c)), acc);
@@ -256,9 +251,9 @@ extern "C" int hn_node_fwd(const hn_node_desc* d, void* stream) {
     p.dw = d->dw;
     p.out = to_view(d->out);
     const int CV = d->out.C / 8;
-    HN_REQUIRE(CV >= 1 && CV * kNodeRows <= 256, "node: C=%d not supported (at most 128 channels)", d->out.C);
+    HN_REQUIRE(CV >= 1 && CV * kNodeRows <= 512, "node: C=%d not supported (at most 128 channels)", d->out.C);
     const int tiles = hn_cdiv(d->out.W, kNodeTW) * hn_cdiv(d->out.H, kNodeTH);
-    size_t smem = (size_t)kNodeHH * kNodeHW * d->out.C * sizeof(float);
+    size_t smem = (size_t)(kNodeHH * kNodeHW + 9) * d->out.C * sizeof(float);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         HN_CHECK_CUDA(cudaFuncSetAttribute(hn_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -631,10 +631,10 @@ __global__ void __launch_bounds__(256) hn_nms2_build_kernel(DetWs ws, long long 
         if (work) {
             const int qq = q + sub;
             if (qq < q_end) {
-                m = ws.cval[qq];
-                if (m < i) {
-                    const float4 kb = ws.cbox[qq];
-                    hit = iou_gt(kb, box_area(kb), b, area, iou_thr);
+                const float4 kb = ws.cbox[qq];
+                if (iou_gt(kb, box_area(kb), b, area, iou_thr)) {  // rare: only then look up the priority
+                    m = ws.cval[qq];
+                    hit = m < i;
                 }
             }
             q += kBuildLanes;
