@@ -149,7 +149,7 @@ __device__ __forceinline__ void node_fetch(const View& v, int mode, int n, int y
 
 static constexpr int kNodeTH = 8, kNodeTW = 16;         // output tile
 static constexpr int kNodeHH = kNodeTH + 2, kNodeHW = kNodeTW + 2;  // halo tile
-static constexpr int kNodeRows = 32;                      // threadIdx.y extent
+static constexpr int kNodeRows = 16;                      // threadIdx.y extent
 
 // fused value (weighted sum -> swish) of one 8-channel vector at (y, x); zero outside the image (the depthwise
 // conv's zero padding)
@@ -176,15 +176,13 @@ __device__ __forceinline__ void node_value(const NodeParams& p, int n, int y, in
     }
 }
 
-// CTA = (C/8) x 32 threads; threadIdx.x is the 8-channel vector (a pixel's channels are contiguous: coalesced),
-// threadIdx.y strides over pixels.  Phase 1 computes the fused value of the (8+2)x(16+2) halo tile once into
-// shared memory (fp32); phase 2 runs the depthwise taps from there, weights also in shared memory (keeps the
-// register count low enough for two 448-thread CTAs per SM: the kernel is latency-bound, occupancy matters).
-__global__ void __launch_bounds__(512, 2) hn_node_kernel(const __grid_constant__ NodeParams p) {
-    extern __shared__ float s_tile[];  // [kNodeHH * kNodeHW][C] fused values, then [9][C] depthwise weights
+// CTA = (C/8) x 16 threads; threadIdx.x is the 8-channel vector (a pixel's channels are contiguous: coalesced),
+// threadIdx.y strides over pixels.  Phase 1 computes the fused value (weighted sum, swish) of the (8+2)x(16+2)
+// halo tile once into shared memory (fp32); phase 2 runs the depthwise taps from there with the 9x8 weights of
+// the thread's channel vector held in registers.
+__global__ void __launch_bounds__(256) hn_node_kernel(const __grid_constant__ NodeParams p) {
+    extern __shared__ float s_tile[];  // [kNodeHH * kNodeHW][C] fused values
     const int C = p.out.C;
-    float* s_w = s_tile + kNodeHH * kNodeHW * C;
-    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 9 * C; i += blockDim.x * blockDim.y) s_w[i] = __ldg(p.dw + i);
     const int cv = threadIdx.x, c = cv * 8;
     const int tiles_x = (p.out.W + kNodeTW - 1) / kNodeTW, tiles_y = (p.out.H + kNodeTH - 1) / kNodeTH;
     const int per_img = tiles_x * tiles_y;
@@ -198,6 +196,14 @@ __global__ void __launch_bounds__(512, 2) hn_node_kernel(const __grid_constant__
         float4* dst = reinterpret_cast<float4*>(s_tile + hp * C + c);
         dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
         dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    float wgt[9][8];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const float4* wv = reinterpret_cast<const float4*>(p.dw + k * C + c);
+        const float4 w0 = __ldg(wv), w1 = __ldg(wv + 1);
+        wgt[k][0] = w0.x; wgt[k][1] = w0.y; wgt[k][2] = w0.z; wgt[k][3] = w0.w;
+        wgt[k][4] = w1.x; wgt[k][5] = w1.y; wgt[k][6] = w1.z; wgt[k][7] = w1.w;
     }
     __syncthreads();
     for (int op = threadIdx.y; op < kNodeTH * kNodeTW; op += kNodeRows) {
@@ -213,16 +219,58 @@ __global__ void __launch_bounds__(512, 2) hn_node_kernel(const __grid_constant__
             for (int kx = 0; kx < 3; ++kx) {
                 const float4* sv = reinterpret_cast<const float4*>(s_tile + ((ty + ky) * kNodeHW + tx + kx) * C + c);
                 const float4 a0 = sv[0], a1 = sv[1];
-                const float4* wv = reinterpret_cast<const float4*>(s_w + (ky * 3 + kx) * C + c);
-                const float4 w0 = wv[0], w1 = wv[1];
-                acc[0] = fmaf(a0.x, w0.x, acc[0]); acc[1] = fmaf(a0.y, w0.y, acc[1]);
-                acc[2] = fmaf(a0.z, w0.z, acc[2]); acc[3] = fmaf(a0.w, w0.w, acc[3]);
-                acc[4] = fmaf(a1.x, w1.x, acc[4]); acc[5] = fmaf(a1.y, w1.y, acc[5]);
-                acc[6] = fmaf(a1.z, w1.z, acc[6]); acc[7] = fmaf(a1.w, w1.w, acc[7]);
+                const float (&w)[8] = wgt[ky * 3 + kx];
+                acc[0] = fmaf(a0.x, w[0], acc[0]); acc[1] = fmaf(a0.y, w[1], acc[1]);
+                acc[2] = fmaf(a0.z, w[2], acc[2]); acc[3] = fmaf(a0.w, w[3], acc[3]);
+                acc[4] = fmaf(a1.x, w[4], acc[4]); acc[5] = fmaf(a1.y, w[5], acc[5]);
+                acc[6] = fmaf(a1.z, w[6], acc[6]); acc[7] = fmaf(a1.w, w[7], acc[7]);
             }
         }
         store8(const_cast<bf16*>(vptr(p.out, n, y, x, c)), acc);
     }
+}
+
+// Plain depthwise 3x3 (one input at the output resolution, no fusion): one thread per output 8-channel vector,
+// all nine 16-byte loads issued up front (neighbouring threads share them through L1), no shared memory, no
+// barrier: the op is latency-bound, so what matters is loads in flight per SM.
+__global__ void __launch_bounds__(256) hn_dw_kernel(View in, View out, const float* __restrict__ dw) {
+    const int C = out.C, CV = C >> 3;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)out.N * out.H * out.W * CV;
+    if (idx >= total) return;
+    const int cv = (int)(idx % CV);
+    long long t = idx / CV;
+    const int x = (int)(t % out.W);
+    t /= out.W;
+    const int y = (int)(t % out.H);
+    const int n = (int)(t / out.H);
+    const int c = cv * 8;
+    uint4 raw[9];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int iy = y + ky - 1, ix = x + kx - 1;
+            raw[ky * 3 + kx] = (iy >= 0 && iy < out.H && ix >= 0 && ix < out.W)
+                                   ? *reinterpret_cast<const uint4*>(vptr(in, n, iy, ix, c))
+                                   : make_uint4(0, 0, 0, 0);
+        }
+    }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const float4* wv = reinterpret_cast<const float4*>(dw + k * C + c);
+        const float4 w0 = __ldg(wv), w1 = __ldg(wv + 1);
+        const float2 a = hn_unpack_bf16x2(raw[k].x), b = hn_unpack_bf16x2(raw[k].y), cc = hn_unpack_bf16x2(raw[k].z),
+                     d = hn_unpack_bf16x2(raw[k].w);
+        acc[0] = fmaf(a.x, w0.x, acc[0]); acc[1] = fmaf(a.y, w0.y, acc[1]);
+        acc[2] = fmaf(b.x, w0.z, acc[2]); acc[3] = fmaf(b.y, w0.w, acc[3]);
+        acc[4] = fmaf(cc.x, w1.x, acc[4]); acc[5] = fmaf(cc.y, w1.y, acc[5]);
+        acc[6] = fmaf(d.x, w1.z, acc[6]); acc[7] = fmaf(d.y, w1.w, acc[7]);
+    }
+    store8(const_cast<bf16*>(vptr(out, n, y, x, c)), acc);
 }
 
 extern "C" int hn_node_fwd(const hn_node_desc* d, void* stream) {
@@ -250,10 +298,16 @@ extern "C" int hn_node_fwd(const hn_node_desc* d, void* stream) {
     p.swish = d->swish;
     p.dw = d->dw;
     p.out = to_view(d->out);
+    if (d->n_in == 1 && d->mode[0] == HN_IN_SAME && !d->swish && d->w[0] == 1.0f) {
+        long long total = (long long)d->out.N * d->out.H * d->out.W * (d->out.C / 8);
+        hn_dw_kernel<<<hn_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p.in[0], p.out, d->dw);
+        HN_CHECK_CUDA(cudaGetLastError());
+        return HN_OK;
+    }
     const int CV = d->out.C / 8;
-    HN_REQUIRE(CV >= 1 && CV * kNodeRows <= 512, "node: C=%d not supported (at most 128 channels)", d->out.C);
+    HN_REQUIRE(CV >= 1 && CV * kNodeRows <= 256, "node: C=%d not supported (at most 128 channels)", d->out.C);
     const int tiles = hn_cdiv(d->out.W, kNodeTW) * hn_cdiv(d->out.H, kNodeTH);
-    size_t smem = (size_t)(kNodeHH * kNodeHW + 9) * d->out.C * sizeof(float);
+    size_t smem = (size_t)kNodeHH * kNodeHW * d->out.C * sizeof(float);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         HN_CHECK_CUDA(cudaFuncSetAttribute(hn_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

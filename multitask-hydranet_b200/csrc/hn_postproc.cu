@@ -538,6 +538,7 @@ __global__ void hn_nms2_prepare_kernel(DetWs ws, long long NA, int A, int nms_mo
     ws.cval[i] = (int)i;
     ws.kflag[i] = 0;
     ws.status[i] = 2;
+    ws.npred[i] = 0;
     if (key == ~0ull) { ws.ckey[i] = 0xFFFFFFFFu; return; }
     const int seg = (int)(key >> kClsShift), n = seg / kMaxCls, cls = seg % kMaxCls;
     const int a = (int)(key & ((1u << kAnchorBits) - 1));
@@ -560,98 +561,66 @@ __global__ void hn_nms2_cells_kernel(DetWs ws, long long NA) {
     ws.cbox[q] = ws.sbox[ws.cval[q]];
 }
 
-// Eight lanes per candidate.  Cells of one grid row are consecutive in cell order, so the members of the
-// cells x_lo..x_hi of a window row form ONE contiguous index range: the group strides over it with coalesced
-// index / box loads; conflicts with earlier boxes are appended through a ballot.
+// Conflict-graph construction, eight lanes per candidate.  Cells of one grid row are consecutive in cell
+// order, so the members of the cells x_lo..x_hi of a window row form ONE contiguous index range that the
+// group strides over with coalesced box loads.  Every conflicting pair is discovered ONCE, from its smaller
+// box: a candidate scans only its own size level and the coarser ones (few, large cells) and records the edge
+// at the later box of the pair, i.e. in its own predecessor list or -- atomically -- in the other box's.
 static constexpr int kBuildLanes = 8;
+__device__ __forceinline__ void nms2_add_pred(DetWs& ws, long long later, int earlier, int n) {
+    const int pos = atomicAdd(ws.npred + later, 1);
+    if (pos < kMaxPreds) ws.preds[later * kMaxPreds + pos] = earlier;
+    else ws.overflow[n] = 1;
+}
 __global__ void __launch_bounds__(256) hn_nms2_build_kernel(DetWs ws, long long NA, int nms_mode, float iou_thr, GridGeom g) {
     // candidates are taken in CELL order: neighbouring groups scan overlapping index ranges (L1 / L2 locality)
     const long long slot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kBuildLanes;
-    const int lane = threadIdx.x & 31, sub = lane & (kBuildLanes - 1), grp_shift = lane & ~(kBuildLanes - 1);
-    const unsigned grp_mask = ((1u << kBuildLanes) - 1u) << grp_shift;
-    uint64_t key = ~0ull;
-    long long i = 0;
-    if (slot < NA && ws.ckey[slot] != 0xFFFFFFFFu) {
-        i = ws.cval[slot];
-        key = ws.keys[i];
-    }
-    const bool active = key != ~0ull;  // inactive groups still take part in the warp-wide ballots
-    int seg = 0, n = 0;
-    float offset = 0.0f, area = 0.0f, wj = 0.0f, hj = 0.0f, cx = 0.0f, cy = 0.0f;
-    float4 b = make_float4(0, 0, 0, 0);
-    int l_lo = 0, l_hi = -1;
-    if (active) {
-        seg = (int)(key >> kClsShift);
-        n = seg / kMaxCls;
-        offset = seg_offset(ws, n, seg % kMaxCls, nms_mode);
-        b = ws.sbox[i];
-        area = box_area(b);
-        wj = b.z - b.x; hj = b.w - b.y;
-        cx = 0.5f * (b.x + b.z) - offset; cy = 0.5f * (b.y + b.w) - offset;
-        const int t = grid_level(fmaxf(wj, hj), g);
-        l_lo = max(0, t - g.delta); l_hi = min(g.nlev - 1, t + g.delta);
-    }
-    int* my = ws.preds + (active ? i : 0) * kMaxPreds;
-    int cnt = 0;  // group-uniform
-    // the loops are warp-uniform in structure: every group walks its own (level, row, range) sequence, and the
-    // warp iterates until all four groups are done
-    int l = l_lo, yy = 0, y_hi = -1, q = 0, q_end = 0;
-    bool row_ready = false;
-    while (true) {
-        // advance to the next non-empty range of this group
-        while (active && !row_ready && l <= l_hi) {
-            const float cl = g.c0 * (float)(1 << l);
-            const float inv = 1.0f / cl;
-            const int nx = g.nx[l], ny = g.ny[l];
-            int x_lo = 0, x_hi = 0, y_lo = 0;
-            if (yy > y_hi) {  // entering level l: compute its window
-                int yh = 0;
-                if (nx * ny > 1) {
-                    const float ry = g.rfac * (0.5f * fmaxf(hj, 0.0f) + cl) + 1.0f;
-                    y_lo = clampi((int)floorf((cy - ry) * inv), 0, ny - 1);
-                    yh = clampi((int)floorf((cy + ry) * inv), 0, ny - 1);
-                }
-                yy = y_lo; y_hi = yh;
-            }
-            if (nx * ny > 1) {
-                const float rx = g.rfac * (0.5f * fmaxf(wj, 0.0f) + cl) + 1.0f;
-                x_lo = clampi((int)floorf((cx - rx) * inv), 0, nx - 1);
-                x_hi = clampi((int)floorf((cx + rx) * inv), 0, nx - 1);
-            }
+    const int sub = threadIdx.x & (kBuildLanes - 1);
+    if (slot >= NA || ws.ckey[slot] == 0xFFFFFFFFu) return;
+    const long long i = ws.cval[slot];
+    const uint64_t key = ws.keys[i];
+    const int seg = (int)(key >> kClsShift), n = seg / kMaxCls;
+    const float offset = seg_offset(ws, n, seg % kMaxCls, nms_mode);
+    const float4 b = ws.sbox[i];
+    const float area = box_area(b);
+    const float wj = b.z - b.x, hj = b.w - b.y;
+    const float cx = 0.5f * (b.x + b.z) - offset, cy = 0.5f * (b.y + b.w) - offset;
+    const int t = grid_level(fmaxf(wj, hj), g);
+    const int l_hi = min(g.nlev - 1, t + g.delta);
+    for (int l = t; l <= l_hi; ++l) {
+        const float cl = g.c0 * (float)(1 << l);
+        const float inv = 1.0f / cl;
+        const int nx = g.nx[l], ny = g.ny[l];
+        int x_lo = 0, x_hi = 0, y_lo = 0, y_hi = 0;
+        if (nx * ny > 1) {
+            const float rx = g.rfac * (0.5f * fmaxf(wj, 0.0f) + cl) + 1.0f, ry = g.rfac * (0.5f * fmaxf(hj, 0.0f) + cl) + 1.0f;
+            x_lo = clampi((int)floorf((cx - rx) * inv), 0, nx - 1);
+            x_hi = clampi((int)floorf((cx + rx) * inv), 0, nx - 1);
+            y_lo = clampi((int)floorf((cy - ry) * inv), 0, ny - 1);
+            y_hi = clampi((int)floorf((cy + ry) * inv), 0, ny - 1);
+        }
+        for (int yy = y_lo; yy <= y_hi; ++yy) {
             const uint32_t k0 = (uint32_t)seg * kCellStride + (uint32_t)(g.base[l] + yy * nx + x_lo);
-            q = ws.cell_begin[k0];
-            q_end = ws.cell_begin[k0 + (x_hi - x_lo) + 1];
-            row_ready = q < q_end;
-            if (++yy > y_hi) { ++l; yy = 0; y_hi = -1; }
-        }
-        const bool work = active && row_ready;
-        if (!__any_sync(0xffffffffu, work)) break;
-        int m = 0x7FFFFFFF;
-        bool hit = false;
-        if (work) {
-            const int qq = q + sub;
-            if (qq < q_end) {
-                const float4 kb = ws.cbox[qq];
+            const int q_end = ws.cell_begin[k0 + (x_hi - x_lo) + 1];
+            for (int q = ws.cell_begin[k0] + sub; q < q_end; q += kBuildLanes) {
+                const float4 kb = ws.cbox[q];
                 if (iou_gt(kb, box_area(kb), b, area, iou_thr)) {  // rare: only then look up the priority
-                    m = ws.cval[qq];
-                    hit = m < i;
+                    const int m = ws.cval[q];
+                    if (m < i) nms2_add_pred(ws, i, m, n);
+                    else if (m > i && l > t) nms2_add_pred(ws, m, (int)i, n);  // same level: the other box records it itself
                 }
             }
-            q += kBuildLanes;
-            if (q >= q_end) row_ready = false;
         }
-        const unsigned hm = __ballot_sync(0xffffffffu, hit) & grp_mask;
-        if (hit) {
-            const int pos = cnt + __popc(hm & ((1u << lane) - 1u));
-            if (pos < kMaxPreds) my[pos] = m;
-        }
-        cnt += __popc(hm);
     }
-    if (active && sub == 0) {
-        ws.npred[i] = min(cnt, kMaxPreds);
-        if (cnt > kMaxPreds) ws.overflow[n] = 1;
-        ws.status[i] = cnt == 0 ? 1 : 0;
-    }
+}
+
+// after all edges are in place: boxes without predecessors are kept outright
+__global__ void hn_nms2_seed_kernel(DetWs ws, long long NA) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NA || ws.keys[i] == ~0ull) return;
+    const int np = ws.npred[i];
+    if (np > kMaxPreds) ws.npred[i] = kMaxPreds;
+    ws.status[i] = np == 0 ? 1 : 0;
 }
 
 __global__ void __launch_bounds__(256) hn_nms2_rounds_kernel(DetWs ws, long long NA) {
@@ -816,6 +785,8 @@ extern "C" int hn_det_decode_nms(const hn_det_desc* d, void* stream) {
         tb = ws.cub2_bytes;
         HN_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(ws.cub2_tmp, tb, ws.cell_cnt, ws.cell_begin, (int)T, s));
         hn_nms2_build_kernel<<<hn_cdiv(NA * kBuildLanes, 256), 256, 0, s>>>(ws, NA, d->nms_mode, d->iou_thres, geom);
+        HN_CHECK_CUDA(cudaGetLastError());
+        hn_nms2_seed_kernel<<<hn_cdiv(NA, 256), 256, 0, s>>>(ws, NA);
         HN_CHECK_CUDA(cudaGetLastError());
         {
             static int blocks_per_sm = 0;
