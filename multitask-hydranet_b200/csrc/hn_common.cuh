@@ -110,13 +110,30 @@ __device__ __forceinline__ void hn_tma_load_4d(void* dst, const void* tmap, uint
         : "memory");
 }
 
-// B-tile slice multicast to every CTA of the cluster in `mask` (same smem offset / same mbarrier offset in each)
-__device__ __forceinline__ void hn_tma_load_2d_mcast(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t mask) {
+// ---- CTA pair (cta_group::2): both CTAs load their halves, the barrier of the leader CTA (cluster rank 0)
+// collects the transaction bytes of both ----
+__device__ __forceinline__ uint32_t hn_mapa(uint32_t smem_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void hn_tma_load_2d_pair(void* dst, const void* tmap, uint32_t leader_bar, int c0, int c1) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
-        "[%2], %5;" ::"r"(hn_smem_u32(dst)),
-        "l"((uint64_t)tmap), "r"(hn_smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            hn_smem_u32(dst)),
+        "l"((uint64_t)tmap), "r"(leader_bar), "r"(c0), "r"(c1)
         : "memory");
+}
+__device__ __forceinline__ void hn_tma_load_4d_pair(void* dst, const void* tmap, uint32_t leader_bar, int c0, int c1, int c2,
+                                                    int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2];" ::"r"(hn_smem_u32(dst)),
+        "l"((uint64_t)tmap), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void hn_mbar_arrive_remote(uint32_t cluster_bar_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t hn_cluster_ctarank() {
     uint32_t r;
@@ -176,11 +193,33 @@ __device__ __forceinline__ void hn_umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(hn_smem_u32(bar))
                  : "memory");
 }
-// same, arriving on the barrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void hn_umma_commit_mcast(uint64_t* bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+// ---- cta_group::2 flavours: one thread of the leader CTA drives the tensor cores of both SMs (M = 256) ----
+__device__ __forceinline__ void hn_tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(hn_smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void hn_tmem_relinquish_pair() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void hn_tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void hn_umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+// arrives on the barrier at this offset in both CTAs of the pair once the issued MMAs have retired
+__device__ __forceinline__ void hn_umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                      hn_smem_u32(bar)),
-                 "h"(mask)
+                 "h"((uint16_t)3)
                  : "memory");
 }
 __device__ __forceinline__ void hn_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {

@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int BN = p.bn;
     const int stages = p.stages;
-    const int b_tile_bytes = BN * 128;
+    const int b_tile_bytes = (p.cluster == 2 ? BN / 2 : BN) * 128;  // a CTA of a pair holds half of the weight rows
     uint8_t* sA = smem;
     uint8_t* sB = smem + stages * kATileBytes;
     uint8_t* sO = sB + stages * b_tile_bytes;  // n_staging x 16 KB output staging (1024-byte aligned)
@@ -213,12 +213,13 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    // persistent loop over work items, one item per cluster per iteration
-    const int CS = p.cluster;
-    const int rank = CS > 1 ? (int)hn_cluster_ctarank() : 0;
+    // persistent loop over work items, one item per CTA (or per CTA pair) per iteration
+    const int CS = p.cluster;          // 2: CTA pair driving one 256-row cta_group::2 MMA
+    const bool PAIR = CS == 2;
+    const int rank = PAIR ? (int)hn_cluster_ctarank() : 0;
+    const bool leader = rank == 0;
     const int total_tiles = p.m_groups * p.n_tiles;
     const int t_first = blockIdx.x / CS, t_step = gridDim.x / CS;
-    const uint16_t cmask = (uint16_t)((1u << CS) - 1u);
     long long* dbg = p.dbg ? p.dbg + (long long)blockIdx.x * 16 : nullptr;
     if (dbg && threadIdx.x == 0) dbg[0] = hn_globaltimer();
 
@@ -228,21 +229,21 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
         if (p.n_staging) hn_tma_prefetch_desc(&p.tmO);
         for (int s = 0; s < stages; ++s) {
             hn_mbar_init(&bar_full[s], 1);
-            hn_mbar_init(&bar_empty[s], CS);  // every CTA of the cluster must have consumed the slot (B is multicast into it)
+            hn_mbar_init(&bar_empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             hn_mbar_init(&bar_acc_full[a], 1);
-            hn_mbar_init(&bar_acc_empty[a], kEpiThreads / 32);
+            hn_mbar_init(&bar_acc_empty[a], CS * (kEpiThreads / 32));  // pair: the peer's epilogue warps arrive here too
         }
         hn_mbar_fence_init();
     }
     if (warp == 1) {
-        hn_tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-        hn_tmem_relinquish();
+        if (PAIR) { hn_tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols); hn_tmem_relinquish_pair(); }
+        else { hn_tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols); hn_tmem_relinquish(); }
     }
     hn_tc_fence_before();
     __syncthreads();
-    if (CS > 1) hn_cluster_sync();  // peers' barriers are initialised before anything remote touches them
+    if (PAIR) hn_cluster_sync();  // the peer's barriers are initialised before anything remote touches them
     hn_tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (dbg && threadIdx.x == 0) dbg[1] = hn_globaltimer();
@@ -253,30 +254,35 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
             const uint32_t stage_bytes = (uint32_t)(kATileBytes + b_tile_bytes);
             int s = 0;
             uint32_t ph = 0;
-            const int b_rows = BN / CS;  // this CTA's slice of the weight tile
             for (int t = t_first; t < total_tiles; t += t_step) {
                 const TileOrigin o = tile_origin(p, t, rank);
                 const int c_shift = p.grouped ? o.n0 : 0;
                 for (int k = 0; k < p.num_taps; ++k) {
                     hn_mbar_wait(&bar_empty[s], ph ^ 1);
-                    hn_mbar_expect_tx(&bar_full[s], stage_bytes);
                     const hn_tap tp = p.taps[k];
-                    hn_tma_load_4d(sA + s * kATileBytes, &p.tmA[tp.src], &bar_full[s], (int)tp.c0 + c_shift, o.x0 + (int)tp.dx,
-                                   o.y0 + (int)tp.dy, o.img);
-                    if (CS == 1)
+                    if (!PAIR) {
+                        hn_mbar_expect_tx(&bar_full[s], stage_bytes);
+                        hn_tma_load_4d(sA + s * kATileBytes, &p.tmA[tp.src], &bar_full[s], (int)tp.c0 + c_shift, o.x0 + (int)tp.dx,
+                                       o.y0 + (int)tp.dy, o.img);
                         hn_tma_load_2d(sB + s * b_tile_bytes, &p.tmB, &bar_full[s], k * 64, o.n0);
-                    else
-                        hn_tma_load_2d_mcast(sB + s * b_tile_bytes + rank * b_rows * 128, &p.tmBpart, &bar_full[s], k * 64,
-                                             o.n0 + rank * b_rows, cmask);
+                    } else {
+                        // each CTA loads its own 128 A rows and its half of the weight rows; all bytes are counted on the
+                        // leader's barrier, which is the one the (single) MMA issuer waits on
+                        if (leader) hn_mbar_expect_tx(&bar_full[s], 2u * stage_bytes);
+                        const uint32_t lbar = hn_mapa(hn_smem_u32(&bar_full[s]), 0);
+                        hn_tma_load_4d_pair(sA + s * kATileBytes, &p.tmA[tp.src], lbar, (int)tp.c0 + c_shift, o.x0 + (int)tp.dx,
+                                            o.y0 + (int)tp.dy, o.img);
+                        hn_tma_load_2d_pair(sB + s * b_tile_bytes, &p.tmBpart, lbar, k * 64, o.n0 + rank * (BN / 2));
+                    }
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
                 if (dbg && t == t_first) dbg[2] = hn_globaltimer();
             }
         }
     } else if (warp == 1) {
-        // ------------------------------ MMA issuer ------------------------------
-        if (lane == 0) {
-            const uint32_t idesc = hn_umma_idesc_bf16(128, BN);
+        // ------------------------------ MMA issuer (pair: leader CTA only) ------------------------------
+        if (lane == 0 && leader) {
+            const uint32_t idesc = hn_umma_idesc_bf16(PAIR ? 256 : 128, BN);
             int s = 0, a = 0;
             uint32_t ph = 0, aph = 0;
             for (int t = t_first; t < total_tiles; t += t_step) {
@@ -293,13 +299,15 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
                     for (int kk = 0; kk < 4; ++kk) {
                         uint64_t da = hn_umma_desc_sw128(a_addr + kk * 32);
                         uint64_t db = hn_umma_desc_sw128(b_addr + kk * 32);
-                        hn_umma_bf16(d_tmem, da, db, idesc, (uint32_t)((k | kk) != 0));
+                        if (PAIR) hn_umma_bf16_pair(d_tmem, da, db, idesc, (uint32_t)((k | kk) != 0));
+                        else hn_umma_bf16(d_tmem, da, db, idesc, (uint32_t)((k | kk) != 0));
                     }
-                    // frees the smem slot once these MMAs retire -- in every CTA of the cluster, whose producers multicast into it
-                    if (CS == 1) hn_umma_commit(&bar_empty[s]); else hn_umma_commit_mcast(&bar_empty[s], cmask);
+                    // frees the smem slot once these MMAs retire (pair: in both CTAs)
+                    if (PAIR) hn_umma_commit_pair(&bar_empty[s]); else hn_umma_commit(&bar_empty[s]);
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
-                hn_umma_commit(&bar_acc_full[a]);  // accumulator complete
+                // accumulator complete (pair: each CTA's epilogue drains its own 128 rows)
+                if (PAIR) hn_umma_commit_pair(&bar_acc_full[a]); else hn_umma_commit(&bar_acc_full[a]);
                 if (dbg && t == t_first) dbg[4] = hn_globaltimer();
                 if (++a == 2) { a = 0; aph ^= 1; }
             }
@@ -410,7 +418,10 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
             // all TMEM reads of this accumulator are complete: hand it back to the MMA issuer
             hn_tc_fence_before();
             __syncwarp();
-            if (lane == 0) hn_mbar_arrive(&bar_acc_empty[a]);
+            if (lane == 0) {
+                if (PAIR) hn_mbar_arrive_remote(hn_mapa(hn_smem_u32(&bar_acc_empty[a]), 0));  // the issuer lives in the leader CTA
+                else hn_mbar_arrive(&bar_acc_empty[a]);
+            }
             if (dbg && ntile == 0 && et == 0) dbg[6] = hn_globaltimer();
             if (++a == 2) { a = 0; aph ^= 1; }
         }
@@ -420,10 +431,11 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
 
     hn_tc_fence_before();
     __syncthreads();
-    if (CS > 1) hn_cluster_sync();  // no CTA leaves while a peer may still multicast into it / arrive on its barriers
+    if (PAIR) hn_cluster_sync();  // neither CTA leaves while the pair's MMAs / remote arrivals may still touch it
     if (warp == 1) {
         hn_tc_fence_after();
-        hn_tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+        if (PAIR) hn_tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
+        else hn_tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
     if (dbg && threadIdx.x == 0) dbg[7] = hn_globaltimer();
 }
@@ -574,17 +586,26 @@ int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L) {
     if (d->epi == HN_EPI_SEGOUT) n_tiles = 1;
     p.m_tiles = m_tiles;
     p.n_tiles = n_tiles;
-    // clusters of 2 along M share the weight tile through TMA multicast (halves its L2 traffic) for wide N tiles
-    // (measured on B200: no gain -- the main loop is bound by shared-memory bandwidth, not L2 -- so off by default)
-    int cs = (g_conv_cluster > 0) ? g_conv_cluster : 1;
-    if (d->bn < 128 || m_tiles < 2 || d->epi != HN_EPI_STD || (d->bn / cs) % 8 != 0) cs = 1;
+    // CTA pairs (cta_group::2, M = 256): each SM stages and reads only half of the weight tile.  The 1-CTA main
+    // loop of a wide tile is bound by shared-memory bandwidth (TMA fill + operand reads ~ 96 KB per 64-deep K step);
+    // the pair cuts that to 64 KB.  Used for N tiles >= 128 when there are at least two M tiles.
+    int cs = (g_conv_cluster > 0) ? g_conv_cluster : 2;
+    if (cs != 2 || d->bn < 128 || d->bn % 32 != 0 || m_tiles < 2 || d->epi != HN_EPI_STD) cs = 1;
     p.cluster = cs;
     p.m_groups = hn_cdiv(m_tiles, cs);
-    if (cs > 1) {
-        int rc3 = encode_weight_map(&p.tmBpart, d->weight, d->w_rows, d->num_taps * 64, d->bn / cs);
+    int stages = d->stages;
+    if (cs == 2) {
+        int rc3 = encode_weight_map(&p.tmBpart, d->weight, d->w_rows, d->num_taps * 64, d->bn / 2);
         if (rc3) return rc3;
+        // half-size B stages: room for a deeper ring
+        int fit = (int)((227 * 1024 - 16 * 1024 - 6 * 1024) / (kATileBytes + d->bn * 64));
+        stages = d->num_taps < fit ? d->num_taps : fit;
+        if (stages > 8) stages = 8;
+        if (stages < 2) stages = 2;
+        p.stages = stages;
     }
-    const size_t base_smem = 1024 + (size_t)d->stages * (kATileBytes + d->bn * 128) + (2 * d->stages + 4) * 8 + 16 + 2 * d->bn * 4 + 64;
+    const int b_rows_cta = cs == 2 ? d->bn / 2 : d->bn;
+    const size_t base_smem = 1024 + (size_t)stages * (kATileBytes + b_rows_cta * 128) + (2 * stages + 4) * 8 + 16 + 2 * d->bn * 4 + 64;
     // bf16 outputs leave through shared memory + TMA store (coalesced, clipped by the tensor map) when the
     // 64-channel slabs of an N tile never spill into the next tile's channels
     p.n_staging = 0;

@@ -127,7 +127,9 @@ struct DetWs {
     int* kflag;          // [N*A] kept as int, and its exclusive scan
     int* kscan;
     int* overflow;       // [N] image has a box with more than kMaxPreds predecessors -> sequential kernel
-    int* changed;        // [2]
+    int* changed;        // [8] worklist sizes (ping-pong), round counter
+    int* wl_a;           // [N*A] undecided boxes, ping
+    int* wl_b;           // [N*A] pong
     size_t cub2_bytes;
     void* cub2_tmp;
 };
@@ -221,7 +223,9 @@ static size_t det_layout(int N, int A, void* base, DetWs* ws) {
     w.kflag = reinterpret_cast<int*>(take(NA * 4));
     w.kscan = reinterpret_cast<int*>(take(NA * 4));
     w.overflow = reinterpret_cast<int*>(take(N * 4));
-    w.changed = reinterpret_cast<int*>(take(16));
+    w.changed = reinterpret_cast<int*>(take(64));
+    w.wl_a = reinterpret_cast<int*>(take(NA * 4));
+    w.wl_b = reinterpret_cast<int*>(take(NA * 4));
     {
         size_t b1 = 0, b2 = 0;
         cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr);
@@ -566,7 +570,8 @@ __global__ void hn_nms2_cells_kernel(DetWs ws, long long NA) {
 // group strides over with coalesced box loads.  Every conflicting pair is discovered ONCE, from its smaller
 // box: a candidate scans only its own size level and the coarser ones (few, large cells) and records the edge
 // at the later box of the pair, i.e. in its own predecessor list or -- atomically -- in the other box's.
-static constexpr int kBuildLanes = 8;
+static constexpr int kBuildLanes = 4;
+static constexpr int kBuildMaxRanges = 24;
 __device__ __forceinline__ void nms2_add_pred(DetWs& ws, long long later, int earlier, int n) {
     const int pos = atomicAdd(ws.npred + later, 1);
     if (pos < kMaxPreds) ws.preds[later * kMaxPreds + pos] = earlier;
@@ -587,6 +592,10 @@ __global__ void __launch_bounds__(256) hn_nms2_build_kernel(DetWs ws, long long 
     const float cx = 0.5f * (b.x + b.z) - offset, cy = 0.5f * (b.y + b.w) - offset;
     const int t = grid_level(fmaxf(wj, hj), g);
     const int l_hi = min(g.nlev - 1, t + g.delta);
+    int scanned = 0, edges = 0;
+    // pass 1: the index range of every window row (independent loads, all in flight together)
+    int r_beg[kBuildMaxRanges], r_end[kBuildMaxRanges];
+    int nr = 0, n_same = 0;  // ranges [0, n_same) belong to the candidate's own level
     for (int l = t; l <= l_hi; ++l) {
         const float cl = g.c0 * (float)(1 << l);
         const float inv = 1.0f / cl;
@@ -601,16 +610,42 @@ __global__ void __launch_bounds__(256) hn_nms2_build_kernel(DetWs ws, long long 
         }
         for (int yy = y_lo; yy <= y_hi; ++yy) {
             const uint32_t k0 = (uint32_t)seg * kCellStride + (uint32_t)(g.base[l] + yy * nx + x_lo);
-            const int q_end = ws.cell_begin[k0 + (x_hi - x_lo) + 1];
-            for (int q = ws.cell_begin[k0] + sub; q < q_end; q += kBuildLanes) {
-                const float4 kb = ws.cbox[q];
-                if (iou_gt(kb, box_area(kb), b, area, iou_thr)) {  // rare: only then look up the priority
-                    const int m = ws.cval[q];
-                    if (m < i) nms2_add_pred(ws, i, m, n);
-                    else if (m > i && l > t) nms2_add_pred(ws, m, (int)i, n);  // same level: the other box records it itself
+            if (nr < kBuildMaxRanges) {
+                r_beg[nr] = ws.cell_begin[k0];
+                r_end[nr] = ws.cell_begin[k0 + (x_hi - x_lo) + 1];
+                ++nr;
+            } else {  // (never with the default geometry) fall back to scanning this row right away
+                const int q_end = ws.cell_begin[k0 + (x_hi - x_lo) + 1];
+                for (int q = ws.cell_begin[k0] + sub; q < q_end; q += kBuildLanes) {
+                    const float4 kb = ws.cbox[q];
+                    if (iou_gt(kb, box_area(kb), b, area, iou_thr)) {
+                        const int m = ws.cval[q];
+                        if (m < i) nms2_add_pred(ws, i, m, n);
+                        else if (m > i && l > t) nms2_add_pred(ws, m, (int)i, n);
+                    }
                 }
             }
         }
+        if (l == t) n_same = nr;
+    }
+    // pass 2: scan
+    for (int r = 0; r < nr; ++r) {
+        const bool upper = r >= n_same;
+        const int q_end = r_end[r];
+        for (int q = r_beg[r] + sub; q < q_end; q += kBuildLanes) {
+            const float4 kb = ws.cbox[q];
+            ++scanned;
+            if (iou_gt(kb, box_area(kb), b, area, iou_thr)) {  // rare: only then look up the priority
+                const int m = ws.cval[q];
+                ++edges;
+                if (m < i) nms2_add_pred(ws, i, m, n);
+                else if (m > i && upper) nms2_add_pred(ws, m, (int)i, n);  // same level: the other box records it itself
+            }
+        }
+    }
+    if (ws.dbg) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(ws.dbg) + 0, (unsigned long long)scanned);
+        atomicAdd(reinterpret_cast<unsigned long long*>(ws.dbg) + 1, (unsigned long long)edges);
     }
 }
 
@@ -621,40 +656,69 @@ __global__ void hn_nms2_seed_kernel(DetWs ws, long long NA) {
     const int np = ws.npred[i];
     if (np > kMaxPreds) ws.npred[i] = kMaxPreds;
     ws.status[i] = np == 0 ? 1 : 0;
+    // undecided boxes go on the first worklist (warp-aggregated append; order is irrelevant)
+    const bool und = np != 0;
+    const unsigned m = __ballot_sync(__activemask(), und);
+    if (und) {
+        const unsigned lane = threadIdx.x & 31;
+        const int leader = __ffs(m) - 1;
+        int base = 0;
+        if ((int)lane == leader) base = atomicAdd(ws.changed + 0, __popc(m));
+        base = __shfl_sync(m, base, leader);
+        ws.wl_a[base + __popc(m & ((1u << lane) - 1u))] = (int)i;
+    }
 }
 
+// Rounds over a shrinking worklist: every round decides the boxes whose predecessors are all decided and
+// carries the rest over; the loop ends when the worklist is empty (the earliest undecided box of every
+// segment always gets decided, so every round makes progress).
 __global__ void __launch_bounds__(256) hn_nms2_rounds_kernel(DetWs ws, long long NA) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
-    volatile int* changed = ws.changed;
+    volatile int* cnt = ws.changed;  // [0] = size of the current list, [1] = size of the next list
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int* cur = ws.wl_a;
+    int* nxt = ws.wl_b;
     int round = 0;
     while (true) {
-        int* flag = ws.changed + (round & 1);
-        if (tid0 == 0) ws.changed[(round + 1) & 1] = 0;  // reset the other flag for the next round
-        bool any = false;
-        for (long long i = tid0; i < NA; i += stride) {
-            if (__ldcg(ws.status + i) != 0) continue;
-            const int np = ws.npred[i];
-            const int* my = ws.preds + i * kMaxPreds;
-            bool kept_pred = false, all_supp = true;
-            for (int k = 0; k < np; ++k) {
-                const unsigned char st = __ldcg(ws.status + my[k]);
-                if (st == 1) { kept_pred = true; break; }
-                if (st == 0) all_supp = false;
+        const int n_cur = cnt[round & 1];
+        if (n_cur == 0) break;
+        const long long n_pad = ((long long)n_cur + 31) & ~31ll;  // whole warps iterate together (ballot below)
+        for (long long w = tid0; w < n_pad; w += stride) {
+            bool carry = false;
+            int i = 0;
+            if (w < n_cur) {
+                i = __ldcg(cur + w);
+                const int np = ws.npred[i];
+                const int* my = ws.preds + (long long)i * kMaxPreds;
+                bool kept_pred = false, all_supp = true;
+                for (int k = 0; k < np; ++k) {
+                    const unsigned char st = __ldcg(ws.status + my[k]);
+                    if (st == 1) { kept_pred = true; break; }
+                    if (st == 0) all_supp = false;
+                }
+                if (kept_pred) ws.status[i] = 2;
+                else if (all_supp) ws.status[i] = 1;
+                else carry = true;
             }
-            if (kept_pred) { ws.status[i] = 2; any = true; }
-            else if (all_supp) { ws.status[i] = 1; any = true; }
+            // warp-aggregated append to the next worklist: one atomic per warp
+            const unsigned m = __ballot_sync(0xffffffffu, carry);
+            if (m) {
+                const unsigned lane = threadIdx.x & 31;
+                int base = 0;
+                if (lane == 0) base = atomicAdd(ws.changed + ((round + 1) & 1), __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (carry) nxt[base + __popc(m & ((1u << lane) - 1u))] = i;
+            }
         }
-        if (any) *flag = 1;
         grid.sync();
-        const int c = changed[round & 1];
-        if (!c) break;
+        if (tid0 == 0) ws.changed[round & 1] = 0;  // becomes the "next" counter of the following round
+        int* t = cur; cur = nxt; nxt = t;
         ++round;
         grid.sync();
     }
-    if (tid0 == 0) ws.changed[2] = round + 1;  // diagnostics: number of rounds
+    if (tid0 == 0) ws.changed[2] = round;  // diagnostics: number of rounds
     for (long long i = tid0; i < NA; i += stride) ws.kflag[i] = __ldcg(ws.status + i) == 1 ? 1 : 0;
 }
 
@@ -717,7 +781,7 @@ __global__ void hn_det_init_kernel(DetWs ws, int N) {
         ws.max_coord[i] = float_to_ordered(-INFINITY);
         ws.overflow[i] = 0;
     }
-    if (i < 2) ws.changed[i] = 0;
+    if (i < 8) ws.changed[i] = 0;
     if (i < N * kMaxCls) {
         ws.seg_start[i] = 0;
         ws.seg_end[i] = 0;
@@ -793,7 +857,8 @@ extern "C" int hn_det_decode_nms(const hn_det_desc* d, void* stream) {
             if (blocks_per_sm == 0)
                 HN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, hn_nms2_rounds_kernel, 256, 0));
             int sms = hn_device_sm_count();
-            long long want = (NA + 255) / 256, cap = (long long)sms * (blocks_per_sm > 0 ? blocks_per_sm : 1);
+            // few, fat CTAs: the loop is dominated by grid-wide barriers, whose cost grows with the CTA count
+            long long want = (NA + 255) / 256, cap = (long long)sms * (blocks_per_sm > 2 ? 2 : (blocks_per_sm > 0 ? blocks_per_sm : 1));
             dim3 grid((unsigned)(want < cap ? want : cap));
             long long na = NA;
             void* args[] = {&ws, &na};
