@@ -195,12 +195,14 @@ __device__ __forceinline__ void epi_segout(const ConvParams& p, const EpiRow& e,
 // concurrently running CTAs share the weight tile in L2).  Shared-memory ring (full/empty mbarriers)
 // between the TMA producer and the MMA issuer; two TMEM accumulators (acc_full/acc_empty) so the
 // epilogue of tile i overlaps the main loop of tile i+1.
+// kPair = true: the cta_group::2 build (must be launched as 2-CTA clusters); false: no pair instructions at all
+template <bool kPair>
 __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int BN = p.bn;
     const int stages = p.stages;
-    const int b_tile_bytes = (p.cluster == 2 ? BN / 2 : BN) * 128;  // a CTA of a pair holds half of the weight rows
+    const int b_tile_bytes = (kPair ? BN / 2 : BN) * 128;  // a CTA of a pair holds half of the weight rows
     uint8_t* sA = smem;
     uint8_t* sB = smem + stages * kATileBytes;
     uint8_t* sO = sB + stages * b_tile_bytes;  // n_staging x 16 KB output staging (1024-byte aligned)
@@ -214,9 +216,10 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     // persistent loop over work items, one item per CTA (or per CTA pair) per iteration
-    const int CS = p.cluster;          // 2: CTA pair driving one 256-row cta_group::2 MMA
-    const bool PAIR = CS == 2;
-    const int rank = PAIR ? (int)hn_cluster_ctarank() : 0;
+    constexpr int CS = kPair ? 2 : 1;  // 2: CTA pair driving one 256-row cta_group::2 MMA
+    constexpr bool PAIR = kPair;
+    int rank = 0;
+    if constexpr (PAIR) rank = (int)hn_cluster_ctarank();
     const bool leader = rank == 0;
     const int total_tiles = p.m_groups * p.n_tiles;
     const int t_first = blockIdx.x / CS, t_step = gridDim.x / CS;
@@ -238,12 +241,12 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
         hn_mbar_fence_init();
     }
     if (warp == 1) {
-        if (PAIR) { hn_tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols); hn_tmem_relinquish_pair(); }
+        if constexpr (PAIR) { hn_tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols); hn_tmem_relinquish_pair(); }
         else { hn_tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols); hn_tmem_relinquish(); }
     }
     hn_tc_fence_before();
     __syncthreads();
-    if (PAIR) hn_cluster_sync();  // the peer's barriers are initialised before anything remote touches them
+    if constexpr (PAIR) hn_cluster_sync();  // the peer's barriers are initialised before anything remote touches them
     hn_tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (dbg && threadIdx.x == 0) dbg[1] = hn_globaltimer();
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
                 for (int k = 0; k < p.num_taps; ++k) {
                     hn_mbar_wait(&bar_empty[s], ph ^ 1);
                     const hn_tap tp = p.taps[k];
-                    if (!PAIR) {
+                    if constexpr (!PAIR) {
                         hn_mbar_expect_tx(&bar_full[s], stage_bytes);
                         hn_tma_load_4d(sA + s * kATileBytes, &p.tmA[tp.src], &bar_full[s], (int)tp.c0 + c_shift, o.x0 + (int)tp.dx,
                                        o.y0 + (int)tp.dy, o.img);
@@ -299,15 +302,15 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
                     for (int kk = 0; kk < 4; ++kk) {
                         uint64_t da = hn_umma_desc_sw128(a_addr + kk * 32);
                         uint64_t db = hn_umma_desc_sw128(b_addr + kk * 32);
-                        if (PAIR) hn_umma_bf16_pair(d_tmem, da, db, idesc, (uint32_t)((k | kk) != 0));
+                        if constexpr (PAIR) hn_umma_bf16_pair(d_tmem, da, db, idesc, (uint32_t)((k | kk) != 0));
                         else hn_umma_bf16(d_tmem, da, db, idesc, (uint32_t)((k | kk) != 0));
                     }
                     // frees the smem slot once these MMAs retire (pair: in both CTAs)
-                    if (PAIR) hn_umma_commit_pair(&bar_empty[s]); else hn_umma_commit(&bar_empty[s]);
+                    if constexpr (PAIR) hn_umma_commit_pair(&bar_empty[s]); else hn_umma_commit(&bar_empty[s]);
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
                 // accumulator complete (pair: each CTA's epilogue drains its own 128 rows)
-                if (PAIR) hn_umma_commit_pair(&bar_acc_full[a]); else hn_umma_commit(&bar_acc_full[a]);
+                if constexpr (PAIR) hn_umma_commit_pair(&bar_acc_full[a]); else hn_umma_commit(&bar_acc_full[a]);
                 if (dbg && t == t_first) dbg[4] = hn_globaltimer();
                 if (++a == 2) { a = 0; aph ^= 1; }
             }
@@ -419,7 +422,7 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
             hn_tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (PAIR) hn_mbar_arrive_remote(hn_mapa(hn_smem_u32(&bar_acc_empty[a]), 0));  // the issuer lives in the leader CTA
+                if constexpr (PAIR) hn_mbar_arrive_remote(hn_mapa(hn_smem_u32(&bar_acc_empty[a]), 0));  // the issuer lives in the leader CTA
                 else hn_mbar_arrive(&bar_acc_empty[a]);
             }
             if (dbg && ntile == 0 && et == 0) dbg[6] = hn_globaltimer();
@@ -431,10 +434,10 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
 
     hn_tc_fence_before();
     __syncthreads();
-    if (PAIR) hn_cluster_sync();  // neither CTA leaves while the pair's MMAs / remote arrivals may still touch it
+    if constexpr (PAIR) hn_cluster_sync();  // neither CTA leaves while the pair's MMAs / remote arrivals may still touch it
     if (warp == 1) {
         hn_tc_fence_after();
-        if (PAIR) hn_tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
+        if constexpr (PAIR) hn_tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
         else hn_tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
     if (dbg && threadIdx.x == 0) dbg[7] = hn_globaltimer();
@@ -642,11 +645,13 @@ int hn_conv_launch(const ConvLaunch* L, cudaStream_t stream) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(hn_conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_err = cudaFuncSetAttribute(hn_conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(hn_conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     HN_CHECK_CUDA(attr_err);
     if (L->cluster <= 1) {
-        hn_conv_gemm_kernel<<<L->grid, 192, L->smem, stream>>>(L->prm);
+        hn_conv_gemm_kernel<false><<<L->grid, 192, L->smem, stream>>>(L->prm);
         HN_CHECK_CUDA(cudaGetLastError());
         return HN_OK;
     }
@@ -663,7 +668,7 @@ int hn_conv_launch(const ConvLaunch* L, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, hn_conv_gemm_kernel, L->prm));
+    HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, hn_conv_gemm_kernel<true>, L->prm));
     return HN_OK;
 }
 
