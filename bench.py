@@ -173,21 +173,50 @@ def run_native(args):
             ev_in[k].record(s_in)
 
     segcopy = [torch.empty((B, H, W), dtype=torch.uint8, device=dev) for _ in range(2)]
+    pin_seg = [torch.empty((B, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    pin_cnt = [torch.empty((2, B), dtype=torch.int32).pin_memory() for _ in range(2)]
+    A_tot = 76725
+    pin_det = [torch.empty((B, A_tot, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
+    pin_lane = [torch.empty((B, 400, 4 + 1 + 80), dtype=torch.float32).pin_memory() for _ in range(2)]
+    pending = [None, None]
+    d2h_bytes = [0]
 
-    def download(k, seg_u8, d, l):
+    def enqueue_small(k, seg_u8, d, l):
+        """Stage 1 of the download (stream s_out): class map + per-image counts."""
         boxes, scores, cids, count, _ = d
-        srcs = [seg_u8, count, boxes, scores, cids, l[0], l[1], l[2], l[3]]
-        if pinned[k] is None:
-            pinned[k] = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in srcs]
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_done[k])
-            for p_, t in zip(pinned[k], srcs):
+            for t in (seg_u8, count, boxes, scores, cids, l[0], l[1], l[2], l[3]):
                 t.record_stream(s_out)  # per-call decoder outputs: keep the allocator from recycling them early
-                p_.copy_(t, non_blocking=True)
-        return pinned[k]
+            pin_seg[k].copy_(seg_u8, non_blocking=True)
+            pin_cnt[k][0].copy_(count, non_blocking=True)
+            pin_cnt[k][1].copy_(l[0], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(s_out)
+        pending[k] = (ev, d, l)
+
+    def finish(k):
+        """Stage 2: once the counts are on the host, fetch exactly the kept detections / lanes (like the reference's
+        `.cpu().numpy()` on the sliced tensors, detection_loss.py:99-103)."""
+        if pending[k] is None:
+            return
+        ev, d, l = pending[k]
+        pending[k] = None
+        ev.synchronize()
+        boxes, scores, cids, count, _ = d
+        kmax, lmax = int(pin_cnt[k][0].max()), int(pin_cnt[k][1].max())
+        with torch.cuda.stream(s_out):
+            if kmax:
+                pin_det[k][:, :kmax, 0:4].copy_(boxes[:, :kmax], non_blocking=True)
+                pin_det[k][:, :kmax, 4].copy_(scores[:, :kmax], non_blocking=True)
+                pin_det[k][:, :kmax, 5].copy_(cids[:, :kmax], non_blocking=True)
+            if lmax:
+                pin_lane[k][:, :lmax, 0:4].copy_(l[1][:, :lmax], non_blocking=True)
+                pin_lane[k][:, :lmax, 4].copy_(l[2][:, :lmax], non_blocking=True)
+                pin_lane[k][:, :lmax, 5:].copy_(l[3][:, :lmax], non_blocking=True)
+        d2h_bytes[0] = B * H * W + 2 * B * 4 + B * kmax * 24 + B * lmax * 85 * 4
 
     def e2e_loop(n):
-        res = None
         for k in range(2):
             ev_free[k].record(stream)
         upload(0)
@@ -200,15 +229,17 @@ def run_native(args):
             ev_free[k].record(stream)
             segcopy[k].copy_(out["seg_cls_u8"])  # the class map is the plan's static buffer: snapshot it for the download
             ev_done[k].record(stream)
-            res = download(k, segcopy[k], d, l)
+            enqueue_small(k, segcopy[k], d, l)
+            finish(1 - k)  # while step i runs, complete the download of step i-1
+        finish((n - 1) % 2)
         s_out.synchronize()
-        return res
+        return None
 
     e2e_loop(max(3, args.warmup // 2))
     barrier()
     t0 = time.perf_counter()
     e0.record(stream)
-    res = e2e_loop(args.steps)
+    e2e_loop(args.steps)
     torch.cuda.synchronize(dev)
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3
     barrier()
@@ -218,7 +249,17 @@ def run_native(args):
     e2e_ms = float(t.item())
     e2e_val = world * B * args.steps / (e2e_ms / 1e3)
     h2d = host[0].numel() * 4
-    d2h = sum(r.numel() * r.element_size() for r in res)
+    d2h = d2h_bytes[0]
+    # host link speed, for context (pinned memory, 157 MB)
+    tcp = []
+    for _ in range(3):
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record(stream)
+        xin[0].copy_(host[0], non_blocking=True)
+        b_.record(stream)
+        torch.cuda.synchronize(dev)
+        tcp.append(a_.elapsed_time(b_))
+    h2d_gbs = h2d / (min(tcp) * 1e-3) / 1e9
 
     # ---------------- roofline of the dominant kernel (tcgen05 implicit-GEMM conv) ----------------
     roof = cpu = None
@@ -300,7 +341,8 @@ def run_native(args):
                            "global_batch": world * B, "parallelism": "batch-sharded x%d, no collective" % world,
                            "l2_policy": "2 alternating input batches of 157 MB each (> 126 MB L2)"},
                 "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": round(e2e_ms / args.steps, 3)},
+                        "ms_per_step": round(e2e_ms / args.steps, 3), "h2d_link_gbs": round(h2d_gbs, 1),
+                        "pipeline": "upload of step i+1 and download of step i-1 overlap the compute of step i"},
                 "gpu_launches": n_launch * args.steps, "clocks": clocks, "latency_b1_ms": lat, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -41,6 +41,7 @@ extern "C" {
 
 #define HN_MAX_SRC 6
 #define HN_MAX_TAPS 96
+#define HN_MAX_GROUPS 8
 
 /* 4-D NHWC bf16 view; channel stride is 1; strides in elements. */
 typedef struct hn_view {
@@ -86,6 +87,17 @@ typedef struct hn_conv_desc {
     int32_t grouped; /* 1: block-diagonal (grouped) conv: tap channel offset += n-tile origin; needs bn == 64 */
     void* out2;      /* HN_EPI_SEGOUT: uint8 class map [N][2*out_h][2*out_w] or NULL */
     int32_t n_cls;   /* HN_EPI_SEGOUT: classes per sub-pixel (columns = 4 parities x 8) */
+    /* Row groups (flat mode): one launch over several stacked problems that share the weights -- the five pyramid
+     * levels of a detection tower (detection.py:30-37: shared conv, per-level BatchNorm).  Rows [group_end[g-1],
+     * group_end[g]) form group g. */
+    int32_t n_groups; /* 0 = off */
+    int32_t group_end[HN_MAX_GROUPS];
+    const float* group_scale; /* fp32 [n_groups][n_tiles*bn]: epilogue = act(acc * scale + shift); NULL = plain bias */
+    const float* group_shift;
+    int32_t group_addr;       /* 1: output row address = n*out_stride_n + group_out_base[g] + pix*out_stride_x with
+                                 (n, pix) = divmod(row - group start, group_hw[g]) (fp32 head outputs) */
+    int32_t group_hw[HN_MAX_GROUPS];
+    int64_t group_out_base[HN_MAX_GROUPS];
 } hn_conv_desc;
 
 /* Stem: 3x3 s2 p1 conv 3->32 + folded BN + ReLU, fp32 NCHW in, bf16 NHWC out (anynet.py:8-20). */
@@ -113,6 +125,15 @@ typedef struct hn_node_desc {
     const float* dw; /* fp32 [9][C] */
     hn_view out;
 } hn_node_desc;
+
+/* Plain depthwise 3x3 (zero pad 1) over up to HN_MAX_GROUPS independent (input, output) view pairs that share the
+ * weights: all pyramid levels of a detection-tower layer in one launch (detection.py:33-37). */
+typedef struct hn_dw_multi_desc {
+    int32_t n;
+    hn_view in[HN_MAX_GROUPS];
+    hn_view out[HN_MAX_GROUPS];
+    const float* dw; /* fp32 [9][C] */
+} hn_dw_multi_desc;
 
 #define HN_POOL_ZERO_RB 0 /* MaxPool2dStaticSamePadding(3,2): zero pad right/bottom, zeros take part */
 #define HN_POOL_NEGINF 1  /* nn.MaxPool2d(3,2,padding=1) (lanedetect.py:41) */
@@ -195,6 +216,7 @@ typedef struct hn_lane_desc {
 int hn_conv_fwd(const hn_conv_desc* d, void* stream);
 int hn_stem_fwd(const hn_stem_desc* d, void* stream);
 int hn_node_fwd(const hn_node_desc* d, void* stream);
+int hn_dw_multi_fwd(const hn_dw_multi_desc* d, void* stream);
 int hn_pool_fwd(const hn_pool_desc* d, void* stream);
 int hn_lanefuse_fwd(const hn_lanefuse_desc* d, void* stream);
 int hn_se_pool_fwd(const hn_se_pool_desc* d, void* stream);
@@ -214,6 +236,7 @@ int hn_plan_destroy(hn_plan* p);
 int hn_plan_add_conv(hn_plan* p, const hn_conv_desc* d);
 int hn_plan_add_stem(hn_plan* p, const hn_stem_desc* d);
 int hn_plan_add_node(hn_plan* p, const hn_node_desc* d);
+int hn_plan_add_dw_multi(hn_plan* p, const hn_dw_multi_desc* d);
 int hn_plan_add_pool(hn_plan* p, const hn_pool_desc* d);
 int hn_plan_add_lanefuse(hn_plan* p, const hn_lanefuse_desc* d);
 int hn_plan_add_se_pool(hn_plan* p, const hn_se_pool_desc* d);

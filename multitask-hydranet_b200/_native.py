@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libhydranet_b200.so")
 
 HN_MAX_SRC = 6
 HN_MAX_TAPS = 96
+HN_MAX_GROUPS = 8
 
 ACT_NONE, ACT_RELU, ACT_SWISH, ACT_ELU, ACT_SIGMOID = range(5)
 HALO_NONE, HALO_REFLECT, HALO_REPLICATE = range(3)
@@ -41,7 +42,10 @@ class ConvDesc(C.Structure):
                 ("out_stride_n", C.c_int64), ("out_stride_y", C.c_int64), ("out_stride_x", C.c_int64),
                 ("out_scale", C.c_int32), ("out_oy", C.c_int32), ("out_ox", C.c_int32), ("halo", C.c_int32),
                 ("res", C.c_void_p), ("res_stride_n", C.c_int64), ("res_stride_y", C.c_int64), ("res_stride_x", C.c_int64),
-                ("res_relu", C.c_int32), ("grouped", C.c_int32), ("out2", C.c_void_p), ("n_cls", C.c_int32)]
+                ("res_relu", C.c_int32), ("grouped", C.c_int32), ("out2", C.c_void_p), ("n_cls", C.c_int32),
+                ("n_groups", C.c_int32), ("group_end", C.c_int32 * HN_MAX_GROUPS), ("group_scale", C.c_void_p),
+                ("group_shift", C.c_void_p), ("group_addr", C.c_int32), ("group_hw", C.c_int32 * HN_MAX_GROUPS),
+                ("group_out_base", C.c_int64 * HN_MAX_GROUPS)]
 
 
 class StemDesc(C.Structure):
@@ -52,6 +56,10 @@ class StemDesc(C.Structure):
 class NodeDesc(C.Structure):
     _fields_ = [("n_in", C.c_int32), ("in_", View * 3), ("mode", C.c_int32 * 3), ("w", C.c_float * 3),
                 ("swish", C.c_int32), ("dw", C.c_void_p), ("out", View)]
+
+
+class DwMultiDesc(C.Structure):
+    _fields_ = [("n", C.c_int32), ("in_", View * HN_MAX_GROUPS), ("out", View * HN_MAX_GROUPS), ("dw", C.c_void_p)]
 
 
 class PoolDesc(C.Structure):
@@ -95,6 +103,7 @@ SYMBOLS = {
     "hn_conv_fwd": (C.c_int, [C.POINTER(ConvDesc), _P]),
     "hn_stem_fwd": (C.c_int, [C.POINTER(StemDesc), _P]),
     "hn_node_fwd": (C.c_int, [C.POINTER(NodeDesc), _P]),
+    "hn_dw_multi_fwd": (C.c_int, [C.POINTER(DwMultiDesc), _P]),
     "hn_pool_fwd": (C.c_int, [C.POINTER(PoolDesc), _P]),
     "hn_lanefuse_fwd": (C.c_int, [C.POINTER(LaneFuseDesc), _P]),
     "hn_se_pool_fwd": (C.c_int, [C.POINTER(SePoolDesc), _P]),
@@ -110,6 +119,7 @@ SYMBOLS = {
     "hn_plan_add_conv": (C.c_int, [_P, C.POINTER(ConvDesc)]),
     "hn_plan_add_stem": (C.c_int, [_P, C.POINTER(StemDesc)]),
     "hn_plan_add_node": (C.c_int, [_P, C.POINTER(NodeDesc)]),
+    "hn_plan_add_dw_multi": (C.c_int, [_P, C.POINTER(DwMultiDesc)]),
     "hn_plan_add_pool": (C.c_int, [_P, C.POINTER(PoolDesc)]),
     "hn_plan_add_lanefuse": (C.c_int, [_P, C.POINTER(LaneFuseDesc)]),
     "hn_plan_add_se_pool": (C.c_int, [_P, C.POINTER(SePoolDesc)]),

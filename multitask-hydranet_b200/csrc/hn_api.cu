@@ -27,13 +27,14 @@ extern "C" int hn_device_sm_count(void) {
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
-enum OpKind { OP_CONV, OP_STEM, OP_NODE, OP_POOL, OP_LANEFUSE, OP_SE_POOL, OP_SE_SCALE, OP_DET, OP_LANE };
+enum OpKind { OP_CONV, OP_STEM, OP_NODE, OP_DW_MULTI, OP_POOL, OP_LANEFUSE, OP_SE_POOL, OP_SE_SCALE, OP_DET, OP_LANE };
 
 struct PlanOp {
     OpKind kind;
     ConvLaunch conv;  // OP_CONV (tensor maps pre-encoded)
     hn_stem_desc stem;
     hn_node_desc node;
+    hn_dw_multi_desc dw_multi;
     hn_pool_desc pool;
     hn_lanefuse_desc lanefuse;
     hn_se_pool_desc se_pool;
@@ -75,6 +76,7 @@ extern "C" int hn_plan_size(const hn_plan* p) { return p ? (int)p->ops.size() : 
     }
 PLAN_ADD(stem, OP_STEM, stem, hn_stem_desc)
 PLAN_ADD(node, OP_NODE, node, hn_node_desc)
+PLAN_ADD(dw_multi, OP_DW_MULTI, dw_multi, hn_dw_multi_desc)
 PLAN_ADD(pool, OP_POOL, pool, hn_pool_desc)
 PLAN_ADD(lanefuse, OP_LANEFUSE, lanefuse, hn_lanefuse_desc)
 PLAN_ADD(se_pool, OP_SE_POOL, se_pool, hn_se_pool_desc)
@@ -121,6 +123,7 @@ extern "C" int hn_plan_run_range(hn_plan* p, int first, int last, void* stream) 
             case OP_CONV: rc = hn_conv_launch(&o->conv, s); break;
             case OP_STEM: rc = hn_stem_fwd(&o->stem, stream); break;
             case OP_NODE: rc = hn_node_fwd(&o->node, stream); break;
+            case OP_DW_MULTI: rc = hn_dw_multi_fwd(&o->dw_multi, stream); break;
             case OP_POOL: rc = hn_pool_fwd(&o->pool, stream); break;
             case OP_LANEFUSE: rc = hn_lanefuse_fwd(&o->lanefuse, stream); break;
             case OP_SE_POOL: rc = hn_se_pool_fwd(&o->se_pool, stream); break;

@@ -99,13 +99,18 @@ static constexpr int kNoCoord = -2147483647;
 // `stage_row`: this thread's 128-byte row of the shared-memory staging tile (nullptr = direct global stores);
 // 16-byte chunk j of the row lives at chunk (j ^ (row & 7)) -- the 128B swizzle the output tensor map expects.
 template <int NC>
-__device__ __forceinline__ void epi_chunk_std(const ConvParams& p, const EpiRow& e, const float* s_bias, int c, int n0,
-                                              uint32_t (&v)[NC], uint8_t* stage_row, int row) {
+__device__ __forceinline__ void epi_chunk_std(const ConvParams& p, const EpiRow& e, const float* s_bias, const float* s_scale,
+                                              int c, int n0, uint32_t (&v)[NC], uint8_t* stage_row, int row) {
     const int n = n0 + c;
     if (!e.valid || n >= p.cout) return;
     float f[NC];
+    if (s_scale) {
 #pragma unroll
-    for (int j = 0; j < NC; ++j) f[j] = __uint_as_float(v[j]) + s_bias[c + j];
+        for (int j = 0; j < NC; ++j) f[j] = fmaf(__uint_as_float(v[j]), s_scale[c + j], s_bias[c + j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) f[j] = __uint_as_float(v[j]) + s_bias[c + j];
+    }
     apply_act<NC>(f, p.act);
     if (p.out_fp32) {
         float* outf = reinterpret_cast<float*>(p.out) + e.off0;
@@ -211,7 +216,9 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
     uint64_t* bar_acc_full = bar_empty + stages;   // [2]
     uint64_t* bar_acc_empty = bar_acc_full + 2;    // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
-    float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);  // [2][BN]
+    // per accumulator: [BN] bias, or with row groups [n_groups][BN] shift followed by [n_groups][BN] scale
+    float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
+    const int bias_slots = p.n_groups > 0 ? 2 * p.n_groups : 1;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -325,18 +332,43 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
         int ntile = 0, st_count = 0;
         for (int t = t_first; t < total_tiles; t += t_step, ++ntile) {
             const TileOrigin o = tile_origin(p, t, rank);
-            float* bias_s = s_bias + a * BN;
-            for (int i = et; i < BN; i += kEpiThreads) bias_s[i] = p.bias ? p.bias[o.n0 + i] : 0.0f;
+            float* bias_s = s_bias + a * bias_slots * BN;
+            const float* scale_s = nullptr;
+            if (p.n_groups > 0 && p.group_shift) {
+                for (int i = et; i < p.n_groups * BN; i += kEpiThreads) {
+                    const int gi = i / BN, ci = i - gi * BN;
+                    bias_s[i] = p.group_shift[(long long)gi * p.gstride + o.n0 + ci];
+                    bias_s[p.n_groups * BN + i] = p.group_scale ? p.group_scale[(long long)gi * p.gstride + o.n0 + ci] : 1.0f;
+                }
+            } else {
+                for (int i = et; i < BN; i += kEpiThreads) bias_s[i] = p.bias ? p.bias[o.n0 + i] : 0.0f;
+            }
             EpiRow e;
             e.ym1 = e.ym2 = e.xm1 = e.xm2 = kNoCoord;
             e.Y = e.X = 0;
             if (p.flat) {
                 long long m = (long long)o.x0 + row;
                 e.valid = m < p.flat_m;
-                e.n_i = (int)(m / p.flat_hw);
-                long long pix = m - (long long)e.n_i * p.flat_hw;
-                e.off0 = (long long)e.n_i * p.osn + pix * p.osx;
-                e.roff = (long long)e.n_i * p.rsn + pix * p.rsx;
+                int g = 0;
+                if (p.n_groups > 0) {
+                    while (g < p.n_groups - 1 && m >= p.group_end[g]) ++g;
+                    if (p.group_shift) {  // this row's shift / scale vectors
+                        bias_s += g * BN;
+                        scale_s = bias_s + p.n_groups * BN;
+                    }
+                }
+                if (p.n_groups > 0 && p.group_addr) {
+                    const long long ml = m - (g > 0 ? p.group_end[g - 1] : 0);
+                    e.n_i = (int)(ml / p.group_hw[g]);
+                    const long long pix = ml - (long long)e.n_i * p.group_hw[g];
+                    e.off0 = (long long)e.n_i * p.osn + p.group_out_base[g] + pix * p.osx;
+                    e.roff = 0;
+                } else {
+                    e.n_i = (int)(m / p.flat_hw);
+                    long long pix = m - (long long)e.n_i * p.flat_hw;
+                    e.off0 = (long long)e.n_i * p.osn + pix * p.osx;
+                    e.roff = (long long)e.n_i * p.rsn + pix * p.rsx;
+                }
             } else {
                 int ty = row / p.TW, tx = row - ty * p.TW;
                 int y = o.y0 + ty, x = o.x0 + tx;
@@ -387,12 +419,12 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
                             uint32_t v[32];
                             hn_tmem_ld32(t_row + cc, v);
                             hn_tmem_ld_wait();
-                            epi_chunk_std<32>(p, e, bias_s, cc, o.n0, v, stage_row, row);
+                            epi_chunk_std<32>(p, e, bias_s, scale_s, cc, o.n0, v, stage_row, row);
                         } else if (cc + 16 <= BN) {
                             uint32_t v[16];
                             hn_tmem_ld16(t_row + cc, v);
                             hn_tmem_ld_wait();
-                            epi_chunk_std<16>(p, e, bias_s, cc, o.n0, v, stage_row, row);
+                            epi_chunk_std<16>(p, e, bias_s, scale_s, cc, o.n0, v, stage_row, row);
                         }
                     }
                     hn_fence_proxy_async();
@@ -409,13 +441,13 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
                     uint32_t v[32];
                     hn_tmem_ld32(t_row + c, v);
                     hn_tmem_ld_wait();
-                    epi_chunk_std<32>(p, e, bias_s, c, o.n0, v, nullptr, row);
+                    epi_chunk_std<32>(p, e, bias_s, scale_s, c, o.n0, v, nullptr, row);
                 }
                 if (c < BN) {
                     uint32_t v[16];
                     hn_tmem_ld16(t_row + c, v);
                     hn_tmem_ld_wait();
-                    epi_chunk_std<16>(p, e, bias_s, c, o.n0, v, nullptr, row);
+                    epi_chunk_std<16>(p, e, bias_s, scale_s, c, o.n0, v, nullptr, row);
                 }
             }
             // all TMEM reads of this accumulator are complete: hand it back to the MMA issuer
@@ -563,6 +595,17 @@ int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L) {
     HN_REQUIRE(!d->grouped || d->bn == 64, "grouped conv needs bn == 64");
     p.out2 = reinterpret_cast<uint8_t*>(d->out2);
     p.n_cls = d->n_cls;
+    HN_REQUIRE(d->n_groups >= 0 && d->n_groups <= HN_MAX_GROUPS, "n_groups=%d out of range", d->n_groups);
+    HN_REQUIRE(d->n_groups == 0 || d->flat, "row groups need flat mode");
+    p.n_groups = d->n_groups;
+    p.group_addr = d->group_addr;
+    p.group_scale = d->group_scale;
+    p.group_shift = d->group_shift;
+    for (int g = 0; g < d->n_groups; ++g) {
+        p.group_end[g] = d->group_end[g];
+        p.group_hw[g] = d->group_hw[g] > 0 ? d->group_hw[g] : 1;
+        p.group_out_base[g] = d->group_out_base[g];
+    }
     int m_tiles;
     if (d->flat) {
         HN_REQUIRE(d->flat_hw > 0, "flat conv needs flat_hw");
@@ -591,9 +634,10 @@ int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L) {
     p.n_tiles = n_tiles;
     // CTA pairs (cta_group::2, M = 256): each SM stages and reads only half of the weight tile.  The 1-CTA main
     // loop of a wide tile is bound by shared-memory bandwidth (TMA fill + operand reads ~ 96 KB per 64-deep K step);
-    // the pair cuts that to 64 KB.  Used for N tiles >= 128 when there are at least two M tiles.
+    // the pair cuts that to 64 KB.  Used for N tiles >= 192 when there are at least two M tiles (narrower tiles do
+    // better as two independent CTAs per SM).
     int cs = (g_conv_cluster > 0) ? g_conv_cluster : 2;
-    if (cs != 2 || d->bn < 128 || d->bn % 32 != 0 || m_tiles < 2 || d->epi != HN_EPI_STD) cs = 1;
+    if (cs != 2 || d->bn < 192 || d->bn % 32 != 0 || m_tiles < 2 || d->epi != HN_EPI_STD) cs = 1;
     p.cluster = cs;
     p.m_groups = hn_cdiv(m_tiles, cs);
     int stages = d->stages;
@@ -608,11 +652,14 @@ int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L) {
         p.stages = stages;
     }
     const int b_rows_cta = cs == 2 ? d->bn / 2 : d->bn;
-    const size_t base_smem = 1024 + (size_t)stages * (kATileBytes + b_rows_cta * 128) + (2 * stages + 4) * 8 + 16 + 2 * d->bn * 4 + 64;
+    p.gstride = n_tiles * d->bn;
+    const int bias_slots = d->n_groups > 0 ? 2 * d->n_groups : 1;
+    const size_t base_smem = 1024 + (size_t)stages * (kATileBytes + b_rows_cta * 128) + (2 * stages + 4) * 8 + 16 +
+                             2 * (size_t)bias_slots * d->bn * 4 + 64;
     // bf16 outputs leave through shared memory + TMA store (coalesced, clipped by the tensor map) when the
     // 64-channel slabs of an N tile never spill into the next tile's channels
     p.n_staging = 0;
-    bool tma_out = d->epi == HN_EPI_STD && !d->out_fp32 && (n_tiles == 1 || d->bn % 64 == 0) &&
+    bool tma_out = d->epi == HN_EPI_STD && !d->out_fp32 && !d->group_addr && (n_tiles == 1 || d->bn % 64 == 0) &&
                    (!d->flat || d->out_stride_n == (int64_t)d->flat_hw * d->out_stride_x);
     if (tma_out && base_smem + kATileBytes <= 227 * 1024) {
         p.n_staging = (base_smem + 2 * kATileBytes <= 227 * 1024) ? 2 : 1;

@@ -273,6 +273,80 @@ __global__ void __launch_bounds__(256) hn_dw_kernel(View in, View out, const flo
     store8(const_cast<bf16*>(vptr(out, n, y, x, c)), acc);
 }
 
+// the same over several (input, output) pairs sharing the weights: one launch for all pyramid levels
+struct DwMultiParams {
+    int n;
+    View in[HN_MAX_GROUPS], out[HN_MAX_GROUPS];
+    long long end[HN_MAX_GROUPS];  // exclusive prefix of work items
+    const float* dw;
+};
+__global__ void __launch_bounds__(256) hn_dw_multi_kernel(const __grid_constant__ DwMultiParams p) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.end[p.n - 1]) return;
+    int g = 0;
+    while (g < p.n - 1 && idx >= p.end[g]) ++g;
+    if (g > 0) idx -= p.end[g - 1];
+    const View& in = p.in[g];
+    const View& out = p.out[g];
+    const int C = out.C, CV = C >> 3;
+    const int cv = (int)(idx % CV);
+    long long t = idx / CV;
+    const int x = (int)(t % out.W);
+    t /= out.W;
+    const int y = (int)(t % out.H);
+    const int n = (int)(t / out.H);
+    const int c = cv * 8;
+    uint4 raw[9];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int iy = y + ky - 1, ix = x + kx - 1;
+            raw[ky * 3 + kx] = (iy >= 0 && iy < out.H && ix >= 0 && ix < out.W)
+                                   ? *reinterpret_cast<const uint4*>(vptr(in, n, iy, ix, c))
+                                   : make_uint4(0, 0, 0, 0);
+        }
+    }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const float4* wv = reinterpret_cast<const float4*>(p.dw + k * C + c);
+        const float4 w0 = __ldg(wv), w1 = __ldg(wv + 1);
+        const float2 a = hn_unpack_bf16x2(raw[k].x), b = hn_unpack_bf16x2(raw[k].y), cc = hn_unpack_bf16x2(raw[k].z),
+                     d = hn_unpack_bf16x2(raw[k].w);
+        acc[0] = fmaf(a.x, w0.x, acc[0]); acc[1] = fmaf(a.y, w0.y, acc[1]);
+        acc[2] = fmaf(b.x, w0.z, acc[2]); acc[3] = fmaf(b.y, w0.w, acc[3]);
+        acc[4] = fmaf(cc.x, w1.x, acc[4]); acc[5] = fmaf(cc.y, w1.y, acc[5]);
+        acc[6] = fmaf(d.x, w1.z, acc[6]); acc[7] = fmaf(d.y, w1.w, acc[7]);
+    }
+    store8(const_cast<bf16*>(vptr(out, n, y, x, c)), acc);
+}
+
+extern "C" int hn_dw_multi_fwd(const hn_dw_multi_desc* d, void* stream) {
+    HN_REQUIRE(d && d->n >= 1 && d->n <= HN_MAX_GROUPS && d->dw, "dw_multi: bad descriptor");
+    DwMultiParams p;
+    memset(&p, 0, sizeof(p));
+    p.n = d->n;
+    p.dw = d->dw;
+    long long total = 0;
+    for (int i = 0; i < d->n; ++i) {
+        if (int rc = check_view(d->in[i], "dw_multi.in")) return rc;
+        if (int rc = check_view(d->out[i], "dw_multi.out")) return rc;
+        HN_REQUIRE(d->in[i].N == d->out[i].N && d->in[i].H == d->out[i].H && d->in[i].W == d->out[i].W &&
+                       d->in[i].C == d->out[i].C && d->in[i].C == d->in[0].C,
+                   "dw_multi: pair %d shape mismatch", i);
+        p.in[i] = to_view(d->in[i]);
+        p.out[i] = to_view(d->out[i]);
+        total += (long long)d->out[i].N * d->out[i].H * d->out[i].W * (d->out[i].C / 8);
+        p.end[i] = total;
+    }
+    hn_dw_multi_kernel<<<hn_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
 extern "C" int hn_node_fwd(const hn_node_desc* d, void* stream) {
     HN_REQUIRE(d && d->n_in >= 1 && d->n_in <= 3 && d->dw, "node: bad descriptor");
     if (int rc = check_view(d->out, "node.out")) return rc;

@@ -25,6 +25,12 @@ struct alignas(64) ConvParams {
     int res_relu, grouped;
     uint8_t* out2;
     int n_cls;
+    int n_groups, group_addr;
+    int group_end[HN_MAX_GROUPS], group_hw[HN_MAX_GROUPS];
+    long long group_out_base[HN_MAX_GROUPS];
+    const float* group_scale;
+    const float* group_shift;
+    int gstride;  // floats between consecutive groups in group_scale / group_shift
     hn_tap taps[HN_MAX_TAPS];
 };
 

@@ -114,6 +114,13 @@ class ConvSpec:
         self.n_cls = 0
         self.macs = 0          # algorithmic multiply-accumulates of the reference layer(s) this op computes
         self.group = ""        # subsystem tag for per-op timing
+        # row groups (flat mode): stacked problems sharing the weights
+        self.group_end = []    # exclusive row end per group
+        self.group_scale = None  # fp32 [n_groups, rows] or None
+        self.group_shift = None
+        self.group_addr = 0
+        self.group_hw = []
+        self.group_out_base = []
 
     def to_desc(self):
         d = nv.ConvDesc()
@@ -143,6 +150,16 @@ class ConvSpec:
         d.res_relu, d.grouped = self.res_relu, self.grouped
         d.out2 = self.out2.data_ptr() if self.out2 is not None else None
         d.n_cls = self.n_cls
+        d.n_groups = len(self.group_end)
+        for i, e in enumerate(self.group_end):
+            d.group_end[i] = e
+        if self.group_shift is not None:
+            assert self.group_shift.shape == (len(self.group_end), self.weight.shape[0]), self.name
+            d.group_shift = self.group_shift.data_ptr()
+            d.group_scale = self.group_scale.data_ptr() if self.group_scale is not None else None
+        d.group_addr = self.group_addr
+        for i, (hw, base) in enumerate(zip(self.group_hw, self.group_out_base)):
+            d.group_hw[i], d.group_out_base[i] = hw, base
         return d
 
     def add_to(self, plan):
@@ -188,6 +205,25 @@ class NodeSpec:
 
     def add_to(self, plan):
         nv.check(nv.lib.hn_plan_add_node(plan, self.to_desc()))
+
+
+class DwMultiSpec:
+    kind, launches = "dw_multi", 1
+
+    def __init__(self, name, ins, outs, dw, group):
+        self.name, self.ins, self.outs, self.dw, self.group = name, ins, outs, dw, group
+        self.macs = sum(o.N * o.H * o.W * o.C * 9 for o in outs)
+
+    def to_desc(self):
+        d = nv.DwMultiDesc()
+        d.n = len(self.ins)
+        for i, (a, b) in enumerate(zip(self.ins, self.outs)):
+            d.in_[i], d.out[i] = a.to_c(), b.to_c()
+        d.dw = self.dw.data_ptr()
+        return d
+
+    def add_to(self, plan):
+        nv.check(nv.lib.hn_plan_add_dw_multi(plan, self.to_desc()))
 
 
 class PoolSpec:
@@ -680,24 +716,82 @@ class Builder:
 
     # -- detection head --
     def det_head(self, levels):
+        """Both towers run every layer ONCE over all pyramid levels: the levels' pixels are stacked into one
+        [sum_l B*H_l*W_l, C] matrix (level-major), the shared depthwise / pointwise weights are applied in one
+        launch each, and the per-level BatchNorm (detection.py:20-24,30-37) becomes a per-row-group scale / shift
+        in the GEMM epilogue.  The header GEMMs scatter their rows straight into the reference's
+        [B, sum_l H_l*W_l*9, k] layout."""
         dh = self.m.detectheader
         na, ncls = dh.num_anchors, dh.num_classes
-        total = sum(l.H * l.W for l in levels) * na
-        reg = torch.zeros((self.B, total, 4), dtype=torch.float32, device=self.dev)
-        cls = torch.zeros((self.B, total, ncls), dtype=torch.float32, device=self.dev)
-        row0 = 0
-        for li, lv in enumerate(levels):
-            for tname, tower, out_t, k, act in (("reg", dh.regressor, reg, 4, nv.ACT_NONE),
-                                                ("cls", dh.classifier, cls, ncls, nv.ACT_SIGMOID)):
-                cur = lv
-                for i in range(tower.num_layers):
-                    ob = self.buf(lv.H, lv.W, lv.C)
-                    self.sepconv("det.%s.l%d.%d" % (tname, li, i), [cur.interior()], [nv.IN_SAME], [1.0], 0, tower.conv_list[i],
-                                 tower.bn_list[li][i], ob, nv.ACT_SWISH, "detect", lv.H, lv.W)
-                    cur = ob
-                self.sepconv("det.%s.l%d.hdr" % (tname, li), [cur.interior()], [nv.IN_SAME], [1.0], 0, tower.header, None, None,
-                             act, "detect", lv.H, lv.W, out_fp32=(out_t, row0, k))
-            row0 += lv.H * lv.W * na
+        B, C = self.B, levels[0].C
+        hws = [l.H * l.W for l in levels]
+        total = sum(hws) * na
+        reg = torch.zeros((B, total, 4), dtype=torch.float32, device=self.dev)
+        cls = torch.zeros((B, total, ncls), dtype=torch.float32, device=self.dev)
+        ends, acc = [], 0
+        for hw in hws:
+            acc += B * hw
+            ends.append(acc)
+        R = acc
+
+        def stacked():
+            t = torch.zeros((R, C), dtype=self.dt, device=self.dev)
+            views, r0 = [], 0
+            for l in levels:
+                views.append(V(t, r0 * C, B, l.H, l.W, C, l.H * l.W * C, l.W * C, C))
+                r0 += B * l.H * l.W
+            return t, views
+
+        def rows_view(t):
+            return V(t, 0, 1, 1, R, C, 0, 0, C)
+
+        for tname, tower, out_t, k, act in (("reg", dh.regressor, reg, 4, nv.ACT_NONE), ("cls", dh.classifier, cls, ncls, nv.ACT_SIGMOID)):
+            cur = [l.interior() for l in levels]
+            for i in range(tower.num_layers):
+                sep = tower.conv_list[i]
+                dwt, dwv = stacked()
+                self.ops.append(DwMultiSpec("det.%s.%d.dw" % (tname, i), cur, dwv,
+                                            self.f32(sep.depthwise_conv.conv.weight.reshape(C, 9).t()), "detect"))
+                pw = sep.pointwise_conv.conv
+                ot, ov = stacked()
+                cs = ConvSpec("det.%s.%d.pw" % (tname, i))
+                cs.group, cs.act = "detect", nv.ACT_SWISH
+                cs.flat, cs.flat_hw = 1, R
+                cs.src = [rows_view(dwt)]
+                cs.out_t, cs.out_off, cs.out_strides = ot, 0, (R * C, 0, C)
+                cs.macs = R * C * C
+                cs.group_end = list(ends)
+                self._finish(cs, [(0, 0, 0, pw.weight.detach().float().reshape(C, C))], C, torch.zeros(C))
+                scales, shifts = [], []
+                for li in range(len(levels)):
+                    bn = tower.bn_list[li][i]
+                    sc = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+                    sh = (pw.bias.detach().float() - bn.running_mean.detach().float()) * sc + bn.bias.detach().float()
+                    scales.append(pad_bias(sc.to(self.dev), C, cs.bn))
+                    shifts.append(pad_bias(sh.to(self.dev), C, cs.bn))
+                cs.group_scale, cs.group_shift = torch.stack(scales).contiguous(), torch.stack(shifts).contiguous()
+                cur = ov
+            sep = tower.header
+            dwt, dwv = stacked()
+            self.ops.append(DwMultiSpec("det.%s.hdr.dw" % tname, cur, dwv,
+                                        self.f32(sep.depthwise_conv.conv.weight.reshape(C, 9).t()), "detect"))
+            pw = sep.pointwise_conv.conv
+            cout = pw.weight.shape[0]
+            cs = ConvSpec("det.%s.hdr.pw" % tname)
+            cs.group, cs.act = "detect", act
+            cs.flat, cs.flat_hw = 1, R
+            cs.src = [rows_view(dwt)]
+            cs.out_t, cs.out_off, cs.out_fp32 = out_t, 0, 1
+            cs.out_strides = (total * k, 0, cout)
+            cs.macs = R * cout * C
+            cs.group_end, cs.group_addr = list(ends), 1
+            cs.group_hw = list(hws)
+            bases, a0 = [], 0
+            for hw in hws:
+                bases.append(a0 * k)
+                a0 += hw * na
+            cs.group_out_base = bases
+            self._finish(cs, [(0, 0, 0, pw.weight.detach().float().reshape(cout, C))], cout, pw.bias.detach().float())
         self.out["regression"], self.out["classification"] = reg, cls
 
     # -- lane head --

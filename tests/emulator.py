@@ -67,7 +67,16 @@ def run_conv(cs):
         else:
             a = _gather(cs.src[s], [y + dy for y in ys], [x + dx for x in xs], c0)
             acc += a @ wk.t()
-    acc = acc + bias
+    if cs.group_shift is not None:  # per-row-group affine instead of the plain bias (flat mode)
+        M = W
+        starts = [0] + list(cs.group_end[:-1])
+        gidx = torch.zeros(M, dtype=torch.long)
+        for g, (a0, a1) in enumerate(zip(starts, cs.group_end)):
+            gidx[a0:a1] = g
+        sc = cs.group_scale.float()[gidx] if cs.group_scale is not None else 1.0
+        acc = (acc[0, 0] * sc + cs.group_shift.float()[gidx])[None, None]
+    else:
+        acc = acc + bias
     out_flat = cs.out_t.view(-1)
     if cs.epi == nv.EPI_SEGOUT:
         N = acc.shape[0]
@@ -87,6 +96,12 @@ def run_conv(cs):
         m = torch.arange(M)
         n_i, pix = m // hw, m % hw
         off = cs.out_off + n_i * sn + pix * sx
+        if cs.group_addr:
+            starts = [0] + list(cs.group_end[:-1])
+            off = torch.zeros(M, dtype=torch.long)
+            for g, (a0, a1) in enumerate(zip(starts, cs.group_end)):
+                ml = torch.arange(a1 - a0)
+                off[a0:a1] = cs.out_off + (ml // cs.group_hw[g]) * sn + cs.group_out_base[g] + (ml % cs.group_hw[g]) * sx
         val = acc[0, 0]
         if cs.res is not None:
             r = cs.res
@@ -167,6 +182,15 @@ def run_node(ns):
     o.torch_view().copy_(y.permute(0, 2, 3, 1))
 
 
+def run_dw_multi(ds):
+    for vin, vout in zip(ds.ins, ds.outs):
+        C = vout.C
+        t = vin.torch_view().float().permute(0, 3, 1, 2)
+        w = ds.dw.t().reshape(C, 1, 3, 3)
+        y = F.conv2d(F.pad(t, [1, 1, 1, 1]), w, None, 1, 0, 1, C)
+        vout.torch_view().copy_(y.permute(0, 2, 3, 1))
+
+
 def run_pool(ps):
     t = ps.vin.torch_view().float().permute(0, 3, 1, 2)
     y = F.max_pool2d(F.pad(t, [0, 1, 0, 1]), 3, 2) if ps.mode == nv.POOL_ZERO_RB else F.max_pool2d(t, 3, 2, 1)
@@ -200,7 +224,7 @@ def run_stem(st):
     st.out.torch_view().copy_(y.permute(0, 2, 3, 1))
 
 
-RUNNERS = {"conv": run_conv, "node": run_node, "pool": run_pool, "lanefuse": run_lanefuse, "se_pool": run_se_pool, "se_scale": run_se_scale, "stem": run_stem}
+RUNNERS = {"conv": run_conv, "node": run_node, "dw_multi": run_dw_multi, "pool": run_pool, "lanefuse": run_lanefuse, "se_pool": run_se_pool, "se_scale": run_se_scale, "stem": run_stem}
 
 
 def run_ops(ops):

@@ -14,6 +14,8 @@ def _tensors_in(op):
         return ts
     if op.kind == "node":
         return [v.t for v in op.ins]
+    if op.kind == "dw_multi":
+        return [v.t for v in op.ins]
     if op.kind == "pool":
         return [op.vin.t]
     if op.kind == "lanefuse":
@@ -32,6 +34,8 @@ def _tensors_out(op):
         return [op.out_t] + ([op.out2] if op.out2 is not None else [])
     if op.kind == "node":
         return [op.out.t]
+    if op.kind == "dw_multi":
+        return [op.outs[0].t]
     if op.kind == "pool":
         return [op.vout.t]
     if op.kind == "lanefuse":

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_struct_layouts_match_the_c_compiler():
     structs = {"hn_view": nv.View, "hn_tap": nv.Tap, "hn_conv_desc": nv.ConvDesc, "hn_stem_desc": nv.StemDesc,
-               "hn_node_desc": nv.NodeDesc, "hn_pool_desc": nv.PoolDesc, "hn_lanefuse_desc": nv.LaneFuseDesc,
+               "hn_node_desc": nv.NodeDesc, "hn_dw_multi_desc": nv.DwMultiDesc, "hn_pool_desc": nv.PoolDesc, "hn_lanefuse_desc": nv.LaneFuseDesc,
                "hn_se_pool_desc": nv.SePoolDesc, "hn_se_scale_desc": nv.SeScaleDesc, "hn_det_desc": nv.DetDesc, "hn_lane_desc": nv.LaneDesc}
     prog = '#include <stdio.h>\n#include <stddef.h>\n#include "hydranet_b200.h"\nint main(){\n'
     for c in structs:
