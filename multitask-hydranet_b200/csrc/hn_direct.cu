@@ -50,12 +50,12 @@ __global__ void __launch_bounds__(128) hn_stem_kernel(const float* __restrict__ 
     if (threadIdx.x < 32) sb[threadIdx.x] = b[threadIdx.x];
     __syncthreads();
     const int OH = out.H, OW = out.W;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)N * OH * OW;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned total = (unsigned)N * OH * OW;
     if (idx >= total) return;
-    int ox = (int)(idx % OW);
-    int oy = (int)((idx / OW) % OH);
-    int n = (int)(idx / ((long long)OW * OH));
+    int ox = (int)(idx % (unsigned)OW);
+    int oy = (int)((idx / (unsigned)OW) % (unsigned)OH);
+    int n = (int)(idx / ((unsigned)OW * OH));
     float acc[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) acc[c] = sb[c];
@@ -98,6 +98,7 @@ extern "C" int hn_stem_fwd(const hn_stem_desc* d, void* stream) {
                "stem: output view %dx%dx%dx%d does not match input %dx3x%dx%d", d->out.N, d->out.H, d->out.W, d->out.C, d->N,
                d->H, d->W);
     long long total = (long long)d->N * d->out.H * d->out.W;
+    HN_REQUIRE(total < 0x7fffffffLL, "stem: too many output pixels for one launch");
     hn_stem_kernel<<<hn_cdiv(total, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d->x, d->N, d->H, d->W, d->w,
                                                                                           d->b, to_view(d->out));
     HN_CHECK_CUDA(cudaGetLastError());
@@ -234,16 +235,17 @@ __global__ void __launch_bounds__(256) hn_node_kernel(const __grid_constant__ No
 // all nine 16-byte loads issued up front (neighbouring threads share them through L1), no shared memory, no
 // barrier: the op is latency-bound, so what matters is loads in flight per SM.
 __global__ void __launch_bounds__(256) hn_dw_kernel(View in, View out, const float* __restrict__ dw) {
+    // 32-bit index arithmetic throughout: 64-bit div/mod costs more than the nine loads
     const int C = out.C, CV = C >> 3;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)out.N * out.H * out.W * CV;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned total = (unsigned)out.N * out.H * out.W * CV;
     if (idx >= total) return;
-    const int cv = (int)(idx % CV);
-    long long t = idx / CV;
-    const int x = (int)(t % out.W);
-    t /= out.W;
-    const int y = (int)(t % out.H);
-    const int n = (int)(t / out.H);
+    const int cv = (int)(idx % (unsigned)CV);
+    unsigned t = idx / (unsigned)CV;
+    const int x = (int)(t % (unsigned)out.W);
+    t /= (unsigned)out.W;
+    const int y = (int)(t % (unsigned)out.H);
+    const int n = (int)(t / (unsigned)out.H);
     const int c = cv * 8;
     uint4 raw[9];
 #pragma unroll
@@ -277,11 +279,11 @@ __global__ void __launch_bounds__(256) hn_dw_kernel(View in, View out, const flo
 struct DwMultiParams {
     int n;
     View in[HN_MAX_GROUPS], out[HN_MAX_GROUPS];
-    long long end[HN_MAX_GROUPS];  // exclusive prefix of work items
+    unsigned end[HN_MAX_GROUPS];  // exclusive prefix of work items
     const float* dw;
 };
 __global__ void __launch_bounds__(256) hn_dw_multi_kernel(const __grid_constant__ DwMultiParams p) {
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.end[p.n - 1]) return;
     int g = 0;
     while (g < p.n - 1 && idx >= p.end[g]) ++g;
@@ -289,12 +291,12 @@ __global__ void __launch_bounds__(256) hn_dw_multi_kernel(const __grid_constant_
     const View& in = p.in[g];
     const View& out = p.out[g];
     const int C = out.C, CV = C >> 3;
-    const int cv = (int)(idx % CV);
-    long long t = idx / CV;
-    const int x = (int)(t % out.W);
-    t /= out.W;
-    const int y = (int)(t % out.H);
-    const int n = (int)(t / out.H);
+    const int cv = (int)(idx % (unsigned)CV);
+    unsigned t = idx / (unsigned)CV;
+    const int x = (int)(t % (unsigned)out.W);
+    t /= (unsigned)out.W;
+    const int y = (int)(t % (unsigned)out.H);
+    const int n = (int)(t / (unsigned)out.H);
     const int c = cv * 8;
     uint4 raw[9];
 #pragma unroll
@@ -340,7 +342,8 @@ extern "C" int hn_dw_multi_fwd(const hn_dw_multi_desc* d, void* stream) {
         p.in[i] = to_view(d->in[i]);
         p.out[i] = to_view(d->out[i]);
         total += (long long)d->out[i].N * d->out[i].H * d->out[i].W * (d->out[i].C / 8);
-        p.end[i] = total;
+        HN_REQUIRE(total < 0x7fffffffLL, "dw_multi: too many work items");
+        p.end[i] = (unsigned)total;
     }
     hn_dw_multi_kernel<<<hn_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     HN_CHECK_CUDA(cudaGetLastError());
@@ -374,6 +377,7 @@ extern "C" int hn_node_fwd(const hn_node_desc* d, void* stream) {
     p.out = to_view(d->out);
     if (d->n_in == 1 && d->mode[0] == HN_IN_SAME && !d->swish && d->w[0] == 1.0f) {
         long long total = (long long)d->out.N * d->out.H * d->out.W * (d->out.C / 8);
+        HN_REQUIRE(total < 0x7fffffffLL, "node: too many work items for one launch");
         hn_dw_kernel<<<hn_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p.in[0], p.out, d->dw);
         HN_CHECK_CUDA(cudaGetLastError());
         return HN_OK;
@@ -414,15 +418,15 @@ __device__ __forceinline__ void pool_neginf(const View& v, int n, int y, int x, 
 
 __global__ void hn_pool_kernel(View in, View out, int mode) {
     const int CV = out.C >> 3;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)out.N * out.H * out.W * CV;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned total = (unsigned)out.N * out.H * out.W * CV;
     if (idx >= total) return;
-    int cv = (int)(idx % CV);
-    long long t = idx / CV;
-    int x = (int)(t % out.W);
-    t /= out.W;
-    int y = (int)(t % out.H);
-    int n = (int)(t / out.H);
+    int cv = (int)(idx % (unsigned)CV);
+    unsigned t = idx / (unsigned)CV;
+    int x = (int)(t % (unsigned)out.W);
+    t /= (unsigned)out.W;
+    int y = (int)(t % (unsigned)out.H);
+    int n = (int)(t / (unsigned)out.H);
     float f[8];
     if (mode == HN_POOL_ZERO_RB) node_fetch(in, HN_IN_POOL, n, y, x, cv * 8, f);
     else pool_neginf(in, n, y, x, cv * 8, f);
@@ -439,6 +443,7 @@ extern "C" int hn_pool_fwd(const hn_pool_desc* d, void* stream) {
     else
         HN_REQUIRE((d->in.H - 1) / 2 + 1 == d->out.H && (d->in.W - 1) / 2 + 1 == d->out.W, "pool: size mismatch");
     long long total = (long long)d->out.N * d->out.H * d->out.W * (d->out.C / 8);
+    HN_REQUIRE(total < 0x7fffffffLL, "pool: too many work items for one launch");
     hn_pool_kernel<<<hn_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(to_view(d->in), to_view(d->out),
                                                                                           d->mode);
     HN_CHECK_CUDA(cudaGetLastError());
@@ -455,17 +460,17 @@ struct LaneFuseParams {
 
 __global__ void hn_lanefuse_kernel(const __grid_constant__ LaneFuseParams p) {
     const int C = p.p3.C, CV = C >> 3;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)p.out.N * p.out.H * p.out.W * 4 * CV;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned total = (unsigned)p.out.N * p.out.H * p.out.W * 4 * CV;
     if (idx >= total) return;
-    int cv = (int)(idx % CV);
-    long long t = idx / CV;
-    int part = (int)(t % 4);
-    t /= 4;
-    int x = (int)(t % p.out.W);
-    t /= p.out.W;
-    int y = (int)(t % p.out.H);
-    int n = (int)(t / p.out.H);
+    int cv = (int)(idx % (unsigned)CV);
+    unsigned t = idx / (unsigned)CV;
+    int part = (int)(t % 4u);
+    t /= 4u;
+    int x = (int)(t % (unsigned)p.out.W);
+    t /= (unsigned)p.out.W;
+    int y = (int)(t % (unsigned)p.out.H);
+    int n = (int)(t / (unsigned)p.out.H);
     const int c = cv * 8;
     float f[8];
     if (p.stride == 32) {
@@ -521,6 +526,7 @@ extern "C" int hn_lanefuse_fwd(const hn_lanefuse_desc* d, void* stream) {
     p.p3 = to_view(d->p3); p.p4 = to_view(d->p4); p.p5 = to_view(d->p5); p.p6 = to_view(d->p6); p.out = to_view(d->out);
     p.stride = d->stride;
     long long total = (long long)d->out.N * d->out.H * d->out.W * 4 * (d->p3.C / 8);
+    HN_REQUIRE(total < 0x7fffffffLL, "lanefuse: too many work items for one launch");
     hn_lanefuse_kernel<<<hn_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
@@ -588,15 +594,15 @@ __global__ void __launch_bounds__(kSeThreads) hn_se_pool_kernel(View x, float* _
 
 __global__ void hn_se_scale_kernel(View x, const bf16* __restrict__ scale) {
     const int CV = x.C >> 3;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)x.N * x.H * x.W * CV;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned total = (unsigned)x.N * x.H * x.W * CV;
     if (idx >= total) return;
-    int cv = (int)(idx % CV);
-    long long t = idx / CV;
-    int xx = (int)(t % x.W);
-    t /= x.W;
-    int y = (int)(t % x.H);
-    int n = (int)(t / x.H);
+    int cv = (int)(idx % (unsigned)CV);
+    unsigned t = idx / (unsigned)CV;
+    int xx = (int)(t % (unsigned)x.W);
+    t /= (unsigned)x.W;
+    int y = (int)(t % (unsigned)x.H);
+    int n = (int)(t / (unsigned)x.H);
     bf16* p = const_cast<bf16*>(vptr(x, n, y, xx, cv * 8));
     float f[8], sc[8];
     load8(p, f);
@@ -626,6 +632,7 @@ extern "C" int hn_se_scale_fwd(const hn_se_scale_desc* d, void* stream) {
     HN_REQUIRE(d && d->scale, "se_scale: bad descriptor");
     if (int rc = check_view(d->x, "se_scale.x")) return rc;
     long long total = (long long)d->x.N * d->x.H * d->x.W * (d->x.C / 8);
+    HN_REQUIRE(total < 0x7fffffffLL, "se_scale: too many work items for one launch");
     hn_se_scale_kernel<<<hn_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         to_view(d->x), reinterpret_cast<const bf16*>(d->scale));
     HN_CHECK_CUDA(cudaGetLastError());

@@ -251,10 +251,11 @@ int hn_det_num_launches(const hn_det_desc*) { return 11 + 16; }  // 11 own kerne
 __global__ void hn_det_decode_kernel(const float* __restrict__ anchors, const float* __restrict__ reg,
                                      const float* __restrict__ cls, const float* __restrict__ pre_boxes, int N, int A,
                                      int ncls, float wmax, float hmax, float thr, DetWs ws) {
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = idx < (long long)N * A;
-    if (!valid) idx = (long long)N * A - 1;
-    int n = (int)(idx / A), a = (int)(idx - (long long)n * A);
+    unsigned uidx = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = uidx < (unsigned)N * (unsigned)A;
+    if (!valid) uidx = (unsigned)N * (unsigned)A - 1u;
+    const int n = (int)(uidx / (unsigned)A), a = (int)(uidx - (unsigned)n * (unsigned)A);
+    const long long idx = uidx;
     const float* c = cls + idx * ncls;
     float best = c[0];
     int bi = 0;
