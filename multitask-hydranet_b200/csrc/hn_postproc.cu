@@ -569,94 +569,87 @@ __global__ void hn_nms2_cells_kernel(DetWs ws, long long NA) {
     if (q == 0 || ws.ckey[q - 1] != ck) ws.cell_list[atomicAdd(ws.changed + 3, 1)] = (int)q;
 }
 
-// Conflict-graph construction, one warp per non-empty grid cell (lane = one candidate of the cell).  All candidates
-// of a cell share (a superset of) the same search window, so the window's boxes are staged once per warp in shared
-// memory, 32 at a time with coalesced loads, and every lane tests its candidate against them from there: no
-// global-memory latency in the inner loop.  Cells of one grid row are consecutive in cell order, hence every
-// window row is ONE contiguous index range.  Every conflicting pair is discovered once, from its smaller box: a
-// cell scans its own size level and the coarser ones, and the edge is recorded at the later box of the pair.
+// Conflict-graph construction, four lanes per candidate.  Cells of one grid row are consecutive in cell
+// order, so the members of the cells x_lo..x_hi of a window row form ONE contiguous index range that the
+// group strides over with coalesced box loads.  Every conflicting pair is discovered ONCE, from its smaller
+// box: a candidate scans only its own size level and the coarser ones (few, large cells) and records the edge
+// at the later box of the pair, i.e. in its own predecessor list or -- atomically -- in the other box's.
+static constexpr int kBuildLanes = 4;
+static constexpr int kBuildMaxRanges = 24;
 __device__ __forceinline__ void nms2_add_pred(DetWs& ws, long long later, int earlier, int n) {
     const int pos = atomicAdd(ws.npred + later, 1);
     if (pos < kMaxPreds) ws.preds[later * kMaxPreds + pos] = earlier;
     else ws.overflow[n] = 1;
 }
-static constexpr int kBuildWarps = 8;
-__global__ void __launch_bounds__(kBuildWarps * 32) hn_nms2_build_kernel(DetWs ws, long long NA, int nms_mode, float iou_thr,
-                                                                         GridGeom g) {
-    __shared__ float4 s_ent[kBuildWarps][32];
-    __shared__ int s_idx[kBuildWarps][32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ncell = *reinterpret_cast<volatile int*>(ws.changed + 3);
-    unsigned long long scanned = 0, edges = 0;
-    for (int ci = blockIdx.x * kBuildWarps + warp; ci < ncell; ci += gridDim.x * kBuildWarps) {
-        const int q0 = ws.cell_list[ci];
-        const uint32_t ck = ws.ckey[q0];
-        const int seg = (int)(ck / kCellStride), cell = (int)(ck % kCellStride), n = seg / kMaxCls;
-        const int q1 = ws.cell_begin[ck + 1];  // members of this cell: cell order [q0, q1)
-        int t = 0;
-        while (t < g.nlev - 1 && cell >= g.base[t + 1]) ++t;
-        const int cyy = (cell - g.base[t]) / g.nx[t], cxx = (cell - g.base[t]) - cyy * g.nx[t];
-        const float ct = g.c0 * (float)(1 << t);
-        // centres of this cell's boxes lie in [cxx*ct, (cxx+1)*ct) x [cyy*ct, ...) (border cells: clamped, handled by
-        // clamping the window the same way); their half sizes are below ct (top level: unbounded -> single cell)
-        const int l_hi = min(g.nlev - 1, t + g.delta);
-        for (int mb = q0; mb < q1; mb += 32) {  // member batches (cells rarely hold more than 32 candidates)
-            const int qm = mb + lane;
-            const bool have = qm < q1;
-            long long i = 0;
-            float4 b = make_float4(0, 0, 0, 0);
-            float area = 0.0f;
-            if (have) {
-                i = ws.cval[qm];
-                b = ws.cbox[qm];
-                area = box_area(b);
-            }
-            for (int l = t; l <= l_hi; ++l) {
-                const float cl = g.c0 * (float)(1 << l);
-                const float inv = 1.0f / cl;
-                const int nx = g.nx[l], ny = g.ny[l];
-                int x_lo = 0, x_hi = 0, y_lo = 0, y_hi = 0;
-                if (nx * ny > 1) {
-                    const float r = g.rfac * (ct + cl) + 1.0f;
-                    const bool edge_x0 = cxx == 0, edge_x1 = cxx == g.nx[t] - 1, edge_y0 = cyy == 0, edge_y1 = cyy == g.ny[t] - 1;
-                    // border cells also hold the boxes whose centre was clamped into them: open the window to the rim
-                    x_lo = edge_x0 ? 0 : clampi((int)floorf(((float)cxx * ct - r) * inv), 0, nx - 1);
-                    x_hi = edge_x1 ? nx - 1 : clampi((int)floorf(((float)(cxx + 1) * ct + r) * inv), 0, nx - 1);
-                    y_lo = edge_y0 ? 0 : clampi((int)floorf(((float)cyy * ct - r) * inv), 0, ny - 1);
-                    y_hi = edge_y1 ? ny - 1 : clampi((int)floorf(((float)(cyy + 1) * ct + r) * inv), 0, ny - 1);
-                }
-                const bool upper = l > t;
-                for (int yy = y_lo; yy <= y_hi; ++yy) {
-                    const uint32_t k0 = (uint32_t)seg * kCellStride + (uint32_t)(g.base[l] + yy * nx + x_lo);
-                    const int qb = ws.cell_begin[k0], qe = ws.cell_begin[k0 + (x_hi - x_lo) + 1];
-                    for (int e0 = qb; e0 < qe; e0 += 32) {
-                        const int cnt = min(32, qe - e0);
-                        __syncwarp();
-                        if (lane < cnt) {
-                            s_ent[warp][lane] = ws.cbox[e0 + lane];
-                            s_idx[warp][lane] = ws.cval[e0 + lane];
-                        }
-                        __syncwarp();
-                        if (have) {
-                            for (int e = 0; e < cnt; ++e) {
-                                const float4 kb = s_ent[warp][e];
-                                if (iou_gt(kb, box_area(kb), b, area, iou_thr)) {
-                                    const int m = s_idx[warp][e];
-                                    ++edges;
-                                    if (m < i) nms2_add_pred(ws, i, m, n);
-                                    else if (m > i && upper) nms2_add_pred(ws, m, (int)i, n);  // same level: the other box records it
-                                }
-                            }
-                            scanned += cnt;
-                        }
+__global__ void __launch_bounds__(256) hn_nms2_build_kernel(DetWs ws, long long NA, int nms_mode, float iou_thr, GridGeom g) {
+    // candidates are taken in CELL order: neighbouring groups scan overlapping index ranges (L1 / L2 locality)
+    const long long slot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kBuildLanes;
+    const int sub = threadIdx.x & (kBuildLanes - 1);
+    if (slot >= NA || ws.ckey[slot] == 0xFFFFFFFFu) return;
+    const long long i = ws.cval[slot];
+    const uint64_t key = ws.keys[i];
+    const int seg = (int)(key >> kClsShift), n = seg / kMaxCls;
+    const float offset = seg_offset(ws, n, seg % kMaxCls, nms_mode);
+    const float4 b = ws.sbox[i];
+    const float area = box_area(b);
+    const float wj = b.z - b.x, hj = b.w - b.y;
+    const float cx = 0.5f * (b.x + b.z) - offset, cy = 0.5f * (b.y + b.w) - offset;
+    const int t = grid_level(fmaxf(wj, hj), g);
+    const int l_hi = min(g.nlev - 1, t + g.delta);
+    int scanned = 0, edges = 0;
+    // pass 1: the index range of every window row (independent loads, all in flight together)
+    int r_beg[kBuildMaxRanges], r_end[kBuildMaxRanges];
+    int nr = 0, n_same = 0;  // ranges [0, n_same) belong to the candidate's own level
+    for (int l = t; l <= l_hi; ++l) {
+        const float cl = g.c0 * (float)(1 << l);
+        const float inv = 1.0f / cl;
+        const int nx = g.nx[l], ny = g.ny[l];
+        int x_lo = 0, x_hi = 0, y_lo = 0, y_hi = 0;
+        if (nx * ny > 1) {
+            const float rx = g.rfac * (0.5f * fmaxf(wj, 0.0f) + cl) + 1.0f, ry = g.rfac * (0.5f * fmaxf(hj, 0.0f) + cl) + 1.0f;
+            x_lo = clampi((int)floorf((cx - rx) * inv), 0, nx - 1);
+            x_hi = clampi((int)floorf((cx + rx) * inv), 0, nx - 1);
+            y_lo = clampi((int)floorf((cy - ry) * inv), 0, ny - 1);
+            y_hi = clampi((int)floorf((cy + ry) * inv), 0, ny - 1);
+        }
+        for (int yy = y_lo; yy <= y_hi; ++yy) {
+            const uint32_t k0 = (uint32_t)seg * kCellStride + (uint32_t)(g.base[l] + yy * nx + x_lo);
+            if (nr < kBuildMaxRanges) {
+                r_beg[nr] = ws.cell_begin[k0];
+                r_end[nr] = ws.cell_begin[k0 + (x_hi - x_lo) + 1];
+                ++nr;
+            } else {  // (never with the default geometry) fall back to scanning this row right away
+                const int q_end = ws.cell_begin[k0 + (x_hi - x_lo) + 1];
+                for (int q = ws.cell_begin[k0] + sub; q < q_end; q += kBuildLanes) {
+                    const float4 kb = ws.cbox[q];
+                    if (iou_gt(kb, box_area(kb), b, area, iou_thr)) {
+                        const int m = ws.cval[q];
+                        if (m < i) nms2_add_pred(ws, i, m, n);
+                        else if (m > i && l > t) nms2_add_pred(ws, m, (int)i, n);
                     }
                 }
             }
         }
+        if (l == t) n_same = nr;
+    }
+    // pass 2: scan
+    for (int r = 0; r < nr; ++r) {
+        const bool upper = r >= n_same;
+        const int q_end = r_end[r];
+        for (int q = r_beg[r] + sub; q < q_end; q += kBuildLanes) {
+            const float4 kb = ws.cbox[q];
+            ++scanned;
+            if (iou_gt(kb, box_area(kb), b, area, iou_thr)) {  // rare: only then look up the priority
+                const int m = ws.cval[q];
+                ++edges;
+                if (m < i) nms2_add_pred(ws, i, m, n);
+                else if (m > i && upper) nms2_add_pred(ws, m, (int)i, n);  // same level: the other box records it itself
+            }
+        }
     }
     if (ws.dbg) {
-        atomicAdd(reinterpret_cast<unsigned long long*>(ws.dbg) + 0, scanned);
-        atomicAdd(reinterpret_cast<unsigned long long*>(ws.dbg) + 1, edges);
+        atomicAdd(reinterpret_cast<unsigned long long*>(ws.dbg) + 0, (unsigned long long)scanned);
+        atomicAdd(reinterpret_cast<unsigned long long*>(ws.dbg) + 1, (unsigned long long)edges);
     }
 }
 
@@ -859,7 +852,7 @@ extern "C" int hn_det_decode_nms(const hn_det_desc* d, void* stream) {
         HN_CHECK_CUDA(cudaGetLastError());
         tb = ws.cub2_bytes;
         HN_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(ws.cub2_tmp, tb, ws.cell_cnt, ws.cell_begin, (int)T, s));
-        hn_nms2_build_kernel<<<hn_device_sm_count() * 8, kBuildWarps * 32, 0, s>>>(ws, NA, d->nms_mode, d->iou_thres, geom);
+        hn_nms2_build_kernel<<<hn_cdiv(NA * kBuildLanes, 256), 256, 0, s>>>(ws, NA, d->nms_mode, d->iou_thres, geom);
         HN_CHECK_CUDA(cudaGetLastError());
         hn_nms2_seed_kernel<<<hn_cdiv(NA, 256), 256, 0, s>>>(ws, NA);
         HN_CHECK_CUDA(cudaGetLastError());
