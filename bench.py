@@ -216,24 +216,38 @@ def run_native(args):
                 pin_lane[k][:, :lmax, 5:].copy_(l[3][:, :lmax], non_blocking=True)
         d2h_bytes[0] = B * H * W + 2 * B * 4 + B * kmax * 24 + B * lmax * 85 * 4
 
-    def e2e_loop(n):
+    def e2e_loop(n, do_up=True, do_down=True):
         for k in range(2):
             ev_free[k].record(stream)
-        upload(0)
+        if do_up:
+            upload(0)
         for i in range(n):
             k = i % 2
-            if i + 1 < n:
-                upload(i + 1)
-            stream.wait_event(ev_in[k])
+            if do_up:
+                if i + 1 < n:
+                    upload(i + 1)
+                stream.wait_event(ev_in[k])
             out, d, l = step(xin[k])
             ev_free[k].record(stream)
-            segcopy[k].copy_(out["seg_cls_u8"])  # the class map is the plan's static buffer: snapshot it for the download
-            ev_done[k].record(stream)
-            enqueue_small(k, segcopy[k], d, l)
-            finish(1 - k)  # while step i runs, complete the download of step i-1
-        finish((n - 1) % 2)
+            if do_down:
+                segcopy[k].copy_(out["seg_cls_u8"])  # the class map is the plan's static buffer: snapshot it for the download
+                ev_done[k].record(stream)
+                enqueue_small(k, segcopy[k], d, l)
+                finish(1 - k)  # while step i runs, complete the download of step i-1
+        if do_down:
+            finish((n - 1) % 2)
         s_out.synchronize()
         return None
+
+    if args.e2e_probe and rank == 0:
+        for name, up, down in (("compute only", False, False), ("upload+compute", True, False), ("compute+download", False, True),
+                               ("full", True, True)):
+            e2e_loop(4, up, down)
+            torch.cuda.synchronize(dev)
+            tp0 = time.perf_counter()
+            e2e_loop(args.steps, up, down)
+            torch.cuda.synchronize(dev)
+            print("e2e probe %-18s %.3f ms/step" % (name, (time.perf_counter() - tp0) * 1e3 / args.steps), flush=True)
 
     e2e_loop(max(3, args.warmup // 2))
     barrier()
@@ -414,6 +428,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--dump-ops", action="store_true", help="write per-op device times to gpurun_out/op_times.txt")
+    ap.add_argument("--e2e-probe", action="store_true", help="print the e2e loop time with upload / download switched off")
     ap.add_argument("--no-latency", action="store_true", help="skip the batch-1 latency measurement")
     ap.add_argument("--no-graph", action="store_true", help="launch the forward kernel by kernel instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -190,13 +190,50 @@ __global__ void __launch_bounds__(256) hn_node_kernel(const __grid_constant__ No
     const int n = blockIdx.x / per_img;
     const int r = blockIdx.x - n * per_img;
     const int y0 = (r / tiles_x) * kNodeTH, x0 = (r % tiles_x) * kNodeTW;
-    for (int hp = threadIdx.y; hp < kNodeHH * kNodeHW; hp += kNodeRows) {
-        const int hy = hp / kNodeHW, hx = hp - hy * kNodeHW;
-        float acc[8];
-        node_value(p, n, y0 + hy - 1, x0 + hx - 1, c, acc);
-        float4* dst = reinterpret_cast<float4*>(s_tile + hp * C + c);
-        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    // Phase 1, four halo pixels per thread at a time: all their input vectors are fetched first (the loop is bound
+    // by global-load latency, so loads in flight per thread is what counts), then fused.
+    constexpr int kBatch = 4;
+    for (int hp0 = threadIdx.y; hp0 < kNodeHH * kNodeHW; hp0 += kNodeRows * kBatch) {
+        float val[kBatch][3][8];
+        bool inside[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int hp = hp0 + u * kNodeRows;
+            const int hy = hp / kNodeHW, hx = hp - hy * kNodeHW;
+            const int y = y0 + hy - 1, x = x0 + hx - 1;
+            inside[u] = hp < kNodeHH * kNodeHW && y >= 0 && y < p.out.H && x >= 0 && x < p.out.W;
+            if (inside[u]) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    if (i < p.n_in) node_fetch(p.in[i], p.mode[i], n, y, x, c, val[u][i]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int hp = hp0 + u * kNodeRows;
+            if (hp >= kNodeHH * kNodeHW) break;
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+            if (inside[u]) {
+                // the reference evaluates w0*a + w1*b (+ w2*c) left to right in fp32 (bifpn.py:170-231)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = p.w[0] * val[u][0][j];
+#pragma unroll
+                for (int i = 1; i < 3; ++i)
+                    if (i < p.n_in) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[j] = acc[j] + p.w[i] * val[u][i][j];
+                    }
+                if (p.swish) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = acc[j] * hn_sigmoid(acc[j]);
+                }
+            }
+            float4* dst = reinterpret_cast<float4*>(s_tile + hp * C + c);
+            dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
     }
     float wgt[9][8];
 #pragma unroll
