@@ -3,20 +3,28 @@
 // (16-byte) vectors so every global access is a coalesced 128-bit transaction.
 #include "hn_ops.h"
 
+// device-side view with 32-bit element strides: every offset inside one activation tensor fits an int (checked in
+// check_view), and 64-bit address arithmetic would otherwise dominate the instruction count of these kernels
 struct View {
     const bf16* ptr;
     int N, H, W, C;
-    long long sn, sy, sx;
+    int sn, sy, sx;
 };
 static inline View to_view(const hn_view& v) {
     View r;
     r.ptr = reinterpret_cast<const bf16*>(v.ptr);
     r.N = v.N; r.H = v.H; r.W = v.W; r.C = v.C;
-    r.sn = v.stride_n; r.sy = v.stride_y; r.sx = v.stride_x;
+    r.sn = (int)v.stride_n; r.sy = (int)v.stride_y; r.sx = (int)v.stride_x;
     return r;
 }
 static int check_view(const hn_view& v, const char* what) {
     HN_REQUIRE(v.ptr != nullptr, "%s: null view", what);
+    {
+        long long span = (long long)(v.N > 0 ? v.N - 1 : 0) * v.stride_n + (long long)(v.H > 0 ? v.H - 1 : 0) * v.stride_y +
+                         (long long)(v.W > 0 ? v.W - 1 : 0) * v.stride_x + v.C;
+        HN_REQUIRE(span < 0x7fffffffLL && v.stride_n >= 0 && v.stride_y >= 0 && v.stride_x >= 0,
+                   "%s: view spans more than 2^31 elements", what);
+    }
     HN_REQUIRE((reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0 && v.C % 8 == 0 && v.stride_x % 8 == 0 && v.stride_y % 8 == 0 &&
                    v.stride_n % 8 == 0,
                "%s: view must be 16-byte aligned with C and strides in multiples of 8 (C=%d)", what, v.C);
@@ -35,7 +43,7 @@ __device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
     *reinterpret_cast<uint4*>(p) = u;
 }
 __device__ __forceinline__ const bf16* vptr(const View& v, int n, int y, int x, int c) {
-    return v.ptr + (long long)n * v.sn + (long long)y * v.sy + (long long)x * v.sx + c;
+    return v.ptr + (n * v.sn + y * v.sy + x * v.sx + c);
 }
 
 // ------------------------------------------------------------------------------------------------
