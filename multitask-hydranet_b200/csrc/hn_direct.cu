@@ -192,7 +192,9 @@ __device__ __forceinline__ void node_value(const NodeParams& p, int n, int y, in
 __global__ void __launch_bounds__(256) hn_node_kernel(const __grid_constant__ NodeParams p) {
     extern __shared__ float s_tile[];  // [kNodeHH * kNodeHW][C] fused values
     const int C = p.out.C;
-    const int cv = threadIdx.x, c = cv * 8;
+    const int CB = blockDim.x * 8;                        // channels of this CTA's slice (blockIdx.y picks it)
+    const int lc = threadIdx.x * 8;                       // channel offset inside the shared tile
+    const int c = blockIdx.y * CB + lc;
     const int tiles_x = (p.out.W + kNodeTW - 1) / kNodeTW, tiles_y = (p.out.H + kNodeTH - 1) / kNodeTH;
     const int per_img = tiles_x * tiles_y;
     const int n = blockIdx.x / per_img;
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(256) hn_node_kernel(const __grid_constant__ No
                     for (int j = 0; j < 8; ++j) acc[j] = acc[j] * hn_sigmoid(acc[j]);
                 }
             }
-            float4* dst = reinterpret_cast<float4*>(s_tile + hp * C + c);
+            float4* dst = reinterpret_cast<float4*>(s_tile + hp * CB + lc);
             dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
             dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
         }
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(256) hn_node_kernel(const __grid_constant__ No
         for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                const float4* sv = reinterpret_cast<const float4*>(s_tile + ((ty + ky) * kNodeHW + tx + kx) * C + c);
+                const float4* sv = reinterpret_cast<const float4*>(s_tile + ((ty + ky) * kNodeHW + tx + kx) * CB + lc);
                 const float4 a0 = sv[0], a1 = sv[1];
                 const float (&w)[8] = wgt[ky * 3 + kx];
                 acc[0] = fmaf(a0.x, w[0], acc[0]); acc[1] = fmaf(a0.y, w[1], acc[1]);
@@ -424,15 +426,23 @@ extern "C" int hn_node_fwd(const hn_node_desc* d, void* stream) {
         return HN_OK;
     }
     const int CV = d->out.C / 8;
-    HN_REQUIRE(CV >= 1 && CV * kNodeRows <= 256, "node: C=%d not supported (at most 128 channels)", d->out.C);
+    // Channel slices: depthwise work never crosses channels, so a CTA takes CV/split 8-channel vectors.  Smaller
+    // slices mean a smaller shared tile and more resident CTAs per SM (the load phase of one overlaps the tap phase
+    // of another); a slice keeps an even vector count so that every pixel's slice starts on a 32-byte sector.
+    int split = 1;
+    while (split < 4 && CV % (split * 2) == 0 && (CV / (split * 2)) % 2 == 0 &&
+           (size_t)kNodeHH * kNodeHW * (CV / split) * 8 * sizeof(float) > 60 * 1024)
+        split *= 2;
+    const int CB = CV / split;
+    HN_REQUIRE(CB >= 1 && CB * kNodeRows <= 256, "node: C=%d not supported", d->out.C);
     const int tiles = hn_cdiv(d->out.W, kNodeTW) * hn_cdiv(d->out.H, kNodeTH);
-    size_t smem = (size_t)kNodeHH * kNodeHW * d->out.C * sizeof(float);
+    size_t smem = (size_t)kNodeHH * kNodeHW * CB * 8 * sizeof(float);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         HN_CHECK_CUDA(cudaFuncSetAttribute(hn_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    hn_node_kernel<<<tiles * d->out.N, dim3(CV, kNodeRows), smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    hn_node_kernel<<<dim3(tiles * d->out.N, split), dim3(CB, kNodeRows), smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }
