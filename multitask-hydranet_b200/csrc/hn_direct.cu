@@ -158,123 +158,140 @@ __device__ __forceinline__ void node_fetch(const View& v, int mode, int n, int y
 
 static constexpr int kNodeTH = 8, kNodeTW = 16;         // output tile
 static constexpr int kNodeHH = kNodeTH + 2, kNodeHW = kNodeTW + 2;  // halo tile
-static constexpr int kNodeRows = 16;                      // threadIdx.y extent
+static constexpr int kNodeRows = 8;                       // threadIdx.y extent: one per pair of output columns
 
-// fused value (weighted sum -> swish) of one 8-channel vector at (y, x); zero outside the image (the depthwise
-// conv's zero padding)
-__device__ __forceinline__ void node_value(const NodeParams& p, int n, int y, int x, int c, float (&acc)[8]) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-    if (y < 0 || y >= p.out.H || x < 0 || x >= p.out.W) return;
-    for (int i = 0; i < p.n_in; ++i) {
-        float f[8];
-        node_fetch(p.in[i], p.mode[i], n, y, x, c, f);
-        // the reference evaluates w0*a + w1*b (+ w2*c) left to right in fp32 (bifpn.py:170-231)
-        const float w = p.w[i];
-        if (i == 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = w * f[j];
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = acc[j] + w * f[j];
-        }
-    }
-    if (p.swish) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = acc[j] * hn_sigmoid(acc[j]);
-    }
+// packed bf16x2 max (max commutes with the monotonic bf16 -> fp32 widening, so this equals max on the widened values)
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+    __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a), y = *reinterpret_cast<__nv_bfloat162*>(&b);
+    __nv_bfloat162 m = __hmax2(x, y);
+    return *reinterpret_cast<uint32_t*>(&m);
 }
 
-// CTA = (C/8) x 16 threads; threadIdx.x is the 8-channel vector (a pixel's channels are contiguous: coalesced),
-// threadIdx.y strides over pixels.  Phase 1 computes the fused value (weighted sum, swish) of the (8+2)x(16+2)
-// halo tile once into shared memory (fp32); phase 2 runs the depthwise taps from there with the 9x8 weights of
-// the thread's channel vector held in registers.
-__global__ void __launch_bounds__(256) hn_node_kernel(const __grid_constant__ NodeParams p) {
-    extern __shared__ float s_tile[];  // [kNodeHH * kNodeHW][C] fused values
+// CTA = L x 8 threads over an 8x16 output tile of a channel slice (L four-channel vectors, blockIdx.y picks the
+// slice; depthwise work never crosses channels).  threadIdx.x is the channel vector: a pixel's channels are
+// contiguous, so global accesses coalesce and neighbouring lanes hit neighbouring shared-memory banks.
+// Phase 1 computes the fused value (weighted sum, swish) of the (8+2)x(16+2) halo tile once into shared memory
+// (fp32), kNodeBatch pixels per thread at a time.  The phase is bound by global-load latency, so its loads are
+// branch-free (clamped coordinates, the up-sampling as a shift, the input count and the pooled input as template
+// parameters): the compiler can then put a whole batch in flight before the first use.
+// Phase 2: thread (lane, j) owns output columns 2j, 2j+1 and walks down the ten halo rows with the 9x4 weights in
+// registers; each halo row is read once (4 vectors) and feeds the three output rows it touches, whose
+// accumulators roll.
+static constexpr int kNodeBatch = 6;
+template <int kNin, bool kPoolLast>
+__global__ void __launch_bounds__(512) hn_node_kernel(const __grid_constant__ NodeParams p) {
+    extern __shared__ float s_tile[];  // [kNodeHH * kNodeHW][CB] fused values
+    constexpr int kDirect = kPoolLast ? kNin - 1 : kNin;
     const int C = p.out.C;
-    const int CB = blockDim.x * 8;                        // channels of this CTA's slice (blockIdx.y picks it)
-    const int lc = threadIdx.x * 8;                       // channel offset inside the shared tile
+    const int CB = blockDim.x * 4;
+    const int lc = threadIdx.x * 4;
     const int c = blockIdx.y * CB + lc;
     const int tiles_x = (p.out.W + kNodeTW - 1) / kNodeTW, tiles_y = (p.out.H + kNodeTH - 1) / kNodeTH;
     const int per_img = tiles_x * tiles_y;
     const int n = blockIdx.x / per_img;
     const int r = blockIdx.x - n * per_img;
     const int y0 = (r / tiles_x) * kNodeTH, x0 = (r % tiles_x) * kNodeTW;
-    // Phase 1, four halo pixels per thread at a time: all their input vectors are fetched first (the loop is bound
-    // by global-load latency, so loads in flight per thread is what counts), then fused.
-    constexpr int kBatch = 4;
-    for (int hp0 = threadIdx.y; hp0 < kNodeHH * kNodeHW; hp0 += kNodeRows * kBatch) {
-        float val[kBatch][3][8];
-        bool inside[kBatch];
+    constexpr int kHalo = kNodeHH * kNodeHW;
+    const bf16* base[kNin];
+    int sh[kNin];
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-            const int hp = hp0 + u * kNodeRows;
+    for (int i = 0; i < kNin; ++i) {
+        base[i] = p.in[i].ptr + n * p.in[i].sn + c;
+        sh[i] = p.mode[i] == HN_IN_UP2 ? 1 : 0;
+    }
+    for (int hp0 = threadIdx.y; hp0 < kHalo; hp0 += kNodeRows * kNodeBatch) {
+        uint2 raw[kNodeBatch][kNin];
+        bool inside[kNodeBatch];
+#pragma unroll
+        for (int u = 0; u < kNodeBatch; ++u) {
+            const int hp = min(hp0 + u * kNodeRows, kHalo - 1);
             const int hy = hp / kNodeHW, hx = hp - hy * kNodeHW;
             const int y = y0 + hy - 1, x = x0 + hx - 1;
-            inside[u] = hp < kNodeHH * kNodeHW && y >= 0 && y < p.out.H && x >= 0 && x < p.out.W;
-            if (inside[u]) {
+            inside[u] = y >= 0 && y < p.out.H && x >= 0 && x < p.out.W;
+            const int yc = min(max(y, 0), p.out.H - 1), xc = min(max(x, 0), p.out.W - 1);
 #pragma unroll
-                for (int i = 0; i < 3; ++i)
-                    if (i < p.n_in) node_fetch(p.in[i], p.mode[i], n, y, x, c, val[u][i]);
+            for (int i = 0; i < kDirect; ++i)
+                raw[u][i] = *reinterpret_cast<const uint2*>(base[i] + (yc >> sh[i]) * p.in[i].sy + (xc >> sh[i]) * p.in[i].sx);
+            if (kPoolLast) {
+                // 3x3 stride-2 max over the input padded with one zero row/col at the bottom/right
+                const View& v = p.in[kNin - 1];
+                uint2 m = make_uint2(0xff80ff80u, 0xff80ff80u);  // -inf
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const int iy = 2 * yc + dy, ix = 2 * xc + dx;
+                        const bool ok = iy < v.H && ix < v.W;
+                        uint2 q = *reinterpret_cast<const uint2*>(base[kNin - 1] + min(iy, v.H - 1) * v.sy + min(ix, v.W - 1) * v.sx);
+                        if (!ok) q = make_uint2(0u, 0u);
+                        m.x = bf16x2_max(m.x, q.x);
+                        m.y = bf16x2_max(m.y, q.y);
+                    }
+                }
+                raw[u][kNin - 1] = m;
             }
         }
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
+        for (int u = 0; u < kNodeBatch; ++u) {
             const int hp = hp0 + u * kNodeRows;
-            if (hp >= kNodeHH * kNodeHW) break;
-            float acc[8];
+            if (hp >= kHalo) break;
+            float acc[4];
+            // the reference evaluates w0*a + w1*b (+ w2*c) left to right in fp32 (bifpn.py:170-231)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-            if (inside[u]) {
-                // the reference evaluates w0*a + w1*b (+ w2*c) left to right in fp32 (bifpn.py:170-231)
+            for (int i = 0; i < kNin; ++i) {
+                const float2 a = hn_unpack_bf16x2(raw[u][i].x), b = hn_unpack_bf16x2(raw[u][i].y);
+                const float w = p.w[i];
+                if (i == 0) { acc[0] = w * a.x; acc[1] = w * a.y; acc[2] = w * b.x; acc[3] = w * b.y; }
+                else { acc[0] = acc[0] + w * a.x; acc[1] = acc[1] + w * a.y; acc[2] = acc[2] + w * b.x; acc[3] = acc[3] + w * b.y; }
+            }
+            if (p.swish) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = p.w[0] * val[u][0][j];
+                for (int j = 0; j < 4; ++j) acc[j] = acc[j] * hn_sigmoid(acc[j]);
+            }
+            if (!inside[u]) acc[0] = acc[1] = acc[2] = acc[3] = 0.0f;  // the depthwise conv's zero padding
+            *reinterpret_cast<float4*>(s_tile + hp * CB + lc) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        }
+    }
+    float4 wgt[9];
 #pragma unroll
-                for (int i = 1; i < 3; ++i)
-                    if (i < p.n_in) {
+    for (int k = 0; k < 9; ++k) wgt[k] = __ldg(reinterpret_cast<const float4*>(p.dw + k * C + c));
+    __syncthreads();
+    const int tx = threadIdx.y * 2;  // first of the two output columns
+    float4 acc[kNodeTH][2];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) acc[j] = acc[j] + p.w[i] * val[u][i][j];
-                    }
-                if (p.swish) {
+    for (int hy = 0; hy < kNodeHH; ++hy) {
+        float4 a[4];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] = acc[j] * hn_sigmoid(acc[j]);
+        for (int q = 0; q < 4; ++q) a[q] = *reinterpret_cast<const float4*>(s_tile + (hy * kNodeHW + tx + q) * CB + lc);
+#pragma unroll
+        for (int ky = 2; ky >= 0; --ky) {  // output row o = hy - ky takes this halo row through kernel row ky
+            const int o = hy - ky;
+            if (o < 0 || o >= kNodeTH) continue;
+#pragma unroll
+            for (int col = 0; col < 2; ++col) {
+                float4 v = ky == 0 ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : acc[o][col];
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4 w = wgt[ky * 3 + kx];
+                    const float4 s = a[col + kx];
+                    v.x = fmaf(s.x, w.x, v.x); v.y = fmaf(s.y, w.y, v.y); v.z = fmaf(s.z, w.z, v.z); v.w = fmaf(s.w, w.w, v.w);
+                }
+                acc[o][col] = v;
+            }
+        }
+        const int o = hy - 2;  // complete after its third halo row
+        if (o >= 0) {
+            const int y = y0 + o;
+#pragma unroll
+            for (int col = 0; col < 2; ++col) {
+                const int x = x0 + tx + col;
+                if (y < p.out.H && x < p.out.W) {
+                    const float4 v = acc[o][col];
+                    *reinterpret_cast<uint2*>(const_cast<bf16*>(vptr(p.out, n, y, x, c))) =
+                        make_uint2(hn_pack_bf16x2(v.x, v.y), hn_pack_bf16x2(v.z, v.w));
                 }
             }
-            float4* dst = reinterpret_cast<float4*>(s_tile + hp * CB + lc);
-            dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
         }
-    }
-    float wgt[9][8];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        const float4* wv = reinterpret_cast<const float4*>(p.dw + k * C + c);
-        const float4 w0 = __ldg(wv), w1 = __ldg(wv + 1);
-        wgt[k][0] = w0.x; wgt[k][1] = w0.y; wgt[k][2] = w0.z; wgt[k][3] = w0.w;
-        wgt[k][4] = w1.x; wgt[k][5] = w1.y; wgt[k][6] = w1.z; wgt[k][7] = w1.w;
-    }
-    __syncthreads();
-    for (int op = threadIdx.y; op < kNodeTH * kNodeTW; op += kNodeRows) {
-        const int ty = op / kNodeTW, tx = op - ty * kNodeTW;
-        const int y = y0 + ty, x = x0 + tx;
-        if (y >= p.out.H || x >= p.out.W) continue;
-        float acc[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const float4* sv = reinterpret_cast<const float4*>(s_tile + ((ty + ky) * kNodeHW + tx + kx) * CB + lc);
-                const float4 a0 = sv[0], a1 = sv[1];
-                const float (&w)[8] = wgt[ky * 3 + kx];
-                acc[0] = fmaf(a0.x, w[0], acc[0]); acc[1] = fmaf(a0.y, w[1], acc[1]);
-                acc[2] = fmaf(a0.z, w[2], acc[2]); acc[3] = fmaf(a0.w, w[3], acc[3]);
-                acc[4] = fmaf(a1.x, w[4], acc[4]); acc[5] = fmaf(a1.y, w[5], acc[5]);
-                acc[6] = fmaf(a1.z, w[6], acc[6]); acc[7] = fmaf(a1.w, w[7], acc[7]);
-            }
-        }
-        store8(const_cast<bf16*>(vptr(p.out, n, y, x, c)), acc);
     }
 }
 
@@ -425,24 +442,31 @@ extern "C" int hn_node_fwd(const hn_node_desc* d, void* stream) {
         HN_CHECK_CUDA(cudaGetLastError());
         return HN_OK;
     }
-    const int CV = d->out.C / 8;
-    // Channel slices: depthwise work never crosses channels, so a CTA takes CV/split 8-channel vectors.  Smaller
-    // slices mean a smaller shared tile and more resident CTAs per SM (the load phase of one overlaps the tap phase
-    // of another); a slice keeps an even vector count so that every pixel's slice starts on a 32-byte sector.
+    // Channel slices: a CTA takes L = (C/4)/split four-channel vectors.  Smaller slices mean a smaller shared tile
+    // and more resident CTAs per SM, so the load phase of one overlaps the tap phase of another.
+    const int L4 = d->out.C / 4;
     int split = 1;
-    while (split < 4 && CV % (split * 2) == 0 && (CV / (split * 2)) % 2 == 0 &&
-           (size_t)kNodeHH * kNodeHW * (CV / split) * 8 * sizeof(float) > 60 * 1024)
+    while (split < 4 && (L4 / split) % 2 == 0 && L4 / split > 8 &&
+           (size_t)kNodeHH * kNodeHW * (L4 / split) * 4 * sizeof(float) > 44 * 1024)
         split *= 2;
-    const int CB = CV / split;
-    HN_REQUIRE(CB >= 1 && CB * kNodeRows <= 256, "node: C=%d not supported", d->out.C);
+    const int CB = L4 / split;
+    HN_REQUIRE(CB >= 1 && CB * kNodeRows <= 512, "node: C=%d not supported", d->out.C);
     const int tiles = hn_cdiv(d->out.W, kNodeTW) * hn_cdiv(d->out.H, kNodeTH);
-    size_t smem = (size_t)kNodeHH * kNodeHW * CB * 8 * sizeof(float);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        HN_CHECK_CUDA(cudaFuncSetAttribute(hn_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    size_t smem = (size_t)kNodeHH * kNodeHW * CB * 4 * sizeof(float);
+    // pooled inputs: only as the last one (the BiFPN bottom-up nodes: same-level inputs, then the level below)
+    bool pool_last = d->mode[d->n_in - 1] == HN_IN_POOL;
+    for (int i = 0; i + 1 < d->n_in; ++i) HN_REQUIRE(d->mode[i] != HN_IN_POOL, "node: a pooled input must be the last input");
+    void (*kern)(const NodeParams) = nullptr;
+    switch (d->n_in * 2 + (pool_last ? 1 : 0)) {
+        case 2: kern = hn_node_kernel<1, false>; break;
+        case 3: kern = hn_node_kernel<1, true>; break;
+        case 4: kern = hn_node_kernel<2, false>; break;
+        case 5: kern = hn_node_kernel<2, true>; break;
+        case 6: kern = hn_node_kernel<3, false>; break;
+        default: kern = hn_node_kernel<3, true>; break;
     }
-    hn_node_kernel<<<dim3(tiles * d->out.N, split), dim3(CB, kNodeRows), smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    if (smem > 48 * 1024) HN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(tiles * d->out.N, split), dim3(CB, kNodeRows), smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }
