@@ -74,6 +74,10 @@ __device__ __forceinline__ void hn_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 __device__ __forceinline__ void hn_mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hn_smem_u32(bar)) : "memory");
 }
+// The suspend-time hint lets the hardware park a waiting warp until the phase completes instead of returning
+// early: a polling producer / MMA lane otherwise eats a fifth of its scheduler's issue slots, which the epilogue
+// warps of the same SM partition need.
+static constexpr uint32_t kMbarSuspendNs = 20000;
 __device__ __forceinline__ void hn_mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t addr = hn_smem_u32(bar);
     uint32_t done;
@@ -81,11 +85,11 @@ __device__ __forceinline__ void hn_mbar_wait(uint64_t* bar, uint32_t parity) {
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t"
             "}\n"
             : "=r"(done)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(kMbarSuspendNs)
             : "memory");
     } while (!done);
 }
@@ -251,6 +255,11 @@ __device__ __forceinline__ uint32_t hn_umma_idesc_bf16(int M, int N) {
 }
 
 // ---- numerics ----
+__device__ __forceinline__ float hn_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float hn_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float hn_act(float x, int act) {
     switch (act) {

@@ -6,15 +6,18 @@
 // the pre-packed K-major weight matrix.  Both land 128-byte swizzled, exactly the canonical K-major
 // UMMA layout, so four tcgen05.mma (K=16 each) consume a stage.
 //
-// CTA = 192 threads: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (one elected lane),
-// warps 2..5 epilogue (TMEM -> registers -> bias/activation/residual -> global, plus halo mirrors).
+// CTA = 320 threads: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (one elected lane),
+// warps 2..9 epilogue (TMEM -> registers -> bias/activation/residual -> global, plus halo mirrors): two warps
+// per TMEM lane quarter, each taking every other 32-column chunk -- the epilogue is latency-bound per warp, and
+// for narrow / short-K tiles it, not the MMA, sets the tile rate.
 // Accumulator: 128 lanes x BN fp32 columns in TMEM.
 #include <mutex>
 
 #include "hn_ops.h"
 
 static constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
-static constexpr int kEpiThreads = 128;
+static constexpr int kEpiThreads = 256;
+static constexpr int kCtaThreads = 64 + kEpiThreads;
 
 __device__ __forceinline__ long long hn_globaltimer() {
     long long t;
@@ -77,7 +80,7 @@ __device__ __forceinline__ void apply_act(float (&f)[NC], int act) {
             break;
         case HN_ACT_ELU:
 #pragma unroll
-            for (int j = 0; j < NC; ++j) f[j] = f[j] > 0.0f ? f[j] : __expf(f[j]) - 1.0f;
+            for (int j = 0; j < NC; ++j) f[j] = f[j] > 0.0f ? f[j] : hn_ex2(f[j] * 1.4426950408889634f) - 1.0f;
             break;
         case HN_ACT_SIGMOID:
 #pragma unroll
@@ -173,20 +176,19 @@ __device__ __forceinline__ void epi_chunk_std(const ConvParams& p, const EpiRow&
 
 // columns = 4 sub-pixel parities x 8 (n_cls valid): fp32 NCHW logits + fused arg-max.  The two x-parities of
 // a class are adjacent in memory: one float2 (uchar2 for the class map) per (class, y-parity).
-__device__ __forceinline__ void epi_segout(const ConvParams& p, const EpiRow& e, const float* s_bias, uint32_t (&v)[32]) {
+__device__ __forceinline__ void epi_segout(const ConvParams& p, const EpiRow& e, const float* s_bias, uint32_t (&v)[16], int py) {
     if (!e.valid) return;
     const int OH = p.H * 2, OW = p.W * 2;
     float* outf = reinterpret_cast<float*>(p.out);
-#pragma unroll
-    for (int py = 0; py < 2; ++py) {
+    {
         const int yy = e.Y * 2 + py, xx = e.X * 2;
         float b0 = 0.f, b1 = 0.f;
         int i0 = 0, i1 = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             if (k < p.n_cls) {
-                float f0 = __uint_as_float(v[(py * 2 + 0) * 8 + k]) + s_bias[(py * 2 + 0) * 8 + k];
-                float f1 = __uint_as_float(v[(py * 2 + 1) * 8 + k]) + s_bias[(py * 2 + 1) * 8 + k];
+                float f0 = __uint_as_float(v[k]) + s_bias[(py * 2 + 0) * 8 + k];
+                float f1 = __uint_as_float(v[8 + k]) + s_bias[(py * 2 + 1) * 8 + k];
                 *reinterpret_cast<float2*>(outf + (((long long)e.n_i * p.n_cls + k) * OH + yy) * OW + xx) = make_float2(f0, f1);
                 if (k == 0 || f0 > b0) { b0 = f0; i0 = k; }
                 if (k == 0 || f1 > b1) { b1 = f1; i1 = k; }
@@ -202,7 +204,7 @@ __device__ __forceinline__ void epi_segout(const ConvParams& p, const EpiRow& e,
 // epilogue of tile i overlaps the main loop of tile i+1.
 // kPair = true: the cta_group::2 build (must be launched as 2-CTA clusters); false: no pair instructions at all
 template <bool kPair>
-__global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(kCtaThreads) hn_conv_gemm_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int BN = p.bn;
@@ -323,8 +325,9 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
             }
         }
     } else {
-        // ------------------------------ epilogue (warps 2..5) ------------------------------
-        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        // ------------------------------ epilogue (warps 2..9) ------------------------------
+        const int q = warp & 3;          // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;  // which of the quarter's two warps: it takes the odd or the even 32-column chunks
         const int row = q * 32 + lane;
         const int et = threadIdx.x - 64;
         int a = 0;
@@ -399,10 +402,10 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
             if (dbg && ntile == 0 && et == 0) dbg[5] = hn_globaltimer();
             const uint32_t t_row = tmem_base + (uint32_t)(a * p.acc_stride) + ((uint32_t)(q * 32) << 16);
             if (p.epi == HN_EPI_SEGOUT) {
-                uint32_t v[32];
-                hn_tmem_ld32(t_row, v);
+                uint32_t v[16];  // this warp's output-row parity: columns [half][x parity][8]
+                hn_tmem_ld16(t_row + half * 16, v);
                 hn_tmem_ld_wait();
-                epi_segout(p, e, bias_s, v);
+                epi_segout(p, e, bias_s, v, half);
             } else if (p.n_staging) {
                 // 64-channel slabs: registers -> swizzled shared-memory tile -> one TMA store per slab
                 for (int c = 0; c < BN; c += 64) {
@@ -412,9 +415,8 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
                     }
                     hn_named_bar_sync(2, kEpiThreads);  // slab is free again
                     uint8_t* stage_row = slab + row * 128;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int cc = c + h * 32;
+                    {
+                        const int cc = c + half * 32;
                         if (cc + 32 <= BN) {
                             uint32_t v[32];
                             hn_tmem_ld32(t_row + cc, v);
@@ -436,14 +438,14 @@ __global__ void __launch_bounds__(192) hn_conv_gemm_kernel(const __grid_constant
                     ++st_count;
                 }
             } else {
-                int c = 0;
-                for (; c + 32 <= BN; c += 32) {
+                int c = half * 32;
+                for (; c + 32 <= BN; c += 64) {
                     uint32_t v[32];
                     hn_tmem_ld32(t_row + c, v);
                     hn_tmem_ld_wait();
                     epi_chunk_std<32>(p, e, bias_s, scale_s, c, o.n0, v, nullptr, row);
                 }
-                if (c < BN) {
+                if (c < BN) {  // a 16-column tail chunk (BN % 32 == 16)
                     uint32_t v[16];
                     hn_tmem_ld16(t_row + c, v);
                     hn_tmem_ld_wait();
@@ -698,14 +700,14 @@ int hn_conv_launch(const ConvLaunch* L, cudaStream_t stream) {
     });
     HN_CHECK_CUDA(attr_err);
     if (L->cluster <= 1) {
-        hn_conv_gemm_kernel<false><<<L->grid, 192, L->smem, stream>>>(L->prm);
+        hn_conv_gemm_kernel<false><<<L->grid, kCtaThreads, L->smem, stream>>>(L->prm);
         HN_CHECK_CUDA(cudaGetLastError());
         return HN_OK;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = L->grid;
-    cfg.blockDim = dim3(192);
+    cfg.blockDim = dim3(kCtaThreads);
     cfg.dynamicSmemBytes = L->smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
