@@ -134,6 +134,7 @@ SYMBOLS = {
     "hn_plan_graph_launch": (C.c_int, [_P, _P]),
     "hn_conv_set_debug_buffer": (None, [_P]),
     "hn_conv_set_cluster": (None, [C.c_int]),
+    "hn_conv_set_tap_runs": (None, [C.c_int]),
     "hn_det_set_debug_buffer": (None, [_P]),
     "hn_det_force_sequential": (None, [C.c_int]),
     "hn_version": (C.c_int, []),
@@ -151,6 +152,11 @@ for _name, (_res, _args) in SYMBOLS.items():
     _fn = getattr(lib, _name)  # AttributeError here == header / library mismatch
     _fn.restype = _res
     _fn.argtypes = _args
+# tuning knobs for A/B measurements (tools/, bench.py); the defaults are the shipped policy
+if os.environ.get("HN_TAP_RUNS"):
+    lib.hn_conv_set_tap_runs(int(os.environ["HN_TAP_RUNS"]))
+if os.environ.get("HN_CLUSTER"):
+    lib.hn_conv_set_cluster(int(os.environ["HN_CLUSTER"]))
 
 
 class NativeError(RuntimeError):

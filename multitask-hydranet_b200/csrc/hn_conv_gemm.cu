@@ -11,6 +11,7 @@
 // per TMEM lane quarter, each taking every other 32-column chunk -- the epilogue is latency-bound per warp, and
 // for narrow / short-K tiles it, not the MMA, sets the tile rate.
 // Accumulator: 128 lanes x BN fp32 columns in TMEM.
+#include <algorithm>
 #include <mutex>
 
 #include "hn_ops.h"
@@ -210,9 +211,13 @@ __global__ void __launch_bounds__(kCtaThreads) hn_conv_gemm_kernel(const __grid_
     const int BN = p.bn;
     const int stages = p.stages;
     const int b_tile_bytes = (kPair ? BN / 2 : BN) * 128;  // a CTA of a pair holds half of the weight rows
+    // a stage holds one tap RUN: the A box of (TH + run_max - 1) tile rows -- consecutive dy taps of one (source,
+    // dx, channel slice) are row-shifted windows of it -- and run_max weight tiles
+    const int a_stage = p.a_stage_bytes, b_stage = p.run_max * b_tile_bytes;
+    const int a_row_bytes = p.TW * 128;  // one tile row of the A box (a multiple of the 1024-byte swizzle atom)
     uint8_t* sA = smem;
-    uint8_t* sB = smem + stages * kATileBytes;
-    uint8_t* sO = sB + stages * b_tile_bytes;  // n_staging x 16 KB output staging (1024-byte aligned)
+    uint8_t* sB = smem + stages * a_stage;
+    uint8_t* sO = sB + stages * b_stage;  // n_staging x 16 KB output staging (1024-byte aligned)
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(sO + p.n_staging * kATileBytes);
     uint64_t* bar_empty = bar_full + stages;
     uint64_t* bar_acc_full = bar_empty + stages;   // [2]
@@ -263,29 +268,35 @@ __global__ void __launch_bounds__(kCtaThreads) hn_conv_gemm_kernel(const __grid_
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
-            const uint32_t stage_bytes = (uint32_t)(kATileBytes + b_tile_bytes);
             int s = 0;
             uint32_t ph = 0;
             for (int t = t_first; t < total_tiles; t += t_step) {
                 const TileOrigin o = tile_origin(p, t, rank);
                 const int c_shift = p.grouped ? o.n0 : 0;
-                for (int k = 0; k < p.num_taps; ++k) {
+                for (int k = 0; k < p.num_taps;) {
                     hn_mbar_wait(&bar_empty[s], ph ^ 1);
                     const hn_tap tp = p.taps[k];
+                    const int run = tp.rsv0;  // taps k .. k+run-1 share this A box (run == 1: the plain 128-row tile)
+                    const CUtensorMap* tma = run > 1 ? &p.tmArun[tp.src] : &p.tmA[tp.src];
+                    const uint32_t stage_bytes = (uint32_t)((run > 1 ? a_stage : kATileBytes) + run * b_tile_bytes);
                     if constexpr (!PAIR) {
                         hn_mbar_expect_tx(&bar_full[s], stage_bytes);
-                        hn_tma_load_4d(sA + s * kATileBytes, &p.tmA[tp.src], &bar_full[s], (int)tp.c0 + c_shift, o.x0 + (int)tp.dx,
+                        hn_tma_load_4d(sA + s * a_stage, tma, &bar_full[s], (int)tp.c0 + c_shift, o.x0 + (int)tp.dx,
                                        o.y0 + (int)tp.dy, o.img);
-                        hn_tma_load_2d(sB + s * b_tile_bytes, &p.tmB, &bar_full[s], k * 64, o.n0);
+                        for (int j = 0; j < run; ++j)
+                            hn_tma_load_2d(sB + s * b_stage + j * b_tile_bytes, &p.tmB, &bar_full[s], (int)p.taps[k + j].rsv1 * 64, o.n0);
                     } else {
                         // each CTA loads its own 128 A rows and its half of the weight rows; all bytes are counted on the
                         // leader's barrier, which is the one the (single) MMA issuer waits on
                         if (leader) hn_mbar_expect_tx(&bar_full[s], 2u * stage_bytes);
                         const uint32_t lbar = hn_mapa(hn_smem_u32(&bar_full[s]), 0);
-                        hn_tma_load_4d_pair(sA + s * kATileBytes, &p.tmA[tp.src], lbar, (int)tp.c0 + c_shift, o.x0 + (int)tp.dx,
+                        hn_tma_load_4d_pair(sA + s * a_stage, tma, lbar, (int)tp.c0 + c_shift, o.x0 + (int)tp.dx,
                                             o.y0 + (int)tp.dy, o.img);
-                        hn_tma_load_2d_pair(sB + s * b_tile_bytes, &p.tmBpart, lbar, k * 64, o.n0 + rank * (BN / 2));
+                        for (int j = 0; j < run; ++j)
+                            hn_tma_load_2d_pair(sB + s * b_stage + j * b_tile_bytes, &p.tmBpart, lbar, (int)p.taps[k + j].rsv1 * 64,
+                                                o.n0 + rank * (BN / 2));
                     }
+                    k += run;
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
                 if (dbg && t == t_first) dbg[2] = hn_globaltimer();
@@ -301,21 +312,26 @@ __global__ void __launch_bounds__(kCtaThreads) hn_conv_gemm_kernel(const __grid_
                 hn_mbar_wait(&bar_acc_empty[a], aph ^ 1);  // epilogue has drained this accumulator
                 hn_tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.acc_stride);
-                for (int k = 0; k < p.num_taps; ++k) {
+                for (int k = 0; k < p.num_taps;) {
+                    const int run = p.taps[k].rsv0;
                     hn_mbar_wait(&bar_full[s], ph);
                     hn_tc_fence_after();
                     if (dbg && t == t_first && k == 0) dbg[3] = hn_globaltimer();
-                    const uint32_t a_addr = hn_smem_u32(sA + s * kATileBytes);
-                    const uint32_t b_addr = hn_smem_u32(sB + s * b_tile_bytes);
+                    for (int j = 0; j < run; ++j) {
+                        // tap k+j reads the A box from tile row j on
+                        const uint32_t a_addr = hn_smem_u32(sA + s * a_stage + j * a_row_bytes);
+                        const uint32_t b_addr = hn_smem_u32(sB + s * b_stage + j * b_tile_bytes);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        uint64_t da = hn_umma_desc_sw128(a_addr + kk * 32);
-                        uint64_t db = hn_umma_desc_sw128(b_addr + kk * 32);
-                        if constexpr (PAIR) hn_umma_bf16_pair(d_tmem, da, db, idesc, (uint32_t)((k | kk) != 0));
-                        else hn_umma_bf16(d_tmem, da, db, idesc, (uint32_t)((k | kk) != 0));
+                        for (int kk = 0; kk < 4; ++kk) {
+                            uint64_t da = hn_umma_desc_sw128(a_addr + kk * 32);
+                            uint64_t db = hn_umma_desc_sw128(b_addr + kk * 32);
+                            if constexpr (PAIR) hn_umma_bf16_pair(d_tmem, da, db, idesc, (uint32_t)((k | j | kk) != 0));
+                            else hn_umma_bf16(d_tmem, da, db, idesc, (uint32_t)((k | j | kk) != 0));
+                        }
                     }
                     // frees the smem slot once these MMAs retire (pair: in both CTAs)
                     if constexpr (PAIR) hn_umma_commit_pair(&bar_empty[s]); else hn_umma_commit(&bar_empty[s]);
+                    k += run;
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
                 // accumulator complete (pair: each CTA's epilogue drains its own 128 rows)
@@ -538,6 +554,9 @@ static void* g_conv_dbg = nullptr;
 extern "C" void hn_conv_set_debug_buffer(void* p) { g_conv_dbg = p; }
 static int g_conv_cluster = 0;  // 0 = default policy
 extern "C" void hn_conv_set_cluster(int cs) { g_conv_cluster = cs; }
+static int g_conv_runs = 1;  // 0: never share A boxes between taps; 1: default policy (narrow N tiles); 2: wherever they fit
+extern "C" void hn_conv_set_tap_runs(int mode) { g_conv_runs = mode; }
+static constexpr int kMaxRun = 3;
 
 static int round_pow2_cols(int bn) {
     int c = 32;
@@ -565,6 +584,8 @@ int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L) {
     for (int k = 0; k < d->num_taps; ++k) {
         HN_REQUIRE(d->taps[k].src >= 0 && d->taps[k].src < d->n_src, "tap %d: bad source %d", k, d->taps[k].src);
         p.taps[k] = d->taps[k];
+        p.taps[k].rsv0 = 1;            // run length (set on the first tap of a run)
+        p.taps[k].rsv1 = (int16_t)k;  // K block of the weight matrix (the caller's tap index)
     }
     p.flat = d->flat;
     p.TH = TH;
@@ -656,15 +677,81 @@ int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L) {
     const int b_rows_cta = cs == 2 ? d->bn / 2 : d->bn;
     p.gstride = n_tiles * d->bn;
     const int bias_slots = d->n_groups > 0 ? 2 * d->n_groups : 1;
-    const size_t base_smem = 1024 + (size_t)stages * (kATileBytes + b_rows_cta * 128) + (2 * stages + 4) * 8 + 16 +
-                             2 * (size_t)bias_slots * d->bn * 4 + 64;
     // bf16 outputs leave through shared memory + TMA store (coalesced, clipped by the tensor map) when the
     // 64-channel slabs of an N tile never spill into the next tile's channels
     p.n_staging = 0;
     bool tma_out = d->epi == HN_EPI_STD && !d->out_fp32 && !d->group_addr && (n_tiles == 1 || d->bn % 64 == 0) &&
                    (!d->flat || d->out_stride_n == (int64_t)d->flat_hw * d->out_stride_x);
-    if (tma_out && base_smem + kATileBytes <= 227 * 1024) {
-        p.n_staging = (base_smem + 2 * kATileBytes <= 227 * 1024) ? 2 : 1;
+    const size_t fixed_smem = 1024 + (2 * 8 + 4) * 8 + 16 + 2 * (size_t)bias_slots * d->bn * 4 + 64;
+    // Tap runs: consecutive taps that differ only by dy = +1 read row-shifted windows of ONE (TH+2)-row A box, so a
+    // 3x3 window costs 3 box loads (3.75 tiles' worth of bytes) instead of 9 tile loads.  A window starts dy*TW rows
+    // into the box; with TW % 8 == 0 that is a whole number of 1024-byte swizzle atoms, so the shifted window is
+    // still a canonical K-major SWIZZLE_128B operand.  Narrow N tiles are bound by exactly this L2 -> shared-memory
+    // traffic.  The ring then holds fewer, fatter stages (one run each); runs are used when two such stages plus
+    // one output staging slab fit next to a second CTA on the SM (narrow tiles) or in the SM (wide tiles).
+    p.run_max = 1;
+    p.a_stage_bytes = kATileBytes;
+    size_t smem_cap = 227 * 1024;
+    if (g_conv_runs && !d->flat && TW % 8 == 0) {
+        // candidate order: runs adjacent (dy innermost), and consecutive runs one pixel apart (dx next)
+        int order[HN_MAX_TAPS];
+        for (int k = 0; k < d->num_taps; ++k) order[k] = k;
+        auto key_less = [&](int a, int b) {
+            const hn_tap &x = d->taps[a], &y = d->taps[b];
+            if (x.src != y.src) return x.src < y.src;
+            if (x.c0 != y.c0) return x.c0 < y.c0;
+            if (x.dx != y.dx) return x.dx < y.dx;
+            return x.dy < y.dy;
+        };
+        std::stable_sort(order, order + d->num_taps, key_less);
+        int n_runs = 0, longest = 1, shortest = kMaxRun;
+        uint8_t run_len[HN_MAX_TAPS];
+        for (int k = 0; k < d->num_taps;) {
+            int r = 1;
+            const hn_tap& t0 = d->taps[order[k]];
+            while (r < kMaxRun && k + r < d->num_taps) {
+                const hn_tap& t1 = d->taps[order[k + r]];
+                if (t1.src != t0.src || t1.dx != t0.dx || t1.c0 != t0.c0 || t1.dy != t0.dy + r) break;
+                ++r;
+            }
+            run_len[k] = (uint8_t)r;
+            if (r > longest) longest = r;
+            if (r < shortest) shortest = r;
+            k += r;
+            ++n_runs;
+        }
+        const size_t run_stage = (size_t)(TH + kMaxRun - 1) * TW * 128 + (size_t)kMaxRun * b_rows_cta * 128;
+        // default policy: narrow N tiles (bound by L2 -> shared-memory traffic), and the big plain 3x3 layers on CTA
+        // pairs; wide tiles with 2-tap runs (the parity-collapsed up-convolutions) are MMA-bound and only lose
+        // pipeline granularity
+        const bool want = longest > 1 && (g_conv_runs > 1 || d->bn <= 64 || (cs == 2 && shortest == kMaxRun && d->num_taps >= 36));
+        const bool two_per_sm = d->bn <= 128 && 2 * p.tmem_cols <= 512;
+        const size_t cap = two_per_sm ? (227 * 1024) / 2 - 1024 : 227 * 1024;
+        const size_t avail = cap - fixed_smem - (tma_out ? kATileBytes : 0);
+        if (want && 2 * run_stage <= avail) {
+            p.run_max = kMaxRun;
+            p.a_stage_bytes = (TH + kMaxRun - 1) * TW * 128;
+            for (int k = 0; k < d->num_taps; ++k) {
+                p.taps[k] = d->taps[order[k]];
+                p.taps[k].rsv0 = 1;
+                p.taps[k].rsv1 = (int16_t)order[k];
+            }
+            for (int k = 0; k < d->num_taps; k += run_len[k]) p.taps[k].rsv0 = (int8_t)run_len[k];
+            for (int i = 0; i < d->n_src; ++i) {
+                int rc4 = encode_view_map(&p.tmArun[i], d->src[i], TW, TH + kMaxRun - 1);
+                if (rc4) return rc4;
+            }
+            stages = (int)(avail / run_stage);
+            if (stages > n_runs) stages = n_runs < 2 ? 2 : n_runs;
+            if (stages > 8) stages = 8;
+            p.stages = stages;
+            smem_cap = cap;
+        }
+    }
+    const size_t base_smem = 1024 + (size_t)stages * (p.a_stage_bytes + (size_t)p.run_max * b_rows_cta * 128) +
+                             (2 * stages + 4) * 8 + 16 + 2 * (size_t)bias_slots * d->bn * 4 + 64;
+    if (tma_out && base_smem + kATileBytes <= smem_cap) {
+        p.n_staging = (base_smem + 2 * kATileBytes <= smem_cap) ? 2 : 1;
         hn_view ov;
         if (d->flat) {
             ov.ptr = d->out; ov.N = 1; ov.H = 1; ov.W = p.flat_m; ov.C = d->cout;

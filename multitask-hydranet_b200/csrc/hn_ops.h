@@ -4,6 +4,8 @@
 
 struct alignas(64) ConvParams {
     CUtensorMap tmA[HN_MAX_SRC];
+    CUtensorMap tmArun[HN_MAX_SRC];  // the same views with a (TH + 2)-row box: one load feeds a run of dy taps
+    int run_max, a_stage_bytes;      // taps per ring stage (1 or 3), bytes of a stage's A region
     CUtensorMap tmB;
     CUtensorMap tmBpart;  // B tile slice of bn/cluster rows (cluster multicast)
     int cluster;          // CTAs per cluster sharing the weight tile (1, 2 or 4)

@@ -134,7 +134,7 @@ struct DetWs {
     size_t cub2_bytes;
     void* cub2_tmp;
 };
-static constexpr int kCellStride = 8192;  // >= kGridHeads, power of two
+static constexpr int kCellStride = 32768;  // >= kGridHeads, power of two
 static constexpr int kMaxPreds = 64;
 
 static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
@@ -145,7 +145,11 @@ static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
 // heights are each within a factor 1/thr, so a candidate only visits levels within +-delta of its own
 // and the cells its extent (grown by one cell) touches: exact pruning, not an approximation.
 static constexpr int kGridLevels = 8;
-static constexpr int kGridHeads = 6144;
+static constexpr int kGridHeads = 24576;
+// A level's cells are kGridFX x kGridFY per (level size)^2: narrow in x, where a window row is ONE contiguous index
+// range whatever the cell width, so finer cells cost nothing and trim the scan to the window; in y every extra
+// row is an extra range.
+static constexpr float kGridFX = 4.0f, kGridFY = 2.0f;
 struct GridGeom {
     int nlev, delta, prune;
     float c0;
@@ -164,7 +168,7 @@ static GridGeom make_grid(int img_h, int img_w, float iou_thr) {
     int off = 0;
     for (int l = 0; l < kGridLevels; ++l) {
         float c = c0 * (float)(1 << l);
-        int nx = (int)(img_w / c) + 2, ny = (int)(img_h / c) + 2;
+        int nx = (int)(img_w * kGridFX / c) + 2, ny = (int)(img_h * kGridFY / c) + 2;
         if (l == kGridLevels - 1) nx = ny = 1;  // unbounded sizes: one bucket
         if (off + nx * ny > kGridHeads) { nx = ny = 1; }
         g.nx[l] = nx; g.ny[l] = ny; g.base[l] = off;
@@ -418,10 +422,10 @@ __global__ void __launch_bounds__(kNmsChunk) hn_det_nms_kernel(DetWs ws, int A, 
                     int x_lo = 0, x_hi = 0, y_lo = 0, y_hi = 0;
                     if (nx * ny > 1) {
                         const float rx = g.rfac * (0.5f * fmaxf(wj, 0.0f) + cl) + 1.0f, ry = g.rfac * (0.5f * fmaxf(hj, 0.0f) + cl) + 1.0f;
-                        x_lo = clampi((int)floorf((cx - rx) * inv), 0, nx - 1);
-                        x_hi = clampi((int)floorf((cx + rx) * inv), 0, nx - 1);
-                        y_lo = clampi((int)floorf((cy - ry) * inv), 0, ny - 1);
-                        y_hi = clampi((int)floorf((cy + ry) * inv), 0, ny - 1);
+                        x_lo = clampi((int)floorf((cx - rx) * inv * kGridFX), 0, nx - 1);
+                        x_hi = clampi((int)floorf((cx + rx) * inv * kGridFX), 0, nx - 1);
+                        y_lo = clampi((int)floorf((cy - ry) * inv * kGridFY), 0, ny - 1);
+                        y_hi = clampi((int)floorf((cy + ry) * inv * kGridFY), 0, ny - 1);
                     }
                     for (int yy = y_lo; yy <= y_hi && alive; ++yy) {
                         for (int xx = x_lo; xx <= x_hi && alive; ++xx) {
@@ -499,7 +503,7 @@ __global__ void __launch_bounds__(kNmsChunk) hn_det_nms_kernel(DetWs ws, int A, 
                     const float inv = 1.0f / (g.c0 * (float)(1 << l));
                     int cell = g.base[l];
                     if (g.nx[l] * g.ny[l] > 1)
-                        cell += clampi((int)floorf(cy * inv), 0, g.ny[l] - 1) * g.nx[l] + clampi((int)floorf(cx * inv), 0, g.nx[l] - 1);
+                        cell += clampi((int)floorf(cy * inv * kGridFY), 0, g.ny[l] - 1) * g.nx[l] + clampi((int)floorf(cx * inv * kGridFX), 0, g.nx[l] - 1);
                     kept_next[slot] = atomicExch(&heads[cell], slot);
                 }
             }
@@ -534,7 +538,7 @@ __device__ __forceinline__ int grid_cell(const float4& b, float offset, const Gr
     const float inv = 1.0f / (g.c0 * (float)(1 << l));
     int cell = g.base[l];
     if (g.nx[l] * g.ny[l] > 1)
-        cell += clampi((int)floorf(cy * inv), 0, g.ny[l] - 1) * g.nx[l] + clampi((int)floorf(cx * inv), 0, g.nx[l] - 1);
+        cell += clampi((int)floorf(cy * inv * kGridFY), 0, g.ny[l] - 1) * g.nx[l] + clampi((int)floorf(cx * inv * kGridFX), 0, g.nx[l] - 1);
     return cell;
 }
 
@@ -607,10 +611,10 @@ __global__ void __launch_bounds__(256) hn_nms2_build_kernel(DetWs ws, long long 
         int x_lo = 0, x_hi = 0, y_lo = 0, y_hi = 0;
         if (nx * ny > 1) {
             const float rx = g.rfac * (0.5f * fmaxf(wj, 0.0f) + cl) + 1.0f, ry = g.rfac * (0.5f * fmaxf(hj, 0.0f) + cl) + 1.0f;
-            x_lo = clampi((int)floorf((cx - rx) * inv), 0, nx - 1);
-            x_hi = clampi((int)floorf((cx + rx) * inv), 0, nx - 1);
-            y_lo = clampi((int)floorf((cy - ry) * inv), 0, ny - 1);
-            y_hi = clampi((int)floorf((cy + ry) * inv), 0, ny - 1);
+            x_lo = clampi((int)floorf((cx - rx) * inv * kGridFX), 0, nx - 1);
+            x_hi = clampi((int)floorf((cx + rx) * inv * kGridFX), 0, nx - 1);
+            y_lo = clampi((int)floorf((cy - ry) * inv * kGridFY), 0, ny - 1);
+            y_hi = clampi((int)floorf((cy + ry) * inv * kGridFY), 0, ny - 1);
         }
         for (int yy = y_lo; yy <= y_hi; ++yy) {
             const uint32_t k0 = (uint32_t)seg * kCellStride + (uint32_t)(g.base[l] + yy * nx + x_lo);

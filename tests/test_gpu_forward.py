@@ -164,15 +164,42 @@ def test_cluster_multicast_equals_single_cta():
     _, m_gpu, sd = _models(cfg)
     x = synth.synth_input(3, 256, 256, seed=13).cuda()
     outs = []
-    for cs in (1, 2):
-        nv.lib.hn_conv_set_cluster(cs)
-        try:
+    nv.lib.hn_conv_set_tap_runs(0)  # the run policy depends on the pairing and changes the K order (fp32 summation order)
+    try:
+        for cs in (1, 2):
+            nv.lib.hn_conv_set_cluster(cs)
             m_gpu._plans = {}
             with torch.no_grad():
                 o = m_gpu(x)
             outs.append({"seg": o["seg"].clone(), "reg": o["detection"]["regression"].clone(), "loc": o["lane"]["predict_loc"].clone()})
-        finally:
-            nv.lib.hn_conv_set_cluster(0)
+    finally:
+        nv.lib.hn_conv_set_cluster(0)
+        nv.lib.hn_conv_set_tap_runs(1)
     m_gpu._plans = {}
     for k in outs[0]:
         assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+def test_tap_runs_equal_tap_per_stage():
+    """Row-shared A boxes (one TMA box feeding a run of dy taps) against one box per tap: the same products, summed
+    in a different K order, so the head tensors agree to accumulation-order noise amplified by the bf16 roundings downstream (inside the 1e-2 budget)."""
+    from hydranet_b200 import _native as nv
+    cfg = big_cfg(256, 256)
+    _, m_gpu, sd = _models(cfg)
+    x = synth.synth_input(2, 256, 256, seed=17).cuda()
+    outs = []
+    try:
+        for mode in (0, 2):
+            nv.lib.hn_conv_set_tap_runs(mode)
+            m_gpu._plans = {}
+            with torch.no_grad():
+                o = m_gpu(x)
+            outs.append({"seg": o["seg"].clone(), "reg": o["detection"]["regression"].clone(),
+                         "cls": o["detection"]["classification"].clone(), "loc": o["lane"]["predict_loc"].clone()})
+    finally:
+        nv.lib.hn_conv_set_tap_runs(1)
+    m_gpu._plans = {}
+    for k in outs[0]:
+        a, b = outs[0][k].float(), outs[1][k].float()
+        assert torch.isfinite(b).all()
+        assert (a - b).abs().max().item() <= 1e-2 * a.abs().max().item(), k
