@@ -130,7 +130,6 @@ struct DetWs {
     int* changed;        // [8] worklist sizes (ping-pong), round counter
     int* wl_a;           // [N*A] undecided boxes, ping
     int* wl_b;           // [N*A] pong
-    int* cell_list;      // [N*A] first cell-order index of every non-empty cell (changed[3] = how many)
     size_t cub2_bytes;
     void* cub2_tmp;
 };
@@ -231,7 +230,6 @@ static size_t det_layout(int N, int A, void* base, DetWs* ws) {
     w.changed = reinterpret_cast<int*>(take(64));
     w.wl_a = reinterpret_cast<int*>(take(NA * 4));
     w.wl_b = reinterpret_cast<int*>(take(NA * 4));
-    w.cell_list = reinterpret_cast<int*>(take(NA * 4));
     {
         size_t b1 = 0, b2 = 0;
         cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr);
@@ -570,7 +568,6 @@ __global__ void hn_nms2_cells_kernel(DetWs ws, long long NA) {
     const uint32_t ck = ws.ckey[q];
     if (ck == 0xFFFFFFFFu) return;
     ws.cbox[q] = ws.sbox[ws.cval[q]];
-    if (q == 0 || ws.ckey[q - 1] != ck) ws.cell_list[atomicAdd(ws.changed + 3, 1)] = (int)q;
 }
 
 // Conflict-graph construction, one thread per candidate, candidates taken in CELL order.  Cells of one grid row
@@ -686,15 +683,19 @@ __global__ void hn_nms2_seed_kernel(DetWs ws, long long NA) {
 __global__ void __launch_bounds__(256) hn_nms2_rounds_kernel(DetWs ws, long long NA) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
-    volatile int* cnt = ws.changed;  // [0] = size of the current list, [1] = size of the next list
+    // three rotating worklist counters: [r % 3] = size of the current list, [(r+1) % 3] = the list being built,
+    // [(r+2) % 3] = reset now for the round after next -- so one grid barrier per round is enough
+    volatile int* cnt = ws.changed;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int* cur = ws.wl_a;
     int* nxt = ws.wl_b;
     int round = 0;
     while (true) {
-        const int n_cur = cnt[round & 1];
+        const int c_cur = round % 3, c_nxt = (round + 1) % 3, c_clr = (round + 2) % 3;
+        const int n_cur = cnt[c_cur];
         if (n_cur == 0) break;
+        if (tid0 == 0) ws.changed[c_clr] = 0;
         const long long n_pad = ((long long)n_cur + 31) & ~31ll;  // whole warps iterate together (ballot below)
         for (long long w = tid0; w < n_pad; w += stride) {
             bool carry = false;
@@ -702,12 +703,17 @@ __global__ void __launch_bounds__(256) hn_nms2_rounds_kernel(DetWs ws, long long
             if (w < n_cur) {
                 i = __ldcg(cur + w);
                 const int np = ws.npred[i];
-                const int* my = ws.preds + (long long)i * kMaxPreds;
+                const int4* my = reinterpret_cast<const int4*>(ws.preds + (long long)i * kMaxPreds);
                 bool kept_pred = false, all_supp = true;
-                for (int k = 0; k < np; ++k) {
-                    const unsigned char st = __ldcg(ws.status + my[k]);
-                    if (st == 1) { kept_pred = true; break; }
-                    if (st == 0) all_supp = false;
+                // four predecessors at a time: their status loads are independent (the loop is latency-bound)
+                for (int k = 0; k < np && !kept_pred; k += 4) {
+                    const int4 pr = __ldcg(my + (k >> 2));
+                    const unsigned char s0 = __ldcg(ws.status + pr.x);
+                    const unsigned char s1 = k + 1 < np ? __ldcg(ws.status + pr.y) : (unsigned char)2;
+                    const unsigned char s2 = k + 2 < np ? __ldcg(ws.status + pr.z) : (unsigned char)2;
+                    const unsigned char s3 = k + 3 < np ? __ldcg(ws.status + pr.w) : (unsigned char)2;
+                    kept_pred = s0 == 1 || s1 == 1 || s2 == 1 || s3 == 1;
+                    if (s0 == 0 || s1 == 0 || s2 == 0 || s3 == 0) all_supp = false;
                 }
                 if (kept_pred) ws.status[i] = 2;
                 else if (all_supp) ws.status[i] = 1;
@@ -718,18 +724,16 @@ __global__ void __launch_bounds__(256) hn_nms2_rounds_kernel(DetWs ws, long long
             if (m) {
                 const unsigned lane = threadIdx.x & 31;
                 int base = 0;
-                if (lane == 0) base = atomicAdd(ws.changed + ((round + 1) & 1), __popc(m));
+                if (lane == 0) base = atomicAdd(ws.changed + c_nxt, __popc(m));
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (carry) nxt[base + __popc(m & ((1u << lane) - 1u))] = i;
             }
         }
-        grid.sync();
-        if (tid0 == 0) ws.changed[round & 1] = 0;  // becomes the "next" counter of the following round
         int* t = cur; cur = nxt; nxt = t;
         ++round;
         grid.sync();
     }
-    if (tid0 == 0) ws.changed[2] = round;  // diagnostics: number of rounds
+    if (tid0 == 0) ws.changed[4] = round;  // diagnostics: number of rounds
     for (long long i = tid0; i < NA; i += stride) ws.kflag[i] = __ldcg(ws.status + i) == 1 ? 1 : 0;
 }
 
