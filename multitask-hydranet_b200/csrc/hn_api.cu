@@ -15,6 +15,9 @@ void hn_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+int g_hn_pdl = 0;  // measured on B200 (batch 32, graph replay): 10.37 ms/step with PDL edges vs 10.06 without -> off by default
+extern "C" void hn_set_pdl(int on) { g_hn_pdl = on ? 1 : 0; }
+
 extern "C" const char* hn_last_error(void) { return g_err; }
 extern "C" int hn_version(void) { return 100; }
 extern "C" int hn_device_sm_count(void) {

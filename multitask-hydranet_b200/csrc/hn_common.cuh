@@ -94,6 +94,15 @@ __device__ __forceinline__ void hn_mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!done);
 }
 
+// ---- programmatic dependent launch ----
+// With hn_set_pdl(1) every kernel of the forward plan is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may
+// be scheduled while the previous kernel's last CTAs are still running, run their prologue (barrier init, TMEM
+// allocation, descriptor prefetch, index math) and then block in hn_pdl_wait() until the previous grid has
+// completed and its writes are visible.  NOTHING produced by an earlier kernel may be read, and nothing an earlier
+// kernel may still read may be written, before hn_pdl_wait().
+__device__ __forceinline__ void hn_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void hn_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- TMA ----
 __device__ __forceinline__ void hn_tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tmap) : "memory");
@@ -280,3 +289,21 @@ __device__ __forceinline__ float2 hn_unpack_bf16x2(uint32_t u) {
 }
 
 #endif  // __CUDACC__
+
+// host: launch with the programmatic-serialization attribute (hn_set_pdl(0) turns it into a plain launch)
+extern int g_hn_pdl;
+template <typename... KArgs, typename... Args>
+static inline cudaError_t hn_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_hn_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}

@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(kCtaThreads) hn_conv_gemm_kernel(const __grid_
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    hn_pdl_launch_dependents();
     // persistent loop over work items, one item per CTA (or per CTA pair) per iteration
     constexpr int CS = kPair ? 2 : 1;  // 2: CTA pair driving one 256-row cta_group::2 MMA
     constexpr bool PAIR = kPair;
@@ -264,6 +265,8 @@ __global__ void __launch_bounds__(kCtaThreads) hn_conv_gemm_kernel(const __grid_
     hn_tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (dbg && threadIdx.x == 0) dbg[1] = hn_globaltimer();
+    // prologue done (it overlapped the previous kernel's tail): from here on we read what that kernel wrote
+    hn_pdl_wait();
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
@@ -787,7 +790,7 @@ int hn_conv_launch(const ConvLaunch* L, cudaStream_t stream) {
     });
     HN_CHECK_CUDA(attr_err);
     if (L->cluster <= 1) {
-        hn_conv_gemm_kernel<false><<<L->grid, kCtaThreads, L->smem, stream>>>(L->prm);
+        HN_CHECK_CUDA(hn_launch(hn_conv_gemm_kernel<false>, L->grid, dim3(kCtaThreads), L->smem, stream, L->prm));
         HN_CHECK_CUDA(cudaGetLastError());
         return HN_OK;
     }
@@ -797,13 +800,15 @@ int hn_conv_launch(const ConvLaunch* L, cudaStream_t stream) {
     cfg.blockDim = dim3(kCtaThreads);
     cfg.dynamicSmemBytes = L->smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)L->cluster;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_hn_pdl ? 2 : 1;
     HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, hn_conv_gemm_kernel<true>, L->prm));
     return HN_OK;
 }

@@ -52,6 +52,8 @@ __device__ __forceinline__ const bf16* vptr(const View& v, int n, int y, int x, 
 __global__ void __launch_bounds__(128) hn_stem_kernel(const float* __restrict__ x, int N, int H, int W,
                                                       const float* __restrict__ w, const float* __restrict__ b,
                                                       View out) {
+    hn_pdl_launch_dependents();
+    hn_pdl_wait();
     __shared__ float sw[27 * 32];
     __shared__ float sb[32];
     for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = w[i];
@@ -107,8 +109,8 @@ extern "C" int hn_stem_fwd(const hn_stem_desc* d, void* stream) {
                d->H, d->W);
     long long total = (long long)d->N * d->out.H * d->out.W;
     HN_REQUIRE(total < 0x7fffffffLL, "stem: too many output pixels for one launch");
-    hn_stem_kernel<<<hn_cdiv(total, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d->x, d->N, d->H, d->W, d->w,
-                                                                                          d->b, to_view(d->out));
+    HN_CHECK_CUDA(hn_launch(hn_stem_kernel, dim3(hn_cdiv(total, 128)), dim3(128), (size_t)(0), reinterpret_cast<cudaStream_t>(stream), d->x, d->N, d->H, d->W, d->w,
+                                                                                          d->b, to_view(d->out)));
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }
@@ -180,6 +182,8 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 static constexpr int kNodeBatch = 6;
 template <int kNin, bool kPoolLast>
 __global__ void __launch_bounds__(512) hn_node_kernel(const __grid_constant__ NodeParams p) {
+    hn_pdl_launch_dependents();
+    hn_pdl_wait();
     extern __shared__ float s_tile[];  // [kNodeHH * kNodeHW][CB] fused values
     constexpr int kDirect = kPoolLast ? kNin - 1 : kNin;
     const int C = p.out.C;
@@ -348,6 +352,8 @@ __device__ __forceinline__ void dw_strip(const View& in, const View& out, const 
 }
 
 __global__ void __launch_bounds__(256) hn_dw_kernel(View in, View out, const float* __restrict__ dw) {
+    hn_pdl_launch_dependents();
+    hn_pdl_wait();
     const int CV = out.C >> 3, WB = (out.W + kDwPx - 1) / kDwPx;
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned total = (unsigned)out.N * out.H * WB * CV;
@@ -369,6 +375,8 @@ struct DwMultiParams {
     const float* dw;
 };
 __global__ void __launch_bounds__(256) hn_dw_multi_kernel(const __grid_constant__ DwMultiParams p) {
+    hn_pdl_launch_dependents();
+    hn_pdl_wait();
     unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.end[p.n - 1]) return;
     int g = 0;
@@ -405,7 +413,7 @@ extern "C" int hn_dw_multi_fwd(const hn_dw_multi_desc* d, void* stream) {
         HN_REQUIRE(total < 0x7fffffffLL, "dw_multi: too many work items");
         p.end[i] = (unsigned)total;
     }
-    hn_dw_multi_kernel<<<hn_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    HN_CHECK_CUDA(hn_launch(hn_dw_multi_kernel, dim3(hn_cdiv(total, 256)), dim3(256), (size_t)(0), reinterpret_cast<cudaStream_t>(stream), p));
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }
@@ -438,7 +446,7 @@ extern "C" int hn_node_fwd(const hn_node_desc* d, void* stream) {
     if (d->n_in == 1 && d->mode[0] == HN_IN_SAME && !d->swish && d->w[0] == 1.0f) {
         long long total = (long long)d->out.N * d->out.H * ((d->out.W + kDwPx - 1) / kDwPx) * (d->out.C / 8);
         HN_REQUIRE(total < 0x7fffffffLL, "node: too many work items for one launch");
-        hn_dw_kernel<<<hn_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p.in[0], p.out, d->dw);
+        HN_CHECK_CUDA(hn_launch(hn_dw_kernel, dim3(hn_cdiv(total, 256)), dim3(256), (size_t)(0), reinterpret_cast<cudaStream_t>(stream), p.in[0], p.out, d->dw));
         HN_CHECK_CUDA(cudaGetLastError());
         return HN_OK;
     }
@@ -466,7 +474,7 @@ extern "C" int hn_node_fwd(const hn_node_desc* d, void* stream) {
         default: kern = hn_node_kernel<3, true>; break;
     }
     if (smem > 48 * 1024) HN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(tiles * d->out.N, split), dim3(CB, kNodeRows), smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    HN_CHECK_CUDA(hn_launch(kern, dim3(tiles * d->out.N, split), dim3(CB, kNodeRows), smem, reinterpret_cast<cudaStream_t>(stream), p));
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }
@@ -492,6 +500,8 @@ __device__ __forceinline__ void pool_neginf(const View& v, int n, int y, int x, 
 }
 
 __global__ void hn_pool_kernel(View in, View out, int mode) {
+    hn_pdl_launch_dependents();
+    hn_pdl_wait();
     const int CV = out.C >> 3;
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned total = (unsigned)out.N * out.H * out.W * CV;
@@ -519,8 +529,8 @@ extern "C" int hn_pool_fwd(const hn_pool_desc* d, void* stream) {
         HN_REQUIRE((d->in.H - 1) / 2 + 1 == d->out.H && (d->in.W - 1) / 2 + 1 == d->out.W, "pool: size mismatch");
     long long total = (long long)d->out.N * d->out.H * d->out.W * (d->out.C / 8);
     HN_REQUIRE(total < 0x7fffffffLL, "pool: too many work items for one launch");
-    hn_pool_kernel<<<hn_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(to_view(d->in), to_view(d->out),
-                                                                                          d->mode);
+    HN_CHECK_CUDA(hn_launch(hn_pool_kernel, dim3(hn_cdiv(total, 256)), dim3(256), (size_t)(0), reinterpret_cast<cudaStream_t>(stream), to_view(d->in), to_view(d->out),
+                                                                                          d->mode));
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }
@@ -534,6 +544,8 @@ struct LaneFuseParams {
 };
 
 __global__ void hn_lanefuse_kernel(const __grid_constant__ LaneFuseParams p) {
+    hn_pdl_launch_dependents();
+    hn_pdl_wait();
     const int C = p.p3.C, CV = C >> 3;
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned total = (unsigned)p.out.N * p.out.H * p.out.W * 4 * CV;
@@ -602,7 +614,7 @@ extern "C" int hn_lanefuse_fwd(const hn_lanefuse_desc* d, void* stream) {
     p.stride = d->stride;
     long long total = (long long)d->out.N * d->out.H * d->out.W * 4 * (d->p3.C / 8);
     HN_REQUIRE(total < 0x7fffffffLL, "lanefuse: too many work items for one launch");
-    hn_lanefuse_kernel<<<hn_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    HN_CHECK_CUDA(hn_launch(hn_lanefuse_kernel, dim3(hn_cdiv(total, 256)), dim3(256), (size_t)(0), reinterpret_cast<cudaStream_t>(stream), p));
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }
@@ -615,6 +627,8 @@ static constexpr int kSeThreads = 512;
 
 __global__ void __launch_bounds__(kSeThreads) hn_se_pool_kernel(View x, float* __restrict__ partial, int* __restrict__ counter,
                                                                 bf16* __restrict__ mean_out, float inv_hw, int kSePix) {
+    hn_pdl_launch_dependents();
+    hn_pdl_wait();
     extern __shared__ float sm[];  // [lanes][C] partial sums
     __shared__ int s_last;
     const int C = x.C, CV = C >> 3;
@@ -668,6 +682,8 @@ __global__ void __launch_bounds__(kSeThreads) hn_se_pool_kernel(View x, float* _
 }
 
 __global__ void hn_se_scale_kernel(View x, const bf16* __restrict__ scale) {
+    hn_pdl_launch_dependents();
+    hn_pdl_wait();
     const int CV = x.C >> 3;
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned total = (unsigned)x.N * x.H * x.W * CV;
@@ -697,8 +713,8 @@ extern "C" int hn_se_pool_fwd(const hn_se_pool_desc* d, void* stream) {
     int lanes = kSeThreads / CV;
     size_t smem = (size_t)lanes * C * sizeof(float);
     HN_REQUIRE(smem <= 48 * 1024, "se_pool: shared memory");
-    hn_se_pool_kernel<<<grid, kSeThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-        to_view(d->x), d->partial, d->counter, reinterpret_cast<bf16*>(d->mean), 1.0f / (float)HW, d->pix_per_block);
+    HN_CHECK_CUDA(hn_launch(hn_se_pool_kernel, dim3(grid), dim3(kSeThreads), (size_t)(smem), reinterpret_cast<cudaStream_t>(stream), 
+        to_view(d->x), d->partial, d->counter, reinterpret_cast<bf16*>(d->mean), 1.0f / (float)HW, d->pix_per_block));
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }
@@ -708,8 +724,8 @@ extern "C" int hn_se_scale_fwd(const hn_se_scale_desc* d, void* stream) {
     if (int rc = check_view(d->x, "se_scale.x")) return rc;
     long long total = (long long)d->x.N * d->x.H * d->x.W * (d->x.C / 8);
     HN_REQUIRE(total < 0x7fffffffLL, "se_scale: too many work items for one launch");
-    hn_se_scale_kernel<<<hn_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        to_view(d->x), reinterpret_cast<const bf16*>(d->scale));
+    HN_CHECK_CUDA(hn_launch(hn_se_scale_kernel, dim3(hn_cdiv(total, 256)), dim3(256), (size_t)(0), reinterpret_cast<cudaStream_t>(stream), 
+        to_view(d->x), reinterpret_cast<const bf16*>(d->scale)));
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }
