@@ -46,6 +46,13 @@ __device__ __forceinline__ void hn_tmem_ldN(uint32_t taddr, uint32_t (&v)[NC]) {
     else hn_tmem_ld16(taddr, v);
 }
 
+// n / d for a launch-constant divisor: magic = floor(2^64 / d) + 1 (0 stands for d == 1); exact for every 32-bit n
+// (the error term n * (magic*d - 2^64) stays below 2^64).  The per-tile index math runs in every epilogue thread of
+// every tile; hardware integer division costs ~20 (32-bit) to ~100 (64-bit) instructions.
+__device__ __forceinline__ unsigned hn_fastdiv(unsigned n, unsigned long long magic) {
+    return magic ? (unsigned)__umul64hi((unsigned long long)n, magic) : n;
+}
+
 // tile index -> origin
 struct TileOrigin {
     int n0, img, y0, x0;
@@ -54,16 +61,17 @@ struct TileOrigin {
 // (an m tile index past the end yields out-of-bounds coordinates: zero-filled loads, clipped / masked stores)
 __device__ __forceinline__ TileOrigin tile_origin(const ConvParams& p, int t, int rank) {
     TileOrigin o;
-    int nt = t / p.m_groups, mt = (t - nt * p.m_groups) * p.cluster + rank;
+    const int nt = (int)hn_fastdiv((unsigned)t, p.div_m_groups), mt = (t - nt * p.m_groups) * p.cluster + rank;
     o.n0 = nt * p.bn;
     if (p.flat) {
         o.img = 0; o.y0 = 0; o.x0 = mt * 128;
     } else {
-        int per_img = p.tiles_x * p.tiles_y;
-        o.img = mt / per_img;
-        int r = mt - o.img * per_img;
-        o.y0 = (r / p.tiles_x) * p.TH;
-        o.x0 = (r % p.tiles_x) * p.TW;
+        const int per_img = p.tiles_x * p.tiles_y;
+        o.img = (int)hn_fastdiv((unsigned)mt, p.div_per_img);
+        const int r = mt - o.img * per_img;
+        const int ry = (int)hn_fastdiv((unsigned)r, p.div_tiles_x);
+        o.y0 = ry * p.TH;
+        o.x0 = (r - ry * p.tiles_x) * p.TW;
     }
     return o;
 }
@@ -352,19 +360,31 @@ __global__ void __launch_bounds__(kCtaThreads) hn_conv_gemm_kernel(const __grid_
         int a = 0;
         uint32_t aph = 0;
         int ntile = 0, st_count = 0;
+        // bias (or per-row-group shift / scale) of output channels n0 .. n0+BN into one accumulator's slot
+        auto stage_bias = [&](float* dst, int n0) {
+            if (p.n_groups > 0 && p.group_shift) {
+                for (int i = et; i < p.n_groups * BN; i += kEpiThreads) {
+                    const int gi = i / BN, ci = i - gi * BN;
+                    dst[i] = p.group_shift[(long long)gi * p.gstride + n0 + ci];
+                    dst[p.n_groups * BN + i] = p.group_scale ? p.group_scale[(long long)gi * p.gstride + n0 + ci] : 1.0f;
+                }
+            } else {
+                for (int i = et; i < BN; i += kEpiThreads) dst[i] = p.bias ? p.bias[n0 + i] : 0.0f;
+            }
+        };
+        // a single N tile: every work item has the same channels -- stage once (a global-load round trip and a barrier
+        // less per tile, which is what bounds short-K tiles)
+        const bool bias_once = p.n_tiles == 1;
+        if (bias_once) {
+            stage_bias(s_bias, 0);
+            stage_bias(s_bias + bias_slots * BN, 0);
+            hn_named_bar_sync(1, kEpiThreads);
+        }
         for (int t = t_first; t < total_tiles; t += t_step, ++ntile) {
             const TileOrigin o = tile_origin(p, t, rank);
             float* bias_s = s_bias + a * bias_slots * BN;
             const float* scale_s = nullptr;
-            if (p.n_groups > 0 && p.group_shift) {
-                for (int i = et; i < p.n_groups * BN; i += kEpiThreads) {
-                    const int gi = i / BN, ci = i - gi * BN;
-                    bias_s[i] = p.group_shift[(long long)gi * p.gstride + o.n0 + ci];
-                    bias_s[p.n_groups * BN + i] = p.group_scale ? p.group_scale[(long long)gi * p.gstride + o.n0 + ci] : 1.0f;
-                }
-            } else {
-                for (int i = et; i < BN; i += kEpiThreads) bias_s[i] = p.bias ? p.bias[o.n0 + i] : 0.0f;
-            }
+            if (!bias_once) stage_bias(bias_s, o.n0);
             EpiRow e;
             e.ym1 = e.ym2 = e.xm1 = e.xm2 = kNoCoord;
             e.Y = e.X = 0;
@@ -386,13 +406,13 @@ __global__ void __launch_bounds__(kCtaThreads) hn_conv_gemm_kernel(const __grid_
                     e.off0 = (long long)e.n_i * p.osn + p.group_out_base[g] + pix * p.osx;
                     e.roff = 0;
                 } else {
-                    e.n_i = (int)(m / p.flat_hw);
+                    e.n_i = (int)hn_fastdiv((unsigned)m, p.div_flat_hw);  // m < flat_m < 2^31
                     long long pix = m - (long long)e.n_i * p.flat_hw;
                     e.off0 = (long long)e.n_i * p.osn + pix * p.osx;
                     e.roff = (long long)e.n_i * p.rsn + pix * p.rsx;
                 }
             } else {
-                int ty = row / p.TW, tx = row - ty * p.TW;
+                int ty = row >> p.tw_shift, tx = row - (ty << p.tw_shift);  // TW is a power of two (TH*TW == 128)
                 int y = o.y0 + ty, x = o.x0 + tx;
                 e.valid = (y < p.H) && (x < p.W) && (o.img < p.n_img);
                 e.n_i = o.img;
@@ -415,7 +435,7 @@ __global__ void __launch_bounds__(kCtaThreads) hn_conv_gemm_kernel(const __grid_
                     }
                 }
             }
-            hn_named_bar_sync(1, kEpiThreads);  // bias staged
+            if (!bias_once) hn_named_bar_sync(1, kEpiThreads);  // bias staged
             hn_mbar_wait(&bar_acc_full[a], aph);
             hn_tc_fence_after();
             if (dbg && ntile == 0 && et == 0) dbg[5] = hn_globaltimer();
@@ -428,7 +448,7 @@ __global__ void __launch_bounds__(kCtaThreads) hn_conv_gemm_kernel(const __grid_
             } else if (p.n_staging) {
                 // 64-channel slabs: registers -> swizzled shared-memory tile -> one TMA store per slab
                 for (int c = 0; c < BN; c += 64) {
-                    uint8_t* slab = sO + (st_count % p.n_staging) * kATileBytes;
+                    uint8_t* slab = sO + (st_count & (p.n_staging - 1)) * kATileBytes;  // n_staging is 1 or 2
                     if (et == 0) {
                         if (p.n_staging == 2) hn_tma_store_wait_read<1>(); else hn_tma_store_wait_read<0>();
                     }
@@ -666,13 +686,23 @@ int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L) {
     if (cs != 2 || d->bn < 192 || d->bn % 32 != 0 || m_tiles < 2 || d->epi != HN_EPI_STD) cs = 1;
     p.cluster = cs;
     p.m_groups = hn_cdiv(m_tiles, cs);
+    {
+        auto magic = [](long long dv) -> unsigned long long { return dv <= 1 ? 0ull : ~0ull / (unsigned long long)dv + 1ull; };
+        p.div_m_groups = magic(p.m_groups);
+        p.div_per_img = magic(d->flat ? 1 : (long long)p.tiles_x * p.tiles_y);
+        p.div_tiles_x = magic(d->flat ? 1 : p.tiles_x);
+        p.div_flat_hw = magic(d->flat ? p.flat_hw : 1);
+        p.tw_shift = 0;
+        while ((1 << p.tw_shift) < TW) ++p.tw_shift;
+        HN_REQUIRE((1 << p.tw_shift) == TW, "tile width %d must be a power of two", TW);
+    }
     int stages = d->stages;
     if (cs == 2) {
         int rc3 = encode_weight_map(&p.tmBpart, d->weight, d->w_rows, d->num_taps * 64, d->bn / 2);
         if (rc3) return rc3;
         // half-size B stages: room for a deeper ring
         int fit = (int)((227 * 1024 - 16 * 1024 - 6 * 1024) / (kATileBytes + d->bn * 64));
-        stages = d->num_taps < fit ? d->num_taps : fit;
+        stages = fit;  // the ring runs across tiles (persistent CTAs): its depth is not tied to the taps of one tile
         if (stages > 8) stages = 8;
         if (stages < 2) stages = 2;
         p.stages = stages;
@@ -685,6 +715,9 @@ int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L) {
     p.n_staging = 0;
     bool tma_out = d->epi == HN_EPI_STD && !d->out_fp32 && !d->group_addr && (n_tiles == 1 || d->bn % 64 == 0) &&
                    (!d->flat || d->out_stride_n == (int64_t)d->flat_hw * d->out_stride_x);
+    // a dense flat output of at most 32 channels: a warp's direct 16-byte stores already cover one contiguous span
+    // (32 rows x cout*2 bytes), so the staging slab, its two barriers and the TMA store would be pure overhead
+    if (d->flat && d->cout <= 32 && d->out_stride_x == d->cout) tma_out = false;
     const size_t fixed_smem = 1024 + (2 * 8 + 4) * 8 + 16 + 2 * (size_t)bias_slots * d->bn * 4 + 64;
     // Tap runs: consecutive taps that differ only by dy = +1 read row-shifted windows of ONE (TH+2)-row A box, so a
     // 3x3 window costs 3 box loads (3.75 tiles' worth of bytes) instead of 9 tile loads.  A window starts dy*TW rows
@@ -745,7 +778,6 @@ int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L) {
                 if (rc4) return rc4;
             }
             stages = (int)(avail / run_stage);
-            if (stages > n_runs) stages = n_runs < 2 ? 2 : n_runs;
             if (stages > 8) stages = 8;
             p.stages = stages;
             smem_cap = cap;
@@ -753,8 +785,12 @@ int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L) {
     }
     const size_t base_smem = 1024 + (size_t)stages * (p.a_stage_bytes + (size_t)p.run_max * b_rows_cta * 128) +
                              (2 * stages + 4) * 8 + 16 + 2 * (size_t)bias_slots * d->bn * 4 + 64;
+    // two staging slabs if that still leaves room for a second CTA on the SM (narrow tiles), else one, else whatever fits
+    const auto two_per_sm_ok = [&](size_t bytes) { return 2 * (bytes + 1024) <= 227 * 1024 && 2 * p.tmem_cols <= 512; };
     if (tma_out && base_smem + kATileBytes <= smem_cap) {
-        p.n_staging = (base_smem + 2 * kATileBytes <= smem_cap) ? 2 : 1;
+        if (two_per_sm_ok(base_smem + 2 * kATileBytes)) p.n_staging = 2;
+        else if (two_per_sm_ok(base_smem + kATileBytes)) p.n_staging = 1;
+        else p.n_staging = (base_smem + 2 * kATileBytes <= smem_cap) ? 2 : 1;
         hn_view ov;
         if (d->flat) {
             ov.ptr = d->out; ov.N = 1; ov.H = 1; ov.W = p.flat_m; ov.C = d->cout;

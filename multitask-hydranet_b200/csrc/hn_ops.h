@@ -15,6 +15,8 @@ struct alignas(64) ConvParams {
     int flat, TH, TW, n_img, H, W, tiles_x, tiles_y, flat_hw, flat_m;
     int num_taps, cout, bn, stages, tmem_cols;
     int m_tiles, n_tiles, acc_stride;
+    unsigned long long div_m_groups, div_per_img, div_tiles_x, div_flat_hw;  // hn_fastdiv magics
+    int tw_shift;                                                            // log2(TW)
     long long* dbg;  // optional per-CTA timestamps (globaltimer ns), 16 slots per CTA
     const float* bias;
     int act, epi;

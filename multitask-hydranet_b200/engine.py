@@ -306,7 +306,9 @@ def choose_stages(bn, ntaps):
     for a second co-resident CTA (227 KB and 512 TMEM columns per SM)."""
     stage = 16384 + bn * 128
     budget = (227 - 16 - 5) * 1024 if bn > 128 else (113 - 32 - 5) * 1024
-    return int(max(2, min(8, ntaps, budget // stage)))
+    # the ring runs across the tiles of a persistent CTA, so its depth is not capped by the taps of one tile: short-K
+    # layers are bound by bytes in flight (load latency x ring depth)
+    return int(max(2, min(8, budget // stage)))
 
 
 def choose_tile(H, W):
