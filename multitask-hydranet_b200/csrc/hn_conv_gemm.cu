@@ -112,9 +112,10 @@ static constexpr int kNoCoord = -2147483647;
 // 16-byte chunk j of the row lives at chunk (j ^ (row & 7)) -- the 128B swizzle the output tensor map expects.
 template <int NC>
 __device__ __forceinline__ void epi_chunk_std(const ConvParams& p, const EpiRow& e, const float* s_bias, const float* s_scale,
-                                              int c, int n0, uint32_t (&v)[NC], uint8_t* stage_row, int row) {
+                                              int c, int n0, uint32_t (&v)[NC], uint8_t* stage_row, int row, float* tr = nullptr) {
     const int n = n0 + c;
-    if (!e.valid || n >= p.cout) return;
+    if (n >= p.cout) return;                               // warp-uniform
+    if (!e.valid && !(p.out_fp32 && tr)) return;           // the transposing fp32 path needs the whole warp
     float f[NC];
     if (s_scale) {
 #pragma unroll
@@ -125,6 +126,25 @@ __device__ __forceinline__ void epi_chunk_std(const ConvParams& p, const EpiRow&
     }
     apply_act<NC>(f, p.act);
     if (p.out_fp32) {
+        if (tr) {
+            // fp32 head outputs ([.., HW*9, 4 or 9]: a row is 36 or 81 floats): a thread owns a ROW, so direct stores hit
+            // 32 different sectors per instruction.  Transpose the 32x32 block through the warp's scratch so that a store
+            // instruction writes 32 consecutive floats of one row.
+            const int lane = threadIdx.x & 31;
+#pragma unroll
+            for (int j = 0; j < NC; ++j) tr[lane * 33 + j] = f[j];
+            __syncwarp();
+            const int ncol = min(NC, p.cout - n);
+            float* outf = reinterpret_cast<float*>(p.out);
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr) {
+                const long long off = __shfl_sync(0xffffffffu, e.off0, rr);
+                const int ok = __shfl_sync(0xffffffffu, (int)e.valid, rr);
+                if (ok && lane < ncol) outf[off + n + lane] = tr[rr * 33 + lane];
+            }
+            __syncwarp();
+            return;
+        }
         float* outf = reinterpret_cast<float*>(p.out) + e.off0;
 #pragma unroll
         for (int j = 0; j < NC; ++j)
@@ -477,18 +497,19 @@ __global__ void __launch_bounds__(kCtaThreads) hn_conv_gemm_kernel(const __grid_
                     ++st_count;
                 }
             } else {
+                float* tr = p.tr_off ? reinterpret_cast<float*>(smem + p.tr_off) + (warp - 2) * (32 * 33) : nullptr;
                 int c = half * 32;
                 for (; c + 32 <= BN; c += 64) {
                     uint32_t v[32];
                     hn_tmem_ld32(t_row + c, v);
                     hn_tmem_ld_wait();
-                    epi_chunk_std<32>(p, e, bias_s, scale_s, c, o.n0, v, nullptr, row);
+                    epi_chunk_std<32>(p, e, bias_s, scale_s, c, o.n0, v, nullptr, row, tr);
                 }
                 if (c < BN) {  // a 16-column tail chunk (BN % 32 == 16)
                     uint32_t v[16];
                     hn_tmem_ld16(t_row + c, v);
                     hn_tmem_ld_wait();
-                    epi_chunk_std<16>(p, e, bias_s, scale_s, c, o.n0, v, nullptr, row);
+                    epi_chunk_std<16>(p, e, bias_s, scale_s, c, o.n0, v, nullptr, row, tr);
                 }
             }
             // all TMEM reads of this accumulator are complete: hand it back to the MMA issuer
@@ -804,6 +825,16 @@ int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L) {
         if (rc2) return rc2;
     }
     L->smem = base_smem + (size_t)p.n_staging * kATileBytes;
+    p.tr_off = 0;
+    if (d->out_fp32 && d->epi == HN_EPI_STD) {  // per-warp 32x33 transpose scratch for coalesced fp32 stores
+        const size_t tr_bytes = (size_t)(kEpiThreads / 32) * 32 * 33 * 4;
+        // offsets count from the 1024-byte aligned base; L->smem carries 1024 bytes of slack for that alignment
+        const size_t off = (L->smem - 1024 + 15) & ~size_t(15);
+        if (off + tr_bytes + 1024 <= 227 * 1024) {
+            p.tr_off = (int)off;
+            L->smem = off + tr_bytes + 1024;
+        }
+    }
     HN_REQUIRE(L->smem <= 227 * 1024, "conv needs %zu bytes of shared memory (> 227 KB): lower stages/bn", L->smem);
     // persistent grid: one CTA per SM, or two when shared memory and TMEM (512 columns) allow it
     int sms = hn_device_sm_count();

@@ -629,38 +629,59 @@ __global__ void __launch_bounds__(kSeThreads) hn_se_pool_kernel(View x, float* _
                                                                 bf16* __restrict__ mean_out, float inv_hw, int kSePix) {
     hn_pdl_launch_dependents();
     hn_pdl_wait();
-    extern __shared__ float sm[];  // [lanes][C] partial sums
+    extern __shared__ float sm[];  // [lanes][CG*8] partial sums of this CTA's channel group
     __shared__ int s_last;
     const int C = x.C, CV = C >> 3;
     const int n = blockIdx.y;
     const int HW = x.H * x.W;
     const int p0 = blockIdx.x * kSePix, p1 = min(p0 + kSePix, HW);
-    const int lanes = blockDim.x / CV;
-    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
-    if (pl < lanes) {
+    // blockIdx.z = channel group of CG 8-channel vectors: small maps with many channels (10x10x936) would otherwise
+    // leave each thread a long serial chain of dependent-latency loads on a handful of CTAs
+    const int CG = (CV + gridDim.z - 1) / gridDim.z, cv0 = blockIdx.z * CG;
+    const int lanes = blockDim.x / CG;
+    const int cvl = threadIdx.x % CG, pl = threadIdx.x / CG, cv = cv0 + cvl;
+    if (pl < lanes && cv < CV) {
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-        for (int px = p0 + pl; px < p1; px += lanes) {
-            int y = px / x.W, xx = px - y * x.W;
+        const bf16* base = x.ptr + n * x.sn + cv * 8;
+        int px = p0 + pl;
+        for (; px + 3 * lanes < p1; px += 4 * lanes) {  // four independent loads in flight
+            uint4 r[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int q = px + u * lanes, y = q / x.W, xx = q - y * x.W;
+                r[u] = *reinterpret_cast<const uint4*>(base + y * x.sy + xx * x.sx);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {  // same summation order as the one-at-a-time loop
+                const float2 a = hn_unpack_bf16x2(r[u].x), b = hn_unpack_bf16x2(r[u].y), c2 = hn_unpack_bf16x2(r[u].z),
+                             d2 = hn_unpack_bf16x2(r[u].w);
+                acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+                acc[4] += c2.x; acc[5] += c2.y; acc[6] += d2.x; acc[7] += d2.y;
+            }
+        }
+        for (; px < p1; px += lanes) {
+            const int y = px / x.W, xx = px - y * x.W;
             float f[8];
-            load8(vptr(x, n, y, xx, cv * 8), f);
+            load8(base + y * x.sy + xx * x.sx, f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] += f[j];
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sm[pl * C + cv * 8 + j] = acc[j];
+        for (int j = 0; j < 8; ++j) sm[(pl * CG + cvl) * 8 + j] = acc[j];
     }
     __syncthreads();
     const int nchunk = gridDim.x;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    for (int c = threadIdx.x; c < CG * 8; c += blockDim.x) {
+        if (cv0 * 8 + c >= C) break;
         float a = 0.0f;
-        for (int l = 0; l < lanes; ++l) a += sm[l * C + c];
-        partial[((long long)n * nchunk + blockIdx.x) * C + c] = a;  // fixed summation order: deterministic
+        for (int l = 0; l < lanes; ++l) a += sm[l * CG * 8 + c];
+        partial[((long long)n * nchunk + blockIdx.x) * C + cv0 * 8 + c] = a;  // fixed summation order: deterministic
     }
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(counter + n, 1) == nchunk - 1);
+    if (threadIdx.x == 0) s_last = (atomicAdd(counter + n, 1) == nchunk * (int)gridDim.z - 1);
     __syncthreads();
     if (!s_last) return;
     __threadfence();
@@ -709,9 +730,11 @@ extern "C" int hn_se_pool_fwd(const hn_se_pool_desc* d, void* stream) {
     const int C = d->x.C, CV = C / 8, HW = d->x.H * d->x.W;
     HN_REQUIRE(CV <= kSeThreads, "se_pool: C=%d too wide", C);
     HN_REQUIRE(d->pix_per_block >= 128 && d->pix_per_block % 128 == 0, "se_pool: pix_per_block must be a multiple of 128");
-    dim3 grid(hn_cdiv(HW, d->pix_per_block), d->x.N);
-    int lanes = kSeThreads / CV;
-    size_t smem = (size_t)lanes * C * sizeof(float);
+    const int gz = hn_cdiv(CV, 32);  // channel groups of at most 32 vectors (>= 16 pixel lanes per CTA)
+    const int CG = hn_cdiv(CV, gz);
+    dim3 grid(hn_cdiv(HW, d->pix_per_block), d->x.N, gz);
+    int lanes = kSeThreads / CG;
+    size_t smem = (size_t)lanes * CG * 8 * sizeof(float);
     HN_REQUIRE(smem <= 48 * 1024, "se_pool: shared memory");
     HN_CHECK_CUDA(hn_launch(hn_se_pool_kernel, dim3(grid), dim3(kSeThreads), (size_t)(smem), reinterpret_cast<cudaStream_t>(stream), 
         to_view(d->x), d->partial, d->counter, reinterpret_cast<bf16*>(d->mean), 1.0f / (float)HW, d->pix_per_block));

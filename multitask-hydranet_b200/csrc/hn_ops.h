@@ -16,6 +16,7 @@ struct alignas(64) ConvParams {
     int num_taps, cout, bn, stages, tmem_cols;
     int m_tiles, n_tiles, acc_stride;
     unsigned long long div_m_groups, div_per_img, div_tiles_x, div_flat_hw;  // hn_fastdiv magics
+    int tr_off;    // byte offset (from the aligned shared-memory base) of the fp32 transpose scratch, 0 = none
     int tw_shift;                                                            // log2(TW)
     long long* dbg;  // optional per-CTA timestamps (globaltimer ns), 16 slots per CTA
     const float* bias;
