@@ -167,6 +167,18 @@ typedef struct hn_se_scale_desc {
     const void* scale;
 } hn_se_scale_desc;
 
+/* Image pre-processing, the step in front of HydraNet.forward (model/demo.py:191-196 with imagenet_normalize
+ * demo.py:26-40; C++ twin deploy/hydranet_model.cpp:159-248): BGR -> RGB, cv2.resize (uint8 INTER_LINEAR in OpenCV's
+ * 11-bit fixed point; INTER_AREA for an exact 2x2 down-scale), (x/255 - mean)/std in float64 rounded to fp32,
+ * HWC -> planar.  Bit-exact against cv2 4.13 + numpy (oracle/preprocess_ref.py). */
+typedef struct hn_preprocess_desc {
+    const uint8_t* src;  /* [N] images of src_h x src_w x 3 (B,G,R), row pitch src_pitch bytes, image stride src_stride bytes */
+    int32_t N, src_h, src_w;
+    int64_t src_pitch, src_stride;
+    float* dst;          /* [N][3 (R,G,B)][dst_h][dst_w] fp32, contiguous: the `x` of HydraNet.forward */
+    int32_t dst_h, dst_w;
+} hn_preprocess_desc;
+
 /* Detection decode + NMS (detection_loss.py:7-108; torchvision.ops.boxes.batched_nms semantics). */
 #define HN_NMS_AUTO_CUDA 0 /* coordinate trick iff 4*n <= 100000 (torchvision boxes.py, CUDA tensors) */
 #define HN_NMS_AUTO_CPU 1  /* coordinate trick iff 4*n <= 4000 */
@@ -221,6 +233,7 @@ int hn_pool_fwd(const hn_pool_desc* d, void* stream);
 int hn_lanefuse_fwd(const hn_lanefuse_desc* d, void* stream);
 int hn_se_pool_fwd(const hn_se_pool_desc* d, void* stream);
 int hn_se_scale_fwd(const hn_se_scale_desc* d, void* stream);
+int hn_preprocess_fwd(const hn_preprocess_desc* d, void* stream);
 int hn_seg_argmax(const float* logits, int32_t N, int32_t C, int64_t HW, int64_t* out_i64, uint8_t* out_u8,
                   void* stream);
 int hn_u8_to_i64(const uint8_t* in, int64_t* out, int64_t n, void* stream);

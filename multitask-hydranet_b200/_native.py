@@ -78,6 +78,12 @@ class SeScaleDesc(C.Structure):
     _fields_ = [("x", View), ("scale", C.c_void_p)]
 
 
+class PreprocessDesc(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("N", C.c_int32), ("src_h", C.c_int32), ("src_w", C.c_int32),
+                ("src_pitch", C.c_int64), ("src_stride", C.c_int64), ("dst", C.c_void_p),
+                ("dst_h", C.c_int32), ("dst_w", C.c_int32)]
+
+
 class DetDesc(C.Structure):
     _fields_ = [("anchors", C.c_void_p), ("regression", C.c_void_p), ("classification", C.c_void_p),
                 ("N", C.c_int32), ("A", C.c_int32), ("ncls", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32),
@@ -108,6 +114,7 @@ SYMBOLS = {
     "hn_lanefuse_fwd": (C.c_int, [C.POINTER(LaneFuseDesc), _P]),
     "hn_se_pool_fwd": (C.c_int, [C.POINTER(SePoolDesc), _P]),
     "hn_se_scale_fwd": (C.c_int, [C.POINTER(SeScaleDesc), _P]),
+    "hn_preprocess_fwd": (C.c_int, [C.POINTER(PreprocessDesc), _P]),
     "hn_seg_argmax": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P]),
     "hn_u8_to_i64": (C.c_int, [_P, _P, C.c_int64, _P]),
     "hn_det_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),

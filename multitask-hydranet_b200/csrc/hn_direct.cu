@@ -752,3 +752,91 @@ extern "C" int hn_se_scale_fwd(const hn_se_scale_desc* d, void* stream) {
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// image pre-processing (demo.py:191-196): BGR u8 HWC -> resized, normalised fp32 planar RGB
+// ------------------------------------------------------------------------------------------------
+struct PreParams {
+    const uint8_t* src;
+    int N, sh, sw;
+    long long pitch, istride;
+    float* dst;
+    int dh, dw;
+    double scale_x, scale_y;  // 1 / (dst / src), as cv2 computes them
+    int area2;                // exact 2x2 down-scale: cv2 switches INTER_LINEAR to INTER_AREA
+};
+
+// cv2's fixed-point coefficient pair for one destination coordinate (resize.cpp, INTER_RESIZE_COEF_BITS = 11)
+__device__ __forceinline__ void pre_coeff(int d, double scale, int src, bool clamp_fraction, int& s, int& w0, int& w1) {
+    float f = (float)__dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5);  // separate multiply and subtract, as the host code does
+    s = (int)floorf(f);
+    f = __fsub_rn(f, (float)s);
+    if (clamp_fraction) {
+        if (s < 0) { f = 0.0f; s = 0; }
+        if (s >= src - 1) { f = 0.0f; s = src - 1; }
+    }
+    w0 = __float2int_rn(__fmul_rn(__fsub_rn(1.0f, f), 2048.0f));  // saturate_cast<short> = round half to even
+    w1 = __float2int_rn(__fmul_rn(f, 2048.0f));
+}
+
+__global__ void __launch_bounds__(256) hn_preprocess_kernel(const PreParams p) {
+    __shared__ float lut[3][256];  // value of every uint8 level per output channel (R, G, B), float64 arithmetic
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+        const int c = i >> 8, v = i & 255;
+        const double mean = c == 0 ? 0.485 : (c == 1 ? 0.456 : 0.406), sd = c == 0 ? 0.229 : (c == 1 ? 0.224 : 0.225);
+        lut[c][v] = (float)__ddiv_rn(__dsub_rn(__ddiv_rn((double)(float)v, 255.0), mean), sd);
+    }
+    __syncthreads();
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned total = (unsigned)p.N * p.dh * p.dw;
+    if (idx >= total) return;
+    const int x = (int)(idx % (unsigned)p.dw);
+    const int y = (int)((idx / (unsigned)p.dw) % (unsigned)p.dh);
+    const int n = (int)(idx / ((unsigned)p.dw * p.dh));
+    const uint8_t* img = p.src + (long long)n * p.istride;
+    int out[3];
+    if (p.area2) {
+        const uint8_t* r0 = img + (long long)(2 * y) * p.pitch + (long long)(2 * x) * 3;
+        const uint8_t* r1 = r0 + p.pitch;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) out[c] = ((int)r0[c] + (int)r0[3 + c] + (int)r1[c] + (int)r1[3 + c] + 2) >> 2;
+    } else {
+        int sx, ax0, ax1, sy, by0, by1;
+        pre_coeff(x, p.scale_x, p.sw, true, sx, ax0, ax1);
+        pre_coeff(y, p.scale_y, p.sh, false, sy, by0, by1);
+        const int sx1 = min(sx + 1, p.sw - 1);
+        const int y0 = min(max(sy, 0), p.sh - 1), y1 = min(max(sy + 1, 0), p.sh - 1);
+        const uint8_t* r0 = img + (long long)y0 * p.pitch;
+        const uint8_t* r1 = img + (long long)y1 * p.pitch;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int h0 = (int)r0[sx * 3 + c] * ax0 + (int)r0[sx1 * 3 + c] * ax1;
+            const int h1 = (int)r1[sx * 3 + c] * ax0 + (int)r1[sx1 * 3 + c] * ax1;
+            out[c] = (((by0 * (h0 >> 4)) >> 16) + ((by1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        }
+    }
+    const long long plane = (long long)p.dh * p.dw;
+    float* o = p.dst + (long long)n * 3 * plane + (long long)y * p.dw + x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c * plane] = lut[c][out[2 - c] & 255];  // plane c = R,G,B <- source byte 2-c
+}
+
+extern "C" int hn_preprocess_fwd(const hn_preprocess_desc* d, void* stream) {
+    HN_REQUIRE(d && d->src && d->dst, "preprocess: null pointer");
+    HN_REQUIRE(d->N >= 0 && d->src_h >= 1 && d->src_w >= 1 && d->dst_h >= 1 && d->dst_w >= 1, "preprocess: bad sizes");
+    HN_REQUIRE(d->src_pitch >= (int64_t)d->src_w * 3 && d->src_stride >= d->src_pitch * (d->src_h - 1) + (int64_t)d->src_w * 3,
+               "preprocess: pitch/stride smaller than the image");
+    if (d->N == 0) return HN_OK;
+    const long long total = (long long)d->N * d->dst_h * d->dst_w;
+    HN_REQUIRE(total < 0x7fffffffLL, "preprocess: too many output pixels for one launch");
+    PreParams p;
+    p.src = d->src; p.N = d->N; p.sh = d->src_h; p.sw = d->src_w; p.pitch = d->src_pitch; p.istride = d->src_stride;
+    p.dst = d->dst; p.dh = d->dst_h; p.dw = d->dst_w;
+    p.scale_x = 1.0 / ((double)d->dst_w / (double)d->src_w);
+    p.scale_y = 1.0 / ((double)d->dst_h / (double)d->src_h);
+    p.area2 = (d->src_w == 2 * d->dst_w && d->src_h == 2 * d->dst_h) ? 1 : 0;
+    hn_preprocess_kernel<<<hn_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+

@@ -106,5 +106,48 @@ def main(out_dir=GOLD):
               "det kept", [len(r["scores"]) for r in ref_det], "lanes", [len(lane_gold["lane%d_prob" % b]) for b in range(2)])
 
 
+def reference_imagenet_normalize():
+    """The reference's own ``imagenet_normalize`` (model/demo.py:26-40), compiled from its source text at generation
+    time -- demo.py cannot be imported (argparse + checkpoint loading at module level)."""
+    import ast
+    src = open("/root/reference/model/demo.py").read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "imagenet_normalize"][0]
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "demo.py", "exec"), ns)
+    return ns["imagenet_normalize"]
+
+
+def make_preprocess_golden(out_dir=GOLD):
+    """tests/golden/preprocess.npz: demo.py:191-196 run LIVE (cv2 + the reference's normalise) on small frames."""
+    import cv2
+    from oracle import preprocess_ref
+    norm = reference_imagenet_normalize()
+    rng = np.random.default_rng(7)
+    real = cv2.imread(sorted(__import__("glob").glob("/root/reference/model/demo/images/*.jpg"))[0])
+    cases = {"down_45x80_to_48x32": (rng.integers(0, 256, (45, 80, 3), dtype=np.uint8), (48, 32)),
+             "area_64x96_to_48x32": (rng.integers(0, 256, (64, 96, 3), dtype=np.uint8), (48, 32)),
+             "up_37x53_to_96x64": (rng.integers(0, 256, (37, 53, 3), dtype=np.uint8), (96, 64)),
+             "real_crop_90x160_to_64x64": (np.ascontiguousarray(real[200:290, 300:460]), (64, 64))}
+    blob = {}
+    for name, (img, (w, h)) in cases.items():
+        x = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+        x = cv2.resize(x, (w, h))
+        x = x.astype(np.float32)
+        x = norm(x)
+        x = np.transpose(x, (2, 0, 1))
+        ref = torch.tensor(x).float().numpy()
+        mine = preprocess_ref.preprocess(img, w, h)
+        assert np.array_equal(ref, mine), name  # pins the restatement while generating
+        blob[name + ".img"] = img
+        blob[name + ".size"] = np.array([w, h], dtype=np.int32)
+        blob[name + ".out"] = ref
+    np.savez_compressed(os.path.join(out_dir, "preprocess.npz"), **blob)
+    print("wrote preprocess.npz:", {k: v.shape for k, v in blob.items() if k.endswith(".out")}, "cv2", cv2.__version__)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "preprocess":
+        make_preprocess_golden()
+    else:
+        main()
+        make_preprocess_golden()

@@ -84,3 +84,37 @@ def test_oracle_pinned_against_live_reference():
             assert sorted(a.files) == sorted(b.files)
             for k in a.files:
                 assert np.array_equal(a[k], b[k]), (name, k)
+
+
+# ------------------------------------------------------------------ pre-processing
+def _pre_cases():
+    g = np.load(os.path.join(GOLD, "preprocess.npz"))
+    names = sorted({k.rsplit(".", 1)[0] for k in g.files})
+    return g, names
+
+
+def test_preprocess_oracle_matches_golden():
+    """oracle/preprocess_ref.py against tensors the LIVE pipeline (cv2 4.13 + the reference's imagenet_normalize) produced."""
+    from oracle import preprocess_ref as pp
+    g, names = _pre_cases()
+    assert len(names) == 4
+    for n in names:
+        w, h = (int(v) for v in g[n + ".size"])
+        assert np.array_equal(pp.preprocess(g[n + ".img"], w, h), g[n + ".out"]), n
+
+
+def test_preprocess_oracle_matches_cv2_live():
+    """the resize restatement against cv2 itself, bit for bit: down, up, exact 2x (INTER_AREA), identity, odd sizes."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import preprocess_ref as pp
+    rng = np.random.default_rng(0)
+    sizes = [(720, 1280, 640, 640), (1280, 1280, 640, 640), (360, 640, 640, 640), (717, 1283, 640, 640), (1080, 1920, 384, 640),
+             (640, 640, 640, 640), (100, 37, 128, 256), (1280, 1920, 640, 640), (100, 100, 128, 100), (100, 100, 100, 128),
+             (50, 50, 100, 100), (64, 64, 640, 640), (300, 300, 640, 640), (500, 700, 640, 640), (2, 2, 7, 5), (1, 9, 4, 4),
+             (9, 1, 4, 4), (33, 65, 16, 32), (31, 63, 16, 32), (480, 854, 256, 512)]
+    for (h, w, H, W) in sizes:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(pp.resize_u8(img, W, H), cv2.resize(img, (W, H))), (h, w, H, W)
+    lut = pp.normalize_lut()
+    lv = np.arange(256, dtype=np.uint8).reshape(16, 16, 1).repeat(3, 2)
+    assert np.array_equal(pp.imagenet_normalize(lv.astype(np.float32)).astype(np.float32).reshape(256, 3).T, lut)
