@@ -122,7 +122,8 @@ struct DetWs {
     int* cell_cnt;       // [N*16*kCellStride + 1] members per (segment, cell) ...
     int* cell_begin;     // ... and its exclusive scan = first cell-order index of every cell (rows are contiguous)
     int* preds;          // [N*A][kMaxPreds] earlier boxes of the same class with IoU > thr
-    int* npred;          // [N*A]
+    int* npred;          // [N*A] predecessors found by the box's own scan: preds[0 .. npred)
+    int* nfor;           // [N*A] predecessors recorded by other boxes' scans: preds[kMaxPreds-1 .. kMaxPreds-nfor] (downwards)
     unsigned char* status; // [N*A] 0 undecided, 1 kept, 2 suppressed
     int* kflag;          // [N*A] kept as int, and its exclusive scan
     int* kscan;
@@ -223,6 +224,7 @@ static size_t det_layout(int N, int A, void* base, DetWs* ws) {
     w.cell_begin = reinterpret_cast<int*>(take(((size_t)N * kMaxCls * kCellStride + 1) * 4));
     w.preds = reinterpret_cast<int*>(take(NA * kMaxPreds * 4));
     w.npred = reinterpret_cast<int*>(take(NA * 4));
+    w.nfor = reinterpret_cast<int*>(take(NA * 4));
     w.status = reinterpret_cast<unsigned char*>(take(NA));
     w.kflag = reinterpret_cast<int*>(take(NA * 4));
     w.kscan = reinterpret_cast<int*>(take(NA * 4));
@@ -333,7 +335,15 @@ __device__ __forceinline__ bool iou_gt(const float4& a, float area_a, const floa
     float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
     if (thr >= 0.0f && (w <= 0.0f || h <= 0.0f)) return false;  // inter == 0 -> ovr is 0 or NaN: never > thr
     float inter = __fmul_rn(w, h);
-    float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+    const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    // the decision is fl(inter / uni) > thr; away from the boundary a multiplication settles it (relative margins of
+    // 1e-5 dwarf the rounding of one division and one product), the exact division runs only inside the band
+    if (thr > 0.0f && uni > 0.0f) {
+        const float tu = thr * uni;
+        if (inter < tu * 0.99999f) return false;
+        if (inter > tu * 1.00001f) return true;
+    }
+    float ovr = __fdiv_rn(inter, uni);
     return ovr > thr;
 }
 __device__ __forceinline__ float box_area(const float4& b) { return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y)); }
@@ -548,6 +558,7 @@ __global__ void hn_nms2_prepare_kernel(DetWs ws, long long NA, int A, int nms_mo
     ws.kflag[i] = 0;
     ws.status[i] = 2;
     ws.npred[i] = 0;
+    ws.nfor[i] = 0;
     if (key == ~0ull) { ws.ckey[i] = 0xFFFFFFFFu; return; }
     const int seg = (int)(key >> kClsShift), n = seg / kMaxCls, cls = seg % kMaxCls;
     const int a = (int)(key & ((1u << kAnchorBits) - 1));
@@ -581,11 +592,6 @@ __global__ void hn_nms2_cells_kernel(DetWs ws, long long NA) {
 // predecessor list or -- atomically -- in the other box's.
 static constexpr int kBuildLanes = 1;
 static constexpr int kBuildMaxRanges = 24;
-__device__ __forceinline__ void nms2_add_pred(DetWs& ws, long long later, int earlier, int n) {
-    const int pos = atomicAdd(ws.npred + later, 1);
-    if (pos < kMaxPreds) ws.preds[later * kMaxPreds + pos] = earlier;
-    else ws.overflow[n] = 1;
-}
 __global__ void __launch_bounds__(256) hn_nms2_build_kernel(DetWs ws, long long NA, int nms_mode, float iou_thr, GridGeom g) {
     const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= NA || ws.ckey[slot] == 0xFFFFFFFFu) return;
@@ -600,14 +606,25 @@ __global__ void __launch_bounds__(256) hn_nms2_build_kernel(DetWs ws, long long 
     const int t = grid_level(fmaxf(wj, hj), g);
     const int l_hi = min(g.nlev - 1, t + g.delta);
     int scanned = 0, edges = 0;
+    // The box's own predecessor list grows from the front with plain stores (only this thread writes there); edges
+    // owed to ANOTHER box take an atomic slot counted down from the far end of that box's list.  A returning atomic
+    // in the scan loop stalls the warp for an L2 round trip, and with ~10 % of the entries hitting, some lane of the
+    // warp hits in nearly every iteration.
+    int n_own = 0;
+    int* my_preds = ws.preds + i * kMaxPreds;
     auto visit = [&](int q, bool upper) {
         const float4 kb = ws.cbox[q];
         ++scanned;
-        if (iou_gt(kb, box_area(kb), b, area, iou_thr)) {  // rare: only then look up the priority
+        if (iou_gt(kb, box_area(kb), b, area, iou_thr)) {  // only then look up the priority
             const int m = ws.cval[q];
             ++edges;
-            if (m < i) nms2_add_pred(ws, i, m, n);
-            else if (m > i && upper) nms2_add_pred(ws, m, (int)i, n);  // same level: the other box records it itself
+            if (m < i) {
+                if (n_own < kMaxPreds) my_preds[n_own] = m;
+                ++n_own;
+            } else if (m > i && upper) {  // same level: the other box records it itself
+                const int pos = atomicAdd(ws.nfor + m, 1);
+                if (pos < kMaxPreds) ws.preds[(long long)m * kMaxPreds + (kMaxPreds - 1 - pos)] = (int)i;
+            }
         }
     };
     // pass 1: the non-empty index range of every window row
@@ -651,6 +668,7 @@ __global__ void __launch_bounds__(256) hn_nms2_build_kernel(DetWs ws, long long 
             }
         }
     }
+    ws.npred[i] = n_own;
     if (ws.dbg) {
         atomicAdd(reinterpret_cast<unsigned long long*>(ws.dbg) + 0, (unsigned long long)scanned);
         atomicAdd(reinterpret_cast<unsigned long long*>(ws.dbg) + 1, (unsigned long long)edges);
@@ -661,8 +679,15 @@ __global__ void __launch_bounds__(256) hn_nms2_build_kernel(DetWs ws, long long 
 __global__ void hn_nms2_seed_kernel(DetWs ws, long long NA) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NA || ws.keys[i] == ~0ull) return;
-    const int np = ws.npred[i];
-    if (np > kMaxPreds) ws.npred[i] = kMaxPreds;
+    int own = ws.npred[i], fgn = ws.nfor[i];
+    if (own + fgn > kMaxPreds) {  // the two ends of the list ran into each other: the sequential kernel redoes the image
+        ws.overflow[(int)(ws.keys[i] >> kClsShift) / kMaxCls] = 1;
+        own = min(own, kMaxPreds);
+        fgn = min(fgn, kMaxPreds - own);
+        ws.npred[i] = own;
+        ws.nfor[i] = fgn;
+    }
+    const int np = own + fgn;
     ws.status[i] = np == 0 ? 1 : 0;
     // undecided boxes go on the first worklist (warp-aggregated append; order is irrelevant)
     const bool und = np != 0;
@@ -702,19 +727,26 @@ __global__ void __launch_bounds__(256) hn_nms2_rounds_kernel(DetWs ws, long long
             int i = 0;
             if (w < n_cur) {
                 i = __ldcg(cur + w);
-                const int np = ws.npred[i];
+                const int own = ws.npred[i], fgn = ws.nfor[i];
                 const int4* my = reinterpret_cast<const int4*>(ws.preds + (long long)i * kMaxPreds);
                 bool kept_pred = false, all_supp = true;
-                // four predecessors at a time: their status loads are independent (the loop is latency-bound)
-                for (int k = 0; k < np && !kept_pred; k += 4) {
-                    const int4 pr = __ldcg(my + (k >> 2));
-                    const unsigned char s0 = __ldcg(ws.status + pr.x);
-                    const unsigned char s1 = k + 1 < np ? __ldcg(ws.status + pr.y) : (unsigned char)2;
-                    const unsigned char s2 = k + 2 < np ? __ldcg(ws.status + pr.z) : (unsigned char)2;
-                    const unsigned char s3 = k + 3 < np ? __ldcg(ws.status + pr.w) : (unsigned char)2;
-                    kept_pred = s0 == 1 || s1 == 1 || s2 == 1 || s3 == 1;
-                    if (s0 == 0 || s1 == 0 || s2 == 0 || s3 == 0) all_supp = false;
-                }
+                // four predecessors at a time: their status loads are independent (the loop is latency-bound).
+                // own part preds[0 .. own), then the foreign part preds[kMaxPreds - fgn .. kMaxPreds)
+                auto look = [&](int first, int count) {
+                    const int k0 = first & ~3;  // aligned int4 reads; entries outside [first, first+count) are skipped
+                    for (int k = k0; k < first + count && !kept_pred; k += 4) {
+                        const int4 pr = __ldcg(my + (k >> 2));
+                        const int lo = first, hi = first + count;
+                        const unsigned char s0 = (k + 0 >= lo && k + 0 < hi) ? __ldcg(ws.status + pr.x) : (unsigned char)2;
+                        const unsigned char s1 = (k + 1 >= lo && k + 1 < hi) ? __ldcg(ws.status + pr.y) : (unsigned char)2;
+                        const unsigned char s2 = (k + 2 >= lo && k + 2 < hi) ? __ldcg(ws.status + pr.z) : (unsigned char)2;
+                        const unsigned char s3 = (k + 3 >= lo && k + 3 < hi) ? __ldcg(ws.status + pr.w) : (unsigned char)2;
+                        kept_pred = s0 == 1 || s1 == 1 || s2 == 1 || s3 == 1;
+                        if (s0 == 0 || s1 == 0 || s2 == 0 || s3 == 0) all_supp = false;
+                    }
+                };
+                look(0, own);
+                if (fgn > 0) look(kMaxPreds - fgn, fgn);
                 if (kept_pred) ws.status[i] = 2;
                 else if (all_supp) ws.status[i] = 1;
                 else carry = true;
