@@ -49,6 +49,9 @@ __device__ __forceinline__ const bf16* vptr(const View& v, int n, int y, int x, 
 // ------------------------------------------------------------------------------------------------
 // stem: 3x3 s2 p1, 3 -> 32, fp32 NCHW -> bf16 NHWC, BN folded, ReLU
 // ------------------------------------------------------------------------------------------------
+// One thread = two horizontally adjacent output pixels x 32 channels: the kernel is bound by the shared-memory reads
+// of the weights (8 LDS.128 per tap), and two pixels share every weight vector (and 9 of their 54 input samples).
+// The accumulation order per output (ci, ky, kx) is the same as a one-pixel loop.
 __global__ void __launch_bounds__(128) hn_stem_kernel(const float* __restrict__ x, int N, int H, int W,
                                                       const float* __restrict__ w, const float* __restrict__ b,
                                                       View out) {
@@ -59,45 +62,60 @@ __global__ void __launch_bounds__(128) hn_stem_kernel(const float* __restrict__ 
     for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = w[i];
     if (threadIdx.x < 32) sb[threadIdx.x] = b[threadIdx.x];
     __syncthreads();
-    const int OH = out.H, OW = out.W;
+    const int OH = out.H, OW = out.W, OW2 = (OW + 1) >> 1;
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned total = (unsigned)N * OH * OW;
+    const unsigned total = (unsigned)N * OH * OW2;
     if (idx >= total) return;
-    int ox = (int)(idx % (unsigned)OW);
-    int oy = (int)((idx / (unsigned)OW) % (unsigned)OH);
-    int n = (int)(idx / ((unsigned)OW * OH));
-    float acc[32];
+    const int ox = (int)(idx % (unsigned)OW2) * 2;
+    const int oy = (int)((idx / (unsigned)OW2) % (unsigned)OH);
+    const int n = (int)(idx / ((unsigned)OW2 * OH));
+    float acc[2][32];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) acc[c] = sb[c];
+    for (int c = 0; c < 32; ++c) acc[0][c] = acc[1][c] = sb[c];
     const float* xin = x + (long long)n * 3 * H * W;
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci) {
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-            int iy = oy * 2 - 1 + ky;
+            const int iy = oy * 2 - 1 + ky;
+            const bool row_ok = iy >= 0 && iy < H;
+            const float* rowp = xin + ((long long)ci * H + (row_ok ? iy : 0)) * W;
+            float v[5];  // input columns 2*ox-1 .. 2*ox+3
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                const int ix = ox * 2 - 1 + q;
+                v[q] = (row_ok && ix >= 0 && ix < W) ? __ldg(rowp + ix) : 0.0f;
+            }
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                int ix = ox * 2 - 1 + kx;
-                float v = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xin + ((long long)ci * H + iy) * W + ix) : 0.0f;
                 const float4* wr = reinterpret_cast<const float4*>(sw + (ci * 9 + ky * 3 + kx) * 32);
+                const float v0 = v[kx], v1 = v[kx + 2];
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
-                    float4 ww = wr[c4];
-                    acc[c4 * 4 + 0] = fmaf(v, ww.x, acc[c4 * 4 + 0]);
-                    acc[c4 * 4 + 1] = fmaf(v, ww.y, acc[c4 * 4 + 1]);
-                    acc[c4 * 4 + 2] = fmaf(v, ww.z, acc[c4 * 4 + 2]);
-                    acc[c4 * 4 + 3] = fmaf(v, ww.w, acc[c4 * 4 + 3]);
+                    const float4 ww = wr[c4];
+                    acc[0][c4 * 4 + 0] = fmaf(v0, ww.x, acc[0][c4 * 4 + 0]);
+                    acc[0][c4 * 4 + 1] = fmaf(v0, ww.y, acc[0][c4 * 4 + 1]);
+                    acc[0][c4 * 4 + 2] = fmaf(v0, ww.z, acc[0][c4 * 4 + 2]);
+                    acc[0][c4 * 4 + 3] = fmaf(v0, ww.w, acc[0][c4 * 4 + 3]);
+                    acc[1][c4 * 4 + 0] = fmaf(v1, ww.x, acc[1][c4 * 4 + 0]);
+                    acc[1][c4 * 4 + 1] = fmaf(v1, ww.y, acc[1][c4 * 4 + 1]);
+                    acc[1][c4 * 4 + 2] = fmaf(v1, ww.z, acc[1][c4 * 4 + 2]);
+                    acc[1][c4 * 4 + 3] = fmaf(v1, ww.w, acc[1][c4 * 4 + 3]);
                 }
             }
         }
     }
-    bf16* o = const_cast<bf16*>(vptr(out, n, oy, ox, 0));
 #pragma unroll
-    for (int c8 = 0; c8 < 4; ++c8) {
-        float f[8];
+    for (int px = 0; px < 2; ++px) {
+        if (ox + px >= OW) break;
+        bf16* o = const_cast<bf16*>(vptr(out, n, oy, ox + px, 0));
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = fmaxf(acc[c8 * 8 + j], 0.0f);
-        store8(o + c8 * 8, f);
+        for (int c8 = 0; c8 < 4; ++c8) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaxf(acc[px][c8 * 8 + j], 0.0f);
+            store8(o + c8 * 8, f);
+        }
     }
 }
 
@@ -107,7 +125,7 @@ extern "C" int hn_stem_fwd(const hn_stem_desc* d, void* stream) {
     HN_REQUIRE(d->out.C == 32 && d->out.N == d->N && d->out.H == (d->H + 1) / 2 && d->out.W == (d->W + 1) / 2,
                "stem: output view %dx%dx%dx%d does not match input %dx3x%dx%d", d->out.N, d->out.H, d->out.W, d->out.C, d->N,
                d->H, d->W);
-    long long total = (long long)d->N * d->out.H * d->out.W;
+    long long total = (long long)d->N * d->out.H * ((d->out.W + 1) / 2);  // two output pixels per thread
     HN_REQUIRE(total < 0x7fffffffLL, "stem: too many output pixels for one launch");
     HN_CHECK_CUDA(hn_launch(hn_stem_kernel, dim3(hn_cdiv(total, 128)), dim3(128), (size_t)(0), reinterpret_cast<cudaStream_t>(stream), d->x, d->N, d->H, d->W, d->w,
                                                                                           d->b, to_view(d->out)));

@@ -722,11 +722,16 @@ __global__ void __launch_bounds__(256) hn_nms2_rounds_kernel(DetWs ws, long long
         if (n_cur == 0) break;
         if (tid0 == 0) ws.changed[c_clr] = 0;
         const long long n_pad = ((long long)n_cur + 31) & ~31ll;  // whole warps iterate together (ballot below)
+        // Short lists are bound by the grid barrier and by load latency, not by work: walk them several times per
+        // round, so that chains of dependent boxes advance more than one link per barrier (a later pass sees what
+        // other threads decided meanwhile; stale reads only delay a decision, they never change it).
+        const int passes = n_cur < 400000 ? 3 : 1;
+        for (int pass = 0; pass < passes; ++pass)
         for (long long w = tid0; w < n_pad; w += stride) {
             bool carry = false;
             int i = 0;
-            if (w < n_cur) {
-                i = __ldcg(cur + w);
+            if (w < n_cur) i = __ldcg(cur + w);
+            if (w < n_cur && (pass == 0 || __ldcg(ws.status + i) == 0)) {
                 const int own = ws.npred[i], fgn = ws.nfor[i];
                 const int4* my = reinterpret_cast<const int4*>(ws.preds + (long long)i * kMaxPreds);
                 bool kept_pred = false, all_supp = true;
@@ -749,7 +754,7 @@ __global__ void __launch_bounds__(256) hn_nms2_rounds_kernel(DetWs ws, long long
                 if (fgn > 0) look(kMaxPreds - fgn, fgn);
                 if (kept_pred) ws.status[i] = 2;
                 else if (all_supp) ws.status[i] = 1;
-                else carry = true;
+                else carry = pass == passes - 1;
             }
             // warp-aggregated append to the next worklist: one atomic per warp
             const unsigned m = __ballot_sync(0xffffffffu, carry);
