@@ -80,6 +80,12 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of hn_conv_gemm_kernel, averaged over the 216 launches of one batch-32
+# step (profiles/r01_launches_step_b32.csv: 5.83 GB in total; ncu flushes the caches before every kernel, so this
+# is an upper figure for the replayed step, where the L2 keeps part of each layer's output for the next one)
+CONV_DRAM_BYTES_PER_LAUNCH = 27.0e6
+
+
 def build_model(device):
     import hydranet_b200 as hb
     from hydranet_b200.config import big_cfg
@@ -294,6 +300,10 @@ def run_native(args):
         reps = 3
         for rep in range(reps + 1):
             plan.x.copy_(resident[rep % 2])
+            # Park the GPU first (~15 ms spin on this stream) so that the host gets ahead and enqueues all launches and
+            # events: otherwise the gap between two events is the host's per-launch cost (ctypes call + event record,
+            # ~10 us), not the kernel, for every kernel shorter than that.
+            torch.cuda._sleep(30_000_000)
             evs[0].record(stream)
             for i in range(len(plan.ops)):
                 plan.run_range(i, i + 1, sp)
@@ -321,7 +331,7 @@ def run_native(args):
         achieved = conv_flops / (conv_ms / 1e3) / 1e12
         peak = pk["bf16_tflops_sustained"]
         roof = {"bound": "tensor", "kernel": "hn_conv_gemm_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": pk_src + " (sustained: kernel timed inside a step)",
+                "frac": round(achieved / peak, 4), "traffic": CONV_DRAM_BYTES_PER_LAUNCH, "peak_source": pk_src + " (sustained: kernel timed inside a step)",
                 "launches_per_step": conv_n, "ms_per_step_in_kernel": round(conv_ms, 3), "share_of_forward": round(conv_ms / all_ms, 3),
                 "algorithmic_gflop_per_launch_avg": round(conv_flops / conv_n / 1e9, 3),
                 "breakdown_ms": {"%s/%s" % k: round(v[0], 3) for k, v in sorted(tot.items())}}
