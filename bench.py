@@ -294,7 +294,9 @@ def run_native(args):
     if rank == 0:
         plan = m.plan(B, H, W, dev)
         pk, pk_src = peaks()
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(plan.ops) + 1)]
+        # per-launch device times: every op of the plan (both half-batch plans when the batch is split) between events
+        units = [(part, i, op) for part in getattr(plan, "parts", [plan]) for i, op in enumerate(part.ops)]
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(units) + 1)]
         sp = stream.cuda_stream
         tot = {}
         reps = 3
@@ -305,25 +307,25 @@ def run_native(args):
             # ~10 us), not the kernel, for every kernel shorter than that.
             torch.cuda._sleep(30_000_000)
             evs[0].record(stream)
-            for i in range(len(plan.ops)):
-                plan.run_range(i, i + 1, sp)
-                evs[i + 1].record(stream)
+            for j, (part, i, op) in enumerate(units):
+                part.run_range(i, i + 1, sp)
+                evs[j + 1].record(stream)
             torch.cuda.synchronize(dev)
             if rep == 0:
                 continue
-            for i, op in enumerate(plan.ops):
+            for j, (part, i, op) in enumerate(units):
                 k = (op.kind, op.group)
                 a = tot.setdefault(k, [0.0, 0, 0])
-                a[0] += evs[i].elapsed_time(evs[i + 1]) / reps
+                a[0] += evs[j].elapsed_time(evs[j + 1]) / reps
                 a[1] += op.macs if rep == 1 else 0
                 a[2] += 1 if rep == 1 else 0
         if args.dump_ops:
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             with open(os.path.join(ROOT, "gpurun_out", "op_times.txt"), "w") as f:
-                for i, op in enumerate(plan.ops):
-                    ms_i = evs[i].elapsed_time(evs[i + 1])
-                    f.write("%4d %-30s %-8s %-9s %9.4f ms %8.3f GFLOP %8.2f TFLOP/s\n" % (
-                        i, op.name, op.kind, op.group, ms_i, 2e-9 * op.macs, 2e-9 * op.macs / max(ms_i, 1e-6)))
+                for j, (part, i, op) in enumerate(units):
+                    ms_i = evs[j].elapsed_time(evs[j + 1])
+                    f.write("%4d %-30s %-8s %-9s %9.4f ms %8.3f GFLOP %8.2f TFLOP/s  (batch %d)\n" % (
+                        j, op.name, op.kind, op.group, ms_i, 2e-9 * op.macs, 2e-9 * op.macs / max(ms_i, 1e-6), part.B))
         conv_ms = sum(v[0] for k, v in tot.items() if k[0] == "conv")
         conv_flops = 2.0 * sum(v[1] for k, v in tot.items() if k[0] == "conv")
         conv_n = sum(v[2] for k, v in tot.items() if k[0] == "conv")

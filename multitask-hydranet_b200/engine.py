@@ -352,11 +352,20 @@ UP_SETS = {0: [(-1, [0]), (0, [1, 2])], 1: [(0, [0, 1]), (1, [2])]}
 class Builder:
     """Emits the op list for one (batch, height, width)."""
 
-    def __init__(self, model, B, H, W, device, act_dtype=torch.bfloat16):
+    def __init__(self, model, B, H, W, device, act_dtype=torch.bfloat16, out_alloc=None):
         self.m, self.B, self.H, self.W, self.dev, self.dt = model, B, H, W, device, act_dtype
         self.ops = []
         self.keep = []  # tensors that must stay alive
         self.out = {}
+        self.out_alloc = out_alloc  # optional (name, shape, dtype) -> tensor: lets a caller own the head outputs
+
+    def new_out(self, name, shape, dtype):
+        """A head output tensor [B, ...]: fresh zeros, or the caller's buffer (e.g. a batch slice of a larger one)."""
+        if self.out_alloc is not None:
+            t = self.out_alloc(name, tuple(shape), dtype)
+            assert tuple(t.shape) == tuple(shape) and t.dtype == dtype and t.is_contiguous(), name
+            return t
+        return torch.zeros(tuple(shape), dtype=dtype, device=self.dev)
 
     # -- small helpers --
     def buf(self, H, W, C, pad=0, halo=nv.HALO_NONE):
@@ -710,8 +719,8 @@ class Builder:
             x = ob
         oc = dec[-1].conv
         ncls = oc.weight.shape[0]
-        logits = torch.zeros((self.B, ncls, x.H * 2, x.W * 2), dtype=torch.float32, device=self.dev)
-        cls_map = torch.zeros((self.B, x.H * 2, x.W * 2), dtype=torch.uint8, device=self.dev)
+        logits = self.new_out("seg", (self.B, ncls, x.H * 2, x.W * 2), torch.float32)
+        cls_map = self.new_out("seg_cls_u8", (self.B, x.H * 2, x.W * 2), torch.uint8)
         self.seg_out("seg.out", x, oc.weight.detach().float(), oc.bias.detach().float(), logits, cls_map)
         self.out["seg"] = logits
         self.out["seg_cls_u8"] = cls_map
@@ -728,8 +737,8 @@ class Builder:
         B, C = self.B, levels[0].C
         hws = [l.H * l.W for l in levels]
         total = sum(hws) * na
-        reg = torch.zeros((B, total, 4), dtype=torch.float32, device=self.dev)
-        cls = torch.zeros((B, total, ncls), dtype=torch.float32, device=self.dev)
+        reg = self.new_out("regression", (B, total, 4), torch.float32)
+        cls = self.new_out("classification", (B, total, ncls), torch.float32)
         ends, acc = [], 0
         for hw in hws:
             acc += B * hw
@@ -815,8 +824,8 @@ class Builder:
         self.conv1x1("lane.hidden", fused.interior(), torch.cat(ws, 0), torch.cat(bs, 0), hid, nv.ACT_RELU, "lane")
         ncls = lh.num_classes
         nup, ndown = lh.lane_up_pts_num, lh.lane_down_pts_num
-        pcls = torch.zeros((self.B, fh * fw, ncls), dtype=torch.float32, device=self.dev)
-        ploc = torch.zeros((self.B, fh * fw, nup + ndown), dtype=torch.float32, device=self.dev)
+        pcls = self.new_out("predict_cls", (self.B, fh * fw, ncls), torch.float32)
+        ploc = self.new_out("predict_loc", (self.B, fh * fw, nup + ndown), torch.float32)
         for bi, (br, t, col0) in enumerate(((lh.conv_cls_conv, pcls, 0), (lh.conv_up_conv, ploc, ndown), (lh.conv_down_conv, ploc, 0))):
             conv = br[3]
             cout = conv.weight.shape[0]
@@ -845,10 +854,10 @@ class Builder:
 class Plan:
     """Compiled schedule for one input shape: static input, buffers, native plan handle."""
 
-    def __init__(self, model, B, H, W, device):
+    def __init__(self, model, B, H, W, device, x=None, out_alloc=None):
         self.B, self.H, self.W, self.device = B, H, W, device
-        self.x = torch.zeros((B, 3, H, W), dtype=torch.float32, device=device)
-        self.builder = Builder(model, B, H, W, device).build(self.x)
+        self.x = x if x is not None else torch.zeros((B, 3, H, W), dtype=torch.float32, device=device)
+        self.builder = Builder(model, B, H, W, device, out_alloc=out_alloc).build(self.x)
         self.ops = self.builder.ops
         self.out = self.builder.out
         import ctypes
@@ -881,3 +890,59 @@ class Plan:
                 nv.lib.hn_plan_destroy(self.handle)
         except Exception:
             pass
+
+
+class SplitPlan:
+    """The batch as two half-batch plans replayed on two streams inside ONE CUDA graph (fork / join).
+
+    Most launches of the forward are latency-bound, not throughput-bound: a RegNet block is seven small dependent
+    kernels (1x1 GEMM, grouped 3x3, pool, two FC GEMMs, scale, 1x1 GEMM) that each occupy a fraction of the SMs for
+    10-20 us.  Two independent half-batches interleave on the idle SMs and fill each other's tile-quantisation tails,
+    while the wide, throughput-bound layers simply take turns.  Both halves write batch slices of the same output
+    tensors, so callers see one [B, ...] result; the input is one static [B, 3, H, W] tensor as well."""
+
+    def __init__(self, model, B, H, W, device):
+        assert B >= 2
+        self.B, self.H, self.W, self.device = B, H, W, device
+        self.x = torch.zeros((B, 3, H, W), dtype=torch.float32, device=device)
+        self.out = {}
+        b0 = (B + 1) // 2
+        self.bounds = [(0, b0), (b0, B)]
+        self.parts = []
+        for lo, hi in self.bounds:
+            def alloc(name, shape, dtype, lo=lo, hi=hi):
+                if name not in self.out:
+                    self.out[name] = torch.zeros((B,) + tuple(shape[1:]), dtype=dtype, device=device)
+                return self.out[name][lo:hi]
+            self.parts.append(Plan(model, hi - lo, H, W, device, x=self.x[lo:hi], out_alloc=alloc))
+        self.ops = self.parts[0].ops  # (diagnostics: the op list of one half)
+        self.n_launches = sum(p.n_launches for p in self.parts)
+        self.side = torch.cuda.Stream(device)
+        self.graph = None
+        self.graph_ready = False
+
+    def _run_forked(self, main):
+        """main: torch stream.  Half 0 on `main`, half 1 on the side stream, joined back into `main`."""
+        self.side.wait_stream(main)
+        self.parts[0].run(main.cuda_stream)
+        self.parts[1].run(self.side.cuda_stream)
+        main.wait_stream(self.side)
+
+    def run(self, stream_ptr):
+        self._run_forked(torch.cuda.current_stream(self.device))
+
+    def run_range(self, first, last, stream_ptr):  # diagnostics only: both halves, one after the other
+        for p in self.parts:
+            p.run_range(first, last, stream_ptr)
+
+    def capture(self, stream_ptr):
+        main = torch.cuda.current_stream(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=main):
+            self._run_forked(torch.cuda.current_stream(self.device))
+        self.graph = g
+        self.graph_ready = True
+
+    def launch_graph(self, stream_ptr):
+        self.graph.replay()
+

@@ -25,6 +25,7 @@ def main():
             bench.postproc(hb, m, out, codec, ws)
         torch.cuda.synchronize()
         plan = m.plan(B, 640, 640, dev)
+        plan = getattr(plan, 'parts', [plan])[0]  # op order of one half-batch plan when the batch is split
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "op_order.txt"), "w") as f:
             for i, op in enumerate(plan.ops):
