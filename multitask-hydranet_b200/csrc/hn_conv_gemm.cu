@@ -466,13 +466,17 @@ __global__ void __launch_bounds__(kCtaThreads) hn_conv_gemm_kernel(const __grid_
                 hn_tmem_ld_wait();
                 epi_segout(p, e, bias_s, v, half);
             } else if (p.n_staging) {
-                // 64-channel slabs: registers -> swizzled shared-memory tile -> one TMA store per slab
+                // 64-channel slabs: registers -> swizzled shared-memory tile -> TMA store.  Each TMEM lane quarter (its
+                // two warps, 32 tile rows = a 4 KB sub-slab) stores its own box and synchronises on its own 64-thread
+                // named barriers: no quarter waits for another.
+                const bool qlead = half == 0 && lane == 0;
+                const int q_dx = (q * 32) & (p.TW - 1), q_dy = (q * 32) >> p.tw_shift;  // the quarter's first tile row
                 for (int c = 0; c < BN; c += 64) {
                     uint8_t* slab = sO + (st_count & (p.n_staging - 1)) * kATileBytes;  // n_staging is 1 or 2
-                    if (et == 0) {
+                    if (qlead) {
                         if (p.n_staging == 2) hn_tma_store_wait_read<1>(); else hn_tma_store_wait_read<0>();
                     }
-                    hn_named_bar_sync(2, kEpiThreads);  // slab is free again
+                    hn_named_bar_sync(2 + q, 64);  // the quarter's sub-slab is free again
                     uint8_t* stage_row = slab + row * 128;
                     {
                         const int cc = c + half * 32;
@@ -489,9 +493,9 @@ __global__ void __launch_bounds__(kCtaThreads) hn_conv_gemm_kernel(const __grid_
                         }
                     }
                     hn_fence_proxy_async();
-                    hn_named_bar_sync(3, kEpiThreads);  // slab fully written
-                    if (et == 0) {
-                        hn_tma_store_4d(&p.tmO, slab, o.n0 + c, o.x0, o.y0, o.img);
+                    hn_named_bar_sync(6 + q, 64);  // sub-slab fully written
+                    if (qlead) {
+                        hn_tma_store_4d(&p.tmO, slab + q * 4096, o.n0 + c, o.x0 + q_dx, o.y0 + q_dy, o.img);
                         hn_tma_store_commit();
                     }
                     ++st_count;
@@ -522,7 +526,7 @@ __global__ void __launch_bounds__(kCtaThreads) hn_conv_gemm_kernel(const __grid_
             if (dbg && ntile == 0 && et == 0) dbg[6] = hn_globaltimer();
             if (++a == 2) { a = 0; aph ^= 1; }
         }
-        if (p.n_staging && et == 0) hn_tma_store_wait_all();  // shared memory must outlive the bulk stores
+        if (p.n_staging && half == 0 && lane == 0) hn_tma_store_wait_all();  // shared memory must outlive the bulk stores
         if (dbg && et == 0) dbg[8] = ntile;
     }
 
@@ -821,7 +825,8 @@ int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L) {
             ov.N = p.n_img; ov.H = p.H; ov.W = p.W; ov.C = d->cout;
             ov.stride_n = p.osn; ov.stride_y = p.osy * p.oscale; ov.stride_x = p.osx * p.oscale;
         }
-        int rc2 = encode_view_map(&p.tmO, ov, TW, TH);
+        // the output box is one TMEM lane quarter of the tile: 32 rows = 32 pixels of a tile row, or 32/TW whole tile rows
+        int rc2 = TW >= 32 ? encode_view_map(&p.tmO, ov, 32, 1) : encode_view_map(&p.tmO, ov, TW, 32 / TW);
         if (rc2) return rc2;
     }
     L->smem = base_smem + (size_t)p.n_staging * kATileBytes;
