@@ -61,7 +61,7 @@ struct TileOrigin {
 // (an m tile index past the end yields out-of-bounds coordinates: zero-filled loads, clipped / masked stores)
 __device__ __forceinline__ TileOrigin tile_origin(const ConvParams& p, int t, int rank) {
     TileOrigin o;
-    const int nt = (int)hn_fastdiv((unsigned)t, p.div_m_groups), mt = (t - nt * p.m_groups) * p.cluster + rank;
+    const int nt = p.n_tiles == 1 ? 0 : (int)hn_fastdiv((unsigned)t, p.div_m_groups), mt = (t - nt * p.m_groups) * p.cluster + rank;
     o.n0 = nt * p.bn;
     if (p.flat) {
         o.img = 0; o.y0 = 0; o.x0 = mt * 128;
@@ -185,7 +185,7 @@ __device__ __forceinline__ void epi_chunk_std(const ConvParams& p, const EpiRow&
         for (int q = 0; q < NC / 8; ++q)
             if (q < nvec) dst[q] = pk[q];
     }
-    if (p.halo != HN_HALO_NONE) {
+    if (p.halo != HN_HALO_NONE && (e.ym1 != kNoCoord || e.ym2 != kNoCoord || e.xm1 != kNoCoord || e.xm2 != kNoCoord)) {  // border rows only
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             const int yy = a == 0 ? e.Y : (a == 1 ? e.ym1 : e.ym2);
@@ -233,7 +233,7 @@ __device__ __forceinline__ void epi_segout(const ConvParams& p, const EpiRow& e,
 // epilogue of tile i overlaps the main loop of tile i+1.
 // kPair = true: the cta_group::2 build (must be launched as 2-CTA clusters); false: no pair instructions at all
 template <bool kPair>
-__global__ void __launch_bounds__(kCtaThreads) hn_conv_gemm_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(kCtaThreads, kPair ? 1 : 2) hn_conv_gemm_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int BN = p.bn;
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(kCtaThreads) hn_conv_gemm_kernel(const __grid_
     uint64_t* bar_acc_empty = bar_acc_full + 2;    // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
     // per accumulator: [BN] bias, or with row groups [n_groups][BN] shift followed by [n_groups][BN] scale
-    float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
+    float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 2) + 15) & ~uintptr_t(15));  // float4 reads
     const int bias_slots = p.n_groups > 0 ? 2 * p.n_groups : 1;
 
     const int warp = threadIdx.x >> 5;
@@ -426,10 +426,14 @@ __global__ void __launch_bounds__(kCtaThreads) hn_conv_gemm_kernel(const __grid_
                     e.off0 = (long long)e.n_i * p.osn + p.group_out_base[g] + pix * p.osx;
                     e.roff = 0;
                 } else {
-                    e.n_i = (int)hn_fastdiv((unsigned)m, p.div_flat_hw);  // m < flat_m < 2^31
-                    long long pix = m - (long long)e.n_i * p.flat_hw;
-                    e.off0 = (long long)e.n_i * p.osn + pix * p.osx;
-                    e.roff = (long long)e.n_i * p.rsn + pix * p.rsx;
+                    e.off0 = e.roff = 0;
+                    e.n_i = 0;
+                    if (!p.n_staging || p.res) {
+                        e.n_i = (int)hn_fastdiv((unsigned)m, p.div_flat_hw);  // m < flat_m < 2^31
+                        long long pix = m - (long long)e.n_i * p.flat_hw;
+                        e.off0 = (long long)e.n_i * p.osn + pix * p.osx;
+                        e.roff = (long long)e.n_i * p.rsn + pix * p.rsx;
+                    }
                 }
             } else {
                 int ty = row >> p.tw_shift, tx = row - (ty << p.tw_shift);  // TW is a power of two (TH*TW == 128)
@@ -438,8 +442,11 @@ __global__ void __launch_bounds__(kCtaThreads) hn_conv_gemm_kernel(const __grid_
                 e.n_i = o.img;
                 e.Y = y * p.oscale + p.ooy;
                 e.X = x * p.oscale + p.oox;
-                e.off0 = (long long)e.n_i * p.osn + (long long)e.Y * p.osy + (long long)e.X * p.osx;
-                e.roff = (long long)e.n_i * p.rsn + (long long)e.Y * p.rsy + (long long)e.X * p.rsx;
+                // element offsets only where something addresses global memory directly (the staged path stores
+                // through the tensor map): this setup runs in every epilogue thread for every tile
+                e.off0 = e.roff = 0;
+                if (!p.n_staging) e.off0 = (long long)e.n_i * p.osn + (long long)e.Y * p.osy + (long long)e.X * p.osx;
+                if (p.res) e.roff = (long long)e.n_i * p.rsn + (long long)e.Y * p.rsy + (long long)e.X * p.rsx;
                 if (p.halo != HN_HALO_NONE && p.epi == HN_EPI_STD) {
                     const int OH = p.H * p.oscale, OW = p.W * p.oscale;
                     if (p.halo == HN_HALO_REFLECT) {
@@ -484,7 +491,9 @@ __global__ void __launch_bounds__(kCtaThreads) hn_conv_gemm_kernel(const __grid_
                             uint32_t v[32];
                             hn_tmem_ld32(t_row + cc, v);
                             hn_tmem_ld_wait();
+                            if (dbg && ntile == 0 && et == 0 && c == 0) dbg[9] = hn_globaltimer();
                             epi_chunk_std<32>(p, e, bias_s, scale_s, cc, o.n0, v, stage_row, row);
+                            if (dbg && ntile == 0 && et == 0 && c == 0) dbg[10] = hn_globaltimer();
                         } else if (cc + 16 <= BN) {
                             uint32_t v[16];
                             hn_tmem_ld16(t_row + cc, v);
@@ -494,10 +503,13 @@ __global__ void __launch_bounds__(kCtaThreads) hn_conv_gemm_kernel(const __grid_
                     }
                     hn_fence_proxy_async();
                     hn_named_bar_sync(6 + q, 64);  // sub-slab fully written
+                    if (dbg && ntile == 0 && et == 0 && c == 0) dbg[11] = hn_globaltimer();
                     if (qlead) {
                         hn_tma_store_4d(&p.tmO, slab + q * 4096, o.n0 + c, o.x0 + q_dx, o.y0 + q_dy, o.img);
                         hn_tma_store_commit();
                     }
+                    if (dbg && ntile == 0 && et == 0 && c == 0) dbg[12] = hn_globaltimer();
+                    if (dbg && ntile == 0 && et == 0 && c == 64) dbg[13] = hn_globaltimer();
                     ++st_count;
                 }
             } else {

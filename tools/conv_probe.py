@@ -41,12 +41,12 @@ def main():
         d = dbg.view(-1, 16).cpu()
         d = d[d[:, 0] > 0]
         t0 = d[:, 0].min()
-        rel = (d[:, :8] - t0).float() / 1e3  # us
+        rel = (d[:, :16] - t0).float() / 1e3  # us
         tiles = d[:, 8].float()
         f = lambda c: "%.1f/%.1f" % (rel[:, c].median().item(), rel[:, c].max().item())
-        out.write("%-22s ev %.1f us | ctas %d tiles/cta %.1f | taps %d bn %d st %d | start %s setup %s prod1 %s full1 %s mma1 %s accfull1 %s epi1 %s end %s | GFLOP %.1f\n" % (
+        out.write("%-22s ev %.1f us | ctas %d tiles/cta %.1f | taps %d bn %d st %d | start %s setup %s prod1 %s full1 %s mma1 %s accfull1 %s [ld1 %s math1 %s bar1 %s store1 %s slab2 %s] epi1 %s end %s | GFLOP %.1f\n" % (
             op.name, e0.elapsed_time(e1) * 1e3, d.shape[0], tiles.mean().item(), len(op.taps), op.bn, op.stages,
-            f(0), f(1), f(2), f(3), f(4), f(5), f(6), f(7), 2e-9 * op.macs))
+            f(0), f(1), f(2), f(3), f(4), f(5), f(9), f(10), f(11), f(12), f(13), f(6), f(7), 2e-9 * op.macs))
         out.flush()
     out.close()
     print(open(os.path.join(ROOT, "gpurun_out", "conv_probe.txt")).read())
