@@ -232,8 +232,10 @@ __device__ __forceinline__ void epi_segout(const ConvParams& p, const EpiRow& e,
 // between the TMA producer and the MMA issuer; two TMEM accumulators (acc_full/acc_empty) so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 // kPair = true: the cta_group::2 build (must be launched as 2-CTA clusters); false: no pair instructions at all
-template <bool kPair>
-__global__ void __launch_bounds__(kCtaThreads, kPair ? 1 : 2) hn_conv_gemm_kernel(const __grid_constant__ ConvParams p) {
+// kMinBlocks: 2 caps the registers (96) so that two CTAs share an SM (narrow tiles); 1 lets the epilogue keep its
+// values in registers (168) when the CTA owns the SM anyway
+template <bool kPair, int kMinBlocks = kPair ? 1 : 2>
+__global__ void __launch_bounds__(kCtaThreads, kMinBlocks) hn_conv_gemm_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int BN = p.bn;
@@ -861,6 +863,8 @@ int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L) {
     long long g = (long long)sms * per_sm / cs;               // resident clusters
     L->grid = dim3((unsigned)((total < g ? total : g) * cs), 1, 1);
     L->cluster = cs;
+    // the 168-register build whenever no SM gets a second CTA of this launch anyway
+    L->per_sm = (per_sm == 1 || (long long)L->grid.x <= sms) ? 1 : 2;
     return HN_OK;
 }
 
@@ -870,11 +874,14 @@ int hn_conv_launch(const ConvLaunch* L, cudaStream_t stream) {
     std::call_once(once, [] {
         attr_err = cudaFuncSetAttribute(hn_conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(hn_conv_gemm_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (attr_err == cudaSuccess)
             attr_err = cudaFuncSetAttribute(hn_conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     HN_CHECK_CUDA(attr_err);
     if (L->cluster <= 1) {
-        HN_CHECK_CUDA(hn_launch(hn_conv_gemm_kernel<false>, L->grid, dim3(kCtaThreads), L->smem, stream, L->prm));
+        if (L->per_sm == 1) HN_CHECK_CUDA(hn_launch(hn_conv_gemm_kernel<false, 1>, L->grid, dim3(kCtaThreads), L->smem, stream, L->prm));
+        else HN_CHECK_CUDA(hn_launch(hn_conv_gemm_kernel<false>, L->grid, dim3(kCtaThreads), L->smem, stream, L->prm));
         HN_CHECK_CUDA(cudaGetLastError());
         return HN_OK;
     }

@@ -45,6 +45,7 @@ struct ConvLaunch {
     dim3 grid;
     size_t smem;
     int cluster;
+    int per_sm;  // CTAs of this launch that fit on one SM (1 or 2)
 };
 
 int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L);
