@@ -392,24 +392,65 @@ struct DwMultiParams {
     unsigned end[HN_MAX_GROUPS];  // exclusive prefix of work items
     const float* dw;
 };
+// thread = one 4-channel vector (threadIdx.x) with its 9x4 weights in registers, walking strips of kDwPx output pixels of
+// a row (grid-stride over the strips of all levels).  Per kernel row a strip loads kDwPx+2 input vectors, branch-free
+// (clamped coordinates + select), and reuses them across its outputs.  `end[g]` counts strips here.
 __global__ void __launch_bounds__(256) hn_dw_multi_kernel(const __grid_constant__ DwMultiParams p) {
     hn_pdl_launch_dependents();
     hn_pdl_wait();
-    unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.end[p.n - 1]) return;
-    int g = 0;
-    while (g < p.n - 1 && idx >= p.end[g]) ++g;
-    if (g > 0) idx -= p.end[g - 1];
-    const View& in = p.in[g];
-    const View& out = p.out[g];
-    const int CV = out.C >> 3, WB = (out.W + kDwPx - 1) / kDwPx;
-    const int cv = (int)(idx % (unsigned)CV);
-    unsigned t = idx / (unsigned)CV;
-    const int xb = (int)(t % (unsigned)WB);
-    t /= (unsigned)WB;
-    const int y = (int)(t % (unsigned)out.H);
-    const int n = (int)(t / (unsigned)out.H);
-    dw_strip(in, out, p.dw, n, y, xb * kDwPx, cv * 8);
+    const int C = p.out[0].C;
+    const int c = threadIdx.x * 4;
+    float4 wgt[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wgt[k] = __ldg(reinterpret_cast<const float4*>(p.dw + k * C + c));
+    const unsigned total = p.end[p.n - 1];
+    for (unsigned s = blockIdx.x * blockDim.y + threadIdx.y; s < total; s += gridDim.x * blockDim.y) {
+        int g = 0;
+        while (g < p.n - 1 && s >= p.end[g]) ++g;
+        unsigned t = g > 0 ? s - p.end[g - 1] : s;
+        const View& in = p.in[g];
+        const View& out = p.out[g];
+        const int H = out.H, W = out.W, WB = (W + kDwPx - 1) / kDwPx;
+        const int xb = (int)(t % (unsigned)WB);
+        t /= (unsigned)WB;
+        const int y = (int)(t % (unsigned)H);
+        const int n = (int)(t / (unsigned)H);
+        const int x0 = xb * kDwPx;
+        float4 acc[kDwPx];
+#pragma unroll
+        for (int q = 0; q < kDwPx; ++q) acc[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = y + ky - 1;
+            const bool row_ok = iy >= 0 && iy < H;
+            const bf16* rowp = in.ptr + n * in.sn + min(max(iy, 0), H - 1) * in.sy + c;
+            uint2 raw[kDwPx + 2];
+#pragma unroll
+            for (int q = 0; q < kDwPx + 2; ++q) {
+                const int ix = x0 + q - 1;
+                raw[q] = *reinterpret_cast<const uint2*>(rowp + min(max(ix, 0), W - 1) * in.sx);
+                if (!(row_ok && ix >= 0 && ix < W)) raw[q] = make_uint2(0u, 0u);
+            }
+#pragma unroll
+            for (int q = 0; q < kDwPx + 2; ++q) {
+                const float2 a = hn_unpack_bf16x2(raw[q].x), b = hn_unpack_bf16x2(raw[q].y);
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int o = q - kx;  // input column q feeds output o through tap kx
+                    if (o >= 0 && o < kDwPx) {
+                        const float4 w = wgt[ky * 3 + kx];
+                        acc[o].x = fmaf(a.x, w.x, acc[o].x); acc[o].y = fmaf(a.y, w.y, acc[o].y);
+                        acc[o].z = fmaf(b.x, w.z, acc[o].z); acc[o].w = fmaf(b.y, w.w, acc[o].w);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kDwPx; ++q)
+            if (x0 + q < W)
+                *reinterpret_cast<uint2*>(const_cast<bf16*>(vptr(out, n, y, x0 + q, c))) =
+                    make_uint2(hn_pack_bf16x2(acc[q].x, acc[q].y), hn_pack_bf16x2(acc[q].z, acc[q].w));
+    }
 }
 
 extern "C" int hn_dw_multi_fwd(const hn_dw_multi_desc* d, void* stream) {
@@ -427,11 +468,18 @@ extern "C" int hn_dw_multi_fwd(const hn_dw_multi_desc* d, void* stream) {
                    "dw_multi: pair %d shape mismatch", i);
         p.in[i] = to_view(d->in[i]);
         p.out[i] = to_view(d->out[i]);
-        total += (long long)d->out[i].N * d->out[i].H * ((d->out[i].W + kDwPx - 1) / kDwPx) * (d->out[i].C / 8);
+        total += (long long)d->out[i].N * d->out[i].H * ((d->out[i].W + kDwPx - 1) / kDwPx);  // strips
         HN_REQUIRE(total < 0x7fffffffLL, "dw_multi: too many work items");
         p.end[i] = (unsigned)total;
     }
-    HN_CHECK_CUDA(hn_launch(hn_dw_multi_kernel, dim3(hn_cdiv(total, 256)), dim3(256), (size_t)(0), reinterpret_cast<cudaStream_t>(stream), p));
+    const int lanes = d->out[0].C / 4;
+    HN_REQUIRE(lanes >= 1 && lanes <= 256, "dw_multi: C=%d not supported", d->out[0].C);
+    const int rows = 256 / lanes;
+    int sms = hn_device_sm_count();
+    if (sms <= 0) sms = 148;
+    long long blocks = hn_cdiv(total, rows);
+    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;  // grid-stride: the weights are loaded once per thread
+    HN_CHECK_CUDA(hn_launch(hn_dw_multi_kernel, dim3((unsigned)blocks), dim3(lanes, rows), (size_t)0, reinterpret_cast<cudaStream_t>(stream), p));
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }
