@@ -303,12 +303,35 @@ __global__ void hn_det_decode_kernel(const float* __restrict__ anchors, const fl
         ws.scores[idx] = best;
         ws.keys[idx] = key;
     }
-    // per-image candidate count and max coordinate: one atomic per warp when the warp sits in one image
+    // per-image candidate count and max coordinate.  These are same-address atomics (one address per image), which
+    // the L2 serialises: reduce per warp, then per block through shared memory, and issue ONE pair per block when the
+    // whole block sits in one image (all but the blocks straddling an image boundary).
+    __shared__ int s_cnt[8], s_max[8], s_img[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n0 = __shfl_sync(0xffffffffu, n, 0);
     const unsigned m = __ballot_sync(0xffffffffu, cand);
-    if (__all_sync(0xffffffffu, n == n0)) {
-        int wmaxo = __reduce_max_sync(0xffffffffu, ord);
-        if ((threadIdx.x & 31) == 0 && m) {
+    const bool warp_one = __all_sync(0xffffffffu, n == n0);
+    const int wmaxo = __reduce_max_sync(0xffffffffu, ord);
+    if (lane == 0) {
+        s_cnt[wid] = __popc(m);
+        s_max[wid] = wmaxo;
+        s_img[wid] = warp_one ? n0 : -1;
+    }
+    __syncthreads();
+    bool block_one = true;
+    const int nw = blockDim.x >> 5;
+    for (int w = 0; w < nw; ++w) block_one = block_one && s_img[w] == s_img[0] && s_img[w] >= 0;
+    if (block_one) {
+        if (threadIdx.x == 0) {
+            int cnt = 0, mx = s_max[0];
+            for (int w = 0; w < nw; ++w) { cnt += s_cnt[w]; mx = max(mx, s_max[w]); }
+            if (cnt) {
+                atomicAdd(ws.n_cand + s_img[0], cnt);
+                atomicMax(ws.max_coord + s_img[0], mx);
+            }
+        }
+    } else if (warp_one) {
+        if (lane == 0 && m) {
             atomicAdd(ws.n_cand + n0, __popc(m));
             atomicMax(ws.max_coord + n0, wmaxo);
         }
@@ -676,30 +699,36 @@ __global__ void __launch_bounds__(256) hn_nms2_build_kernel(DetWs ws, long long 
 }
 
 // after all edges are in place: boxes without predecessors are kept outright
-__global__ void hn_nms2_seed_kernel(DetWs ws, long long NA) {
+__global__ void __launch_bounds__(256) hn_nms2_seed_kernel(DetWs ws, long long NA) {
+    __shared__ int s_cnt[8], s_base;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= NA || ws.keys[i] == ~0ull) return;
-    int own = ws.npred[i], fgn = ws.nfor[i];
-    if (own + fgn > kMaxPreds) {  // the two ends of the list ran into each other: the sequential kernel redoes the image
-        ws.overflow[(int)(ws.keys[i] >> kClsShift) / kMaxCls] = 1;
-        own = min(own, kMaxPreds);
-        fgn = min(fgn, kMaxPreds - own);
-        ws.npred[i] = own;
-        ws.nfor[i] = fgn;
+    bool und = false;
+    if (i < NA && ws.keys[i] != ~0ull) {
+        int own = ws.npred[i], fgn = ws.nfor[i];
+        if (own + fgn > kMaxPreds) {  // the two ends of the list ran into each other: the sequential kernel redoes the image
+            ws.overflow[(int)(ws.keys[i] >> kClsShift) / kMaxCls] = 1;
+            own = min(own, kMaxPreds);
+            fgn = min(fgn, kMaxPreds - own);
+            ws.npred[i] = own;
+            ws.nfor[i] = fgn;
+        }
+        const int np = own + fgn;
+        ws.status[i] = np == 0 ? 1 : 0;
+        und = np != 0;
     }
-    const int np = own + fgn;
-    ws.status[i] = np == 0 ? 1 : 0;
-    // undecided boxes go on the first worklist (warp-aggregated append; order is irrelevant)
-    const bool und = np != 0;
-    const unsigned m = __ballot_sync(__activemask(), und);
-    if (und) {
-        const unsigned lane = threadIdx.x & 31;
-        const int leader = __ffs(m) - 1;
-        int base = 0;
-        if ((int)lane == leader) base = atomicAdd(ws.changed + 0, __popc(m));
-        base = __shfl_sync(m, base, leader);
-        ws.wl_a[base + __popc(m & ((1u << lane) - 1u))] = (int)i;
+    // undecided boxes go on the first worklist: ONE atomic per block (they all hit the same counter, which the L2
+    // serialises), slots from a block-wide prefix; order is irrelevant
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(0xffffffffu, und);
+    if (lane == 0) s_cnt[wid] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; ++w) { const int c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+        s_base = tot ? atomicAdd(ws.changed + 0, tot) : 0;
     }
+    __syncthreads();
+    if (und) ws.wl_a[s_base + s_cnt[wid] + __popc(m & ((1u << lane) - 1u))] = (int)i;
 }
 
 // Rounds over a shrinking worklist: every round decides the boxes whose predecessors are all decided and
@@ -796,13 +825,14 @@ __global__ void hn_det_gather_kernel(DetWs ws, int A, float* __restrict__ out_bo
     const int n = seg / kMaxCls, cls = seg % kMaxCls;
     const int nk = ws.seg_kept[seg];
     const uint64_t low_mask = (1ull << kClsShift) - 1;
-    if (cls == 0 && threadIdx.x == 0) {
+    if (cls == 0 && threadIdx.x == 0 && blockIdx.y == 0) {
         int tot = 0;
         for (int c = 0; c < kMaxCls; ++c) tot += ws.seg_kept[n * kMaxCls + c];
         out_count[n] = tot;
     }
     const uint64_t* mine = ws.kept_keys + ws.seg_start[seg];
-    for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+    // blockIdx.y strides over the segment too: with skewed classes one segment holds a third of an image's boxes
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < nk; i += gridDim.y * blockDim.x) {
         uint64_t key = mine[i] & low_mask;
         int rank = i;
         for (int c = 0; c < kMaxCls; ++c) {
@@ -924,7 +954,7 @@ extern "C" int hn_det_decode_nms(const hn_det_desc* d, void* stream) {
     // sequential kernel: whole problem when pruning is impossible (thr ~ 0), otherwise only flagged images
     hn_det_nms_kernel<<<d->N * kMaxCls, kNmsChunk, 0, s>>>(ws, d->A, d->iou_thres, d->nms_mode, geom, parallel ? 1 : 0);
     HN_CHECK_CUDA(cudaGetLastError());
-    hn_det_gather_kernel<<<d->N * kMaxCls, 256, 0, s>>>(ws, d->A, d->out_boxes, d->out_scores, d->out_class, d->out_count);
+    hn_det_gather_kernel<<<dim3(d->N * kMaxCls, 8), 256, 0, s>>>(ws, d->A, d->out_boxes, d->out_scores, d->out_class, d->out_count);
     HN_CHECK_CUDA(cudaGetLastError());
     if (d->out_cand) {
         hn_copy_i32_kernel<<<hn_cdiv(d->N, 256), 256, 0, s>>>(ws.n_cand, d->out_cand, d->N);
