@@ -737,6 +737,7 @@ __global__ void __launch_bounds__(256) hn_nms2_seed_kernel(DetWs ws, long long N
 __global__ void __launch_bounds__(256) hn_nms2_rounds_kernel(DetWs ws, long long NA) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
+    __shared__ int s_cnt[8], s_base;
     // three rotating worklist counters: [r % 3] = size of the current list, [(r+1) % 3] = the list being built,
     // [(r+2) % 3] = reset now for the round after next -- so one grid barrier per round is enough
     volatile int* cnt = ws.changed;
@@ -750,7 +751,7 @@ __global__ void __launch_bounds__(256) hn_nms2_rounds_kernel(DetWs ws, long long
         const int n_cur = cnt[c_cur];
         if (n_cur == 0) break;
         if (tid0 == 0) ws.changed[c_clr] = 0;
-        const long long n_pad = ((long long)n_cur + 31) & ~31ll;  // whole warps iterate together (ballot below)
+        const long long n_pad = ((long long)n_cur + 255) & ~255ll;  // whole CTAs iterate together (block-wide append below)
         // Short lists are bound by the grid barrier and by load latency, not by work: walk them several times per
         // round, so that chains of dependent boxes advance more than one link per barrier (a later pass sees what
         // other threads decided meanwhile; stale reads only delay a decision, they never change it).
@@ -785,15 +786,19 @@ __global__ void __launch_bounds__(256) hn_nms2_rounds_kernel(DetWs ws, long long
                 else if (all_supp) ws.status[i] = 1;
                 else carry = pass == passes - 1;
             }
-            // warp-aggregated append to the next worklist: one atomic per warp
+            // append to the next worklist: one atomic per CTA (every append hits the same counter)
             const unsigned m = __ballot_sync(0xffffffffu, carry);
-            if (m) {
-                const unsigned lane = threadIdx.x & 31;
-                int base = 0;
-                if (lane == 0) base = atomicAdd(ws.changed + c_nxt, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (carry) nxt[base + __popc(m & ((1u << lane) - 1u))] = i;
+            const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+            if (lane == 0) s_cnt[wid] = __popc(m);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int tot = 0;
+                for (int k = 0; k < 8; ++k) { const int c = s_cnt[k]; s_cnt[k] = tot; tot += c; }
+                s_base = tot ? atomicAdd(ws.changed + c_nxt, tot) : 0;
             }
+            __syncthreads();
+            if (carry) nxt[s_base + s_cnt[wid] + __popc(m & ((1u << lane) - 1u))] = i;
+            __syncthreads();  // s_cnt / s_base are reused by the next iteration
         }
         int* t = cur; cur = nxt; nxt = t;
         ++round;
