@@ -111,7 +111,8 @@ def run_native(args):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        dist.init_process_group("nccl")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     hb, m, cfg = build_model(dev)
