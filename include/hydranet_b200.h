@@ -149,16 +149,23 @@ typedef struct hn_lanefuse_desc {
     int32_t stride; /* 16 or 32 */
 } hn_lanefuse_desc;
 
-/* Squeeze-excite (anynet.py:39-47,68-69) = hn_se_pool_fwd -> two tiny tensor-core GEMMs (hn_conv_fwd:
- * FC1+ReLU over all images at once, FC2+sigmoid) -> hn_se_scale_fwd.
+/* Squeeze-excite (anynet.py:39-47,68-69) = hn_se_pool_fwd (pool + both FC layers) -> hn_se_scale_fwd.
  * pool: mean over H*W of every channel, bf16 [N][C].  Deterministic: per-chunk partial sums are added in
- * chunk order by the block that arrives last for its image.  `counter` must be zero on first use. */
+ * chunk order by the block that arrives last for its image.  `counter` must be zero on first use.
+ * With S > 0 that block also runs the two FC layers of its image: hidden = ReLU(W1 . mean + b1) (rounded to
+ * bf16), gate = sigmoid(W2 . hidden + b2) -> bf16 [N][C]: one launch instead of three. */
 typedef struct hn_se_pool_desc {
     hn_view x;
     int32_t pix_per_block; /* pixels summed by one block (multiple of 128) */
     float* partial;   /* scratch fp32 [N][ceil(H*W/pix_per_block)][C] */
     int32_t* counter; /* scratch int32 [N] */
     void* mean;       /* bf16 [N][C] */
+    int32_t S;        /* hidden width padded to a multiple of 8 (zero rows / columns); 0 = pool only */
+    const void* w1;   /* bf16 [S][C] */
+    const float* b1;  /* fp32 [S] */
+    const void* w2;   /* bf16 [C][S] */
+    const float* b2;  /* fp32 [C] */
+    void* gate;       /* bf16 [N][C] */
 } hn_se_pool_desc;
 
 /* scale: x[n, :, :, c] *= scale[n][c] in place, scale bf16 [N][C] */

@@ -71,7 +71,8 @@ class LaneFuseDesc(C.Structure):
 
 
 class SePoolDesc(C.Structure):
-    _fields_ = [("x", View), ("pix_per_block", C.c_int32), ("partial", C.c_void_p), ("counter", C.c_void_p), ("mean", C.c_void_p)]
+    _fields_ = [("x", View), ("pix_per_block", C.c_int32), ("partial", C.c_void_p), ("counter", C.c_void_p), ("mean", C.c_void_p),
+                ("S", C.c_int32), ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("gate", C.c_void_p)]
 
 
 class SeScaleDesc(C.Structure):

@@ -691,12 +691,57 @@ extern "C" int hn_lanefuse_fwd(const hn_lanefuse_desc* d, void* stream) {
 // ------------------------------------------------------------------------------------------------
 static constexpr int kSeThreads = 512;
 
+struct SeFc {
+    int S;            // padded hidden width (multiple of 8), 0 = no FC stage
+    const bf16* w1;   // [S][C]
+    const float* b1;  // [S]
+    const bf16* w2;   // [C][S]
+    const float* b2;  // [C]
+    bf16* gate;       // [N][C]
+};
+
+// dot product of `len` (a multiple of 8) bf16 weights with fp32 activations in shared memory, 16-byte weight loads
+__device__ __forceinline__ float se_dot(const bf16* __restrict__ w, const float* act, int v0, int v1) {
+    float acc = 0.0f;
+    constexpr int U = 16;  // weight vectors in flight per thread: the FC stage is one CTA per image, bound by L2 latency
+    for (int vb = v0; vb < v1; vb += U) {
+        uint4 r[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) r[u] = vb + u < v1 ? __ldg(reinterpret_cast<const uint4*>(w) + vb + u) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (vb + u >= v1) break;
+            const float2 a = hn_unpack_bf16x2(r[u].x), b = hn_unpack_bf16x2(r[u].y), c = hn_unpack_bf16x2(r[u].z), d = hn_unpack_bf16x2(r[u].w);
+            const float* x = act + (vb + u) * 8;
+            acc = fmaf(a.x, x[0], acc); acc = fmaf(a.y, x[1], acc); acc = fmaf(b.x, x[2], acc); acc = fmaf(b.y, x[3], acc);
+            acc = fmaf(c.x, x[4], acc); acc = fmaf(c.y, x[5], acc); acc = fmaf(d.x, x[6], acc); acc = fmaf(d.y, x[7], acc);
+        }
+    }
+    return acc;
+}
+
 __global__ void __launch_bounds__(kSeThreads) hn_se_pool_kernel(View x, float* __restrict__ partial, int* __restrict__ counter,
-                                                                bf16* __restrict__ mean_out, float inv_hw, int kSePix) {
+                                                                bf16* __restrict__ mean_out, float inv_hw, int kSePix, SeFc fc) {
     hn_pdl_launch_dependents();
     hn_pdl_wait();
     extern __shared__ float sm[];  // [lanes][CG*8] partial sums of this CTA's channel group
     __shared__ int s_last;
+    if (fc.S) {
+        // The FC stage at the end is a chain of dependent loads run by ONE block per image; its weights were last
+        // touched a whole step ago (evicted to DRAM).  All blocks pull them into the L2 now, while they pool.
+        const long long nb = (long long)gridDim.x * gridDim.y * gridDim.z;
+        const long long bid = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        const long long wbytes = (long long)fc.S * x.C * 2;
+        const long long lines = (wbytes + 127) >> 7;
+        for (long long l = bid * blockDim.x + threadIdx.x; l < 2 * lines; l += nb * blockDim.x) {
+            const char* p = l < lines ? reinterpret_cast<const char*>(fc.w1) + (l << 7) : reinterpret_cast<const char*>(fc.w2) + ((l - lines) << 7);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        }
+        if (bid == 0) {
+            for (int l = threadIdx.x; l * 32 < fc.S; l += blockDim.x) asm volatile("prefetch.global.L2 [%0];" ::"l"(fc.b1 + l * 32));
+            for (int l = threadIdx.x; l * 32 < x.C; l += blockDim.x) asm volatile("prefetch.global.L2 [%0];" ::"l"(fc.b2 + l * 32));
+        }
+    }
     const int C = x.C, CV = C >> 3;
     const int n = blockIdx.y;
     const int HW = x.H * x.W;
@@ -763,9 +808,34 @@ __global__ void __launch_bounds__(kSeThreads) hn_se_pool_kernel(View x, float* _
             for (int j = 0; j < 8; ++j) a += v[j];
         }
         for (; k < nchunk; ++k) a += __ldcg(pp + (long long)k * C);
-        mean_out[(long long)n * C + c] = __float2bfloat16(a * inv_hw);
+        const bf16 mb = __float2bfloat16(a * inv_hw);
+        mean_out[(long long)n * C + c] = mb;
+        if (fc.S) sm[c] = __bfloat162float(mb);  // the FC stage reads the rounded mean, as a separate GEMM launch would
     }
     if (threadIdx.x == 0) counter[n] = 0;
+    if (!fc.S) return;
+    // ---- FC1 + ReLU, FC2 + sigmoid for this image (this block arrived last, so it is the only one left) ----
+    float* s_mean = sm;
+    float* s_hid = sm + ((C + 7) & ~7);
+    __syncthreads();
+    const int S = fc.S;
+    {   // FC1: T adjacent lanes per hidden unit (T = largest power of two with S*T <= blockDim.x, at most 32)
+        int T = 1;
+        while (T < 32 && S * T * 2 <= (int)blockDim.x) T *= 2;
+        const int nv = C >> 3, per = (nv + T - 1) / T;
+        for (int s0 = 0; s0 < S; s0 += blockDim.x / T) {
+            const int srow = s0 + threadIdx.x / T, part = threadIdx.x % T;
+            float acc = 0.0f;
+            if (srow < S) acc = se_dot(fc.w1 + (long long)srow * C, s_mean, min(part * per, nv), min(part * per + per, nv));
+            for (int o = T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (srow < S && part == 0) s_hid[srow] = __bfloat162float(__float2bfloat16(fmaxf(acc + fc.b1[srow], 0.0f)));
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {  // FC2: one thread per channel, its weight row is contiguous
+        const float acc = se_dot(fc.w2 + (long long)c * S, s_hid, 0, S >> 3) + fc.b2[c];
+        fc.gate[(long long)n * C + c] = __float2bfloat16(1.0f / (1.0f + expf(-acc)));
+    }
 }
 
 __global__ void hn_se_scale_kernel(View x, const bf16* __restrict__ scale) {
@@ -802,8 +872,20 @@ extern "C" int hn_se_pool_fwd(const hn_se_pool_desc* d, void* stream) {
     int lanes = kSeThreads / CG;
     size_t smem = (size_t)lanes * CG * 8 * sizeof(float);
     HN_REQUIRE(smem <= 48 * 1024, "se_pool: shared memory");
-    HN_CHECK_CUDA(hn_launch(hn_se_pool_kernel, dim3(grid), dim3(kSeThreads), (size_t)(smem), reinterpret_cast<cudaStream_t>(stream), 
-        to_view(d->x), d->partial, d->counter, reinterpret_cast<bf16*>(d->mean), 1.0f / (float)HW, d->pix_per_block));
+    SeFc fc;
+    memset(&fc, 0, sizeof(fc));
+    if (d->S > 0) {
+        HN_REQUIRE(d->S % 8 == 0 && d->w1 && d->b1 && d->w2 && d->b2 && d->gate, "se_pool: FC stage needs S %% 8 == 0 and all five pointers");
+        HN_REQUIRE(((reinterpret_cast<uintptr_t>(d->w1) | reinterpret_cast<uintptr_t>(d->w2)) & 15) == 0, "se_pool: FC weights must be 16-byte aligned");
+        fc.S = d->S;
+        fc.w1 = reinterpret_cast<const bf16*>(d->w1); fc.b1 = d->b1;
+        fc.w2 = reinterpret_cast<const bf16*>(d->w2); fc.b2 = d->b2;
+        fc.gate = reinterpret_cast<bf16*>(d->gate);
+        const size_t need = (size_t)(((C + 7) & ~7) + d->S) * sizeof(float);  // mean + hidden reuse the pooling scratch
+        if (need > smem) smem = need;
+    }
+    HN_CHECK_CUDA(hn_launch(hn_se_pool_kernel, dim3(grid), dim3(kSeThreads), (size_t)(smem), reinterpret_cast<cudaStream_t>(stream),
+        to_view(d->x), d->partial, d->counter, reinterpret_cast<bf16*>(d->mean), 1.0f / (float)HW, d->pix_per_block, fc));
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }

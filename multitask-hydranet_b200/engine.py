@@ -253,13 +253,21 @@ class LaneFuseSpec:
 
 
 class SePoolSpec:
+    """Global average pool and, when FC weights are given, the two squeeze-excite FC layers (one launch)."""
     kind, launches, group, macs = "se_pool", 1, "backbone", 0
 
-    def __init__(self, name, x, pix, partial, counter, mean):
+    def __init__(self, name, x, pix, partial, counter, mean, fc=None):
         self.name, self.x, self.pix, self.partial, self.counter, self.mean = name, x, pix, partial, counter, mean
+        self.fc = fc  # None or dict(S, w1 bf16 [S][C], b1 fp32 [S], w2 bf16 [C][S], b2 fp32 [C], gate bf16 [N][C])
+        if fc is not None:
+            self.macs = 2 * x.N * fc["S"] * x.C
 
     def to_desc(self):
-        return nv.SePoolDesc(self.x.to_c(), self.pix, self.partial.data_ptr(), self.counter.data_ptr(), self.mean.data_ptr())
+        d = nv.SePoolDesc(self.x.to_c(), self.pix, self.partial.data_ptr(), self.counter.data_ptr(), self.mean.data_ptr())
+        if self.fc is not None:
+            f = self.fc
+            d.S, d.w1, d.b1, d.w2, d.b2, d.gate = f["S"], f["w1"].data_ptr(), f["b1"].data_ptr(), f["w2"].data_ptr(), f["b2"].data_ptr(), f["gate"].data_ptr()
+        return d
 
     def add_to(self, plan):
         nv.check(nv.lib.hn_plan_add_se_pool(plan, self.to_desc()))
@@ -484,16 +492,16 @@ class Builder:
         partial = torch.zeros((B, (hw + pix - 1) // pix, C), dtype=torch.float32, device=dev)
         counter = torch.zeros((B,), dtype=torch.int32, device=dev)
         mean = torch.zeros((B, C), dtype=self.dt, device=dev)
-        hidden = torch.zeros((B, Sp), dtype=self.dt, device=dev)
         scale = torch.zeros((B, C), dtype=self.dt, device=dev)
-        self.ops.append(SePoolSpec(name + ".pool", g.interior(), pix, partial, counter, mean))
         w1 = torch.zeros((Sp, C), dtype=torch.float32, device=se[1].weight.device)
         b1 = torch.zeros((Sp,), dtype=torch.float32, device=w1.device)
         w1[:S], b1[:S] = se[1].weight.detach().float().reshape(S, C), se[1].bias.detach().float()
         w2 = torch.zeros((C, Sp), dtype=torch.float32, device=w1.device)
         w2[:, :S] = se[3].weight.detach().float().reshape(C, S)
-        self.fc(name + ".fc1", V(mean, 0, 1, 1, B, C, 0, 0, C), w1, b1, hidden, nv.ACT_RELU)
-        self.fc(name + ".fc2", V(hidden, 0, 1, 1, B, Sp, 0, 0, Sp), w2, se[3].bias.detach().float(), scale, nv.ACT_SIGMOID)
+        # pool -> FC1 + ReLU -> FC2 + sigmoid in ONE launch: the block that finishes an image's pooling runs its FCs
+        fc = dict(S=Sp, w1=w1.to(self.dt).contiguous().to(dev), b1=b1.to(dev), w2=w2.to(self.dt).contiguous().to(dev),
+                  b2=se[3].bias.detach().float().contiguous().to(dev), gate=scale)
+        self.ops.append(SePoolSpec(name + ".gate", g.interior(), pix, partial, counter, mean, fc))
         self.ops.append(SeScaleSpec(name + ".scale", g.interior(), scale))
 
     def gconv(self, name, a, blk, ob, stride):

@@ -211,6 +211,10 @@ def run_lanefuse(ls):
 def run_se_pool(ss):
     x = ss.x.torch_view()
     ss.mean.copy_(x.float().mean(dim=(1, 2)).to(ss.mean.dtype))
+    if ss.fc is not None:  # FC1 + ReLU -> FC2 + sigmoid on the stored (rounded) mean; hidden rounded to the activation dtype
+        f = ss.fc
+        hid = F.relu(ss.mean.float() @ f["w1"].float().t() + f["b1"].float()).to(ss.mean.dtype)
+        f["gate"].copy_(torch.sigmoid(hid.float() @ f["w2"].float().t() + f["b2"].float()).to(f["gate"].dtype))
 
 
 def run_se_scale(ss):

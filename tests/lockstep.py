@@ -41,7 +41,7 @@ def _tensors_out(op):
     if op.kind == "lanefuse":
         return [op.out.t]
     if op.kind == "se_pool":
-        return [op.mean]
+        return [op.mean] + ([op.fc["gate"]] if op.fc is not None else [])
     if op.kind == "se_scale":
         return [op.x.t]
     if op.kind == "stem":
