@@ -151,15 +151,16 @@ def test_det_public_decode_api_and_empty():
     assert hb.DetectionHeader.decode(None, None, None, None) is None
 
 
-def test_det_stress_max_anchors_640():
-    """BASELINE config 5(i): every one of the 76 725 anchors is an NMS candidate."""
-    H = W = 640
+@pytest.mark.parametrize("size,n_anchor", [(640, 76725), (1280, 306900)])
+def test_det_stress_max_anchors(size, n_anchor):
+    """BASELINE config 5(i): every one of the 76 725 (640^2) / 306 900 (1280^2) anchors is an NMS candidate."""
+    H = W = size
     anc, reg, cls = _synth_det(1, H, W, 11, hot=True)
-    assert anc.shape[1] == 76725
+    assert anc.shape[1] == n_anchor
     boxes, scores, cids, count, cand = hb.DetectionHeader.decode_device((H, W), torch.from_numpy(reg).cuda(), torch.from_numpy(cls).cuda(),
                                                                         torch.from_numpy(anc).cuda(), 0.3, 0.3)
-    assert int(cand[0]) == 76725
-    ref = pr.det_postprocess(anc, reg, cls, H, W, 0.3, 0.3, device="cuda")[0]  # 306 900 coords > 100 000 -> per-class
+    assert int(cand[0]) == n_anchor
+    ref = pr.det_postprocess(anc, reg, cls, H, W, 0.3, 0.3, device="cuda")[0]  # more than 100 000 coordinates -> per-class
     k = int(count[0])
     out = {"rois": boxes[0, :k].cpu().numpy(), "class_ids": cids[0, :k].cpu().numpy(), "scores": scores[0, :k].cpu().numpy()}
     _det_compare([out], [ref], ties_as_sets=True)
