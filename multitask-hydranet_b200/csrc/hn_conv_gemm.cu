@@ -93,7 +93,8 @@ __device__ __forceinline__ void apply_act(float (&f)[NC], int act) {
             break;
         case HN_ACT_SIGMOID:
 #pragma unroll
-            for (int j = 0; j < NC; ++j) f[j] = 1.0f / (1.0f + expf(-f[j]));
+            // ex2.approx + fast reciprocal: ~2 ulp of the fp32 sigmoid (the head scores; far inside the 1e-2 parity budget)
+            for (int j = 0; j < NC; ++j) f[j] = __fdividef(1.0f, 1.0f + __expf(-f[j]));
             break;
         default: break;
     }
