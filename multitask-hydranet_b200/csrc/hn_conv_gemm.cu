@@ -617,6 +617,8 @@ static void* g_conv_dbg = nullptr;
 extern "C" void hn_conv_set_debug_buffer(void* p) { g_conv_dbg = p; }
 static int g_conv_cluster = 0;  // 0 = default policy
 extern "C" void hn_conv_set_cluster(int cs) { g_conv_cluster = cs; }
+static int g_conv_pair_min_bn = 192;  // narrowest N tile that runs on CTA pairs
+extern "C" void hn_conv_set_pair_min_bn(int bn) { g_conv_pair_min_bn = bn; }
 static int g_conv_runs = 1;  // 0: never share A boxes between taps; 1: default policy (narrow N tiles); 2: wherever they fit
 extern "C" void hn_conv_set_tap_runs(int mode) { g_conv_runs = mode; }
 static constexpr int kMaxRun = 3;
@@ -723,7 +725,7 @@ int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L) {
     // the pair cuts that to 64 KB.  Used for N tiles >= 192 when there are at least two M tiles (narrower tiles do
     // better as two independent CTAs per SM).
     int cs = (g_conv_cluster > 0) ? g_conv_cluster : 2;
-    if (cs != 2 || d->bn < 192 || d->bn % 32 != 0 || m_tiles < 2 || d->epi != HN_EPI_STD) cs = 1;
+    if (cs != 2 || d->bn < g_conv_pair_min_bn || d->bn % 32 != 0 || m_tiles < 2 || d->epi != HN_EPI_STD) cs = 1;
     p.cluster = cs;
     p.m_groups = hn_cdiv(m_tiles, cs);
     {
