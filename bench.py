@@ -80,10 +80,10 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of hn_conv_gemm_kernel, averaged over the 216 launches of one batch-32
-# step (profiles/r01_launches_step_b32.csv: 5.83 GB in total; ncu flushes the caches before every kernel, so this
+# dram__bytes_read.sum + dram__bytes_write.sum of hn_conv_gemm_kernel, averaged over the 156 launches of one batch-32
+# step (profiles/r01_launches_step_b32.csv: 5.79 GB in total; ncu flushes the caches before every kernel, so this
 # is an upper figure for the replayed step, where the L2 keeps part of each layer's output for the next one)
-CONV_DRAM_BYTES_PER_LAUNCH = 27.0e6
+CONV_DRAM_BYTES_PER_LAUNCH = 37.1e6
 
 
 def build_model(device):

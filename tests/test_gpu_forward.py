@@ -95,11 +95,13 @@ def test_forward_matches_live_reference_golden(name, cfg, hw):
     assert torch.equal(dep[0], torch.argmax(out["seg"], 1))
 
 
-def test_forward_640_vs_oracle_on_gpu():
-    """Full-size config (big cfg, 640x640, batch 2) against the fp32 oracle running on the same GPU."""
-    cfg = big_cfg()
+@pytest.mark.parametrize("B,H,W", [(2, 640, 640), (1, 384, 640), (5, 256, 384)])
+def test_forward_full_size_vs_oracle_on_gpu(B, H, W):
+    """Full-size configs (big cfg: the default 640x640, a non-square 384x640 frame at batch 1, an odd batch) against the
+    fp32 oracle running on the same GPU."""
+    cfg = big_cfg(W, H)
     _, m_gpu, sd = _models(cfg)
-    x = synth.synth_input(2, 640, 640, seed=5).cuda()
+    x = synth.synth_input(B, H, W, seed=5).cuda()
     with torch.no_grad():
         ref = hydranet_ref.forward(sd, cfg, x)
         out = m_gpu(x)
@@ -111,7 +113,7 @@ def test_forward_640_vs_oracle_on_gpu():
             "predict_loc": _rel(ref["lane"]["predict_loc"], out["lane"]["predict_loc"])}
     raw, dec, near, frac = _argmax_report(ref["seg"], torch.argmax(out["seg"], 1))
     os.makedirs(OUT, exist_ok=True)
-    with open(os.path.join(OUT, "forward_640_errors.txt"), "w") as f:
+    with open(os.path.join(OUT, "forward_%dx%dx%d_errors.txt" % (B, H, W)), "w") as f:
         f.write(repr(errs) + " argmax raw=%r decisive=%r decisive_fraction=%r near_ties_only=%r\n" % (raw, dec, frac, near))
     assert max(errs.values()) <= 1e-2, errs
     assert dec >= 0.999 and near and raw >= 0.99, (raw, dec, near)
