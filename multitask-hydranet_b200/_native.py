@@ -138,6 +138,7 @@ SYMBOLS = {
     "hn_plan_num_launches": (C.c_int, [_P]),
     "hn_plan_run": (C.c_int, [_P, _P]),
     "hn_plan_run_range": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "hn_plan_set_branch": (C.c_int, [_P, C.c_int]),
     "hn_plan_graph_capture": (C.c_int, [_P, _P]),
     "hn_plan_graph_launch": (C.c_int, [_P, _P]),
     "hn_conv_set_debug_buffer": (None, [_P]),

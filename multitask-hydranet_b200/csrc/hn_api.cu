@@ -34,6 +34,7 @@ enum OpKind { OP_CONV, OP_STEM, OP_NODE, OP_DW_MULTI, OP_POOL, OP_LANEFUSE, OP_S
 
 struct PlanOp {
     OpKind kind;
+    int branch = 0;   // 0 = trunk (caller's stream); k > 0 = independent branch k, forked after the trunk
     ConvLaunch conv;  // OP_CONV (tensor maps pre-encoded)
     hn_stem_desc stem;
     hn_node_desc node;
@@ -46,16 +47,36 @@ struct PlanOp {
     hn_lane_desc lane;
 };
 
+static constexpr int kMaxBranches = 4;
 struct hn_plan {
     std::vector<PlanOp*> ops;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
+    int cur_branch = 0;  // branch given to the ops added next
+    cudaStream_t side[kMaxBranches] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[kMaxBranches] = {nullptr, nullptr, nullptr, nullptr};
     ~hn_plan() {
         for (auto* o : ops) delete o;
         if (exec) cudaGraphExecDestroy(exec);
         if (graph) cudaGraphDestroy(graph);
+        for (int b = 0; b < kMaxBranches; ++b) {
+            if (side[b]) cudaStreamDestroy(side[b]);
+            if (ev_join[b]) cudaEventDestroy(ev_join[b]);
+        }
+        if (ev_fork) cudaEventDestroy(ev_fork);
     }
 };
+
+// Ops added after hn_plan_set_branch(p, k), k > 0, form branch k: they depend on the trunk (branch 0) ops added
+// before them but not on other branches.  hn_plan_run forks them onto the plan's own streams after the trunk and joins
+// them back into the caller's stream (inside a capture this becomes a forked graph): the three heads of the network
+// read the same pyramid and write disjoint outputs, and at small batch each of their kernels fills only a few SMs.
+extern "C" int hn_plan_set_branch(hn_plan* p, int branch) {
+    HN_REQUIRE(p != nullptr && branch >= 0 && branch <= kMaxBranches, "bad branch %d", branch);
+    HN_REQUIRE(branch >= p->cur_branch || branch == 0, "branches must be added in increasing order");
+    p->cur_branch = branch;
+    return HN_OK;
+}
 
 extern "C" int hn_plan_create(hn_plan** out) {
     HN_REQUIRE(out != nullptr, "null out");
@@ -73,6 +94,7 @@ extern "C" int hn_plan_size(const hn_plan* p) { return p ? (int)p->ops.size() : 
         HN_REQUIRE(p != nullptr && d != nullptr, "null plan/desc");          \
         PlanOp* o = new PlanOp();                                            \
         o->kind = KIND;                                                      \
+        o->branch = p->cur_branch;                                           \
         o->FIELD = *d;                                                       \
         p->ops.push_back(o);                                                 \
         return HN_OK;                                                        \
@@ -91,6 +113,7 @@ extern "C" int hn_plan_add_conv(hn_plan* p, const hn_conv_desc* d) {
     HN_REQUIRE(p != nullptr && d != nullptr, "null plan/desc");
     PlanOp* o = new PlanOp();
     o->kind = OP_CONV;
+    o->branch = p->cur_branch;
     int rc = hn_conv_prepare(d, &o->conv);
     if (rc) {
         delete o;
@@ -141,7 +164,43 @@ extern "C" int hn_plan_run_range(hn_plan* p, int first, int last, void* stream) 
 
 extern "C" int hn_plan_run(hn_plan* p, void* stream) {
     HN_REQUIRE(p != nullptr, "null plan");
-    return hn_plan_run_range(p, 0, (int)p->ops.size(), stream);
+    const int n = (int)p->ops.size();
+    int first_branch_op = n;
+    for (int i = 0; i < n; ++i)
+        if (p->ops[i]->branch > 0) { first_branch_op = i; break; }
+    if (first_branch_op == n) return hn_plan_run_range(p, 0, n, stream);
+    for (int i = first_branch_op + 1; i < n; ++i)
+        HN_REQUIRE(p->ops[i]->branch >= p->ops[i - 1]->branch, "plan: op %d (branch %d) after an op of branch %d", i,
+                   p->ops[i]->branch, p->ops[i - 1]->branch);
+    cudaStream_t main_s = reinterpret_cast<cudaStream_t>(stream);
+    int rc = hn_plan_run_range(p, 0, first_branch_op, stream);
+    if (rc) return rc;
+    if (!p->ev_fork) HN_CHECK_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    HN_CHECK_CUDA(cudaEventRecord(p->ev_fork, main_s));
+    // branch 1 stays on the caller's stream, the others go to side streams
+    int i = first_branch_op;
+    bool used[kMaxBranches] = {false, false, false, false};
+    while (i < n) {
+        const int b = p->ops[i]->branch;
+        int j = i;
+        while (j < n && p->ops[j]->branch == b) ++j;
+        if (b == p->ops[first_branch_op]->branch) {
+            rc = hn_plan_run_range(p, i, j, stream);
+        } else {
+            const int k = b - 1;
+            if (!p->side[k]) HN_CHECK_CUDA(cudaStreamCreateWithFlags(&p->side[k], cudaStreamNonBlocking));
+            if (!p->ev_join[k]) HN_CHECK_CUDA(cudaEventCreateWithFlags(&p->ev_join[k], cudaEventDisableTiming));
+            HN_CHECK_CUDA(cudaStreamWaitEvent(p->side[k], p->ev_fork, 0));
+            rc = hn_plan_run_range(p, i, j, p->side[k]);
+            if (rc == HN_OK) HN_CHECK_CUDA(cudaEventRecord(p->ev_join[k], p->side[k]));
+            used[k] = true;
+        }
+        if (rc) return rc;
+        i = j;
+    }
+    for (int k = 0; k < kMaxBranches; ++k)
+        if (used[k]) HN_CHECK_CUDA(cudaStreamWaitEvent(main_s, p->ev_join[k], 0));
+    return HN_OK;
 }
 
 extern "C" int hn_plan_graph_capture(hn_plan* p, void* stream) {

@@ -850,12 +850,16 @@ class Builder:
     def build(self, x_static):
         feats = self.backbone(x_static)
         levels = self.neck(feats)
-        if self.m.segheader is not None:
-            self.seg_head(feats[0], levels)
-        if self.m.detectheader is not None:
-            self.det_head(levels)
-        if self.m.laneheader is not None:
-            self.lane_head(levels)
+        # the heads read the same pyramid and write disjoint buffers: independent branches of the plan
+        for branch, (head, fn) in enumerate(((self.m.segheader, lambda: self.seg_head(feats[0], levels)),
+                                             (self.m.detectheader, lambda: self.det_head(levels)),
+                                             (self.m.laneheader, lambda: self.lane_head(levels))), start=1):
+            if head is None:
+                continue
+            n0 = len(self.ops)
+            fn()
+            for op in self.ops[n0:]:
+                op.branch = branch
         return self
 
 
@@ -871,8 +875,14 @@ class Plan:
         import ctypes
         self.handle = ctypes.c_void_p()
         nv.check(nv.lib.hn_plan_create(ctypes.byref(self.handle)))
+        branches = bool(getattr(model, "head_branches", False))
+        cur = 0
         for op in self.ops:
             try:
+                b = getattr(op, "branch", 0) if branches else 0
+                if b != cur:
+                    nv.check(nv.lib.hn_plan_set_branch(self.handle, b))
+                    cur = b
                 op.add_to(self.handle)
             except nv.NativeError as e:
                 raise nv.NativeError("while adding op %s: %s" % (op.name, e))

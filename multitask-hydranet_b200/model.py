@@ -63,6 +63,8 @@ class HydraNet(nn.Module):
         self._sig = None
         self._last_plan = None
         self.use_graph = False
+        # run the three heads as independent branches of the plan (forked streams / a forked CUDA graph)
+        self.head_branches = os.environ.get("HN_BRANCHES", "1") != "0"
         # batches >= 4 as two half-batch plans interleaved on two streams (engine.SplitPlan).  Off by default: measured
         # 9.67 vs 9.40 ms/step at batch 32 -- the persistent conv CTAs take a whole SM's shared memory, so kernels of the
         # two halves cannot share SMs and every launch's fixed cost is simply paid twice.
