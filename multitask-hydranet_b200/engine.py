@@ -860,6 +860,13 @@ class Builder:
             fn()
             for op in self.ops[n0:]:
                 op.branch = branch
+        # ... and so are the two detection towers (branches must be contiguous and ascending: seg 1, reg 2, cls 3, lane 4)
+        for op in self.ops:
+            b = getattr(op, "branch", 0)
+            if b == 3 or (b == 2 and op.name.startswith("det.cls")):
+                op.branch = b + 1
+        order = [getattr(op, "branch", 0) for op in self.ops]
+        assert order == sorted(order), "head ops must be grouped by branch"
         return self
 
 
