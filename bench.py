@@ -96,6 +96,8 @@ def build_model(device):
 
 
 def postproc(hb, m, out, codec, ws):
+    if m._fused_post is not None:  # serving mode: the decoders ran inside forward, in the plan's detection / lane branches
+        return m.postprocess_results()
     det = out["detection"]
     d = hb.DetectionHeader.decode_device((m.net_input_height, m.net_input_width), det["regression"], det["classification"],
                                          det["anchors"], DET_THR[0], DET_THR[1], workspace=ws)
@@ -120,6 +122,8 @@ def run_native(args):
     from hydranet_b200 import _native as nv
     B, H, W = args.batch, 640, 640
     codec = hb.LaneCodec(W, H, cfg["lane"]["anchor_stride"], int(H / cfg["lane"]["interval"]), True, 1, True)
+    if not args.no_fuse_postproc:
+        m.fuse_postprocess(det=DET_THR, lane=(codec, LANE_THR[0], LANE_THR[1], False))
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
     host = [torch.randn(B, 3, H, W, generator=g).pin_memory() for _ in range(2)]  # 157 MB each: larger than the 126 MB L2
     resident = [h.to(dev) for h in host]
@@ -367,7 +371,8 @@ def run_native(args):
                "what": "forward (CUDA graph replay) + det/lane/seg post-processing, device time"}
 
     if rank == 0:
-        n_launch = m.plan(B, H, W, dev).n_launches + 27 + 1 + 1  # forward + det (5 own + radix sort passes) + lane + u8->i64
+        # forward (+ det: 11 own kernels + radix sort / scan passes, + lane, when fused into the plan) + u8->i64
+        n_launch = m.plan(B, H, W, dev).n_launches + (1 if m._fused_post is not None else 27 + 1 + 1)
         line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
@@ -450,6 +455,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--dump-ops", action="store_true", help="write per-op device times to gpurun_out/op_times.txt")
     ap.add_argument("--e2e-probe", action="store_true", help="print the e2e loop time with upload / download switched off")
+    ap.add_argument("--no-fuse-postproc", action="store_true", help="run the decoders after forward instead of inside the plan's head branches")
     ap.add_argument("--no-latency", action="store_true", help="skip the batch-1 latency measurement")
     ap.add_argument("--no-graph", action="store_true", help="launch the forward kernel by kernel instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -273,6 +273,62 @@ class SePoolSpec:
         nv.check(nv.lib.hn_plan_add_se_pool(plan, self.to_desc()))
 
 
+class DetPostSpec:
+    """Detection decode + NMS (DetectionHeader.decode_device) as an op of the plan: runs in the detection branch, so it
+    overlaps the segmentation head instead of following the whole forward."""
+    kind, launches, group, macs = "det_post", 27, "detect", 0
+
+    def __init__(self, name, anchors, reg, cls, img_hw, conf_thres, iou_thres, dev):
+        self.name = name
+        N, A, ncls = cls.shape
+        self.anchors, self.reg, self.cls = anchors, reg, cls
+        self.ws = torch.empty(nv.lib.hn_det_workspace_bytes(N, A), dtype=torch.uint8, device=dev)
+        self.boxes = torch.zeros((N, A, 4), dtype=torch.float32, device=dev)
+        self.scores = torch.zeros((N, A), dtype=torch.float32, device=dev)
+        self.cids = torch.zeros((N, A), dtype=torch.int64, device=dev)
+        self.count = torch.zeros((N,), dtype=torch.int32, device=dev)
+        self.cand = torch.zeros((N,), dtype=torch.int32, device=dev)
+        self.desc = nv.DetDesc(anchors.data_ptr(), reg.data_ptr(), cls.data_ptr(), N, A, ncls, int(img_hw[0]), int(img_hw[1]),
+                               float(conf_thres), float(iou_thres), int(nv.NMS_AUTO_CUDA), self.ws.data_ptr(), self.ws.numel(),
+                               self.boxes.data_ptr(), self.scores.data_ptr(), self.cids.data_ptr(), self.count.data_ptr(),
+                               self.cand.data_ptr(), None)
+
+    def result(self):
+        return self.boxes, self.scores, self.cids, self.count, self.cand
+
+    def add_to(self, plan):
+        nv.check(nv.lib.hn_plan_add_det(plan, self.desc))
+
+
+class LanePostSpec:
+    """Lane decode + lane NMS (LaneHeader.decode_device) as an op of the plan (lane branch)."""
+    kind, launches, group, macs = "lane_post", 1, "lane", 0
+
+    def __init__(self, name, pcls, ploc, codec, conf_thres, nms_thres, use_mean, dev):
+        import numpy as np
+        self.name = name
+        N, na = pcls.shape[0], pcls.shape[1]
+        fh, fw, ppl = codec.feature_height, codec.feature_width, codec.points_per_line
+        assert na == fh * fw and ploc.shape[2] == 2 * ppl + 2, "lane predictions do not match the codec geometry"
+        self.ws = torch.empty(nv.lib.hn_lane_workspace_bytes(N, na, ppl), dtype=torch.uint8, device=dev)
+        self.count = torch.zeros((N,), dtype=torch.int32, device=dev)
+        self.cand = torch.zeros((N,), dtype=torch.int32, device=dev)
+        self.meta = torch.zeros((N, na, 4), dtype=torch.int32, device=dev)
+        self.prob = torch.zeros((N, na), dtype=torch.float32, device=dev)
+        self.xs = torch.zeros((N, na, ppl), dtype=torch.float32, device=dev)
+        self.desc = nv.LaneDesc(pcls.data_ptr(), ploc.data_ptr(), N, fh, fw, ppl, 0, float(np.float32(conf_thres)),
+                                float(np.float32(nms_thres)), int(bool(use_mean)), float(codec.step_w), float(codec.interval),
+                                float(codec.points_per_anchor), float(codec.input_width), 100.0, self.ws.data_ptr(),
+                                self.count.data_ptr(), self.meta.data_ptr(), self.prob.data_ptr(), self.xs.data_ptr(),
+                                self.cand.data_ptr())
+
+    def result(self):
+        return self.count, self.meta, self.prob, self.xs, self.cand
+
+    def add_to(self, plan):
+        nv.check(nv.lib.hn_plan_add_lane(plan, self.desc))
+
+
 class SeScaleSpec:
     kind, launches, group, macs = "se_scale", 1, "backbone", 0
 
@@ -812,6 +868,16 @@ class Builder:
             cs.group_out_base = bases
             self._finish(cs, [(0, 0, 0, pw.weight.detach().float().reshape(cout, C))], cout, pw.bias.detach().float())
         self.out["regression"], self.out["classification"] = reg, cls
+        post = getattr(self.m, "_fused_post", None)
+        if post and post.get("det") and self.dev.type == "cuda":
+            from .heads import make_anchors
+            conf, iou = post["det"]
+            a = self.m.detectheader.anchors
+            anc = torch.from_numpy(make_anchors((self.H, self.W), a.anchor_scale, a.strides, a.scales, a.ratios)).to(self.dev).view(-1, 4).contiguous()
+            self.keep.append(anc)
+            dp = DetPostSpec("det.post", anc, reg, cls, (self.H, self.W), conf, iou, self.dev)
+            self.ops.append(dp)
+            self.out["det_post"] = dp
 
     # -- lane head --
     def lane_head(self, levels):
@@ -846,6 +912,12 @@ class Builder:
             cs.macs = self.B * fh * fw * cout * 4 * C
             self._finish(cs, [(0, 0, 0, conv.weight.detach().float().reshape(cout, -1))], cout, conv.bias.detach().float())
         self.out["predict_cls"], self.out["predict_loc"] = pcls, ploc
+        post = getattr(self.m, "_fused_post", None)
+        if post and post.get("lane") and self.dev.type == "cuda":
+            codec, conf, nms_thres, use_mean = post["lane"]
+            lp = LanePostSpec("lane.post", pcls, ploc, codec, conf, nms_thres, use_mean, self.dev)
+            self.ops.append(lp)
+            self.out["lane_post"] = lp
 
     def build(self, x_static):
         feats = self.backbone(x_static)
@@ -863,6 +935,8 @@ class Builder:
         # ... and so are the two detection towers (branches must be contiguous and ascending: seg 1, reg 2, cls 3, lane 4)
         for op in self.ops:
             b = getattr(op, "branch", 0)
+            if "det_post" in self.out:
+                continue  # the fused NMS needs both towers: they stay one branch
             if b == 3 or (b == 2 and op.name.startswith("det.cls")):
                 op.branch = b + 1
         order = [getattr(op, "branch", 0) for op in self.ops]

@@ -61,6 +61,7 @@ class HydraNet(nn.Module):
         self.loss_detect = self.loss_seg = self.loss_cls = self.loss_reg = None
         self._plans = {}
         self._sig = None
+        self._fused_post = None
         self._last_plan = None
         self.use_graph = False
         # run the three heads as independent branches of the plan (forked streams / a forked CUDA graph)
@@ -78,7 +79,7 @@ class HydraNet(nn.Module):
         sig = self._signature()
         if sig != self._sig:  # weights changed (load_state_dict, optimizer step, .cuda()): re-pack
             self._plans, self._sig = {}, sig
-        key = (B, H, W, str(device))
+        key = (B, H, W, str(device), repr(self._fused_post and {k: v[-3:] if k == 'lane' else v for k, v in self._fused_post.items()}))
         if key not in self._plans:
             with torch.no_grad():
                 split = self.split_batch and B >= 4
@@ -130,6 +131,19 @@ class HydraNet(nn.Module):
             seg_cls = torch.empty(u8.shape, dtype=torch.int64, device=u8.device)
             nv.check(nv.lib.hn_u8_to_i64(u8.data_ptr(), seg_cls.data_ptr(), u8.numel(), stream))
         return seg_cls, anchors, regression, classification, lane_cls, lane_reg
+
+    def fuse_postprocess(self, det=None, lane=None):
+        """Serving mode: run the decoders INSIDE forward, in the detection / lane branches of the plan, so that they overlap
+        the segmentation head.  det = (conf_thres, iou_thres) as DetectionHeader.decode takes them; lane = (LaneCodec,
+        conf_thres, nms_line_thres, use_mean) as LaneHeader.decode.  ``forward`` returns what it always returns;
+        ``postprocess_results()`` hands out the decoders' device tensors (same tuples as ``decode_device``).
+        Call with no arguments to switch it off."""
+        self._fused_post = {"det": tuple(det) if det else None, "lane": tuple(lane) if lane else None} if (det or lane) else None
+
+    def postprocess_results(self):
+        """(detections, lanes) of the last forward: the tuples DetectionHeader.decode_device / LaneHeader.decode_device return."""
+        o = self._last_plan.out
+        return (o["det_post"].result() if "det_post" in o else None), (o["lane_post"].result() if "lane_post" in o else None)
 
     def seg_class_map(self):
         """uint8 [B,H,W] arg-max of the last forward's seg logits (fused into the final conv's epilogue)."""

@@ -244,3 +244,46 @@ def test_split_batch_equals_single_plan():
     for a, b, c, d, k in zip(ref, eager, g1, g2, keys):
         assert torch.equal(a, b) and torch.equal(a, c) and torch.equal(a, d), k
     assert torch.equal(u8.long(), ref[0].argmax(1)) or (u8.long() == ref[0].argmax(1)).float().mean() > 0.999
+
+
+def test_fused_postprocess_equals_separate_decoders():
+    """Serving mode (decoders inside the plan's detection / lane branches, replayed as one CUDA graph incl. the cooperative
+    NMS kernel) against the stand-alone decoders on the same head tensors: identical device results."""
+    import hydranet_b200 as hb
+    cfg = big_cfg(256, 256)
+    _, m_gpu, sd = _models(cfg)
+    x = synth.synth_input(3, 256, 256, seed=23).cuda()
+    codec = hb.LaneCodec(256, 256, cfg["lane"]["anchor_stride"], int(256 / cfg["lane"]["interval"]), True, 1, True)
+    with torch.no_grad():
+        out = m_gpu(x)
+        d_ref = [t.clone() for t in hb.DetectionHeader.decode_device((256, 256), out["detection"]["regression"], out["detection"]["classification"],
+                                                                     out["detection"]["anchors"], 0.3, 0.3)]
+        l_ref = [t.clone() for t in hb.LaneHeader.decode_device(out["lane"]["predict_cls"], out["lane"]["predict_loc"], codec, 0.3, 100, False)]
+        heads_ref = [out["seg"].clone(), out["detection"]["regression"].clone(), out["lane"]["predict_loc"].clone()]
+    assert int(d_ref[3].sum()) > 0
+    m_gpu.fuse_postprocess(det=(0.3, 0.3), lane=(codec, 0.3, 100, False))
+    try:
+        for graph in (False, True):
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s), torch.no_grad():
+                m_gpu.use_graph = graph
+                for _ in range(2):  # the second call replays the captured graph
+                    out2 = m_gpu(x)
+                    d, l = m_gpu.postprocess_results()
+                s.synchronize()
+            assert torch.equal(out2["seg"], heads_ref[0]) and torch.equal(out2["detection"]["regression"], heads_ref[1])
+            assert torch.equal(out2["lane"]["predict_loc"], heads_ref[2])
+            cnt = d[3].tolist()
+            assert cnt == d_ref[3].tolist() and torch.equal(d[4], d_ref[4])
+            for i, k in enumerate(cnt):
+                for a, b in zip(d[:3], d_ref[:3]):
+                    assert torch.equal(a[i, :k], b[i, :k])
+            lc = l[0].tolist()
+            assert lc == l_ref[0].tolist()
+            for i, k in enumerate(lc):
+                for a, b in zip(l[1:4], l_ref[1:4]):
+                    assert torch.equal(a[i, :k], b[i, :k])
+    finally:
+        m_gpu.use_graph = False
+        m_gpu.fuse_postprocess()
+        m_gpu._plans = {}

@@ -17,6 +17,8 @@ def main():
     hb, m, cfg = bench.build_model(dev)
     from hydranet_b200 import _native as nv
     codec = hb.LaneCodec(640, 640, 32, 80, True, 1, True)
+    if os.environ.get("HN_FUSE_POST", "1") != "0":
+        m.fuse_postprocess(det=bench.DET_THR, lane=(codec, bench.LANE_THR[0], bench.LANE_THR[1], False))
     x = torch.randn(B, 3, 640, 640, device=dev)
     ws = torch.empty(nv.lib.hn_det_workspace_bytes(B, 76725), dtype=torch.uint8, device=dev)
     with torch.no_grad():
