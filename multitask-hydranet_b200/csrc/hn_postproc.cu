@@ -884,6 +884,8 @@ __global__ void hn_copy_i32_kernel(const int* in, int* out, int n) {
 static void* g_det_dbg = nullptr;
 static int g_det_force_sequential = 0;
 extern "C" void hn_det_force_sequential(int on) { g_det_force_sequential = on; }
+static int g_det_rounds_ctas_per_sm = 2;
+extern "C" void hn_det_set_rounds_ctas_per_sm(int n) { g_det_rounds_ctas_per_sm = n < 1 ? 1 : n; }
 extern "C" void hn_det_set_debug_buffer(void* p) { g_det_dbg = p; }
 
 extern "C" int hn_det_decode_nms(const hn_det_desc* d, void* stream) {
@@ -945,7 +947,10 @@ extern "C" int hn_det_decode_nms(const hn_det_desc* d, void* stream) {
                 HN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, hn_nms2_rounds_kernel, 256, 0));
             int sms = hn_device_sm_count();
             // few, fat CTAs: the loop is dominated by grid-wide barriers, whose cost grows with the CTA count
-            long long want = (NA + 255) / 256, cap = (long long)sms * (blocks_per_sm > 2 ? 2 : (blocks_per_sm > 0 ? blocks_per_sm : 1));
+            // and a cooperative grid must be co-resident as a whole: with g_det_rounds_ctas_per_sm = 1 it leaves room on
+            // every SM for a persistent conv CTA of a concurrently running branch of the plan
+            const int per_sm = blocks_per_sm > g_det_rounds_ctas_per_sm ? g_det_rounds_ctas_per_sm : (blocks_per_sm > 0 ? blocks_per_sm : 1);
+            long long want = (NA + 255) / 256, cap = (long long)sms * per_sm;
             dim3 grid((unsigned)(want < cap ? want : cap));
             long long na = NA;
             void* args[] = {&ws, &na};
