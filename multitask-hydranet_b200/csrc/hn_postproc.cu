@@ -615,7 +615,7 @@ __global__ void hn_nms2_cells_kernel(DetWs ws, long long NA) {
 // predecessor list or -- atomically -- in the other box's.
 static constexpr int kBuildLanes = 1;
 static constexpr int kBuildMaxRanges = 24;
-__global__ void __launch_bounds__(256) hn_nms2_build_kernel(DetWs ws, long long NA, int nms_mode, float iou_thr, GridGeom g) {
+__global__ void __launch_bounds__(256, 6) hn_nms2_build_kernel(DetWs ws, long long NA, int nms_mode, float iou_thr, GridGeom g) {
     const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= NA || ws.ckey[slot] == 0xFFFFFFFFu) return;
     const long long i = ws.cval[slot];
