@@ -48,6 +48,8 @@ struct PlanOp {
 };
 
 static constexpr int kMaxBranches = 4;
+static int g_branch_priority = 1;
+extern "C" void hn_plan_set_branch_priority(int on) { g_branch_priority = on ? 1 : 0; }
 struct hn_plan {
     std::vector<PlanOp*> ops;
     cudaGraph_t graph = nullptr;
@@ -188,7 +190,13 @@ extern "C" int hn_plan_run(hn_plan* p, void* stream) {
             rc = hn_plan_run_range(p, i, j, stream);
         } else {
             const int k = b - 1;
-            if (!p->side[k]) HN_CHECK_CUDA(cudaStreamCreateWithFlags(&p->side[k], cudaStreamNonBlocking));
+            if (!p->side[k]) {
+                // the side branches (detection towers + NMS, lanes) are the longer ones: give their CTAs precedence over
+                // the caller-stream branch whenever an SM frees up
+                int lo = 0, hi = 0;
+                HN_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                HN_CHECK_CUDA(cudaStreamCreateWithPriority(&p->side[k], cudaStreamNonBlocking, g_branch_priority ? hi : lo));
+            }
             if (!p->ev_join[k]) HN_CHECK_CUDA(cudaEventCreateWithFlags(&p->ev_join[k], cudaEventDisableTiming));
             HN_CHECK_CUDA(cudaStreamWaitEvent(p->side[k], p->ev_fork, 0));
             rc = hn_plan_run_range(p, i, j, p->side[k]);
