@@ -339,7 +339,7 @@ def run_native(args):
         peak = pk["bf16_tflops_sustained"]
         roof = {"bound": "tensor", "kernel": "hn_conv_gemm_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s",
                 "frac": round(achieved / peak, 4), "traffic": CONV_DRAM_BYTES_PER_LAUNCH, "peak_source": pk_src + " (sustained: kernel timed inside a step)",
-                "launches_per_step": conv_n, "ms_per_step_in_kernel": round(conv_ms, 3), "share_of_forward": round(conv_ms / all_ms, 3),
+                "launches_per_step": conv_n, "ms_per_step_in_kernel": round(conv_ms, 3), "share_of_step": round(conv_ms / all_ms, 3),
                 "algorithmic_gflop_per_launch_avg": round(conv_flops / conv_n / 1e9, 3),
                 "breakdown_ms": {"%s/%s" % k: round(v[0], 3) for k, v in sorted(tot.items())}}
         # ---------------- CPU baseline: the oracle port of the reference path on the host cores ----------------
