@@ -277,6 +277,7 @@ void hn_conv_set_cluster(int ctas); /* tuning knob: CTAs per cluster sharing a w
 void hn_conv_set_pair_min_bn(int bn); /* tuning knob: narrowest N tile run on CTA pairs (default 192) */
 void hn_det_set_rounds_ctas_per_sm(int n); /* tuning knob: CTAs per SM of the cooperative NMS rounds kernel (default 2) */
 void hn_plan_set_branch_priority(int on); /* tuning knob: side branches of a plan on high-priority streams (default on) */
+void hn_det_set_rounds_passes(int n); /* tuning knob: passes over a short NMS worklist per grid barrier (default 3) */
 void hn_set_pdl(int on); /* tuning knob: programmatic dependent launch of the plan's kernels (default off: measured slower in graph replay) */
 void hn_conv_set_tap_runs(int mode); /* tuning knob: dy taps sharing one A box (0 = off, 1 = default policy, 2 = wherever they fit) */
 void hn_det_set_debug_buffer(void* device_i64); /* [N*16][8] int64 cycle counters of the NMS kernel */

@@ -145,6 +145,7 @@ SYMBOLS = {
     "hn_conv_set_cluster": (None, [C.c_int]),
     "hn_conv_set_tap_runs": (None, [C.c_int]),
     "hn_set_pdl": (None, [C.c_int]),
+    "hn_det_set_rounds_passes": (None, [C.c_int]),
     "hn_plan_set_branch_priority": (None, [C.c_int]),
     "hn_det_set_rounds_ctas_per_sm": (None, [C.c_int]),
     "hn_conv_set_pair_min_bn": (None, [C.c_int]),
@@ -176,6 +177,8 @@ if os.environ.get("HN_ROUNDS_CTAS"):
     lib.hn_det_set_rounds_ctas_per_sm(int(os.environ["HN_ROUNDS_CTAS"]))
 if os.environ.get("HN_BRANCH_PRIO"):
     lib.hn_plan_set_branch_priority(int(os.environ["HN_BRANCH_PRIO"]))
+if os.environ.get("HN_ROUNDS_PASSES"):
+    lib.hn_det_set_rounds_passes(int(os.environ["HN_ROUNDS_PASSES"]))
 if os.environ.get("HN_CLUSTER"):
     lib.hn_conv_set_cluster(int(os.environ["HN_CLUSTER"]))
 

@@ -734,7 +734,7 @@ __global__ void __launch_bounds__(256) hn_nms2_seed_kernel(DetWs ws, long long N
 // Rounds over a shrinking worklist: every round decides the boxes whose predecessors are all decided and
 // carries the rest over; the loop ends when the worklist is empty (the earliest undecided box of every
 // segment always gets decided, so every round makes progress).
-__global__ void __launch_bounds__(256) hn_nms2_rounds_kernel(DetWs ws, long long NA) {
+__global__ void __launch_bounds__(256) hn_nms2_rounds_kernel(DetWs ws, long long NA, int g_rounds_passes) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     __shared__ int s_cnt[8], s_base;
@@ -755,7 +755,7 @@ __global__ void __launch_bounds__(256) hn_nms2_rounds_kernel(DetWs ws, long long
         // Short lists are bound by the grid barrier and by load latency, not by work: walk them several times per
         // round, so that chains of dependent boxes advance more than one link per barrier (a later pass sees what
         // other threads decided meanwhile; stale reads only delay a decision, they never change it).
-        const int passes = n_cur < 400000 ? 3 : 1;
+        const int passes = n_cur < 400000 ? g_rounds_passes : 1;
         for (int pass = 0; pass < passes; ++pass)
         for (long long w = tid0; w < n_pad; w += stride) {
             bool carry = false;
@@ -885,6 +885,8 @@ static void* g_det_dbg = nullptr;
 static int g_det_force_sequential = 0;
 extern "C" void hn_det_force_sequential(int on) { g_det_force_sequential = on; }
 static int g_det_rounds_ctas_per_sm = 2;
+static int g_det_rounds_passes = 3;
+extern "C" void hn_det_set_rounds_passes(int n) { g_det_rounds_passes = n < 1 ? 1 : n; }
 extern "C" void hn_det_set_rounds_ctas_per_sm(int n) { g_det_rounds_ctas_per_sm = n < 1 ? 1 : n; }
 extern "C" void hn_det_set_debug_buffer(void* p) { g_det_dbg = p; }
 
@@ -953,7 +955,8 @@ extern "C" int hn_det_decode_nms(const hn_det_desc* d, void* stream) {
             long long want = (NA + 255) / 256, cap = (long long)sms * per_sm;
             dim3 grid((unsigned)(want < cap ? want : cap));
             long long na = NA;
-            void* args[] = {&ws, &na};
+            int passes = g_det_rounds_passes;
+            void* args[] = {&ws, &na, &passes};
             HN_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)hn_nms2_rounds_kernel, grid, dim3(256), args, 0, s));
         }
         tb = ws.cub2_bytes;
