@@ -613,7 +613,6 @@ __global__ void hn_nms2_cells_kernel(DetWs ws, long long NA) {
 // Every conflicting pair is discovered ONCE, from its smaller box: a candidate scans only its own size level and
 // the coarser ones (few, large cells) and records the edge at the later box of the pair, i.e. in its own
 // predecessor list or -- atomically -- in the other box's.
-static constexpr int kBuildLanes = 1;
 static constexpr int kBuildMaxRanges = 24;
 __global__ void __launch_bounds__(256, 6) hn_nms2_build_kernel(DetWs ws, long long NA, int nms_mode, float iou_thr, GridGeom g) {
     const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -939,7 +938,7 @@ extern "C" int hn_det_decode_nms(const hn_det_desc* d, void* stream) {
         HN_CHECK_CUDA(cudaGetLastError());
         tb = ws.cub2_bytes;
         HN_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(ws.cub2_tmp, tb, ws.cell_cnt, ws.cell_begin, (int)T, s));
-        hn_nms2_build_kernel<<<hn_cdiv(NA * kBuildLanes, 256), 256, 0, s>>>(ws, NA, d->nms_mode, d->iou_thres, geom);
+        hn_nms2_build_kernel<<<hn_cdiv(NA, 256), 256, 0, s>>>(ws, NA, d->nms_mode, d->iou_thres, geom);
         HN_CHECK_CUDA(cudaGetLastError());
         hn_nms2_seed_kernel<<<hn_cdiv(NA, 256), 256, 0, s>>>(ws, NA);
         HN_CHECK_CUDA(cudaGetLastError());
