@@ -251,7 +251,7 @@ extern "C" int64_t hn_det_workspace_bytes(int32_t N, int32_t A) {
     return (int64_t)det_layout(N, A, nullptr, nullptr);
 }
 
-int hn_det_num_launches(const hn_det_desc*) { return 11 + 16; }  // 11 own kernels + CUB sort / scan passes
+int hn_det_num_launches(const hn_det_desc*) { return 12; }  // own kernels (the two CUB radix sorts and two scans add 20 library launches)
 
 // decode (BBoxTransform + ClipBoxes, detection_loss.py:7-52), score = max over classes, threshold
 __global__ void hn_det_decode_kernel(const float* __restrict__ anchors, const float* __restrict__ reg,

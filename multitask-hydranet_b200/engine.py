@@ -276,7 +276,7 @@ class SePoolSpec:
 class DetPostSpec:
     """Detection decode + NMS (DetectionHeader.decode_device) as an op of the plan: runs in the detection branch, so it
     overlaps the segmentation head instead of following the whole forward."""
-    kind, launches, group, macs = "det_post", 27, "detect", 0
+    kind, launches, group, macs = "det_post", 12, "detect", 0
 
     def __init__(self, name, anchors, reg, cls, img_hw, conf_thres, iou_thres, dev):
         self.name = name
