@@ -79,10 +79,10 @@ class HydraNet(nn.Module):
         sig = self._signature()
         if sig != self._sig:  # weights changed (load_state_dict, optimizer step, .cuda()): re-pack
             self._plans, self._sig = {}, sig
-        key = (B, H, W, str(device), repr(self._fused_post and {k: v[-3:] if k == 'lane' else v for k, v in self._fused_post.items()}))
+        key = (B, H, W, str(device), self._fused_key())
         if key not in self._plans:
             with torch.no_grad():
-                split = self.split_batch and B >= 4
+                split = self.split_batch and B >= 4 and self._fused_post is None
                 self._plans[key] = (SplitPlan if split else Plan)(self, B, H, W, device)
         return self._plans[key]
 
@@ -139,6 +139,16 @@ class HydraNet(nn.Module):
         ``postprocess_results()`` hands out the decoders' device tensors (same tuples as ``decode_device``).
         Call with no arguments to switch it off."""
         self._fused_post = {"det": tuple(det) if det else None, "lane": tuple(lane) if lane else None} if (det or lane) else None
+
+    def _fused_key(self):
+        f = self._fused_post
+        if not f:
+            return None
+        lane = f.get("lane")
+        if lane:
+            c = lane[0]
+            lane = (c.feature_height, c.feature_width, c.points_per_line, float(c.step_w), float(c.interval)) + tuple(lane[1:])
+        return (f.get("det"), lane)
 
     def postprocess_results(self):
         """(detections, lanes) of the last forward: the tuples DetectionHeader.decode_device / LaneHeader.decode_device return."""
