@@ -56,7 +56,7 @@ def test_algorithmic_macs_match_survey():
     m = hb.HydraNet(big_cfg()).eval()
     b = engine.Builder(m, 1, 640, 640, torch.device("cpu"), act_dtype=torch.float32)
     b.build(torch.zeros(1, 3, 640, 640))
-    macs = sum(op.macs for op in b.ops if op.kind in ("conv", "stem", "node", "dw_multi"))
+    macs = sum(op.macs for op in b.ops if op.kind in ("conv", "stem", "node", "dw_multi", "se_pool"))
     assert abs(macs - 31698401632) / 31698401632 < 2e-3, macs
 
 
@@ -114,3 +114,16 @@ def test_tiling_heuristics():
     for hw in ((20, 20), (40, 40), (160, 160), (5, 5), (12, 20)):
         th, tw = engine.choose_tile(*hw)
         assert th * tw == 128
+
+
+def test_head_branches_are_contiguous_and_cover_the_heads():
+    """Plan branches (hn_plan_set_branch): trunk ops 0, then seg 1, detection towers 2 and 3, lane 4 -- ascending and
+    contiguous, which is what hn_plan_run requires to fork them after the trunk."""
+    m = hb.HydraNet(big_cfg(128, 128)).eval()
+    b = engine.Builder(m, 1, 128, 128, torch.device("cpu"), act_dtype=torch.float32).build(torch.zeros(1, 3, 128, 128))
+    br = [getattr(op, "branch", 0) for op in b.ops]
+    assert br == sorted(br) and set(br) == {0, 1, 2, 3, 4}
+    for op in b.ops:
+        want = {"seg": 1, "det.reg": 2, "det.cls": 3, "lane": 4}
+        pre = next((k for k in want if op.name.startswith(k)), None)
+        assert getattr(op, "branch", 0) == (want[pre] if pre else 0), op.name
