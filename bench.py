@@ -331,6 +331,34 @@ def run_native(args):
                     ms_i = evs[j].elapsed_time(evs[j + 1])
                     f.write("%4d %-30s %-8s %-9s %9.4f ms %8.3f GFLOP %8.2f TFLOP/s  (batch %d)\n" % (
                         j, op.name, op.kind, op.group, ms_i, 2e-9 * op.macs, 2e-9 * op.macs / max(ms_i, 1e-6), part.B))
+        # HBM-bound kernels: algorithmic bytes (every input view read once + every output view written once) / event time
+        def vbytes(v):
+            return v.N * v.H * v.W * v.C * v.t.element_size()
+
+        def op_bytes(op):
+            if op.kind == "stem":
+                return op.x.numel() * op.x.element_size() + vbytes(op.out)
+            if op.kind == "node":
+                return sum(vbytes(v) for v in op.ins) + vbytes(op.out)
+            if op.kind == "dw_multi":
+                return sum(vbytes(v) for v in op.ins) + sum(vbytes(v) for v in op.outs)
+            if op.kind == "se_pool":
+                return vbytes(op.x)
+            if op.kind == "se_scale":
+                return 2 * vbytes(op.x)
+            if op.kind == "lanefuse":
+                return sum(vbytes(v) for v in (op.p3, op.p4, op.p5, op.p6, op.out))
+            return 0
+        hbm = {}
+        for j, (part, i, op) in enumerate(units):
+            b = op_bytes(op)
+            if b:
+                a = hbm.setdefault(op.kind, [0.0, 0.0])
+                a[0] += b
+                a[1] += evs[j].elapsed_time(evs[j + 1])
+        hbm_peak = pk.get("hbm_gbs_sustained") or pk.get("hbm_gbs") or 0.0
+        hbm = {k: {"GB/s": round(v[0] / (v[1] * 1e-3) / 1e9, 1), "ms": round(v[1], 3),
+                   "frac": round(v[0] / (v[1] * 1e-3) / 1e9 / hbm_peak, 3) if hbm_peak else None} for k, v in sorted(hbm.items())}
         conv_ms = sum(v[0] for k, v in tot.items() if k[0] == "conv")
         conv_flops = 2.0 * sum(v[1] for k, v in tot.items() if k[0] == "conv")
         conv_n = sum(v[2] for k, v in tot.items() if k[0] == "conv")
@@ -341,7 +369,8 @@ def run_native(args):
                 "frac": round(achieved / peak, 4), "traffic": CONV_DRAM_BYTES_PER_LAUNCH, "peak_source": pk_src + " (sustained: kernel timed inside a step)",
                 "launches_per_step": conv_n, "ms_per_step_in_kernel": round(conv_ms, 3), "share_of_step": round(conv_ms / all_ms, 3),
                 "algorithmic_gflop_per_launch_avg": round(conv_flops / conv_n / 1e9, 3),
-                "breakdown_ms": {"%s/%s" % k: round(v[0], 3) for k, v in sorted(tot.items())}}
+                "breakdown_ms": {"%s/%s" % k: round(v[0], 3) for k, v in sorted(tot.items())},
+                "hbm_bound_kernels": hbm, "hbm_peak_gbs": hbm_peak}
         # ---------------- CPU baseline: the oracle port of the reference path on the host cores ----------------
         cpu = cpu_baseline(m, cfg, seconds=args.cpu_seconds)
 
