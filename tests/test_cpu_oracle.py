@@ -118,3 +118,41 @@ def test_preprocess_oracle_matches_cv2_live():
     lut = pp.normalize_lut()
     lv = np.arange(256, dtype=np.uint8).reshape(16, 16, 1).repeat(3, 2)
     assert np.array_equal(pp.imagenet_normalize(lv.astype(np.float32)).astype(np.float32).reshape(256, 3).T, lut)
+
+
+# ------------------------------------------------------------------ training step: golden only
+def test_train_step_golden_is_reproducible_and_product_refuses_train_mode():
+    """The training step is NOT built.  What exists is its pin: one step of train.py:241-269 run by
+    the live reference (oracle/train_golden.py).  Here: the fixture is well-formed, the live reference reproduces it when
+    present, and the product refuses train mode loudly instead of falling back."""
+    g = np.load(os.path.join(GOLD, "train_step_big_640x640.npz"))
+    for k in ("loss_total", "loss_seg", "loss_det_cls", "loss_det_reg", "loss_lane_cls_pos", "loss_lane_cls_neg", "loss_lane_loc",
+              "gradnorm.all", "gradnorm.backbone", "n_params_without_grad"):
+        assert k in g.files and np.isfinite(g[k]), k
+    assert int(g["n_params_without_grad"]) == 4  # neck.bifpn.0.p5_to_p6.* (SURVEY section 8e)
+    total = 5.0 * g["loss_seg"] + (g["loss_det_cls"] + 50.0 * g["loss_det_reg"]) + (g["loss_lane_cls_pos"] + g["loss_lane_cls_neg"] + g["loss_lane_loc"])
+    assert abs(total - g["loss_total"]) <= 1e-5 * abs(g["loss_total"])  # train.py:192-203 with the yml weights
+    m = HydraNet(big_cfg(128, 128))
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 3, 128, 128))
+    with pytest.raises(NotImplementedError):
+        m.cal_loss({}, {})
+    if not ref_live.available():
+        return
+    import copy
+    import yaml
+    from oracle import train_golden
+    ref_model, _ = ref_live.import_reference()
+    cfg = copy.deepcopy(yaml.safe_load(open("/root/reference/model/cfgs/hydranet_joint_big_backbone.yml")))
+    torch.set_num_threads(8)
+    saved = torch.Tensor.cuda
+    try:
+        if not torch.cuda.is_available():  # segmentation_loss.py:53 moves its class weights with Tensor.cuda()
+            torch.Tensor.cuda = lambda self, *a, **k: self
+        blob = train_golden.run_step(ref_model, cfg, 640, 640)
+    finally:
+        torch.Tensor.cuda = saved
+    for k in g.files:
+        a, b = np.asarray(blob[k], dtype=np.float64), np.asarray(g[k], dtype=np.float64)
+        assert np.allclose(a, b, rtol=2e-3, atol=1e-6 * max(1.0, float(np.abs(b).max()))), k
