@@ -178,7 +178,8 @@ __device__ __forceinline__ void node_fetch(const View& v, int mode, int n, int y
 
 static constexpr int kNodeTH = 8, kNodeTW = 16;         // output tile
 static constexpr int kNodeHH = kNodeTH + 2, kNodeHW = kNodeTW + 2;  // halo tile
-static constexpr int kNodeRows = 8;                       // threadIdx.y extent: one per pair of output columns
+static constexpr int kNodeCols = 1;                       // output columns per thread in phase 2
+static constexpr int kNodeRows = kNodeTW / kNodeCols;     // threadIdx.y extent: one per group of kNodeCols output columns
 
 // packed bf16x2 max (max commutes with the monotonic bf16 -> fp32 widening, so this equals max on the widened values)
 __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
@@ -278,19 +279,19 @@ __global__ void __launch_bounds__(512) hn_node_kernel(const __grid_constant__ No
 #pragma unroll
     for (int k = 0; k < 9; ++k) wgt[k] = __ldg(reinterpret_cast<const float4*>(p.dw + k * C + c));
     __syncthreads();
-    const int tx = threadIdx.y * 2;  // first of the two output columns
-    float4 acc[kNodeTH][2];
+    const int tx = threadIdx.y * kNodeCols;  // first of this thread's output columns
+    float4 acc[kNodeTH][kNodeCols];
 #pragma unroll
     for (int hy = 0; hy < kNodeHH; ++hy) {
-        float4 a[4];
+        float4 a[kNodeCols + 2];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) a[q] = *reinterpret_cast<const float4*>(s_tile + (hy * kNodeHW + tx + q) * CB + lc);
+        for (int q = 0; q < kNodeCols + 2; ++q) a[q] = *reinterpret_cast<const float4*>(s_tile + (hy * kNodeHW + tx + q) * CB + lc);
 #pragma unroll
         for (int ky = 2; ky >= 0; --ky) {  // output row o = hy - ky takes this halo row through kernel row ky
             const int o = hy - ky;
             if (o < 0 || o >= kNodeTH) continue;
 #pragma unroll
-            for (int col = 0; col < 2; ++col) {
+            for (int col = 0; col < kNodeCols; ++col) {
                 float4 v = ky == 0 ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : acc[o][col];
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(512) hn_node_kernel(const __grid_constant__ No
         if (o >= 0) {
             const int y = y0 + o;
 #pragma unroll
-            for (int col = 0; col < 2; ++col) {
+            for (int col = 0; col < kNodeCols; ++col) {
                 const int x = x0 + tx + col;
                 if (y < p.out.H && x < p.out.W) {
                     const float4 v = acc[o][col];
