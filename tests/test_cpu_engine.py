@@ -127,3 +127,26 @@ def test_head_branches_are_contiguous_and_cover_the_heads():
         want = {"seg": 1, "det.reg": 2, "det.cls": 3, "lane": 4}
         pre = next((k for k in want if op.name.startswith(k)), None)
         assert getattr(op, "branch", 0) == (want[pre] if pre else 0), op.name
+
+
+def test_serving_mode_plan_key_and_cpu_refusals():
+    """Host logic that needs no GPU: the plan cache key follows the fused decoders' configuration; CPU tensors are refused
+    loudly by the pre-processing and the forward (no CPU fallback)."""
+    m = hb.HydraNet(big_cfg(128, 128)).eval()
+    assert m._fused_key() is None
+    codec = hb.LaneCodec(128, 128, 32, 16, True, 1, True)
+    m.fuse_postprocess(det=(0.4, 0.3), lane=(codec, 0.9, 80, False))
+    k1 = m._fused_key()
+    m.fuse_postprocess(det=(0.3, 0.3), lane=(codec, 0.9, 80, False))
+    k2 = m._fused_key()
+    m.fuse_postprocess(det=(0.3, 0.3))
+    k3 = m._fused_key()
+    assert k1 != k2 and k2 != k3 and k3[1] is None
+    m.fuse_postprocess()
+    assert m._fused_key() is None
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 128, 128))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        hb.preprocess(torch.zeros((1, 8, 8, 3), dtype=torch.uint8), (4, 4))
+    with pytest.raises(TypeError):
+        hb.preprocess(torch.zeros((1, 8, 8, 3)), (4, 4))
