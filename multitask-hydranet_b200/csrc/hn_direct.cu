@@ -687,8 +687,8 @@ extern "C" int hn_lanefuse_fwd(const hn_lanefuse_desc* d, void* stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// squeeze-excite: global average pool (deterministic) and in-place channel scaling; the two FC layers
-// in between run as tensor-core GEMMs over all images at once (engine.py)
+// squeeze-excite: global average pool (deterministic) + the two FC layers of the gate in one launch, and the
+// in-place channel scaling
 // ------------------------------------------------------------------------------------------------
 static constexpr int kSeThreads = 512;
 
