@@ -151,7 +151,8 @@ class HydraNet(nn.Module):
         return (f.get("det"), lane)
 
     def postprocess_results(self):
-        """(detections, lanes) of the last forward: the tuples DetectionHeader.decode_device / LaneHeader.decode_device return."""
+        """(detections, lanes) of the last forward: the tuples DetectionHeader.decode_device / LaneHeader.decode_device return.
+        They are the plan's static buffers: valid until the next forward of the same shape (clone to keep them)."""
         o = self._last_plan.out
         return (o["det_post"].result() if "det_post" in o else None), (o["lane_post"].result() if "lane_post" in o else None)
 
