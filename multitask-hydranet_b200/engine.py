@@ -282,7 +282,7 @@ class DetPostSpec:
         self.name = name
         N, A, ncls = cls.shape
         self.anchors, self.reg, self.cls = anchors, reg, cls
-        self.ws = torch.empty(nv.lib.hn_det_workspace_bytes(N, A), dtype=torch.uint8, device=dev)
+        self.ws = torch.zeros(nv.lib.hn_det_workspace_bytes(N, A), dtype=torch.uint8, device=dev)
         self.boxes = torch.zeros((N, A, 4), dtype=torch.float32, device=dev)
         self.scores = torch.zeros((N, A), dtype=torch.float32, device=dev)
         self.cids = torch.zeros((N, A), dtype=torch.int64, device=dev)
@@ -385,28 +385,27 @@ def choose_tile(H, W):
 
 
 def pack_weight(entries, cout, bn, wdtype, device):
-    """entries: [(src, dy, dx, W[cout, Csrc])] -> (taps, K-major matrix [rows_pad, ntaps*64])."""
-    taps, cols = [], []
+    """entries: [(src, dy, dx, W[cout, Csrc])] -> (taps, K-major matrix [rows_pad, ntaps*64]).  Assembled where the weights
+    live (the CPU shadow of the parameters) and uploaded once."""
+    taps, spans, k = [], [], 0
     for (s, dy, dx, wt) in entries:
         cs = wt.shape[1]
         for c0 in range(0, cs, 64):
-            w = min(64, cs - c0)
-            blk = torch.zeros((cout, 64), dtype=torch.float32, device=device)
-            blk[:, :w] = wt[:, c0:c0 + w]
             taps.append((s, dy, dx, c0))
-            cols.append(blk)
-    wm = torch.cat(cols, 1)
+            spans.append((wt, c0, min(64, cs - c0), k))
+            k += 64
     rows = (cout + bn - 1) // bn * bn
-    out = torch.zeros((rows, wm.shape[1]), dtype=torch.float32, device=device)
-    out[:cout] = wm
-    return taps, out.to(wdtype).contiguous()
+    out = torch.zeros((rows, k), dtype=torch.float32, device=entries[0][3].device)
+    for wt, c0, w, k0 in spans:
+        out[:cout, k0:k0 + w] = wt[:, c0:c0 + w]
+    return taps, out.to(wdtype).contiguous().to(device)
 
 
-def pad_bias(b, cout, bn):
+def pad_bias(b, cout, bn, device=None):
     rows = (cout + bn - 1) // bn * bn
     out = torch.zeros(rows, dtype=torch.float32, device=b.device)
     out[:cout] = b
-    return out
+    return out.to(device) if device is not None else out
 
 
 # row/column tap sets of the parity-collapsed up-sampled 3x3 conv: parity -> [(source shift, [k...])]
@@ -444,7 +443,7 @@ class Builder:
         cs.cout = cout
         cs.bn = bn or choose_bn(cout)
         cs.taps, cs.weight = pack_weight(entries, cout, cs.bn, self.dt, self.dev)
-        cs.bias = pad_bias(bias.to(self.dev), cout, cs.bn)
+        cs.bias = pad_bias(bias, cout, cs.bn, self.dev)
         cs.stages = choose_stages(cs.bn, len(cs.taps))
         self.ops.append(cs)
         return cs
@@ -593,7 +592,7 @@ class Builder:
                     wm[co, t * 64 + base + j] = w[:, j, ky, kx]
         cs.cout, cs.bn = C, bn_t
         cs.taps, cs.weight = taps, wm.to(self.dt).contiguous().to(self.dev)
-        cs.bias = pad_bias(b.to(self.dev), C, bn_t)
+        cs.bias = pad_bias(b, C, bn_t, self.dev)
         cs.stages = choose_stages(bn_t, 9)
         cs.macs = ob.N * ob.H * ob.W * C * 8 * 9
         self.ops.append(cs)
@@ -836,14 +835,14 @@ class Builder:
                 cs.out_t, cs.out_off, cs.out_strides = ot, 0, (R * C, 0, C)
                 cs.macs = R * C * C
                 cs.group_end = list(ends)
-                self._finish(cs, [(0, 0, 0, pw.weight.detach().float().reshape(C, C))], C, torch.zeros(C))
+                self._finish(cs, [(0, 0, 0, pw.weight.detach().float().reshape(C, C))], C, torch.zeros(C, device=pw.weight.device))
                 scales, shifts = [], []
                 for li in range(len(levels)):
                     bn = tower.bn_list[li][i]
                     sc = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
                     sh = (pw.bias.detach().float() - bn.running_mean.detach().float()) * sc + bn.bias.detach().float()
-                    scales.append(pad_bias(sc.to(self.dev), C, cs.bn))
-                    shifts.append(pad_bias(sh.to(self.dev), C, cs.bn))
+                    scales.append(pad_bias(sc, C, cs.bn, self.dev))
+                    shifts.append(pad_bias(sh, C, cs.bn, self.dev))
                 cs.group_scale, cs.group_shift = torch.stack(scales).contiguous(), torch.stack(shifts).contiguous()
                 cur = ov
             sep = tower.header
@@ -950,7 +949,8 @@ class Plan:
     def __init__(self, model, B, H, W, device, x=None, out_alloc=None):
         self.B, self.H, self.W, self.device = B, H, W, device
         self.x = x if x is not None else torch.zeros((B, 3, H, W), dtype=torch.float32, device=device)
-        self.builder = Builder(model, B, H, W, device, out_alloc=out_alloc).build(self.x)
+        src = model.packing_source() if hasattr(model, "packing_source") else model
+        self.builder = Builder(src, B, H, W, device, out_alloc=out_alloc).build(self.x)
         self.ops = self.builder.ops
         self.out = self.builder.out
         import ctypes

@@ -54,7 +54,8 @@ class SegmentHeader(nn.Module):
             m = m.float().contiguous()
         B, Cc, H, W = m.shape
         out = torch.empty((B, H, W), dtype=torch.int64, device=m.device)
-        nv.check(nv.lib.hn_seg_argmax(m.data_ptr(), B, Cc, H * W, out.data_ptr(), None, _stream_ptr(m.device)))
+        with torch.cuda.device(m.device):
+            nv.check(nv.lib.hn_seg_argmax(m.data_ptr(), B, Cc, H * W, out.data_ptr(), None, _stream_ptr(m.device)))
         return out
 
     @staticmethod
@@ -163,7 +164,7 @@ class DetectionHeader(nn.Module):
         pre = pre_boxes.detach().float().contiguous() if pre_boxes is not None else None
         nbytes = nv.lib.hn_det_workspace_bytes(N, A)
         if workspace is None or workspace.numel() < nbytes:
-            workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            workspace = torch.zeros(nbytes, dtype=torch.uint8, device=dev)  # zeroed: the rounds kernel's masked int4 loads read past list ends
         boxes = torch.empty((N, A, 4), dtype=torch.float32, device=dev)
         scores = torch.empty((N, A), dtype=torch.float32, device=dev)
         cids = torch.empty((N, A), dtype=torch.int64, device=dev)
@@ -173,7 +174,8 @@ class DetectionHeader(nn.Module):
                        cls.data_ptr(), N, A, ncls, int(img_hw[0]), int(img_hw[1]), float(conf_thres), float(iou_thres),
                        int(nms_mode), workspace.data_ptr(), workspace.numel(), boxes.data_ptr(), scores.data_ptr(),
                        cids.data_ptr(), count.data_ptr(), cand.data_ptr(), pre.data_ptr() if pre is not None else None)
-        nv.check(nv.lib.hn_det_decode_nms(d, _stream_ptr(dev)))
+        with torch.cuda.device(dev):
+            nv.check(nv.lib.hn_det_decode_nms(d, _stream_ptr(dev)))
         return boxes, scores, cids, count[:N], cand[:N]
 
     @staticmethod
@@ -194,8 +196,45 @@ class DetectionHeader(nn.Module):
         return out
 
     @staticmethod
+    def class_color(index, n):
+        """BGR colour of class ``index`` of ``n``: evenly spaced hues (the reference looks CSS colour names up through
+        ``webcolors``, display.py:35-51 -- cosmetic, and that package is not a dependency here)."""
+        import colorsys
+        r, g, b = colorsys.hsv_to_rgb((index % max(n, 1)) / float(max(n, 1)), 0.75, 1.0)
+        return int(b * 255), int(g * 255), int(r * 255)
+
+    @staticmethod
     def display(decode, imgs, obj_list, org_size, target_size):
-        raise NotImplementedError("drawing is outside the hot path (SURVEY.md section 2.1 row 11)")
+        """Draw the decoded boxes on the original-size frames (detection.py:247-252 -> display.py:53-84).
+
+        ``decode``: list of {'rois','class_ids','scores'} in network-input pixels; boxes are truncated to int, scaled by
+        org_size / target_size and drawn with a '<class><score %>' tag.  As in the reference, the list is returned after
+        the first frame that has detections (display.py:84 returns inside its loop; demo.py runs batch 1), and frames
+        without detections are returned untouched."""
+        import cv2
+        sx, sy = org_size[0] / float(target_size[0]), org_size[1] / float(target_size[1])
+        for i in range(len(imgs)):
+            rois = decode[i]['rois']
+            if len(rois) == 0:
+                continue
+            canvas = imgs[i] = imgs[i].copy()
+            thick = int(round(0.003 * max(canvas.shape[0:2]))) or 1
+            font_thick, font_scale = max(thick - 2, 1), float(thick) / 3
+            for box, cid, score in zip(rois, decode[i]['class_ids'], decode[i]['scores']):
+                x1, y1, x2, y2 = (int(v) for v in box)
+                p1 = (int(x1 * sx), int(y1 * sy))
+                p2 = (int(x2 * sx), int(y2 * sy))
+                name = obj_list[int(cid)]
+                colour = DetectionHeader.class_color(obj_list.index(name), len(obj_list))
+                cv2.rectangle(canvas, p1, p2, colour, thickness=thick)
+                pct = '{:.0%}'.format(float(score))
+                (tw, th), _ = cv2.getTextSize(name, 0, fontScale=font_scale, thickness=font_thick)
+                (sw, _), _ = cv2.getTextSize(pct, 0, fontScale=font_scale, thickness=font_thick)
+                cv2.rectangle(canvas, p1, (p1[0] + tw + sw + 15, p1[1] - th - 3), colour, -1)
+                cv2.putText(canvas, name + pct, (p1[0], p1[1] - 2), 0, font_scale, [0, 0, 0], thickness=font_thick,
+                            lineType=cv2.FONT_HERSHEY_SIMPLEX)
+            return imgs
+        return imgs
 
 
 # ------------------------------------------------------------------------------------------------
@@ -246,7 +285,8 @@ class LaneHeader(nn.Module):
                         float(pointlane.step_w), float(pointlane.interval), float(pointlane.points_per_anchor),
                         float(pointlane.input_width), 100.0, ws.data_ptr(), count.data_ptr(), meta.data_ptr(),
                         prob.data_ptr(), xs.data_ptr(), cand.data_ptr())
-        nv.check(nv.lib.hn_lane_decode_nms(d, _stream_ptr(dev)))
+        with torch.cuda.device(dev):
+            nv.check(nv.lib.hn_lane_decode_nms(d, _stream_ptr(dev)))
         return count, meta, prob, xs, cand
 
     @staticmethod
@@ -277,4 +317,29 @@ class LaneHeader(nn.Module):
 
     @staticmethod
     def visual(imgs, predict_jsons, org_width=1920, min_length=2, filter_vertical=True, filter_thres=65):
-        raise NotImplementedError("drawing is outside the hot path (SURVEY.md section 2.1 row 11)")
+        """Draw lanes (``scale_to_org(...)["Lines"]`` per frame) in place on the frames (lanedetect.py:126-178): lines shorter
+        than ``min_length`` points are skipped, so are -- with ``filter_vertical`` -- lines whose least-squares slope is
+        steeper than ``filter_thres`` degrees; each lane is a 15-px polyline plus a 'Lane: <score>' tag."""
+        import cv2
+        out = []
+        for frame, lines in zip(imgs, predict_jsons):
+            for line in lines:
+                pts = [(int(p["x"]), int(p["y"])) for p in line["points"]]
+                if len(pts) < min_length:
+                    continue
+                if filter_vertical:
+                    arr = np.array(pts)
+                    slope = np.polyfit(arr[:, 0], arr[:, 1], 1)[0]
+                    if abs(np.arctan(slope)) / 3.1415 * 180 > filter_thres:
+                        continue
+                for a, b in zip(pts[:-1], pts[1:]):
+                    frame = cv2.line(frame, a, b, color=(255, 255, 0), thickness=15)
+                tx, ty = pts[min_length - 1]
+                if tx < 0:
+                    tx = 30
+                if tx > org_width:
+                    tx, ty = org_width - 300, ty - 60
+                cv2.putText(frame, "%s: %.2f" % ("Lane", float(line["score"])), (tx, ty - 10), cv2.FONT_HERSHEY_SIMPLEX, 2.0,
+                            (255, 255, 0), 7)
+            out.append(frame)
+        return out

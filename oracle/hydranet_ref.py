@@ -13,11 +13,25 @@ Reference call sites restated (all under /root/reference/model):
   lane       head_lane/lanedetect.py:66-96
   facade     model.py:159-198
 """
+import contextlib
 import itertools
 
 import numpy as np
 import torch
 import torch.nn.functional as F
+
+
+@contextlib.contextmanager
+def ieee_fp32():
+    """True fp32 on CUDA: torch's defaults let cuDNN convolutions (and, if enabled, matmuls) run on TF32 tensor cores
+    (10-bit mantissa) -- useless as a parity oracle for a bf16 engine.  Every oracle forward runs inside this guard."""
+    conv, mm = torch.backends.cudnn.conv.fp32_precision, torch.backends.cuda.matmul.fp32_precision
+    torch.backends.cudnn.conv.fp32_precision = "ieee"
+    torch.backends.cuda.matmul.fp32_precision = "ieee"
+    try:
+        yield
+    finally:
+        torch.backends.cudnn.conv.fp32_precision, torch.backends.cuda.matmul.fp32_precision = conv, mm
 
 
 def _bn(sd, p, x, eps):
@@ -198,7 +212,12 @@ def lane_head(sd, fused, stride, num_classes, n_loc):
 
 
 def forward(sd, cfg, x, want_feats=False):
-    """state_dict + cfg + fp32 NCHW input -> the reference's output dict (model.py:159-192)."""
+    """state_dict + cfg + fp32 NCHW input -> the reference's output dict (model.py:159-192).  IEEE fp32 on any device."""
+    with ieee_fp32():
+        return _forward(sd, cfg, x, want_feats)
+
+
+def _forward(sd, cfg, x, want_feats=False):
     sd = {k: v.to(x.device) for k, v in sd.items()}
     feats = backbone(sd, x, cfg["backbone"]["group_width"], cfg["backbone"]["stride"])
     fused = neck(sd, feats)

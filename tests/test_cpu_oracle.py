@@ -121,10 +121,10 @@ def test_preprocess_oracle_matches_cv2_live():
 
 
 # ------------------------------------------------------------------ training step: golden only
-def test_train_step_golden_is_reproducible_and_product_refuses_train_mode():
-    """The training step is NOT built.  What exists is its pin: one step of train.py:241-269 run by
-    the live reference (oracle/train_golden.py).  Here: the fixture is well-formed, the live reference reproduces it when
-    present, and the product refuses train mode loudly instead of falling back."""
+def test_train_step_golden_is_reproducible_and_product_refuses_cpu():
+    """The pin of the training step: one step of train.py:241-269 run by the live reference (oracle/train_golden.py).
+    Here: the fixture is well-formed, the live reference reproduces it when present, and the product refuses CPU tensors
+    in train mode loudly instead of falling back (tests/test_gpu_train.py reproduces the fixture on the GPU)."""
     g = np.load(os.path.join(GOLD, "train_step_big_640x640.npz"))
     for k in ("loss_total", "loss_seg", "loss_det_cls", "loss_det_reg", "loss_lane_cls_pos", "loss_lane_cls_neg", "loss_lane_loc",
               "gradnorm.all", "gradnorm.backbone", "n_params_without_grad"):
@@ -134,10 +134,8 @@ def test_train_step_golden_is_reproducible_and_product_refuses_train_mode():
     assert abs(total - g["loss_total"]) <= 1e-5 * abs(g["loss_total"])  # train.py:192-203 with the yml weights
     m = HydraNet(big_cfg(128, 128))
     m.train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):  # train mode runs on the native kernels too: no CPU fallback
         m(torch.zeros(1, 3, 128, 128))
-    with pytest.raises(NotImplementedError):
-        m.cal_loss({}, {})
     if not ref_live.available():
         return
     import copy
