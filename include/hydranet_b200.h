@@ -107,6 +107,7 @@ typedef struct hn_stem_desc {
     const float* w; /* [27][32] fp32, BN folded: index (ci*9+ky*3+kx)*32+co */
     const float* b; /* [32] */
     hn_view out;    /* [N][H/2][W/2][32] */
+    int32_t no_relu; /* 1: raw convolution output (training: BatchNorm follows as its own op) */
 } hn_stem_desc;
 
 #define HN_IN_SAME 0
@@ -270,6 +271,207 @@ int hn_plan_run(hn_plan* p, void* stream);
 int hn_plan_run_range(hn_plan* p, int first, int last, void* stream);
 int hn_plan_graph_capture(hn_plan* p, void* stream); /* instantiate a CUDA graph of the whole plan */
 int hn_plan_graph_launch(hn_plan* p, void* stream);
+
+
+/* =====================================================================================================================
+ * Training step (reference: model/train.py:241-269 -- forward in train mode, cal_loss,
+ * backward, Adam).  The reference runs it through PyTorch autograd over cuDNN; here every layer's forward / backward is
+ * one of the entry points below (plus hn_conv_fwd, which also serves as the data-gradient GEMM: dgrad of a convolution
+ * is a convolution of the output gradient with the transposed, spatially flipped filter).
+ * Activations and activation gradients: bf16, NHWC, as `hn_view`s or as row matrices `hn_mat` ([pixels][channels]).
+ * Parameters and parameter gradients: fp32 in the reference's own layouts (OIHW filters).
+ * ===================================================================================================================== */
+
+/* bf16 row-major matrix [rows][cols], `ld` elements between rows; cols and ld multiples of 8, ptr 16-byte aligned. */
+typedef struct hn_mat {
+    void* ptr;
+    int64_t rows;
+    int32_t cols;
+    int64_t ld;
+} hn_mat;
+
+#define HN_MAX_SEG 8
+
+/* BatchNorm2d in training mode (+ activation, + residual): nn.BatchNorm2d.forward with batch statistics and the
+ * running-statistics update (anynet.py:14-17,31-60; common.py:95-99; detection.py:20-24 per-level lists; lanedetect.py:48).
+ * Row segments carry independent statistics / parameters: the pyramid levels of a detection tower layer are one
+ * stacked matrix with five BatchNorms.
+ *   fwd: mean/var over the rows of each segment (deterministic two-level sum), running stats updated in place
+ *        (momentum, unbiased variance), y = act(z * scale + shift [+ res]).
+ *   bwd: dz_act = dy * act'(.), dgamma = sum dz_act * xhat, dbeta = sum dz_act,
+ *        dz = gamma * invstd * (dz_act - mean(dz_act) - xhat * mean(dz_act * xhat)); dres = dz_act (optional). */
+typedef struct hn_bn_desc {
+    hn_mat z;
+    int32_t n_seg;
+    int64_t seg_end[HN_MAX_SEG]; /* exclusive row end of each segment */
+    const float* gamma[HN_MAX_SEG];
+    const float* beta[HN_MAX_SEG];
+    float* running_mean[HN_MAX_SEG]; /* may be NULL (no update) */
+    float* running_var[HN_MAX_SEG];
+    float eps, momentum;
+    float* stats;   /* fp32 [n_seg][4][cols]: mean, invstd, scale, shift -- written by fwd, read by bwd */
+    int32_t act;    /* HN_ACT_NONE / HN_ACT_RELU / HN_ACT_SWISH */
+    hn_mat res;     /* optional residual (ptr NULL = none), added before the activation */
+    hn_mat y;       /* fwd output; bwd: the saved output (ReLU mask) */
+    float* scratch; /* device scratch for partial sums */
+    int64_t scratch_bytes;
+    hn_mat dy;      /* bwd in */
+    hn_mat dz;      /* bwd out: gradient of z */
+    hn_mat dres;    /* bwd out (optional): gradient of the residual input */
+    float* dgamma[HN_MAX_SEG]; /* fp32 [cols], written */
+    float* dbeta[HN_MAX_SEG];
+} hn_bn_desc;
+int hn_bn_train_fwd(const hn_bn_desc* d, void* stream);
+int hn_bn_train_bwd(const hn_bn_desc* d, void* stream);
+
+/* Column reductions over the rows of `a` (deterministic): per segment of `rows_per_seg` consecutive rows
+ * (0 = one segment).  mode 0: out0 = sum a, out1 = sum a^2 (out1 may be NULL); mode 1: out0 = sum a*b.
+ * Serves bias gradients, squeeze-excite pooling (segments = images) and the fusion-weight gradients. */
+int hn_col_reduce(const hn_mat* a, const hn_mat* b, int32_t mode, int64_t rows_per_seg, float* out0, float* out1,
+                  float scale, float* scratch, int64_t scratch_bytes, void* stream);
+
+/* dz = dy * act'(ref): ref is the layer OUTPUT for ReLU / ELU / sigmoid and the PRE-activation for swish.
+ * Up to 3 extra scaled copies out[k] = w[k] * dz (the inputs of a BiFPN fusion node, bifpn.py:170-231). */
+typedef struct hn_actbwd_desc {
+    hn_mat dy, ref, dz;
+    int32_t act;
+    int32_t n_scaled;
+    hn_mat scaled[3];
+    const float* w; /* device, fp32 [n_scaled] (the normalised fusion weights live on the device: no host sync) */
+} hn_actbwd_desc;
+int hn_act_bwd(const hn_actbwd_desc* d, void* stream);
+
+/* s = sum_i w[i] * in[i]; a = swish(s) (both stored: s feeds the backward).  bifpn.py:170-231. */
+typedef struct hn_wsum_desc {
+    int32_t n_in;
+    hn_mat in[3];
+    const float* w; /* device, fp32 [n_in] */
+    hn_mat s, a;
+} hn_wsum_desc;
+int hn_wsum_swish_fwd(const hn_wsum_desc* d, void* stream);
+
+/* Re-sampling ops and their adjoints.  mode: HN_RS_UP2 nearest x2 (F.interpolate / upsample), HN_RS_POOL_ZERO
+ * (MaxPool2dStaticSamePadding(3,2), common.py:117-151), HN_RS_POOL_NEGINF (nn.MaxPool2d(3,2,1), lanedetect.py:41).
+ * bwd: din = adjoint(dout); pooling routes each output gradient to the FIRST maximum of its window in scan order
+ * (PyTorch's max_pool2d backward); `x` is the forward input. */
+#define HN_RS_UP2 0
+#define HN_RS_POOL_ZERO 1
+#define HN_RS_POOL_NEGINF 2
+typedef struct hn_resample_desc {
+    int32_t mode;
+    hn_view x;    /* forward input */
+    hn_view y;    /* forward output (fwd: written) */
+    hn_view dy;   /* bwd in */
+    hn_view dx;   /* bwd out */
+} hn_resample_desc;
+int hn_resample_fwd(const hn_resample_desc* d, void* stream);
+int hn_resample_bwd(const hn_resample_desc* d, void* stream);
+
+/* Segmentation-decoder input assembly (segmentation.py:84-105): out = ReflectionPad2d(1)(cat(up2(low), skip)),
+ * either part optional (low NULL: plain reflect pad of skip).  bwd folds the halo back and sums the 2x2 blocks. */
+typedef struct hn_seggather_desc {
+    hn_view low;   /* [N][H/2][W/2][Cl] or ptr NULL */
+    hn_view skip;  /* [N][H][W][Cs] or ptr NULL */
+    hn_view out;   /* [N][H+2][W+2][Cl+Cs] (fwd out / bwd in: gradient of the padded tensor) */
+    hn_view dlow, dskip; /* bwd out */
+} hn_seggather_desc;
+int hn_seggather_fwd(const hn_seggather_desc* d, void* stream);
+int hn_seggather_bwd(const hn_seggather_desc* d, void* stream);
+
+/* fp32 head tensors <-> bf16 gradient rows.  The reference's head outputs are [B, sum_l H_l*W_l*A, k] (detection.py:40-43),
+ * [B, H*W, k] (lanedetect.py:84-96) and NCHW logits (segmentation.py:105); their gradients arrive from the PyTorch
+ * losses in those layouts.  dz[row][c] = dout[addr(row) + c * stride_c] * act'(out[...]) for c < cols_valid, 0 up to dz.cols.
+ * Row addressing: plain (n = row / rows_per_img, pix = row % rows_per_img: n*stride_n + pix*stride_pix) or by row groups
+ * as in hn_conv_desc (group_addr). */
+typedef struct hn_headgrad_desc {
+    const float* dout;
+    const float* out; /* saved forward output (sigmoid) or NULL */
+    int32_t act;      /* HN_ACT_NONE or HN_ACT_SIGMOID */
+    int32_t cols_valid;
+    int64_t stride_n, stride_pix, stride_c;
+    int64_t rows_per_img;
+    int32_t n_groups;
+    int64_t group_end[HN_MAX_GROUPS];
+    int64_t group_hw[HN_MAX_GROUPS];
+    int64_t group_out_base[HN_MAX_GROUPS];
+    hn_mat dz;
+} hn_headgrad_desc;
+int hn_head_grad(const hn_headgrad_desc* d, void* stream);
+
+/* Depthwise 3x3 weight gradient: dw[tap][c] = sum_{n,y,x} dy[n,y,x,c] * x[n,y+ky-1,x+kx-1,c] (zero padding),
+ * fp32 [9][C]; accumulate != 0 adds to dw (shared filters applied to several pyramid levels). */
+int hn_dw_wgrad(const hn_view* x, const hn_view* dy, float* dw, int32_t accumulate, float* scratch, int64_t scratch_bytes,
+                void* stream);
+
+/* Stem weight gradient (anynet.py:8-20): dW[co][ci][ky][kx] = sum dz[n,oy,ox,co] * x[n,ci,2oy+ky-1,2ox+kx-1]. */
+int hn_stem_wgrad(const float* x, int32_t N, int32_t H, int32_t W, const hn_view* dz, float* dw, float* scratch,
+                  int64_t scratch_bytes, void* stream);
+
+/* Squeeze-excite in training (anynet.py:39-47,68-69), fp32 vectors: mean [N][C] -> h = relu(W1 mean + b1) [N][S]
+ * -> gate = sigmoid(W2 h + b2) [N][C]; parameters fp32 in the reference layout ([S][C], [C][S]). */
+typedef struct hn_sefc_desc {
+    int32_t N, C, S;
+    const float* mean;
+    const float *w1, *b1, *w2, *b2;
+    float *h, *gate;
+    /* bwd */
+    const float* dgate; /* [N][C] gradient of the gate */
+    float* dmean;       /* [N][C] out */
+    float *dw1, *db1, *dw2, *db2; /* out (written) */
+    float* tmp;         /* scratch fp32 [N][C + S] */
+} hn_sefc_desc;
+int hn_se_fc_fwd(const hn_sefc_desc* d, void* stream);
+int hn_se_fc_bwd(const hn_sefc_desc* d, void* stream);
+/* y[n, pix, c] = x[n, pix, c] * gate[n][c] (+ add[n][c]);  rows_per_img rows per image. */
+int hn_se_apply(const hn_mat* x, const float* gate, const float* add, int64_t rows_per_img, const hn_mat* y, void* stream);
+
+/* Weight packing for the GEMM kernels, all layers in one launch: fp32 parameters -> bf16 K-major blocks.
+ * One entry = one 64-wide K block of one packed matrix: dst[r][j] = src[off + r*s_r + j*s_c] for r < rows, j < cols
+ * (0 elsewhere up to rows_pad x 64); grouped: only the 8x8 diagonal blocks of a group-width-8 convolution. */
+typedef struct hn_pack_entry {
+    const float* src;
+    void* dst;       /* bf16, first element of the block (row 0, column j0) */
+    int64_t dst_ld;  /* elements between packed rows */
+    int32_t rows, rows_pad, cols;
+    int64_t s_r, s_c; /* source strides (elements) */
+    int32_t grouped;  /* 0 plain; 1 forward grouped (row = co, col = ci within the 64-block); 2 dgrad grouped */
+    int32_t rsv;
+} hn_pack_entry;
+int hn_pack_weights(const hn_pack_entry* entries_device, int32_t n, int32_t max_rows_pad, void* stream);
+
+/* Convolution weight gradient on tcgen05: dW[co][tap][ci] += sum_pixels dY[pix][co] * X[pix + tap][ci].
+ * Both operands are read through TMA as MN-major tiles ([pixel][channel] rows), K = pixels; split-K partial sums are
+ * added with fp32 reductions into `dw`, which must be zero (or hold the value to accumulate onto) on entry.
+ * Element (co, tap t, ci) lives at dw[co*s_co + ci*s_ci + tap_off[t]]. */
+typedef struct hn_wgrad_desc {
+    hn_view dy;              /* [N][H][W][Cout] (or flat rows: N=H=1) */
+    hn_view src[HN_MAX_SRC]; /* input views, as in the forward conv */
+    int32_t n_src;
+    int32_t num_taps;
+    hn_tap taps[HN_MAX_TAPS]; /* (source, dy, dx, c0): c0 = first input channel of this K block in its source */
+    int64_t tap_off[HN_MAX_TAPS]; /* dw offset of (co = 0, ci = c0) for this tap */
+    int32_t tap_cin[HN_MAX_TAPS]; /* valid input channels of the block (<= 64) */
+    int32_t flat;
+    int32_t tile_h, tile_w;
+    int32_t cout;
+    int64_t s_co, s_ci;
+    int32_t grouped; /* 1: group width 8 -- only ci in the row's group are stored, at ci_local * s_ci */
+    float* dw;
+} hn_wgrad_desc;
+int hn_conv_wgrad(const hn_wgrad_desc* d, void* stream);
+
+/* Adam step over many tensors in one launch (torch.optim.Adam semantics, train.py:147: L2 weight decay added to the
+ * gradient, bias-corrected moments).  Tensor table on the device. */
+typedef struct hn_adam_tensor {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    int64_t n;
+} hn_adam_tensor;
+int hn_adam_step(const hn_adam_tensor* tensors_device, const int32_t* chunk_tensor_device, const int32_t* chunk_index_device,
+                 int32_t n_chunks, int32_t chunk_elems, float lr, float beta1, float beta2, float eps, float weight_decay,
+                 int32_t step, float grad_scale, void* stream);
 
 /* diagnostics: when set (before a conv is prepared), every conv CTA stores 16 int64 globaltimer stamps */
 void hn_conv_set_debug_buffer(void* device_i64);

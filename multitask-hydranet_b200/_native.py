@@ -50,7 +50,7 @@ class ConvDesc(C.Structure):
 
 class StemDesc(C.Structure):
     _fields_ = [("x", C.c_void_p), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
-                ("w", C.c_void_p), ("b", C.c_void_p), ("out", View)]
+                ("w", C.c_void_p), ("b", C.c_void_p), ("out", View), ("no_relu", C.c_int32)]
 
 
 class NodeDesc(C.Structure):
@@ -104,6 +104,73 @@ class LaneDesc(C.Structure):
                 ("out_cand", C.c_void_p)]
 
 
+
+# ---- training step (include/hydranet_b200.h, "Training step") ----
+HN_MAX_SEG = 8
+RS_UP2, RS_POOL_ZERO, RS_POOL_NEGINF = range(3)
+
+
+class Mat(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("rows", C.c_int64), ("cols", C.c_int32), ("ld", C.c_int64)]
+
+
+class BnDesc(C.Structure):
+    _fields_ = [("z", Mat), ("n_seg", C.c_int32), ("seg_end", C.c_int64 * HN_MAX_SEG),
+                ("gamma", C.c_void_p * HN_MAX_SEG), ("beta", C.c_void_p * HN_MAX_SEG),
+                ("running_mean", C.c_void_p * HN_MAX_SEG), ("running_var", C.c_void_p * HN_MAX_SEG),
+                ("eps", C.c_float), ("momentum", C.c_float), ("stats", C.c_void_p), ("act", C.c_int32),
+                ("res", Mat), ("y", Mat), ("scratch", C.c_void_p), ("scratch_bytes", C.c_int64),
+                ("dy", Mat), ("dz", Mat), ("dres", Mat),
+                ("dgamma", C.c_void_p * HN_MAX_SEG), ("dbeta", C.c_void_p * HN_MAX_SEG)]
+
+
+class ActBwdDesc(C.Structure):
+    _fields_ = [("dy", Mat), ("ref", Mat), ("dz", Mat), ("act", C.c_int32), ("n_scaled", C.c_int32),
+                ("scaled", Mat * 3), ("w", C.c_void_p)]
+
+
+class WsumDesc(C.Structure):
+    _fields_ = [("n_in", C.c_int32), ("in_", Mat * 3), ("w", C.c_void_p), ("s", Mat), ("a", Mat)]
+
+
+class ResampleDesc(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("x", View), ("y", View), ("dy", View), ("dx", View)]
+
+
+class SegGatherDesc(C.Structure):
+    _fields_ = [("low", View), ("skip", View), ("out", View), ("dlow", View), ("dskip", View)]
+
+
+class HeadGradDesc(C.Structure):
+    _fields_ = [("dout", C.c_void_p), ("out", C.c_void_p), ("act", C.c_int32), ("cols_valid", C.c_int32),
+                ("stride_n", C.c_int64), ("stride_pix", C.c_int64), ("stride_c", C.c_int64), ("rows_per_img", C.c_int64),
+                ("n_groups", C.c_int32), ("group_end", C.c_int64 * HN_MAX_GROUPS), ("group_hw", C.c_int64 * HN_MAX_GROUPS),
+                ("group_out_base", C.c_int64 * HN_MAX_GROUPS), ("dz", Mat)]
+
+
+class SeFcDesc(C.Structure):
+    _fields_ = [("N", C.c_int32), ("C", C.c_int32), ("S", C.c_int32), ("mean", C.c_void_p),
+                ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+                ("h", C.c_void_p), ("gate", C.c_void_p), ("dgate", C.c_void_p), ("dmean", C.c_void_p),
+                ("dw1", C.c_void_p), ("db1", C.c_void_p), ("dw2", C.c_void_p), ("db2", C.c_void_p), ("tmp", C.c_void_p)]
+
+
+class PackEntry(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("dst_ld", C.c_int64), ("rows", C.c_int32), ("rows_pad", C.c_int32),
+                ("cols", C.c_int32), ("s_r", C.c_int64), ("s_c", C.c_int64), ("grouped", C.c_int32), ("rsv", C.c_int32)]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [("dy", View), ("src", View * HN_MAX_SRC), ("n_src", C.c_int32), ("num_taps", C.c_int32),
+                ("taps", Tap * HN_MAX_TAPS), ("tap_off", C.c_int64 * HN_MAX_TAPS), ("tap_cin", C.c_int32 * HN_MAX_TAPS),
+                ("flat", C.c_int32), ("tile_h", C.c_int32), ("tile_w", C.c_int32), ("cout", C.c_int32),
+                ("s_co", C.c_int64), ("s_ci", C.c_int64), ("grouped", C.c_int32), ("dw", C.c_void_p)]
+
+
+class AdamTensor(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_int64)]
+
+
 #: every symbol ``include/hydranet_b200.h`` declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -122,6 +189,25 @@ SYMBOLS = {
     "hn_det_decode_nms": (C.c_int, [C.POINTER(DetDesc), _P]),
     "hn_lane_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "hn_lane_decode_nms": (C.c_int, [C.POINTER(LaneDesc), _P]),
+    "hn_bn_train_fwd": (C.c_int, [C.POINTER(BnDesc), _P]),
+    "hn_bn_train_bwd": (C.c_int, [C.POINTER(BnDesc), _P]),
+    "hn_col_reduce": (C.c_int, [C.POINTER(Mat), C.POINTER(Mat), C.c_int32, C.c_int64, _P, _P, C.c_float, _P, C.c_int64, _P]),
+    "hn_act_bwd": (C.c_int, [C.POINTER(ActBwdDesc), _P]),
+    "hn_wsum_swish_fwd": (C.c_int, [C.POINTER(WsumDesc), _P]),
+    "hn_resample_fwd": (C.c_int, [C.POINTER(ResampleDesc), _P]),
+    "hn_resample_bwd": (C.c_int, [C.POINTER(ResampleDesc), _P]),
+    "hn_seggather_fwd": (C.c_int, [C.POINTER(SegGatherDesc), _P]),
+    "hn_seggather_bwd": (C.c_int, [C.POINTER(SegGatherDesc), _P]),
+    "hn_head_grad": (C.c_int, [C.POINTER(HeadGradDesc), _P]),
+    "hn_dw_wgrad": (C.c_int, [C.POINTER(View), C.POINTER(View), _P, C.c_int32, _P, C.c_int64, _P]),
+    "hn_stem_wgrad": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(View), _P, _P, C.c_int64, _P]),
+    "hn_se_fc_fwd": (C.c_int, [C.POINTER(SeFcDesc), _P]),
+    "hn_se_fc_bwd": (C.c_int, [C.POINTER(SeFcDesc), _P]),
+    "hn_se_apply": (C.c_int, [C.POINTER(Mat), _P, _P, C.c_int64, C.POINTER(Mat), _P]),
+    "hn_pack_weights": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "hn_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), _P]),
+    "hn_adam_step": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
+                               C.c_float, _P]),
     "hn_plan_create": (C.c_int, [C.POINTER(_P)]),
     "hn_plan_destroy": (C.c_int, [_P]),
     "hn_plan_add_conv": (C.c_int, [_P, C.POINTER(ConvDesc)]),

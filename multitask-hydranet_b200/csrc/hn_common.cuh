@@ -35,6 +35,17 @@ void hn_set_error(const char* fmt, ...);
 
 static inline int hn_cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// cuTensorMapEncodeTiled is a DRIVER entry point and needs a current context on the calling thread.  Threads that have
+// only ever been handed device pointers (PyTorch's autograd worker running a backward) may not have one yet: bind the
+// runtime's primary context once per thread.
+static inline void hn_ensure_context() {
+    static thread_local bool done = false;
+    if (!done) {
+        cudaFree(nullptr);
+        done = true;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // device-side PTX wrappers
 // ------------------------------------------------------------------------------------------------
@@ -241,6 +252,18 @@ __device__ __forceinline__ void hn_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) 
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void hn_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
+          "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]),
+          "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
 }

@@ -28,18 +28,6 @@ __device__ __forceinline__ long long hn_globaltimer() {
 __device__ __forceinline__ void hn_named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ void hn_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
-          "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]),
-          "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
 template <int NC>
 __device__ __forceinline__ void hn_tmem_ldN(uint32_t taddr, uint32_t (&v)[NC]) {
     if constexpr (NC == 32) hn_tmem_ld32(taddr, v);
@@ -392,7 +380,7 @@ __global__ void __launch_bounds__(kCtaThreads, kMinBlocks) hn_conv_gemm_kernel(c
                     dst[p.n_groups * BN + i] = p.group_scale ? p.group_scale[(long long)gi * p.gstride + n0 + ci] : 1.0f;
                 }
             } else {
-                for (int i = et; i < BN; i += kEpiThreads) dst[i] = p.bias ? p.bias[n0 + i] : 0.0f;
+                for (int i = et; i < BN; i += kEpiThreads) dst[i] = (p.bias && n0 + i < p.cout) ? p.bias[n0 + i] : 0.0f;  // callers may pass an unpadded [cout] vector
             }
         };
         // a single N tile: every work item has the same channels -- stage once (a global-load round trip and a barrier
@@ -579,6 +567,7 @@ static PFN_encodeTiled get_encode_fn() {
 static int encode_view_map(CUtensorMap* tm, const hn_view& v, int box_w, int box_h) {
     PFN_encodeTiled enc = get_encode_fn();
     HN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+    hn_ensure_context();
     HN_REQUIRE(v.ptr != nullptr && (reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0, "view base must be 16-byte aligned");
     HN_REQUIRE(v.C % 8 == 0 && v.stride_x % 8 == 0 && v.stride_y % 8 == 0 && v.stride_n % 8 == 0,
                "view channels/strides must be multiples of 8 elements (16 bytes): C=%d sx=%lld sy=%lld sn=%lld", v.C,
@@ -601,6 +590,7 @@ static int encode_view_map(CUtensorMap* tm, const hn_view& v, int box_w, int box
 static int encode_weight_map(CUtensorMap* tm, const void* w, int rows, int kcols, int bn) {
     PFN_encodeTiled enc = get_encode_fn();
     HN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+    hn_ensure_context();
     HN_REQUIRE(w != nullptr && (reinterpret_cast<uintptr_t>(w) & 15) == 0, "weights must be 16-byte aligned");
     cuuint64_t dims[2] = {(cuuint64_t)kcols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)kcols * 2};

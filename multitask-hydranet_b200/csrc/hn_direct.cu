@@ -3,49 +3,6 @@
 // (16-byte) vectors so every global access is a coalesced 128-bit transaction.
 #include "hn_ops.h"
 
-// device-side view with 32-bit element strides: every offset inside one activation tensor fits an int (checked in
-// check_view), and 64-bit address arithmetic would otherwise dominate the instruction count of these kernels
-struct View {
-    const bf16* ptr;
-    int N, H, W, C;
-    int sn, sy, sx;
-};
-static inline View to_view(const hn_view& v) {
-    View r;
-    r.ptr = reinterpret_cast<const bf16*>(v.ptr);
-    r.N = v.N; r.H = v.H; r.W = v.W; r.C = v.C;
-    r.sn = (int)v.stride_n; r.sy = (int)v.stride_y; r.sx = (int)v.stride_x;
-    return r;
-}
-static int check_view(const hn_view& v, const char* what) {
-    HN_REQUIRE(v.ptr != nullptr, "%s: null view", what);
-    {
-        long long span = (long long)(v.N > 0 ? v.N - 1 : 0) * v.stride_n + (long long)(v.H > 0 ? v.H - 1 : 0) * v.stride_y +
-                         (long long)(v.W > 0 ? v.W - 1 : 0) * v.stride_x + v.C;
-        HN_REQUIRE(span < 0x7fffffffLL && v.stride_n >= 0 && v.stride_y >= 0 && v.stride_x >= 0,
-                   "%s: view spans more than 2^31 elements", what);
-    }
-    HN_REQUIRE((reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0 && v.C % 8 == 0 && v.stride_x % 8 == 0 && v.stride_y % 8 == 0 &&
-                   v.stride_n % 8 == 0,
-               "%s: view must be 16-byte aligned with C and strides in multiples of 8 (C=%d)", what, v.C);
-    return HN_OK;
-}
-
-__device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
-    uint4 u = *reinterpret_cast<const uint4*>(p);
-    float2 a = hn_unpack_bf16x2(u.x), b = hn_unpack_bf16x2(u.y), c = hn_unpack_bf16x2(u.z), d = hn_unpack_bf16x2(u.w);
-    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
-}
-__device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
-    uint4 u;
-    u.x = hn_pack_bf16x2(f[0], f[1]); u.y = hn_pack_bf16x2(f[2], f[3]);
-    u.z = hn_pack_bf16x2(f[4], f[5]); u.w = hn_pack_bf16x2(f[6], f[7]);
-    *reinterpret_cast<uint4*>(p) = u;
-}
-__device__ __forceinline__ const bf16* vptr(const View& v, int n, int y, int x, int c) {
-    return v.ptr + (n * v.sn + y * v.sy + x * v.sx + c);
-}
-
 // ------------------------------------------------------------------------------------------------
 // stem: 3x3 s2 p1, 3 -> 32, fp32 NCHW -> bf16 NHWC, BN folded, ReLU
 // ------------------------------------------------------------------------------------------------
@@ -54,7 +11,7 @@ __device__ __forceinline__ const bf16* vptr(const View& v, int n, int y, int x, 
 // The accumulation order per output (ci, ky, kx) is the same as a one-pixel loop.
 __global__ void __launch_bounds__(128) hn_stem_kernel(const float* __restrict__ x, int N, int H, int W,
                                                       const float* __restrict__ w, const float* __restrict__ b,
-                                                      View out) {
+                                                      View out, int no_relu) {
     hn_pdl_launch_dependents();
     hn_pdl_wait();
     __shared__ float sw[27 * 32];
@@ -113,7 +70,7 @@ __global__ void __launch_bounds__(128) hn_stem_kernel(const float* __restrict__ 
         for (int c8 = 0; c8 < 4; ++c8) {
             float f[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaxf(acc[px][c8 * 8 + j], 0.0f);
+            for (int j = 0; j < 8; ++j) f[j] = no_relu ? acc[px][c8 * 8 + j] : fmaxf(acc[px][c8 * 8 + j], 0.0f);
             store8(o + c8 * 8, f);
         }
     }
@@ -128,7 +85,7 @@ extern "C" int hn_stem_fwd(const hn_stem_desc* d, void* stream) {
     long long total = (long long)d->N * d->out.H * ((d->out.W + 1) / 2);  // two output pixels per thread
     HN_REQUIRE(total < 0x7fffffffLL, "stem: too many output pixels for one launch");
     HN_CHECK_CUDA(hn_launch(hn_stem_kernel, dim3(hn_cdiv(total, 128)), dim3(128), (size_t)(0), reinterpret_cast<cudaStream_t>(stream), d->x, d->N, d->H, d->W, d->w,
-                                                                                          d->b, to_view(d->out)));
+                                                                                          d->b, to_view(d->out), (int)d->no_relu));
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }

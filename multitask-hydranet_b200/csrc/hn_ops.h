@@ -48,6 +48,52 @@ struct ConvLaunch {
     int per_sm;  // CTAs of this launch that fit on one SM (1 or 2)
 };
 
+#ifdef __CUDACC__
+// device-side view with 32-bit element strides: every offset inside one activation tensor fits an int (checked in
+// check_view), and 64-bit address arithmetic would otherwise dominate the instruction count of these kernels
+struct View {
+    const bf16* ptr;
+    int N, H, W, C;
+    int sn, sy, sx;
+};
+static inline View to_view(const hn_view& v) {
+    View r;
+    r.ptr = reinterpret_cast<const bf16*>(v.ptr);
+    r.N = v.N; r.H = v.H; r.W = v.W; r.C = v.C;
+    r.sn = (int)v.stride_n; r.sy = (int)v.stride_y; r.sx = (int)v.stride_x;
+    return r;
+}
+static inline int check_view(const hn_view& v, const char* what) {
+    HN_REQUIRE(v.ptr != nullptr, "%s: null view", what);
+    {
+        long long span = (long long)(v.N > 0 ? v.N - 1 : 0) * v.stride_n + (long long)(v.H > 0 ? v.H - 1 : 0) * v.stride_y +
+                         (long long)(v.W > 0 ? v.W - 1 : 0) * v.stride_x + v.C;
+        HN_REQUIRE(span < 0x7fffffffLL && v.stride_n >= 0 && v.stride_y >= 0 && v.stride_x >= 0,
+                   "%s: view spans more than 2^31 elements", what);
+    }
+    HN_REQUIRE((reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0 && v.C % 8 == 0 && v.stride_x % 8 == 0 && v.stride_y % 8 == 0 &&
+                   v.stride_n % 8 == 0,
+               "%s: view must be 16-byte aligned with C and strides in multiples of 8 (C=%d)", what, v.C);
+    return HN_OK;
+}
+
+__device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    float2 a = hn_unpack_bf16x2(u.x), b = hn_unpack_bf16x2(u.y), c = hn_unpack_bf16x2(u.z), d = hn_unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
+    uint4 u;
+    u.x = hn_pack_bf16x2(f[0], f[1]); u.y = hn_pack_bf16x2(f[2], f[3]);
+    u.z = hn_pack_bf16x2(f[4], f[5]); u.w = hn_pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ const bf16* vptr(const View& v, int n, int y, int x, int c) {
+    return v.ptr + (n * v.sn + y * v.sy + x * v.sx + c);
+}
+
+#endif  // __CUDACC__
+
 int hn_conv_prepare(const hn_conv_desc* d, ConvLaunch* L);
 int hn_conv_launch(const ConvLaunch* L, cudaStream_t stream);
 int hn_det_num_launches(const hn_det_desc* d);

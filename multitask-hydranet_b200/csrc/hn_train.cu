@@ -1,0 +1,1252 @@
+// HBM-bound operators of the training step (reference: the autograd graph behind
+// model/train.py:248-264): train-mode BatchNorm forward / backward, activation derivatives, the BiFPN fusion sum,
+// re-sampling adjoints, the segmentation decoder's pad / up-sample / concat assembly and its adjoint, head-gradient
+// layout conversion, depthwise and stem weight gradients, squeeze-excite FC layers, weight packing and Adam.
+// Activations / activation gradients are bf16 (NHWC views or [pixels][channels] row matrices); every thread owns
+// 8-channel (16-byte) vectors; all reductions are deterministic (two-level: per-chunk partials summed in chunk order).
+#include "hn_ops.h"
+
+// ------------------------------------------------------------------------------------------------
+// row-matrix helpers
+// ------------------------------------------------------------------------------------------------
+struct Mat {
+    bf16* ptr;
+    long long rows, ld;
+    int cols;
+};
+static inline Mat to_mat(const hn_mat& m) {
+    Mat r;
+    r.ptr = reinterpret_cast<bf16*>(m.ptr);
+    r.rows = m.rows;
+    r.ld = m.ld;
+    r.cols = m.cols;
+    return r;
+}
+static inline int check_mat(const hn_mat& m, const char* what) {
+    HN_REQUIRE(m.ptr != nullptr && m.rows >= 0 && m.cols > 0, "%s: null / empty matrix", what);
+    HN_REQUIRE((reinterpret_cast<uintptr_t>(m.ptr) & 15) == 0 && m.cols % 8 == 0 && m.ld % 8 == 0 && m.ld >= m.cols,
+               "%s: matrix must be 16-byte aligned with cols / ld multiples of 8 (cols=%d ld=%lld)", what, m.cols, (long long)m.ld);
+    HN_REQUIRE(m.cols <= 2048, "%s: at most 2048 columns (got %d)", what, m.cols);
+    return HN_OK;
+}
+static inline bool same_shape(const hn_mat& a, const hn_mat& b) { return a.rows == b.rows && a.cols == b.cols; }
+
+__device__ __forceinline__ float hn_sigmoid_acc(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// derivative of the activation; `ref` = output for ReLU / ELU / sigmoid, pre-activation for swish
+__device__ __forceinline__ float act_grad(float ref, int act) {
+    switch (act) {
+        case HN_ACT_RELU: return ref > 0.0f ? 1.0f : 0.0f;
+        case HN_ACT_ELU: return ref > 0.0f ? 1.0f : ref + 1.0f;
+        case HN_ACT_SIGMOID: return ref * (1.0f - ref);
+        case HN_ACT_SWISH: {
+            const float s = hn_sigmoid_acc(ref);
+            return s * (1.0f + ref * (1.0f - s));
+        }
+        default: return 1.0f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// two-level column reduction framework
+// ------------------------------------------------------------------------------------------------
+// Rows are cut into chunks that never straddle a segment; stage 1 (one CTA per chunk) writes per-chunk sums
+// partial[chunk][k][C] (k = 0,1), stage 2 adds a segment's chunks in order.
+struct RedGeom {
+    long long rows;
+    int C, CV;
+    int rows_per_chunk, n_chunks, n_seg;
+    // table mode (n_seg <= HN_MAX_SEG): explicit segment ends; uniform mode: segments of `uniform` rows each
+    long long uniform;
+    int chunks_per_seg;  // uniform mode
+    long long seg_end[HN_MAX_SEG];
+    int chunk_start[HN_MAX_SEG + 1];
+};
+
+__device__ __forceinline__ void red_locate(const RedGeom& g, int chunk, int& seg, long long& r0, long long& r1) {
+    if (g.uniform > 0) {
+        seg = chunk / g.chunks_per_seg;
+        const long long b = (long long)seg * g.uniform;
+        r0 = b + (long long)(chunk - seg * g.chunks_per_seg) * g.rows_per_chunk;
+        r1 = min(r0 + g.rows_per_chunk, b + g.uniform);
+    } else {
+        seg = 0;
+        while (seg < g.n_seg - 1 && chunk >= g.chunk_start[seg + 1]) ++seg;
+        const long long b = seg > 0 ? g.seg_end[seg - 1] : 0;
+        r0 = b + (long long)(chunk - g.chunk_start[seg]) * g.rows_per_chunk;
+        r1 = min(r0 + g.rows_per_chunk, g.seg_end[seg]);
+    }
+}
+__device__ __forceinline__ int seg_of_row(const RedGeom& g, long long row) {
+    if (g.uniform > 0) return (int)(row / g.uniform);
+    int s = 0;
+    while (s < g.n_seg - 1 && row >= g.seg_end[s]) ++s;
+    return s;
+}
+
+static int make_geom(RedGeom* g, long long rows, int C, int n_seg, const int64_t* seg_end, long long uniform, int target_chunks) {
+    memset(g, 0, sizeof(*g));
+    g->rows = rows;
+    g->C = C;
+    g->CV = C / 8;
+    long long rpc = (rows + target_chunks - 1) / target_chunks;
+    if (rpc < 32) rpc = 32;
+    g->rows_per_chunk = (int)rpc;
+    if (uniform > 0) {
+        HN_REQUIRE(rows % uniform == 0, "col reduce: rows %lld not a multiple of the segment size %lld", rows, uniform);
+        g->uniform = uniform;
+        g->n_seg = (int)(rows / uniform);
+        // keep at least ~target_chunks chunks in total, at least one per segment
+        long long per = (target_chunks + g->n_seg - 1) / g->n_seg;
+        rpc = (uniform + per - 1) / per;
+        if (rpc < 32) rpc = 32;
+        g->rows_per_chunk = (int)rpc;
+        g->chunks_per_seg = (int)((uniform + rpc - 1) / rpc);
+        g->n_chunks = g->chunks_per_seg * g->n_seg;
+    } else {
+        HN_REQUIRE(n_seg >= 1 && n_seg <= HN_MAX_SEG, "n_seg=%d out of range", n_seg);
+        g->n_seg = n_seg;
+        long long prev = 0;
+        int c = 0;
+        for (int s = 0; s < n_seg; ++s) {
+            const long long e = n_seg == 1 && !seg_end ? rows : seg_end[s];
+            HN_REQUIRE(e > prev && e <= rows, "segment %d end %lld out of order (rows %lld)", s, e, rows);
+            g->seg_end[s] = e;
+            g->chunk_start[s] = c;
+            c += (int)((e - prev + rpc - 1) / rpc);
+            prev = e;
+        }
+        HN_REQUIRE(prev == rows, "segments cover %lld of %lld rows", prev, rows);
+        g->chunk_start[n_seg] = c;
+        g->n_chunks = c;
+    }
+    return HN_OK;
+}
+static inline size_t partial_bytes(const RedGeom& g) { return (size_t)g.n_chunks * 2 * g.C * sizeof(float); }
+
+template <class F>
+__global__ void __launch_bounds__(256) hn_red1_kernel(const RedGeom g, const F f, float* __restrict__ partial) {
+    __shared__ float sm[256 * 16];
+    const int CV = g.CV;
+    const int rpi = 256 / CV;  // rows in flight per iteration (CV <= 256)
+    const int cv = threadIdx.x % CV, rl = threadIdx.x / CV;
+    const bool active = rl < rpi;
+    int seg;
+    long long r0, r1;
+    red_locate(g, blockIdx.x, seg, r0, r1);
+    float a0[8], a1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.0f;
+    if (active)
+        for (long long r = r0 + rl; r < r1; r += rpi) f(seg, r, cv, a0, a1);
+    float* mine = sm + (size_t)threadIdx.x * 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { mine[j] = a0[j]; mine[8 + j] = a1[j]; }
+    __syncthreads();
+    if (rl == 0) {
+        for (int q = 1; q < rpi; ++q) {
+            const float* o = sm + (size_t)(q * CV + cv) * 16;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a0[j] += o[j]; a1[j] += o[8 + j]; }
+        }
+        float* p0 = partial + ((size_t)blockIdx.x * 2) * g.C + cv * 8;
+        float* p1 = p0 + g.C;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { p0[j] = a0[j]; p1[j] = a1[j]; }
+    }
+}
+
+__device__ __forceinline__ void red_sum_chunks(const RedGeom& g, const float* partial, int seg, int c, double& s0, double& s1) {
+    int cb, ce;
+    if (g.uniform > 0) { cb = seg * g.chunks_per_seg; ce = cb + g.chunks_per_seg; }
+    else { cb = g.chunk_start[seg]; ce = g.chunk_start[seg + 1]; }
+    s0 = s1 = 0.0;
+    for (int k = cb; k < ce; ++k) {
+        s0 += (double)partial[((size_t)k * 2) * g.C + c];
+        s1 += (double)partial[((size_t)k * 2 + 1) * g.C + c];
+    }
+}
+__device__ __forceinline__ long long seg_rows(const RedGeom& g, int seg) {
+    if (g.uniform > 0) return g.uniform;
+    return g.seg_end[seg] - (seg > 0 ? g.seg_end[seg - 1] : 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm (training)
+// ------------------------------------------------------------------------------------------------
+struct BnPtrs {
+    const float* gamma[HN_MAX_SEG];
+    const float* beta[HN_MAX_SEG];
+    float* rmean[HN_MAX_SEG];
+    float* rvar[HN_MAX_SEG];
+    float* dgamma[HN_MAX_SEG];
+    float* dbeta[HN_MAX_SEG];
+};
+
+struct StatsF {
+    Mat z;
+    __device__ __forceinline__ void operator()(int, long long r, int cv, float (&a0)[8], float (&a1)[8]) const {
+        float v[8];
+        load8(z.ptr + r * z.ld + cv * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a0[j] += v[j]; a1[j] = fmaf(v[j], v[j], a1[j]); }
+    }
+};
+
+// stats layout: [seg][4][C] = mean, invstd, scale (gamma * invstd), shift (beta - mean * scale)
+__global__ void hn_bn_finalize_kernel(const RedGeom g, const float* __restrict__ partial, BnPtrs bp, float eps, float momentum,
+                                      float* __restrict__ stats) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n_seg * g.C) return;
+    const int seg = i / g.C, c = i - seg * g.C;
+    double s0, s1;
+    red_sum_chunks(g, partial, seg, c, s0, s1);
+    const double n = (double)seg_rows(g, seg);
+    const double mean = s0 / n;
+    double var = s1 / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float ga = bp.gamma[seg] ? bp.gamma[seg][c] : 1.0f, be = bp.beta[seg] ? bp.beta[seg][c] : 0.0f;
+    float* st = stats + (size_t)seg * 4 * g.C;
+    st[c] = (float)mean;
+    st[g.C + c] = invstd;
+    st[2 * g.C + c] = ga * invstd;
+    st[3 * g.C + c] = be - (float)mean * ga * invstd;
+    if (bp.rmean[seg]) {
+        const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+        bp.rmean[seg][c] = (1.0f - momentum) * bp.rmean[seg][c] + momentum * (float)mean;
+        bp.rvar[seg][c] = (1.0f - momentum) * bp.rvar[seg][c] + momentum * (float)unbiased;
+    }
+}
+
+__global__ void __launch_bounds__(256) hn_bn_apply_kernel(const RedGeom g, Mat z, const float* __restrict__ stats, int act, Mat res, Mat y) {
+    const long long total = g.rows * g.CV;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / g.CV;
+        const int cv = (int)(i - r * g.CV);
+        const int seg = seg_of_row(g, r);
+        const float* sc = stats + ((size_t)seg * 4 + 2) * g.C + cv * 8;
+        const float* sh = sc + g.C;
+        float v[8];
+        load8(z.ptr + r * z.ld + cv * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+        if (res.ptr) {
+            float q[8];
+            load8(res.ptr + r * res.ld + cv * 8, q);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += q[j];
+        }
+        if (act == HN_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+        } else if (act == HN_ACT_SWISH) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = v[j] * hn_sigmoid_acc(v[j]);
+        }
+        store8(y.ptr + r * y.ld + cv * 8, v);
+    }
+}
+
+static int fill_bn_ptrs(const hn_bn_desc* d, BnPtrs* bp) {
+    for (int s = 0; s < HN_MAX_SEG; ++s) {
+        const bool on = s < d->n_seg;
+        bp->gamma[s] = on ? d->gamma[s] : nullptr;
+        bp->beta[s] = on ? d->beta[s] : nullptr;
+        bp->rmean[s] = on ? d->running_mean[s] : nullptr;
+        bp->rvar[s] = on ? d->running_var[s] : nullptr;
+        bp->dgamma[s] = on ? d->dgamma[s] : nullptr;
+        bp->dbeta[s] = on ? d->dbeta[s] : nullptr;
+        if (on) HN_REQUIRE((bp->rmean[s] == nullptr) == (bp->rvar[s] == nullptr), "bn: running_mean / running_var must come together");
+    }
+    return HN_OK;
+}
+static inline int ew_grid(long long total_vec) {
+    long long b = (total_vec + 255) / 256;
+    long long cap = 148LL * 16;
+    return (int)(b < 1 ? 1 : (b < cap ? b : cap));
+}
+static constexpr int kTargetChunks = 592;  // 148 SMs x 4
+
+extern "C" int hn_bn_train_fwd(const hn_bn_desc* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    HN_REQUIRE(d != nullptr && d->stats != nullptr && d->scratch != nullptr, "bn fwd: null pointer");
+    if (int rc = check_mat(d->z, "bn.z")) return rc;
+    if (int rc = check_mat(d->y, "bn.y")) return rc;
+    HN_REQUIRE(same_shape(d->z, d->y), "bn: z / y shape mismatch");
+    if (d->res.ptr) {
+        if (int rc = check_mat(d->res, "bn.res")) return rc;
+        HN_REQUIRE(same_shape(d->z, d->res), "bn: residual shape mismatch");
+    }
+    HN_REQUIRE(d->act == HN_ACT_NONE || d->act == HN_ACT_RELU || d->act == HN_ACT_SWISH, "bn: unsupported activation %d", d->act);
+    if (d->z.rows == 0) return HN_OK;
+    RedGeom g;
+    if (int rc = make_geom(&g, d->z.rows, d->z.cols, d->n_seg, d->seg_end, 0, kTargetChunks)) return rc;
+    HN_REQUIRE((int64_t)partial_bytes(g) <= d->scratch_bytes, "bn: scratch too small (%zu > %lld)", partial_bytes(g), (long long)d->scratch_bytes);
+    BnPtrs bp;
+    if (int rc = fill_bn_ptrs(d, &bp)) return rc;
+    StatsF f{to_mat(d->z)};
+    hn_red1_kernel<StatsF><<<g.n_chunks, 256, 0, stream>>>(g, f, d->scratch);
+    HN_CHECK_CUDA(cudaGetLastError());
+    hn_bn_finalize_kernel<<<hn_cdiv((long)g.n_seg * g.C, 128), 128, 0, stream>>>(g, d->scratch, bp, d->eps, d->momentum, d->stats);
+    HN_CHECK_CUDA(cudaGetLastError());
+    Mat res{nullptr, 0, 0, 0};
+    if (d->res.ptr) res = to_mat(d->res);
+    hn_bn_apply_kernel<<<ew_grid(g.rows * g.CV), 256, 0, stream>>>(g, to_mat(d->z), d->stats, d->act, res, to_mat(d->y));
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+// backward stage 1: dz_act = dy * act'(.), sums of dz_act and dz_act * xhat
+struct BnBwdF {
+    Mat dy, z, y;
+    const float* stats;
+    int C, act;
+    __device__ __forceinline__ void dz_act(int seg, long long r, int cv, float (&dzv)[8], float (&xh)[8]) const {
+        const float* st = stats + (size_t)seg * 4 * C + cv * 8;
+        float g[8], zz[8];
+        load8(dy.ptr + r * dy.ld + cv * 8, g);
+        load8(z.ptr + r * z.ld + cv * 8, zz);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xh[j] = (zz[j] - st[j]) * st[C + j];
+        if (act == HN_ACT_RELU) {
+            float o[8];
+            load8(y.ptr + r * y.ld + cv * 8, o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dzv[j] = o[j] > 0.0f ? g[j] : 0.0f;
+        } else if (act == HN_ACT_SWISH) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dzv[j] = g[j] * act_grad(fmaf(zz[j], st[2 * C + j], st[3 * C + j]), HN_ACT_SWISH);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dzv[j] = g[j];
+        }
+    }
+    __device__ __forceinline__ void operator()(int seg, long long r, int cv, float (&a0)[8], float (&a1)[8]) const {
+        float dzv[8], xh[8];
+        dz_act(seg, r, cv, dzv, xh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a0[j] += dzv[j]; a1[j] = fmaf(dzv[j], xh[j], a1[j]); }
+    }
+};
+
+// sums[seg][2][C] = (mean of dz_act, mean of dz_act * xhat); parameter gradients written
+__global__ void hn_bn_bwd_finalize_kernel(const RedGeom g, const float* __restrict__ partial, BnPtrs bp, float* __restrict__ sums) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n_seg * g.C) return;
+    const int seg = i / g.C, c = i - seg * g.C;
+    double s0, s1;
+    red_sum_chunks(g, partial, seg, c, s0, s1);
+    const double n = (double)seg_rows(g, seg);
+    if (bp.dbeta[seg]) bp.dbeta[seg][c] = (float)s0;
+    if (bp.dgamma[seg]) bp.dgamma[seg][c] = (float)s1;
+    sums[((size_t)seg * 2) * g.C + c] = (float)(s0 / n);
+    sums[((size_t)seg * 2 + 1) * g.C + c] = (float)(s1 / n);
+}
+
+__global__ void __launch_bounds__(256) hn_bn_bwd_apply_kernel(const RedGeom g, const BnBwdF f, const float* __restrict__ sums, Mat dz, Mat dres) {
+    const long long total = g.rows * g.CV;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / g.CV;
+        const int cv = (int)(i - r * g.CV);
+        const int seg = seg_of_row(g, r);
+        float dzv[8], xh[8];
+        f.dz_act(seg, r, cv, dzv, xh);
+        if (dres.ptr) store8(dres.ptr + r * dres.ld + cv * 8, dzv);
+        const float* sc = f.stats + ((size_t)seg * 4 + 2) * g.C + cv * 8;  // gamma * invstd
+        const float* m0 = sums + ((size_t)seg * 2) * g.C + cv * 8;
+        const float* m1 = m0 + g.C;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = sc[j] * (dzv[j] - m0[j] - xh[j] * m1[j]);
+        store8(dz.ptr + r * dz.ld + cv * 8, o);
+    }
+}
+
+extern "C" int hn_bn_train_bwd(const hn_bn_desc* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    HN_REQUIRE(d != nullptr && d->stats != nullptr && d->scratch != nullptr, "bn bwd: null pointer");
+    if (int rc = check_mat(d->z, "bn.z")) return rc;
+    if (int rc = check_mat(d->dy, "bn.dy")) return rc;
+    if (int rc = check_mat(d->dz, "bn.dz")) return rc;
+    HN_REQUIRE(same_shape(d->z, d->dy) && same_shape(d->z, d->dz), "bn bwd: shape mismatch");
+    if (d->act == HN_ACT_RELU) {
+        if (int rc = check_mat(d->y, "bn.y")) return rc;
+        HN_REQUIRE(same_shape(d->z, d->y), "bn bwd: y shape mismatch");
+    }
+    if (d->dres.ptr) {
+        if (int rc = check_mat(d->dres, "bn.dres")) return rc;
+        HN_REQUIRE(same_shape(d->z, d->dres), "bn bwd: dres shape mismatch");
+    }
+    if (d->z.rows == 0) return HN_OK;
+    RedGeom g;
+    if (int rc = make_geom(&g, d->z.rows, d->z.cols, d->n_seg, d->seg_end, 0, kTargetChunks)) return rc;
+    const size_t need = partial_bytes(g) + (size_t)g.n_seg * 2 * g.C * sizeof(float);
+    HN_REQUIRE((int64_t)need <= d->scratch_bytes, "bn bwd: scratch too small (%zu > %lld)", need, (long long)d->scratch_bytes);
+    BnPtrs bp;
+    if (int rc = fill_bn_ptrs(d, &bp)) return rc;
+    Mat ym{nullptr, 0, 0, 0};
+    if (d->act == HN_ACT_RELU) ym = to_mat(d->y);
+    BnBwdF f{to_mat(d->dy), to_mat(d->z), ym, d->stats, g.C, d->act};
+    float* sums = d->scratch + (size_t)g.n_chunks * 2 * g.C;
+    hn_red1_kernel<BnBwdF><<<g.n_chunks, 256, 0, stream>>>(g, f, d->scratch);
+    HN_CHECK_CUDA(cudaGetLastError());
+    hn_bn_bwd_finalize_kernel<<<hn_cdiv((long)g.n_seg * g.C, 128), 128, 0, stream>>>(g, d->scratch, bp, sums);
+    HN_CHECK_CUDA(cudaGetLastError());
+    Mat dres{nullptr, 0, 0, 0};
+    if (d->dres.ptr) dres = to_mat(d->dres);
+    hn_bn_bwd_apply_kernel<<<ew_grid(g.rows * g.CV), 256, 0, stream>>>(g, f, sums, to_mat(d->dz), dres);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic column reductions
+// ------------------------------------------------------------------------------------------------
+struct SumF {
+    Mat a;
+    __device__ __forceinline__ void operator()(int, long long r, int cv, float (&a0)[8], float (&a1)[8]) const {
+        float v[8];
+        load8(a.ptr + r * a.ld + cv * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a0[j] += v[j]; a1[j] = fmaf(v[j], v[j], a1[j]); }
+    }
+};
+struct DotF {
+    Mat a, b;
+    __device__ __forceinline__ void operator()(int, long long r, int cv, float (&a0)[8], float (&)[8]) const {
+        float v[8], w[8];
+        load8(a.ptr + r * a.ld + cv * 8, v);
+        load8(b.ptr + r * b.ld + cv * 8, w);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a0[j] = fmaf(v[j], w[j], a0[j]);
+    }
+};
+__global__ void hn_red2_kernel(const RedGeom g, const float* __restrict__ partial, float scale, float* __restrict__ out0, float* __restrict__ out1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n_seg * g.C) return;
+    const int seg = i / g.C, c = i - seg * g.C;
+    double s0, s1;
+    red_sum_chunks(g, partial, seg, c, s0, s1);
+    out0[i] = (float)(s0 * (double)scale);
+    if (out1) out1[i] = (float)(s1 * (double)scale);
+}
+
+extern "C" int hn_col_reduce(const hn_mat* a, const hn_mat* b, int32_t mode, int64_t rows_per_seg, float* out0, float* out1, float scale,
+                             float* scratch, int64_t scratch_bytes, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    HN_REQUIRE(a != nullptr && out0 != nullptr && scratch != nullptr, "col reduce: null pointer");
+    if (int rc = check_mat(*a, "reduce.a")) return rc;
+    HN_REQUIRE(a->rows > 0, "col reduce: empty matrix");
+    RedGeom g;
+    if (int rc = make_geom(&g, a->rows, a->cols, 1, nullptr, rows_per_seg > 0 ? rows_per_seg : a->rows, kTargetChunks)) return rc;
+    HN_REQUIRE((int64_t)partial_bytes(g) <= scratch_bytes, "col reduce: scratch too small (%zu > %lld)", partial_bytes(g), (long long)scratch_bytes);
+    if (mode == 0) {
+        SumF f{to_mat(*a)};
+        hn_red1_kernel<SumF><<<g.n_chunks, 256, 0, stream>>>(g, f, scratch);
+    } else if (mode == 1) {
+        HN_REQUIRE(b != nullptr, "col reduce: dot needs b");
+        if (int rc = check_mat(*b, "reduce.b")) return rc;
+        HN_REQUIRE(same_shape(*a, *b), "col reduce: a / b shape mismatch");
+        DotF f{to_mat(*a), to_mat(*b)};
+        hn_red1_kernel<DotF><<<g.n_chunks, 256, 0, stream>>>(g, f, scratch);
+        out1 = nullptr;
+    } else {
+        HN_REQUIRE(false, "col reduce: unknown mode %d", mode);
+    }
+    HN_CHECK_CUDA(cudaGetLastError());
+    hn_red2_kernel<<<hn_cdiv((long)g.n_seg * g.C, 128), 128, 0, stream>>>(g, scratch, scale, out0, out1);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// element-wise: activation backward (+ scaled copies), fusion sum + swish, squeeze-excite apply
+// ------------------------------------------------------------------------------------------------
+struct ActBwdParams {
+    Mat dy, ref, dz;
+    int act, n_scaled;
+    Mat scaled[3];
+    const float* w;
+};
+__global__ void __launch_bounds__(256) hn_act_bwd_kernel(const ActBwdParams p) {
+    const int CV = p.dy.cols / 8;
+    const long long total = p.dy.rows * CV;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / CV;
+        const int c = (int)(i - r * CV) * 8;
+        float g[8];
+        load8(p.dy.ptr + r * p.dy.ld + c, g);
+        if (p.act != HN_ACT_NONE) {
+            float q[8];
+            load8(p.ref.ptr + r * p.ref.ld + c, q);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] *= act_grad(q[j], p.act);
+        }
+        if (p.dz.ptr) store8(p.dz.ptr + r * p.dz.ld + c, g);
+        for (int k = 0; k < p.n_scaled; ++k) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = g[j] * p.w[k];
+            store8(p.scaled[k].ptr + r * p.scaled[k].ld + c, o);
+        }
+    }
+}
+extern "C" int hn_act_bwd(const hn_actbwd_desc* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    HN_REQUIRE(d != nullptr, "act bwd: null desc");
+    if (int rc = check_mat(d->dy, "actbwd.dy")) return rc;
+    ActBwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.dy = to_mat(d->dy);
+    p.act = d->act;
+    if (d->act != HN_ACT_NONE) {
+        if (int rc = check_mat(d->ref, "actbwd.ref")) return rc;
+        HN_REQUIRE(same_shape(d->dy, d->ref), "act bwd: ref shape mismatch");
+        p.ref = to_mat(d->ref);
+    }
+    if (d->dz.ptr) {
+        if (int rc = check_mat(d->dz, "actbwd.dz")) return rc;
+        HN_REQUIRE(same_shape(d->dy, d->dz), "act bwd: dz shape mismatch");
+        p.dz = to_mat(d->dz);
+    }
+    HN_REQUIRE(d->n_scaled >= 0 && d->n_scaled <= 3, "act bwd: n_scaled=%d", d->n_scaled);
+    p.n_scaled = d->n_scaled;
+    for (int k = 0; k < d->n_scaled; ++k) {
+        if (int rc = check_mat(d->scaled[k], "actbwd.scaled")) return rc;
+        HN_REQUIRE(same_shape(d->dy, d->scaled[k]), "act bwd: scaled output shape mismatch");
+        p.scaled[k] = to_mat(d->scaled[k]);
+    }
+    HN_REQUIRE(d->n_scaled == 0 || d->w != nullptr, "act bwd: scaled outputs need the weight vector");
+    p.w = d->w;
+    if (d->dy.rows == 0) return HN_OK;
+    hn_act_bwd_kernel<<<ew_grid(p.dy.rows * (p.dy.cols / 8)), 256, 0, stream>>>(p);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+struct WsumParams {
+    int n_in;
+    Mat in[3];
+    const float* w;
+    Mat s, a;
+};
+__global__ void __launch_bounds__(256) hn_wsum_kernel(const WsumParams p) {
+    const int CV = p.s.cols / 8;
+    const long long total = p.s.rows * CV;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / CV;
+        const int c = (int)(i - r * CV) * 8;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+        for (int k = 0; k < p.n_in; ++k) {
+            float v[8];
+            load8(p.in[k].ptr + r * p.in[k].ld + c, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(p.w[k], v[j], acc[j]);
+        }
+        store8(p.s.ptr + r * p.s.ld + c, acc);
+        // the swish reads the ROUNDED sum: the backward differentiates exactly what was stored
+        float sr[8];
+        load8(p.s.ptr + r * p.s.ld + c, sr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sr[j] = sr[j] * hn_sigmoid_acc(sr[j]);
+        store8(p.a.ptr + r * p.a.ld + c, sr);
+    }
+}
+extern "C" int hn_wsum_swish_fwd(const hn_wsum_desc* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    HN_REQUIRE(d != nullptr && d->n_in >= 1 && d->n_in <= 3, "wsum: bad desc");
+    if (int rc = check_mat(d->s, "wsum.s")) return rc;
+    if (int rc = check_mat(d->a, "wsum.a")) return rc;
+    HN_REQUIRE(same_shape(d->s, d->a), "wsum: s / a shape mismatch");
+    WsumParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_in = d->n_in;
+    for (int k = 0; k < d->n_in; ++k) {
+        if (int rc = check_mat(d->in[k], "wsum.in")) return rc;
+        HN_REQUIRE(same_shape(d->s, d->in[k]), "wsum: input %d shape mismatch", k);
+        p.in[k] = to_mat(d->in[k]);
+    }
+    HN_REQUIRE(d->w != nullptr, "wsum: null weight vector");
+    p.w = d->w;
+    p.s = to_mat(d->s);
+    p.a = to_mat(d->a);
+    if (d->s.rows == 0) return HN_OK;
+    hn_wsum_kernel<<<ew_grid(p.s.rows * (p.s.cols / 8)), 256, 0, stream>>>(p);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+__global__ void __launch_bounds__(256) hn_se_apply_kernel(Mat x, const float* __restrict__ gate, const float* __restrict__ add, long long rpi, Mat y) {
+    const int CV = x.cols / 8;
+    const long long total = x.rows * CV;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / CV;
+        const int c = (int)(i - r * CV) * 8;
+        const long long n = r / rpi;
+        float v[8];
+        load8(x.ptr + r * x.ld + c, v);
+        const float* gp = gate + n * x.cols + c;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= gp[j];
+        if (add) {
+            const float* ap = add + n * x.cols + c;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += ap[j];
+        }
+        store8(y.ptr + r * y.ld + c, v);
+    }
+}
+extern "C" int hn_se_apply(const hn_mat* x, const float* gate, const float* add, int64_t rows_per_img, const hn_mat* y, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    HN_REQUIRE(x && y && gate && rows_per_img > 0, "se apply: bad arguments");
+    if (int rc = check_mat(*x, "se.x")) return rc;
+    if (int rc = check_mat(*y, "se.y")) return rc;
+    HN_REQUIRE(same_shape(*x, *y) && x->rows % rows_per_img == 0, "se apply: shape mismatch");
+    if (x->rows == 0) return HN_OK;
+    hn_se_apply_kernel<<<ew_grid(x->rows * (x->cols / 8)), 256, 0, stream>>>(to_mat(*x), gate, add, rows_per_img, to_mat(*y));
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// re-sampling: nearest x2 up-sampling, the two 3x3 stride-2 max-pools, and their adjoints
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void decode4(unsigned idx, const View& v, int& n, int& y, int& x, int& cv) {
+    const unsigned CV = (unsigned)(v.C >> 3);
+    cv = (int)(idx % CV);
+    unsigned t = idx / CV;
+    x = (int)(t % (unsigned)v.W);
+    t /= (unsigned)v.W;
+    y = (int)(t % (unsigned)v.H);
+    n = (int)(t / (unsigned)v.H);
+}
+__global__ void hn_up2_kernel(View in, View out) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)out.N * out.H * out.W * (out.C >> 3)) return;
+    int n, y, x, cv;
+    decode4(idx, out, n, y, x, cv);
+    *reinterpret_cast<uint4*>(const_cast<bf16*>(vptr(out, n, y, x, cv * 8))) =
+        *reinterpret_cast<const uint4*>(vptr(in, n, min(y >> 1, in.H - 1), min(x >> 1, in.W - 1), cv * 8));
+}
+__global__ void hn_up2_bwd_kernel(View dy, View dx) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)dx.N * dx.H * dx.W * (dx.C >> 3)) return;
+    int n, y, x, cv;
+    decode4(idx, dx, n, y, x, cv);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+            const int Y = 2 * y + a, X = 2 * x + b;
+            if (Y >= dy.H || X >= dy.W) continue;
+            float g[8];
+            load8(vptr(dy, n, Y, X, cv * 8), g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += g[j];
+        }
+    store8(const_cast<bf16*>(vptr(dx, n, y, x, cv * 8)), acc);
+}
+// Pool backward, gather form: input pixel (Y, X) collects the gradient of every output window that contains it and whose
+// FIRST maximum in (ky, kx) scan order is (Y, X).  pad = 0: window rows 2y .. 2y+2, zeros beyond the bottom / right edge
+// take part (and swallow the gradient when they win); pad = 1: window rows 2y-1 .. 2y+1, outside = -inf.
+__global__ void hn_pool_bwd_kernel(View x, View dy, View dx, int pad) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)dx.N * dx.H * dx.W * (dx.C >> 3)) return;
+    int n, Y, X, cv;
+    decode4(idx, dx, n, Y, X, cv);
+    const int c = cv * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    // windows containing Y: 2y - pad <= Y <= 2y - pad + 2
+    const int y_lo = max(0, (Y + pad - 2 + 1) >> 1), y_hi = min(dy.H - 1, (Y + pad) >> 1);
+    const int x_lo = max(0, (X + pad - 2 + 1) >> 1), x_hi = min(dy.W - 1, (X + pad) >> 1);
+    for (int oy = y_lo; oy <= y_hi; ++oy)
+        for (int ox = x_lo; ox <= x_hi; ++ox) {
+            float best[8];
+            int arg[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = -1; }
+            const int mine = (Y - (2 * oy - pad)) * 3 + (X - (2 * ox - pad));
+            for (int ky = 0; ky < 3; ++ky)
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int iy = 2 * oy - pad + ky, ix = 2 * ox - pad + kx;
+                    float v[8];
+                    if (iy >= 0 && iy < x.H && ix >= 0 && ix < x.W) {
+                        load8(vptr(x, n, iy, ix, c), v);
+                    } else if (pad == 0) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+                    } else {
+                        continue;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (v[j] > best[j] || arg[j] < 0) { best[j] = v[j]; arg[j] = ky * 3 + kx; }
+                }
+            float g[8];
+            load8(vptr(dy, n, oy, ox, c), g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (arg[j] == mine) acc[j] += g[j];
+        }
+    store8(const_cast<bf16*>(vptr(dx, n, Y, X, c)), acc);
+}
+
+extern "C" int hn_pool_fwd(const hn_pool_desc* d, void* stream);
+extern "C" int hn_resample_fwd(const hn_resample_desc* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    HN_REQUIRE(d != nullptr, "resample: null desc");
+    if (d->mode == HN_RS_UP2) {
+        if (int rc = check_view(d->x, "up2.x")) return rc;
+        if (int rc = check_view(d->y, "up2.y")) return rc;
+        HN_REQUIRE(d->y.H == 2 * d->x.H && d->y.W == 2 * d->x.W && d->y.C == d->x.C && d->y.N == d->x.N, "up2: shape mismatch");
+        const long long total = (long long)d->y.N * d->y.H * d->y.W * (d->y.C / 8);
+        HN_REQUIRE(total < 0x7fffffffLL, "up2: too many work items");
+        if (total == 0) return HN_OK;
+        hn_up2_kernel<<<hn_cdiv(total, 256), 256, 0, stream>>>(to_view(d->x), to_view(d->y));
+        HN_CHECK_CUDA(cudaGetLastError());
+        return HN_OK;
+    }
+    hn_pool_desc pd;
+    pd.in = d->x;
+    pd.out = d->y;
+    pd.mode = d->mode == HN_RS_POOL_ZERO ? HN_POOL_ZERO_RB : HN_POOL_NEGINF;
+    return hn_pool_fwd(&pd, stream_);
+}
+extern "C" int hn_resample_bwd(const hn_resample_desc* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    HN_REQUIRE(d != nullptr, "resample bwd: null desc");
+    if (int rc = check_view(d->dy, "resample.dy")) return rc;
+    if (int rc = check_view(d->dx, "resample.dx")) return rc;
+    HN_REQUIRE(d->dy.C == d->dx.C && d->dy.N == d->dx.N, "resample bwd: channel / batch mismatch");
+    const long long total = (long long)d->dx.N * d->dx.H * d->dx.W * (d->dx.C / 8);
+    HN_REQUIRE(total < 0x7fffffffLL, "resample bwd: too many work items");
+    if (total == 0) return HN_OK;
+    if (d->mode == HN_RS_UP2) {
+        HN_REQUIRE(d->dy.H == 2 * d->dx.H && d->dy.W == 2 * d->dx.W, "up2 bwd: shape mismatch");
+        hn_up2_bwd_kernel<<<hn_cdiv(total, 256), 256, 0, stream>>>(to_view(d->dy), to_view(d->dx));
+    } else {
+        if (int rc = check_view(d->x, "pool.x")) return rc;
+        HN_REQUIRE(d->x.H == d->dx.H && d->x.W == d->dx.W && d->x.C == d->dx.C && d->x.N == d->dx.N, "pool bwd: x / dx mismatch");
+        const int pad = d->mode == HN_RS_POOL_ZERO ? 0 : 1;
+        if (pad == 0) HN_REQUIRE((d->x.H - 2) / 2 + 1 == d->dy.H && (d->x.W - 2) / 2 + 1 == d->dy.W, "pool bwd: size mismatch");
+        else HN_REQUIRE((d->x.H - 1) / 2 + 1 == d->dy.H && (d->x.W - 1) / 2 + 1 == d->dy.W, "pool bwd: size mismatch");
+        hn_pool_bwd_kernel<<<hn_cdiv(total, 256), 256, 0, stream>>>(to_view(d->x), to_view(d->dy), to_view(d->dx), pad);
+    }
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// segmentation decoder input: ReflectionPad2d(1)(cat(up2(low), skip)) and its adjoint
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect1(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+__global__ void hn_seggather_kernel(View low, View skip, View out, int Cl) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)out.N * out.H * out.W * (out.C >> 3)) return;
+    int n, Y, X, cv;
+    decode4(idx, out, n, Y, X, cv);
+    const int H = out.H - 2, W = out.W - 2;
+    const int y = reflect1(Y - 1, H), x = reflect1(X - 1, W), c = cv * 8;
+    const bf16* src = c < Cl ? vptr(low, n, y >> 1, x >> 1, c) : vptr(skip, n, y, x, c - Cl);
+    *reinterpret_cast<uint4*>(const_cast<bf16*>(vptr(out, n, Y, X, c))) = *reinterpret_cast<const uint4*>(src);
+}
+// folded gradient of interior pixel (y, x): the padded positions that mirror onto it
+__device__ __forceinline__ void seg_fold(const View& d, int n, int y, int x, int c, int H, int W, float (&acc)[8]) {
+    int ys[3], xs[3], ny = 0, nx = 0;
+    ys[ny++] = y + 1;
+    if (y == 1) ys[ny++] = 0;
+    if (y == H - 2) ys[ny++] = H + 1;
+    xs[nx++] = x + 1;
+    if (x == 1) xs[nx++] = 0;
+    if (x == W - 2) xs[nx++] = W + 1;
+    for (int a = 0; a < ny; ++a)
+        for (int b = 0; b < nx; ++b) {
+            float g[8];
+            load8(vptr(d, n, ys[a], xs[b], c), g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += g[j];
+        }
+}
+__global__ void hn_seggather_bwd_skip_kernel(View dpad, View dskip, int Cl) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)dskip.N * dskip.H * dskip.W * (dskip.C >> 3)) return;
+    int n, y, x, cv;
+    decode4(idx, dskip, n, y, x, cv);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    seg_fold(dpad, n, y, x, Cl + cv * 8, dskip.H, dskip.W, acc);
+    store8(const_cast<bf16*>(vptr(dskip, n, y, x, cv * 8)), acc);
+}
+__global__ void hn_seggather_bwd_low_kernel(View dpad, View dlow) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)dlow.N * dlow.H * dlow.W * (dlow.C >> 3)) return;
+    int n, y, x, cv;
+    decode4(idx, dlow, n, y, x, cv);
+    const int H = dpad.H - 2, W = dpad.W - 2;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) seg_fold(dpad, n, 2 * y + a, 2 * x + b, cv * 8, H, W, acc);
+    store8(const_cast<bf16*>(vptr(dlow, n, y, x, cv * 8)), acc);
+}
+static int seggather_check(const hn_seggather_desc* d, const hn_view& lo, const hn_view& sk, int* Cl) {
+    if (int rc = check_view(d->out, "seggather.out")) return rc;
+    const int H = d->out.H - 2, W = d->out.W - 2;
+    HN_REQUIRE(H >= 3 && W >= 3, "seggather: map too small for reflection padding");
+    *Cl = 0;
+    if (lo.ptr) {
+        if (int rc = check_view(lo, "seggather.low")) return rc;
+        HN_REQUIRE(lo.H * 2 == H && lo.W * 2 == W && lo.N == d->out.N, "seggather: low-resolution input shape mismatch");
+        *Cl = lo.C;
+    }
+    int Cs = 0;
+    if (sk.ptr) {
+        if (int rc = check_view(sk, "seggather.skip")) return rc;
+        HN_REQUIRE(sk.H == H && sk.W == W && sk.N == d->out.N, "seggather: skip input shape mismatch");
+        Cs = sk.C;
+    }
+    HN_REQUIRE(*Cl + Cs == d->out.C && d->out.C > 0, "seggather: channels %d + %d != %d", *Cl, Cs, d->out.C);
+    HN_REQUIRE((long long)d->out.N * d->out.H * d->out.W * (d->out.C / 8) < 0x7fffffffLL, "seggather: too many work items");
+    return HN_OK;
+}
+extern "C" int hn_seggather_fwd(const hn_seggather_desc* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    HN_REQUIRE(d != nullptr, "seggather: null desc");
+    int Cl;
+    if (int rc = seggather_check(d, d->low, d->skip, &Cl)) return rc;
+    View lo, sk;
+    memset(&lo, 0, sizeof(lo));
+    memset(&sk, 0, sizeof(sk));
+    if (d->low.ptr) lo = to_view(d->low);
+    if (d->skip.ptr) sk = to_view(d->skip);
+    const long long total = (long long)d->out.N * d->out.H * d->out.W * (d->out.C / 8);
+    if (total == 0) return HN_OK;
+    hn_seggather_kernel<<<hn_cdiv(total, 256), 256, 0, stream>>>(lo, sk, to_view(d->out), Cl);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+extern "C" int hn_seggather_bwd(const hn_seggather_desc* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    HN_REQUIRE(d != nullptr, "seggather bwd: null desc");
+    int Cl;
+    if (int rc = seggather_check(d, d->dlow, d->dskip, &Cl)) return rc;
+    if (d->dskip.ptr) {
+        const long long total = (long long)d->dskip.N * d->dskip.H * d->dskip.W * (d->dskip.C / 8);
+        if (total) hn_seggather_bwd_skip_kernel<<<hn_cdiv(total, 256), 256, 0, stream>>>(to_view(d->out), to_view(d->dskip), Cl);
+        HN_CHECK_CUDA(cudaGetLastError());
+    }
+    if (d->dlow.ptr) {
+        const long long total = (long long)d->dlow.N * d->dlow.H * d->dlow.W * (d->dlow.C / 8);
+        if (total) hn_seggather_bwd_low_kernel<<<hn_cdiv(total, 256), 256, 0, stream>>>(to_view(d->out), to_view(d->dlow));
+        HN_CHECK_CUDA(cudaGetLastError());
+    }
+    return HN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// head gradients: fp32 tensors in the reference's output layouts -> bf16 gradient rows
+// ------------------------------------------------------------------------------------------------
+struct HeadGradParams {
+    const float* dout;
+    const float* out;
+    int act, cols_valid, n_groups;
+    long long sn, spix, sc, rows_per_img;
+    long long group_end[HN_MAX_GROUPS], group_hw[HN_MAX_GROUPS], group_out_base[HN_MAX_GROUPS];
+    Mat dz;
+};
+__global__ void __launch_bounds__(256) hn_head_grad_kernel(const HeadGradParams p) {
+    const int CV = p.dz.cols / 8;
+    const long long total = p.dz.rows * CV;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        // rows fastest within a vector column: neighbouring threads read neighbouring pixels (coalesced for NCHW sources)
+        const int cv = (int)(i / p.dz.rows);
+        const long long r = i - (long long)cv * p.dz.rows;
+        long long base;
+        if (p.n_groups > 0) {
+            int g = 0;
+            while (g < p.n_groups - 1 && r >= p.group_end[g]) ++g;
+            const long long ml = r - (g > 0 ? p.group_end[g - 1] : 0);
+            const long long n = ml / p.group_hw[g], pix = ml - n * p.group_hw[g];
+            base = n * p.sn + p.group_out_base[g] + pix * p.spix;
+        } else {
+            const long long n = r / p.rows_per_img, pix = r - n * p.rows_per_img;
+            base = n * p.sn + pix * p.spix;
+        }
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = cv * 8 + j;
+            float g = 0.0f;
+            if (c < p.cols_valid) {
+                g = p.dout[base + c * p.sc];
+                if (p.act == HN_ACT_SIGMOID) {
+                    const float o = p.out[base + c * p.sc];
+                    g *= o * (1.0f - o);
+                }
+            }
+            v[j] = g;
+        }
+        store8(p.dz.ptr + r * p.dz.ld + cv * 8, v);
+    }
+}
+extern "C" int hn_head_grad(const hn_headgrad_desc* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    HN_REQUIRE(d != nullptr && d->dout != nullptr, "head grad: null pointer");
+    if (int rc = check_mat(d->dz, "headgrad.dz")) return rc;
+    HN_REQUIRE(d->cols_valid >= 1 && d->cols_valid <= d->dz.cols, "head grad: cols_valid=%d of %d", d->cols_valid, d->dz.cols);
+    HN_REQUIRE(d->act == HN_ACT_NONE || (d->act == HN_ACT_SIGMOID && d->out != nullptr), "head grad: unsupported activation");
+    HN_REQUIRE(d->n_groups >= 0 && d->n_groups <= HN_MAX_GROUPS, "head grad: n_groups=%d", d->n_groups);
+    HN_REQUIRE(d->n_groups > 0 || d->rows_per_img > 0, "head grad: rows_per_img missing");
+    HeadGradParams p;
+    memset(&p, 0, sizeof(p));
+    p.dout = d->dout;
+    p.out = d->out;
+    p.act = d->act;
+    p.cols_valid = d->cols_valid;
+    p.n_groups = d->n_groups;
+    p.sn = d->stride_n;
+    p.spix = d->stride_pix;
+    p.sc = d->stride_c;
+    p.rows_per_img = d->rows_per_img;
+    for (int g = 0; g < d->n_groups; ++g) {
+        p.group_end[g] = d->group_end[g];
+        p.group_hw[g] = d->group_hw[g] > 0 ? d->group_hw[g] : 1;
+        p.group_out_base[g] = d->group_out_base[g];
+    }
+    p.dz = to_mat(d->dz);
+    if (d->dz.rows == 0) return HN_OK;
+    hn_head_grad_kernel<<<ew_grid(p.dz.rows * (p.dz.cols / 8)), 256, 0, stream>>>(p);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise 3x3 weight gradient
+// ------------------------------------------------------------------------------------------------
+// CTA = chunk of pixels; thread = (8-channel vector, pixel lane) with 9 x 8 accumulators; per-chunk partial sums
+// [chunk][9][C], summed in chunk order by the finalize kernel.
+__global__ void __launch_bounds__(256) hn_dw_wgrad_kernel(View x, View dy, int pix_per_chunk, float* __restrict__ partial) {
+    __shared__ float sm[256 * 8];
+    const int CV = x.C >> 3;
+    const int ppi = 256 / CV;
+    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+    const bool active = pl < ppi;
+    const long long total = (long long)x.N * x.H * x.W;
+    const long long p0 = (long long)blockIdx.x * pix_per_chunk, p1 = min(p0 + pix_per_chunk, total);
+    float acc[9][8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[t][j] = 0.0f;
+    if (active)
+        for (long long p = p0 + pl; p < p1; p += ppi) {
+            const int xx = (int)(p % x.W);
+            const long long q = p / x.W;
+            const int yy = (int)(q % x.H), n = (int)(q / x.H);
+            float g[8];
+            load8(vptr(dy, n, yy, xx, cv * 8), g);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int iy = yy + ky - 1;
+                if (iy < 0 || iy >= x.H) continue;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ix = xx + kx - 1;
+                    if (ix < 0 || ix >= x.W) continue;
+                    float v[8];
+                    load8(vptr(x, n, iy, ix, cv * 8), v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[ky * 3 + kx][j] = fmaf(g[j], v[j], acc[ky * 3 + kx][j]);
+                }
+            }
+        }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sm[threadIdx.x * 8 + j] = acc[t][j];
+        __syncthreads();
+        if (pl == 0) {
+            float s[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] = acc[t][j];
+            for (int q = 1; q < ppi; ++q)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s[j] += sm[(q * CV + cv) * 8 + j];
+            float* o = partial + ((size_t)blockIdx.x * 9 + t) * x.C + cv * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = s[j];
+        }
+    }
+}
+__global__ void hn_sum_partials_kernel(const float* __restrict__ partial, int n_chunks, int n, float* __restrict__ out, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = accumulate ? (double)out[i] : 0.0;
+    for (int k = 0; k < n_chunks; ++k) s += (double)partial[(size_t)k * n + i];
+    out[i] = (float)s;
+}
+extern "C" int hn_dw_wgrad(const hn_view* x, const hn_view* dy, float* dw, int32_t accumulate, float* scratch, int64_t scratch_bytes, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    HN_REQUIRE(x && dy && dw && scratch, "dw wgrad: null pointer");
+    if (int rc = check_view(*x, "dwwgrad.x")) return rc;
+    if (int rc = check_view(*dy, "dwwgrad.dy")) return rc;
+    HN_REQUIRE(x->N == dy->N && x->H == dy->H && x->W == dy->W && x->C == dy->C && x->C <= 2048, "dw wgrad: shape mismatch");
+    const long long total = (long long)x->N * x->H * x->W;
+    if (total == 0) return HN_OK;
+    long long ppc = (total + kTargetChunks - 1) / kTargetChunks;
+    if (ppc < 64) ppc = 64;
+    const int chunks = (int)((total + ppc - 1) / ppc);
+    HN_REQUIRE((int64_t)((size_t)chunks * 9 * x->C * 4) <= scratch_bytes, "dw wgrad: scratch too small");
+    hn_dw_wgrad_kernel<<<chunks, 256, 0, stream>>>(to_view(*x), to_view(*dy), (int)ppc, scratch);
+    HN_CHECK_CUDA(cudaGetLastError());
+    hn_sum_partials_kernel<<<hn_cdiv(9 * x->C, 128), 128, 0, stream>>>(scratch, chunks, 9 * x->C, dw, accumulate);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem weight gradient: dW[co][k] (k = ci*9 + ky*3 + kx), warp = strip of output pixels, lane = output channel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hn_stem_wgrad_kernel(const float* __restrict__ x, int N, int H, int W, View dz, int pix_per_chunk,
+                                                            float* __restrict__ partial) {
+    __shared__ float sm[8][27][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int OH = dz.H, OW = dz.W;
+    const long long total = (long long)N * OH * OW;
+    const long long p0 = (long long)blockIdx.x * pix_per_chunk, p1 = min(p0 + pix_per_chunk, total);
+    float acc[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) acc[k] = 0.0f;
+    const int ci = lane / 9, kk = lane - ci * 9, ky = kk / 3, kx = kk - ky * 3;  // lanes 0..26 fetch one input sample each
+    for (long long p = p0 + warp; p < p1; p += 8) {
+        const int ox = (int)(p % OW);
+        const long long q = p / OW;
+        const int oy = (int)(q % OH), n = (int)(q / OH);
+        const float g = __bfloat162float(*vptr(dz, n, oy, ox, lane));
+        float v = 0.0f;
+        if (lane < 27) {
+            const int iy = 2 * oy - 1 + ky, ix = 2 * ox - 1 + kx;
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + (((long long)n * 3 + ci) * H + iy) * W + ix);
+        }
+#pragma unroll
+        for (int k = 0; k < 27; ++k) acc[k] = fmaf(g, __shfl_sync(0xffffffffu, v, k), acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 27; ++k) sm[warp][k][lane] = acc[k];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 27 * 32; i += 256) {
+        const int k = i >> 5, co = i & 31;
+        float s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += sm[w][k][co];
+        partial[(size_t)blockIdx.x * 864 + co * 27 + k] = s;  // OIHW order: [co][ci][ky][kx]
+    }
+}
+extern "C" int hn_stem_wgrad(const float* x, int32_t N, int32_t H, int32_t W, const hn_view* dz, float* dw, float* scratch, int64_t scratch_bytes,
+                             void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    HN_REQUIRE(x && dz && dw && scratch, "stem wgrad: null pointer");
+    if (int rc = check_view(*dz, "stemwgrad.dz")) return rc;
+    HN_REQUIRE(dz->C == 32 && dz->N == N && dz->H == (H + 1) / 2 && dz->W == (W + 1) / 2, "stem wgrad: shape mismatch");
+    const long long total = (long long)N * dz->H * dz->W;
+    if (total == 0) return HN_OK;
+    long long ppc = (total + 2 * kTargetChunks - 1) / (2 * kTargetChunks);
+    if (ppc < 64) ppc = 64;
+    const int chunks = (int)((total + ppc - 1) / ppc);
+    HN_REQUIRE((int64_t)((size_t)chunks * 864 * 4) <= scratch_bytes, "stem wgrad: scratch too small");
+    hn_stem_wgrad_kernel<<<chunks, 256, 0, stream>>>(x, N, H, W, to_view(*dz), (int)ppc, scratch);
+    HN_CHECK_CUDA(cudaGetLastError());
+    hn_sum_partials_kernel<<<hn_cdiv(864, 128), 128, 0, stream>>>(scratch, chunks, 864, dw, 0);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// squeeze-excite FC layers (fp32, one CTA per image)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__global__ void __launch_bounds__(256) hn_se_fc_fwd_kernel(const hn_sefc_desc d) {
+    extern __shared__ float sm[];  // mean [C], h [S]
+    float* s_mean = sm;
+    float* s_h = sm + d.C;
+    const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = threadIdx.x; c < d.C; c += 256) s_mean[c] = d.mean[(size_t)n * d.C + c];
+    __syncthreads();
+    for (int s = warp; s < d.S; s += 8) {
+        const float* w = d.w1 + (size_t)s * d.C;
+        float a = 0.0f;
+        for (int c = lane; c < d.C; c += 32) a = fmaf(w[c], s_mean[c], a);
+        a = warp_sum(a);
+        if (lane == 0) {
+            const float h = fmaxf(a + d.b1[s], 0.0f);
+            s_h[s] = h;
+            d.h[(size_t)n * d.S + s] = h;
+        }
+    }
+    __syncthreads();
+    for (int c = warp; c < d.C; c += 8) {
+        const float* w = d.w2 + (size_t)c * d.S;
+        float a = 0.0f;
+        for (int s = lane; s < d.S; s += 32) a = fmaf(w[s], s_h[s], a);
+        a = warp_sum(a);
+        if (lane == 0) d.gate[(size_t)n * d.C + c] = 1.0f / (1.0f + expf(-(a + d.b2[c])));
+    }
+}
+// per image: ds2 = dgate * gate * (1 - gate); dh = (h > 0) * W2^T ds2; dmean = W1^T dh.  tmp[n] = [ds2 (C) | dh (S)]
+__global__ void __launch_bounds__(256) hn_se_fc_bwd_kernel(const hn_sefc_desc d) {
+    extern __shared__ float sm[];  // ds2 [C], dh [S]
+    float* s_ds2 = sm;
+    float* s_dh = sm + d.C;
+    const int n = blockIdx.x;
+    float* tmp = d.tmp + (size_t)n * (d.C + d.S);
+    for (int c = threadIdx.x; c < d.C; c += 256) {
+        const float g = d.gate[(size_t)n * d.C + c];
+        const float v = d.dgate[(size_t)n * d.C + c] * g * (1.0f - g);
+        s_ds2[c] = v;
+        tmp[c] = v;
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < d.S; s += 256) {
+        float a = 0.0f;
+        for (int c = 0; c < d.C; ++c) a = fmaf(d.w2[(size_t)c * d.S + s], s_ds2[c], a);
+        a = d.h[(size_t)n * d.S + s] > 0.0f ? a : 0.0f;
+        s_dh[s] = a;
+        tmp[d.C + s] = a;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d.C; c += 256) {
+        float a = 0.0f;
+        for (int s = 0; s < d.S; ++s) a = fmaf(d.w1[(size_t)s * d.C + c], s_dh[s], a);
+        d.dmean[(size_t)n * d.C + c] = a;
+    }
+}
+// parameter gradients: sums over the batch, one thread per element
+__global__ void hn_se_fc_wgrad_kernel(const hn_sefc_desc d) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n2 = (long long)d.C * d.S;
+    const int T = d.C + d.S;
+    if (i < n2) {  // dW2[c][s] = sum_n ds2[n][c] * h[n][s]
+        const int c = (int)(i / d.S), s = (int)(i - (long long)c * d.S);
+        float a = 0.0f;
+        for (int n = 0; n < d.N; ++n) a = fmaf(d.tmp[(size_t)n * T + c], d.h[(size_t)n * d.S + s], a);
+        d.dw2[i] = a;
+    } else if (i < 2 * n2) {  // dW1[s][c] = sum_n dh[n][s] * mean[n][c]
+        const long long k = i - n2;
+        const int s = (int)(k / d.C), c = (int)(k - (long long)s * d.C);
+        float a = 0.0f;
+        for (int n = 0; n < d.N; ++n) a = fmaf(d.tmp[(size_t)n * T + d.C + s], d.mean[(size_t)n * d.C + c], a);
+        d.dw1[k] = a;
+    } else if (i < 2 * n2 + d.C) {
+        const int c = (int)(i - 2 * n2);
+        float a = 0.0f;
+        for (int n = 0; n < d.N; ++n) a += d.tmp[(size_t)n * T + c];
+        d.db2[c] = a;
+    } else if (i < 2 * n2 + d.C + d.S) {
+        const int s = (int)(i - 2 * n2 - d.C);
+        float a = 0.0f;
+        for (int n = 0; n < d.N; ++n) a += d.tmp[(size_t)n * T + d.C + s];
+        d.db1[s] = a;
+    }
+}
+extern "C" int hn_se_fc_fwd(const hn_sefc_desc* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    HN_REQUIRE(d && d->mean && d->w1 && d->b1 && d->w2 && d->b2 && d->h && d->gate, "se fc: null pointer");
+    HN_REQUIRE(d->N >= 1 && d->C >= 1 && d->S >= 1 && (size_t)(d->C + d->S) * 4 <= 48 * 1024, "se fc: bad sizes N=%d C=%d S=%d", d->N, d->C, d->S);
+    hn_se_fc_fwd_kernel<<<d->N, 256, (size_t)(d->C + d->S) * 4, stream>>>(*d);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+extern "C" int hn_se_fc_bwd(const hn_sefc_desc* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    HN_REQUIRE(d && d->mean && d->w1 && d->w2 && d->h && d->gate && d->dgate && d->dmean && d->dw1 && d->db1 && d->dw2 && d->db2 && d->tmp,
+               "se fc bwd: null pointer");
+    HN_REQUIRE(d->N >= 1 && d->C >= 1 && d->S >= 1 && (size_t)(d->C + d->S) * 4 <= 48 * 1024, "se fc bwd: bad sizes");
+    hn_se_fc_bwd_kernel<<<d->N, 256, (size_t)(d->C + d->S) * 4, stream>>>(*d);
+    HN_CHECK_CUDA(cudaGetLastError());
+    const long long total = 2LL * d->C * d->S + d->C + d->S;
+    hn_se_fc_wgrad_kernel<<<hn_cdiv(total, 256), 256, 0, stream>>>(*d);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: fp32 parameters -> bf16 K-major 64-column blocks, every layer in one launch
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hn_pack_kernel(const hn_pack_entry* __restrict__ entries) {
+    const hn_pack_entry e = entries[blockIdx.x];
+    const int r = blockIdx.y * 32 + (threadIdx.x >> 3);
+    if (r >= e.rows_pad) return;
+    const int j0 = (threadIdx.x & 7) * 8;
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int j = j0 + q;
+        float x = 0.0f;
+        if (r < e.rows) {
+            if (e.grouped == 0) {
+                if (j < e.cols) x = e.src[(long long)r * e.s_r + (long long)j * e.s_c];
+            } else if (e.grouped == 1) {  // forward: row = co, column = input channel within the 64-block; group = 8 channels
+                if ((j >> 3) == ((r & 63) >> 3)) x = e.src[(long long)r * e.s_r + (long long)(j & 7) * e.s_c];
+            } else {  // dgrad: row = ci, column = co within the 64-block
+                const int co = (r & ~63) + j;
+                if (co < e.rows && (j >> 3) == ((r & 63) >> 3)) x = e.src[(long long)co * e.s_r + (long long)(r & 7) * e.s_c];
+            }
+        }
+        v[q] = x;
+    }
+    store8(reinterpret_cast<bf16*>(e.dst) + (long long)r * e.dst_ld + j0, v);
+}
+extern "C" int hn_pack_weights(const hn_pack_entry* entries_device, int32_t n, int32_t max_rows_pad, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    HN_REQUIRE(entries_device != nullptr && n >= 1 && max_rows_pad >= 1, "pack: bad arguments");
+    HN_REQUIRE(hn_cdiv(max_rows_pad, 32) <= 65535, "pack: too many rows");
+    hn_pack_kernel<<<dim3((unsigned)n, (unsigned)hn_cdiv(max_rows_pad, 32)), 256, 0, stream>>>(entries_device);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam: L2 weight decay folded into the gradient, bias-corrected moments)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hn_adam_kernel(const hn_adam_tensor* __restrict__ tensors, const int32_t* __restrict__ chunk_tensor,
+                                                      const int32_t* __restrict__ chunk_index, int chunk_elems, float lr, float beta1, float beta2,
+                                                      float eps, float wd, float bc1, float bc2_sqrt, float grad_scale) {
+    const hn_adam_tensor t = tensors[chunk_tensor[blockIdx.x]];
+    const long long b = (long long)chunk_index[blockIdx.x] * chunk_elems;
+    const long long e = min(b + chunk_elems, (long long)t.n);
+    const float step_size = lr / bc1;
+    for (long long i = b + threadIdx.x; i < e; i += 256) {
+        const float p = t.p[i];
+        float g = t.g[i] * grad_scale;
+        g = fmaf(wd, p, g);
+        const float m = beta1 * t.m[i] + (1.0f - beta1) * g;
+        const float v = beta2 * t.v[i] + (1.0f - beta2) * g * g;
+        t.m[i] = m;
+        t.v[i] = v;
+        const float denom = sqrtf(v) / bc2_sqrt + eps;
+        t.p[i] = p - step_size * (m / denom);
+    }
+}
+extern "C" int hn_adam_step(const hn_adam_tensor* tensors_device, const int32_t* chunk_tensor_device, const int32_t* chunk_index_device,
+                            int32_t n_chunks, int32_t chunk_elems, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                            float grad_scale, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    HN_REQUIRE(tensors_device && chunk_tensor_device && chunk_index_device && n_chunks >= 1 && chunk_elems >= 256 && step >= 1, "adam: bad arguments");
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    hn_adam_kernel<<<n_chunks, 256, 0, stream>>>(tensors_device, chunk_tensor_device, chunk_index_device, chunk_elems, lr, beta1, beta2, eps, weight_decay,
+                                                 (float)bc1, (float)sqrt(bc2), grad_scale);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}

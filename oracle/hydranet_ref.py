@@ -34,8 +34,14 @@ def ieee_fp32():
         torch.backends.cudnn.conv.fp32_precision, torch.backends.cuda.matmul.fp32_precision = conv, mm
 
 
+_TRAIN = False  # set by forward(train=True): batch statistics + running-stat update, as nn.BatchNorm2d in .train() mode
+
+
 def _bn(sd, p, x, eps):
-    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"], False, 0.0, eps)
+    # momentum follows the reference's constructors: default 0.1 with eps 1e-5 (backbone, lane head), 0.01 with eps 1e-3
+    # (neck, detection head: common.py:97, detection.py:22)
+    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"], _TRAIN,
+                        (0.1 if eps == 1e-5 else 0.01) if _TRAIN else 0.0, eps)
 
 
 def _swish(x):
@@ -211,10 +217,17 @@ def lane_head(sd, fused, stride, num_classes, n_loc):
     return cls, loc.view(loc.shape[0], -1, n_loc)
 
 
-def forward(sd, cfg, x, want_feats=False):
-    """state_dict + cfg + fp32 NCHW input -> the reference's output dict (model.py:159-192).  IEEE fp32 on any device."""
-    with ieee_fp32():
-        return _forward(sd, cfg, x, want_feats)
+def forward(sd, cfg, x, want_feats=False, train=False):
+    """state_dict + cfg + fp32 NCHW input -> the reference's output dict (model.py:159-192).  IEEE fp32 on any device.
+    train=True: BatchNorm uses batch statistics and updates sd's running statistics in place (train.py:242); tensors of
+    ``sd`` that require grad stay leaves, so ``backward`` on a loss of the outputs yields the reference's gradients."""
+    global _TRAIN
+    _TRAIN = bool(train)
+    try:
+        with ieee_fp32():
+            return _forward(sd, cfg, x, want_feats)
+    finally:
+        _TRAIN = False
 
 
 def _forward(sd, cfg, x, want_feats=False):

@@ -140,8 +140,8 @@ def test_errors():
     with pytest.raises(ValueError):
         m_gpu(torch.zeros(1, 3, 96, 128, device="cuda"))  # not divisible by the P7 stride (detection.py:141-142)
     m_gpu.train()
-    with pytest.raises(NotImplementedError):
-        m_gpu(torch.zeros(1, 3, 128, 128, device="cuda"))
+    with pytest.raises(RuntimeError):
+        m_gpu(torch.zeros(1, 3, 128, 128))  # train mode is native too: still no CPU fallback
 
 
 def test_cuda_graph_replay():
@@ -170,14 +170,14 @@ def test_cluster_multicast_equals_single_cta():
     try:
         for cs in (1, 2):
             nv.lib.hn_conv_set_cluster(cs)
-            m_gpu._plans = {}
+            m_gpu._plans.clear()
             with torch.no_grad():
                 o = m_gpu(x)
             outs.append({"seg": o["seg"].clone(), "reg": o["detection"]["regression"].clone(), "loc": o["lane"]["predict_loc"].clone()})
     finally:
         nv.lib.hn_conv_set_cluster(0)
         nv.lib.hn_conv_set_tap_runs(1)
-    m_gpu._plans = {}
+    m_gpu._plans.clear()
     for k in outs[0]:
         assert torch.equal(outs[0][k], outs[1][k]), k
 
@@ -193,14 +193,14 @@ def test_tap_runs_equal_tap_per_stage():
     try:
         for mode in (0, 2):
             nv.lib.hn_conv_set_tap_runs(mode)
-            m_gpu._plans = {}
+            m_gpu._plans.clear()
             with torch.no_grad():
                 o = m_gpu(x)
             outs.append({"seg": o["seg"].clone(), "reg": o["detection"]["regression"].clone(),
                          "cls": o["detection"]["classification"].clone(), "loc": o["lane"]["predict_loc"].clone()})
     finally:
         nv.lib.hn_conv_set_tap_runs(1)
-    m_gpu._plans = {}
+    m_gpu._plans.clear()
     for k in outs[0]:
         a, b = outs[0][k].float(), outs[1][k].float()
         assert torch.isfinite(b).all()
@@ -224,23 +224,23 @@ def test_split_batch_equals_single_plan():
             out.append(t.clone())
         return out
     m_gpu.split_batch = False
-    m_gpu._plans = {}
+    m_gpu._plans.clear()
     with torch.no_grad():
         ref = grab(m_gpu(x))
     m_gpu.split_batch = True
-    m_gpu._plans = {}
+    m_gpu._plans.clear()
     with torch.no_grad():
         eager = grab(m_gpu(x))
     s = torch.cuda.Stream()
     with torch.cuda.stream(s), torch.no_grad():
         m_gpu.use_graph = True
-        m_gpu._plans = {}
+        m_gpu._plans.clear()
         g1 = grab(m_gpu(x))
         g2 = grab(m_gpu(x))
         u8 = m_gpu.seg_class_map().clone()
     s.synchronize()
     m_gpu.use_graph = False
-    m_gpu._plans = {}
+    m_gpu._plans.clear()
     for a, b, c, d, k in zip(ref, eager, g1, g2, keys):
         assert torch.equal(a, b) and torch.equal(a, c) and torch.equal(a, d), k
     assert torch.equal(u8.long(), ref[0].argmax(1)) or (u8.long() == ref[0].argmax(1)).float().mean() > 0.999
@@ -286,4 +286,4 @@ def test_fused_postprocess_equals_separate_decoders():
     finally:
         m_gpu.use_graph = False
         m_gpu.fuse_postprocess()
-        m_gpu._plans = {}
+        m_gpu._plans.clear()
