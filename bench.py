@@ -119,6 +119,7 @@ def run_native(args):
     dev = torch.device("cuda", local)
     hb, m, cfg = build_model(dev)
     m.use_graph = not args.no_graph
+    m.static_outputs = True  # serving mode: zero-copy views of the plan's buffers (this loop snapshots what it downloads itself)
     from hydranet_b200 import _native as nv
     B, H, W = args.batch, 640, 640
     codec = hb.LaneCodec(W, H, cfg["lane"]["anchor_stride"], int(H / cfg["lane"]["interval"]), True, 1, True)
@@ -169,8 +170,11 @@ def run_native(args):
     # ---------------- end to end through the public API with host buffers ----------------
     # Every step copies its own input batch host->device (pinned memory) and reads its results back; the
     # copies run on side streams so that step i+1's upload and step i-1's download overlap step i's compute.
+    # Inputs travel as uint8 HWC camera frames (B x 640 x 640 x 3 = 39 MB instead of 157 MB of fp32 NCHW); the GPU pre-processing
+    # kernel (demo.py:191-196: BGR->RGB, resize, normalise, HWC->CHW) writes straight into the plan's static input.
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    xin = [torch.empty((B, 3, H, W), dtype=torch.float32, device=dev) for _ in range(2)]
+    host_u8 = [torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(2)]
+    xin = [torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]
     ev_done = [torch.cuda.Event() for _ in range(2)]
@@ -180,7 +184,7 @@ def run_native(args):
         k = i % 2
         with torch.cuda.stream(s_in):
             s_in.wait_event(ev_free[k])  # the compute that last read xin[k] has finished
-            xin[k].copy_(host[i % 2], non_blocking=True)
+            xin[k].copy_(host_u8[i % 2], non_blocking=True)
             ev_in[k].record(s_in)
 
     segcopy = [torch.empty((B, H, W), dtype=torch.uint8, device=dev) for _ in range(2)]
@@ -249,8 +253,10 @@ def run_native(args):
                 if i + 1 < n:
                     upload(i + 1)
                 stream.wait_event(ev_in[k])
-            out, d, l = step(xin[k])
-            ev_free[k].record(stream)
+            x_plan = m.input_buffer(B, H, W, dev)
+            hb.preprocess(xin[k], (W, H), out=x_plan)
+            ev_free[k].record(stream)  # the frame buffer is free as soon as it has been pre-processed
+            out, d, l = step(x_plan)
             if do_down:
                 stream.wait_event(ev_read[k])  # the download that last used snapshot set k (two steps ago) is complete
                 segcopy[k].copy_(out["seg_cls_u8"])  # the class map is the plan's static buffer: snapshot it for the download
@@ -295,14 +301,14 @@ def run_native(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
     e2e_val = world * B * args.steps / (e2e_ms / 1e3)
-    h2d = host[0].numel() * 4
+    h2d = host_u8[0].numel()
     d2h = d2h_bytes[0]
     # host link speed, for context (pinned memory, 157 MB)
     tcp = []
     for _ in range(3):
         a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a_.record(stream)
-        xin[0].copy_(host[0], non_blocking=True)
+        xin[0].copy_(host_u8[0], non_blocking=True)
         b_.record(stream)
         torch.cuda.synchronize(dev)
         tcp.append(a_.elapsed_time(b_))
@@ -410,8 +416,18 @@ def run_native(args):
             torch.cuda.synchronize(dev)
             ts.append(a.elapsed_time(b_))
         ts.sort()
+        # host cost of one forward call (Python facade + one graph launch), GPU kept busy so nothing waits on the device
+        x1p = m.input_buffer(1, H, W, dev)
+        torch.cuda.synchronize(dev)
+        th0 = time.perf_counter()
+        with torch.no_grad():
+            for _ in range(100):
+                m(x1p)
+        host_us = (time.perf_counter() - th0) * 1e4
+        torch.cuda.synchronize(dev)
         lat = {"p50": round(ts[len(ts) // 2], 3), "p90": round(ts[int(len(ts) * 0.9)], 3), "unit": "ms", "batch": 1,
-               "what": "forward (CUDA graph replay) + det/lane/seg post-processing, device time"}
+               "what": "forward (CUDA graph replay) + det/lane/seg post-processing, device time",
+               "forward_host_us": round(host_us, 1)}
 
     if rank == 0:
         # own kernels per step: the plan (forward; + 12 detection + 1 lane kernels when the decoders are plan ops); the
@@ -426,8 +442,167 @@ def run_native(args):
                            "l2_policy": "2 alternating input batches of 157 MB each (> 126 MB L2)"},
                 "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": round(e2e_ms / args.steps, 3), "h2d_link_gbs": round(h2d_gbs, 1),
-                        "pipeline": "upload of step i+1 and download of step i-1 overlap the compute of step i"},
+                        "pipeline": "uint8 HWC frames up (39 MB) -> GPU pre-processing into the plan input -> forward + decoders -> results down; "
+                                    "upload of step i+1 and download of step i-1 overlap the compute of step i"},
                 "gpu_launches": n_launch * args.steps, "library_launches": 20 * args.steps, "clocks": clocks, "latency_b1_ms": lat, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+
+def run_train(args):
+    """--mode train: BASELINE.json configs[3] -- one data-parallel training step per "step": train-mode forward (batch-stat
+    BatchNorm), cal_loss (model.py:201-264), weighted total (train.py:192-203), backward (native dgrad / wgrad), bucketed NCCL
+    gradient all-reduce overlapped with backward, Adam (train.py:147: lr 1e-5, wd 1e-8) in one kernel.  Weak scaling: `--batch`
+    images per GPU.  Inputs and synthetic ground truth are resident on the device; e2e uploads them from pinned host memory every
+    step and reads the loss back."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    import hydranet_b200 as hb
+    from hydranet_b200.config import big_cfg
+    from oracle import train_golden  # synthetic ground-truth generator only (config 4 formats); nothing of the oracle is timed
+    cfg = big_cfg()
+    torch.manual_seed(0)
+    m = hb.HydraNet(cfg).to(dev).train()
+    B, H, W = args.batch, 640, 640
+    opt = hb.FusedAdam(m.parameters(), lr=cfg["train"]["lr"], weight_decay=cfg["train"]["weight_decay"])
+    red = hb.GradAllReduce(m.parameters(), bucket_mb=25.0)
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    host_x = [torch.randn(B, 3, H, W, generator=g).pin_memory() for _ in range(2)]
+    gt_host = train_golden.synthetic_gt(B, H, W, H // 32, W // 32, H // 8, seed=5 + rank)
+    gt_host = {k: v.pin_memory() for k, v in gt_host.items()}
+    xs = [h.to(dev) for h in host_x]
+    gt = {k: v.to(dev) for k, v in gt_host.items()}
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    # graph mode (default): forward + loss + backward (+ Adam when there is nothing to exchange) replayed as ONE CUDA graph,
+    # gradients averaged after it by one coalesced NCCL all-reduce; --no-graph: eager launches with the bucketed exchange
+    # overlapped with backward (GradAllReduce hooks)
+    if args.no_graph:
+        ts = hb.TrainStep(m, opt, graph=False, reducer=red)
+    else:
+        red.remove()
+        ts = hb.TrainStep(m, opt, graph=True)
+
+    def step(x, gtd, measure=False):
+        return ts(x, gtd)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(xs[i % 2], gt)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for i in range(args.steps):
+        loss = step(xs[i % 2], gt)
+    e1.record(stream)
+    host_ms = (time.perf_counter() - t0) * 1e3  # host time to ENQUEUE the steps (Python + launches)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms / 1e3)
+    # exposed (non-overlapped) part of the gradient exchange: time the compute stream waits for the comm stream at the end of backward
+    exposed = None
+    if world > 1:
+        vals = []
+        for i in range(3):
+            if args.no_graph:  # time the compute stream spends waiting for the side-stream exchange after backward
+                loss_, _ = ts._fwd_bwd(xs[i % 2], gt)
+                red.finish(measure=True)
+                opt.step()
+                vals.append(red.exposed_ms)
+            else:  # graph mode: the exchange follows the graph, nothing overlaps it
+                ts.static[0].copy_(xs[i % 2])
+                ts.graph.replay()
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record(stream)
+                ts._exchange()
+                b_.record(stream)
+                opt.step()
+                b_.synchronize()
+                vals.append(a_.elapsed_time(b_))
+        exposed = sorted(vals)[1]
+    # e2e: pinned host -> device every step, loss read back
+    barrier()
+    xin = [torch.empty_like(xs[0]) for _ in range(2)]
+    gin = [{k: torch.empty_like(v) for k, v in gt.items()} for _ in range(2)]
+    s_in = torch.cuda.Stream(dev)
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(i):
+        k = i % 2
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_free[k])
+            xin[k].copy_(host_x[k], non_blocking=True)
+            for kk, v in gt_host.items():
+                gin[k][kk].copy_(v, non_blocking=True)
+            ev_in[k].record(s_in)
+
+    def e2e_loop(n):
+        for k in range(2):
+            ev_free[k].record(stream)
+        upload(0)
+        losses_ = []
+        for i in range(n):
+            k = i % 2
+            if i + 1 < n:
+                upload(i + 1)
+            stream.wait_event(ev_in[k])
+            l = step(xin[k], gin[k])
+            ev_free[k].record(stream)
+            losses_.append(l.detach())
+        return [float(v) for v in losses_]  # device -> host read of every step's loss
+
+    e2e_loop(3)
+    barrier()
+    t0 = time.perf_counter()
+    vals = e2e_loop(args.steps)
+    torch.cuda.synchronize(dev)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([e2e_ms], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    h2d = host_x[0].numel() * 4 + sum(v.numel() * v.element_size() for v in gt_host.values())
+    if rank == 0:
+        n_param = sum(p.numel() for p in m.parameters())
+        line = {"metric": "images/s train step (fwd+loss+bwd+allreduce+Adam)", "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "HydraNet big cfg training step, batch %d/GPU, 640x640, bf16 activations / fp32 master weights, 3 heads, "
+                                       "cal_loss + Adam(lr 1e-5, wd 1e-8); random-init weights, synthetic ground truth (config 4)" % B,
+                           "global_batch": world * B, "parallelism": "data-parallel x%d, NCCL gradient all-reduce (%.1f MB fp32), %s"
+                                                                     % (world, n_param * 4 / 1e6, "bucketed, overlapped with backward (eager)" if args.no_graph
+                                                                        else "one coalesced call after the CUDA-graph step"),
+                           "launch": "eager" if args.no_graph else "CUDA graph (forward + loss + backward%s)" % (" + Adam" if world == 1 else ""),
+                           "l2_policy": "2 alternating input batches (%d MB each)" % (host_x[0].numel() * 4 // 1000000)},
+                "e2e": {"value": round(world * B * args.steps / (e2e_ms / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "ms_per_step": round(e2e_ms / args.steps, 3)},
+                "host_enqueue_ms_per_step": round(host_ms / args.steps, 3), "allreduce_exposed_ms": exposed, "final_loss": vals[-1], "clocks": clocks}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -453,20 +628,65 @@ def cpu_baseline(m, cfg, seconds=15.0, steps=None, batch=2):
                       "batched_nms + lane decode + argmax, all host threads" % (n, batch, dt)}
 
 
+def _reference_cfg():
+    """The keys oracle/hydranet_ref.forward reads, with the values of model/cfgs/hydranet_joint_big_backbone.yml."""
+    return {"train": {"train_detect": True, "train_seg": True, "train_lane": True},
+            "dataloader": {"network_input_width": 640, "network_input_height": 640},
+            "backbone": {"group_width": 8, "stride": 2},
+            "detection": {"num_classes": 9, "aspect_ratios_factor": [1.4, 0.7], "scales_factor": [0.0, 0.333, 0.667], "box_class_repeats": 3,
+                          "pyramid_levels": 5, "anchor_scale": 2.0},
+            "lane": {"anchor_stride": 32, "interval": 8, "num_classes": 2}}
+
+
+def _reference_init(template, seed=0):
+    """Random initialisation as the reference builds it: backbone convolutions N(0, sqrt(2 / fan_out)) (anynet.py:124-134), every
+    other convolution PyTorch's default (kaiming_uniform(a=sqrt(5)) weights, U(+-1/sqrt(fan_in)) biases), BatchNorm gamma 1 / beta 0,
+    running statistics 0 / 1, BiFPN fusion weights 1 (bifpn.py:104-123)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, t in template.items():
+        shape = tuple(t.shape)
+        stem = k.rsplit(".", 1)[0]
+        if k.endswith("num_batches_tracked"):
+            v = torch.zeros(shape, dtype=torch.int64)
+        elif k.endswith("running_mean"):
+            v = torch.zeros(shape)
+        elif k.endswith("running_var") or "_w1" in k or "_w2" in k:
+            v = torch.ones(shape)
+        elif (stem + ".running_mean") in template:
+            v = torch.ones(shape) if k.endswith(".weight") else torch.zeros(shape)
+        elif len(shape) == 4:
+            fan_in = shape[1] * shape[2] * shape[3]
+            if k.startswith("backbone."):
+                v = torch.randn(shape, generator=g) * (2.0 / (shape[0] * shape[2] * shape[3])) ** 0.5
+            else:
+                v = (torch.rand(shape, generator=g) * 2 - 1) / fan_in ** 0.5
+        else:  # conv bias
+            w = template.get(stem + ".weight")
+            fan_in = (w.shape[1] * w.shape[2] * w.shape[3]) if w is not None and w.dim() == 4 else shape[0]
+            v = (torch.rand(shape, generator=g) * 2 - 1) / fan_in ** 0.5
+        sd[k] = v
+    return sd
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; the live
     reference tree does not exist on the GPU box), bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import hydranet_b200  # noqa: F401  (parameter tree only; nothing native is launched)
-    from hydranet_b200.config import big_cfg
-    from hydranet_b200.model import HydraNet
     from oracle import cpu_baseline as cb
-    cfg = big_cfg()
-    torch.manual_seed(0)
-    m = HydraNet(cfg).eval()
-    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    cfg = _reference_cfg()
+    # The state_dict is rebuilt from the committed key / shape list of the reference's big cfg (tests/golden/state_dict_keys_big.txt,
+    # written next to the live reference): the reference arm never imports the native package, so none of its code or its .so is
+    # mapped into this process.  Values: the reference's random initialisation (below), as in the native arm: detection scores
+    # sit near 0.5, so every anchor passes the 0.4 threshold and the NMS sees the same maximum-candidate workload.
+    template = {}
+    for line in open(os.path.join(ROOT, "tests", "golden", "state_dict_keys_big.txt")):
+        name, rest = line.split(" ", 1)
+        shape = tuple(int(v) for v in rest[rest.index("(") + 1:rest.index(")")].replace(",", " ").split())
+        template[name] = torch.empty(shape, dtype=torch.int64 if "int64" in rest else torch.float32)
+    sd = _reference_init(template)
     torch.set_num_threads(os.cpu_count() or 1)
     batch = 2
     x = torch.randn(batch, 3, 640, 640, generator=torch.Generator().manual_seed(0))
@@ -494,8 +714,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default 32 for inference, 16 for training)")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"], help="infer: configs[1]/[2] (the headline metric); train: configs[3], the training step")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--dump-ops", action="store_true", help="write per-op device times to gpurun_out/op_times.txt")
     ap.add_argument("--e2e-probe", action="store_true", help="print the e2e loop time with upload / download switched off")
@@ -504,10 +725,14 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the forward kernel by kernel instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.batch is None:
+        args.batch = 16 if args.mode == "train" else 32
     if args.impl == "reference":
         return run_reference(args)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the native arm has no CPU fallback (use --impl reference for the CPU path)")
+    if args.mode == "train":
+        return run_train(args)
     run_native(args)
 
 

@@ -471,10 +471,15 @@ typedef struct hn_adam_tensor {
 } hn_adam_tensor;
 int hn_adam_step(const hn_adam_tensor* tensors_device, const int32_t* chunk_tensor_device, const int32_t* chunk_index_device,
                  int32_t n_chunks, int32_t chunk_elems, float lr, float beta1, float beta2, float eps, float weight_decay,
-                 int32_t step, float grad_scale, void* stream);
+                 int32_t step, float grad_scale, float* dyn_device, void* stream);
+/* dyn_device (optional): fp32 [2] = {learning rate, number of steps taken so far}.  When given, `lr` / `step` are ignored:
+ * the kernel reads them from the device and a second one-thread kernel advances the step count -- so a CUDA graph that
+ * captured the call keeps stepping correctly, and a scheduler changes the rate with one small device write. */
 
 /* diagnostics: when set (before a conv is prepared), every conv CTA stores 16 int64 globaltimer stamps */
 void hn_conv_set_debug_buffer(void* device_i64);
+void hn_se_set_split_fc(int on); /* tuning knob: squeeze-excite FC layers as two batched launches after the pooling (default on) or fused into the pooling kernel's tail */
+int hn_se_pool_num_launches(const hn_se_pool_desc* d);
 void hn_conv_set_cluster(int ctas); /* tuning knob: CTAs per cluster sharing a weight tile (0 = default, 1 = off) */
 void hn_conv_set_pair_min_bn(int bn); /* tuning knob: narrowest N tile run on CTA pairs (default 192) */
 void hn_det_set_rounds_ctas_per_sm(int n); /* tuning knob: CTAs per SM of the cooperative NMS rounds kernel (default 2) */

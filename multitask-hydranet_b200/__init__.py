@@ -10,6 +10,7 @@ from .model import HydraNet  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .parallel import GradAllReduce  # noqa: F401
 from .preprocess import preprocess  # noqa: F401
+from .train import TrainStep  # noqa: F401
 
 __all__ = ["HydraNet", "SegmentHeader", "DetectionHeader", "LaneHeader", "LaneCodec", "Lane", "Point",
-           "make_anchors", "order_lane_x_axis", "convert_lane_to_dict", "preprocess", "FusedAdam", "GradAllReduce"]
+           "make_anchors", "order_lane_x_axis", "convert_lane_to_dict", "preprocess", "FusedAdam", "GradAllReduce", "TrainStep"]

@@ -207,7 +207,7 @@ SYMBOLS = {
     "hn_pack_weights": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "hn_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), _P]),
     "hn_adam_step": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
-                               C.c_float, _P]),
+                               C.c_float, _P, _P]),
     "hn_plan_create": (C.c_int, [C.POINTER(_P)]),
     "hn_plan_destroy": (C.c_int, [_P]),
     "hn_plan_add_conv": (C.c_int, [_P, C.POINTER(ConvDesc)]),
@@ -228,6 +228,8 @@ SYMBOLS = {
     "hn_plan_graph_capture": (C.c_int, [_P, _P]),
     "hn_plan_graph_launch": (C.c_int, [_P, _P]),
     "hn_conv_set_debug_buffer": (None, [_P]),
+    "hn_se_set_split_fc": (None, [C.c_int]),
+    "hn_se_pool_num_launches": (C.c_int, [C.POINTER(SePoolDesc)]),
     "hn_conv_set_cluster": (None, [C.c_int]),
     "hn_conv_set_tap_runs": (None, [C.c_int]),
     "hn_set_pdl": (None, [C.c_int]),
@@ -265,6 +267,8 @@ if os.environ.get("HN_BRANCH_PRIO"):
     lib.hn_plan_set_branch_priority(int(os.environ["HN_BRANCH_PRIO"]))
 if os.environ.get("HN_ROUNDS_PASSES"):
     lib.hn_det_set_rounds_passes(int(os.environ["HN_ROUNDS_PASSES"]))
+if os.environ.get("HN_SE_SPLIT_FC"):
+    lib.hn_se_set_split_fc(int(os.environ["HN_SE_SPLIT_FC"]))
 if os.environ.get("HN_CLUSTER"):
     lib.hn_conv_set_cluster(int(os.environ["HN_CLUSTER"]))
 

@@ -129,6 +129,7 @@ static int op_launches(const PlanOp* o) {
     switch (o->kind) {
         case OP_DET: return hn_det_num_launches(&o->det);
         case OP_LANE: return 1;
+        case OP_SE_POOL: return hn_se_pool_num_launches(&o->se_pool);
         default: return 1;
     }
 }

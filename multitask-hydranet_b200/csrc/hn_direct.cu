@@ -796,6 +796,76 @@ __global__ void __launch_bounds__(kSeThreads) hn_se_pool_kernel(View x, float* _
     }
 }
 
+
+// ---- squeeze-excite FC layers as two batched launches (all images per CTA) ------------------------------------------
+// The fused tail above runs the two FC layers of an image in ONE block (a chain of dependent L2 loads on 32 SMs while
+// the other 116 idle).  Split form: pooling only, then FC1 with a CTA per group of hidden units and FC2 with a CTA per
+// group of channels, each CTA serving every image -- the weights are read once per CTA instead of once per image, and both
+// launches fill the machine.  Same arithmetic and roundings as the fused tail (bf16 mean, bf16 hidden, bf16 gate).
+static constexpr int kFc1Units = 4;   // hidden units per CTA
+static constexpr int kFc2Chans = 32;  // channels per CTA
+__global__ void __launch_bounds__(256) hn_se_fc1_kernel(const bf16* __restrict__ mean, int N, int C, SeFc fc, bf16* __restrict__ hidden) {
+    hn_pdl_launch_dependents();
+    hn_pdl_wait();
+    extern __shared__ float sm[];  // [kFc1Units][C] weights as fp32
+    const int s0 = blockIdx.x * kFc1Units;
+    for (int i = threadIdx.x; i < kFc1Units * C; i += blockDim.x) {
+        const int u = i / C, c = i - u * C;
+        sm[i] = s0 + u < fc.S ? __bfloat162float(fc.w1[(long long)(s0 + u) * C + c]) : 0.0f;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, CV = C >> 3;
+    for (int n = warp; n < N; n += 8) {
+        float acc[kFc1Units];
+#pragma unroll
+        for (int u = 0; u < kFc1Units; ++u) acc[u] = 0.0f;
+        for (int v = lane; v < CV; v += 32) {
+            float m[8];
+            load8(mean + (long long)n * C + v * 8, m);
+#pragma unroll
+            for (int u = 0; u < kFc1Units; ++u) {
+                const float* w = sm + u * C + v * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[u] = fmaf(w[j], m[j], acc[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kFc1Units; ++u) {
+            float a = acc[u];
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0 && s0 + u < fc.S) hidden[(long long)n * fc.S + s0 + u] = __float2bfloat16(fmaxf(a + fc.b1[s0 + u], 0.0f));
+        }
+    }
+}
+__global__ void __launch_bounds__(256) hn_se_fc2_kernel(const bf16* __restrict__ hidden, int N, int C, SeFc fc) {
+    hn_pdl_launch_dependents();
+    hn_pdl_wait();
+    extern __shared__ float sm[];  // [kFc2Chans][S + 1] weights as fp32 (padded rows: no bank conflicts across channels)
+    const int c0 = blockIdx.x * kFc2Chans, S = fc.S, ld = S + 1;
+    for (int i = threadIdx.x; i < kFc2Chans * S; i += blockDim.x) {
+        const int u = i / S, s = i - u * S;
+        sm[u * ld + s] = c0 + u < C ? __bfloat162float(fc.w2[(long long)(c0 + u) * S + s]) : 0.0f;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = c0 + lane;
+    const float b = c < C ? fc.b2[c] : 0.0f;
+    for (int n = warp; n < N; n += 8) {
+        const bf16* h = hidden + (long long)n * S;
+        float acc = 0.0f;
+        for (int s = 0; s < S; s += 8) {
+            float hv[8];
+            load8(h + s, hv);  // the same 16 bytes for every lane: one broadcast transaction
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = fmaf(sm[lane * ld + s + j], hv[j], acc);
+        }
+        if (c < C) fc.gate[(long long)n * C + c] = __float2bfloat16(1.0f / (1.0f + expf(-(acc + b))));
+    }
+}
+static int g_se_split_fc = 1;
+extern "C" void hn_se_set_split_fc(int on) { g_se_split_fc = on ? 1 : 0; }
+extern "C" int hn_se_pool_num_launches(const hn_se_pool_desc* d) { return (d && d->S > 0 && g_se_split_fc) ? 3 : 1; }
+
 __global__ void hn_se_scale_kernel(View x, const bf16* __restrict__ scale) {
     hn_pdl_launch_dependents();
     hn_pdl_wait();
@@ -841,6 +911,22 @@ extern "C" int hn_se_pool_fwd(const hn_se_pool_desc* d, void* stream) {
         fc.gate = reinterpret_cast<bf16*>(d->gate);
         const size_t need = (size_t)(((C + 7) & ~7) + d->S) * sizeof(float);  // mean + hidden reuse the pooling scratch
         if (need > smem) smem = need;
+    }
+    if (fc.S && g_se_split_fc && (size_t)kFc1Units * C * 4 <= 48 * 1024 && (size_t)kFc2Chans * (fc.S + 1) * 4 <= 48 * 1024) {
+        // pooling only, then the two FC layers as batched launches; `partial` is free again once the pool kernel is done
+        // and holds the hidden activations (bf16 [N][S], needs N*S*2 <= N*chunks*C*4 bytes: S <= C always)
+        SeFc none;
+        memset(&none, 0, sizeof(none));
+        const size_t pool_smem = (size_t)lanes * CG * 8 * sizeof(float);
+        HN_CHECK_CUDA(hn_launch(hn_se_pool_kernel, dim3(grid), dim3(kSeThreads), pool_smem, reinterpret_cast<cudaStream_t>(stream),
+            to_view(d->x), d->partial, d->counter, reinterpret_cast<bf16*>(d->mean), 1.0f / (float)HW, d->pix_per_block, none));
+        bf16* hidden = reinterpret_cast<bf16*>(d->partial);
+        HN_CHECK_CUDA(hn_launch(hn_se_fc1_kernel, dim3(hn_cdiv(fc.S, kFc1Units)), dim3(256), (size_t)kFc1Units * C * 4, reinterpret_cast<cudaStream_t>(stream),
+            reinterpret_cast<const bf16*>(d->mean), (int)d->x.N, C, fc, hidden));
+        HN_CHECK_CUDA(hn_launch(hn_se_fc2_kernel, dim3(hn_cdiv(C, kFc2Chans)), dim3(256), (size_t)kFc2Chans * (fc.S + 1) * 4, reinterpret_cast<cudaStream_t>(stream),
+            reinterpret_cast<const bf16*>(hidden), (int)d->x.N, C, fc));
+        HN_CHECK_CUDA(cudaGetLastError());
+        return HN_OK;
     }
     HN_CHECK_CUDA(hn_launch(hn_se_pool_kernel, dim3(grid), dim3(kSeThreads), (size_t)(smem), reinterpret_cast<cudaStream_t>(stream),
         to_view(d->x), d->partial, d->counter, reinterpret_cast<bf16*>(d->mean), 1.0f / (float)HW, d->pix_per_block, fc));

@@ -159,11 +159,27 @@ __device__ __forceinline__ void red_sum_chunks(const RedGeom& g, const float* pa
     int cb, ce;
     if (g.uniform > 0) { cb = seg * g.chunks_per_seg; ce = cb + g.chunks_per_seg; }
     else { cb = g.chunk_start[seg]; ce = g.chunk_start[seg + 1]; }
-    s0 = s1 = 0.0;
-    for (int k = cb; k < ce; ++k) {
-        s0 += (double)partial[((size_t)k * 2) * g.C + c];
-        s1 += (double)partial[((size_t)k * 2 + 1) * g.C + c];
+    // eight independent partial chains (loads in flight), combined in a fixed order: deterministic
+    double a0[8], a1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.0;
+    int k = cb;
+    for (; k + 8 <= ce; k += 8) {
+        float v0[8], v1[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            v0[j] = partial[((size_t)(k + j) * 2) * g.C + c];
+            v1[j] = partial[((size_t)(k + j) * 2 + 1) * g.C + c];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a0[j] += (double)v0[j]; a1[j] += (double)v1[j]; }
     }
+    for (int j = 0; k < ce; ++k, ++j) {
+        a0[j] += (double)partial[((size_t)k * 2) * g.C + c];
+        a1[j] += (double)partial[((size_t)k * 2 + 1) * g.C + c];
+    }
+    s0 = ((a0[0] + a0[1]) + (a0[2] + a0[3])) + ((a0[4] + a0[5]) + (a0[6] + a0[7]));
+    s1 = ((a1[0] + a1[1]) + (a1[2] + a1[3])) + ((a1[4] + a1[5]) + (a1[6] + a1[7]));
 }
 __device__ __forceinline__ long long seg_rows(const RedGeom& g, int seg) {
     if (g.uniform > 0) return g.uniform;
@@ -265,7 +281,7 @@ static inline int ew_grid(long long total_vec) {
     long long cap = 148LL * 16;
     return (int)(b < 1 ? 1 : (b < cap ? b : cap));
 }
-static constexpr int kTargetChunks = 592;  // 148 SMs x 4
+static constexpr int kTargetChunks = 296;  // 148 SMs x 2: stage 1 is HBM-bound, stage 2 walks the partials per channel
 
 extern "C" int hn_bn_train_fwd(const hn_bn_desc* d, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -1077,60 +1093,91 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__global__ void __launch_bounds__(256) hn_se_fc_fwd_kernel(const hn_sefc_desc d) {
-    extern __shared__ float sm[];  // mean [C], h [S]
-    float* s_mean = sm;
-    float* s_h = sm + d.C;
-    const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int c = threadIdx.x; c < d.C; c += 256) s_mean[c] = d.mean[(size_t)n * d.C + c];
+// Both FC layers serve EVERY image per CTA (the weights are read once per CTA, not once per image): FC1 = one CTA per
+// group of 4 hidden units, FC2 = one CTA per group of 32 channels; warps take images, lanes split the reduction.
+static constexpr int kSeU = 4, kSeCh = 32;
+__global__ void __launch_bounds__(256) hn_se_fc1_train_kernel(const hn_sefc_desc d) {
+    extern __shared__ float sm[];  // [kSeU][C]
+    const int s0 = blockIdx.x * kSeU;
+    for (int i = threadIdx.x; i < kSeU * d.C; i += 256) {
+        const int u = i / d.C, c = i - u * d.C;
+        sm[i] = s0 + u < d.S ? d.w1[(size_t)(s0 + u) * d.C + c] : 0.0f;
+    }
     __syncthreads();
-    for (int s = warp; s < d.S; s += 8) {
-        const float* w = d.w1 + (size_t)s * d.C;
-        float a = 0.0f;
-        for (int c = lane; c < d.C; c += 32) a = fmaf(w[c], s_mean[c], a);
-        a = warp_sum(a);
-        if (lane == 0) {
-            const float h = fmaxf(a + d.b1[s], 0.0f);
-            s_h[s] = h;
-            d.h[(size_t)n * d.S + s] = h;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int n = warp; n < d.N; n += 8) {
+        float acc[kSeU];
+#pragma unroll
+        for (int u = 0; u < kSeU; ++u) acc[u] = 0.0f;
+        for (int c = lane; c < d.C; c += 32) {
+            const float m = d.mean[(size_t)n * d.C + c];
+#pragma unroll
+            for (int u = 0; u < kSeU; ++u) acc[u] = fmaf(sm[u * d.C + c], m, acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kSeU; ++u) {
+            const float a = warp_sum(acc[u]);
+            if (lane == 0 && s0 + u < d.S) d.h[(size_t)n * d.S + s0 + u] = fmaxf(a + d.b1[s0 + u], 0.0f);
         }
     }
+}
+__global__ void __launch_bounds__(256) hn_se_fc2_train_kernel(const hn_sefc_desc d) {
+    extern __shared__ float sm[];  // [kSeCh][S + 1]
+    const int c0 = blockIdx.x * kSeCh, ld = d.S + 1;
+    for (int i = threadIdx.x; i < kSeCh * d.S; i += 256) {
+        const int u = i / d.S, s = i - u * d.S;
+        sm[u * ld + s] = c0 + u < d.C ? d.w2[(size_t)(c0 + u) * d.S + s] : 0.0f;
+    }
     __syncthreads();
-    for (int c = warp; c < d.C; c += 8) {
-        const float* w = d.w2 + (size_t)c * d.S;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c = c0 + lane;
+    for (int n = warp; n < d.N; n += 8) {
+        const float* h = d.h + (size_t)n * d.S;
         float a = 0.0f;
-        for (int s = lane; s < d.S; s += 32) a = fmaf(w[s], s_h[s], a);
-        a = warp_sum(a);
-        if (lane == 0) d.gate[(size_t)n * d.C + c] = 1.0f / (1.0f + expf(-(a + d.b2[c])));
+        for (int s = 0; s < d.S; ++s) a = fmaf(sm[lane * ld + s], h[s], a);
+        if (c < d.C) d.gate[(size_t)n * d.C + c] = 1.0f / (1.0f + expf(-(a + d.b2[c])));
     }
 }
-// per image: ds2 = dgate * gate * (1 - gate); dh = (h > 0) * W2^T ds2; dmean = W1^T dh.  tmp[n] = [ds2 (C) | dh (S)]
-__global__ void __launch_bounds__(256) hn_se_fc_bwd_kernel(const hn_sefc_desc d) {
-    extern __shared__ float sm[];  // ds2 [C], dh [S]
-    float* s_ds2 = sm;
-    float* s_dh = sm + d.C;
-    const int n = blockIdx.x;
-    float* tmp = d.tmp + (size_t)n * (d.C + d.S);
-    for (int c = threadIdx.x; c < d.C; c += 256) {
-        const float g = d.gate[(size_t)n * d.C + c];
-        const float v = d.dgate[(size_t)n * d.C + c] * g * (1.0f - g);
-        s_ds2[c] = v;
-        tmp[c] = v;
+// backward: ds2 = dgate * gate * (1 - gate) (tmp[n][0:C]); dh = (h > 0) * W2^T ds2 (tmp[n][C:C+S]); dmean = W1^T dh
+__global__ void __launch_bounds__(256) hn_se_ds2_kernel(const hn_sefc_desc d) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= d.N * d.C) return;
+    const int n = i / d.C, c = i - n * d.C;
+    const float g = d.gate[i];
+    d.tmp[(size_t)n * (d.C + d.S) + c] = d.dgate[i] * g * (1.0f - g);
+}
+__global__ void __launch_bounds__(256) hn_se_dh_kernel(const hn_sefc_desc d) {
+    extern __shared__ float sm[];  // [kSeU][C]: columns s0 .. s0+3 of W2
+    const int s0 = blockIdx.x * kSeU, T = d.C + d.S;
+    for (int i = threadIdx.x; i < kSeU * d.C; i += 256) {
+        const int c = i / kSeU, u = i - c * kSeU;
+        sm[u * d.C + c] = s0 + u < d.S ? d.w2[(size_t)c * d.S + s0 + u] : 0.0f;
     }
     __syncthreads();
-    for (int s = threadIdx.x; s < d.S; s += 256) {
-        float a = 0.0f;
-        for (int c = 0; c < d.C; ++c) a = fmaf(d.w2[(size_t)c * d.S + s], s_ds2[c], a);
-        a = d.h[(size_t)n * d.S + s] > 0.0f ? a : 0.0f;
-        s_dh[s] = a;
-        tmp[d.C + s] = a;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int n = warp; n < d.N; n += 8) {
+        float acc[kSeU];
+#pragma unroll
+        for (int u = 0; u < kSeU; ++u) acc[u] = 0.0f;
+        for (int c = lane; c < d.C; c += 32) {
+            const float v = d.tmp[(size_t)n * T + c];
+#pragma unroll
+            for (int u = 0; u < kSeU; ++u) acc[u] = fmaf(sm[u * d.C + c], v, acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kSeU; ++u) {
+            const float a = warp_sum(acc[u]);
+            if (lane == 0 && s0 + u < d.S) d.tmp[(size_t)n * T + d.C + s0 + u] = d.h[(size_t)n * d.S + s0 + u] > 0.0f ? a : 0.0f;
+        }
     }
-    __syncthreads();
-    for (int c = threadIdx.x; c < d.C; c += 256) {
-        float a = 0.0f;
-        for (int s = 0; s < d.S; ++s) a = fmaf(d.w1[(size_t)s * d.C + c], s_dh[s], a);
-        d.dmean[(size_t)n * d.C + c] = a;
-    }
+}
+__global__ void __launch_bounds__(256) hn_se_dmean_kernel(const hn_sefc_desc d) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= d.N * d.C) return;
+    const int n = i / d.C, c = i - n * d.C;
+    const float* dh = d.tmp + (size_t)n * (d.C + d.S) + d.C;
+    float a = 0.0f;
+    for (int s = 0; s < d.S; ++s) a = fmaf(d.w1[(size_t)s * d.C + c], dh[s], a);
+    d.dmean[i] = a;
 }
 // parameter gradients: sums over the batch, one thread per element
 __global__ void hn_se_fc_wgrad_kernel(const hn_sefc_desc d) {
@@ -1164,7 +1211,10 @@ extern "C" int hn_se_fc_fwd(const hn_sefc_desc* d, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     HN_REQUIRE(d && d->mean && d->w1 && d->b1 && d->w2 && d->b2 && d->h && d->gate, "se fc: null pointer");
     HN_REQUIRE(d->N >= 1 && d->C >= 1 && d->S >= 1 && (size_t)(d->C + d->S) * 4 <= 48 * 1024, "se fc: bad sizes N=%d C=%d S=%d", d->N, d->C, d->S);
-    hn_se_fc_fwd_kernel<<<d->N, 256, (size_t)(d->C + d->S) * 4, stream>>>(*d);
+    HN_REQUIRE((size_t)kSeU * d->C * 4 <= 48 * 1024 && (size_t)kSeCh * (d->S + 1) * 4 <= 48 * 1024, "se fc: layer too wide");
+    hn_se_fc1_train_kernel<<<hn_cdiv(d->S, kSeU), 256, (size_t)kSeU * d->C * 4, stream>>>(*d);
+    HN_CHECK_CUDA(cudaGetLastError());
+    hn_se_fc2_train_kernel<<<hn_cdiv(d->C, kSeCh), 256, (size_t)kSeCh * (d->S + 1) * 4, stream>>>(*d);
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }
@@ -1173,7 +1223,12 @@ extern "C" int hn_se_fc_bwd(const hn_sefc_desc* d, void* stream_) {
     HN_REQUIRE(d && d->mean && d->w1 && d->w2 && d->h && d->gate && d->dgate && d->dmean && d->dw1 && d->db1 && d->dw2 && d->db2 && d->tmp,
                "se fc bwd: null pointer");
     HN_REQUIRE(d->N >= 1 && d->C >= 1 && d->S >= 1 && (size_t)(d->C + d->S) * 4 <= 48 * 1024, "se fc bwd: bad sizes");
-    hn_se_fc_bwd_kernel<<<d->N, 256, (size_t)(d->C + d->S) * 4, stream>>>(*d);
+    HN_REQUIRE((size_t)kSeU * d->C * 4 <= 48 * 1024, "se fc bwd: layer too wide");
+    hn_se_ds2_kernel<<<hn_cdiv((long)d->N * d->C, 256), 256, 0, stream>>>(*d);
+    HN_CHECK_CUDA(cudaGetLastError());
+    hn_se_dh_kernel<<<hn_cdiv(d->S, kSeU), 256, (size_t)kSeU * d->C * 4, stream>>>(*d);
+    HN_CHECK_CUDA(cudaGetLastError());
+    hn_se_dmean_kernel<<<hn_cdiv((long)d->N * d->C, 256), 256, 0, stream>>>(*d);
     HN_CHECK_CUDA(cudaGetLastError());
     const long long total = 2LL * d->C * d->S + d->C + d->S;
     hn_se_fc_wgrad_kernel<<<hn_cdiv(total, 256), 256, 0, stream>>>(*d);
@@ -1222,7 +1277,13 @@ extern "C" int hn_pack_weights(const hn_pack_entry* entries_device, int32_t n, i
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) hn_adam_kernel(const hn_adam_tensor* __restrict__ tensors, const int32_t* __restrict__ chunk_tensor,
                                                       const int32_t* __restrict__ chunk_index, int chunk_elems, float lr, float beta1, float beta2,
-                                                      float eps, float wd, float bc1, float bc2_sqrt, float grad_scale) {
+                                                      float eps, float wd, float bc1, float bc2_sqrt, float grad_scale, const float* __restrict__ dyn) {
+    if (dyn) {  // hyper-parameters on the device: {lr, steps taken so far}
+        lr = dyn[0];
+        const float t = dyn[1] + 1.0f;
+        bc1 = 1.0f - powf(beta1, t);
+        bc2_sqrt = sqrtf(1.0f - powf(beta2, t));
+    }
     const hn_adam_tensor t = tensors[chunk_tensor[blockIdx.x]];
     const long long b = (long long)chunk_index[blockIdx.x] * chunk_elems;
     const long long e = min(b + chunk_elems, (long long)t.n);
@@ -1239,14 +1300,20 @@ __global__ void __launch_bounds__(256) hn_adam_kernel(const hn_adam_tensor* __re
         t.p[i] = p - step_size * (m / denom);
     }
 }
+__global__ void hn_adam_advance_kernel(float* dyn) { dyn[1] += 1.0f; }
 extern "C" int hn_adam_step(const hn_adam_tensor* tensors_device, const int32_t* chunk_tensor_device, const int32_t* chunk_index_device,
                             int32_t n_chunks, int32_t chunk_elems, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
-                            float grad_scale, void* stream_) {
+                            float grad_scale, float* dyn_device, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    HN_REQUIRE(tensors_device && chunk_tensor_device && chunk_index_device && n_chunks >= 1 && chunk_elems >= 256 && step >= 1, "adam: bad arguments");
-    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    HN_REQUIRE(tensors_device && chunk_tensor_device && chunk_index_device && n_chunks >= 1 && chunk_elems >= 256 && (step >= 1 || dyn_device),
+               "adam: bad arguments");
+    const double bc1 = 1.0 - pow((double)beta1, (double)(step > 0 ? step : 1)), bc2 = 1.0 - pow((double)beta2, (double)(step > 0 ? step : 1));
     hn_adam_kernel<<<n_chunks, 256, 0, stream>>>(tensors_device, chunk_tensor_device, chunk_index_device, chunk_elems, lr, beta1, beta2, eps, weight_decay,
-                                                 (float)bc1, (float)sqrt(bc2), grad_scale);
+                                                 (float)bc1, (float)sqrt(bc2), grad_scale, dyn_device);
     HN_CHECK_CUDA(cudaGetLastError());
+    if (dyn_device) {
+        hn_adam_advance_kernel<<<1, 1, 0, stream>>>(dyn_device);
+        HN_CHECK_CUDA(cudaGetLastError());
+    }
     return HN_OK;
 }

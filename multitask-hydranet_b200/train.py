@@ -1022,3 +1022,142 @@ def train_forward(model, x, mode="train"):
         return out
     seg_cls = torch.argmax(out["seg"], dim=1) if model.train_seg else None
     return seg_cls, anchors, regression, classification, lane_cls, lane_reg
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# the step as a callable, optionally replayed as ONE CUDA graph
+# --------------------------------------------------------------------------------------------------------------------
+def weighted_total(cfgs, loss_dict):
+    """train.py:192-203: the yml's loss weights."""
+    t = 0.0
+    if "loss_seg" in loss_dict:
+        t = t + loss_dict["loss_seg"] * cfgs["segment"].get("segment_weight", 1.0)
+    if "loss_det_cls" in loss_dict:
+        d = cfgs["detection"]
+        t = t + (loss_dict["loss_det_cls"] * d.get("loss_cls_weight", 1.0) + loss_dict["loss_det_reg"] * d.get("loss_reg_weight", 1.0)) * d.get("detection_weight", 1.0)
+    if "loss_lane_cls_pos" in loss_dict:
+        l = cfgs["lane"]
+        t = t + (loss_dict["loss_lane_cls_pos"] * l.get("loss_cls_pos_weight", 1.0) + loss_dict["loss_lane_cls_neg"] * l.get("loss_cls_neg_weight", 1.0)
+                 + loss_dict["loss_lane_loc"] * l.get("loss_loc_weight", 1.0)) * l.get("lane_weight", 1.0)
+    return t
+
+
+class TrainStep:
+    """One iteration of the reference's training loop (train.py:246-267) as a callable::
+
+        step = TrainStep(hydranet, optimizer)          # optimizer: FusedAdam or any torch.optim.Optimizer
+        loss = step(inputs, batch)                      # forward -> cal_loss -> weighted total -> zero_grad -> backward -> (all-reduce) -> step
+
+    ``graph=True`` captures forward + loss + backward (and a FusedAdam step when there is no gradient exchange) into ONE CUDA
+    graph on the first call and replays it afterwards: the step launches ~5 000 small kernels, which the Python / launch path
+    cannot feed as fast as the GPU retires them.  Inputs are copied into static buffers; the loss losses are sync-free (losses.py),
+    so nothing in the step waits for the host.  With several ranks (``torch.distributed`` initialised) the gradients are
+    averaged after the graph by one coalesced NCCL all-reduce over all gradient tensors, in place.  In eager mode
+    (``graph=False``) pass a ``GradAllReduce`` as ``reducer`` to overlap the bucketed exchange with backward instead.
+    """
+
+    def __init__(self, model, optimizer, graph=True, reducer=None, warmup=2, process_group=None):
+        import torch.distributed as dist
+        self.model, self.opt, self.use_graph, self.reducer, self.warmup = model, optimizer, graph, reducer, warmup
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.graph = None
+        self.static = None
+        self.opt_in_graph = False
+        self.loss_dict = None
+
+    def _fwd_bwd(self, x, gt):
+        out = self.model(x)
+        ld = self.model.cal_loss(out, gt)
+        loss = weighted_total(self.model.cfgs, ld)
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        return loss, ld
+
+    def _exchange(self):
+        if self.world <= 1:
+            return
+        import torch.distributed as dist
+        grads = [p.grad for p in self.model.parameters() if p.grad is not None]
+        if grads[0].is_cuda:
+            with dist._coalescing_manager(group=self.group, device=grads[0].device, async_ops=False):
+                for g in grads:
+                    dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            for g in grads:
+                dist.all_reduce(g, group=self.group)
+                g.div_(self.world)
+
+    def _eager(self, x, gt):
+        loss, ld = self._fwd_bwd(x, gt)
+        if self.reducer is not None:
+            self.reducer.finish()
+        else:
+            self._exchange()
+        self.opt.step()
+        self.loss_dict = ld
+        return loss.detach()
+
+    def _capture(self, x, gt):
+        from .optim import FusedAdam
+        dev = x.device
+        self.static = (torch.empty_like(x), {k: torch.empty_like(v) for k, v in gt.items()})
+        self.static[0].copy_(x)
+        for k, v in gt.items():
+            self.static[1][k].copy_(v)
+        # the warm-up iterations and the capture must not change the training trajectory: snapshot parameters, buffers and
+        # optimizer state, restore them (in place: the graph holds their addresses) afterwards
+        named = list(self.model.parameters()) + list(self.model.buffers())
+        saved = [t.detach().clone() for t in named]
+        pre = {}
+        for st in self.opt.state.values():
+            for k, v in st.items():
+                pre[(id(st), k)] = v.detach().clone() if torch.is_tensor(v) else v
+        pre_dyn = {gi: t["dyn"].clone() for gi, t in getattr(self.opt, "_tables", {}).items()}
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, self.warmup)):
+                self._fwd_bwd(*self.static)
+                self.opt.step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.opt_in_graph = isinstance(self.opt, FusedAdam) and self.world <= 1
+        self.opt.zero_grad(set_to_none=True)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            loss, ld = self._fwd_bwd(*self.static)
+            if self.opt_in_graph:
+                self.opt.step()
+        self.graph, self.static_loss, self.loss_dict = g, loss.detach(), {k: v.detach() for k, v in ld.items()}
+        with torch.no_grad():
+            for t, s in zip(named, saved):
+                t.copy_(s)
+            for st in self.opt.state.values():  # optimizer state back to its pre-warm-up values (zeros / step 0 if it was fresh)
+                for k, v in list(st.items()):
+                    old = pre.get((id(st), k))
+                    if torch.is_tensor(v):
+                        v.copy_(old) if old is not None else v.zero_()
+                    elif k == "step":
+                        st[k] = old if old is not None else 0
+            for gi, t in getattr(self.opt, "_tables", {}).items():
+                t["dyn"][1:2].copy_(pre_dyn[gi][1:2]) if gi in pre_dyn else t["dyn"][1:2].zero_()
+
+    def __call__(self, x, gt):
+        if not self.use_graph:
+            return self._eager(x, gt)
+        if self.graph is None:
+            self._capture(x, gt)
+        self.static[0].copy_(x, non_blocking=True)
+        for k, v in gt.items():
+            self.static[1][k].copy_(v, non_blocking=True)
+        if hasattr(self.opt, "sync_hyper"):
+            self.opt.sync_hyper()
+        self.graph.replay()
+        if not self.opt_in_graph:
+            self._exchange()
+            self.opt.step()
+        else:
+            for st in self.opt.state.values():
+                if "step" in st and not torch.is_tensor(st["step"]):
+                    st["step"] += 1
+        return self.static_loss

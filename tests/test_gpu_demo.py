@@ -92,8 +92,13 @@ def test_demo_loop_body_random_init():
 def test_demo_loop_body_with_lanes_and_boxes():
     """Synthetic weights and a lane threshold low enough that lanes exist whatever the logits: visual() and display() both draw."""
     cfgs, hydranet, coder, frame = _setup(True)
+    with torch.no_grad():  # make the lane head confident and its lanes long: foreground logit up, both end positions at 40 points
+        hydranet.laneheader.conv_cls_conv[3].bias[1] += 8.0
+        hydranet.laneheader.conv_up_conv[3].bias[80] = 40.0
+        hydranet.laneheader.conv_down_conv[3].bias[80] = 40.0
+    hydranet.refresh()  # parameters edited in place in eval mode
     with torch.no_grad():
-        imgs, lanes, preds, _ = _demo_body(hydranet, frame.copy(), cfgs, coder, lane_conf=0.02)
+        imgs, lanes, preds, _ = _demo_body(hydranet, frame.copy(), cfgs, coder, lane_conf=0.5)
     assert len(lanes[0]) >= 1 and all(set(l) == {"score", "points"} for l in lanes[0])
     assert imgs[0].shape == frame.shape
     os.makedirs(os.path.join(os.path.dirname(GOLD), "..", "gpurun_out"), exist_ok=True)

@@ -124,9 +124,22 @@ def test_regnet_stage_forward_backward_vs_oracle():
         return t
     yr = _train_oracle(ref)
     yr.backward(g.float().permute(0, 3, 1, 2))
-    assert _rel(y.permute(0, 3, 1, 2), yr) <= 2e-2
-    assert _rel(xb.grad.permute(0, 3, 1, 2), xf.grad) <= 4e-2
-    _compare_param_grads(m, sd, "backbone.net.stage_2.", 6e-2)
+    # the same sub-network with PyTorch rounding every conv / BN output to bf16: the floor for this depth
+    sd_fp32 = sd
+    sd = _leaves({k: v.detach() for k, v in m.state_dict().items()})
+    xe = xb.detach().float().permute(0, 3, 1, 2).requires_grad_()
+    xf_saved, xf = xf, xe
+    with _Bf16Forward():
+        ye = _train_oracle(ref)
+    ye.backward(g.float().permute(0, 3, 1, 2))
+    sd_emu, sd, xf = sd, sd_fp32, xf_saved
+    floor_y, floor_dx = _rel(ye, yr), _rel(xe.grad, xf.grad)
+    assert _rel(y.permute(0, 3, 1, 2), yr) <= 1.5 * floor_y + 1e-2, (_rel(y.permute(0, 3, 1, 2), yr), floor_y)
+    assert _rel(xb.grad.permute(0, 3, 1, 2), xf.grad) <= 1.5 * floor_dx + 3e-2, (_rel(xb.grad.permute(0, 3, 1, 2), xf.grad), floor_dx)
+    named = dict(m.named_parameters())
+    nat = [_rel(named[k].grad, sd[k].grad) for k in named if k.startswith("backbone.net.stage_2.") and "conv_block" in k and k.endswith(".0.weight")]
+    emu = [_rel(sd_emu[k].grad, sd[k].grad) for k in named if k.startswith("backbone.net.stage_2.") and "conv_block" in k and k.endswith(".0.weight")]
+    assert float(np.median(nat)) <= 1.5 * float(np.median(emu)) + 3e-2, (nat, emu)
 
 
 def test_bifpn_cell_and_heads_forward_backward_vs_oracle():
@@ -151,27 +164,40 @@ def test_bifpn_cell_and_heads_forward_backward_vs_oracle():
     torch.manual_seed(5)
     gs = [torch.randn_like(o) / o.numel() ** 0.5 for o in outs]
     torch.autograd.backward(outs, gs)
-    feats_r = [t.detach().float().permute(0, 3, 1, 2).requires_grad_() for t in feats_b]
+    def run_ref(sd_, emulate):
+        feats_ = [t.detach().float().permute(0, 3, 1, 2).requires_grad_() for t in feats_b]
 
-    def ref():
-        fused = hydranet_ref.neck(sd, feats_r)
-        s = hydranet_ref.seg_head(sd, [feats_r[0], fused[0], fused[1], fused[2]])
-        r = hydranet_ref._tower(sd, "detectheader.regressor", fused, 3, 4)
-        c = hydranet_ref._tower(sd, "detectheader.classifier", fused, 3, 9).sigmoid()
-        lc, ll = hydranet_ref.lane_head(sd, fused, 32, 2, 2 * (256 // 8 + 1))
-        return [s, r, c, lc, ll]
-    outs_r = _train_oracle(ref)
-    torch.autograd.backward(outs_r, gs)
-    for name, a, b in zip(("seg", "regression", "classification", "predict_cls", "predict_loc"), outs, outs_r):
+        def ref():
+            fused = hydranet_ref.neck(sd_, feats_)
+            s = hydranet_ref.seg_head(sd_, [feats_[0], fused[0], fused[1], fused[2]])
+            r = hydranet_ref._tower(sd_, "detectheader.regressor", fused, 3, 4)
+            c = hydranet_ref._tower(sd_, "detectheader.classifier", fused, 3, 9).sigmoid()
+            lc, ll = hydranet_ref.lane_head(sd_, fused, 32, 2, 2 * (256 // 8 + 1))
+            return [s, r, c, lc, ll]
+        if emulate:
+            with _Bf16Forward():
+                o = _train_oracle(ref)
+        else:
+            o = _train_oracle(ref)
+        torch.autograd.backward(o, gs)
+        return o, feats_
+
+    outs_r, feats_r = run_ref(sd, False)
+    sd_emu = _leaves({k: v.detach() for k, v in m.state_dict().items()})
+    outs_e, feats_e = run_ref(sd_emu, True)
+    # every quantity: error against fp32 bounded by the error of the bf16-rounding PyTorch emulation of the same sub-network
+    for name, a, b, e in zip(("seg", "regression", "classification", "predict_cls", "predict_loc"), outs, outs_r, outs_e):
         assert tuple(a.shape) == tuple(b.shape), name
-        assert _rel(a, b) <= 3e-2, (name, _rel(a, b))
-    for i, (a, b) in enumerate(zip(feats_b, feats_r)):
-        if i == 1:
-            assert a.grad is None and b.grad is None  # feats[1] (stage 1) feeds nothing with five backbone maps
-            continue
-        assert _rel(a.grad.permute(0, 3, 1, 2), b.grad) <= 8e-2, (i, _rel(a.grad.permute(0, 3, 1, 2), b.grad))
+        assert _rel(a, b) <= 1.5 * _rel(e, b) + 1e-2, (name, _rel(a, b), _rel(e, b))
+    for i, (a, b, e) in enumerate(zip(feats_b, feats_r, feats_e)):
+        ra, re_ = _rel(a.grad.permute(0, 3, 1, 2), b.grad), _rel(e.grad, b.grad)
+        assert ra <= 1.5 * re_ + 3e-2, (i, ra, re_)
+    named = dict(m.named_parameters())
     for prefix in ("neck.", "segheader.", "detectheader.", "laneheader."):
-        _compare_param_grads(m, sd, prefix, 8e-2, floor=2e-2)
+        ks = [k for k in named if k.startswith(prefix) and named[k].grad is not None and sd[k].grad is not None and k.endswith("weight") and named[k].dim() == 4]
+        nat = float(np.median([_rel(named[k].grad, sd[k].grad) for k in ks]))
+        emu = float(np.median([_rel(sd_emu[k].grad, sd[k].grad) for k in ks]))
+        assert nat <= 1.5 * emu + 3e-2, (prefix, nat, emu)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -224,7 +250,8 @@ def test_whole_step_error_is_at_the_bf16_floor(H, W, B):
         for gk in sorted(nat):
             a, b = float(np.median(nat[gk])), float(np.median(emu[gk]))
             f.write("%-44s %5d %12.4f %12.4f\n" % (gk, len(nat[gk]), a, b))
-            if a > 1.3 * b + 0.03:
+            # b >= 0.5: the PyTorch emulation itself is decorrelated from fp32 there (chaotic regime) -- nothing to compare
+            if b < 0.5 and a > 1.3 * b + 0.03:
                 bad.append((gk, a, b))
     assert not bad, bad
     # BatchNorm bookkeeping
