@@ -478,7 +478,7 @@ int hn_adam_step(const hn_adam_tensor* tensors_device, const int32_t* chunk_tens
 
 /* diagnostics: when set (before a conv is prepared), every conv CTA stores 16 int64 globaltimer stamps */
 void hn_conv_set_debug_buffer(void* device_i64);
-void hn_se_set_split_fc(int on); /* tuning knob: squeeze-excite FC layers as two batched launches after the pooling (default on) or fused into the pooling kernel's tail */
+void hn_se_set_split_fc(int on); /* tuning knob: squeeze-excite FC layers as two batched launches after the pooling, or (default: measured faster) fused into the pooling kernel's tail */
 int hn_se_pool_num_launches(const hn_se_pool_desc* d);
 void hn_conv_set_cluster(int ctas); /* tuning knob: CTAs per cluster sharing a weight tile (0 = default, 1 = off) */
 void hn_conv_set_pair_min_bn(int bn); /* tuning knob: narrowest N tile run on CTA pairs (default 192) */

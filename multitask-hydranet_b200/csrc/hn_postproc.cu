@@ -185,7 +185,7 @@ static GridGeom make_grid(int img_h, int img_w, float iou_thr) {
 static size_t det_cub_bytes(long long n) {
     size_t bytes = 0;
     cub::DoubleBuffer<uint64_t> db(nullptr, nullptr);
-    cub::DeviceRadixSort::SortKeys(nullptr, bytes, db, (int)n, 0, 64, (cudaStream_t)0);
+    cub::DeviceRadixSort::SortKeys(nullptr, bytes, db, (int)n, kScoreShift, 64, (cudaStream_t)0);
     return bytes;
 }
 
@@ -916,7 +916,9 @@ extern "C" int hn_det_decode_nms(const hn_det_desc* d, void* stream) {
     HN_CHECK_CUDA(cudaGetLastError());
     cub::DoubleBuffer<uint64_t> db(ws.keys, ws.keys_alt);
     size_t tmp = ws.cub_bytes;
-    HN_CHECK_CUDA(cub::DeviceRadixSort::SortKeys(ws.cub_tmp, tmp, db, (int)NA, 0, 64, s));
+    // bits [0, 20) hold the anchor index: candidates are generated in anchor order and the radix sort is stable, so ties on
+    // (image, class, score) already come out anchor-ascending -- 44 key bits = 6 passes instead of 8
+    HN_CHECK_CUDA(cub::DeviceRadixSort::SortKeys(ws.cub_tmp, tmp, db, (int)NA, kScoreShift, 64, s));
     ws.keys = db.Current();
     ws.keys_alt = db.Alternate();
     hn_det_segments_kernel<<<hn_cdiv(NA, 256), 256, 0, s>>>(ws.keys, NA, ws.seg_start, ws.seg_end);

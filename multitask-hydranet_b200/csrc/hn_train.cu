@@ -155,32 +155,43 @@ __global__ void __launch_bounds__(256) hn_red1_kernel(const RedGeom g, const F f
     }
 }
 
-__device__ __forceinline__ void red_sum_chunks(const RedGeom& g, const float* partial, int seg, int c, double& s0, double& s1) {
+// Stage 2, cooperative: a CTA of (32 channels) x (8 chunk slices); slice y adds the chunks cb+y, cb+y+8, ... with four loads
+// in flight, the eight slice sums are combined in slice order through shared memory: deterministic, and the walk over a
+// segment's chunks is 8 x 4 wide instead of one dependent chain per channel.  Every thread of the CTA must call it.
+static constexpr int kFinX = 32, kFinY = 8;
+__device__ __forceinline__ void red_sum_chunks(const RedGeom& g, const float* __restrict__ partial, int seg, int c, bool valid, double& s0, double& s1) {
+    __shared__ double sh[2][kFinY][kFinX];
     int cb, ce;
     if (g.uniform > 0) { cb = seg * g.chunks_per_seg; ce = cb + g.chunks_per_seg; }
     else { cb = g.chunk_start[seg]; ce = g.chunk_start[seg + 1]; }
-    // eight independent partial chains (loads in flight), combined in a fixed order: deterministic
-    double a0[8], a1[8];
+    double a0 = 0.0, a1 = 0.0;
+    if (valid) {
+        int k = cb + threadIdx.y;
+        for (; k + 3 * kFinY < ce; k += 4 * kFinY) {
+            float v0[4], v1[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.0;
-    int k = cb;
-    for (; k + 8 <= ce; k += 8) {
-        float v0[8], v1[8];
+            for (int j = 0; j < 4; ++j) {
+                v0[j] = partial[((size_t)(k + j * kFinY) * 2) * g.C + c];
+                v1[j] = partial[((size_t)(k + j * kFinY) * 2 + 1) * g.C + c];
+            }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            v0[j] = partial[((size_t)(k + j) * 2) * g.C + c];
-            v1[j] = partial[((size_t)(k + j) * 2 + 1) * g.C + c];
+            for (int j = 0; j < 4; ++j) { a0 += (double)v0[j]; a1 += (double)v1[j]; }
         }
+        for (; k < ce; k += kFinY) {
+            a0 += (double)partial[((size_t)k * 2) * g.C + c];
+            a1 += (double)partial[((size_t)k * 2 + 1) * g.C + c];
+        }
+    }
+    sh[0][threadIdx.y][threadIdx.x] = a0;
+    sh[1][threadIdx.y][threadIdx.x] = a1;
+    __syncthreads();
+    s0 = s1 = 0.0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { a0[j] += (double)v0[j]; a1[j] += (double)v1[j]; }
-    }
-    for (int j = 0; k < ce; ++k, ++j) {
-        a0[j] += (double)partial[((size_t)k * 2) * g.C + c];
-        a1[j] += (double)partial[((size_t)k * 2 + 1) * g.C + c];
-    }
-    s0 = ((a0[0] + a0[1]) + (a0[2] + a0[3])) + ((a0[4] + a0[5]) + (a0[6] + a0[7]));
-    s1 = ((a1[0] + a1[1]) + (a1[2] + a1[3])) + ((a1[4] + a1[5]) + (a1[6] + a1[7]));
+    for (int y = 0; y < kFinY; ++y) { s0 += sh[0][y][threadIdx.x]; s1 += sh[1][y][threadIdx.x]; }
 }
+// finalize launch geometry: grid (ceil(C / 32), n_seg), block (32, 8); thread (x, 0) writes channel blockIdx.x * 32 + x
+static inline dim3 fin_grid(const RedGeom& g) { return dim3((unsigned)((g.C + kFinX - 1) / kFinX), (unsigned)g.n_seg); }
+static inline dim3 fin_block() { return dim3(kFinX, kFinY); }
 __device__ __forceinline__ long long seg_rows(const RedGeom& g, int seg) {
     if (g.uniform > 0) return g.uniform;
     return g.seg_end[seg] - (seg > 0 ? g.seg_end[seg - 1] : 0);
@@ -211,11 +222,10 @@ struct StatsF {
 // stats layout: [seg][4][C] = mean, invstd, scale (gamma * invstd), shift (beta - mean * scale)
 __global__ void hn_bn_finalize_kernel(const RedGeom g, const float* __restrict__ partial, BnPtrs bp, float eps, float momentum,
                                       float* __restrict__ stats) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= g.n_seg * g.C) return;
-    const int seg = i / g.C, c = i - seg * g.C;
+    const int seg = blockIdx.y, c = blockIdx.x * kFinX + threadIdx.x;
     double s0, s1;
-    red_sum_chunks(g, partial, seg, c, s0, s1);
+    red_sum_chunks(g, partial, seg, c, c < g.C, s0, s1);
+    if (c >= g.C || threadIdx.y != 0) return;
     const double n = (double)seg_rows(g, seg);
     const double mean = s0 / n;
     double var = s1 / n - mean * mean;
@@ -303,7 +313,7 @@ extern "C" int hn_bn_train_fwd(const hn_bn_desc* d, void* stream_) {
     StatsF f{to_mat(d->z)};
     hn_red1_kernel<StatsF><<<g.n_chunks, 256, 0, stream>>>(g, f, d->scratch);
     HN_CHECK_CUDA(cudaGetLastError());
-    hn_bn_finalize_kernel<<<hn_cdiv((long)g.n_seg * g.C, 128), 128, 0, stream>>>(g, d->scratch, bp, d->eps, d->momentum, d->stats);
+    hn_bn_finalize_kernel<<<fin_grid(g), fin_block(), 0, stream>>>(g, d->scratch, bp, d->eps, d->momentum, d->stats);
     HN_CHECK_CUDA(cudaGetLastError());
     Mat res{nullptr, 0, 0, 0};
     if (d->res.ptr) res = to_mat(d->res);
@@ -347,11 +357,10 @@ struct BnBwdF {
 
 // sums[seg][2][C] = (mean of dz_act, mean of dz_act * xhat); parameter gradients written
 __global__ void hn_bn_bwd_finalize_kernel(const RedGeom g, const float* __restrict__ partial, BnPtrs bp, float* __restrict__ sums) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= g.n_seg * g.C) return;
-    const int seg = i / g.C, c = i - seg * g.C;
+    const int seg = blockIdx.y, c = blockIdx.x * kFinX + threadIdx.x;
     double s0, s1;
-    red_sum_chunks(g, partial, seg, c, s0, s1);
+    red_sum_chunks(g, partial, seg, c, c < g.C, s0, s1);
+    if (c >= g.C || threadIdx.y != 0) return;
     const double n = (double)seg_rows(g, seg);
     if (bp.dbeta[seg]) bp.dbeta[seg][c] = (float)s0;
     if (bp.dgamma[seg]) bp.dgamma[seg][c] = (float)s1;
@@ -406,7 +415,7 @@ extern "C" int hn_bn_train_bwd(const hn_bn_desc* d, void* stream_) {
     float* sums = d->scratch + (size_t)g.n_chunks * 2 * g.C;
     hn_red1_kernel<BnBwdF><<<g.n_chunks, 256, 0, stream>>>(g, f, d->scratch);
     HN_CHECK_CUDA(cudaGetLastError());
-    hn_bn_bwd_finalize_kernel<<<hn_cdiv((long)g.n_seg * g.C, 128), 128, 0, stream>>>(g, d->scratch, bp, sums);
+    hn_bn_bwd_finalize_kernel<<<fin_grid(g), fin_block(), 0, stream>>>(g, d->scratch, bp, sums);
     HN_CHECK_CUDA(cudaGetLastError());
     Mat dres{nullptr, 0, 0, 0};
     if (d->dres.ptr) dres = to_mat(d->dres);
@@ -438,11 +447,11 @@ struct DotF {
     }
 };
 __global__ void hn_red2_kernel(const RedGeom g, const float* __restrict__ partial, float scale, float* __restrict__ out0, float* __restrict__ out1) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= g.n_seg * g.C) return;
-    const int seg = i / g.C, c = i - seg * g.C;
+    const int seg = blockIdx.y, c = blockIdx.x * kFinX + threadIdx.x;
     double s0, s1;
-    red_sum_chunks(g, partial, seg, c, s0, s1);
+    red_sum_chunks(g, partial, seg, c, c < g.C, s0, s1);
+    if (c >= g.C || threadIdx.y != 0) return;
+    const int i = seg * g.C + c;
     out0[i] = (float)(s0 * (double)scale);
     if (out1) out1[i] = (float)(s1 * (double)scale);
 }
@@ -470,7 +479,7 @@ extern "C" int hn_col_reduce(const hn_mat* a, const hn_mat* b, int32_t mode, int
         HN_REQUIRE(false, "col reduce: unknown mode %d", mode);
     }
     HN_CHECK_CUDA(cudaGetLastError());
-    hn_red2_kernel<<<hn_cdiv((long)g.n_seg * g.C, 128), 128, 0, stream>>>(g, scratch, scale, out0, out1);
+    hn_red2_kernel<<<fin_grid(g), fin_block(), 0, stream>>>(g, scratch, scale, out0, out1);
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }

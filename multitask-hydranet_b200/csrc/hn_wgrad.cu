@@ -24,6 +24,7 @@ struct alignas(64) WgradParams {
     int flat, TH, TW, n_img, H, W, tiles_x, tiles_y;
     int k_tiles, k_per_split, splits;
     int num_taps, nb, tap_groups, m_tiles;
+    unsigned char grp_first[HN_MAX_TAPS], grp_len[HN_MAX_TAPS], grp_merge[HN_MAX_TAPS];
     int cout, grouped, stages, tmem_cols;
     long long s_co, s_ci;
     float* dw;
@@ -59,7 +60,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) hn_conv_wgrad_kernel(const __gr
     const int tg = rest % p.tap_groups, mt = rest / p.tap_groups;
     const int kt0 = split * p.k_per_split, kt1 = min(kt0 + p.k_per_split, p.k_tiles);
     if (kt0 >= kt1) return;  // whole CTA: nothing to add
-    const int t0 = tg * p.nb, nb = min(p.nb, p.num_taps - t0);
+    const int t0 = p.grp_first[tg], nb = p.grp_len[tg];
+    const bool merged = p.grp_merge[tg] != 0;
     const int m0 = mt * 128;
 
     const int stage_bytes = (2 + p.nb) * kBoxBytes;
@@ -106,9 +108,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) hn_conv_wgrad_kernel(const __gr
                 }
                 hn_mbar_wait(&bar_empty[s], ph ^ 1);
                 uint8_t* st = sStage + s * stage_bytes;
-                hn_mbar_expect_tx(&bar_full[s], (uint32_t)((2 + nb) * kBoxBytes));
+                // the second 64-channel block of dY only if it holds real output channels: the rows of a block that is not
+                // loaded multiply whatever the slot held before -- each accumulator row depends on its own A row only, and
+                // the epilogue never reads rows >= cout
+                const bool second = m0 + 64 < p.cout;
+                hn_mbar_expect_tx(&bar_full[s], (uint32_t)((1 + (second ? 1 : 0) + nb) * kBoxBytes));
                 hn_tma_load_4d(st, &p.tmDy, &bar_full[s], m0, x0, y0, img);
-                hn_tma_load_4d(st + kBoxBytes, &p.tmDy, &bar_full[s], m0 + 64, x0, y0, img);
+                if (second) hn_tma_load_4d(st + kBoxBytes, &p.tmDy, &bar_full[s], m0 + 64, x0, y0, img);
                 for (int j = 0; j < nb; ++j) {
                     const hn_tap tp = p.taps[t0 + j];
                     const int c0 = (int)tp.c0 + (p.grouped ? m0 : 0);
@@ -119,14 +125,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) hn_conv_wgrad_kernel(const __gr
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = hn_umma_idesc_bf16_mn(128, 64);
+            const uint32_t idesc = hn_umma_idesc_bf16_mn(128, merged ? 64 * nb : 64);
             int s = 0;
             uint32_t ph = 0;
             for (int kt = kt0; kt < kt1; ++kt) {
                 hn_mbar_wait(&bar_full[s], ph);
                 hn_tc_fence_after();
                 const uint32_t a_addr = hn_smem_u32(sStage + s * stage_bytes);
-                for (int j = 0; j < nb; ++j) {
+                for (int j = 0; j < (merged ? 1 : nb); ++j) {
+                    // merged: the group's boxes are consecutive 64-channel blocks of one shifted window -> one N = 64 * nb operand
+                    // (64-channel atoms one box apart: LBO)
                     const uint32_t b_addr = a_addr + (uint32_t)((2 + j) * kBoxBytes);
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) {  // 16 pixels (K) per instruction = 16 rows of 128 bytes
@@ -265,8 +273,28 @@ extern "C" int hn_conv_wgrad(const hn_wgrad_desc* d, void* stream_) {
     p.s_ci = d->s_ci;
     p.dw = d->dw;
     p.m_tiles = hn_cdiv(d->cout, 128);
-    p.nb = d->num_taps < kMaxTapsPerItem ? d->num_taps : kMaxTapsPerItem;
-    p.tap_groups = hn_cdiv(d->num_taps, p.nb);
+    {   // tap groups: consecutive taps, at most kMaxTapsPerItem, cut where (source, shift) changes so that a group can be one operand
+        int g = 0, longest = 1;
+        for (int t = 0; t < d->num_taps;) {
+            int len = 1;
+            while (len < kMaxTapsPerItem && t + len < d->num_taps && !d->grouped) {  // run of channel-consecutive blocks of one window
+                const hn_tap &a = d->taps[t + len - 1], &b = d->taps[t + len];
+                if (a.src != b.src || a.dy != b.dy || a.dx != b.dx || b.c0 != a.c0 + 64) break;
+                ++len;
+            }
+            const bool merge = len > 1;
+            if (!merge)  // single blocks: bundle up to four arbitrary taps, they still share the dY tile of every stage
+                while (len < kMaxTapsPerItem && t + len < d->num_taps) ++len;
+            p.grp_first[g] = (unsigned char)t;
+            p.grp_len[g] = (unsigned char)len;
+            p.grp_merge[g] = merge ? 1 : 0;
+            if (len > longest) longest = len;
+            t += len;
+            ++g;
+        }
+        p.tap_groups = g;
+        p.nb = longest;
+    }
     p.tmem_cols = p.nb * 64 <= 64 ? 64 : (p.nb * 64 <= 128 ? 128 : 256);
     const int stage_bytes = (2 + p.nb) * kBoxBytes;
     int stages = (int)((200 * 1024) / stage_bytes);

@@ -97,7 +97,7 @@ def lane_cls_loss(cls_targets, cls_preds, negative_ratio=15, alpha=10):
     # k-th smallest background log-probability among the negatives (the hardest `negative_num` negatives), without a sync:
     # positives are pushed to +inf, the index is a device tensor
     ranked = torch.sort(torch.where(nmask, bg.detach(), torch.full_like(bg, float("inf")))).values
-    kth = ranked[torch.clamp(negative_num - 1, max=ranked.numel() - 1)]
+    kth = ranked.index_select(0, torch.clamp(negative_num - 1, max=ranked.numel() - 1).reshape(1)).squeeze(0)  # (ranked[tensor] would sync)
     ohem = (bg <= kth).float() * fn
     total_pos = -torch.sum(alpha * fg * fp) / positive_num
     total_neg = -torch.sum(alpha * bg * ohem) / positive_num
@@ -126,7 +126,11 @@ def cal_loss(model, pred_dict, gt_dict):
         sc = model.cfgs["segment"]
         if sc.get("use_lovasz", False):
             raise NotImplementedError("use_lovasz=True is not configured by any reference cfg (model/cfgs/*.yml)")
-        out["loss_seg"] = seg_loss(pred_dict["seg"], gt_dict["gt_seg"].to(pred_dict["seg"].device).long(), torch.tensor(sc["class_weight"]),
+        dev = pred_dict["seg"].device
+        cache = model.__dict__.setdefault("_loss_consts", {})
+        if ("seg_w", dev) not in cache:  # uploaded once: a CUDA-graph capture of the step must not see host->device copies
+            cache[("seg_w", dev)] = torch.tensor(sc["class_weight"], dtype=torch.float32, device=dev)
+        out["loss_seg"] = seg_loss(pred_dict["seg"], gt_dict["gt_seg"].to(dev).long(), cache[("seg_w", dev)],
                                    sc["use_top_k"], sc["top_k_ratio"], sc["use_focal"])
     if model.train_detect:
         det = pred_dict["detection"]

@@ -21,6 +21,7 @@ Activations and activation gradients are bf16 NHWC; parameters, their gradients 
 statistics are fp32.  Parameter gradients are returned through autograd in the parameters' own layouts.
 """
 import ctypes as C
+import os
 
 import torch
 from torch.autograd import Function
@@ -326,7 +327,17 @@ def _gemm_spatial(dev, srcs, blocks, n_out, out, tile_hw, bias=None, act=nv.ACT_
     nv.check(nv.lib.hn_conv_fwd(C.byref(d), _stream(dev)))
 
 
+_PROFILE_NAMES = bool(os.environ.get("HN_PROFILE_NAMES"))
+
+
 def _wgrad(dev, rec, dy_view, src_views, flat, tile, dw):
+    if _PROFILE_NAMES:  # tools/profile_train.py: per-layer device time of the weight-gradient kernel
+        with torch.profiler.record_function("wgrad:" + rec.name):
+            return _wgrad_launch(dev, rec, dy_view, src_views, flat, tile, dw)
+    return _wgrad_launch(dev, rec, dy_view, src_views, flat, tile, dw)
+
+
+def _wgrad_launch(dev, rec, dy_view, src_views, flat, tile, dw):
     d = nv.WgradDesc()
     d.dy = dy_view
     for i, v in enumerate(src_views):

@@ -3,6 +3,8 @@ import argparse
 import os
 import sys
 
+os.environ.setdefault("HN_PROFILE_NAMES", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
@@ -53,6 +55,10 @@ def main():
         f.write("training step, batch %d: %.2f ms of device time per step in %d launches\n" % (B, tot, sum(r[1] for r in rows)))
         for ms, n, k in rows[:60]:
             f.write("%9.3f ms %6d x  %s\n" % (ms, n, k[:110]))
+        f.write("\nweight-gradient kernel per layer (device time of the launches under each record_function range)\n")
+        wg = sorted(((e.device_time_total / 2e3, e.key) for e in prof.key_averages() if e.key.startswith("wgrad:")), key=lambda r: -r[0])
+        for ms, k in wg[:40]:
+            f.write("%9.3f ms  %s\n" % (ms, k))
     print(open(args.out).read())
 
 
