@@ -256,6 +256,7 @@ int hn_plan_create(hn_plan** out);
 int hn_plan_destroy(hn_plan* p);
 int hn_plan_add_conv(hn_plan* p, const hn_conv_desc* d);
 int hn_plan_set_branch(hn_plan* p, int branch); /* ops added next belong to `branch`: 0 = trunk, 1..4 = independent branches forked after the trunk by hn_plan_run (e.g. the three heads) */
+int hn_plan_add_wait(hn_plan* p, int branch); /* the current branch continues only after branch `branch` (a smaller index) has completed */
 int hn_plan_add_stem(hn_plan* p, const hn_stem_desc* d);
 int hn_plan_add_node(hn_plan* p, const hn_node_desc* d);
 int hn_plan_add_dw_multi(hn_plan* p, const hn_dw_multi_desc* d);

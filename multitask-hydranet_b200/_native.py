@@ -211,6 +211,7 @@ SYMBOLS = {
     "hn_plan_create": (C.c_int, [C.POINTER(_P)]),
     "hn_plan_destroy": (C.c_int, [_P]),
     "hn_plan_add_conv": (C.c_int, [_P, C.POINTER(ConvDesc)]),
+    "hn_plan_add_wait": (C.c_int, [_P, C.c_int]),
     "hn_plan_add_stem": (C.c_int, [_P, C.POINTER(StemDesc)]),
     "hn_plan_add_node": (C.c_int, [_P, C.POINTER(NodeDesc)]),
     "hn_plan_add_dw_multi": (C.c_int, [_P, C.POINTER(DwMultiDesc)]),

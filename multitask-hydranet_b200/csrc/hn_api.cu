@@ -30,7 +30,7 @@ extern "C" int hn_device_sm_count(void) {
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
-enum OpKind { OP_CONV, OP_STEM, OP_NODE, OP_DW_MULTI, OP_POOL, OP_LANEFUSE, OP_SE_POOL, OP_SE_SCALE, OP_DET, OP_LANE };
+enum OpKind { OP_CONV, OP_STEM, OP_NODE, OP_DW_MULTI, OP_POOL, OP_LANEFUSE, OP_SE_POOL, OP_SE_SCALE, OP_DET, OP_LANE, OP_WAIT };
 
 struct PlanOp {
     OpKind kind;
@@ -45,6 +45,7 @@ struct PlanOp {
     hn_se_scale_desc se_scale;
     hn_det_desc det;
     hn_lane_desc lane;
+    int wait_branch = 0;  // OP_WAIT: the branch whose completion this branch waits for here
 };
 
 static constexpr int kMaxBranches = 4;
@@ -111,6 +112,20 @@ PLAN_ADD(se_scale, OP_SE_SCALE, se_scale, hn_se_scale_desc)
 PLAN_ADD(det, OP_DET, det, hn_det_desc)
 PLAN_ADD(lane, OP_LANE, lane, hn_lane_desc)
 
+// A dependency between two branches: the ops added after it (in the current branch) start only once every op of branch
+// `branch` -- which must have a smaller index, i.e. be enqueued earlier -- has finished.  The two detection towers run as
+// two concurrent branches and the decode + NMS, which needs both, waits for the other tower.
+extern "C" int hn_plan_add_wait(hn_plan* p, int branch) {
+    HN_REQUIRE(p != nullptr, "null plan");
+    HN_REQUIRE(branch >= 1 && branch < p->cur_branch, "plan: wait for branch %d from branch %d", branch, p->cur_branch);
+    PlanOp* o = new PlanOp();
+    o->kind = OP_WAIT;
+    o->branch = p->cur_branch;
+    o->wait_branch = branch;
+    p->ops.push_back(o);
+    return HN_OK;
+}
+
 extern "C" int hn_plan_add_conv(hn_plan* p, const hn_conv_desc* d) {
     HN_REQUIRE(p != nullptr && d != nullptr, "null plan/desc");
     PlanOp* o = new PlanOp();
@@ -130,6 +145,7 @@ static int op_launches(const PlanOp* o) {
         case OP_DET: return hn_det_num_launches(&o->det);
         case OP_LANE: return 1;
         case OP_SE_POOL: return hn_se_pool_num_launches(&o->se_pool);
+        case OP_WAIT: return 0;
         default: return 1;
     }
 }
@@ -141,6 +157,7 @@ extern "C" int hn_plan_num_launches(const hn_plan* p) {
     return n;
 }
 
+static thread_local bool t_in_plan_run = false;
 extern "C" int hn_plan_run_range(hn_plan* p, int first, int last, void* stream) {
     HN_REQUIRE(p != nullptr, "null plan");
     HN_REQUIRE(first >= 0 && last <= (int)p->ops.size() && first <= last, "bad op range [%d,%d)", first, last);
@@ -159,13 +176,25 @@ extern "C" int hn_plan_run_range(hn_plan* p, int first, int last, void* stream) 
             case OP_SE_SCALE: rc = hn_se_scale_fwd(&o->se_scale, stream); break;
             case OP_DET: rc = hn_det_decode_nms(&o->det, stream); break;
             case OP_LANE: rc = hn_lane_decode_nms(&o->lane, stream); break;
+            case OP_WAIT:
+                // only inside hn_plan_run, where the awaited branch has just been enqueued and its join event recorded in
+                // the same (possibly capturing) context; a stand-alone run_range is sequential on one stream anyway
+                if (t_in_plan_run && p->ev_join[o->wait_branch - 1]) HN_CHECK_CUDA(cudaStreamWaitEvent(s, p->ev_join[o->wait_branch - 1], 0));
+                break;
         }
         if (rc) return rc;
     }
     return HN_OK;
 }
 
+static int plan_run_impl(hn_plan* p, void* stream);
 extern "C" int hn_plan_run(hn_plan* p, void* stream) {
+    t_in_plan_run = true;
+    const int rc = plan_run_impl(p, stream);
+    t_in_plan_run = false;
+    return rc;
+}
+static int plan_run_impl(hn_plan* p, void* stream) {
     HN_REQUIRE(p != nullptr, "null plan");
     const int n = (int)p->ops.size();
     int first_branch_op = n;
@@ -189,6 +218,10 @@ extern "C" int hn_plan_run(hn_plan* p, void* stream) {
         while (j < n && p->ops[j]->branch == b) ++j;
         if (b == p->ops[first_branch_op]->branch) {
             rc = hn_plan_run_range(p, i, j, stream);
+            if (rc == HN_OK) {  // later branches may wait for this one (hn_plan_add_wait)
+                if (!p->ev_join[b - 1]) HN_CHECK_CUDA(cudaEventCreateWithFlags(&p->ev_join[b - 1], cudaEventDisableTiming));
+                HN_CHECK_CUDA(cudaEventRecord(p->ev_join[b - 1], main_s));
+            }
         } else {
             const int k = b - 1;
             if (!p->side[k]) {

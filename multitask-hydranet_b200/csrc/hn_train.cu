@@ -32,6 +32,10 @@ static inline int check_mat(const hn_mat& m, const char* what) {
 static inline bool same_shape(const hn_mat& a, const hn_mat& b) { return a.rows == b.rows && a.cols == b.cols; }
 
 __device__ __forceinline__ float hn_sigmoid_acc(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    const float2 a = hn_unpack_bf16x2(u.x), b = hn_unpack_bf16x2(u.y), c = hn_unpack_bf16x2(u.z), d = hn_unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
 // derivative of the activation; `ref` = output for ReLU / ELU / sigmoid, pre-activation for swish
 __device__ __forceinline__ float act_grad(float ref, int act) {
     switch (act) {
@@ -136,8 +140,10 @@ __global__ void __launch_bounds__(256) hn_red1_kernel(const RedGeom g, const F f
     float a0[8], a1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.0f;
-    if (active)
+    if (active) {
+#pragma unroll 4
         for (long long r = r0 + rl; r < r1; r += rpi) f(seg, r, cv, a0, a1);
+    }
     float* mine = sm + (size_t)threadIdx.x * 16;
 #pragma unroll
     for (int j = 0; j < 8; ++j) { mine[j] = a0[j]; mine[8 + j] = a1[j]; }
@@ -244,32 +250,50 @@ __global__ void hn_bn_finalize_kernel(const RedGeom g, const float* __restrict__
     }
 }
 
+// Element-wise passes: four independent 16-byte items per thread and iteration (all loads issued before the first use);
+// with one item in flight these kernels ran at ~1/3 of the HBM rate.
+static constexpr int kEwU = 1;  // measured: 4 items per thread made the (mostly small, latency-bound) BatchNorm passes slower (2.1 -> 2.5 ms per step)
 __global__ void __launch_bounds__(256) hn_bn_apply_kernel(const RedGeom g, Mat z, const float* __restrict__ stats, int act, Mat res, Mat y) {
-    const long long total = g.rows * g.CV;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / g.CV;
-        const int cv = (int)(i - r * g.CV);
-        const int seg = seg_of_row(g, r);
-        const float* sc = stats + ((size_t)seg * 4 + 2) * g.C + cv * 8;
-        const float* sh = sc + g.C;
-        float v[8];
-        load8(z.ptr + r * z.ld + cv * 8, v);
+    const long long total = g.rows * g.CV, stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * kEwU) {
+        uint4 zv[kEwU], rv[kEwU];
+        long long rr[kEwU];
+        int cc[kEwU];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
-        if (res.ptr) {
-            float q[8];
-            load8(res.ptr + r * res.ld + cv * 8, q);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += q[j];
+        for (int u = 0; u < kEwU; ++u) {
+            const long long i = i0 + u * stride;
+            rr[u] = i / g.CV;
+            cc[u] = (int)(i - rr[u] * g.CV) * 8;
+            if (i < total) {
+                zv[u] = *reinterpret_cast<const uint4*>(z.ptr + rr[u] * z.ld + cc[u]);
+                if (res.ptr) rv[u] = *reinterpret_cast<const uint4*>(res.ptr + rr[u] * res.ld + cc[u]);
+            }
         }
-        if (act == HN_ACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
-        } else if (act == HN_ACT_SWISH) {
+        for (int u = 0; u < kEwU; ++u) {
+            if (i0 + u * stride >= total) break;
+            const int seg = seg_of_row(g, rr[u]);
+            const float* sc = stats + ((size_t)seg * 4 + 2) * g.C + cc[u];
+            const float* sh = sc + g.C;
+            float v[8];
+            unpack8(zv[u], v);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = v[j] * hn_sigmoid_acc(v[j]);
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+            if (res.ptr) {
+                float q[8];
+                unpack8(rv[u], q);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += q[j];
+            }
+            if (act == HN_ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+            } else if (act == HN_ACT_SWISH) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = v[j] * hn_sigmoid_acc(v[j]);
+            }
+            store8(y.ptr + rr[u] * y.ld + cc[u], v);
         }
-        store8(y.ptr + r * y.ld + cv * 8, v);
     }
 }
 
@@ -287,7 +311,7 @@ static int fill_bn_ptrs(const hn_bn_desc* d, BnPtrs* bp) {
     return HN_OK;
 }
 static inline int ew_grid(long long total_vec) {
-    long long b = (total_vec + 255) / 256;
+    long long b = (total_vec + 256 * kEwU - 1) / (256 * kEwU);
     long long cap = 148LL * 16;
     return (int)(b < 1 ? 1 : (b < cap ? b : cap));
 }
@@ -327,16 +351,22 @@ struct BnBwdF {
     Mat dy, z, y;
     const float* stats;
     int C, act;
-    __device__ __forceinline__ void dz_act(int seg, long long r, int cv, float (&dzv)[8], float (&xh)[8]) const {
+    struct Raw { uint4 g, z, y; };
+    __device__ __forceinline__ void load(long long r, int cv, Raw& w) const {
+        w.g = *reinterpret_cast<const uint4*>(dy.ptr + r * dy.ld + cv * 8);
+        w.z = *reinterpret_cast<const uint4*>(z.ptr + r * z.ld + cv * 8);
+        if (act == HN_ACT_RELU) w.y = *reinterpret_cast<const uint4*>(y.ptr + r * y.ld + cv * 8);
+    }
+    __device__ __forceinline__ void compute(int seg, int cv, const Raw& w, float (&dzv)[8], float (&xh)[8]) const {
         const float* st = stats + (size_t)seg * 4 * C + cv * 8;
         float g[8], zz[8];
-        load8(dy.ptr + r * dy.ld + cv * 8, g);
-        load8(z.ptr + r * z.ld + cv * 8, zz);
+        unpack8(w.g, g);
+        unpack8(w.z, zz);
 #pragma unroll
         for (int j = 0; j < 8; ++j) xh[j] = (zz[j] - st[j]) * st[C + j];
         if (act == HN_ACT_RELU) {
             float o[8];
-            load8(y.ptr + r * y.ld + cv * 8, o);
+            unpack8(w.y, o);
 #pragma unroll
             for (int j = 0; j < 8; ++j) dzv[j] = o[j] > 0.0f ? g[j] : 0.0f;
         } else if (act == HN_ACT_SWISH) {
@@ -348,8 +378,10 @@ struct BnBwdF {
         }
     }
     __device__ __forceinline__ void operator()(int seg, long long r, int cv, float (&a0)[8], float (&a1)[8]) const {
+        Raw w;
+        load(r, cv, w);
         float dzv[8], xh[8];
-        dz_act(seg, r, cv, dzv, xh);
+        compute(seg, cv, w, dzv, xh);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { a0[j] += dzv[j]; a1[j] = fmaf(dzv[j], xh[j], a1[j]); }
     }
@@ -369,21 +401,33 @@ __global__ void hn_bn_bwd_finalize_kernel(const RedGeom g, const float* __restri
 }
 
 __global__ void __launch_bounds__(256) hn_bn_bwd_apply_kernel(const RedGeom g, const BnBwdF f, const float* __restrict__ sums, Mat dz, Mat dres) {
-    const long long total = g.rows * g.CV;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / g.CV;
-        const int cv = (int)(i - r * g.CV);
-        const int seg = seg_of_row(g, r);
-        float dzv[8], xh[8];
-        f.dz_act(seg, r, cv, dzv, xh);
-        if (dres.ptr) store8(dres.ptr + r * dres.ld + cv * 8, dzv);
-        const float* sc = f.stats + ((size_t)seg * 4 + 2) * g.C + cv * 8;  // gamma * invstd
-        const float* m0 = sums + ((size_t)seg * 2) * g.C + cv * 8;
-        const float* m1 = m0 + g.C;
-        float o[8];
+    const long long total = g.rows * g.CV, stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * kEwU) {
+        BnBwdF::Raw w[kEwU];
+        long long rr[kEwU];
+        int cv[kEwU];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = sc[j] * (dzv[j] - m0[j] - xh[j] * m1[j]);
-        store8(dz.ptr + r * dz.ld + cv * 8, o);
+        for (int u = 0; u < kEwU; ++u) {
+            const long long i = i0 + u * stride;
+            rr[u] = i / g.CV;
+            cv[u] = (int)(i - rr[u] * g.CV);
+            if (i < total) f.load(rr[u], cv[u], w[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kEwU; ++u) {
+            if (i0 + u * stride >= total) break;
+            const int seg = seg_of_row(g, rr[u]);
+            float dzv[8], xh[8];
+            f.compute(seg, cv[u], w[u], dzv, xh);
+            if (dres.ptr) store8(dres.ptr + rr[u] * dres.ld + cv[u] * 8, dzv);
+            const float* sc = f.stats + ((size_t)seg * 4 + 2) * g.C + cv[u] * 8;  // gamma * invstd
+            const float* m0 = sums + ((size_t)seg * 2) * g.C + cv[u] * 8;
+            const float* m1 = m0 + g.C;
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = sc[j] * (dzv[j] - m0[j] - xh[j] * m1[j]);
+            store8(dz.ptr + rr[u] * dz.ld + cv[u] * 8, o);
+        }
     }
 }
 

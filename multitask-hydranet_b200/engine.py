@@ -329,6 +329,17 @@ class LanePostSpec:
         nv.check(nv.lib.hn_plan_add_lane(plan, self.desc))
 
 
+class WaitSpec:
+    """Branch dependency (hn_plan_add_wait): the ops after it in this branch start once branch ``wait_for`` has finished."""
+    kind, launches, macs = "wait", 0, 0
+
+    def __init__(self, name, wait_for, group):
+        self.name, self.wait_for, self.group = name, wait_for, group
+
+    def add_to(self, plan):
+        nv.check(nv.lib.hn_plan_add_wait(plan, self.wait_for))
+
+
 class SeScaleSpec:
     kind, launches, group, macs = "se_scale", 1, "backbone", 0
 
@@ -875,6 +886,7 @@ class Builder:
             anc = torch.from_numpy(make_anchors((self.H, self.W), a.anchor_scale, a.strides, a.scales, a.ratios)).to(self.dev).view(-1, 4).contiguous()
             self.keep.append(anc)
             dp = DetPostSpec("det.post", anc, reg, cls, (self.H, self.W), conf, iou, self.dev)
+            self.ops.append(WaitSpec("det.join", 2, "detect"))  # the decode needs the regression tower (branch 2) too
             self.ops.append(dp)
             self.out["det_post"] = dp
 
@@ -931,12 +943,11 @@ class Builder:
             fn()
             for op in self.ops[n0:]:
                 op.branch = branch
-        # ... and so are the two detection towers (branches must be contiguous and ascending: seg 1, reg 2, cls 3, lane 4)
+        # ... and so are the two detection towers (branches must be contiguous and ascending: seg 1, reg 2, cls 3, lane 4); the
+        # fused decode + NMS sits at the end of the classification tower's branch behind a wait for the regression tower
         for op in self.ops:
             b = getattr(op, "branch", 0)
-            if "det_post" in self.out:
-                continue  # the fused NMS needs both towers: they stay one branch
-            if b == 3 or (b == 2 and op.name.startswith("det.cls")):
+            if b == 3 or (b == 2 and not op.name.startswith("det.reg")):
                 op.branch = b + 1
         order = [getattr(op, "branch", 0) for op in self.ops]
         assert order == sorted(order), "head ops must be grouped by branch"
@@ -959,6 +970,8 @@ class Plan:
         branches = bool(getattr(model, "head_branches", False))
         cur = 0
         for op in self.ops:
+            if op.kind == "wait" and not branches:
+                continue  # one stream: program order already is the dependency
             try:
                 b = getattr(op, "branch", 0) if branches else 0
                 if b != cur:

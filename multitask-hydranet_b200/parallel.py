@@ -24,7 +24,10 @@ def shard_batch(global_batch, world_size, rank):
 
 
 class GradAllReduce:
-    def __init__(self, params, bucket_mb=25.0, process_group=None):
+    def __init__(self, params, bucket_mb=25.0, process_group=None, model=None):
+        # the hooks read a gradient the moment autograd accumulates it: weight-gradient kernels must then stay on the main
+        # stream (train.py puts them on a side stream otherwise)
+        self.model = model
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.params = [p for p in params if p.requires_grad]
@@ -59,6 +62,10 @@ class GradAllReduce:
 
     def _launch(self, bi):
         self.launched[bi] = True
+        st = getattr(self.model, "_train_state", None) if self.model is not None else None
+        if st is not None and st.side_dirty:  # gradients produced on the training state's side stream
+            from .train import join_side_stream
+            join_side_stream(st, st.device)
         grads = [p.grad for p in self.buckets[bi] if p.grad is not None]
         if not grads:
             return

@@ -195,6 +195,9 @@ class TrainState:
         self.recs = {}
         self.scratch = torch.empty(_SCRATCH_FLOATS, dtype=torch.float32, device=device)
         self.bn_seen = []
+        self.side_stream = torch.cuda.Stream(device) if device.type == "cuda" else None
+        self.side_wgrad = self.side_stream is not None and os.environ.get("HN_SIDE_WGRAD", "1") != "0"
+        self.side_dirty = False
         if model is not None:
             self._build(model)
             self._upload_table()
@@ -330,14 +333,41 @@ def _gemm_spatial(dev, srcs, blocks, n_out, out, tile_hw, bias=None, act=nv.ACT_
 _PROFILE_NAMES = bool(os.environ.get("HN_PROFILE_NAMES"))
 
 
-def _wgrad(dev, rec, dy_view, src_views, flat, tile, dw):
+def _wgrad(st, rec, dy_t, src_ts, dy_view, src_views, flat, tile, dw):
+    """Weight gradient of one convolution.  Nothing downstream in backward depends on it (only the optimizer does), and most of
+    these launches are small and latency-bound, so they go to a SIDE stream: they fill the SMs the main chain (data gradient ->
+    BatchNorm backward -> next layer) leaves idle.  Joined back in StemConv.backward (the last node of every backward) and in
+    TrainStep.  Not used when the parameter already holds a gradient (autograd would add to it on the main stream at once)."""
+    dev = dw.device
+    side = st.side_stream if (st.side_wgrad and rec.w.grad is None) else None
+    if side is None:
+        return _wgrad_named(dev, rec, dy_view, src_views, flat, tile, dw, _stream(dev))
+    main = torch.cuda.current_stream(dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        _wgrad_named(dev, rec, dy_view, src_views, flat, tile, dw, side.cuda_stream)
+    for t in (dy_t, dw) + tuple(src_ts):
+        t.record_stream(side)
+    if not st.side_dirty:
+        st.side_dirty = True
+        # join when this backward pass is over, whatever its last node is (runs on the thread that called backward())
+        torch.autograd.Variable._execution_engine.queue_callback(lambda: join_side_stream(st, dev))
+
+
+def join_side_stream(st, dev):
+    if st.side_dirty:
+        torch.cuda.current_stream(dev).wait_stream(st.side_stream)
+        st.side_dirty = False
+
+
+def _wgrad_named(dev, rec, dy_view, src_views, flat, tile, dw, stream):
     if _PROFILE_NAMES:  # tools/profile_train.py: per-layer device time of the weight-gradient kernel
         with torch.profiler.record_function("wgrad:" + rec.name):
-            return _wgrad_launch(dev, rec, dy_view, src_views, flat, tile, dw)
-    return _wgrad_launch(dev, rec, dy_view, src_views, flat, tile, dw)
+            return _wgrad_launch(dev, rec, dy_view, src_views, flat, tile, dw, stream)
+    return _wgrad_launch(dev, rec, dy_view, src_views, flat, tile, dw, stream)
 
 
-def _wgrad_launch(dev, rec, dy_view, src_views, flat, tile, dw):
+def _wgrad_launch(dev, rec, dy_view, src_views, flat, tile, dw, stream):
     d = nv.WgradDesc()
     d.dy = dy_view
     for i, v in enumerate(src_views):
@@ -355,7 +385,7 @@ def _wgrad_launch(dev, rec, dy_view, src_views, flat, tile, dw):
     d.s_co, d.s_ci = rec.s_co, rec.s_ci
     d.grouped = rec.grouped
     d.dw = dw.data_ptr()
-    nv.check(nv.lib.hn_conv_wgrad(C.byref(d), _stream(dev)))
+    nv.check(nv.lib.hn_conv_wgrad(C.byref(d), stream))
 
 
 def _colsum(st, t, valid=None):
@@ -410,6 +440,7 @@ class StemConv(Function):
         dw = torch.empty((32, 3, 3, 3), dtype=torch.float32, device=x.device)
         v = _view(dz)
         nv.check(nv.lib.hn_stem_wgrad(x.data_ptr(), N, H, W, C.byref(v), dw.data_ptr(), st.scratch.data_ptr(), st.scratch.numel() * 4, _stream(x.device)))
+        join_side_stream(st, x.device)  # every other backward node has run by now: the weight gradients on the side stream are complete
         return None, None, dw
 
 
@@ -439,7 +470,7 @@ class Conv1x1(Function):
         dx_full = torch.empty(tuple(dy.shape[:-1]) + (rec.cin,), dtype=BF, device=dev)
         _gemm_rows(dev, dy, rec.dgrad, rec.cin, dx_full)
         dw = torch.zeros_like(rec.w)
-        _wgrad(dev, rec, _rows_view(dy), [_rows_view(x) for x in xs], True, (1, 128), dw)
+        _wgrad(st, rec, dy, xs, _rows_view(dy), [_rows_view(x) for x in xs], True, (1, 128), dw)
         db = _colsum(st, dy) if ctx.has_bias else None
         if len(xs) == 1:
             dxs = (dx_full,)
@@ -472,7 +503,7 @@ class Conv1x1S2(Function):
         dx = torch.zeros_like(x)  # only the (0,0) phase receives gradient
         _gemm_spatial(x.device, [_view(dy)], rec.dgrad, rec.cin, dx, (dy.shape[1], dy.shape[2]), out_scale=2)
         dw = torch.zeros_like(rec.w)
-        _wgrad(x.device, rec, _view(dy), [_view(_phase(x, 0, 0))], False, choose_tile(dy.shape[1], dy.shape[2]), dw)
+        _wgrad(ctx.st, rec, dy, [x], _view(dy), [_view(_phase(x, 0, 0))], False, choose_tile(dy.shape[1], dy.shape[2]), dw)
         return None, None, dw, dx
 
 
@@ -508,7 +539,7 @@ class GroupedConv3x3(Function):
             for (ry, rx), blocks in rec.dgrad.items():
                 _gemm_spatial(dev, [_view(dy)], blocks, rec.cin, dx, (x.shape[1] // 2, x.shape[2] // 2), grouped=1, out_scale=2, oy=ry, ox=rx)
         dw = torch.zeros_like(rec.w)
-        _wgrad(dev, rec, _view(dy), GroupedConv3x3._srcs(x, rec.stride), False, choose_tile(dy.shape[1], dy.shape[2]), dw)
+        _wgrad(ctx.st, rec, dy, [x], _view(dy), GroupedConv3x3._srcs(x, rec.stride), False, choose_tile(dy.shape[1], dy.shape[2]), dw)
         return None, None, dw, dx
 
 
@@ -549,7 +580,7 @@ class Conv3x3Padded(Function):
         dxp = torch.empty_like(xp)
         _gemm_spatial(dev, [_view(dz)], rec.dgrad, rec.cin, dxp, (Hp, Wp))
         dw = torch.zeros_like(rec.w)
-        _wgrad(dev, rec, _view(dz), [_view(xp)], False, choose_tile(Hp - 2, Wp - 2), dw)
+        _wgrad(st, rec, dz, [xp], _view(dz), [_view(xp)], False, choose_tile(Hp - 2, Wp - 2), dw)
         return None, None, None, None, dw, db, dxp
 
 
@@ -845,7 +876,7 @@ class HeadConv(Function):
         dx = torch.empty_like(x, memory_format=torch.contiguous_format)
         _gemm_rows(dev, dz, rec.dgrad, rec.cin, dx)
         dw = torch.zeros_like(rec.w)
-        _wgrad(dev, rec, _rows_view(dz), [_rows_view(x)], True, (1, 128), dw)
+        _wgrad(st, rec, dz, [x], _rows_view(dz), [_rows_view(x)], True, (1, 128), dw)
         db = _colsum(st, dz, rec.cout)
         return None, None, None, None, None, dw, db, dx
 
@@ -1083,6 +1114,9 @@ class TrainStep:
         loss = weighted_total(self.model.cfgs, ld)
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
+        st = getattr(self.model, "_train_state", None)
+        if st is not None:
+            join_side_stream(st, x.device)
         return loss, ld
 
     def _exchange(self):

@@ -107,11 +107,11 @@ def _conv_case(kind, cin, cout, H, W, stride=1, bias=False, srcs=None, N=2):
 def test_conv1x1_fwd_dgrad_wgrad(cin, cout, bias, srcs):
     st, rec, w, b, _ = _conv_case("pw", cin, cout, 20, 20, bias=bias, srcs=srcs)
     x = torch.randn(2, 20, 20, cin, device=DEV).to(BF)
-    xs = [t.contiguous().requires_grad_() for t in (x.split(srcs, dim=3) if srcs else [x])]
+    xs = [t.clone().requires_grad_() for t in (x.split(srcs, dim=3) if srcs else [x])]
     y = T.Conv1x1.apply(st, rec, b, w, *xs)
     gy = torch.randn_like(y)
     y.backward(gy)
-    xf = x.float().requires_grad_()
+    xf = x.detach().float().requires_grad_()
     wf = bf(w.detach()).requires_grad_()
     bfp = b.detach().clone().requires_grad_() if bias else None
     yr = F.conv2d(xf.permute(0, 3, 1, 2), wf, bfp)

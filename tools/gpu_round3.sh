@@ -1,0 +1,9 @@
+#!/bin/bash
+timeout 1500 python -m pytest tests -x -q -m gpu --no-header -p no:cacheprovider 2>&1 | tail -6
+timeout 900 python bench.py --steps 10 --warmup 5 --dump-ops 2>&1 | tail -2 > gpurun_out/bench_infer.log
+python -c "
+import json; d=json.loads(open('gpurun_out/bench_infer.log').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['latency_b1_ms'], d['roofline']['frac'], d['gpu_launches'])"
+grep "det\.\|lane\." gpurun_out/op_times.txt | tail -22
+timeout 600 python bench.py --mode train --steps 5 --warmup 3 2>&1 | tail -1 | cut -c1-160
+timeout 600 python bench.py --mode train --steps 5 --warmup 3 --batch 32 2>&1 | tail -1 | cut -c1-160
+timeout 600 python tools/profile_train.py > /dev/null 2>gpurun_out/prof_err.log; head -34 gpurun_out/train_profile.txt
