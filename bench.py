@@ -80,10 +80,16 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of hn_conv_gemm_kernel, averaged over the 156 launches of one batch-32
-# step (profiles/r01_launches_step_b32.csv: 5.79 GB in total; ncu flushes the caches before every kernel, so this
-# is an upper figure for the replayed step, where the L2 keeps part of each layer's output for the next one)
-CONV_DRAM_BYTES_PER_LAUNCH = 37.1e6
+def conv_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of hn_conv_gemm_kernel per launch, MEASURED: the newest
+    profiles/rNN_conv_traffic.json, written by tools/ncu_traffic.py from the committed ncu launch list of one step (ncu flushes the
+    caches before every kernel, so this is an upper figure for the replayed step).  None when no profile has been taken."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_conv_traffic.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    return d["dram_bytes_per_launch"], os.path.relpath(files[-1], ROOT)
 
 
 def build_model(device):
@@ -386,7 +392,7 @@ def run_native(args):
         achieved = conv_flops / (conv_ms / 1e3) / 1e12
         peak = pk["bf16_tflops_sustained"]
         roof = {"bound": "tensor", "kernel": "hn_conv_gemm_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s",
-                "frac": round(achieved / peak, 4), "traffic": CONV_DRAM_BYTES_PER_LAUNCH, "peak_source": pk_src + " (sustained: kernel timed inside a step)",
+                "frac": round(achieved / peak, 4), "traffic": conv_traffic()[0], "traffic_source": conv_traffic()[1], "peak_source": pk_src + " (sustained: kernel timed inside a step)",
                 "launches_per_step": conv_n, "ms_per_step_in_kernel": round(conv_ms, 3), "share_of_step": round(conv_ms / all_ms, 3),
                 "algorithmic_gflop_per_launch_avg": round(conv_flops / conv_n / 1e9, 3),
                 "breakdown_ms": {"%s/%s" % k: round(v[0], 3) for k, v in sorted(tot.items())},

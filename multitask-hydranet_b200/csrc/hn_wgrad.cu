@@ -301,15 +301,27 @@ extern "C" int hn_conv_wgrad(const hn_wgrad_desc* d, void* stream_) {
     if (stages > 4) stages = 4;
     if (stages < 2) stages = 2;
     p.stages = stages;
-    // split K so that the grid fills the machine (~2 CTAs' worth of items per SM) but every CTA keeps >= 2 pixel tiles
+    // Split K: CTAs = pairs x splits run in waves of `sms` (one CTA per SM: ~200 KB of shared memory each); every CTA walks
+    // ceil(k_tiles / splits) pixel tiles and then pays a fixed prologue + reduction epilogue (~kFixed tiles' worth).  Pick the split
+    // that minimises waves x (tiles per CTA + fixed): it lands on whole waves instead of e.g. 324 CTAs = 2.2 waves.
     int sms = hn_device_sm_count();
     if (sms <= 0) sms = 148;
     const long long pairs = (long long)p.m_tiles * p.tap_groups;
-    long long splits = (2LL * sms + pairs - 1) / pairs;
-    if (splits > p.k_tiles / 2) splits = p.k_tiles / 2;
-    if (splits < 1) splits = 1;
-    p.k_per_split = hn_cdiv(p.k_tiles, splits);
-    p.splits = hn_cdiv(p.k_tiles, p.k_per_split);
+    {
+        const int kFixed = 6;
+        long long best_cost = -1;
+        int best = 1;
+        const int max_s = p.k_tiles < 256 ? p.k_tiles : 256;
+        for (int sp = 1; sp <= max_s; ++sp) {
+            const long long per = (p.k_tiles + sp - 1) / sp;
+            const long long ctas = pairs * ((p.k_tiles + per - 1) / per);
+            const long long waves = (ctas + sms - 1) / sms;
+            const long long cost = waves * (per + kFixed);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = sp; }
+        }
+        p.k_per_split = hn_cdiv(p.k_tiles, best);
+        p.splits = hn_cdiv(p.k_tiles, p.k_per_split);
+    }
     const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 16 + 4 * 32 * 33 * 4 + 64;
     HN_REQUIRE(smem <= 227 * 1024, "wgrad: %zu bytes of shared memory", smem);
     static std::once_flag once;

@@ -259,6 +259,12 @@ class TrainState:
         self.table = raw.to(self.device)
         self.n_entries, self.max_rows = len(entries), max_rows
         self.sig = tuple(r.w.data_ptr() for r in self.recs.values())
+        self.grad_offset, off = {}, 0
+        for r in self.recs.values():
+            self.grad_offset[r.name] = off
+            off += (r.w.numel() + 63) // 64 * 64  # 256-byte aligned slices
+        self.grad_elems = off
+        self.token = StepToken(self)
 
     def pack(self):
         """fp32 parameters -> bf16 GEMM operands (forward and data-gradient matrices of every conv): one launch."""
@@ -266,6 +272,24 @@ class TrainState:
 
     def valid_for(self, model):
         return self.sig == tuple(r.w.data_ptr() for r in self.recs.values())
+
+
+class StepToken:
+    """Per-forward handle: the backward of THIS forward allocates one zeroed fp32 arena for all convolution weight gradients
+    (the split-K kernel accumulates into zeros) instead of ~150 separately filled tensors; the gradients handed to autograd are
+    views of it (a fresh arena per step: nothing aliases a gradient the caller may still hold from the previous step)."""
+
+    def __init__(self, st):
+        self.st, self.arena, self.taken = st, None, set()
+
+    def dw(self, rec):
+        if rec.name in self.taken:  # a second backward through the same forward (retain_graph) or a re-used state: own buffer
+            return torch.zeros_like(rec.w)
+        self.taken.add(rec.name)
+        if self.arena is None:
+            self.arena = torch.zeros(self.st.grad_elems, dtype=torch.float32, device=self.st.device)
+        off = self.st.grad_offset[rec.name]
+        return self.arena[off:off + rec.w.numel()].view(rec.w.shape)
 
 
 def get_state(model, device):
@@ -360,7 +384,16 @@ def join_side_stream(st, dev):
         st.side_dirty = False
 
 
+_NVTX = bool(os.environ.get("HN_NVTX"))
+
+
 def _wgrad_named(dev, rec, dy_view, src_views, flat, tile, dw, stream):
+    if _NVTX:  # tools/profile_train_step.py under `ncu --nvtx --nvtx-include "wgrad:<layer>/"`
+        torch.cuda.nvtx.range_push("wgrad:" + rec.name)
+        try:
+            return _wgrad_launch(dev, rec, dy_view, src_views, flat, tile, dw, stream)
+        finally:
+            torch.cuda.nvtx.range_pop()
     if _PROFILE_NAMES:  # tools/profile_train.py: per-layer device time of the weight-gradient kernel
         with torch.profiler.record_function("wgrad:" + rec.name):
             return _wgrad_launch(dev, rec, dy_view, src_views, flat, tile, dw, stream)
@@ -457,7 +490,7 @@ class Conv1x1(Function):
         d = _conv_desc([_rows_view(x) for x in xs], rec.fwd, flat=True, cout=rec.cout, out_ptr=m.ptr, out_strides=(m.rows * m.ld, 0, m.ld),
                        flat_hw=max(m.rows, 1), bias=bias.detach().data_ptr() if bias is not None else None)
         nv.check(nv.lib.hn_conv_fwd(C.byref(d), _stream(dev)))
-        ctx.st, ctx.rec, ctx.has_bias = st, rec, bias is not None
+        ctx.st, ctx.rec, ctx.has_bias, ctx.tok = st, rec, bias is not None, st.token
         ctx.save_for_backward(*xs)
         return out
 
@@ -469,7 +502,7 @@ class Conv1x1(Function):
         dy = _c(dy)
         dx_full = torch.empty(tuple(dy.shape[:-1]) + (rec.cin,), dtype=BF, device=dev)
         _gemm_rows(dev, dy, rec.dgrad, rec.cin, dx_full)
-        dw = torch.zeros_like(rec.w)
+        dw = ctx.tok.dw(rec)
         _wgrad(st, rec, dy, xs, _rows_view(dy), [_rows_view(x) for x in xs], True, (1, 128), dw)
         db = _colsum(st, dy) if ctx.has_bias else None
         if len(xs) == 1:
@@ -491,7 +524,7 @@ class Conv1x1S2(Function):
         Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
         out = torch.empty((N, Ho, Wo, rec.cout), dtype=BF, device=x.device)
         _gemm_spatial(x.device, [_view(_phase(x, 0, 0))], rec.fwd, rec.cout, out, (Ho, Wo))
-        ctx.st, ctx.rec = st, rec
+        ctx.st, ctx.rec, ctx.tok = st, rec, st.token
         ctx.save_for_backward(x)
         return out
 
@@ -502,7 +535,7 @@ class Conv1x1S2(Function):
         dy = _c(dy)
         dx = torch.zeros_like(x)  # only the (0,0) phase receives gradient
         _gemm_spatial(x.device, [_view(dy)], rec.dgrad, rec.cin, dx, (dy.shape[1], dy.shape[2]), out_scale=2)
-        dw = torch.zeros_like(rec.w)
+        dw = ctx.tok.dw(rec)
         _wgrad(ctx.st, rec, dy, [x], _view(dy), [_view(_phase(x, 0, 0))], False, choose_tile(dy.shape[1], dy.shape[2]), dw)
         return None, None, dw, dx
 
@@ -522,7 +555,7 @@ class GroupedConv3x3(Function):
         assert s == 1 or (H % 2 == 0 and W % 2 == 0), "strided grouped conv expects even maps"
         out = torch.empty((N, Ho, Wo, Cc), dtype=BF, device=x.device)
         _gemm_spatial(x.device, GroupedConv3x3._srcs(x, s), rec.fwd, Cc, out, (Ho, Wo), grouped=1)
-        ctx.st, ctx.rec = st, rec
+        ctx.st, ctx.rec, ctx.tok = st, rec, st.token
         ctx.save_for_backward(x)
         return out
 
@@ -538,7 +571,7 @@ class GroupedConv3x3(Function):
         else:
             for (ry, rx), blocks in rec.dgrad.items():
                 _gemm_spatial(dev, [_view(dy)], blocks, rec.cin, dx, (x.shape[1] // 2, x.shape[2] // 2), grouped=1, out_scale=2, oy=ry, ox=rx)
-        dw = torch.zeros_like(rec.w)
+        dw = ctx.tok.dw(rec)
         _wgrad(ctx.st, rec, dy, [x], _view(dy), GroupedConv3x3._srcs(x, rec.stride), False, choose_tile(dy.shape[1], dy.shape[2]), dw)
         return None, None, dw, dx
 
@@ -554,7 +587,7 @@ class Conv3x3Padded(Function):
         dev = xp.device
         out = torch.empty((N, H, W, rec.cout), dtype=torch.float32 if logits else BF, device=dev)
         _gemm_spatial(dev, [_view(xp)], rec.fwd, rec.cout, out, (H, W), bias=bias.detach(), act=act, out_fp32=1 if logits else 0)
-        ctx.st, ctx.rec, ctx.act, ctx.logits = st, rec, act, logits
+        ctx.st, ctx.rec, ctx.act, ctx.logits, ctx.tok = st, rec, act, logits, st.token
         ctx.save_for_backward(xp, out)
         return out
 
@@ -579,7 +612,7 @@ class Conv3x3Padded(Function):
             db = _colsum(st, dz)
         dxp = torch.empty_like(xp)
         _gemm_spatial(dev, [_view(dz)], rec.dgrad, rec.cin, dxp, (Hp, Wp))
-        dw = torch.zeros_like(rec.w)
+        dw = ctx.tok.dw(rec)
         _wgrad(st, rec, dz, [xp], _view(dz), [_view(xp)], False, choose_tile(Hp - 2, Wp - 2), dw)
         return None, None, None, None, dw, db, dxp
 
@@ -849,7 +882,7 @@ class HeadConv(Function):
         d = _conv_desc([_rows_view(x)], rec.fwd, flat=True, cout=rec.cout, out_ptr=out.data_ptr() + 4 * off, out_strides=(sn, 0, spix),
                        flat_hw=rpi if rpi else max(m.rows, 1), bias=bias.detach().data_ptr(), act=act, out_fp32=1, groups=groups)
         nv.check(nv.lib.hn_conv_fwd(C.byref(d), _stream(dev)))
-        ctx.st, ctx.rec, ctx.act, ctx.layout = st, rec, act, layout
+        ctx.st, ctx.rec, ctx.act, ctx.layout, ctx.tok = st, rec, act, layout, st.token
         ctx.save_for_backward(x, out)
         return out
 
@@ -875,7 +908,7 @@ class HeadConv(Function):
         nv.check(nv.lib.hn_head_grad(C.byref(hd), _stream(dev)))
         dx = torch.empty_like(x, memory_format=torch.contiguous_format)
         _gemm_rows(dev, dz, rec.dgrad, rec.cin, dx)
-        dw = torch.zeros_like(rec.w)
+        dw = ctx.tok.dw(rec)
         _wgrad(st, rec, dz, [x], _rows_view(dz), [_rows_view(x)], True, (1, 128), dw)
         db = _colsum(st, dz, rec.cout)
         return None, None, None, None, None, dw, db, dx
@@ -1044,6 +1077,7 @@ def train_forward(model, x, mode="train"):
     st = get_state(model, dev)
     x = x.detach().float().contiguous()
     st.bn_seen = []
+    st.token = StepToken(st)
     st.pack()
     feats = _backbone(st, model, x)
     levels = _neck(st, model, feats)
