@@ -250,6 +250,18 @@ int hn_det_decode_nms(const hn_det_desc* d, void* stream);
 int64_t hn_lane_workspace_bytes(int32_t N, int32_t n_anchor, int32_t ppl);
 int hn_lane_decode_nms(const hn_lane_desc* d, void* stream);
 
+/* Host tails of the decoders on the device.
+ * hn_det_invert_affine: DetectionHeader.invert_affine (detection.py:218-230) in place on the kept boxes of hn_det_decode_nms;
+ *   scale_xy: device fp32 [N][2] = float32(new_w / old_w), float32(new_h / old_h).
+ * hn_lane_scale_to_org: LaneHeader.scale_to_org's arithmetic (lanedetect.py:118-124, lane_codec_utils.py:128-182,236-282) for the
+ *   kept lanes of hn_lane_decode_nms: ordering keys [N][n_anchor][4] = (cross_x, k, first x, last x) and the points scaled to
+ *   the original frame (x fp32, y fp64, as numpy / Python compute them).  The final ordering (a non-transitive comparator
+ *   under Python's sort) and the dict stay on the host. */
+int hn_det_invert_affine(float* boxes, const int32_t* count, int32_t N, int32_t A, const float* scale_xy, void* stream);
+int hn_lane_scale_to_org(const int32_t* count, const int32_t* meta, const float* xs, int32_t N, int32_t n_anchor, int32_t ppl,
+                         double input_height, double interval, double cross_y, double scale_x, double scale_y, float* keys, float* x_out,
+                         double* y_out, void* stream);
+
 /* ---- plan: a recorded schedule of the ops above, replayed with one call (or as a CUDA graph) ---- */
 typedef struct hn_plan hn_plan;
 int hn_plan_create(hn_plan** out);

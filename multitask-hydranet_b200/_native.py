@@ -208,6 +208,9 @@ SYMBOLS = {
     "hn_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), _P]),
     "hn_adam_step": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
                                C.c_float, _P, _P]),
+    "hn_det_invert_affine": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
+    "hn_lane_scale_to_org": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                       _P, _P, _P, _P]),
     "hn_plan_create": (C.c_int, [C.POINTER(_P)]),
     "hn_plan_destroy": (C.c_int, [_P]),
     "hn_plan_add_conv": (C.c_int, [_P, C.POINTER(ConvDesc)]),

@@ -1187,3 +1187,74 @@ extern "C" int hn_lane_decode_nms(const hn_lane_desc* d, void* stream) {
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// host tails of the decoders, on the device
+// ------------------------------------------------------------------------------------------------
+// DetectionHeader.invert_affine (head_detect/detection.py:218-230): rois[:, [0, 2]] /= (new_w / old_w), rois[:, [1, 3]] /=
+// (new_h / old_h) -- numpy float32 arrays divided by a Python float: the quotient of the two ints is formed in double, cast
+// to float32, and the division runs in fp32 (NEP 50).  `scale` holds that float32 divisor per image: [N][2] = (x, y).
+__global__ void hn_det_invert_affine_kernel(float* __restrict__ boxes, const int* __restrict__ count, int N, int A, const float* __restrict__ scale) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)N * A) return;
+    const int n = (int)(i / A), k = (int)(i - (long long)n * A);
+    if (k >= count[n]) return;
+    float4 b = reinterpret_cast<float4*>(boxes)[i];
+    const float sx = scale[n * 2], sy = scale[n * 2 + 1];
+    b.x = __fdiv_rn(b.x, sx); b.z = __fdiv_rn(b.z, sx);
+    b.y = __fdiv_rn(b.y, sy); b.w = __fdiv_rn(b.w, sy);
+    reinterpret_cast<float4*>(boxes)[i] = b;
+}
+extern "C" int hn_det_invert_affine(float* boxes, const int32_t* count, int32_t N, int32_t A, const float* scale_xy, void* stream) {
+    HN_REQUIRE(boxes && count && scale_xy && N >= 0 && A >= 0, "invert_affine: bad arguments");
+    const long long total = (long long)N * A;
+    if (total == 0) return HN_OK;
+    hn_det_invert_affine_kernel<<<hn_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(boxes, count, N, A, scale_xy);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+// LaneHeader.scale_to_org (lanedetect.py:118-124 -> lane_codec_utils.py:185-282): for every kept lane the ordering keys of
+// LaneWithCrossK (slope k and x where the extension of its two bottom points crosses y = net_height - 1; lane_codec_utils.py:128-182)
+// and the points scaled to the original frame.  Arithmetic as Python / numpy perform it: x is numpy float32, y a Python float
+// (double); float32 (op) Python-float runs in fp32 with the double operand rounded to fp32 first; y * sy stays in double.
+// keys [N][na][4] = (cross_x, k, first x, last x); xo fp32 [N][na][ppl]; yo fp64 [N][na][ppl].
+__global__ void hn_lane_scale_kernel(const int* __restrict__ count, const int* __restrict__ meta, const float* __restrict__ xs, int na, int ppl,
+                                     double input_height, double interval, double cross_y, double sx, double sy, float* __restrict__ keys,
+                                     float* __restrict__ xo, double* __restrict__ yo) {
+    const int n = blockIdx.y, k = blockIdx.x;
+    if (k >= count[n]) return;
+    const int* m = meta + ((long long)n * na + k) * 4;
+    const int start = m[1], npts = m[3];
+    const float* x = xs + ((long long)n * na + k) * ppl;
+    const float fsx = (float)sx;
+    for (int q = threadIdx.x; q < npts; q += blockDim.x) {
+        const double y = input_height - 1.0 - (double)(start + q) * interval;
+        xo[((long long)n * na + k) * ppl + q] = __fmul_rn(x[q], fsx);
+        yo[((long long)n * na + k) * ppl + q] = y * sy;
+    }
+    if (threadIdx.x == 0) {
+        float* key = keys + ((long long)n * na + k) * 4;
+        const double y0 = input_height - 1.0 - (double)start * interval, y1 = input_height - 1.0 - (double)(start + 1) * interval;
+        // k = (p1.x - p0.x) / (p1.y - p0.y); cross_x = kk * y + (p0.x - kk * p0.y) with kk = (p0.x - p1.x) / (p0.y - p1.y)
+        const float kslope = __fdiv_rn(__fsub_rn(x[1], x[0]), (float)(y1 - y0));
+        float cross = -1.0f;
+        if (fabs(y0 - y1) >= 1e-6) {
+            const float kk = __fdiv_rn(__fsub_rn(x[0], x[1]), (float)(y0 - y1));
+            const float b = __fsub_rn(x[0], __fmul_rn(kk, (float)y0));
+            cross = __fadd_rn(__fmul_rn(kk, (float)cross_y), b);
+        }
+        key[0] = cross; key[1] = kslope; key[2] = x[0]; key[3] = x[npts - 1];
+    }
+}
+extern "C" int hn_lane_scale_to_org(const int32_t* count, const int32_t* meta, const float* xs, int32_t N, int32_t n_anchor, int32_t ppl,
+                                    double input_height, double interval, double cross_y, double scale_x, double scale_y, float* keys, float* x_out,
+                                    double* y_out, void* stream) {
+    HN_REQUIRE(count && meta && xs && keys && x_out && y_out && N >= 0 && n_anchor >= 1 && ppl >= 2, "lane scale: bad arguments");
+    if (N == 0) return HN_OK;
+    hn_lane_scale_kernel<<<dim3((unsigned)n_anchor, (unsigned)N), 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(count, meta, xs, n_anchor, ppl, input_height,
+                                                                                                                  interval, cross_y, scale_x, scale_y, keys, x_out, y_out);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}

@@ -179,11 +179,31 @@ class DetectionHeader(nn.Module):
         return boxes, scores, cids, count[:N], cand[:N]
 
     @staticmethod
-    def decode(imgs, regressions, classifications, anchors, conf_thres=0.6, iou_thres=0.3):
+    def invert_affine_device(metas, boxes, count):
+        """``invert_affine`` (detection.py:218-230) on the device, in place on ``decode_device``'s boxes [N, A, 4] (rows
+        ``[:count[n]]``): same fp32 divisions as numpy performs on the host (float32 rois / Python float).  ``metas``: a float, or
+        per image (new_w, new_h, old_w, old_h, padding_w, padding_h)."""
+        _require_cuda(boxes, "DetectionHeader.invert_affine")
+        N, A = boxes.shape[0], boxes.shape[1]
+        if isinstance(metas, float):
+            sc = np.full((N, 2), np.float32(metas), dtype=np.float32)
+        else:
+            sc = np.array([[np.float32(m[0] / m[2]), np.float32(m[1] / m[3])] for m in metas], dtype=np.float32)
+        scale = torch.from_numpy(sc).to(boxes.device)
+        with torch.cuda.device(boxes.device):
+            nv.check(nv.lib.hn_det_invert_affine(boxes.data_ptr(), count.data_ptr(), N, A, scale.data_ptr(), _stream_ptr(boxes.device)))
+        return boxes
+
+    @staticmethod
+    def decode(imgs, regressions, classifications, anchors, conf_thres=0.6, iou_thres=0.3, metas=None):
+        """detection.py:232-245.  ``metas`` (extension): apply ``invert_affine`` on the device before the download, so the
+        returned rois are in original-image coordinates."""
         if imgs is None:
             return None
         boxes, scores, cids, count, _ = DetectionHeader.decode_device(imgs.shape[2:], regressions, classifications, anchors,
                                                                       conf_thres, iou_thres)
+        if metas is not None:
+            DetectionHeader.invert_affine_device(metas, boxes, count)
         counts = count.cpu().tolist()  # the one host sync the reference also has (.cpu())
         kmax = max(counts) if counts else 0
         b, s, c = boxes[:, :kmax].cpu().numpy(), scores[:, :kmax].cpu().numpy(), cids[:, :kmax].cpu().numpy()
@@ -314,6 +334,47 @@ class LaneHeader(nn.Module):
     def scale_to_org(lane_nms_set, net_input_width, net_input_height, org_width, org_height):
         lane_order_set = order_lane_x_axis(list(lane_nms_set), net_input_height)
         return convert_lane_to_dict(lane_order_set, org_width / net_input_width, org_height / net_input_height)
+
+    @staticmethod
+    def scale_to_org_device(count, meta, prob, xs, pointlane, net_input_width, net_input_height, org_width, org_height, index=0):
+        """``scale_to_org(decode(...))`` without rebuilding ``Lane`` objects on the host: the ordering keys (slope, crossing of the
+        bottom row) and the points in original-frame coordinates are computed by ``hn_lane_scale_to_org`` from ``decode_device``'s
+        tensors; the host only runs the reference's (non-transitive) comparator through Python's sort and builds the dict.
+        Returns exactly what ``scale_to_org`` returns (lanedetect.py:118-124)."""
+        _require_cuda(xs, "LaneHeader.scale_to_org")
+        N, na, ppl = xs.shape
+        dev = xs.device
+        keys = torch.empty((N, na, 4), dtype=torch.float32, device=dev)
+        xo = torch.empty((N, na, ppl), dtype=torch.float32, device=dev)
+        yo = torch.empty((N, na, ppl), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            nv.check(nv.lib.hn_lane_scale_to_org(count.data_ptr(), meta.data_ptr(), xs.data_ptr(), N, na, ppl, float(pointlane.input_height),
+                                                 float(pointlane.interval), float(net_input_height - 1.0), org_width / net_input_width,
+                                                 org_height / net_input_height, keys.data_ptr(), xo.data_ptr(), yo.data_ptr(), _stream_ptr(dev)))
+        k = int(count[index])
+        meta_h, prob_h = meta[index, :k].cpu().numpy(), prob[index, :k].cpu().numpy()
+        keys_h, xo_h, yo_h = keys[index, :k].cpu().numpy(), xo[index, :k].cpu().numpy(), yo[index, :k].cpu().numpy()
+
+        class _Key:  # LaneWithCrossK.__lt__ (lane_codec_utils.py:168-182) on the device-computed keys
+            __slots__ = ("i", "cross_x", "k", "last_x")
+
+            def __init__(self, i):
+                self.i, self.cross_x, self.k, self.last_x = i, keys_h[i, 0], keys_h[i, 1], keys_h[i, 3]
+
+            def __lt__(self, other):
+                if abs(self.cross_x - other.cross_x) > 2.0:
+                    return self.cross_x < other.cross_x
+                return self.last_x < other.last_x
+
+        order = sorted(_Key(i) for i in range(k))
+        lines = []
+        for key in order:
+            i = key.i
+            if prob_h[i] < 0.01:
+                continue
+            n = int(meta_h[i, 3])
+            lines.append({'score': prob_h[i], 'points': [{'x': xo_h[i, q], 'y': float(yo_h[i, q])} for q in range(n)]})
+        return {'Lines': lines}
 
     @staticmethod
     def visual(imgs, predict_jsons, org_width=1920, min_length=2, filter_vertical=True, filter_thres=65):
