@@ -473,6 +473,16 @@ typedef struct hn_wgrad_desc {
 } hn_wgrad_desc;
 int hn_conv_wgrad(const hn_wgrad_desc* d, void* stream);
 
+/* Detection loss (head_detect/detection_loss.py:111-267 FocalLoss): IoU anchor assignment (< 0.4
+ * negative, >= 0.5 positive, between ignored), focal classification loss (alpha, gamma) and smooth-L1 box loss (beta 1/9) per
+ * image -- cls_loss[b], reg_loss[b] normalised as the reference does -- and the gradients of mean_b(cls_loss) w.r.t. the
+ * classification tensor [B][A][K] and of mean_b(reg_loss) w.r.t. the regression tensor [B][A][4], in three launches.
+ * anchors [A][4] (y1,x1,y2,x2); annotations [B][M][5] (x1,y1,x2,y2,class), class -1 = padding, M <= 64.
+ * workspace: B*A*4 + B*24 + 64 bytes. */
+int hn_det_loss(const float* classification, const float* regression, const float* anchors, const float* annotations, int32_t B, int32_t A,
+                int32_t K, int32_t M, float alpha, float gamma, void* workspace, int64_t workspace_bytes, float* cls_loss, float* reg_loss,
+                float* dcls, float* dreg, void* stream);
+
 /* Adam step over many tensors in one launch (torch.optim.Adam semantics, train.py:147: L2 weight decay added to the
  * gradient, bias-corrected moments).  Tensor table on the device. */
 typedef struct hn_adam_tensor {

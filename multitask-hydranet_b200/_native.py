@@ -206,6 +206,7 @@ SYMBOLS = {
     "hn_se_apply": (C.c_int, [C.POINTER(Mat), _P, _P, C.c_int64, C.POINTER(Mat), _P]),
     "hn_pack_weights": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "hn_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), _P]),
+    "hn_det_loss": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, C.c_int64, _P, _P, _P, _P, _P]),
     "hn_adam_step": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
                                C.c_float, _P, _P]),
     "hn_det_invert_affine": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),

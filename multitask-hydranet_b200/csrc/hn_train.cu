@@ -1370,3 +1370,176 @@ extern "C" int hn_adam_step(const hn_adam_tensor* tensors_device, const int32_t*
     }
     return HN_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Detection loss (reference head_detect/detection_loss.py:111-267, FocalLoss.forward):
+// IoU anchor assignment, focal classification loss and smooth-L1 box loss, forward AND gradient in two launches.
+//   kernel 1 (assign): per (image, anchor) IoU against the image's valid boxes -> best box (first maximum, as torch.max),
+//                      state {ignore, negative, positive + box}, positives counted per image;
+//   kernel 2 (loss):   per (image, anchor) the focal terms of its K classes and, for positives, the smooth-L1 of its 4 offsets;
+//                      per-image sums in double (order-insensitive to ~1e-16) and the gradients w.r.t. classification / regression
+//                      of  mean_b(cls_loss_b)  and  mean_b(reg_loss_b)  written directly.
+// Annotations [B][M][5] = (x1, y1, x2, y2, class), class -1 = padding; anchors [A][4] = (y1, x1, y2, x2).
+// ------------------------------------------------------------------------------------------------
+struct DetLossParams {
+    const float *cls, *reg, *anchors, *ann;
+    int B, A, K, M;
+    float alpha, gamma;
+    int* assign;     // [B][A]: -2 ignore, -1 negative, >= 0 index of the assigned box
+    int* num_pos;    // [B]
+    int* has_box;    // [B]
+    double* sums;    // [B][2]: classification, regression (un-normalised)
+    float *dcls, *dreg;
+    float *cls_loss, *reg_loss;  // [B] per-image losses (normalised as the reference does)
+};
+__global__ void __launch_bounds__(256) hn_det_assign_kernel(const DetLossParams p) {
+    const int b = blockIdx.y;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float s_ann[64 * 5];
+    __shared__ int s_pos;
+    if (threadIdx.x == 0) s_pos = 0;
+    for (int i = threadIdx.x; i < p.M * 5; i += blockDim.x) s_ann[i] = p.ann[(size_t)b * p.M * 5 + i];
+    __syncthreads();
+    int any = 0, positive = 0;
+    if (a < p.A) {
+        const float ay1 = p.anchors[a * 4], ax1 = p.anchors[a * 4 + 1], ay2 = p.anchors[a * 4 + 2], ax2 = p.anchors[a * 4 + 3];
+        const float aarea = __fmul_rn(__fsub_rn(ay2, ay1), __fsub_rn(ax2, ax1));
+        float best = -1.0f;
+        int arg = 0;
+        for (int m = 0; m < p.M; ++m) {
+            const float* g = s_ann + m * 5;
+            if (g[4] == -1.0f) continue;
+            any = 1;
+            const float area = __fmul_rn(__fsub_rn(g[2], g[0]), __fsub_rn(g[3], g[1]));
+            const float iw = fmaxf(__fsub_rn(fminf(ax2, g[2]), fmaxf(ax1, g[0])), 0.0f);
+            const float ih = fmaxf(__fsub_rn(fminf(ay2, g[3]), fmaxf(ay1, g[1])), 0.0f);
+            const float inter = __fmul_rn(iw, ih);
+            const float ua = fmaxf(__fsub_rn(__fadd_rn(aarea, area), inter), 1e-8f);
+            const float iou = __fdiv_rn(inter, ua);
+            if (iou > best) { best = iou; arg = m; }
+        }
+        int st = -1;  // no valid box: every anchor is a negative
+        if (any) st = best >= 0.5f ? arg : (best < 0.4f ? -1 : -2);
+        positive = st >= 0;
+        p.assign[(size_t)b * p.A + a] = st;
+    }
+    if (positive) atomicAdd(&s_pos, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_pos) atomicAdd(p.num_pos + b, s_pos);
+        if (blockIdx.x == 0) {
+            int hb = 0;
+            for (int m = 0; m < p.M; ++m) hb |= s_ann[m * 5 + 4] != -1.0f;
+            p.has_box[b] = hb;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) hn_det_loss_kernel(const DetLossParams p) {
+    const int b = blockIdx.y;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double s_sum[2][8];
+    double lc = 0.0, lr = 0.0;
+    if (a < p.A) {
+        const int st = p.assign[(size_t)b * p.A + a];
+        const int npos = p.num_pos[b];
+        const bool hb = p.has_box[b] != 0;
+        const float cnorm = hb ? 1.0f / fmaxf((float)npos, 1.0f) : 1.0f;  // images without boxes are NOT normalised (detection_loss.py:138-160)
+        const float invB = 1.0f / (float)p.B;
+        const float* c = p.cls + ((size_t)b * p.A + a) * p.K;
+        float* dc = p.dcls + ((size_t)b * p.A + a) * p.K;
+        const float* g = p.ann + ((size_t)b * p.M + (st >= 0 ? st : 0)) * 5;
+        const int tcls = st >= 0 ? (int)g[4] : -1;
+        for (int k = 0; k < p.K; ++k) {
+            float grad = 0.0f;
+            if (st != -2) {
+                const float x = c[k];
+                const float v = fminf(fmaxf(x, 1e-4f), 1.0f - 1e-4f);
+                const bool pass = x >= 1e-4f && x <= 1.0f - 1e-4f;  // clamp passes the gradient inside [min, max]
+                float l, dl;
+                if (k == tcls) {  // target 1: -alpha (1 - v)^gamma log v
+                    const float w = powf(1.0f - v, p.gamma), lg = logf(v);
+                    l = -p.alpha * w * lg;
+                    dl = p.alpha * (p.gamma * powf(1.0f - v, p.gamma - 1.0f) * lg - w / v);
+                } else {          // target 0: -(1 - alpha) v^gamma log(1 - v)
+                    const float w = powf(v, p.gamma), lg = logf(1.0f - v);
+                    l = -(1.0f - p.alpha) * w * lg;
+                    dl = (1.0f - p.alpha) * (-p.gamma * powf(v, p.gamma - 1.0f) * lg + w / (1.0f - v));
+                }
+                lc += (double)l;
+                grad = pass ? dl * cnorm * invB : 0.0f;
+            }
+            dc[k] = grad;
+        }
+        float* dr = p.dreg + ((size_t)b * p.A + a) * 4;
+        if (st >= 0) {
+            const float ay1 = p.anchors[a * 4], ax1 = p.anchors[a * 4 + 1], ay2 = p.anchors[a * 4 + 2], ax2 = p.anchors[a * 4 + 3];
+            const float aw = ax2 - ax1, ah = ay2 - ay1, acx = ax1 + 0.5f * aw, acy = ay1 + 0.5f * ah;
+            float gw = g[2] - g[0], gh = g[3] - g[1];
+            const float gcx = g[0] + 0.5f * gw, gcy = g[1] + 0.5f * gh;
+            gw = fmaxf(gw, 1.0f);
+            gh = fmaxf(gh, 1.0f);
+            const float t[4] = {(gcy - acy) / ah, (gcx - acx) / aw, logf(gh / ah), logf(gw / aw)};  // (dy, dx, dh, dw)
+            const float* r = p.reg + ((size_t)b * p.A + a) * 4;
+            const float rnorm = invB / (4.0f * fmaxf((float)npos, 1.0f));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float d = t[j] - r[j], ad = fabsf(d);
+                float l, dl;  // d/d(diff)
+                if (ad <= 1.0f / 9.0f) { l = 0.5f * 9.0f * ad * ad; dl = 9.0f * ad; }
+                else { l = ad - 0.5f / 9.0f; dl = 1.0f; }
+                lr += (double)l;
+                const float sgn = d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f);
+                dr[j] = -sgn * dl * rnorm;  // d|t - r|/dr = -sign(t - r)
+            }
+        } else {
+            dr[0] = dr[1] = dr[2] = dr[3] = 0.0f;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lc += __shfl_xor_sync(0xffffffffu, lc, o);
+        lr += __shfl_xor_sync(0xffffffffu, lr, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_sum[0][threadIdx.x >> 5] = lc; s_sum[1][threadIdx.x >> 5] = lr; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int w = 0; w < 8; ++w) { a0 += s_sum[0][w]; a1 += s_sum[1][w]; }
+        atomicAdd(p.sums + b * 2, a0);
+        atomicAdd(p.sums + b * 2 + 1, a1);
+    }
+}
+__global__ void hn_det_loss_finish_kernel(const DetLossParams p) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    const int npos = p.num_pos[b];
+    const bool hb = p.has_box[b] != 0;
+    p.cls_loss[b] = hb ? (float)(p.sums[b * 2] / fmax((double)npos, 1.0)) : (float)p.sums[b * 2];
+    p.reg_loss[b] = (hb && npos > 0) ? (float)(p.sums[b * 2 + 1] / (4.0 * (double)npos)) : 0.0f;
+}
+extern "C" int hn_det_loss(const float* classification, const float* regression, const float* anchors, const float* annotations, int32_t B, int32_t A,
+                           int32_t K, int32_t M, float alpha, float gamma, void* workspace, int64_t workspace_bytes, float* cls_loss, float* reg_loss,
+                           float* dcls, float* dreg, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    HN_REQUIRE(classification && regression && anchors && annotations && workspace && cls_loss && reg_loss && dcls && dreg, "det loss: null pointer");
+    HN_REQUIRE(B >= 1 && A >= 1 && K >= 1 && M >= 1 && M <= 64, "det loss: bad sizes (B=%d A=%d K=%d M=%d; at most 64 boxes per image)", B, A, K, M);
+    const size_t need = (size_t)B * A * 4 + (size_t)B * 8 + (size_t)B * 16 + 64;
+    HN_REQUIRE((int64_t)need <= workspace_bytes, "det loss: workspace too small (%zu > %lld)", need, (long long)workspace_bytes);
+    DetLossParams p;
+    p.cls = classification; p.reg = regression; p.anchors = anchors; p.ann = annotations;
+    p.B = B; p.A = A; p.K = K; p.M = M; p.alpha = alpha; p.gamma = gamma;
+    uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
+    p.sums = reinterpret_cast<double*>(w);          w += (size_t)B * 16;
+    p.num_pos = reinterpret_cast<int*>(w);          w += (size_t)B * 4;
+    p.has_box = reinterpret_cast<int*>(w);          w += (size_t)B * 4;
+    p.assign = reinterpret_cast<int*>(w);
+    p.dcls = dcls; p.dreg = dreg; p.cls_loss = cls_loss; p.reg_loss = reg_loss;
+    HN_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)B * 24, stream));
+    dim3 grid((unsigned)hn_cdiv(A, 256), (unsigned)B);
+    hn_det_assign_kernel<<<grid, 256, 0, stream>>>(p);
+    HN_CHECK_CUDA(cudaGetLastError());
+    hn_det_loss_kernel<<<grid, 256, 0, stream>>>(p);
+    HN_CHECK_CUDA(cudaGetLastError());
+    hn_det_loss_finish_kernel<<<hn_cdiv(B, 128), 128, 0, stream>>>(p);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}

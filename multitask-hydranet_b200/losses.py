@@ -83,6 +83,41 @@ def detection_loss(classifications, regressions, anchors, annotations, alpha=0.2
     return cls_loss.mean(dim=0, keepdim=True), reg_loss.mean(dim=0, keepdim=True)
 
 
+class NativeDetectionLoss(torch.autograd.Function):
+    """The detection objective as ONE native op (``hn_det_loss``: assignment, focal + smooth-L1 terms and their gradients in
+    three launches instead of ~60 torch kernels over [B, 76 725, M] intermediates).  Returns (mean_b cls_loss_b, mean_b reg_loss_b),
+    the two scalars ``cal_loss`` puts into the loss dict (model.py:224-235).  Checked against ``detection_loss`` above (which is
+    pinned against the live reference) in tests/test_gpu_train_ops.py."""
+
+    @staticmethod
+    def forward(ctx, classifications, regressions, anchors, annotations, alpha=0.25, gamma=2.0):
+        import ctypes as C
+
+        from . import _native as nv
+        cls = classifications.detach().float().contiguous()
+        reg = regressions.detach().float().contiguous()
+        B, A, K = cls.shape
+        dev = cls.device
+        anc = anchors.detach().to(dev, torch.float32).reshape(-1, 4).contiguous()
+        ann = annotations.detach().to(dev, torch.float32).contiguous()
+        M = ann.shape[1]
+        ws = torch.empty(B * A * 4 + B * 24 + 64, dtype=torch.uint8, device=dev)
+        out = torch.empty((2, B), dtype=torch.float32, device=dev)
+        dcls, dreg = torch.empty_like(cls), torch.empty_like(reg)
+        with torch.cuda.device(dev):
+            nv.check(nv.lib.hn_det_loss(cls.data_ptr(), reg.data_ptr(), anc.data_ptr(), ann.data_ptr(), B, A, K, M, float(alpha), float(gamma),
+                                        ws.data_ptr(), ws.numel(), out[0].data_ptr(), out[1].data_ptr(), dcls.data_ptr(), dreg.data_ptr(),
+                                        torch.cuda.current_stream(dev).cuda_stream))
+        ctx.save_for_backward(dcls, dreg)
+        m = out.mean(dim=1)
+        return m[0], m[1]
+
+    @staticmethod
+    def backward(ctx, g_cls, g_reg):
+        dcls, dreg = ctx.saved_tensors
+        return dcls * g_cls, dreg * g_reg, None, None, None, None
+
+
 def lane_cls_loss(cls_targets, cls_preds, negative_ratio=15, alpha=10):
     t = cls_targets[..., 1].reshape(-1)
     pmask = t > 0
@@ -134,8 +169,11 @@ def cal_loss(model, pred_dict, gt_dict):
                                    sc["use_top_k"], sc["top_k_ratio"], sc["use_focal"])
     if model.train_detect:
         det = pred_dict["detection"]
-        c, r = detection_loss(det["classification"], det["regression"], det["anchors"], gt_dict["gt_det"])
-        out["loss_det_cls"], out["loss_det_reg"] = c.mean(), r.mean()
+        if det["classification"].is_cuda and getattr(model, "native_det_loss", True) and gt_dict["gt_det"].shape[1] <= 64:
+            out["loss_det_cls"], out["loss_det_reg"] = NativeDetectionLoss.apply(det["classification"], det["regression"], det["anchors"], gt_dict["gt_det"])
+        else:
+            c, r = detection_loss(det["classification"], det["regression"], det["anchors"], gt_dict["gt_det"])
+            out["loss_det_cls"], out["loss_det_reg"] = c.mean(), r.mean()
     if model.train_lane:
         lane = pred_dict["lane"]
         dev = lane["predict_cls"].device

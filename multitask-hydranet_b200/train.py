@@ -1132,11 +1132,16 @@ class TrainStep:
     (``graph=False``) pass a ``GradAllReduce`` as ``reducer`` to overlap the bucketed exchange with backward instead.
     """
 
-    def __init__(self, model, optimizer, graph=True, reducer=None, warmup=2, process_group=None):
+    def __init__(self, model, optimizer, graph=True, reducer=None, warmup=2, process_group=None, overlap_exchange=True):
         import torch.distributed as dist
         self.model, self.opt, self.use_graph, self.reducer, self.warmup = model, optimizer, graph, reducer, warmup
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        if self.world > 1 and graph and reducer is None and overlap_exchange and os.environ.get("HN_GRAPH_OVERLAP", "1") != "0":
+            # the bucketed exchange INSIDE the captured step: the hooks fire during the captured backward, so the NCCL kernels
+            # become nodes of the graph on a forked stream and overlap the rest of backward (NCCL collectives are capturable)
+            from .parallel import GradAllReduce
+            self.reducer = GradAllReduce(model.parameters(), process_group=process_group, model=model)
         self.graph = None
         self.static = None
         self.opt_in_graph = False
@@ -1151,10 +1156,12 @@ class TrainStep:
         st = getattr(self.model, "_train_state", None)
         if st is not None:
             join_side_stream(st, x.device)
+        if self.reducer is not None:
+            self.reducer.finish()
         return loss, ld
 
     def _exchange(self):
-        if self.world <= 1:
+        if self.world <= 1 or self.reducer is not None:
             return
         import torch.distributed as dist
         grads = [p.grad for p in self.model.parameters() if p.grad is not None]
@@ -1169,10 +1176,7 @@ class TrainStep:
 
     def _eager(self, x, gt):
         loss, ld = self._fwd_bwd(x, gt)
-        if self.reducer is not None:
-            self.reducer.finish()
-        else:
-            self._exchange()
+        self._exchange()
         self.opt.step()
         self.loss_dict = ld
         return loss.detach()

@@ -355,3 +355,34 @@ def test_fused_adam_matches_torch():
         b.step()
     for p, q in zip(ps, qs):
         assert float((p - q).abs().max()) <= 1e-6 * max(1.0, float(q.abs().max()))
+
+
+def test_native_detection_loss_matches_the_pinned_torch_loss():
+    """hn_det_loss (SURVEY f-3) against losses.detection_loss, which tests/test_cpu_losses.py pins against the live reference:
+    loss values and the gradients w.r.t. classification and regression, incl. an image without boxes and ignored anchors."""
+    import hydranet_b200 as hb
+    from hydranet_b200 import losses
+    from oracle import train_golden
+    torch.manual_seed(0)
+    B, A = 3, 76725
+    gt = train_golden.synthetic_gt(B, 640, 640, 20, 20, 80, seed=5)
+    gt["gt_det"][2, :, 4] = -1
+    ann = gt["gt_det"].cuda()
+    anc = torch.from_numpy(hb.make_anchors((640, 640), 2.0, [8, 16, 32, 64, 128], [2 ** 0, 2 ** 0.333, 2 ** 0.667], [(1.0, 1.0), (1.4, 0.7), (0.7, 1.4)])).cuda()
+    cls0 = torch.sigmoid(torch.randn(B, A, 9, device=DEV) * 3)  # some scores outside the [1e-4, 1 - 1e-4] clamp
+    reg0 = 0.3 * torch.randn(B, A, 4, device=DEV)
+    res = {}
+    for name in ("torch", "native"):
+        cls, reg = cls0.clone().requires_grad_(), reg0.clone().requires_grad_()
+        if name == "torch":
+            c, r = losses.detection_loss(cls, reg, anc, ann)
+            c, r = c.mean(), r.mean()
+        else:
+            c, r = losses.NativeDetectionLoss.apply(cls, reg, anc, ann)
+        (2.0 * c + 50.0 * r).backward()
+        res[name] = (float(c), float(r), cls.grad, reg.grad)
+    a, b = res["native"], res["torch"]
+    assert abs(a[0] - b[0]) <= 2e-6 * abs(b[0]) and abs(a[1] - b[1]) <= 2e-6 * abs(b[1]), (a[:2], b[:2])
+    assert float((a[2] - b[2]).abs().max()) <= 2e-5 * float(b[2].abs().max())
+    assert float((a[3] - b[3]).abs().max()) <= 2e-5 * float(b[3].abs().max())
+    assert float(b[3].abs().max()) > 0 and float(b[2].abs().max()) > 0
