@@ -617,6 +617,8 @@ def run_train(args):
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
+        ts.close()  # the graph may hold captured NCCL kernels: release it before the communicator goes away
+        torch.cuda.synchronize(dev)
         dist.destroy_process_group()
 
 

@@ -1225,6 +1225,16 @@ class TrainStep:
             for gi, t in getattr(self.opt, "_tables", {}).items():
                 t["dyn"][1:2].copy_(pre_dyn[gi][1:2]) if gi in pre_dyn else t["dyn"][1:2].zero_()
 
+    def close(self):
+        """Release the captured graph (and the hooks of an internal reducer).  Call before ``destroy_process_group()`` when the
+        graph holds captured NCCL collectives: the communicator cannot shut down while a live graph still references it."""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
+        if self.reducer is not None:
+            self.reducer.remove()
+
     def __call__(self, x, gt):
         if not self.use_graph:
             return self._eager(x, gt)
