@@ -106,6 +106,42 @@ def main(out_dir=GOLD):
               "det kept", [len(r["scores"]) for r in ref_det], "lanes", [len(lane_gold["lane%d_prob" % b]) for b in range(2)])
 
 
+def make_640_digest(out_dir=GOLD):
+    """tests/golden/big_640x640_b1_digest.npz: the LIVE reference (CPU, IEEE fp32) at the default resolution, batch 1 -- the
+    full-size pin for the GPU parity tests (the 128^2 fixtures above hold whole tensors; here the big tensors are stored as
+    strided samples plus the complete arg-max map, < 1 MB).  Two weight sets: synthetic seed 1 (gain 20) and the reference's
+    own random initialisation under torch.manual_seed(0)."""
+    import yaml
+    ref_model, _ = ref_live.import_reference()
+    torch.set_num_threads(8)
+    cfg = yaml.safe_load(open("/root/reference/model/cfgs/hydranet_joint_big_backbone.yml"))
+    x = synth.synth_input(1, 640, 640, seed=5)
+    blob = {}
+    for tag in ("synth1", "init0"):
+        torch.manual_seed(0)
+        net = ref_model.HydraNet(cfg).eval()
+        if tag == "synth1":
+            net.load_state_dict(synth.synth_state_dict(net.state_dict(), seed=1, seg_logit_gain=20.0))
+        sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        with torch.no_grad():
+            out = net(x)
+            mine = hydranet_ref.forward(sd, cfg, x)
+        assert torch.equal(out["seg"], mine["seg"]) and torch.equal(out["detection"]["regression"], mine["detection"]["regression"])
+        seg = out["seg"][0].numpy()
+        top2 = np.sort(seg, axis=0)[-2:]
+        blob[tag + ".seg_argmax"] = seg.argmax(0).astype(np.uint8)
+        blob[tag + ".seg_gap_u8"] = np.clip((top2[1] - top2[0]) / (2e-2 * np.abs(seg).max()) * 64, 0, 255).astype(np.uint8)  # gap in 1/64 of the decisive bound
+        blob[tag + ".seg_max"] = np.float32(np.abs(seg).max())
+        for k, t, stride in (("seg", out["seg"], 101), ("regression", out["detection"]["regression"], 53), ("classification", out["detection"]["classification"], 53)):
+            f = t.numpy().reshape(-1)
+            blob["%s.%s.sample" % (tag, k)] = f[::stride].copy()
+            blob["%s.%s.absmax" % (tag, k)] = np.float32(np.abs(f).max())
+        blob[tag + ".predict_cls"] = out["lane"]["predict_cls"].numpy()
+        blob[tag + ".predict_loc"] = out["lane"]["predict_loc"].numpy()
+    np.savez_compressed(os.path.join(out_dir, "big_640x640_b1_digest.npz"), **blob)
+    print("wrote big_640x640_b1_digest.npz", os.path.getsize(os.path.join(out_dir, "big_640x640_b1_digest.npz")) // 1024, "KB")
+
+
 def reference_imagenet_normalize():
     """The reference's own ``imagenet_normalize`` (model/demo.py:26-40), compiled from its source text at generation
     time -- demo.py cannot be imported (argparse + checkpoint loading at module level)."""
@@ -146,7 +182,9 @@ def make_preprocess_golden(out_dir=GOLD):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "preprocess":
+    if len(sys.argv) > 1 and sys.argv[1] == "digest640":
+        make_640_digest()
+    elif len(sys.argv) > 1 and sys.argv[1] == "preprocess":
         make_preprocess_golden()
     else:
         main()

@@ -6,12 +6,14 @@ Tolerances (BASELINE.json north_star): head tensors max rel err <= 1e-2 of the t
 (bf16 activations and weights, fp32 accumulate); seg argmax agreement >= 99.9 %.
 
 The two criteria are only jointly satisfiable on pixels whose fp32 top-1/top-2 logit gap exceeds twice
-the logit tolerance: a logit error of eps can flip any pixel with gap < 2 eps.  With the synthetic
-(random, BN-stressed) weights ~0.5 % of the pixels are such near-ties (measured: SURVEY.md appendix B,
-profiles/), so the tests assert
+the logit tolerance: a logit error of eps can flip any pixel with gap < 2 eps.  profiles/r02_seg_argmax_vs_precision.txt
+(tools/precision_study.py) measures the floor: with bf16 storage anywhere in the network -- backbone alone, neck alone,
+seg head alone -- raw agreement is already below 99.9 % (all-bf16: 99.39 % on the synthetic set, 99.65 % on default init;
+even with the seg decoder tail in fp32 99.56 %), so the tests assert
   * >= 99.9 % agreement -- in fact 100 % -- on every pixel whose oracle gap is >= 2e-2 * max|logit|,
   * every disagreeing pixel is a near-tie (gap below that bound), never a gross error,
-  * raw agreement >= 99 % (reported, bf16-limited).
+  * raw agreement at the measured floor (>= 99.2 % synthetic, >= 99.5 % default init).
+The oracle runs in IEEE fp32 (cuDNN / cuBLAS TF32 off: oracle/hydranet_ref.ieee_fp32).
 """
 import os
 
@@ -116,7 +118,7 @@ def test_forward_full_size_vs_oracle_on_gpu(B, H, W):
     with open(os.path.join(OUT, "forward_%dx%dx%d_errors.txt" % (B, H, W)), "w") as f:
         f.write(repr(errs) + " argmax raw=%r decisive=%r decisive_fraction=%r near_ties_only=%r\n" % (raw, dec, frac, near))
     assert max(errs.values()) <= 1e-2, errs
-    assert dec >= 0.999 and near and raw >= 0.99, (raw, dec, near)
+    assert dec >= 0.999 and near and raw >= 0.992, (raw, dec, near)
     assert torch.equal(out["detection"]["anchors"], ref["detection"]["anchors"])
 
 
@@ -287,3 +289,72 @@ def test_fused_postprocess_equals_separate_decoders():
         m_gpu.use_graph = False
         m_gpu.fuse_postprocess()
         m_gpu._plans.clear()
+
+
+# ------------------------------------------------------------------ full size, true fp32, several weight sets
+@pytest.mark.parametrize("tag", ["synth1", "init0"])
+def test_forward_640_against_live_reference_digest(tag):
+    """Native forward at the default resolution against the LIVE reference run on the CPU in IEEE fp32
+    (tests/golden/big_640x640_b1_digest.npz, oracle/make_golden.py digest640): strided samples of the big tensors, the whole
+    lane tensors, the complete arg-max map.  `init0` is the reference's own random initialisation -- the weights bench.py runs."""
+    g = np.load(os.path.join(GOLD, "big_640x640_b1_digest.npz"))
+    cfg = big_cfg(640, 640)
+    torch.manual_seed(0)
+    m = hb.HydraNet(cfg).eval()
+    if tag == "synth1":
+        m.load_state_dict(synth.synth_state_dict(m.state_dict(), seed=1, seg_logit_gain=20.0))
+    m = m.cuda()
+    x = synth.synth_input(1, 640, 640, seed=5).cuda()
+    with torch.no_grad():
+        out = m(x)
+        cls_map = m.seg_class_map()[0].cpu().numpy()
+    for k, t, stride in (("seg", out["seg"], 101), ("regression", out["detection"]["regression"], 53), ("classification", out["detection"]["classification"], 53)):
+        got = t.float().cpu().numpy().reshape(-1)[::stride]
+        err = float(np.abs(got - g["%s.%s.sample" % (tag, k)]).max() / g["%s.%s.absmax" % (tag, k)])
+        assert err <= 1e-2, (tag, k, err)
+    for k in ("predict_cls", "predict_loc"):
+        ref = g["%s.%s" % (tag, k)]
+        err = float(np.abs(out["lane"][k].cpu().numpy() - ref).max() / np.abs(ref).max())
+        assert err <= 1e-2, (tag, k, err)
+    agree = cls_map == g[tag + ".seg_argmax"]
+    decisive = g[tag + ".seg_gap_u8"] >= 64  # fp32 top-1/top-2 gap >= 2e-2 * max|logit|
+    raw, dec = float(agree.mean()), float(agree[decisive].mean())
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "forward_640_digest_%s.txt" % tag), "w") as f:
+        f.write("seg argmax raw %.5f decisive %.5f (decisive fraction %.3f)\n" % (raw, dec, float(decisive.mean())))
+    # floor of bf16 storage (profiles/r02_seg_argmax_vs_precision.txt): 0.9939 synthetic, 0.9965 default init; all flips are near-ties
+    assert dec >= 0.999 and raw >= (0.992 if tag == "synth1" else 0.995), (raw, dec)
+    assert bool((g[tag + ".seg_gap_u8"][~agree] < 64).all())
+
+
+def test_forward_parity_over_weight_sets_report():
+    """Three synthetic seeds + default init at 640x640 against the IEEE-fp32 oracle on the GPU: max-normalised error and the
+    element-wise relative error over |ref| >= 0.1 max|ref|, written to gpurun_out/forward_parity_weight_sets.txt."""
+    cfg = big_cfg(640, 640)
+    x = synth.synth_input(1, 640, 640, seed=5).cuda()
+    rows = []
+    for tag, seed in (("synth", 1), ("synth", 2), ("synth", 3), ("init", 0)):
+        torch.manual_seed(seed)
+        m = hb.HydraNet(cfg).eval()
+        if tag == "synth":
+            m.load_state_dict(synth.synth_state_dict(m.state_dict(), seed=seed, seg_logit_gain=20.0))
+        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        m = m.cuda()
+        with torch.no_grad():
+            out = m(x)
+            ref = hydranet_ref.forward(sd, cfg, x)
+        raw, dec, near, _ = _argmax_report(ref["seg"], m.seg_class_map())
+        for k, a, b in (("seg", ref["seg"], out["seg"]), ("regression", ref["detection"]["regression"], out["detection"]["regression"]),
+                        ("classification", ref["detection"]["classification"], out["detection"]["classification"]),
+                        ("predict_cls", ref["lane"]["predict_cls"], out["lane"]["predict_cls"]), ("predict_loc", ref["lane"]["predict_loc"], out["lane"]["predict_loc"])):
+            big = a.abs() >= 0.1 * a.abs().max()
+            elem = float(((a - b).abs()[big] / a.abs()[big]).max())
+            rows.append((tag, seed, k, _rel(a, b), elem))
+            assert _rel(a, b) <= 1e-2, (tag, seed, k, _rel(a, b))
+        rows.append((tag, seed, "seg argmax raw / decisive", raw, dec))
+        assert dec >= 0.999 and near and raw >= 0.992, (tag, seed, raw, dec)
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "forward_parity_weight_sets.txt"), "w") as f:
+        f.write("%-6s %4s %-28s %12s %14s\n" % ("set", "seed", "tensor", "max/max|ref|", "elem-rel (big)"))
+        for r in rows:
+            f.write("%-6s %4d %-28s %12.5f %14.5f\n" % r)
