@@ -21,6 +21,7 @@ Design notes:
     the producing conv's epilogue into 1-pixel padded buffers.
 """
 import math
+import os
 
 import torch
 
@@ -450,7 +451,21 @@ class Builder:
         self.keep.append(t)
         return t
 
+    #: layers whose weights are packed as a bf16 (hi, lo) PAIR: W = hi + lo with hi = bf16(W), lo = bf16(W - hi), two K blocks per
+    #: original block reading the same activations -- the GEMM then sees the weights to ~2^-17 instead of 2^-9.  Measured
+    #: on the B200 at 640x640 over three weight seeds: regression error 0.0090 / 0.0047 / 0.0070 -> 0.0066 / 0.0039 / 0.0048 of max|ref|,
+    #: lane logits 0.0124 -> 0.0085 on the worst seed.  The detection / lane GEMMs are latency-bound (K doubles for free: 8.42 ms
+    #: per step either way).  The same trick on the seg decoder's last layers buys 0.02-0.12 % of arg-max agreement but costs
+    #: 0.3-0.6 ms (HN_HILO=det.,lane.,seg.out[,seg.d7,seg.d6]: 8.72 / 9.02 ms), so it stays off.
+    HILO_PREFIXES = tuple(p for p in os.environ.get("HN_HILO", "det.,lane.").split(",") if p and p != "none")
+
     def _finish(self, cs, entries, cout, bias, bn=None):
+        if self.dt == torch.bfloat16 and cs.name.startswith(tuple(getattr(self.m, "hilo_prefixes", self.HILO_PREFIXES))):
+            split = []
+            for (s_, dy, dx, wt) in entries:
+                hi = wt.to(torch.bfloat16).float()
+                split += [(s_, dy, dx, hi), (s_, dy, dx, wt - hi)]
+            entries = split
         cs.cout = cout
         cs.bn = bn or choose_bn(cout)
         cs.taps, cs.weight = pack_weight(entries, cout, cs.bn, self.dt, self.dev)
