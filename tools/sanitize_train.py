@@ -1,0 +1,29 @@
+"""One small eager training step (big cfg, 128x128, batch 2: every training kernel, every conv flavour) + Adam, for compute-sanitizer."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+import hydranet_b200 as hb
+from hydranet_b200 import losses
+from hydranet_b200.config import big_cfg
+from oracle import synth, train_golden
+
+cfg = big_cfg(128, 128)
+torch.manual_seed(0)
+m = hb.HydraNet(cfg)
+m.load_state_dict(synth.synth_state_dict(m.state_dict(), seed=1))
+m = m.cuda().train()
+os.environ["HN_SIDE_WGRAD"] = os.environ.get("HN_SIDE_WGRAD", "1")
+opt = hb.FusedAdam(m.parameters(), lr=1e-5, weight_decay=1e-8)
+x = synth.synth_input(2, 128, 128, seed=3).cuda()
+gt = {k: v.cuda() for k, v in train_golden.synthetic_gt(2, 128, 128, 4, 4, 16, seed=5).items()}
+out = m(x)
+c, r = losses.NativeDetectionLoss.apply(out["detection"]["classification"], out["detection"]["regression"], out["detection"]["anchors"], gt["gt_det"])
+loss = out["seg"].square().mean() + c + 50 * r + out["lane"]["predict_loc"].square().mean() + out["lane"]["predict_cls"].square().mean()
+loss.backward()
+opt.step()
+torch.cuda.synchronize()
+print("sanitize_train ok: loss %.4f" % float(loss))
