@@ -241,6 +241,13 @@ int hn_pool_fwd(const hn_pool_desc* d, void* stream);
 int hn_lanefuse_fwd(const hn_lanefuse_desc* d, void* stream);
 int hn_se_pool_fwd(const hn_se_pool_desc* d, void* stream);
 int hn_se_scale_fwd(const hn_se_scale_desc* d, void* stream);
+/* The whole squeeze-excite of a block (anynet.py:39-47,68-69) in ONE launch, for small maps: a cluster of 4 CTAs per image, each
+ * owning a quarter of the channels: pool -> FC1 + ReLU -> FC2 + sigmoid -> x *= gate in place.  Same descriptor as
+ * hn_se_pool_fwd (S > 0 required); `partial` is scratch of at least N*S floats, `pix_per_block` and `counter` are unused.
+ * Outputs: mean, gate, and x scaled in place.  hn_se_fused_supported tells whether a shape qualifies (H*W <= 4096,
+ * C >= 64, the channel slice fits in shared memory). */
+int hn_se_fused_fwd(const hn_se_pool_desc* d, void* stream);
+int hn_se_fused_supported(int32_t H, int32_t W, int32_t C, int32_t S);
 int hn_preprocess_fwd(const hn_preprocess_desc* d, void* stream);
 int hn_seg_argmax(const float* logits, int32_t N, int32_t C, int64_t HW, int64_t* out_i64, uint8_t* out_u8,
                   void* stream);
@@ -276,6 +283,7 @@ int hn_plan_add_pool(hn_plan* p, const hn_pool_desc* d);
 int hn_plan_add_lanefuse(hn_plan* p, const hn_lanefuse_desc* d);
 int hn_plan_add_se_pool(hn_plan* p, const hn_se_pool_desc* d);
 int hn_plan_add_se_scale(hn_plan* p, const hn_se_scale_desc* d);
+int hn_plan_add_se_fused(hn_plan* p, const hn_se_pool_desc* d);
 int hn_plan_add_det(hn_plan* p, const hn_det_desc* d);
 int hn_plan_add_lane(hn_plan* p, const hn_lane_desc* d);
 int hn_plan_size(const hn_plan* p);

@@ -182,6 +182,8 @@ SYMBOLS = {
     "hn_lanefuse_fwd": (C.c_int, [C.POINTER(LaneFuseDesc), _P]),
     "hn_se_pool_fwd": (C.c_int, [C.POINTER(SePoolDesc), _P]),
     "hn_se_scale_fwd": (C.c_int, [C.POINTER(SeScaleDesc), _P]),
+    "hn_se_fused_fwd": (C.c_int, [C.POINTER(SePoolDesc), _P]),
+    "hn_se_fused_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "hn_preprocess_fwd": (C.c_int, [C.POINTER(PreprocessDesc), _P]),
     "hn_seg_argmax": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P]),
     "hn_u8_to_i64": (C.c_int, [_P, _P, C.c_int64, _P]),
@@ -223,6 +225,7 @@ SYMBOLS = {
     "hn_plan_add_lanefuse": (C.c_int, [_P, C.POINTER(LaneFuseDesc)]),
     "hn_plan_add_se_pool": (C.c_int, [_P, C.POINTER(SePoolDesc)]),
     "hn_plan_add_se_scale": (C.c_int, [_P, C.POINTER(SeScaleDesc)]),
+    "hn_plan_add_se_fused": (C.c_int, [_P, C.POINTER(SePoolDesc)]),
     "hn_plan_add_det": (C.c_int, [_P, C.POINTER(DetDesc)]),
     "hn_plan_add_lane": (C.c_int, [_P, C.POINTER(LaneDesc)]),
     "hn_plan_size": (C.c_int, [_P]),

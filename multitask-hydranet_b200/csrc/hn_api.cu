@@ -30,7 +30,7 @@ extern "C" int hn_device_sm_count(void) {
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
-enum OpKind { OP_CONV, OP_STEM, OP_NODE, OP_DW_MULTI, OP_POOL, OP_LANEFUSE, OP_SE_POOL, OP_SE_SCALE, OP_DET, OP_LANE, OP_WAIT };
+enum OpKind { OP_CONV, OP_STEM, OP_NODE, OP_DW_MULTI, OP_POOL, OP_LANEFUSE, OP_SE_POOL, OP_SE_SCALE, OP_SE_FUSED, OP_DET, OP_LANE, OP_WAIT };
 
 struct PlanOp {
     OpKind kind;
@@ -109,6 +109,7 @@ PLAN_ADD(pool, OP_POOL, pool, hn_pool_desc)
 PLAN_ADD(lanefuse, OP_LANEFUSE, lanefuse, hn_lanefuse_desc)
 PLAN_ADD(se_pool, OP_SE_POOL, se_pool, hn_se_pool_desc)
 PLAN_ADD(se_scale, OP_SE_SCALE, se_scale, hn_se_scale_desc)
+PLAN_ADD(se_fused, OP_SE_FUSED, se_pool, hn_se_pool_desc)
 PLAN_ADD(det, OP_DET, det, hn_det_desc)
 PLAN_ADD(lane, OP_LANE, lane, hn_lane_desc)
 
@@ -174,6 +175,7 @@ extern "C" int hn_plan_run_range(hn_plan* p, int first, int last, void* stream) 
             case OP_LANEFUSE: rc = hn_lanefuse_fwd(&o->lanefuse, stream); break;
             case OP_SE_POOL: rc = hn_se_pool_fwd(&o->se_pool, stream); break;
             case OP_SE_SCALE: rc = hn_se_scale_fwd(&o->se_scale, stream); break;
+            case OP_SE_FUSED: rc = hn_se_fused_fwd(&o->se_pool, stream); break;
             case OP_DET: rc = hn_det_decode_nms(&o->det, stream); break;
             case OP_LANE: rc = hn_lane_decode_nms(&o->lane, stream); break;
             case OP_WAIT:

@@ -1,6 +1,8 @@
 // HBM-bound operators of the HydraNet forward: stem, BiFPN fusion node (+depthwise), max-pools,
 // lane multi-scale fuse, squeeze-excite.  All activations are NHWC bf16 views; threads own 8-channel
 // (16-byte) vectors so every global access is a coalesced 128-bit transaction.
+#include <mutex>
+
 #include "hn_ops.h"
 
 // ------------------------------------------------------------------------------------------------
@@ -941,6 +943,209 @@ extern "C" int hn_se_scale_fwd(const hn_se_scale_desc* d, void* stream) {
     HN_REQUIRE(total < 0x7fffffffLL, "se_scale: too many work items for one launch");
     HN_CHECK_CUDA(hn_launch(hn_se_scale_kernel, dim3(hn_cdiv(total, 256)), dim3(256), (size_t)(0), reinterpret_cast<cudaStream_t>(stream), 
         to_view(d->x), reinterpret_cast<const bf16*>(d->scale)));
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+
+// ---- squeeze-excite in ONE launch (small maps): pool + FC1 + FC2 + channel scaling ------------------------------------
+// The two-launch form above ends in a serial tail: ONE block per image pulls both FC weight matrices (stage 4: 2 x 438 KB)
+// through its SM's L2 port, 32 SMs busy and 116 idle, and the scaling is a separate launch behind it.  Here a cluster of
+// kSeCl CTAs serves one image and every CTA owns a slice of the CHANNELS: it pools its channels over all pixels (keeping
+// the slice in shared memory), computes 1/kSeCl of the hidden units, then the gate of its own channels, and scales its
+// slice in place.  The mean and the hidden vector cross the cluster through global memory (release / acquire cluster
+// barriers); every sum runs in a fixed order.  Roundings as in the two-launch form: bf16 mean, bf16 hidden, bf16 gate.
+static constexpr int kSeCl = 4;
+struct SeFusedParams {
+    View x;
+    bf16* mean;     // [N][C]
+    float* hidden;  // [N][S] (bf16-rounded values)
+    SeFc fc;
+    float inv_hw;
+    int cvs;   // 8-channel vectors per CTA (the last CTA of a cluster may own fewer)
+    int uss;   // hidden units per CTA
+    int tile;  // the CTA's slice [HW][cvs] stays in shared memory between pooling and scaling
+};
+
+__global__ void __launch_bounds__(kSeThreads) hn_se_fused_kernel(const __grid_constant__ SeFusedParams p) {
+    hn_pdl_launch_dependents();
+    hn_pdl_wait();
+    extern __shared__ __align__(16) uint8_t se_smem[];
+    const View& x = p.x;
+    const int C = x.C, CV = C >> 3, HW = x.H * x.W, S = p.fc.S;
+    const int r = (int)hn_cluster_ctarank(), n = blockIdx.x / kSeCl;
+    const int cvs = p.cvs, v0 = min(CV, r * cvs), nvs = min(cvs, CV - v0);  // this CTA's vectors [v0, v0 + nvs)
+    const int u0 = min(S, r * p.uss), nu = min(p.uss, S - u0);               // ... and hidden units [u0, u0 + nu)
+    const int lanes = kSeThreads / cvs;
+    float* s_mean = reinterpret_cast<float*>(se_smem);  // [C rounded up to 8]
+    float* s_hid = s_mean + ((C + 7) & ~7);             // [S]
+    float* s_gate = s_hid + S;                          // [cvs * 8]
+    float* s_acc = s_gate + cvs * 8;                    // [lanes][cvs * 8]
+    uint4* s_tile = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(s_acc + lanes * cvs * 8) + 15) & ~uintptr_t(15));
+    {   // the weight rows this CTA will read were last touched a whole step ago: pull them into the L2 while pooling
+        const char* w1p = reinterpret_cast<const char*>(p.fc.w1 + (long long)u0 * C);
+        const char* w2p = reinterpret_cast<const char*>(p.fc.w2 + (long long)v0 * 8 * S);
+        const int l1 = (nu * C * 2 + 127) >> 7, l2 = (nvs * 8 * S * 2 + 127) >> 7;
+        for (int l = threadIdx.x; l < l1 + l2; l += blockDim.x) {
+            const char* q = l < l1 ? w1p + (l << 7) : w2p + ((l - l1) << 7);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        }
+    }
+    // ---- pooling of this CTA's channels ----
+    const int vl = threadIdx.x % cvs, pl = threadIdx.x / cvs;
+    const bool active = vl < nvs && pl < lanes;
+    bf16* base = const_cast<bf16*>(x.ptr) + n * x.sn + (v0 + vl) * 8;
+    {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+        if (active) {
+            int px = pl;
+            for (; px + 3 * lanes < HW; px += 4 * lanes) {  // four independent loads in flight
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int q = px + u * lanes, y = q / x.W, xx = q - y * x.W;
+                    v[u] = *reinterpret_cast<const uint4*>(base + y * x.sy + xx * x.sx);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (p.tile) s_tile[(px + u * lanes) * cvs + vl] = v[u];
+                    const float2 a = hn_unpack_bf16x2(v[u].x), b = hn_unpack_bf16x2(v[u].y), c2 = hn_unpack_bf16x2(v[u].z), d2 = hn_unpack_bf16x2(v[u].w);
+                    acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+                    acc[4] += c2.x; acc[5] += c2.y; acc[6] += d2.x; acc[7] += d2.y;
+                }
+            }
+            for (; px < HW; px += lanes) {
+                const int y = px / x.W, xx = px - y * x.W;
+                const uint4 v = *reinterpret_cast<const uint4*>(base + y * x.sy + xx * x.sx);
+                if (p.tile) s_tile[px * cvs + vl] = v;
+                const float2 a = hn_unpack_bf16x2(v.x), b = hn_unpack_bf16x2(v.y), c2 = hn_unpack_bf16x2(v.z), d2 = hn_unpack_bf16x2(v.w);
+                acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+                acc[4] += c2.x; acc[5] += c2.y; acc[6] += d2.x; acc[7] += d2.y;
+            }
+        }
+        if (pl < lanes) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s_acc[(pl * cvs + vl) * 8 + j] = acc[j];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < nvs * 8; c += blockDim.x) {
+        float a = 0.0f;
+        for (int l = 0; l < lanes; ++l) a += s_acc[l * cvs * 8 + c];  // fixed order: deterministic
+        p.mean[(long long)n * C + v0 * 8 + c] = __float2bfloat16(a * p.inv_hw);
+    }
+    hn_cluster_sync();  // release / acquire: the four slices of the mean are visible to the whole cluster
+    // ---- FC1 + ReLU: this CTA's hidden units ----
+    {
+        const unsigned short* mrow = reinterpret_cast<const unsigned short*>(p.mean + (long long)n * C);
+        for (int c = threadIdx.x; c < C; c += blockDim.x) s_mean[c] = __bfloat162float(__ushort_as_bfloat16(__ldcg(mrow + c)));
+    }
+    __syncthreads();
+    {
+        int T = 1;  // adjacent lanes per hidden unit
+        while (T < 32 && p.uss * T * 2 <= (int)blockDim.x) T *= 2;
+        const int nv = C >> 3, per = (nv + T - 1) / T;
+        for (int s0 = 0; s0 < nu; s0 += blockDim.x / T) {
+            const int srow = s0 + threadIdx.x / T, part = threadIdx.x % T;
+            float acc = 0.0f;
+            if (srow < nu) acc = se_dot(p.fc.w1 + (long long)(u0 + srow) * C, s_mean, min(part * per, nv), min(part * per + per, nv));
+            for (int o = T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (srow < nu && part == 0)
+                p.hidden[(long long)n * S + u0 + srow] = __bfloat162float(__float2bfloat16(fmaxf(acc + p.fc.b1[u0 + srow], 0.0f)));
+        }
+    }
+    hn_cluster_sync();
+    // ---- FC2 + sigmoid: the gate of this CTA's channels ----
+    for (int u = threadIdx.x; u < S; u += blockDim.x) s_hid[u] = __ldcg(p.hidden + (long long)n * S + u);
+    __syncthreads();
+    {
+        const int nch = nvs * 8;
+        int T = 1;
+        while (T < 32 && cvs * 8 * T * 2 <= (int)blockDim.x) T *= 2;
+        const int nv = S >> 3, per = (nv + T - 1) / T;
+        for (int c0 = 0; c0 < nch; c0 += blockDim.x / T) {
+            const int cl = c0 + threadIdx.x / T, part = threadIdx.x % T;
+            float acc = 0.0f;
+            if (cl < nch) acc = se_dot(p.fc.w2 + (long long)(v0 * 8 + cl) * S, s_hid, min(part * per, nv), min(part * per + per, nv));
+            for (int o = T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (cl < nch && part == 0) {
+                const bf16 g = __float2bfloat16(1.0f / (1.0f + expf(-(acc + p.fc.b2[v0 * 8 + cl]))));
+                p.fc.gate[(long long)n * C + v0 * 8 + cl] = g;
+                s_gate[cl] = __bfloat162float(g);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- x *= gate, in place ----
+    if (active) {
+        float g[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = s_gate[vl * 8 + j];
+        for (int px = pl; px < HW; px += lanes) {
+            const int y = px / x.W, xx = px - y * x.W;
+            bf16* dst = base + y * x.sy + xx * x.sx;
+            const uint4 v = p.tile ? s_tile[px * cvs + vl] : *reinterpret_cast<const uint4*>(dst);
+            const float2 a = hn_unpack_bf16x2(v.x), b = hn_unpack_bf16x2(v.y), c2 = hn_unpack_bf16x2(v.z), d2 = hn_unpack_bf16x2(v.w);
+            const float f[8] = {a.x * g[0], a.y * g[1], b.x * g[2], b.y * g[3], c2.x * g[4], c2.y * g[5], d2.x * g[6], d2.y * g[7]};
+            store8(dst, f);
+        }
+    }
+}
+
+static constexpr size_t kSeFusedMaxSmem = 200 * 1024;
+// shared-memory bytes of the fused launch; *tile = whether the channel slice fits next to the vectors
+static size_t se_fused_smem(int HW, int C, int S, int* tile) {
+    const int CV = C / 8, cvs = hn_cdiv(CV, kSeCl), lanes = kSeThreads / cvs;
+    const size_t vec = (size_t)(((C + 7) & ~7) + S + cvs * 8 + lanes * cvs * 8) * sizeof(float) + 16;
+    const size_t t = (size_t)HW * cvs * 16;
+    *tile = vec + t <= kSeFusedMaxSmem;
+    return vec + (*tile ? t : 0);
+}
+extern "C" int hn_se_fused_supported(int H, int W, int C, int S) {
+    if (H <= 0 || W <= 0 || C % 8 != 0 || S <= 0 || S % 8 != 0) return 0;
+    const int CV = C / 8, cvs = hn_cdiv(CV, kSeCl);
+    if (CV < 2 * kSeCl || cvs > 64) return 0;           // every CTA of the cluster needs channels of its own
+    if ((long long)H * W > 4096) return 0;              // larger maps: many blocks per image (hn_se_pool_fwd)
+    int tile;
+    return se_fused_smem(H * W, C, S, &tile) <= kSeFusedMaxSmem;
+}
+extern "C" int hn_se_fused_fwd(const hn_se_pool_desc* d, void* stream) {
+    HN_REQUIRE(d && d->partial && d->mean && d->gate && d->w1 && d->b1 && d->w2 && d->b2, "se_fused: bad descriptor");
+    if (int rc = check_view(d->x, "se_fused.x")) return rc;
+    HN_REQUIRE(hn_se_fused_supported(d->x.H, d->x.W, d->x.C, d->S), "se_fused: unsupported shape %dx%dx%d, S=%d", d->x.H, d->x.W, d->x.C, d->S);
+    HN_REQUIRE(((reinterpret_cast<uintptr_t>(d->w1) | reinterpret_cast<uintptr_t>(d->w2)) & 15) == 0, "se_fused: FC weights must be 16-byte aligned");
+    SeFusedParams p;
+    memset(&p, 0, sizeof(p));
+    p.x = to_view(d->x);
+    p.mean = reinterpret_cast<bf16*>(d->mean);
+    p.hidden = d->partial;  // scratch of at least N*S floats (S <= C)
+    p.fc.S = d->S;
+    p.fc.w1 = reinterpret_cast<const bf16*>(d->w1); p.fc.b1 = d->b1;
+    p.fc.w2 = reinterpret_cast<const bf16*>(d->w2); p.fc.b2 = d->b2;
+    p.fc.gate = reinterpret_cast<bf16*>(d->gate);
+    p.inv_hw = 1.0f / (float)(d->x.H * d->x.W);
+    p.cvs = hn_cdiv(d->x.C / 8, kSeCl);
+    p.uss = hn_cdiv(d->S, kSeCl);
+    const size_t smem = se_fused_smem(d->x.H * d->x.W, d->x.C, d->S, &p.tile);
+    static std::once_flag once;
+    static cudaError_t attr_rc = cudaSuccess;
+    std::call_once(once, [] { attr_rc = cudaFuncSetAttribute(hn_se_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeFusedMaxSmem); });
+    HN_CHECK_CUDA(attr_rc);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(d->x.N * kSeCl);
+    cfg.blockDim = dim3(kSeThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kSeCl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_hn_pdl ? 2 : 1;
+    HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, hn_se_fused_kernel, p));
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }

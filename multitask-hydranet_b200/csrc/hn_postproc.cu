@@ -933,7 +933,12 @@ extern "C" int hn_det_decode_nms(const hn_det_desc* d, void* stream) {
         cub::DoubleBuffer<uint32_t> dk(ws.ckey, ws.ckey_alt);
         cub::DoubleBuffer<int> dv(ws.cval, ws.cval_alt);
         size_t tb = ws.cub2_bytes;
-        HN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub2_tmp, tb, dk, dv, (int)NA, 0, 32, s));
+        // key = segment * kCellStride + cell: only the bits a valid key can have set are sorted (batch 32: 24 bits = 3 passes
+        // instead of 4); the all-ones key of a non-candidate reads as (a segment >= the last one, cell 32767 > any real cell)
+        // in those bits and still lands behind every valid key
+        int seg_bits = 1;
+        while ((1 << seg_bits) < d->N * kMaxCls) ++seg_bits;
+        HN_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub2_tmp, tb, dk, dv, (int)NA, 0, 15 + seg_bits, s));
         ws.ckey = dk.Current(); ws.ckey_alt = dk.Alternate();
         ws.cval = dv.Current(); ws.cval_alt = dv.Alternate();
         hn_nms2_cells_kernel<<<hn_cdiv(NA, 256), 256, 0, s>>>(ws, NA);

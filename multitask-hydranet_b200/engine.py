@@ -27,6 +27,9 @@ import torch
 
 from . import _native as nv
 
+#: squeeze-excite of the small maps (stages 2-4) as ONE cluster launch per block instead of pool+FC -> scale (HN_SE_FUSED=0: off)
+SE_FUSED = os.environ.get("HN_SE_FUSED", "1") != "0"
+
 
 # ------------------------------------------------------------------------------------------------
 # views and buffers
@@ -272,6 +275,14 @@ class SePoolSpec:
 
     def add_to(self, plan):
         nv.check(nv.lib.hn_plan_add_se_pool(plan, self.to_desc()))
+
+
+class SeFusedSpec(SePoolSpec):
+    """The whole squeeze-excite of a block in one launch (hn_se_fused_fwd): pool, both FC layers and the in-place scaling."""
+    kind = "se_fused"
+
+    def add_to(self, plan):
+        nv.check(nv.lib.hn_plan_add_se_fused(plan, self.to_desc()))
 
 
 class DetPostSpec:
@@ -582,6 +593,9 @@ class Builder:
         # pool -> FC1 + ReLU -> FC2 + sigmoid in ONE launch: the block that finishes an image's pooling runs its FCs
         fc = dict(S=Sp, w1=w1.to(self.dt).contiguous().to(dev), b1=b1.to(dev), w2=w2.to(self.dt).contiguous().to(dev),
                   b2=se[3].bias.detach().float().contiguous().to(dev), gate=scale)
+        if SE_FUSED and nv.lib.hn_se_fused_supported(g.H, g.W, C, Sp):  # small maps: one cluster launch per block
+            self.ops.append(SeFusedSpec(name, g.interior(), pix, partial, counter, mean, fc))
+            return
         self.ops.append(SePoolSpec(name + ".gate", g.interior(), pix, partial, counter, mean, fc))
         self.ops.append(SeScaleSpec(name + ".scale", g.interior(), scale))
 

@@ -20,7 +20,7 @@ def _tensors_in(op):
         return [op.vin.t]
     if op.kind == "lanefuse":
         return [op.p3.t, op.p4.t, op.p5.t, op.p6.t]
-    if op.kind == "se_pool":
+    if op.kind in ("se_pool", "se_fused"):
         return [op.x.t]
     if op.kind == "se_scale":
         return [op.x.t, op.scale]
@@ -44,6 +44,8 @@ def _tensors_out(op):
         return [op.mean] + ([op.fc["gate"]] if op.fc is not None else [])
     if op.kind == "se_scale":
         return [op.x.t]
+    if op.kind == "se_fused":
+        return [op.mean, op.fc["gate"], op.x.t]
     if op.kind == "stem":
         return [op.out.t]
     raise KeyError(op.kind)

@@ -358,3 +358,60 @@ def test_forward_parity_over_weight_sets_report():
         f.write("%-6s %4s %-28s %12s %14s\n" % ("set", "seed", "tensor", "max/max|ref|", "elem-rel (big)"))
         for r in rows:
             f.write("%-6s %4d %-28s %12.5f %14.5f\n" % r)
+
+
+@pytest.mark.parametrize("B,H,W,C,S", [(32, 10, 10, 936, 234), (3, 20, 20, 376, 94), (2, 40, 40, 152, 38), (5, 4, 4, 936, 234),
+                                       (1, 7, 13, 64, 16), (2, 64, 64, 64, 16)])
+def test_se_fused_launch_equals_pool_fc_scale(B, H, W, C, S):
+    """hn_se_fused_fwd (one cluster launch: pool + FC1 + FC2 + scale) against the two-launch form hn_se_pool_fwd ->
+    hn_se_scale_fwd and against fp32 torch, on a haloed buffer (strided view) with an odd batch and ragged channel slices."""
+    from hydranet_b200 import _native as nv
+    from hydranet_b200.engine import Buf
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(H * 1000 + C)
+    Sp = (S + 7) // 8 * 8
+    assert nv.lib.hn_se_fused_supported(H, W, C, Sp) == 1
+    x0 = torch.randn((B, H, W, C), generator=g).mul_(torch.rand((1, 1, 1, C), generator=g) + 0.5).add_(0.3).relu_()
+    w1 = torch.zeros((Sp, C)); w1[:S] = torch.randn((S, C), generator=g) / C ** 0.5
+    b1 = torch.zeros((Sp,)); b1[:S] = torch.randn((S,), generator=g) * 0.1
+    w2 = torch.zeros((C, Sp)); w2[:, :S] = torch.randn((C, S), generator=g) / S ** 0.5
+    b2 = torch.randn((C,), generator=g) * 0.5
+    w1d, w2d = w1.to(torch.bfloat16).to(dev), w2.to(torch.bfloat16).to(dev)
+    b1d, b2d = b1.to(dev), b2.to(dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    res = {}
+    for mode in ("two", "fused"):
+        buf = Buf(dev, torch.bfloat16, B, H, W, C, pad=1)
+        v = buf.interior()
+        v.torch_view().copy_(x0.to(dev))
+        pix = 128
+        partial = torch.zeros((B, (H * W + pix - 1) // pix, C), dtype=torch.float32, device=dev)
+        counter = torch.zeros((B,), dtype=torch.int32, device=dev)
+        mean = torch.zeros((B, C), dtype=torch.bfloat16, device=dev)
+        gate = torch.zeros((B, C), dtype=torch.bfloat16, device=dev)
+        d = nv.SePoolDesc(v.to_c(), pix, partial.data_ptr(), counter.data_ptr(), mean.data_ptr())
+        d.S, d.w1, d.b1, d.w2, d.b2, d.gate = Sp, w1d.data_ptr(), b1d.data_ptr(), w2d.data_ptr(), b2d.data_ptr(), gate.data_ptr()
+        if mode == "two":
+            nv.check(nv.lib.hn_se_pool_fwd(d, stream))
+            nv.check(nv.lib.hn_se_scale_fwd(nv.SeScaleDesc(v.to_c(), gate.data_ptr()), stream))
+        else:
+            nv.check(nv.lib.hn_se_fused_fwd(d, stream))
+        torch.cuda.synchronize()
+        halo = buf.t.clone()
+        halo[:, 1:-1, 1:-1] = 0
+        assert float(halo.abs().max()) == 0.0, "the halo of the buffer was written"
+        res[mode] = (mean.float().cpu(), gate.float().cpu(), v.torch_view().float().cpu())
+    xb = x0.to(torch.bfloat16).float()
+    m_ref = xb.mean(dim=(1, 2))
+    h_ref = torch.relu(m_ref.to(torch.bfloat16).float() @ w1d.float().cpu().t() + b1)
+    g_ref = torch.sigmoid(h_ref.to(torch.bfloat16).float() @ w2d.float().cpu().t() + b2)
+    y_ref = xb * g_ref[:, None, None, :]
+    for mode in ("two", "fused"):
+        mean, gate, y = res[mode]
+        assert float((mean - m_ref).abs().max()) <= 2 ** -8 * float(m_ref.abs().max()) + 1e-6, mode
+        assert float((gate - g_ref).abs().max()) <= 1e-2, mode  # a 1-ulp flip of a bf16 mean / hidden value moves the gate by < 1e-2
+        assert float((y - y_ref).abs().max()) <= 2e-2 * float(y_ref.abs().max()), mode
+    # the two forms differ only in the order of their fp32 sums: at most a bf16 ulp here and there
+    assert float((res["two"][0] - res["fused"][0]).abs().max()) <= 2 ** -7 * float(m_ref.abs().max())
+    assert float((res["two"][1] - res["fused"][1]).abs().max()) <= 2 ** -6
+    assert float((res["two"][2] - res["fused"][2]).abs().max()) <= 2 ** -6 * float(y_ref.abs().max())
