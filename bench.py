@@ -370,7 +370,7 @@ def run_native(args):
                 return sum(vbytes(v) for v in op.ins) + sum(vbytes(v) for v in op.outs)
             if op.kind == "se_pool":
                 return vbytes(op.x)
-            if op.kind in ("se_scale", "se_fused"):
+            if op.kind in ("se_scale", "se_fused", "gconv_se"):
                 return 2 * vbytes(op.x)
             if op.kind == "lanefuse":
                 return sum(vbytes(v) for v in (op.p3, op.p4, op.p5, op.p6, op.out))

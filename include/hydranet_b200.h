@@ -175,6 +175,18 @@ typedef struct hn_se_scale_desc {
     const void* scale;
 } hn_se_scale_desc;
 
+/* An XBlock's grouped 3x3 convolution (group width 8, stride 1, BN folded, ReLU; anynet.py:60-66) and its squeeze-excite
+ * (anynet.py:39-47,68-69) in ONE launch for small maps (hn_gconv_se_supported): a cluster of 4 CTAs per image, each owning a
+ * quarter of the groups; the 3x3 runs as warp-level tensor-core MMAs out of shared memory, the result is pooled, gated and
+ * scaled before it is written to se.x.  `weight`: bf16 [C/8][10][8 out][8 in] (tap = ky*3+kx, the 10th tap zero);
+ * `bias`: fp32 [C].  `in` and se.x have the same shape and must not alias. */
+typedef struct hn_gconv_se_desc {
+    hn_view in;
+    const void* weight;
+    const float* bias;
+    hn_se_pool_desc se;
+} hn_gconv_se_desc;
+
 /* Image pre-processing, the step in front of HydraNet.forward (model/demo.py:191-196 with imagenet_normalize
  * demo.py:26-40; C++ twin deploy/hydranet_model.cpp:159-248): BGR -> RGB, cv2.resize (uint8 INTER_LINEAR in OpenCV's
  * 11-bit fixed point; INTER_AREA for an exact 2x2 down-scale), (x/255 - mean)/std in float64 rounded to fp32,
@@ -248,6 +260,11 @@ int hn_se_scale_fwd(const hn_se_scale_desc* d, void* stream);
  * C >= 64, the channel slice fits in shared memory). */
 int hn_se_fused_fwd(const hn_se_pool_desc* d, void* stream);
 int hn_se_fused_supported(int32_t H, int32_t W, int32_t C, int32_t S);
+int hn_gconv_se_fwd(const hn_gconv_se_desc* d, void* stream);
+int hn_gconv_se_supported(int32_t H, int32_t W, int32_t C, int32_t S);
+/* profiling aid: device buffer of 8 int64 globaltimer stamps per CTA (N * 4 CTAs) written at the phase boundaries of the two
+ * fused launches above (start, operands staged, conv done, pooled, cluster barrier 1, FC1 + barrier 2, gate done, end); NULL = off */
+void hn_se_fused_set_debug(long long* buf);
 int hn_preprocess_fwd(const hn_preprocess_desc* d, void* stream);
 int hn_seg_argmax(const float* logits, int32_t N, int32_t C, int64_t HW, int64_t* out_i64, uint8_t* out_u8,
                   void* stream);
@@ -284,6 +301,7 @@ int hn_plan_add_lanefuse(hn_plan* p, const hn_lanefuse_desc* d);
 int hn_plan_add_se_pool(hn_plan* p, const hn_se_pool_desc* d);
 int hn_plan_add_se_scale(hn_plan* p, const hn_se_scale_desc* d);
 int hn_plan_add_se_fused(hn_plan* p, const hn_se_pool_desc* d);
+int hn_plan_add_gconv_se(hn_plan* p, const hn_gconv_se_desc* d);
 int hn_plan_add_det(hn_plan* p, const hn_det_desc* d);
 int hn_plan_add_lane(hn_plan* p, const hn_lane_desc* d);
 int hn_plan_size(const hn_plan* p);

@@ -75,6 +75,10 @@ class SePoolDesc(C.Structure):
                 ("S", C.c_int32), ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("gate", C.c_void_p)]
 
 
+class GconvSeDesc(C.Structure):
+    _fields_ = [("vin", View), ("weight", C.c_void_p), ("bias", C.c_void_p), ("se", SePoolDesc)]
+
+
 class SeScaleDesc(C.Structure):
     _fields_ = [("x", View), ("scale", C.c_void_p)]
 
@@ -184,6 +188,9 @@ SYMBOLS = {
     "hn_se_scale_fwd": (C.c_int, [C.POINTER(SeScaleDesc), _P]),
     "hn_se_fused_fwd": (C.c_int, [C.POINTER(SePoolDesc), _P]),
     "hn_se_fused_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "hn_gconv_se_fwd": (C.c_int, [C.POINTER(GconvSeDesc), _P]),
+    "hn_gconv_se_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "hn_se_fused_set_debug": (None, [_P]),
     "hn_preprocess_fwd": (C.c_int, [C.POINTER(PreprocessDesc), _P]),
     "hn_seg_argmax": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P]),
     "hn_u8_to_i64": (C.c_int, [_P, _P, C.c_int64, _P]),
@@ -226,6 +233,7 @@ SYMBOLS = {
     "hn_plan_add_se_pool": (C.c_int, [_P, C.POINTER(SePoolDesc)]),
     "hn_plan_add_se_scale": (C.c_int, [_P, C.POINTER(SeScaleDesc)]),
     "hn_plan_add_se_fused": (C.c_int, [_P, C.POINTER(SePoolDesc)]),
+    "hn_plan_add_gconv_se": (C.c_int, [_P, C.POINTER(GconvSeDesc)]),
     "hn_plan_add_det": (C.c_int, [_P, C.POINTER(DetDesc)]),
     "hn_plan_add_lane": (C.c_int, [_P, C.POINTER(LaneDesc)]),
     "hn_plan_size": (C.c_int, [_P]),

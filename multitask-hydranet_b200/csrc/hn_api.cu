@@ -30,7 +30,7 @@ extern "C" int hn_device_sm_count(void) {
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
-enum OpKind { OP_CONV, OP_STEM, OP_NODE, OP_DW_MULTI, OP_POOL, OP_LANEFUSE, OP_SE_POOL, OP_SE_SCALE, OP_SE_FUSED, OP_DET, OP_LANE, OP_WAIT };
+enum OpKind { OP_CONV, OP_STEM, OP_NODE, OP_DW_MULTI, OP_POOL, OP_LANEFUSE, OP_SE_POOL, OP_SE_SCALE, OP_SE_FUSED, OP_GCONV_SE, OP_DET, OP_LANE, OP_WAIT };
 
 struct PlanOp {
     OpKind kind;
@@ -43,6 +43,7 @@ struct PlanOp {
     hn_lanefuse_desc lanefuse;
     hn_se_pool_desc se_pool;
     hn_se_scale_desc se_scale;
+    hn_gconv_se_desc gconv_se;
     hn_det_desc det;
     hn_lane_desc lane;
     int wait_branch = 0;  // OP_WAIT: the branch whose completion this branch waits for here
@@ -110,6 +111,7 @@ PLAN_ADD(lanefuse, OP_LANEFUSE, lanefuse, hn_lanefuse_desc)
 PLAN_ADD(se_pool, OP_SE_POOL, se_pool, hn_se_pool_desc)
 PLAN_ADD(se_scale, OP_SE_SCALE, se_scale, hn_se_scale_desc)
 PLAN_ADD(se_fused, OP_SE_FUSED, se_pool, hn_se_pool_desc)
+PLAN_ADD(gconv_se, OP_GCONV_SE, gconv_se, hn_gconv_se_desc)
 PLAN_ADD(det, OP_DET, det, hn_det_desc)
 PLAN_ADD(lane, OP_LANE, lane, hn_lane_desc)
 
@@ -176,6 +178,7 @@ extern "C" int hn_plan_run_range(hn_plan* p, int first, int last, void* stream) 
             case OP_SE_POOL: rc = hn_se_pool_fwd(&o->se_pool, stream); break;
             case OP_SE_SCALE: rc = hn_se_scale_fwd(&o->se_scale, stream); break;
             case OP_SE_FUSED: rc = hn_se_fused_fwd(&o->se_pool, stream); break;
+            case OP_GCONV_SE: rc = hn_gconv_se_fwd(&o->gconv_se, stream); break;
             case OP_DET: rc = hn_det_decode_nms(&o->det, stream); break;
             case OP_LANE: rc = hn_lane_decode_nms(&o->lane, stream); break;
             case OP_WAIT:

@@ -947,16 +947,28 @@ extern "C" int hn_se_scale_fwd(const hn_se_scale_desc* d, void* stream) {
     return HN_OK;
 }
 
-// ---- squeeze-excite in ONE launch (small maps): pool + FC1 + FC2 + channel scaling ------------------------------------
+// ---- squeeze-excite in ONE launch (small maps): [grouped 3x3 +] pool + FC1 + FC2 + channel scaling -------------------
 // The two-launch form above ends in a serial tail: ONE block per image pulls both FC weight matrices (stage 4: 2 x 438 KB)
 // through its SM's L2 port, 32 SMs busy and 116 idle, and the scaling is a separate launch behind it.  Here a cluster of
 // kSeCl CTAs serves one image and every CTA owns a slice of the CHANNELS: it pools its channels over all pixels (keeping
 // the slice in shared memory), computes 1/kSeCl of the hidden units, then the gate of its own channels, and scales its
 // slice in place.  The mean and the hidden vector cross the cluster through global memory (release / acquire cluster
 // barriers); every sum runs in a fixed order.  Roundings as in the two-launch form: bf16 mean, bf16 hidden, bf16 gate.
+//
+// kConv: the block's grouped 3x3 convolution (group width 8, stride 1, folded BN + ReLU; anynet.py:60-66) runs in front, in
+// the same launch: a group is exactly one 8-channel vector, so a channel slice is self-contained.  The CTA loads its slice
+// of the 1x1 conv's output into shared memory and runs the 3x3 as warp-level mma.sync m16n8k16 (M = 16 pixels, N = the
+// group's 8 output channels, K = 2 taps x 8 input channels; 5 k-steps, the 10th tap is zero) -- at 13-21 MFLOP per image
+// this conv was a 22-27 us launch of the big GEMM kernel for ~1 us of math.  The result never leaves the SM before it is
+// pooled, gated and scaled.
 static constexpr int kSeCl = 4;
+static constexpr int kGwTaps = 10;                    // 9 taps padded to an even count
+static constexpr int kGwGroupElems = kGwTaps * 64;    // packed weights of one group: [tap][oc][ic] bf16
 struct SeFusedParams {
-    View x;
+    View x;         // the tensor that is pooled and scaled in place (kConv: the conv's output)
+    View in;        // kConv: the conv's input
+    const bf16* wg; // kConv: [C/8][10][8 oc][8 ic]
+    const float* cbias;  // kConv: [C]
     bf16* mean;     // [N][C]
     float* hidden;  // [N][S] (bf16-rounded values)
     SeFc fc;
@@ -964,11 +976,28 @@ struct SeFusedParams {
     int cvs;   // 8-channel vectors per CTA (the last CTA of a cluster may own fewer)
     int uss;   // hidden units per CTA
     int tile;  // the CTA's slice [HW][cvs] stays in shared memory between pooling and scaling
+    long long* dbg;  // optional [CTA][8] globaltimer stamps at the phase boundaries (hn_se_fused_set_debug)
 };
 
+__device__ __forceinline__ void hn_mma_m16n8k16_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void se_stamp(const SeFusedParams& p, int k) {
+    if (p.dbg && threadIdx.x == 0) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.dbg[(long long)blockIdx.x * 8 + k] = t;
+    }
+}
+
+template <bool kConv>
 __global__ void __launch_bounds__(kSeThreads) hn_se_fused_kernel(const __grid_constant__ SeFusedParams p) {
     hn_pdl_launch_dependents();
     hn_pdl_wait();
+    se_stamp(p, 0);
     extern __shared__ __align__(16) uint8_t se_smem[];
     const View& x = p.x;
     const int C = x.C, CV = C >> 3, HW = x.H * x.W, S = p.fc.S;
@@ -976,11 +1005,12 @@ __global__ void __launch_bounds__(kSeThreads) hn_se_fused_kernel(const __grid_co
     const int cvs = p.cvs, v0 = min(CV, r * cvs), nvs = min(cvs, CV - v0);  // this CTA's vectors [v0, v0 + nvs)
     const int u0 = min(S, r * p.uss), nu = min(p.uss, S - u0);               // ... and hidden units [u0, u0 + nu)
     const int lanes = kSeThreads / cvs;
+    const int pv = kConv ? (cvs | 1) : cvs;  // row pitch of the shared-memory tiles in 16-byte vectors (conv: odd, see below)
     float* s_mean = reinterpret_cast<float*>(se_smem);  // [C rounded up to 8]
     float* s_hid = s_mean + ((C + 7) & ~7);             // [S]
     float* s_gate = s_hid + S;                          // [cvs * 8]
     float* s_acc = s_gate + cvs * 8;                    // [lanes][cvs * 8]
-    uint4* s_tile = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(s_acc + lanes * cvs * 8) + 15) & ~uintptr_t(15));
+    uint4* s_tile = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(s_acc + lanes * cvs * 8) + 15) & ~uintptr_t(15));  // [HW][pv]
     {   // the weight rows this CTA will read were last touched a whole step ago: pull them into the L2 while pooling
         const char* w1p = reinterpret_cast<const char*>(p.fc.w1 + (long long)u0 * C);
         const char* w2p = reinterpret_cast<const char*>(p.fc.w2 + (long long)v0 * 8 * S);
@@ -990,10 +1020,97 @@ __global__ void __launch_bounds__(kSeThreads) hn_se_fused_kernel(const __grid_co
             asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
         }
     }
-    // ---- pooling of this CTA's channels ----
     const int vl = threadIdx.x % cvs, pl = threadIdx.x / cvs;
     const bool active = vl < nvs && pl < lanes;
     bf16* base = const_cast<bf16*>(x.ptr) + n * x.sn + (v0 + vl) * 8;
+    if constexpr (kConv) {
+        // ---- grouped 3x3 of this CTA's groups: input slice and weights into shared memory, mma.sync, result into s_tile ----
+        uint4* s_in = s_tile + HW * pv;                                     // [HW][pv]
+        uint32_t* s_w = reinterpret_cast<uint32_t*>(s_in + HW * pv);        // [nvs][10][8 oc][4 ic pairs]
+        uint4* s_zero = reinterpret_cast<uint4*>(s_w + cvs * (kGwGroupElems / 2));  // one zero vector: what a padding tap reads
+        float* s_cb = reinterpret_cast<float*>(s_zero + 1);                 // [nvs * 8] conv bias of the slice
+        if (threadIdx.x == 0) *s_zero = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = threadIdx.x; i < nvs * 8; i += blockDim.x) s_cb[i] = p.cbias[v0 * 8 + i];
+        if (active) {
+            const bf16* ib = p.in.ptr + n * p.in.sn + (v0 + vl) * 8;
+            for (int px = pl; px < HW; px += 8 * lanes) {  // eight independent loads in flight (a load-store loop would serialise them)
+                uint4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int q = px + u * lanes, y = q / x.W, xx = q - y * x.W;
+                    if (q < HW) v[u] = *reinterpret_cast<const uint4*>(ib + y * p.in.sy + xx * p.in.sx);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (px + u * lanes < HW) s_in[(px + u * lanes) * pv + vl] = v[u];
+            }
+        }
+        {
+            const uint4* wsrc = reinterpret_cast<const uint4*>(p.wg + (long long)v0 * kGwGroupElems);
+            uint4* wdst = reinterpret_cast<uint4*>(s_w);
+            for (int i = threadIdx.x; i < nvs * (kGwGroupElems / 8); i += blockDim.x) wdst[i] = __ldg(wsrc + i);
+        }
+        __syncthreads();
+        se_stamp(p, 1);
+        // Work item = (16-pixel m tile, group), m-tile-major; a warp takes a contiguous run.  The A fragment of a k-step (two taps x 8 channels) is ONE ldmatrix.x4: a
+        // matrix row is a pixel's 16-byte group vector, lane l supplies the address of pixel (l & 15) of the tile at tap
+        // 2j + (l >> 4); the odd row pitch keeps the eight rows of a matrix in different bank groups.
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tq = lane & 3;
+        const int nwarps = kSeThreads / 32, MT = (HW + 15) >> 4;
+        const int npair = MT * nvs, per = (npair + nwarps - 1) / nwarps;
+        const int q0 = warp * per, q1 = min(npair, q0 + per);
+        const int W = x.W, H = x.H;
+        const int row_bytes = pv * 16;
+        const uint32_t in_s = hn_smem_u32(s_in), zero_s = hn_smem_u32(s_zero);
+        uint8_t* out_b = reinterpret_cast<uint8_t*>(s_tile) + tq * 4;
+        const int lrow = lane & 15, ltap = lane >> 4;
+        // This loop is bound by instruction issue (16 warps of integer address arithmetic around 5 MMAs), not by the tensor
+        // pipe: items run m-tile-major so the five tap offsets of a lane are computed once per m tile and shared by its groups.
+        int cur_mt = -1;
+        int aoff[kGwTaps / 2];  // byte offset (within a row's first group) of this lane's ldmatrix row per k-step, -1 = padding
+        int mt = q0 / nvs, g = q0 - mt * nvs;
+        for (int q = q0; q < q1; ++q, ++g) {
+            if (g == nvs) { g = 0; ++mt; }
+            if (mt != cur_mt) {
+                cur_mt = mt;
+                const int ar = mt * 16 + lrow, ay = ar / W, ax = ar - ay * W;  // the pixel whose row address this lane supplies
+#pragma unroll
+                for (int j = 0; j < kGwTaps / 2; ++j) {
+                    const int t = 2 * j + ltap, dy = t / 3 - 1, dx = t - (t / 3) * 3 - 1;
+                    const bool ok = t < 9 && ar < HW && ay + dy >= 0 && ay + dy < H && ax + dx >= 0 && ax + dx < W;
+                    aoff[j] = ok ? ((ay + dy) * W + ax + dx) * row_bytes : -1;
+                }
+            }
+            const uint32_t in_g = in_s + (uint32_t)(g * 16);
+            const uint32_t* wq = s_w + g * (kGwGroupElems / 2) + gid * 4 + tq;
+            uint32_t a[kGwTaps / 2][4];
+#pragma unroll
+            for (int j = 0; j < kGwTaps / 2; ++j) {
+                const uint32_t addr = aoff[j] >= 0 ? in_g + (uint32_t)aoff[j] : zero_s;
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(a[j][0]), "=r"(a[j][1]), "=r"(a[j][2]), "=r"(a[j][3]) : "r"(addr));
+            }
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int j = 0; j < kGwTaps / 2; ++j)
+                hn_mma_m16n8k16_bf16(acc, a[j][0], a[j][1], a[j][2], a[j][3], wq[(2 * j) * 32], wq[(2 * j + 1) * 32]);
+            const int r0 = mt * 16 + gid, r1 = r0 + 8;
+            const float2 bz = *reinterpret_cast<const float2*>(s_cb + g * 8 + tq * 2);
+            uint8_t* o = out_b + r0 * row_bytes + g * 16;
+            if (r0 < HW) *reinterpret_cast<uint32_t*>(o) = hn_pack_bf16x2(fmaxf(acc[0] + bz.x, 0.0f), fmaxf(acc[1] + bz.y, 0.0f));
+            if (r1 < HW) *reinterpret_cast<uint32_t*>(o + 8 * row_bytes) = hn_pack_bf16x2(fmaxf(acc[2] + bz.x, 0.0f), fmaxf(acc[3] + bz.y, 0.0f));
+        }
+        __syncthreads();
+    }
+    se_stamp(p, 2);
+    // ---- pooling of this CTA's channels ----
+    auto fetch = [&](int q) -> uint4 {
+        if constexpr (kConv) return s_tile[q * pv + vl];
+        const int y = q / x.W, xx = q - y * x.W;
+        const uint4 v = *reinterpret_cast<const uint4*>(base + y * x.sy + xx * x.sx);
+        if (p.tile) s_tile[q * pv + vl] = v;
+        return v;
+    };
     {
         float acc[8];
 #pragma unroll
@@ -1003,22 +1120,16 @@ __global__ void __launch_bounds__(kSeThreads) hn_se_fused_kernel(const __grid_co
             for (; px + 3 * lanes < HW; px += 4 * lanes) {  // four independent loads in flight
                 uint4 v[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int q = px + u * lanes, y = q / x.W, xx = q - y * x.W;
-                    v[u] = *reinterpret_cast<const uint4*>(base + y * x.sy + xx * x.sx);
-                }
+                for (int u = 0; u < 4; ++u) v[u] = fetch(px + u * lanes);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    if (p.tile) s_tile[(px + u * lanes) * cvs + vl] = v[u];
                     const float2 a = hn_unpack_bf16x2(v[u].x), b = hn_unpack_bf16x2(v[u].y), c2 = hn_unpack_bf16x2(v[u].z), d2 = hn_unpack_bf16x2(v[u].w);
                     acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
                     acc[4] += c2.x; acc[5] += c2.y; acc[6] += d2.x; acc[7] += d2.y;
                 }
             }
             for (; px < HW; px += lanes) {
-                const int y = px / x.W, xx = px - y * x.W;
-                const uint4 v = *reinterpret_cast<const uint4*>(base + y * x.sy + xx * x.sx);
-                if (p.tile) s_tile[px * cvs + vl] = v;
+                const uint4 v = fetch(px);
                 const float2 a = hn_unpack_bf16x2(v.x), b = hn_unpack_bf16x2(v.y), c2 = hn_unpack_bf16x2(v.z), d2 = hn_unpack_bf16x2(v.w);
                 acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
                 acc[4] += c2.x; acc[5] += c2.y; acc[6] += d2.x; acc[7] += d2.y;
@@ -1035,7 +1146,9 @@ __global__ void __launch_bounds__(kSeThreads) hn_se_fused_kernel(const __grid_co
         for (int l = 0; l < lanes; ++l) a += s_acc[l * cvs * 8 + c];  // fixed order: deterministic
         p.mean[(long long)n * C + v0 * 8 + c] = __float2bfloat16(a * p.inv_hw);
     }
+    se_stamp(p, 3);
     hn_cluster_sync();  // release / acquire: the four slices of the mean are visible to the whole cluster
+    se_stamp(p, 4);
     // ---- FC1 + ReLU: this CTA's hidden units ----
     {
         const unsigned short* mrow = reinterpret_cast<const unsigned short*>(p.mean + (long long)n * C);
@@ -1056,6 +1169,7 @@ __global__ void __launch_bounds__(kSeThreads) hn_se_fused_kernel(const __grid_co
         }
     }
     hn_cluster_sync();
+    se_stamp(p, 5);
     // ---- FC2 + sigmoid: the gate of this CTA's channels ----
     for (int u = threadIdx.x; u < S; u += blockDim.x) s_hid[u] = __ldcg(p.hidden + (long long)n * S + u);
     __syncthreads();
@@ -1077,7 +1191,8 @@ __global__ void __launch_bounds__(kSeThreads) hn_se_fused_kernel(const __grid_co
         }
     }
     __syncthreads();
-    // ---- x *= gate, in place ----
+    se_stamp(p, 6);
+    // ---- x *= gate, in place (kConv: x is written here for the first time) ----
     if (active) {
         float g[8];
 #pragma unroll
@@ -1085,39 +1200,67 @@ __global__ void __launch_bounds__(kSeThreads) hn_se_fused_kernel(const __grid_co
         for (int px = pl; px < HW; px += lanes) {
             const int y = px / x.W, xx = px - y * x.W;
             bf16* dst = base + y * x.sy + xx * x.sx;
-            const uint4 v = p.tile ? s_tile[px * cvs + vl] : *reinterpret_cast<const uint4*>(dst);
+            const uint4 v = (kConv || p.tile) ? s_tile[px * pv + vl] : *reinterpret_cast<const uint4*>(dst);
             const float2 a = hn_unpack_bf16x2(v.x), b = hn_unpack_bf16x2(v.y), c2 = hn_unpack_bf16x2(v.z), d2 = hn_unpack_bf16x2(v.w);
             const float f[8] = {a.x * g[0], a.y * g[1], b.x * g[2], b.y * g[3], c2.x * g[4], c2.y * g[5], d2.x * g[6], d2.y * g[7]};
             store8(dst, f);
         }
     }
+    se_stamp(p, 7);
 }
 
-static constexpr size_t kSeFusedMaxSmem = 200 * 1024;
-// shared-memory bytes of the fused launch; *tile = whether the channel slice fits next to the vectors
-static size_t se_fused_smem(int HW, int C, int S, int* tile) {
+static long long* g_se_dbg = nullptr;
+extern "C" void hn_se_fused_set_debug(long long* buf) { g_se_dbg = buf; }  // device buffer of 8 stamps per CTA (N * 4 CTAs), or null
+
+static constexpr size_t kSeFusedMaxSmem = 220 * 1024;
+// shared-memory bytes of the fused launch; *tile = whether the channel slice fits next to the vectors (conv: it must, twice,
+// plus the packed weights of the slice; 0 is returned when it does not)
+static size_t se_fused_smem(int HW, int C, int S, bool conv, int* tile) {
     const int CV = C / 8, cvs = hn_cdiv(CV, kSeCl), lanes = kSeThreads / cvs;
     const size_t vec = (size_t)(((C + 7) & ~7) + S + cvs * 8 + lanes * cvs * 8) * sizeof(float) + 16;
     const size_t t = (size_t)HW * cvs * 16;
+    if (conv) {
+        const size_t need = vec + 2 * (size_t)HW * (cvs | 1) * 16 + (size_t)cvs * kGwGroupElems * 2 + 16 + (size_t)cvs * 8 * sizeof(float);
+        *tile = 1;
+        return need <= kSeFusedMaxSmem ? need : 0;
+    }
     *tile = vec + t <= kSeFusedMaxSmem;
     return vec + (*tile ? t : 0);
 }
-extern "C" int hn_se_fused_supported(int H, int W, int C, int S) {
+static int se_fused_shape_ok(int H, int W, int C, int S) {
     if (H <= 0 || W <= 0 || C % 8 != 0 || S <= 0 || S % 8 != 0) return 0;
     const int CV = C / 8, cvs = hn_cdiv(CV, kSeCl);
     if (CV < 2 * kSeCl || cvs > 64) return 0;           // every CTA of the cluster needs channels of its own
     if ((long long)H * W > 4096) return 0;              // larger maps: many blocks per image (hn_se_pool_fwd)
-    int tile;
-    return se_fused_smem(H * W, C, S, &tile) <= kSeFusedMaxSmem;
+    return 1;
 }
-extern "C" int hn_se_fused_fwd(const hn_se_pool_desc* d, void* stream) {
-    HN_REQUIRE(d && d->partial && d->mean && d->gate && d->w1 && d->b1 && d->w2 && d->b2, "se_fused: bad descriptor");
+extern "C" int hn_se_fused_supported(int H, int W, int C, int S) {
+    int tile;
+    return se_fused_shape_ok(H, W, C, S) && se_fused_smem(H * W, C, S, false, &tile) <= kSeFusedMaxSmem;
+}
+extern "C" int hn_gconv_se_supported(int H, int W, int C, int S) {
+    int tile;
+    return se_fused_shape_ok(H, W, C, S) && se_fused_smem(H * W, C, S, true, &tile) != 0;
+}
+
+static int se_fused_launch(const hn_se_pool_desc* d, const hn_gconv_se_desc* cv, void* stream) {
+    const char* what = cv ? "gconv_se" : "se_fused";
+    HN_REQUIRE(d->partial && d->mean && d->gate && d->w1 && d->b1 && d->w2 && d->b2, "%s: bad descriptor", what);
     if (int rc = check_view(d->x, "se_fused.x")) return rc;
-    HN_REQUIRE(hn_se_fused_supported(d->x.H, d->x.W, d->x.C, d->S), "se_fused: unsupported shape %dx%dx%d, S=%d", d->x.H, d->x.W, d->x.C, d->S);
-    HN_REQUIRE(((reinterpret_cast<uintptr_t>(d->w1) | reinterpret_cast<uintptr_t>(d->w2)) & 15) == 0, "se_fused: FC weights must be 16-byte aligned");
+    HN_REQUIRE(cv ? hn_gconv_se_supported(d->x.H, d->x.W, d->x.C, d->S) : hn_se_fused_supported(d->x.H, d->x.W, d->x.C, d->S),
+               "%s: unsupported shape %dx%dx%d, S=%d", what, d->x.H, d->x.W, d->x.C, d->S);
+    HN_REQUIRE(((reinterpret_cast<uintptr_t>(d->w1) | reinterpret_cast<uintptr_t>(d->w2)) & 15) == 0, "%s: FC weights must be 16-byte aligned", what);
     SeFusedParams p;
     memset(&p, 0, sizeof(p));
     p.x = to_view(d->x);
+    if (cv) {
+        if (int rc = check_view(cv->in, "gconv_se.in")) return rc;
+        HN_REQUIRE(cv->in.N == d->x.N && cv->in.H == d->x.H && cv->in.W == d->x.W && cv->in.C == d->x.C, "gconv_se: input and output shapes differ");
+        HN_REQUIRE(cv->weight && cv->bias && (reinterpret_cast<uintptr_t>(cv->weight) & 15) == 0, "gconv_se: weights");
+        p.in = to_view(cv->in);
+        p.wg = reinterpret_cast<const bf16*>(cv->weight);
+        p.cbias = cv->bias;
+    }
     p.mean = reinterpret_cast<bf16*>(d->mean);
     p.hidden = d->partial;  // scratch of at least N*S floats (S <= C)
     p.fc.S = d->S;
@@ -1127,10 +1270,15 @@ extern "C" int hn_se_fused_fwd(const hn_se_pool_desc* d, void* stream) {
     p.inv_hw = 1.0f / (float)(d->x.H * d->x.W);
     p.cvs = hn_cdiv(d->x.C / 8, kSeCl);
     p.uss = hn_cdiv(d->S, kSeCl);
-    const size_t smem = se_fused_smem(d->x.H * d->x.W, d->x.C, d->S, &p.tile);
+    p.dbg = g_se_dbg;
+    const size_t smem = se_fused_smem(d->x.H * d->x.W, d->x.C, d->S, cv != nullptr, &p.tile);
     static std::once_flag once;
     static cudaError_t attr_rc = cudaSuccess;
-    std::call_once(once, [] { attr_rc = cudaFuncSetAttribute(hn_se_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeFusedMaxSmem); });
+    std::call_once(once, [] {
+        attr_rc = cudaFuncSetAttribute(hn_se_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeFusedMaxSmem);
+        if (attr_rc == cudaSuccess)
+            attr_rc = cudaFuncSetAttribute(hn_se_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeFusedMaxSmem);
+    });
     HN_CHECK_CUDA(attr_rc);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -1145,9 +1293,18 @@ extern "C" int hn_se_fused_fwd(const hn_se_pool_desc* d, void* stream) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_hn_pdl ? 2 : 1;
-    HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, hn_se_fused_kernel, p));
+    if (cv) HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, hn_se_fused_kernel<true>, p));
+    else HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, hn_se_fused_kernel<false>, p));
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
+}
+extern "C" int hn_se_fused_fwd(const hn_se_pool_desc* d, void* stream) {
+    HN_REQUIRE(d != nullptr, "se_fused: null descriptor");
+    return se_fused_launch(d, nullptr, stream);
+}
+extern "C" int hn_gconv_se_fwd(const hn_gconv_se_desc* d, void* stream) {
+    HN_REQUIRE(d != nullptr, "gconv_se: null descriptor");
+    return se_fused_launch(&d->se, d, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

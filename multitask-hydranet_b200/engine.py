@@ -29,6 +29,8 @@ from . import _native as nv
 
 #: squeeze-excite of the small maps (stages 2-4) as ONE cluster launch per block instead of pool+FC -> scale (HN_SE_FUSED=0: off)
 SE_FUSED = os.environ.get("HN_SE_FUSED", "1") != "0"
+#: ... and, for stride-1 blocks, with the block's grouped 3x3 convolution in front, in the same launch (HN_GCONV_SE=0: off)
+GCONV_SE = SE_FUSED and os.environ.get("HN_GCONV_SE", "1") != "0"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -283,6 +285,22 @@ class SeFusedSpec(SePoolSpec):
 
     def add_to(self, plan):
         nv.check(nv.lib.hn_plan_add_se_fused(plan, self.to_desc()))
+
+
+class GconvSeSpec(SePoolSpec):
+    """An XBlock's grouped 3x3 (stride 1, BN folded, ReLU) and its squeeze-excite in one launch (hn_gconv_se_fwd)."""
+    kind = "gconv_se"
+
+    def __init__(self, name, vin, w_ref, b_ref, wq, bias, x, pix, partial, counter, mean, fc):
+        super().__init__(name, x, pix, partial, counter, mean, fc)
+        self.vin, self.w_ref, self.b_ref, self.wq, self.cbias = vin, w_ref, b_ref, wq, bias
+        self.macs += x.N * x.H * x.W * x.C * 8 * 9
+
+    def to_desc(self):
+        return nv.GconvSeDesc(self.vin.to_c(), self.wq.data_ptr(), self.cbias.data_ptr(), super().to_desc())
+
+    def add_to(self, plan):
+        nv.check(nv.lib.hn_plan_add_gconv_se(plan, self.to_desc()))
 
 
 class DetPostSpec:
@@ -540,10 +558,12 @@ class Builder:
                 self.conv1x1(nm + ".c1", vin, w1, b1, a, nv.ACT_RELU, "backbone")
                 # grouped 3x3 (+BN+ReLU), stride st
                 g = self.buf(Ho, Wo, mid)
-                self.gconv(nm + ".c2", a, blk, g, st)
-                # squeeze-excite (in place): pool -> FC1+ReLU -> FC2+sigmoid (GEMMs over all images) -> scale
-                if blk.se is not None:
-                    self.squeeze_excite(nm + ".se", g, blk.se)
+                # small maps, stride 1: the grouped 3x3 and the whole squeeze-excite are ONE launch
+                if not (st == 1 and blk.se is not None and self.squeeze_excite(nm + ".se", g, blk.se, conv=(a, blk))):
+                    self.gconv(nm + ".c2", a, blk, g, st)
+                    # squeeze-excite (in place): pool -> FC1+ReLU -> FC2+sigmoid -> scale
+                    if blk.se is not None:
+                        self.squeeze_excite(nm + ".se", g, blk.se)
                 # shortcut
                 if blk.shortcut is not None:
                     ws, bs = fold_bn(blk.shortcut[0].weight, None, blk.shortcut[1])
@@ -575,7 +595,9 @@ class Builder:
         # one M tile only (rows = batch): narrow N tiles spread the weight read over many SMs
         return self._finish(cs, [(0, 0, 0, w)], cout, b, bn=16 if cout <= 256 else 64)
 
-    def squeeze_excite(self, name, g, se):
+    def squeeze_excite(self, name, g, se, conv=None):
+        """``conv`` = (input Buf, block): also run the block's stride-1 grouped 3x3 in the same launch when the shape allows;
+        returns True when it did (the caller then skips the separate conv op)."""
         B, C, S = self.B, g.C, se[1].weight.shape[0]
         Sp = (S + 7) // 8 * 8  # hidden width padded to the 16-byte channel granule
         dev = self.dev
@@ -593,6 +615,18 @@ class Builder:
         # pool -> FC1 + ReLU -> FC2 + sigmoid in ONE launch: the block that finishes an image's pooling runs its FCs
         fc = dict(S=Sp, w1=w1.to(self.dt).contiguous().to(dev), b1=b1.to(dev), w2=w2.to(self.dt).contiguous().to(dev),
                   b2=se[3].bias.detach().float().contiguous().to(dev), gate=scale)
+        if conv is not None and GCONV_SE and nv.lib.hn_gconv_se_supported(g.H, g.W, C, Sp):
+            a, blk = conv
+            w, b = fold_bn(blk.conv_block_2[0].weight, None, blk.conv_block_2[1])  # [C, 8, 3, 3]
+            assert w.shape[1] == 8 and C % 8 == 0, "grouped conv path assumes group width 8"
+            wq = torch.zeros((C // 8, 10, 8, 8), dtype=torch.float32, device=w.device)  # [group][tap][out][in], 10th tap zero
+            wq[:, :9] = w.detach().float().reshape(C // 8, 8, 8, 9).permute(0, 3, 1, 2)
+            w_ref = w.detach().float().to(self.dt).float().contiguous().to(dev)
+            self.ops.append(GconvSeSpec(name[:-3] + ".c2se", a.interior(), w_ref, b.detach().float().to(dev), wq.to(self.dt).contiguous().to(dev),
+                                        self.f32(b), g.interior(), pix, partial, counter, mean, fc))
+            return True
+        if conv is not None:
+            return False
         if SE_FUSED and nv.lib.hn_se_fused_supported(g.H, g.W, C, Sp):  # small maps: one cluster launch per block
             self.ops.append(SeFusedSpec(name, g.interior(), pix, partial, counter, mean, fc))
             return

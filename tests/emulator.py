@@ -228,13 +228,20 @@ def run_se_fused(ss):
     x.copy_((x.float() * ss.fc["gate"].float()[:, None, None, :]).to(x.dtype))
 
 
+def run_gconv_se(ss):
+    xin = ss.vin.torch_view().float().permute(0, 3, 1, 2)
+    y = F.relu(F.conv2d(xin, ss.w_ref.float().cpu(), ss.b_ref.float().cpu(), padding=1, groups=xin.shape[1] // 8))
+    ss.x.torch_view().copy_(y.permute(0, 2, 3, 1))
+    run_se_fused(ss)
+
+
 def run_stem(st):
     w = st.w.reshape(3, 3, 3, 32).permute(3, 0, 1, 2)
     y = F.relu(F.conv2d(st.x, w, st.b, 2, 1))
     st.out.torch_view().copy_(y.permute(0, 2, 3, 1))
 
 
-RUNNERS = {"conv": run_conv, "node": run_node, "dw_multi": run_dw_multi, "pool": run_pool, "lanefuse": run_lanefuse, "se_pool": run_se_pool, "se_scale": run_se_scale, "se_fused": run_se_fused, "stem": run_stem}
+RUNNERS = {"conv": run_conv, "node": run_node, "dw_multi": run_dw_multi, "pool": run_pool, "lanefuse": run_lanefuse, "se_pool": run_se_pool, "se_scale": run_se_scale, "se_fused": run_se_fused, "gconv_se": run_gconv_se, "stem": run_stem}
 
 
 def run_ops(ops):

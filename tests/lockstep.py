@@ -24,6 +24,8 @@ def _tensors_in(op):
         return [op.x.t]
     if op.kind == "se_scale":
         return [op.x.t, op.scale]
+    if op.kind == "gconv_se":
+        return [op.vin.t]
     if op.kind == "stem":
         return [op.x]
     raise KeyError(op.kind)
@@ -44,7 +46,7 @@ def _tensors_out(op):
         return [op.mean] + ([op.fc["gate"]] if op.fc is not None else [])
     if op.kind == "se_scale":
         return [op.x.t]
-    if op.kind == "se_fused":
+    if op.kind in ("se_fused", "gconv_se"):
         return [op.mean, op.fc["gate"], op.x.t]
     if op.kind == "stem":
         return [op.out.t]

@@ -56,7 +56,7 @@ def test_algorithmic_macs_match_survey():
     m = hb.HydraNet(big_cfg()).eval()
     b = engine.Builder(m, 1, 640, 640, torch.device("cpu"), act_dtype=torch.float32)
     b.build(torch.zeros(1, 3, 640, 640))
-    macs = sum(op.macs for op in b.ops if op.kind in ("conv", "stem", "node", "dw_multi", "se_pool", "se_fused"))
+    macs = sum(op.macs for op in b.ops if op.kind in ("conv", "stem", "node", "dw_multi", "se_pool", "se_fused", "gconv_se"))
     assert abs(macs - 31698401632) / 31698401632 < 2e-3, macs
 
 

@@ -415,3 +415,56 @@ def test_se_fused_launch_equals_pool_fc_scale(B, H, W, C, S):
     assert float((res["two"][0] - res["fused"][0]).abs().max()) <= 2 ** -7 * float(m_ref.abs().max())
     assert float((res["two"][1] - res["fused"][1]).abs().max()) <= 2 ** -6
     assert float((res["two"][2] - res["fused"][2]).abs().max()) <= 2 ** -6 * float(y_ref.abs().max())
+
+
+@pytest.mark.parametrize("B,H,W,C,S", [(32, 10, 10, 936, 234), (3, 20, 20, 376, 94), (5, 4, 4, 936, 234), (2, 7, 13, 64, 16), (1, 3, 21, 376, 94)])
+def test_gconv_se_launch_equals_conv_then_se(B, H, W, C, S):
+    """hn_gconv_se_fwd (grouped 3x3 + squeeze-excite in one cluster launch, mma.sync out of shared memory) against fp32 torch
+    on the bf16-rounded operands: the conv output before the gate is recovered as y / gate."""
+    import torch.nn.functional as F
+    from hydranet_b200 import _native as nv
+    from hydranet_b200.engine import Buf
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(H * 1000 + C + 7)
+    Sp = (S + 7) // 8 * 8
+    assert nv.lib.hn_gconv_se_supported(H, W, C, Sp) == 1
+    x0 = torch.randn((B, H, W, C), generator=g).relu_()
+    wc = torch.randn((C, 8, 3, 3), generator=g) / 72 ** 0.5
+    bc = torch.randn((C,), generator=g) * 0.2
+    w1 = torch.zeros((Sp, C)); w1[:S] = torch.randn((S, C), generator=g) / C ** 0.5
+    b1 = torch.zeros((Sp,)); b1[:S] = torch.randn((S,), generator=g) * 0.1
+    w2 = torch.zeros((C, Sp)); w2[:, :S] = torch.randn((C, S), generator=g) / S ** 0.5
+    b2 = torch.randn((C,), generator=g) * 0.5
+    wq = torch.zeros((C // 8, 10, 8, 8))
+    wq[:, :9] = wc.reshape(C // 8, 8, 8, 9).permute(0, 3, 1, 2)
+    wqd, bcd = wq.to(torch.bfloat16).contiguous().to(dev), bc.to(dev)
+    w1d, w2d, b1d, b2d = w1.to(torch.bfloat16).to(dev), w2.to(torch.bfloat16).to(dev), b1.to(dev), b2.to(dev)
+    bin_, bout = Buf(dev, torch.bfloat16, B, H, W, C, pad=0), Buf(dev, torch.bfloat16, B, H, W, C, pad=1)
+    bin_.interior().torch_view().copy_(x0.to(dev))
+    v = bout.interior()
+    partial = torch.zeros((B, 1, C), dtype=torch.float32, device=dev)
+    counter = torch.zeros((B,), dtype=torch.int32, device=dev)
+    mean = torch.zeros((B, C), dtype=torch.bfloat16, device=dev)
+    gate = torch.zeros((B, C), dtype=torch.bfloat16, device=dev)
+    se = nv.SePoolDesc(v.to_c(), 128, partial.data_ptr(), counter.data_ptr(), mean.data_ptr())
+    se.S, se.w1, se.b1, se.w2, se.b2, se.gate = Sp, w1d.data_ptr(), b1d.data_ptr(), w2d.data_ptr(), b2d.data_ptr(), gate.data_ptr()
+    d = nv.GconvSeDesc(bin_.interior().to_c(), wqd.data_ptr(), bcd.data_ptr(), se)
+    nv.check(nv.lib.hn_gconv_se_fwd(d, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    halo = bout.t.clone()
+    halo[:, 1:-1, 1:-1] = 0
+    assert float(halo.abs().max()) == 0.0, "the halo of the output buffer was written"
+    xb = x0.to(torch.bfloat16).float().permute(0, 3, 1, 2)
+    y_ref = F.relu(F.conv2d(xb, wc.to(torch.bfloat16).float(), bc, padding=1, groups=C // 8)).permute(0, 2, 3, 1)
+    yb = y_ref.to(torch.bfloat16).float()
+    m_ref = yb.mean(dim=(1, 2))
+    h_ref = torch.relu(m_ref.to(torch.bfloat16).float() @ w1d.float().cpu().t() + b1)
+    g_ref = torch.sigmoid(h_ref.to(torch.bfloat16).float() @ w2d.float().cpu().t() + b2)
+    out_ref = yb * g_ref[:, None, None, :]
+    got_mean, got_gate, got = mean.float().cpu(), gate.float().cpu(), v.torch_view().float().cpu()
+    assert float((got_mean - m_ref).abs().max()) <= 2 ** -7 * float(m_ref.abs().max()) + 1e-6
+    assert float((got_gate - g_ref).abs().max()) <= 1e-2
+    assert float((got - out_ref).abs().max()) <= 2e-2 * float(out_ref.abs().max())
+    # the conv itself, gate divided out (gate in (0, 1), bf16): every pixel, including the zero-padded borders
+    conv_got = got / got_gate[:, None, None, :].clamp_min(1e-3)
+    assert float((conv_got - y_ref).abs().max()) <= 2.5e-2 * float(y_ref.abs().max())
