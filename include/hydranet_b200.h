@@ -255,7 +255,7 @@ int hn_se_pool_fwd(const hn_se_pool_desc* d, void* stream);
 int hn_se_scale_fwd(const hn_se_scale_desc* d, void* stream);
 /* The whole squeeze-excite of a block (anynet.py:39-47,68-69) in ONE launch, for small maps: a cluster of 4 CTAs per image, each
  * owning a quarter of the channels: pool -> FC1 + ReLU -> FC2 + sigmoid -> x *= gate in place.  Same descriptor as
- * hn_se_pool_fwd (S > 0 required); `partial` is scratch of at least N*S floats, `pix_per_block` and `counter` are unused.
+ * hn_se_pool_fwd (S > 0 required); `partial`, `pix_per_block` and `counter` are unused.
  * Outputs: mean, gate, and x scaled in place.  hn_se_fused_supported tells whether a shape qualifies (H*W <= 4096,
  * C >= 64, the channel slice fits in shared memory). */
 int hn_se_fused_fwd(const hn_se_pool_desc* d, void* stream);

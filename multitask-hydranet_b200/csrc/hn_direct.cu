@@ -952,8 +952,8 @@ extern "C" int hn_se_scale_fwd(const hn_se_scale_desc* d, void* stream) {
 // through its SM's L2 port, 32 SMs busy and 116 idle, and the scaling is a separate launch behind it.  Here a cluster of
 // kSeCl CTAs serves one image and every CTA owns a slice of the CHANNELS: it pools its channels over all pixels (keeping
 // the slice in shared memory), computes 1/kSeCl of the hidden units, then the gate of its own channels, and scales its
-// slice in place.  The mean and the hidden vector cross the cluster through global memory (release / acquire cluster
-// barriers); every sum runs in a fixed order.  Roundings as in the two-launch form: bf16 mean, bf16 hidden, bf16 gate.
+// slice in place.  The mean and the hidden vector cross the cluster through distributed shared memory (st.shared::cluster into
+// every CTA's copy, release / acquire cluster barriers); every sum runs in a fixed order.  Roundings as in the two-launch form: bf16 mean, bf16 hidden, bf16 gate.
 //
 // kConv: the block's grouped 3x3 convolution (group width 8, stride 1, folded BN + ReLU; anynet.py:60-66) runs in front, in
 // the same launch: a group is exactly one 8-channel vector, so a channel slice is self-contained.  The CTA loads its slice
@@ -970,7 +970,6 @@ struct SeFusedParams {
     const bf16* wg; // kConv: [C/8][10][8 oc][8 ic]
     const float* cbias;  // kConv: [C]
     bf16* mean;     // [N][C]
-    float* hidden;  // [N][S] (bf16-rounded values)
     SeFc fc;
     float inv_hw;
     int cvs;   // 8-channel vectors per CTA (the last CTA of a cluster may own fewer)
@@ -993,10 +992,20 @@ __device__ __forceinline__ void se_stamp(const SeFusedParams& p, int k) {
     }
 }
 
+// one fp32 value into the same shared-memory slot of every CTA of the cluster (distributed shared memory)
+__device__ __forceinline__ void se_bcast_f32(float* slot, float v) {
+    const uint32_t a = hn_smem_u32(slot);
+#pragma unroll
+    for (int rk = 0; rk < kSeCl; ++rk) asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(hn_mapa(a, (uint32_t)rk)), "f"(v) : "memory");
+}
+
 template <bool kConv>
 __global__ void __launch_bounds__(kSeThreads) hn_se_fused_kernel(const __grid_constant__ SeFusedParams p) {
     hn_pdl_launch_dependents();
     hn_pdl_wait();
+    // every CTA of the cluster must be running before a peer stores into its shared memory: arrive now, wait before the first
+    // remote store
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
     se_stamp(p, 0);
     extern __shared__ __align__(16) uint8_t se_smem[];
     const View& x = p.x;
@@ -1141,20 +1150,18 @@ __global__ void __launch_bounds__(kSeThreads) hn_se_fused_kernel(const __grid_co
         }
     }
     __syncthreads();
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // the peers are running (arrived at kernel start)
     for (int c = threadIdx.x; c < nvs * 8; c += blockDim.x) {
         float a = 0.0f;
         for (int l = 0; l < lanes; ++l) a += s_acc[l * cvs * 8 + c];  // fixed order: deterministic
-        p.mean[(long long)n * C + v0 * 8 + c] = __float2bfloat16(a * p.inv_hw);
+        const bf16 mb = __float2bfloat16(a * p.inv_hw);
+        p.mean[(long long)n * C + v0 * 8 + c] = mb;
+        se_bcast_f32(s_mean + v0 * 8 + c, __bfloat162float(mb));  // the FC layers read the rounded mean, as separate launches would
     }
     se_stamp(p, 3);
-    hn_cluster_sync();  // release / acquire: the four slices of the mean are visible to the whole cluster
+    hn_cluster_sync();  // release / acquire: the four slices of the mean are in every CTA's s_mean
     se_stamp(p, 4);
     // ---- FC1 + ReLU: this CTA's hidden units ----
-    {
-        const unsigned short* mrow = reinterpret_cast<const unsigned short*>(p.mean + (long long)n * C);
-        for (int c = threadIdx.x; c < C; c += blockDim.x) s_mean[c] = __bfloat162float(__ushort_as_bfloat16(__ldcg(mrow + c)));
-    }
-    __syncthreads();
     {
         int T = 1;  // adjacent lanes per hidden unit
         while (T < 32 && p.uss * T * 2 <= (int)blockDim.x) T *= 2;
@@ -1165,14 +1172,12 @@ __global__ void __launch_bounds__(kSeThreads) hn_se_fused_kernel(const __grid_co
             if (srow < nu) acc = se_dot(p.fc.w1 + (long long)(u0 + srow) * C, s_mean, min(part * per, nv), min(part * per + per, nv));
             for (int o = T >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (srow < nu && part == 0)
-                p.hidden[(long long)n * S + u0 + srow] = __bfloat162float(__float2bfloat16(fmaxf(acc + p.fc.b1[u0 + srow], 0.0f)));
+                se_bcast_f32(s_hid + u0 + srow, __bfloat162float(__float2bfloat16(fmaxf(acc + p.fc.b1[u0 + srow], 0.0f))));
         }
     }
     hn_cluster_sync();
     se_stamp(p, 5);
     // ---- FC2 + sigmoid: the gate of this CTA's channels ----
-    for (int u = threadIdx.x; u < S; u += blockDim.x) s_hid[u] = __ldcg(p.hidden + (long long)n * S + u);
-    __syncthreads();
     {
         const int nch = nvs * 8;
         int T = 1;
@@ -1262,7 +1267,6 @@ static int se_fused_launch(const hn_se_pool_desc* d, const hn_gconv_se_desc* cv,
         p.cbias = cv->bias;
     }
     p.mean = reinterpret_cast<bf16*>(d->mean);
-    p.hidden = d->partial;  // scratch of at least N*S floats (S <= C)
     p.fc.S = d->S;
     p.fc.w1 = reinterpret_cast<const bf16*>(d->w1); p.fc.b1 = d->b1;
     p.fc.w2 = reinterpret_cast<const bf16*>(d->w2); p.fc.b2 = d->b2;
