@@ -31,7 +31,9 @@ static inline int check_mat(const hn_mat& m, const char* what) {
 }
 static inline bool same_shape(const hn_mat& a, const hn_mat& b) { return a.rows == b.rows && a.cols == b.cols; }
 
-__device__ __forceinline__ float hn_sigmoid_acc(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// ex2.approx + rcp.approx (~2 ulp): the result feeds a value that is rounded to bf16; the IEEE division cost more than the rest of
+// the swish gradient together
+__device__ __forceinline__ float hn_sigmoid_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     const float2 a = hn_unpack_bf16x2(u.x), b = hn_unpack_bf16x2(u.y), c = hn_unpack_bf16x2(u.z), d = hn_unpack_bf16x2(u.w);
     f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
@@ -87,13 +89,13 @@ __device__ __forceinline__ int seg_of_row(const RedGeom& g, long long row) {
     return s;
 }
 
-static int make_geom(RedGeom* g, long long rows, int C, int n_seg, const int64_t* seg_end, long long uniform, int target_chunks) {
+static int make_geom(RedGeom* g, long long rows, int C, int n_seg, const int64_t* seg_end, long long uniform, int target_chunks, int min_rpc = 32) {
     memset(g, 0, sizeof(*g));
     g->rows = rows;
     g->C = C;
     g->CV = C / 8;
     long long rpc = (rows + target_chunks - 1) / target_chunks;
-    if (rpc < 32) rpc = 32;
+    if (rpc < min_rpc) rpc = min_rpc;
     g->rows_per_chunk = (int)rpc;
     if (uniform > 0) {
         HN_REQUIRE(rows % uniform == 0, "col reduce: rows %lld not a multiple of the segment size %lld", rows, uniform);
@@ -102,7 +104,7 @@ static int make_geom(RedGeom* g, long long rows, int C, int n_seg, const int64_t
         // keep at least ~target_chunks chunks in total, at least one per segment
         long long per = (target_chunks + g->n_seg - 1) / g->n_seg;
         rpc = (uniform + per - 1) / per;
-        if (rpc < 32) rpc = 32;
+        if (rpc < min_rpc) rpc = min_rpc;
         g->rows_per_chunk = (int)rpc;
         g->chunks_per_seg = (int)((uniform + rpc - 1) / rpc);
         g->n_chunks = g->chunks_per_seg * g->n_seg;
@@ -250,31 +252,42 @@ __global__ void hn_bn_finalize_kernel(const RedGeom g, const float* __restrict__
     }
 }
 
-// Element-wise passes: four independent 16-byte items per thread and iteration (all loads issued before the first use);
-// with one item in flight these kernels ran at ~1/3 of the HBM rate.
-static constexpr int kEwU = 1;  // measured: 4 items per thread made the (mostly small, latency-bound) BatchNorm passes slower (2.1 -> 2.5 ms per step)
+// Element-wise passes of BatchNorm.  Mapping as in stage 1: a CTA owns a chunk of rows of ONE segment, a thread owns one 8-channel
+// vector (its scale / shift live in registers) and walks the chunk's rows, kApplyU independent rows in flight.  The earlier
+// flat mapping (item = row * CV + vector) spent most of its issue slots on a 64-bit division and 16-32 statistic loads per
+// 16 bytes moved: the mid-size swish layers (BiFPN, detection towers) ran at 1 TB/s.
+static constexpr int kEwU = 1;  // flat element-wise kernels below (activation backward, fusion): one item per thread and iteration
+static constexpr int kApplyU = 4;
+static constexpr int kApplyChunks = 148 * 8;
+__device__ __forceinline__ void load_f8(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
 __global__ void __launch_bounds__(256) hn_bn_apply_kernel(const RedGeom g, Mat z, const float* __restrict__ stats, int act, Mat res, Mat y) {
-    const long long total = g.rows * g.CV, stride = (long long)gridDim.x * blockDim.x;
-    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * kEwU) {
-        uint4 zv[kEwU], rv[kEwU];
-        long long rr[kEwU];
-        int cc[kEwU];
+    const int CV = g.CV, rpi = 256 / CV;
+    const int cv = threadIdx.x % CV, rl = threadIdx.x / CV;
+    if (rl >= rpi) return;
+    int seg;
+    long long r0, r1;
+    red_locate(g, blockIdx.x, seg, r0, r1);
+    float sc[8], sh[8];
+    load_f8(stats + ((size_t)seg * 4 + 2) * g.C + cv * 8, sc);
+    load_f8(stats + ((size_t)seg * 4 + 3) * g.C + cv * 8, sh);
+    const int c = cv * 8;
+    for (long long rb = r0 + rl; rb < r1; rb += (long long)rpi * kApplyU) {
+        uint4 zv[kApplyU], rv[kApplyU];
 #pragma unroll
-        for (int u = 0; u < kEwU; ++u) {
-            const long long i = i0 + u * stride;
-            rr[u] = i / g.CV;
-            cc[u] = (int)(i - rr[u] * g.CV) * 8;
-            if (i < total) {
-                zv[u] = *reinterpret_cast<const uint4*>(z.ptr + rr[u] * z.ld + cc[u]);
-                if (res.ptr) rv[u] = *reinterpret_cast<const uint4*>(res.ptr + rr[u] * res.ld + cc[u]);
+        for (int u = 0; u < kApplyU; ++u) {
+            const long long r = rb + (long long)u * rpi;
+            if (r < r1) {
+                zv[u] = *reinterpret_cast<const uint4*>(z.ptr + r * z.ld + c);
+                if (res.ptr) rv[u] = *reinterpret_cast<const uint4*>(res.ptr + r * res.ld + c);
             }
         }
 #pragma unroll
-        for (int u = 0; u < kEwU; ++u) {
-            if (i0 + u * stride >= total) break;
-            const int seg = seg_of_row(g, rr[u]);
-            const float* sc = stats + ((size_t)seg * 4 + 2) * g.C + cc[u];
-            const float* sh = sc + g.C;
+        for (int u = 0; u < kApplyU; ++u) {
+            const long long r = rb + (long long)u * rpi;
+            if (r >= r1) break;
             float v[8];
             unpack8(zv[u], v);
 #pragma unroll
@@ -292,9 +305,14 @@ __global__ void __launch_bounds__(256) hn_bn_apply_kernel(const RedGeom g, Mat z
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = v[j] * hn_sigmoid_acc(v[j]);
             }
-            store8(y.ptr + rr[u] * y.ld + cc[u], v);
+            store8(y.ptr + r * y.ld + c, v);
         }
     }
+}
+// chunk geometry of the element-wise passes: enough chunks to fill the machine, at least one unrolled iteration per thread
+static int make_apply_geom(RedGeom* g, long long rows, int C, int n_seg, const int64_t* seg_end) {
+    const int rpi = 256 / (C / 8);
+    return make_geom(g, rows, C, n_seg, seg_end, 0, kApplyChunks, rpi * kApplyU);
 }
 
 static int fill_bn_ptrs(const hn_bn_desc* d, BnPtrs* bp) {
@@ -341,7 +359,9 @@ extern "C" int hn_bn_train_fwd(const hn_bn_desc* d, void* stream_) {
     HN_CHECK_CUDA(cudaGetLastError());
     Mat res{nullptr, 0, 0, 0};
     if (d->res.ptr) res = to_mat(d->res);
-    hn_bn_apply_kernel<<<ew_grid(g.rows * g.CV), 256, 0, stream>>>(g, to_mat(d->z), d->stats, d->act, res, to_mat(d->y));
+    RedGeom ga;
+    if (int rc = make_apply_geom(&ga, d->z.rows, d->z.cols, d->n_seg, d->seg_end)) return rc;
+    hn_bn_apply_kernel<<<ga.n_chunks, 256, 0, stream>>>(ga, to_mat(d->z), d->stats, d->act, res, to_mat(d->y));
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }
@@ -377,6 +397,35 @@ struct BnBwdF {
             for (int j = 0; j < 8; ++j) dzv[j] = g[j];
         }
     }
+    // the same with the channel vector's statistics already in registers (the element-wise pass: its stores keep the compiler
+    // from hoisting the loads above out of the row loop)
+    struct St { float mean[8], invstd[8], scale[8], shift[8]; };
+    __device__ __forceinline__ void load_stats(int seg, int cv, St& s) const {
+        const float* st = stats + (size_t)seg * 4 * C + cv * 8;
+        load_f8(st, s.mean);
+        load_f8(st + C, s.invstd);
+        load_f8(st + 2 * C, s.scale);
+        if (act == HN_ACT_SWISH) load_f8(st + 3 * C, s.shift);
+    }
+    __device__ __forceinline__ void compute(const St& s, const Raw& w, float (&dzv)[8], float (&xh)[8]) const {
+        float g[8], zz[8];
+        unpack8(w.g, g);
+        unpack8(w.z, zz);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xh[j] = (zz[j] - s.mean[j]) * s.invstd[j];
+        if (act == HN_ACT_RELU) {
+            float o[8];
+            unpack8(w.y, o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dzv[j] = o[j] > 0.0f ? g[j] : 0.0f;
+        } else if (act == HN_ACT_SWISH) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dzv[j] = g[j] * act_grad(fmaf(zz[j], s.scale[j], s.shift[j]), HN_ACT_SWISH);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dzv[j] = g[j];
+        }
+    }
     __device__ __forceinline__ void operator()(int seg, long long r, int cv, float (&a0)[8], float (&a1)[8]) const {
         Raw w;
         load(r, cv, w);
@@ -400,33 +449,38 @@ __global__ void hn_bn_bwd_finalize_kernel(const RedGeom g, const float* __restri
     sums[((size_t)seg * 2 + 1) * g.C + c] = (float)(s1 / n);
 }
 
+static constexpr int kBwdApplyU = 2;  // three loads per row
 __global__ void __launch_bounds__(256) hn_bn_bwd_apply_kernel(const RedGeom g, const BnBwdF f, const float* __restrict__ sums, Mat dz, Mat dres) {
-    const long long total = g.rows * g.CV, stride = (long long)gridDim.x * blockDim.x;
-    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * kEwU) {
-        BnBwdF::Raw w[kEwU];
-        long long rr[kEwU];
-        int cv[kEwU];
+    const int CV = g.CV, rpi = 256 / CV;
+    const int cv = threadIdx.x % CV, rl = threadIdx.x / CV;
+    if (rl >= rpi) return;
+    int seg;
+    long long r0, r1;
+    red_locate(g, blockIdx.x, seg, r0, r1);
+    BnBwdF::St st;
+    f.load_stats(seg, cv, st);
+    float m0[8], m1[8];
+    load_f8(sums + ((size_t)seg * 2) * g.C + cv * 8, m0);
+    load_f8(sums + ((size_t)seg * 2 + 1) * g.C + cv * 8, m1);
+    const int c = cv * 8;
+    for (long long rb = r0 + rl; rb < r1; rb += (long long)rpi * kBwdApplyU) {
+        BnBwdF::Raw w[kBwdApplyU];
 #pragma unroll
-        for (int u = 0; u < kEwU; ++u) {
-            const long long i = i0 + u * stride;
-            rr[u] = i / g.CV;
-            cv[u] = (int)(i - rr[u] * g.CV);
-            if (i < total) f.load(rr[u], cv[u], w[u]);
+        for (int u = 0; u < kBwdApplyU; ++u) {
+            const long long r = rb + (long long)u * rpi;
+            if (r < r1) f.load(r, cv, w[u]);
         }
 #pragma unroll
-        for (int u = 0; u < kEwU; ++u) {
-            if (i0 + u * stride >= total) break;
-            const int seg = seg_of_row(g, rr[u]);
+        for (int u = 0; u < kBwdApplyU; ++u) {
+            const long long r = rb + (long long)u * rpi;
+            if (r >= r1) break;
             float dzv[8], xh[8];
-            f.compute(seg, cv[u], w[u], dzv, xh);
-            if (dres.ptr) store8(dres.ptr + rr[u] * dres.ld + cv[u] * 8, dzv);
-            const float* sc = f.stats + ((size_t)seg * 4 + 2) * g.C + cv[u] * 8;  // gamma * invstd
-            const float* m0 = sums + ((size_t)seg * 2) * g.C + cv[u] * 8;
-            const float* m1 = m0 + g.C;
+            f.compute(st, w[u], dzv, xh);
+            if (dres.ptr) store8(dres.ptr + r * dres.ld + c, dzv);
             float o[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = sc[j] * (dzv[j] - m0[j] - xh[j] * m1[j]);
-            store8(dz.ptr + rr[u] * dz.ld + cv[u] * 8, o);
+            for (int j = 0; j < 8; ++j) o[j] = st.scale[j] * (dzv[j] - m0[j] - xh[j] * m1[j]);
+            store8(dz.ptr + r * dz.ld + c, o);
         }
     }
 }
@@ -463,7 +517,12 @@ extern "C" int hn_bn_train_bwd(const hn_bn_desc* d, void* stream_) {
     HN_CHECK_CUDA(cudaGetLastError());
     Mat dres{nullptr, 0, 0, 0};
     if (d->dres.ptr) dres = to_mat(d->dres);
-    hn_bn_bwd_apply_kernel<<<ew_grid(g.rows * g.CV), 256, 0, stream>>>(g, f, sums, to_mat(d->dz), dres);
+    RedGeom ga;
+    {
+        const int rpi = 256 / g.CV;
+        if (int rc = make_geom(&ga, d->z.rows, d->z.cols, d->n_seg, d->seg_end, 0, kApplyChunks, rpi * kBwdApplyU)) return rc;
+    }
+    hn_bn_bwd_apply_kernel<<<ga.n_chunks, 256, 0, stream>>>(ga, f, sums, to_mat(d->dz), dres);
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }
