@@ -143,8 +143,10 @@ __global__ void __launch_bounds__(256) hn_red1_kernel(const RedGeom g, const F f
 #pragma unroll
     for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.0f;
     if (active) {
+        typename F::Ctx ctx;  // per-thread constants of the functor (the channel vector's statistics), loaded once
+        f.prepare(seg, cv, ctx);
 #pragma unroll 4
-        for (long long r = r0 + rl; r < r1; r += rpi) f(seg, r, cv, a0, a1);
+        for (long long r = r0 + rl; r < r1; r += rpi) f(ctx, seg, r, cv, a0, a1);
     }
     float* mine = sm + (size_t)threadIdx.x * 16;
 #pragma unroll
@@ -217,9 +219,12 @@ struct BnPtrs {
     float* dbeta[HN_MAX_SEG];
 };
 
+struct NoCtx {};
 struct StatsF {
     Mat z;
-    __device__ __forceinline__ void operator()(int, long long r, int cv, float (&a0)[8], float (&a1)[8]) const {
+    typedef NoCtx Ctx;
+    __device__ __forceinline__ void prepare(int, int, Ctx&) const {}
+    __device__ __forceinline__ void operator()(const Ctx&, int, long long r, int cv, float (&a0)[8], float (&a1)[8]) const {
         float v[8];
         load8(z.ptr + r * z.ld + cv * 8, v);
 #pragma unroll
@@ -334,6 +339,15 @@ static inline int ew_grid(long long total_vec) {
     return (int)(b < 1 ? 1 : (b < cap ? b : cap));
 }
 static constexpr int kTargetChunks = 296;  // 148 SMs x 2: stage 1 is HBM-bound, stage 2 walks the partials per channel
+// chunks of the BatchNorm / column reductions (HN_RED_CHUNKS overrides, for A/B runs)
+static int red_chunks() {
+    static const int v = [] {
+        const char* e = getenv("HN_RED_CHUNKS");
+        const int n = e ? atoi(e) : 0;
+        return n >= 32 && n <= 4096 ? n : kTargetChunks;
+    }();
+    return v;
+}
 
 extern "C" int hn_bn_train_fwd(const hn_bn_desc* d, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -348,7 +362,7 @@ extern "C" int hn_bn_train_fwd(const hn_bn_desc* d, void* stream_) {
     HN_REQUIRE(d->act == HN_ACT_NONE || d->act == HN_ACT_RELU || d->act == HN_ACT_SWISH, "bn: unsupported activation %d", d->act);
     if (d->z.rows == 0) return HN_OK;
     RedGeom g;
-    if (int rc = make_geom(&g, d->z.rows, d->z.cols, d->n_seg, d->seg_end, 0, kTargetChunks)) return rc;
+    if (int rc = make_geom(&g, d->z.rows, d->z.cols, d->n_seg, d->seg_end, 0, red_chunks())) return rc;
     HN_REQUIRE((int64_t)partial_bytes(g) <= d->scratch_bytes, "bn: scratch too small (%zu > %lld)", partial_bytes(g), (long long)d->scratch_bytes);
     BnPtrs bp;
     if (int rc = fill_bn_ptrs(d, &bp)) return rc;
@@ -377,28 +391,7 @@ struct BnBwdF {
         w.z = *reinterpret_cast<const uint4*>(z.ptr + r * z.ld + cv * 8);
         if (act == HN_ACT_RELU) w.y = *reinterpret_cast<const uint4*>(y.ptr + r * y.ld + cv * 8);
     }
-    __device__ __forceinline__ void compute(int seg, int cv, const Raw& w, float (&dzv)[8], float (&xh)[8]) const {
-        const float* st = stats + (size_t)seg * 4 * C + cv * 8;
-        float g[8], zz[8];
-        unpack8(w.g, g);
-        unpack8(w.z, zz);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) xh[j] = (zz[j] - st[j]) * st[C + j];
-        if (act == HN_ACT_RELU) {
-            float o[8];
-            unpack8(w.y, o);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dzv[j] = o[j] > 0.0f ? g[j] : 0.0f;
-        } else if (act == HN_ACT_SWISH) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dzv[j] = g[j] * act_grad(fmaf(zz[j], st[2 * C + j], st[3 * C + j]), HN_ACT_SWISH);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dzv[j] = g[j];
-        }
-    }
-    // the same with the channel vector's statistics already in registers (the element-wise pass: its stores keep the compiler
-    // from hoisting the loads above out of the row loop)
+    // the channel vector's statistics live in registers: loaded once per thread, not once per row
     struct St { float mean[8], invstd[8], scale[8], shift[8]; };
     __device__ __forceinline__ void load_stats(int seg, int cv, St& s) const {
         const float* st = stats + (size_t)seg * 4 * C + cv * 8;
@@ -426,11 +419,13 @@ struct BnBwdF {
             for (int j = 0; j < 8; ++j) dzv[j] = g[j];
         }
     }
-    __device__ __forceinline__ void operator()(int seg, long long r, int cv, float (&a0)[8], float (&a1)[8]) const {
+    typedef St Ctx;
+    __device__ __forceinline__ void prepare(int seg, int cv, Ctx& s) const { load_stats(seg, cv, s); }
+    __device__ __forceinline__ void operator()(const Ctx& s, int, long long r, int cv, float (&a0)[8], float (&a1)[8]) const {
         Raw w;
         load(r, cv, w);
         float dzv[8], xh[8];
-        compute(seg, cv, w, dzv, xh);
+        compute(s, w, dzv, xh);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { a0[j] += dzv[j]; a1[j] = fmaf(dzv[j], xh[j], a1[j]); }
     }
@@ -502,7 +497,7 @@ extern "C" int hn_bn_train_bwd(const hn_bn_desc* d, void* stream_) {
     }
     if (d->z.rows == 0) return HN_OK;
     RedGeom g;
-    if (int rc = make_geom(&g, d->z.rows, d->z.cols, d->n_seg, d->seg_end, 0, kTargetChunks)) return rc;
+    if (int rc = make_geom(&g, d->z.rows, d->z.cols, d->n_seg, d->seg_end, 0, red_chunks())) return rc;
     const size_t need = partial_bytes(g) + (size_t)g.n_seg * 2 * g.C * sizeof(float);
     HN_REQUIRE((int64_t)need <= d->scratch_bytes, "bn bwd: scratch too small (%zu > %lld)", need, (long long)d->scratch_bytes);
     BnPtrs bp;
@@ -532,7 +527,9 @@ extern "C" int hn_bn_train_bwd(const hn_bn_desc* d, void* stream_) {
 // ------------------------------------------------------------------------------------------------
 struct SumF {
     Mat a;
-    __device__ __forceinline__ void operator()(int, long long r, int cv, float (&a0)[8], float (&a1)[8]) const {
+    typedef NoCtx Ctx;
+    __device__ __forceinline__ void prepare(int, int, Ctx&) const {}
+    __device__ __forceinline__ void operator()(const Ctx&, int, long long r, int cv, float (&a0)[8], float (&a1)[8]) const {
         float v[8];
         load8(a.ptr + r * a.ld + cv * 8, v);
 #pragma unroll
@@ -541,7 +538,9 @@ struct SumF {
 };
 struct DotF {
     Mat a, b;
-    __device__ __forceinline__ void operator()(int, long long r, int cv, float (&a0)[8], float (&)[8]) const {
+    typedef NoCtx Ctx;
+    __device__ __forceinline__ void prepare(int, int, Ctx&) const {}
+    __device__ __forceinline__ void operator()(const Ctx&, int, long long r, int cv, float (&a0)[8], float (&)[8]) const {
         float v[8], w[8];
         load8(a.ptr + r * a.ld + cv * 8, v);
         load8(b.ptr + r * b.ld + cv * 8, w);
@@ -566,7 +565,7 @@ extern "C" int hn_col_reduce(const hn_mat* a, const hn_mat* b, int32_t mode, int
     if (int rc = check_mat(*a, "reduce.a")) return rc;
     HN_REQUIRE(a->rows > 0, "col reduce: empty matrix");
     RedGeom g;
-    if (int rc = make_geom(&g, a->rows, a->cols, 1, nullptr, rows_per_seg > 0 ? rows_per_seg : a->rows, kTargetChunks)) return rc;
+    if (int rc = make_geom(&g, a->rows, a->cols, 1, nullptr, rows_per_seg > 0 ? rows_per_seg : a->rows, red_chunks())) return rc;
     HN_REQUIRE((int64_t)partial_bytes(g) <= scratch_bytes, "col reduce: scratch too small (%zu > %lld)", partial_bytes(g), (long long)scratch_bytes);
     if (mode == 0) {
         SumF f{to_mat(*a)};
