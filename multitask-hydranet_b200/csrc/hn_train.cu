@@ -779,26 +779,40 @@ __global__ void hn_up2_bwd_kernel(View dy, View dx) {
 // Pool backward, gather form: input pixel (Y, X) collects the gradient of every output window that contains it and whose
 // FIRST maximum in (ky, kx) scan order is (Y, X).  pad = 0: window rows 2y .. 2y+2, zeros beyond the bottom / right edge
 // take part (and swallow the gradient when they win); pad = 1: window rows 2y-1 .. 2y+1, outside = -inf.
-__global__ void hn_pool_bwd_kernel(View x, View dy, View dx, int pad) {
+// A thread owns a 2x2 block of dx whose first row / column are the ones SHARED by two windows (rows 2*by - pad and 2*by - pad + 1):
+// the block is touched by exactly the windows (by-1 .. by) x (bx-1 .. bx), so the arg-max of a window is evaluated once per block
+// it reaches (9 loads per input pixel instead of the 36 of a per-pixel gather).  Deterministic: no atomics, fixed order.
+__global__ void hn_pool_bwd_kernel(View x, View dy, View dx, int pad, int BH, int BW) {
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (unsigned)dx.N * dx.H * dx.W * (dx.C >> 3)) return;
-    int n, Y, X, cv;
-    decode4(idx, dx, n, Y, X, cv);
+    const unsigned CV = (unsigned)(dx.C >> 3);
+    if (idx >= (unsigned)dx.N * BH * BW * CV) return;
+    const int cv = (int)(idx % CV);
+    unsigned t = idx / CV;
+    const int bx = (int)(t % (unsigned)BW);
+    t /= (unsigned)BW;
+    const int by = (int)(t % (unsigned)BH), n = (int)(t / (unsigned)BH);
     const int c = cv * 8;
-    float acc[8];
+    const int Ya = 2 * by - pad, Xa = 2 * bx - pad;  // block rows Ya, Ya + 1; columns Xa, Xa + 1
+    float acc[2][2][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-    // windows containing Y: 2y - pad <= Y <= 2y - pad + 2
-    const int y_lo = max(0, (Y + pad - 2 + 1) >> 1), y_hi = min(dy.H - 1, (Y + pad) >> 1);
-    const int x_lo = max(0, (X + pad - 2 + 1) >> 1), x_hi = min(dy.W - 1, (X + pad) >> 1);
-    for (int oy = y_lo; oy <= y_hi; ++oy)
-        for (int ox = x_lo; ox <= x_hi; ++ox) {
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b2 = 0; b2 < 2; ++b2)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[a][b2][j] = 0.0f;
+#pragma unroll
+    for (int wy = 0; wy < 2; ++wy) {
+#pragma unroll
+        for (int wx = 0; wx < 2; ++wx) {
+            const int oy = by - 1 + wy, ox = bx - 1 + wx;
+            if (oy < 0 || oy >= dy.H || ox < 0 || ox >= dy.W) continue;
             float best[8];
             int arg[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = -1; }
-            const int mine = (Y - (2 * oy - pad)) * 3 + (X - (2 * ox - pad));
+#pragma unroll
             for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
                     const int iy = 2 * oy - pad + ky, ix = 2 * ox - pad + kx;
                     float v[8];
@@ -816,11 +830,27 @@ __global__ void hn_pool_bwd_kernel(View x, View dy, View dx, int pad) {
                 }
             float g[8];
             load8(vptr(dy, n, oy, ox, c), g);
+            // window cell (ky, kx) is block cell (ky - 2 + 2*wy... ): window row 2*oy - pad + ky = Ya + (ky - 2 + 2 * wy)
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (arg[j] == mine) acc[j] += g[j];
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b2 = 0; b2 < 2; ++b2) {
+                    const int ky = a + 2 - 2 * wy, kx = b2 + 2 - 2 * wx;  // the window's cell at block position (a, b2)
+                    if (ky > 2 || kx > 2) continue;
+                    const int cell = ky * 3 + kx;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (arg[j] == cell) acc[a][b2][j] += g[j];
+                }
         }
-    store8(const_cast<bf16*>(vptr(dx, n, Y, X, c)), acc);
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b2 = 0; b2 < 2; ++b2) {
+            const int Y = Ya + a, X = Xa + b2;
+            if (Y >= 0 && Y < dx.H && X >= 0 && X < dx.W) store8(const_cast<bf16*>(vptr(dx, n, Y, X, c)), acc[a][b2]);
+        }
 }
 
 extern "C" int hn_pool_fwd(const hn_pool_desc* d, void* stream);
@@ -862,7 +892,9 @@ extern "C" int hn_resample_bwd(const hn_resample_desc* d, void* stream_) {
         const int pad = d->mode == HN_RS_POOL_ZERO ? 0 : 1;
         if (pad == 0) HN_REQUIRE((d->x.H - 2) / 2 + 1 == d->dy.H && (d->x.W - 2) / 2 + 1 == d->dy.W, "pool bwd: size mismatch");
         else HN_REQUIRE((d->x.H - 1) / 2 + 1 == d->dy.H && (d->x.W - 1) / 2 + 1 == d->dy.W, "pool bwd: size mismatch");
-        hn_pool_bwd_kernel<<<hn_cdiv(total, 256), 256, 0, stream>>>(to_view(d->x), to_view(d->dy), to_view(d->dx), pad);
+        const int BH = (d->dx.H - 1 + pad) / 2 + 1, BW = (d->dx.W - 1 + pad) / 2 + 1;  // 2x2 blocks of dx (rows 2*by - pad, + 1)
+        const long long nb = (long long)d->dx.N * BH * BW * (d->dx.C / 8);
+        hn_pool_bwd_kernel<<<hn_cdiv(nb, 128), 128, 0, stream>>>(to_view(d->x), to_view(d->dy), to_view(d->dx), pad, BH, BW);
     }
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
