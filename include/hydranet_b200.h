@@ -509,6 +509,28 @@ int hn_det_loss(const float* classification, const float* regression, const floa
                 int32_t K, int32_t M, float alpha, float gamma, void* workspace, int64_t workspace_bytes, float* cls_loss, float* reg_loss,
                 float* dcls, float* dreg, void* stream);
 
+/* Segmentation loss (head_segment/segmentation_loss.py:48-65 with use_top_k): class-weighted cross-entropy
+ * per pixel (ignore_index pixels count as 0), the k largest values of every image, mean over the N*k kept values.  The k-th
+ * value is found by a 3-pass radix select (no sort); ties at the threshold share their weight in the gradient.
+ * logits fp32 [N][C][HW], target int64 [N][HW], weight fp32 [C].  hn_seg_loss_fwd writes loss[0] and keeps what the backward needs
+ * in the workspace (hn_seg_loss_workspace_bytes); hn_seg_loss_bwd writes dlogits = gout[0] * dloss/dlogits (gout: device scalar). */
+typedef struct hn_segloss_desc {
+    const float* logits;
+    const int64_t* target;
+    const float* weight;
+    int32_t N, C;
+    int64_t HW, k;
+    int32_t ignore_index;
+    void* workspace;
+    int64_t workspace_bytes;
+    float* loss;          /* fwd: [1] */
+    const float* gout;    /* bwd: [1] on the device */
+    float* dlogits;       /* bwd: [N][C][HW] */
+} hn_segloss_desc;
+int64_t hn_seg_loss_workspace_bytes(int32_t N, int64_t HW);
+int hn_seg_loss_fwd(const hn_segloss_desc* d, void* stream);
+int hn_seg_loss_bwd(const hn_segloss_desc* d, void* stream);
+
 /* Adam step over many tensors in one launch (torch.optim.Adam semantics, train.py:147: L2 weight decay added to the
  * gradient, bias-corrected moments).  Tensor table on the device. */
 typedef struct hn_adam_tensor {

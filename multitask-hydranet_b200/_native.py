@@ -79,6 +79,12 @@ class GconvSeDesc(C.Structure):
     _fields_ = [("vin", View), ("weight", C.c_void_p), ("bias", C.c_void_p), ("se", SePoolDesc)]
 
 
+class SegLossDesc(C.Structure):
+    _fields_ = [("logits", C.c_void_p), ("target", C.c_void_p), ("weight", C.c_void_p), ("N", C.c_int32), ("C", C.c_int32),
+                ("HW", C.c_int64), ("k", C.c_int64), ("ignore_index", C.c_int32), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+                ("loss", C.c_void_p), ("gout", C.c_void_p), ("dlogits", C.c_void_p)]
+
+
 class SeScaleDesc(C.Structure):
     _fields_ = [("x", View), ("scale", C.c_void_p)]
 
@@ -215,6 +221,9 @@ SYMBOLS = {
     "hn_se_apply": (C.c_int, [C.POINTER(Mat), _P, _P, C.c_int64, C.POINTER(Mat), _P]),
     "hn_pack_weights": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "hn_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), _P]),
+    "hn_seg_loss_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int64]),
+    "hn_seg_loss_fwd": (C.c_int, [C.POINTER(SegLossDesc), _P]),
+    "hn_seg_loss_bwd": (C.c_int, [C.POINTER(SegLossDesc), _P]),
     "hn_det_loss": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, C.c_int64, _P, _P, _P, _P, _P]),
     "hn_adam_step": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
                                C.c_float, _P, _P]),

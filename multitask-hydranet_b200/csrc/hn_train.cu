@@ -1633,3 +1633,227 @@ extern "C" int hn_det_loss(const float* classification, const float* regression,
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// segmentation loss (head_segment/segmentation_loss.py:48-65): class-weighted cross-entropy per
+// pixel, the k largest per image, mean over the N*k kept values -- and its gradient
+// ------------------------------------------------------------------------------------------------
+// Top-k without a sort: the k-th largest loss of an image is found by a 3-pass radix select on the fp32 bit pattern (losses are
+// >= 0, so the unsigned pattern orders like the value): per pass a shared-memory histogram of 11 / 11 / 10 key bits of the
+// elements that match the prefix found so far, then one CTA per image picks the bin that holds the k-th element.  After the last
+// pass tau[b] is exact, `need` = how many elements EQUAL to tau belong to the top k and n_eq = how many there are; the sum of the
+// kept values is sum(l > tau) + need * tau.  Ties at tau share their weight (need / n_eq each) in the gradient: torch.topk keeps
+// an unspecified subset of them, any choice is a valid subgradient, and the loss value is the same.
+static constexpr int kSegPx = 4096;   // pixels per CTA in the per-image passes
+static constexpr int kSelBins = 2048;
+struct SegSel {  // per image
+    unsigned prefix, mask;
+    long long k_rem;  // elements still to take from the matching set
+    float tau, frac;
+    long long n_eq;
+};
+struct SegLossParams {
+    const float* logits;
+    const long long* target;
+    const float* weight;
+    int N, C;
+    long long HW, k;
+    int ignore;
+    float* loss_px;
+    unsigned* hist;    // [N][kSelBins]
+    SegSel* sel;       // [N]
+    double* partial;   // [N][chunks]
+    int chunks;
+    float* loss;       // [1]
+    float* state;      // [N][2] = tau, frac (kept for the backward)
+};
+__global__ void __launch_bounds__(256) hn_segce_kernel(const SegLossParams p) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (i >= p.HW) return;
+    if (i == 0) {
+        SegSel s;
+        s.prefix = 0u; s.mask = 0u; s.k_rem = p.k; s.tau = 0.0f; s.frac = 0.0f; s.n_eq = 0;
+        p.sel[b] = s;
+    }
+    const long long t = p.target[(long long)b * p.HW + i];
+    float l = 0.0f;
+    if (t != p.ignore && t >= 0 && t < p.C) {
+        const float* x = p.logits + (long long)b * p.C * p.HW + i;
+        float m = x[0];
+        for (int c = 1; c < p.C; ++c) m = fmaxf(m, x[(long long)c * p.HW]);
+        float se = 0.0f;
+        for (int c = 0; c < p.C; ++c) se += expf(x[(long long)c * p.HW] - m);
+        l = p.weight[t] * (m + logf(se) - x[t * p.HW]);
+        l = fmaxf(l, 0.0f);  // -0.0 / rounding below zero would break the unsigned key order
+    }
+    p.loss_px[(long long)b * p.HW + i] = l;
+}
+__global__ void __launch_bounds__(256) hn_segsel_hist_kernel(const SegLossParams p, int shift, int bits) {
+    __shared__ unsigned sh[kSelBins];
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) sh[i] = 0u;
+    __syncthreads();
+    const SegSel s = p.sel[b];
+    const long long i0 = (long long)blockIdx.x * kSegPx, i1 = min(i0 + kSegPx, p.HW);
+    const float* l = p.loss_px + (long long)b * p.HW;
+    const unsigned bmask = (1u << bits) - 1u;
+    for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const unsigned key = __float_as_uint(l[i]);
+        if ((key & s.mask) == s.prefix) atomicAdd(&sh[(key >> shift) & bmask], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSelBins; i += blockDim.x)
+        if (sh[i]) atomicAdd(p.hist + (long long)b * kSelBins + i, sh[i]);
+}
+// one CTA of 256 threads per image: the bin (from the top) in which the running count reaches k_rem
+__global__ void __launch_bounds__(256) hn_segsel_pick_kernel(const SegLossParams p, int shift, int bits, int last) {
+    __shared__ unsigned long long tot[256];
+    const int b = blockIdx.x, t = threadIdx.x;
+    unsigned* h = p.hist + (long long)b * kSelBins;
+    unsigned v[8];
+    unsigned long long mine = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[j] = h[t * 8 + j]; mine += v[j]; h[t * 8 + j] = 0u; }  // zeroed for the next pass
+    tot[t] = mine;
+    __syncthreads();
+    unsigned long long above = 0;
+    for (int u = t + 1; u < 256; ++u) above += tot[u];
+    SegSel s = p.sel[b];
+    const unsigned long long k = (unsigned long long)s.k_rem;
+    __syncthreads();
+    if (above < k && k <= above + mine) {  // exactly one thread (k >= 1, k <= matching elements)
+        unsigned long long run = above;
+        int bin = t * 8 + 7;
+        for (int j = 7; j >= 0; --j) {
+            if (run + v[j] >= k) { bin = t * 8 + j; break; }
+            run += v[j];
+        }
+        s.prefix |= (unsigned)bin << shift;
+        s.mask |= ((1u << bits) - 1u) << shift;
+        s.k_rem = (long long)(k - run);
+        if (last) {
+            s.tau = __uint_as_float(s.prefix);
+            s.n_eq = (long long)v[bin - t * 8];
+            s.frac = (float)((double)s.k_rem / (double)s.n_eq);
+            p.state[b * 2] = s.tau;
+            p.state[b * 2 + 1] = s.frac;
+        }
+        p.sel[b] = s;
+    }
+}
+__global__ void __launch_bounds__(256) hn_segsel_sum_kernel(const SegLossParams p) {
+    __shared__ double sh[256];
+    const int b = blockIdx.y;
+    const float tau = p.sel[b].tau;
+    const long long i0 = (long long)blockIdx.x * kSegPx, i1 = min(i0 + kSegPx, p.HW);
+    const float* l = p.loss_px + (long long)b * p.HW;
+    double a = 0.0;
+    for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const float v = l[i];
+        if (v > tau) a += (double)v;
+    }
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {  // fixed tree: deterministic
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) p.partial[(long long)b * p.chunks + blockIdx.x] = sh[0];
+}
+__global__ void hn_segsel_finish_kernel(const SegLossParams p) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double total = 0.0;
+    for (int b = 0; b < p.N; ++b) {
+        double a = 0.0;
+        for (int c = 0; c < p.chunks; ++c) a += p.partial[(long long)b * p.chunks + c];
+        total += a + (double)p.sel[b].k_rem * (double)p.sel[b].tau;
+    }
+    p.loss[0] = (float)(total / ((double)p.N * (double)p.k));
+}
+__global__ void __launch_bounds__(256) hn_segce_bwd_kernel(const SegLossParams p, const float* __restrict__ gout, float* __restrict__ dlogits) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (i >= p.HW) return;
+    const float l = p.loss_px[(long long)b * p.HW + i];
+    const float tau = p.state[b * 2], frac = p.state[b * 2 + 1];
+    const long long t = p.target[(long long)b * p.HW + i];
+    float sel = l > tau ? 1.0f : (l == tau ? frac : 0.0f);
+    if (t == p.ignore || t < 0 || t >= p.C) sel = 0.0f;
+    float* d = dlogits + (long long)b * p.C * p.HW + i;
+    if (sel == 0.0f) {
+        for (int c = 0; c < p.C; ++c) d[(long long)c * p.HW] = 0.0f;
+        return;
+    }
+    const float* x = p.logits + (long long)b * p.C * p.HW + i;
+    float m = x[0];
+    for (int c = 1; c < p.C; ++c) m = fmaxf(m, x[(long long)c * p.HW]);
+    float se = 0.0f;
+    for (int c = 0; c < p.C; ++c) se += expf(x[(long long)c * p.HW] - m);
+    const float scale = sel * p.weight[t] * gout[0] / ((float)p.N * (float)p.k), inv = 1.0f / se;
+    for (int c = 0; c < p.C; ++c) {
+        const float pr = expf(x[(long long)c * p.HW] - m) * inv;
+        d[(long long)c * p.HW] = scale * (pr - (c == t ? 1.0f : 0.0f));
+    }
+}
+static size_t seg_loss_layout(int N, long long HW, SegLossParams* p, void* base) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* q = base ? static_cast<char*>(base) + off : nullptr;
+        off += (bytes + 255) & ~size_t(255);
+        return q;
+    };
+    const int chunks = (int)((HW + kSegPx - 1) / kSegPx);
+    unsigned* hist = static_cast<unsigned*>(take((size_t)N * kSelBins * sizeof(unsigned)));
+    SegSel* sel = static_cast<SegSel*>(take((size_t)N * sizeof(SegSel)));
+    double* partial = static_cast<double*>(take((size_t)N * chunks * sizeof(double)));
+    float* loss_px = static_cast<float*>(take((size_t)N * HW * sizeof(float)));
+    float* state = static_cast<float*>(take((size_t)N * 2 * sizeof(float)));
+    if (p) { p->hist = hist; p->sel = sel; p->partial = partial; p->loss_px = loss_px; p->state = state; p->chunks = chunks; }
+    return off;
+}
+extern "C" int64_t hn_seg_loss_workspace_bytes(int32_t N, int64_t HW) { return (int64_t)seg_loss_layout(N, HW, nullptr, nullptr); }
+static int seg_loss_params(const hn_segloss_desc* d, SegLossParams* p) {
+    HN_REQUIRE(d != nullptr && d->logits && d->target && d->weight && d->workspace, "seg loss: null pointer");
+    HN_REQUIRE(d->N >= 1 && d->C >= 1 && d->C <= 64 && d->HW >= 1 && d->k >= 1 && d->k <= d->HW, "seg loss: bad sizes (N=%d C=%d HW=%lld k=%lld)", d->N,
+               d->C, (long long)d->HW, (long long)d->k);
+    HN_REQUIRE((int64_t)seg_loss_layout(d->N, d->HW, nullptr, nullptr) <= d->workspace_bytes, "seg loss: workspace too small");
+    memset(p, 0, sizeof(*p));
+    p->logits = d->logits; p->target = reinterpret_cast<const long long*>(d->target); p->weight = d->weight;
+    p->N = d->N; p->C = d->C; p->HW = d->HW; p->k = d->k; p->ignore = d->ignore_index;
+    seg_loss_layout(d->N, d->HW, p, d->workspace);
+    return HN_OK;
+}
+extern "C" int hn_seg_loss_fwd(const hn_segloss_desc* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    SegLossParams p;
+    if (int rc = seg_loss_params(d, &p)) return rc;
+    HN_REQUIRE(d->loss != nullptr, "seg loss: null output");
+    p.loss = d->loss;
+    const dim3 gpx((unsigned)hn_cdiv(p.HW, 256), (unsigned)p.N), gch((unsigned)p.chunks, (unsigned)p.N);
+    HN_CHECK_CUDA(cudaMemsetAsync(p.hist, 0, (size_t)p.N * kSelBins * sizeof(unsigned), stream));
+    hn_segce_kernel<<<gpx, 256, 0, stream>>>(p);
+    HN_CHECK_CUDA(cudaGetLastError());
+    const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
+    for (int pass = 0; pass < 3; ++pass) {
+        hn_segsel_hist_kernel<<<gch, 256, 0, stream>>>(p, shifts[pass], bits[pass]);
+        HN_CHECK_CUDA(cudaGetLastError());
+        hn_segsel_pick_kernel<<<p.N, 256, 0, stream>>>(p, shifts[pass], bits[pass], pass == 2);
+        HN_CHECK_CUDA(cudaGetLastError());
+    }
+    hn_segsel_sum_kernel<<<gch, 256, 0, stream>>>(p);
+    HN_CHECK_CUDA(cudaGetLastError());
+    hn_segsel_finish_kernel<<<1, 32, 0, stream>>>(p);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}
+extern "C" int hn_seg_loss_bwd(const hn_segloss_desc* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    SegLossParams p;
+    if (int rc = seg_loss_params(d, &p)) return rc;
+    HN_REQUIRE(d->gout != nullptr && d->dlogits != nullptr, "seg loss bwd: null pointer");
+    const dim3 gpx((unsigned)hn_cdiv(p.HW, 256), (unsigned)p.N);
+    hn_segce_bwd_kernel<<<gpx, 256, 0, stream>>>(p, d->gout, d->dlogits);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}

@@ -38,6 +38,45 @@ def seg_loss(prediction, target, class_weights, use_top_k, top_k_ratio, use_foca
     return torch.mean(loss)
 
 
+class NativeSegLoss(torch.autograd.Function):
+    """``seg_loss`` with ``use_top_k`` as a native op (``hn_seg_loss_fwd/bwd``): cross-entropy kernel, 3-pass radix select of the
+    k-th largest value per image (no sort), deterministic sums; one backward kernel writes the logits' gradient.  Ties at the
+    threshold share their weight (torch.topk keeps an unspecified subset: same loss value, an equally valid subgradient)."""
+
+    @staticmethod
+    def forward(ctx, prediction, target, class_weights, top_k_ratio, ignore_index=255):
+        from . import _native as nv
+        x = prediction.detach().float().contiguous()
+        N, Cc, H, W = x.shape
+        dev = x.device
+        t = target.detach().to(dev, torch.int64).contiguous()
+        w = class_weights.detach().to(dev, torch.float32).contiguous()
+        k = int(top_k_ratio * (H * W))
+        ws = torch.empty(nv.lib.hn_seg_loss_workspace_bytes(N, H * W), dtype=torch.uint8, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        d = nv.SegLossDesc(x.data_ptr(), t.data_ptr(), w.data_ptr(), N, Cc, H * W, k, int(ignore_index), ws.data_ptr(), ws.numel(),
+                           loss.data_ptr(), None, None)
+        with torch.cuda.device(dev):
+            nv.check(nv.lib.hn_seg_loss_fwd(d, torch.cuda.current_stream(dev).cuda_stream))
+        ctx.save_for_backward(x, t, w, ws)
+        ctx.k, ctx.ignore = k, int(ignore_index)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import _native as nv
+        x, t, w, ws = ctx.saved_tensors
+        N, Cc, H, W = x.shape
+        dev = x.device
+        gout = g.detach().to(dev, torch.float32).reshape(1).contiguous()
+        dx = torch.empty_like(x)
+        d = nv.SegLossDesc(x.data_ptr(), t.data_ptr(), w.data_ptr(), N, Cc, H * W, ctx.k, ctx.ignore, ws.data_ptr(), ws.numel(),
+                           None, gout.data_ptr(), dx.data_ptr())
+        with torch.cuda.device(dev):
+            nv.check(nv.lib.hn_seg_loss_bwd(d, torch.cuda.current_stream(dev).cuda_stream))
+        return dx, None, None, None, None
+
+
 def detection_loss(classifications, regressions, anchors, annotations, alpha=0.25, gamma=2.0):
     """annotations: [B, M, 5] (x1, y1, x2, y2, class), rows with class -1 are padding (dataloader.py:593-609)."""
     dtype = classifications.dtype
@@ -165,8 +204,12 @@ def cal_loss(model, pred_dict, gt_dict):
         cache = model.__dict__.setdefault("_loss_consts", {})
         if ("seg_w", dev) not in cache:  # uploaded once: a CUDA-graph capture of the step must not see host->device copies
             cache[("seg_w", dev)] = torch.tensor(sc["class_weight"], dtype=torch.float32, device=dev)
-        out["loss_seg"] = seg_loss(pred_dict["seg"], gt_dict["gt_seg"].to(dev).long(), cache[("seg_w", dev)],
-                                   sc["use_top_k"], sc["top_k_ratio"], sc["use_focal"])
+        if (pred_dict["seg"].is_cuda and getattr(model, "native_seg_loss", True) and sc["use_top_k"] and not sc["use_focal"]
+                and int(sc["top_k_ratio"] * pred_dict["seg"].shape[2] * pred_dict["seg"].shape[3]) >= 1):
+            out["loss_seg"] = NativeSegLoss.apply(pred_dict["seg"], gt_dict["gt_seg"], cache[("seg_w", dev)], sc["top_k_ratio"])
+        else:
+            out["loss_seg"] = seg_loss(pred_dict["seg"], gt_dict["gt_seg"].to(dev).long(), cache[("seg_w", dev)],
+                                       sc["use_top_k"], sc["top_k_ratio"], sc["use_focal"])
     if model.train_detect:
         det = pred_dict["detection"]
         if det["classification"].is_cuda and getattr(model, "native_det_loss", True) and gt_dict["gt_det"].shape[1] <= 64:

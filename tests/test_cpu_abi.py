@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 def test_struct_layouts_match_the_c_compiler():
     structs = {"hn_view": nv.View, "hn_tap": nv.Tap, "hn_conv_desc": nv.ConvDesc, "hn_stem_desc": nv.StemDesc,
                "hn_node_desc": nv.NodeDesc, "hn_dw_multi_desc": nv.DwMultiDesc, "hn_pool_desc": nv.PoolDesc, "hn_lanefuse_desc": nv.LaneFuseDesc,
-               "hn_se_pool_desc": nv.SePoolDesc, "hn_se_scale_desc": nv.SeScaleDesc, "hn_gconv_se_desc": nv.GconvSeDesc, "hn_det_desc": nv.DetDesc, "hn_lane_desc": nv.LaneDesc,
+               "hn_se_pool_desc": nv.SePoolDesc, "hn_se_scale_desc": nv.SeScaleDesc, "hn_gconv_se_desc": nv.GconvSeDesc, "hn_segloss_desc": nv.SegLossDesc, "hn_det_desc": nv.DetDesc, "hn_lane_desc": nv.LaneDesc,
                "hn_mat": nv.Mat, "hn_bn_desc": nv.BnDesc, "hn_actbwd_desc": nv.ActBwdDesc, "hn_wsum_desc": nv.WsumDesc,
                "hn_resample_desc": nv.ResampleDesc, "hn_seggather_desc": nv.SegGatherDesc, "hn_headgrad_desc": nv.HeadGradDesc,
                "hn_sefc_desc": nv.SeFcDesc, "hn_pack_entry": nv.PackEntry, "hn_wgrad_desc": nv.WgradDesc, "hn_adam_tensor": nv.AdamTensor}

@@ -7,6 +7,7 @@ import torch.nn.functional as F
 
 import hydranet_b200  # noqa: F401
 from hydranet_b200 import _native as nv
+from hydranet_b200 import losses
 from hydranet_b200 import train as T
 
 pytestmark = pytest.mark.gpu
@@ -386,3 +387,49 @@ def test_native_detection_loss_matches_the_pinned_torch_loss():
     assert float((a[2] - b[2]).abs().max()) <= 2e-5 * float(b[2].abs().max())
     assert float((a[3] - b[3]).abs().max()) <= 2e-5 * float(b[3].abs().max())
     assert float(b[3].abs().max()) > 0 and float(b[2].abs().max()) > 0
+
+
+@pytest.mark.parametrize("N,H,W,ratio,ignore_frac", [(3, 40, 56, 0.3, 0.1), (2, 64, 64, 0.3, 0.0), (2, 33, 17, 0.05, 0.85), (1, 640, 640, 0.3, 0.02)])
+def test_native_seg_loss_matches_the_pinned_torch_loss(N, H, W, ratio, ignore_frac):
+    """hn_seg_loss_fwd/bwd (cross-entropy + radix-select top-k) against losses.seg_loss, which is pinned
+    against the live reference (tests/test_cpu_losses.py).  Continuous random logits: no ties at the threshold except the zeros
+    of ignored pixels, which carry no gradient either way (third case: k exceeds the number of non-ignored pixels)."""
+    g = torch.Generator().manual_seed(N * 100 + H)
+    logits0 = (torch.randn((N, 5, H, W), generator=g) * 2.0).cuda()
+    tgt = torch.randint(0, 5, (N, H, W), generator=g)
+    tgt[torch.rand((N, H, W), generator=g) < ignore_frac] = 255
+    tgt = tgt.cuda()
+    w = torch.tensor([0.1, 0.5, 1.0, 5.0, 5.0], device="cuda")
+    res = {}
+    for name in ("torch", "native"):
+        x = logits0.clone().requires_grad_()
+        if name == "torch":
+            loss = losses.seg_loss(x, tgt, w, True, ratio, False)
+        else:
+            loss = losses.NativeSegLoss.apply(x, tgt, w, ratio)
+        (5.0 * loss).backward()
+        res[name] = (float(loss), x.grad.clone())
+    a, b = res["native"], res["torch"]
+    assert abs(a[0] - b[0]) <= 2e-6 * abs(b[0]), (a[0], b[0])
+    assert float(b[1].abs().max()) > 0
+    assert float((a[1] - b[1]).abs().max()) <= 2e-5 * float(b[1].abs().max())
+    assert int(((a[1] != 0) != (b[1] != 0)).sum()) == 0, "a different set of pixels was kept"
+
+
+def test_native_seg_loss_ties_share_their_weight():
+    """Identical pixels (exact ties at the threshold): the loss value equals torch's; the gradient is spread over the tied
+    pixels instead of an arbitrary subset, and sums to the same total."""
+    x0 = torch.zeros((1, 5, 8, 8), device="cuda")
+    x0[:, 2] = 1.5  # every pixel identical
+    tgt = torch.ones((1, 8, 8), dtype=torch.int64, device="cuda")
+    w = torch.tensor([0.1, 0.5, 1.0, 5.0, 5.0], device="cuda")
+    res = {}
+    for name in ("torch", "native"):
+        x = x0.clone().requires_grad_()
+        loss = losses.seg_loss(x, tgt, w, True, 0.25, False) if name == "torch" else losses.NativeSegLoss.apply(x, tgt, w, 0.25)
+        loss.backward()
+        res[name] = (float(loss), x.grad.clone())
+    assert abs(res["native"][0] - res["torch"][0]) <= 1e-6 * abs(res["torch"][0])
+    gn, gt = res["native"][1], res["torch"][1]
+    assert torch.allclose(gn.sum(dim=(2, 3)), gt.sum(dim=(2, 3)), rtol=1e-5, atol=1e-7)
+    assert float(gn.abs().max()) <= float(gt.abs().max()) * 0.26  # 16 of 64 pixels kept: a quarter of the weight each
