@@ -531,6 +531,17 @@ int64_t hn_seg_loss_workspace_bytes(int32_t N, int64_t HW);
 int hn_seg_loss_fwd(const hn_segloss_desc* d, void* stream);
 int hn_seg_loss_bwd(const hn_segloss_desc* d, void* stream);
 
+/* Lane losses (head_lane/lanedetect_loss.py:18-78) in three launches: two-class log-softmax with online
+ * hard-negative mining (negative_num = clamp(n_pos * negative_ratio, 1, n_neg) negatives with the smallest background
+ * log-probability, found by a radix select; ties at the threshold included, as `bg <= kth` does) and the masked Huber loss of
+ * the positive anchors (entries weighted_index, weighted_index + 1 of a row weigh alpha; zeros of the target are skipped).
+ * cls_targets / cls_preds fp32 [T][2], loc_targets / loc_preds fp32 [T][L].  out4 = (total_pos, total_neg, loc, positive_num);
+ * dcls [2][T][2] = the gradients of total_pos and of total_neg w.r.t. cls_preds; dloc [T][L] = gradient of loc w.r.t. loc_preds. */
+int64_t hn_lane_loss_workspace_bytes(int32_t T);
+int hn_lane_loss(const float* cls_targets, const float* cls_preds, const float* loc_targets, const float* loc_preds, int32_t T, int32_t L,
+                 int32_t weighted_index, float negative_ratio, float alpha, void* workspace, int64_t workspace_bytes, float* out4, float* dcls,
+                 float* dloc, void* stream);
+
 /* Adam step over many tensors in one launch (torch.optim.Adam semantics, train.py:147: L2 weight decay added to the
  * gradient, bias-corrected moments).  Tensor table on the device. */
 typedef struct hn_adam_tensor {

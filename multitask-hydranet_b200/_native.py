@@ -224,6 +224,8 @@ SYMBOLS = {
     "hn_seg_loss_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int64]),
     "hn_seg_loss_fwd": (C.c_int, [C.POINTER(SegLossDesc), _P]),
     "hn_seg_loss_bwd": (C.c_int, [C.POINTER(SegLossDesc), _P]),
+    "hn_lane_loss_workspace_bytes": (C.c_int64, [C.c_int32]),
+    "hn_lane_loss": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, C.c_int64, _P, _P, _P, _P]),
     "hn_det_loss": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, C.c_int64, _P, _P, _P, _P, _P]),
     "hn_adam_step": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
                                C.c_float, _P, _P]),

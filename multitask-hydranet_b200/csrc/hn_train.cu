@@ -1857,3 +1857,187 @@ extern "C" int hn_seg_loss_bwd(const hn_segloss_desc* d, void* stream_) {
     HN_CHECK_CUDA(cudaGetLastError());
     return HN_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// lane losses (head_lane/lanedetect_loss.py:18-78): two-class log-softmax with online hard-negative
+// mining (the negative_num negatives with the smallest background log-probability, ties included) and the masked Huber
+// regression loss over the positive anchors -- values and gradients
+// ------------------------------------------------------------------------------------------------
+struct LaneLossParams {
+    const float* cls_t;   // [T][2]  (column 1 > 0: positive)
+    const float* cls_p;   // [T][2]
+    const float* loc_t;   // [T][L]
+    const float* loc_p;   // [T][L]
+    int T, L, wpos;       // entries wpos, wpos + 1 of a row carry the weight `alpha`
+    float neg_ratio, alpha;
+    float* out;           // [4] = total_pos, total_neg, loc, positive_num
+    float* dcls;          // [2][T][2]: d total_pos / d cls_p, d total_neg / d cls_p
+    float* dloc;          // [T][L]
+    float* per_anchor;    // [T] scratch
+    unsigned char* pmask; // [T] scratch
+};
+__device__ __forceinline__ unsigned asc_key(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ void lane_logp(const float* x, float& l0, float& l1) {
+    const float m = fmaxf(x[0], x[1]);
+    const float lse = m + logf(expf(x[0] - m) + expf(x[1] - m));
+    l0 = x[0] - lse;
+    l1 = x[1] - lse;
+}
+// deterministic block sums (fixed tree) of up to two doubles / two ints
+__device__ __forceinline__ double lane_block_sum(double v, double* sh) {
+    __syncthreads();
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    return sh[0];
+}
+__global__ void __launch_bounds__(1024) hn_lane_cls_loss_kernel(const LaneLossParams p) {
+    __shared__ double shd[1024];
+    __shared__ unsigned hist[256];
+    __shared__ unsigned s_prefix, s_mask;
+    __shared__ long long s_krem;
+    const int T = p.T;
+    double np = 0.0;
+    float* bg = p.per_anchor;  // the background log-probabilities, computed ONCE: the select and the final test must see the same bits
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+        const bool pos = p.cls_t[i * 2 + 1] > 0.0f;
+        p.pmask[i] = pos ? 1 : 0;
+        np += pos ? 1.0 : 0.0;
+        float l0, l1;
+        lane_logp(p.cls_p + i * 2, l0, l1);
+        bg[i] = l0;
+    }
+    const double n_pos = lane_block_sum(np, shd), n_neg = (double)T - n_pos;
+    const double pos_num = fmax(n_pos, 1.0);
+    long long neg_num = (long long)fmin(fmax(n_pos * (double)p.neg_ratio, 1.0), n_neg);
+    // k-th smallest background log-probability among the negatives: radix select on an order-preserving key, 4 x 8 bits
+    if (threadIdx.x == 0) { s_prefix = 0u; s_mask = 0u; s_krem = neg_num; }
+    float kth = -INFINITY;
+    if (neg_num >= 1) {
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            if (threadIdx.x < 256) hist[threadIdx.x] = 0u;
+            __syncthreads();
+            const unsigned prefix = s_prefix, mask = s_mask;
+            for (int i = threadIdx.x; i < T; i += blockDim.x) {
+                if (p.cls_t[i * 2 + 1] > 0.0f) continue;
+                const unsigned key = asc_key(bg[i]);
+                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long run = 0;
+                const unsigned long long k = (unsigned long long)s_krem;
+                int bin = 255;
+                for (int b = 0; b < 256; ++b) {
+                    if (run + hist[b] >= k) { bin = b; break; }
+                    run += hist[b];
+                }
+                s_prefix = prefix | ((unsigned)bin << shift);
+                s_mask = mask | (255u << shift);
+                s_krem = (long long)(k - run);
+            }
+            __syncthreads();
+        }
+        const unsigned key = s_prefix;  // invert asc_key
+        kth = __uint_as_float((key & 0x80000000u) ? (key & 0x7FFFFFFFu) : ~key);
+    }
+    double sp = 0.0, sn = 0.0;
+    const float cp = -p.alpha / (float)pos_num;
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+        float l0, l1;
+        lane_logp(p.cls_p + i * 2, l0, l1);
+        const bool pos = p.cls_t[i * 2 + 1] > 0.0f;
+        const bool hard = !pos && bg[i] <= kth;
+        const float p0 = expf(l0), p1 = expf(l1);
+        // d logp1 / dx = (-p0, 1 - p1); d logp0 / dx = (1 - p0, -p1)
+        p.dcls[i * 2] = pos ? cp * -p0 : 0.0f;
+        p.dcls[i * 2 + 1] = pos ? cp * (1.0f - p1) : 0.0f;
+        p.dcls[(T + i) * 2] = hard ? cp * (1.0f - p0) : 0.0f;
+        p.dcls[(T + i) * 2 + 1] = hard ? cp * -p1 : 0.0f;
+        if (pos) sp += (double)(p.alpha * l1);
+        if (hard) sn += (double)(p.alpha * l0);
+    }
+    const double tp = lane_block_sum(sp, shd);
+    const double tn = lane_block_sum(sn, shd);
+    if (threadIdx.x == 0) {
+        p.out[0] = (float)(-tp / pos_num);
+        p.out[1] = (float)(-tn / pos_num);
+        p.out[3] = (float)pos_num;
+    }
+}
+// one warp per anchor
+__global__ void __launch_bounds__(256) hn_lane_loc_loss_kernel(const LaneLossParams p) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= p.T) return;
+    const float* t = p.loc_t + (long long)i * p.L;
+    const float* q = p.loc_p + (long long)i * p.L;
+    float* d = p.dloc + (long long)i * p.L;
+    if (!p.pmask[i]) {
+        for (int j = lane; j < p.L; j += 32) d[j] = 0.0f;
+        if (lane == 0) p.per_anchor[i] = 0.0f;
+        return;
+    }
+    float s = 0.0f, nv = 0.0f;
+    for (int j = lane; j < p.L; j += 32) {
+        const float tv = t[j];
+        if (tv != 0.0f) {
+            const float w = (j == p.wpos || j == p.wpos + 1) ? p.alpha : 1.0f;
+            const float e = q[j] - tv, ae = fabsf(e);
+            s += w * (ae < 1.0f ? e * e * 0.5f : ae - 0.5f);
+            nv += 1.0f;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        nv += __shfl_xor_sync(0xffffffffu, nv, o);
+    }
+    const float inv = 1.0f / fmaxf(nv, 1.0f), pn = p.out[3];
+    if (lane == 0) p.per_anchor[i] = s * inv;
+    for (int j = lane; j < p.L; j += 32) {
+        const float tv = t[j];
+        float g = 0.0f;
+        if (tv != 0.0f) {
+            const float w = (j == p.wpos || j == p.wpos + 1) ? p.alpha : 1.0f;
+            const float e = q[j] - tv;
+            g = w * fminf(fmaxf(e, -1.0f), 1.0f) * inv / pn;
+        }
+        d[j] = g;
+    }
+}
+__global__ void __launch_bounds__(1024) hn_lane_loc_finish_kernel(const LaneLossParams p) {
+    __shared__ double shd[1024];
+    double a = 0.0;
+    for (int i = threadIdx.x; i < p.T; i += blockDim.x) a += (double)p.per_anchor[i];
+    const double tot = lane_block_sum(a, shd);
+    if (threadIdx.x == 0) p.out[2] = (float)(tot / (double)p.out[3]);
+}
+extern "C" int64_t hn_lane_loss_workspace_bytes(int32_t T) { return (int64_t)T * 4 + (((int64_t)T + 255) & ~255LL) + 256; }
+extern "C" int hn_lane_loss(const float* cls_targets, const float* cls_preds, const float* loc_targets, const float* loc_preds, int32_t T, int32_t L,
+                            int32_t weighted_index, float negative_ratio, float alpha, void* workspace, int64_t workspace_bytes, float* out4, float* dcls,
+                            float* dloc, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    HN_REQUIRE(cls_targets && cls_preds && loc_targets && loc_preds && workspace && out4 && dcls && dloc, "lane loss: null pointer");
+    HN_REQUIRE(T >= 1 && T <= (1 << 24) && L >= 1 && weighted_index >= 0 && weighted_index + 1 < L, "lane loss: bad sizes (T=%d L=%d)", T, L);
+    HN_REQUIRE(workspace_bytes >= hn_lane_loss_workspace_bytes(T), "lane loss: workspace too small");
+    LaneLossParams p;
+    memset(&p, 0, sizeof(p));
+    p.cls_t = cls_targets; p.cls_p = cls_preds; p.loc_t = loc_targets; p.loc_p = loc_preds;
+    p.T = T; p.L = L; p.wpos = weighted_index; p.neg_ratio = negative_ratio; p.alpha = alpha;
+    p.out = out4; p.dcls = dcls; p.dloc = dloc;
+    p.per_anchor = static_cast<float*>(workspace);
+    p.pmask = static_cast<unsigned char*>(workspace) + (size_t)T * 4;
+    hn_lane_cls_loss_kernel<<<1, 1024, 0, stream>>>(p);
+    HN_CHECK_CUDA(cudaGetLastError());
+    hn_lane_loc_loss_kernel<<<hn_cdiv(T, 8), 256, 0, stream>>>(p);
+    HN_CHECK_CUDA(cudaGetLastError());
+    hn_lane_loc_finish_kernel<<<1, 1024, 0, stream>>>(p);
+    HN_CHECK_CUDA(cudaGetLastError());
+    return HN_OK;
+}

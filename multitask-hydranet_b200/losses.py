@@ -193,6 +193,39 @@ def lane_reg_loss(pmask, positive_num, loc_targets, loc_preds, alpha=10, points_
     return torch.sum(per_anchor) / positive_num
 
 
+class NativeLaneLoss(torch.autograd.Function):
+    """``lane_cls_loss`` + ``lane_reg_loss`` as one native op (``hn_lane_loss``, three launches instead of ~40 torch kernels and a
+    sort): returns (total_pos, total_neg, loc)."""
+
+    @staticmethod
+    def forward(ctx, cls_targets, cls_preds, loc_targets, loc_preds, negative_ratio=15, alpha=10, points_per_line=160):
+        from . import _native as nv
+        dev = cls_preds.device
+        cp = cls_preds.detach().float().reshape(-1, 2).contiguous()
+        ct = cls_targets.detach().to(dev, torch.float32).reshape(-1, 2).contiguous()
+        L = loc_preds.shape[-1]
+        lp = loc_preds.detach().float().reshape(-1, L).contiguous()
+        lt = loc_targets.detach().to(dev, torch.float32).reshape(-1, L).contiguous()
+        T = cp.shape[0]
+        ws = torch.empty(nv.lib.hn_lane_loss_workspace_bytes(T), dtype=torch.uint8, device=dev)
+        out = torch.empty(4, dtype=torch.float32, device=dev)
+        dcls = torch.empty((2, T, 2), dtype=torch.float32, device=dev)
+        dloc = torch.empty((T, L), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            nv.check(nv.lib.hn_lane_loss(ct.data_ptr(), cp.data_ptr(), lt.data_ptr(), lp.data_ptr(), T, L, int(points_per_line), float(negative_ratio),
+                                         float(alpha), ws.data_ptr(), ws.numel(), out.data_ptr(), dcls.data_ptr(), dloc.data_ptr(),
+                                         torch.cuda.current_stream(dev).cuda_stream))
+        ctx.save_for_backward(dcls, dloc)
+        ctx.shapes = (cls_preds.shape, loc_preds.shape)
+        return out[0], out[1], out[2]
+
+    @staticmethod
+    def backward(ctx, g_pos, g_neg, g_loc):
+        dcls, dloc = ctx.saved_tensors
+        cs, ls = ctx.shapes
+        return None, (dcls[0] * g_pos + dcls[1] * g_neg).reshape(cs), None, (dloc * g_loc).reshape(ls), None, None, None
+
+
 def cal_loss(model, pred_dict, gt_dict):
     """model/model.py:201-264: dict of the heads' loss terms (the caller weights and sums them, train.py:192-203)."""
     out = {}
@@ -220,9 +253,14 @@ def cal_loss(model, pred_dict, gt_dict):
     if model.train_lane:
         lane = pred_dict["lane"]
         dev = lane["predict_cls"].device
-        pos, neg, pmask, n_pos = lane_cls_loss(gt_dict["gt_cls"].to(dev), lane["predict_cls"])
-        out["loss_lane_cls_pos"], out["loss_lane_cls_neg"] = pos, neg
-        out["loss_lane_loc"] = lane_reg_loss(pmask, n_pos, gt_dict["gt_loc"].to(dev), lane["predict_loc"])
+        if (lane["predict_cls"].is_cuda and getattr(model, "native_lane_loss", True) and lane["predict_cls"].shape[-1] == 2
+                and lane["predict_loc"].shape[-1] >= 162):
+            out["loss_lane_cls_pos"], out["loss_lane_cls_neg"], out["loss_lane_loc"] = NativeLaneLoss.apply(
+                gt_dict["gt_cls"], lane["predict_cls"], gt_dict["gt_loc"], lane["predict_loc"])
+        else:
+            pos, neg, pmask, n_pos = lane_cls_loss(gt_dict["gt_cls"].to(dev), lane["predict_cls"])
+            out["loss_lane_cls_pos"], out["loss_lane_cls_neg"] = pos, neg
+            out["loss_lane_loc"] = lane_reg_loss(pmask, n_pos, gt_dict["gt_loc"].to(dev), lane["predict_loc"])
     if getattr(model, "check_loss_finite", False):
         for k, v in out.items():
             if float(v) == 0 or not torch.isfinite(v):

@@ -433,3 +433,39 @@ def test_native_seg_loss_ties_share_their_weight():
     gn, gt = res["native"][1], res["torch"][1]
     assert torch.allclose(gn.sum(dim=(2, 3)), gt.sum(dim=(2, 3)), rtol=1e-5, atol=1e-7)
     assert float(gn.abs().max()) <= float(gt.abs().max()) * 0.26  # 16 of 64 pixels kept: a quarter of the weight each
+
+
+@pytest.mark.parametrize("B,na,L,n_pos", [(4, 400, 162, 5), (2, 100, 162, 0), (1, 64, 162, 40), (16, 400, 162, 3)])
+def test_native_lane_loss_matches_the_pinned_torch_losses(B, na, L, n_pos):
+    """hn_lane_loss (OHEM classification + masked Huber regression) against losses.lane_cls_loss /
+    lane_reg_loss, which are pinned against the live reference (tests/test_cpu_losses.py).  Cases: the usual few positives, none
+    at all (positive_num clamps to 1, one hard negative), more positives than negative_ratio leaves negatives for."""
+    g = torch.Generator().manual_seed(B * 1000 + na + n_pos)
+    gt_cls = torch.zeros((B, na, 2)); gt_cls[:, :, 0] = 1.0
+    gt_loc = torch.zeros((B, na, L))
+    for b in range(B):
+        pos = torch.randperm(na, generator=g)[:n_pos]
+        gt_cls[b, pos, 0], gt_cls[b, pos, 1] = 0.0, 1.0
+        gt_loc[b, pos] = torch.randn((n_pos, L), generator=g) * 2.0
+        gt_loc[b, pos, 7] = 0.0  # an invalid point inside a positive row
+        gt_loc[b, pos, L - 2] = torch.randint(1, 80, (n_pos,), generator=g).float()
+        gt_loc[b, pos, L - 1] = torch.randint(1, 80, (n_pos,), generator=g).float()
+    gt_cls, gt_loc = gt_cls.cuda(), gt_loc.cuda()
+    pc0 = (torch.randn((B, na, 2), generator=g) * 1.5).cuda()
+    pl0 = (torch.randn((B, na, L), generator=g) * 1.5).cuda()
+    res = {}
+    for name in ("torch", "native"):
+        pc, pl = pc0.clone().requires_grad_(), pl0.clone().requires_grad_()
+        if name == "torch":
+            pos, neg, pmask, npos = losses.lane_cls_loss(gt_cls, pc)
+            loc = losses.lane_reg_loss(pmask, npos, gt_loc, pl)
+        else:
+            pos, neg, loc = losses.NativeLaneLoss.apply(gt_cls, pc, gt_loc, pl)
+        (1.0 * pos + 2.0 * neg + 3.0 * loc).backward()
+        res[name] = (float(pos), float(neg), float(loc), pc.grad.clone(), pl.grad.clone())
+    a, b = res["native"], res["torch"]
+    for i in range(3):
+        assert abs(a[i] - b[i]) <= 3e-6 * max(abs(b[i]), 1e-3), (i, a[:3], b[:3])
+    assert float((a[3] - b[3]).abs().max()) <= 2e-5 * max(float(b[3].abs().max()), 1e-6)
+    assert float((a[4] - b[4]).abs().max()) <= 2e-5 * max(float(b[4].abs().max()), 1e-6)
+    assert int(((a[3] != 0) != (b[3] != 0)).sum()) == 0, "a different set of hard negatives"
