@@ -22,7 +22,11 @@ x = synth.synth_input(2, 128, 128, seed=3).cuda()
 gt = {k: v.cuda() for k, v in train_golden.synthetic_gt(2, 128, 128, 4, 4, 16, seed=5).items()}
 out = m(x)
 c, r = losses.NativeDetectionLoss.apply(out["detection"]["classification"], out["detection"]["regression"], out["detection"]["anchors"], gt["gt_det"])
-loss = out["seg"].square().mean() + c + 50 * r + out["lane"]["predict_loc"].square().mean() + out["lane"]["predict_cls"].square().mean()
+w = torch.tensor(cfg["segment"]["class_weight"], device="cuda")
+seg = losses.NativeSegLoss.apply(out["seg"], gt["gt_seg"], w, 0.3)
+L = out["lane"]["predict_loc"].shape[-1]
+lp, ln, ll = losses.NativeLaneLoss.apply(gt["gt_cls"], out["lane"]["predict_cls"], gt["gt_loc"], out["lane"]["predict_loc"], 15, 10, L - 2)
+loss = 5 * seg + c + 50 * r + lp + ln + ll
 loss.backward()
 opt.step()
 torch.cuda.synchronize()
