@@ -247,6 +247,7 @@ typedef struct hn_lane_desc {
 /* ---- single-shot entry points (each enqueues on `stream` and returns) ---- */
 int hn_conv_fwd(const hn_conv_desc* d, void* stream);
 int hn_stem_fwd(const hn_stem_desc* d, void* stream);
+void hn_stem_set_mma(int on); /* 1 (default): tensor-core stem with (hi, lo) bf16 splits; 0: the fp32 CUDA-core kernel */
 int hn_node_fwd(const hn_node_desc* d, void* stream);
 int hn_dw_multi_fwd(const hn_dw_multi_desc* d, void* stream);
 int hn_pool_fwd(const hn_pool_desc* d, void* stream);

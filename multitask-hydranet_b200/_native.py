@@ -197,6 +197,7 @@ SYMBOLS = {
     "hn_gconv_se_fwd": (C.c_int, [C.POINTER(GconvSeDesc), _P]),
     "hn_gconv_se_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "hn_se_fused_set_debug": (None, [_P]),
+    "hn_stem_set_mma": (None, [C.c_int]),
     "hn_preprocess_fwd": (C.c_int, [C.POINTER(PreprocessDesc), _P]),
     "hn_seg_argmax": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P]),
     "hn_u8_to_i64": (C.c_int, [_P, _P, C.c_int64, _P]),
@@ -294,6 +295,8 @@ if os.environ.get("HN_BRANCH_PRIO"):
     lib.hn_plan_set_branch_priority(int(os.environ["HN_BRANCH_PRIO"]))
 if os.environ.get("HN_ROUNDS_PASSES"):
     lib.hn_det_set_rounds_passes(int(os.environ["HN_ROUNDS_PASSES"]))
+if os.environ.get("HN_STEM_MMA"):
+    lib.hn_stem_set_mma(int(os.environ["HN_STEM_MMA"]))
 if os.environ.get("HN_SE_SPLIT_FC"):
     lib.hn_se_set_split_fc(int(os.environ["HN_SE_SPLIT_FC"]))
 if os.environ.get("HN_CLUSTER"):

@@ -78,6 +78,147 @@ __global__ void __launch_bounds__(128) hn_stem_kernel(const float* __restrict__ 
     }
 }
 
+// The same convolution on the tensor cores.  The fp32 kernel above is bound by its FMAs (864 per output pixel: 221 us at batch 32,
+// a quarter of the HBM rate).  Here a warp owns 16 consecutive output pixels of a row: the 27 taps are the K dimension (padded to
+// 32, k = ci*9 + ky*3 + kx) of a 16 x 32 x 32 product in mma.sync m16n8k16.  Inputs and weights are split into bf16 (hi, lo)
+// pairs and three products are accumulated (hi*hi + lo*hi + hi*lo, fp32 accumulators): the result carries ~16 mantissa bits, i.e.
+// fp32-conv accuracy at the bf16 output -- the first layer adds no rounding of its own.  A thread gathers exactly the 16 input
+// samples its A fragments need (its 8 k indices x 2 pixel rows); the output tile goes through a padded shared-memory tile so that
+// the global stores are 16-byte vectors of one pixel's channels.
+__device__ __forceinline__ void stem_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    hi = hn_pack_bf16x2(v0, v1);
+    const float2 h = hn_unpack_bf16x2(hi);
+    lo = hn_pack_bf16x2(v0 - h.x, v1 - h.y);
+}
+static constexpr int kStemRowWords = 20;  // 16 words of a pixel's 32 bf16 channels + 4 of padding: conflict-free staging
+__global__ void __launch_bounds__(128, 3) hn_stem_mma_kernel(const float* __restrict__ x, int N, int H, int W, const float* __restrict__ w,
+                                                          const float* __restrict__ b, View out, int no_relu, int tiles, int TX) {
+    hn_pdl_launch_dependents();
+    hn_pdl_wait();
+    __shared__ __align__(16) uint32_t s_out[4][16 * kStemRowWords];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tq = lane & 3;
+    // this thread's k indices: slot (s, h, e) -> k = 16 s + 8 h + 2 tq + e
+    int koff_c[8], k_ky[8], k_kx[8];
+    uint32_t bhi[2][4][2], blo[2][4][2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k0 = 16 * s + 8 * h + 2 * tq;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = k0 + e, kk = k < 27 ? k : 0, ci = kk / 9, r = kk - ci * 9;
+                koff_c[(s * 2 + h) * 2 + e] = k < 27 ? ci : -1;
+                k_ky[(s * 2 + h) * 2 + e] = r / 3;
+                k_kx[(s * 2 + h) * 2 + e] = r - (r / 3) * 3;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = 8 * j + gid;
+                const float w0 = k0 < 27 ? __ldg(w + k0 * 32 + n) : 0.0f, w1 = k0 + 1 < 27 ? __ldg(w + (k0 + 1) * 32 + n) : 0.0f;
+                split_pair(w0, w1, bhi[s][j][h], blo[s][j][h]);
+            }
+        }
+    float bias[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { bias[j][0] = __ldg(b + 8 * j + 2 * tq); bias[j][1] = __ldg(b + 8 * j + 2 * tq + 1); }
+    const int OH = out.H, OW = out.W;
+    uint32_t* so = s_out[warp];
+    // A warp walks whole output rows: the eight row pointers of a thread's taps are set up once per row, and a tile away from the
+    // left / right border needs no bounds checks -- the kernel is bound by instruction issue, not by its 24 MMAs per tile.
+    int ixb[8];  // input column of row gid of tile 0 for tap slot i: 2 * gid - 1 + kx
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ixb[i] = 2 * gid - 1 + k_kx[i];
+    const int rows = N * OH;
+    for (int row = blockIdx.x * 4 + warp; row < rows; row += gridDim.x * 4) {
+        const int n = row / OH, oy = row - n * OH;
+        const float* xin = x + (long long)n * 3 * H * W;
+        const float* rowp[8];
+        bool rok[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int iy = 2 * oy - 1 + k_ky[i];
+            rok[i] = koff_c[i] >= 0 && iy >= 0 && iy < H;
+            rowp[i] = xin + ((long long)(rok[i] ? koff_c[i] : 0) * H + (rok[i] ? iy : 0)) * W + ixb[i];
+        }
+        bf16* orow = const_cast<bf16*>(vptr(out, n, oy, 0, 0));
+        // the 16 samples of tile xb + 1 are requested before tile xb is computed (a warp would otherwise idle for a full memory
+        // round trip per tile)
+        auto gather = [&](int xb, float (&v)[8][2]) {
+            const int ox0 = xb * 16;
+            if (xb > 0 && 2 * (ox0 + 15) + 1 < W && ox0 + 15 < OW) {  // interior tile: every tap of every pixel is inside the image
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    v[i][0] = rok[i] ? __ldg(rowp[i] + 2 * ox0) : 0.0f;
+                    v[i][1] = rok[i] ? __ldg(rowp[i] + 2 * ox0 + 16) : 0.0f;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const int ox = ox0 + gid + 8 * rr, ix = 2 * ox - 1 + k_kx[i];
+                        v[i][rr] = (rok[i] && ix >= 0 && ix < W && ox < OW) ? __ldg(rowp[i] + 2 * ox0 + 16 * rr) : 0.0f;
+                    }
+            }
+        };
+        float vn[8][2];
+        gather(0, vn);
+        for (int xb = 0; xb < TX; ++xb) {
+            const int ox0 = xb * 16;
+            float v[8][2];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[i][0] = vn[i][0]; v[i][1] = vn[i][1]; }
+            if (xb + 1 < TX) gather(xb + 1, vn);
+            uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const int i = (s2 * 2 + h) * 2;
+                        split_pair(v[i][rr], v[i + 1][rr], ahi[s2][h * 2 + rr], alo[s2][h * 2 + rr]);  // a0/a1: k pair h = 0, rows gid / gid+8; a2/a3: h = 1
+                    }
+            float acc[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { acc[j][0] = acc[j][2] = bias[j][0]; acc[j][1] = acc[j][3] = bias[j][1]; }
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    stem_mma(acc[j], ahi[s2], bhi[s2][j][0], bhi[s2][j][1]);
+                    stem_mma(acc[j], alo[s2], bhi[s2][j][0], bhi[s2][j][1]);
+                    stem_mma(acc[j], ahi[s2], blo[s2][j][0], blo[s2][j][1]);
+                }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!no_relu) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[j][q] = fmaxf(acc[j][q], 0.0f);
+                }
+                so[gid * kStemRowWords + 4 * j + tq] = hn_pack_bf16x2(acc[j][0], acc[j][1]);
+                so[(gid + 8) * kStemRowWords + 4 * j + tq] = hn_pack_bf16x2(acc[j][2], acc[j][3]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int idx = lane + 32 * i, px = idx >> 2, q = idx & 3;
+                if (ox0 + px < OW)
+                    *reinterpret_cast<uint4*>(orow + (ox0 + px) * out.sx + q * 8) = *reinterpret_cast<const uint4*>(so + px * kStemRowWords + q * 4);
+            }
+            __syncwarp();
+        }
+    }
+}
+static int g_stem_mma = 1;
+extern "C" void hn_stem_set_mma(int on) { g_stem_mma = on ? 1 : 0; }  // 0: the fp32 CUDA-core kernel (A/B runs)
+
 extern "C" int hn_stem_fwd(const hn_stem_desc* d, void* stream) {
     HN_REQUIRE(d && d->x && d->w && d->b, "stem: null pointer");
     if (int rc = check_view(d->out, "stem.out")) return rc;
@@ -86,6 +227,19 @@ extern "C" int hn_stem_fwd(const hn_stem_desc* d, void* stream) {
                d->H, d->W);
     long long total = (long long)d->N * d->out.H * ((d->out.W + 1) / 2);  // two output pixels per thread
     HN_REQUIRE(total < 0x7fffffffLL, "stem: too many output pixels for one launch");
+    if (g_stem_mma) {
+        const int TX = hn_cdiv(d->out.W, 16);
+        const long long tiles = (long long)d->N * d->out.H * TX;
+        HN_REQUIRE(tiles < 0x7fffffffLL, "stem: too many tiles for one launch");
+        int sms = hn_device_sm_count();
+        if (sms <= 0) sms = 148;
+        long long blocks = hn_cdiv((long long)d->N * d->out.H, 4);       // a warp per output row, grid-stride
+        if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;  // the weight fragments are built once per thread
+        HN_CHECK_CUDA(hn_launch(hn_stem_mma_kernel, dim3((unsigned)blocks), dim3(128), (size_t)0, reinterpret_cast<cudaStream_t>(stream), d->x, d->N, d->H, d->W,
+                                d->w, d->b, to_view(d->out), (int)d->no_relu, (int)tiles, TX));
+        HN_CHECK_CUDA(cudaGetLastError());
+        return HN_OK;
+    }
     HN_CHECK_CUDA(hn_launch(hn_stem_kernel, dim3(hn_cdiv(total, 128)), dim3(128), (size_t)(0), reinterpret_cast<cudaStream_t>(stream), d->x, d->N, d->H, d->W, d->w,
                                                                                           d->b, to_view(d->out), (int)d->no_relu));
     HN_CHECK_CUDA(cudaGetLastError());

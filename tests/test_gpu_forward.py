@@ -468,3 +468,39 @@ def test_gconv_se_launch_equals_conv_then_se(B, H, W, C, S):
     # the conv itself, gate divided out (gate in (0, 1), bf16): every pixel, including the zero-padded borders
     conv_got = got / got_gate[:, None, None, :].clamp_min(1e-3)
     assert float((conv_got - y_ref).abs().max()) <= 2.5e-2 * float(y_ref.abs().max())
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 64, 64), (3, 37, 53), (1, 640, 640), (2, 33, 16)])
+def test_stem_tensor_core_kernel_equals_fp32_kernel(N, H, W):
+    """hn_stem_fwd on the tensor cores ((hi, lo) bf16 splits of inputs and weights, three products) against the fp32 CUDA-core
+    kernel and against torch's fp32 convolution: at most one bf16 ulp apart, odd sizes and ragged 16-pixel tiles included."""
+    import torch.nn.functional as F
+    from hydranet_b200 import _native as nv
+    from hydranet_b200.engine import Buf
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(H * 100 + W)
+    x = (torch.randn((N, 3, H, W), generator=g) * 1.2).to(dev)
+    w = (torch.randn((32, 3, 3, 3), generator=g) * 0.3).to(dev)
+    b = (torch.randn((32,), generator=g) * 0.2).to(dev)
+    wk = w.permute(1, 2, 3, 0).reshape(27, 32).contiguous()
+    OH, OW = (H + 1) // 2, (W + 1) // 2
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), 2, 1)).permute(0, 2, 3, 1).float()
+    got = {}
+    try:
+        for mode in (0, 1):
+            nv.lib.hn_stem_set_mma(mode)
+            buf = Buf(dev, torch.bfloat16, N, OH, OW, 32, pad=1)
+            d = nv.StemDesc(x.data_ptr(), N, H, W, wk.data_ptr(), b.data_ptr(), buf.interior().to_c())
+            nv.check(nv.lib.hn_stem_fwd(d, torch.cuda.current_stream().cuda_stream))
+            torch.cuda.synchronize()
+            halo = buf.t.clone()
+            halo[:, 1:-1, 1:-1] = 0
+            assert float(halo.abs().max()) == 0.0
+            got[mode] = buf.interior().torch_view().float()
+    finally:
+        nv.lib.hn_stem_set_mma(1)
+    ulp = torch.exp2(torch.floor(torch.log2(ref.abs().clamp_min(2.0 ** -20))) - 7)  # bf16 spacing at the value
+    slack = 5e-5 * float(ref.abs().max())  # fp32 accumulation order / the dropped lo*lo products, far below the bf16 spacing of O(1) values
+    for mode in (0, 1):
+        assert bool(((got[mode] - ref).abs() <= 0.5 * ulp + slack).all()), "mode %d is not the rounded fp64 result" % mode
+    assert float((got[0] != got[1]).float().mean()) <= 5e-3  # the two kernels may round a near-tie differently here and there
