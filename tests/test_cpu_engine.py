@@ -58,6 +58,12 @@ def test_algorithmic_macs_match_survey():
     b.build(torch.zeros(1, 3, 640, 640))
     macs = sum(op.macs for op in b.ops if op.kind in ("conv", "stem", "node", "dw_multi", "se_pool", "se_fused", "gconv_se"))
     assert abs(macs - 31698401632) / 31698401632 < 2e-3, macs
+    # launch structure of the big cfg: stride-1 XBlocks of stages 3-4 run their grouped 3x3 and squeeze-excite as
+    # one launch, the other blocks of stages 2-4 their squeeze-excite; stages 0-1 keep pool + scale
+    import collections
+    kinds = collections.Counter(op.kind for op in b.ops)
+    assert (kinds["conv"], kinds["gconv_se"], kinds["se_fused"], kinds["se_pool"], kinds["se_scale"]) == (134, 22, 6, 2, 2), kinds
+    assert (kinds["node"], kinds["dw_multi"], kinds["stem"], kinds["pool"], kinds["lanefuse"]) == (24, 8, 1, 1, 1), kinds
 
 
 def test_state_dict_keys_equal_reference():
