@@ -1416,6 +1416,7 @@ static int se_fused_launch(const hn_se_pool_desc* d, const hn_gconv_se_desc* cv,
         if (int rc = check_view(cv->in, "gconv_se.in")) return rc;
         HN_REQUIRE(cv->in.N == d->x.N && cv->in.H == d->x.H && cv->in.W == d->x.W && cv->in.C == d->x.C, "gconv_se: input and output shapes differ");
         HN_REQUIRE(cv->weight && cv->bias && (reinterpret_cast<uintptr_t>(cv->weight) & 15) == 0, "gconv_se: weights");
+        HN_REQUIRE(cv->in.ptr != d->x.ptr, "gconv_se: input and output must not alias (a CTA reads its neighbours' input pixels)");
         p.in = to_view(cv->in);
         p.wg = reinterpret_cast<const bf16*>(cv->weight);
         p.cbias = cv->bias;
